@@ -1,0 +1,359 @@
+"""Host-side stand-in for ALF's model plugin surface (L1): ``Operator`` (Op_make / Op_set),
+the Bravais lattice, the predefined hoppings (checkerboard / symmetric Trotter) and the
+predefined interactions that the shipped Hamiltonians use.
+
+In a real drop-in this layer is ALF's own, unchanged Fortran (``Hamiltonian_main_mod``,
+``Operator_mod``, ``Predefined_*``); the Fortran toolchain is absent in this image, so the
+tables that the Fortran shim would flatten and hand to the C-ABI (``include/alf_b200.h``)
+are produced here with the same conventions.  Nothing in this file is on the hot path.
+
+Reference: Prog/Operator_mod.F90:56-90,193-215,259-473; Libraries/Modules/lattices_v3_mod.F90:88-330;
+Prog/Predefined_Hop_mod.F90:257-362,1422-1495,1624-1839; Prog/Predefined_Int_mod.F90:59-219;
+Prog/Hamiltonians/Hamiltonian_Hubbard_smod.F90:207-330,477-542; Hamiltonian_Kondo_smod.F90:464-530.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import List, Optional
+
+import numpy as np
+
+EPS_SMALL = 1.0e-10          # Libraries/Modules/natural_constants_mod.F90:8-10 (Eps_small)
+EPS_MACHINE = np.finfo(np.float64).eps
+
+
+class HamiltonianError(RuntimeError):
+    """Mirrors Terminate_on_error(ERROR_HAMILTONIAN, ...) (Libraries/Modules/runtime_error_mod.F90:56-68)."""
+
+
+@dataclass
+class Operator:
+    """Prog/Operator_mod.F90:56-90.  ``P`` is 1-based, as in Fortran."""
+    N: int
+    O: np.ndarray = None
+    P: np.ndarray = None
+    g: complex = 0.0
+    alpha: complex = 0.0
+    type: int = 0
+    flip_protocol: int = 1
+    N_non_zero: int = 0
+    diag: bool = False
+    U: Optional[np.ndarray] = None
+    E: Optional[np.ndarray] = None
+
+
+def Op_make(N: int) -> Operator:
+    """Prog/Operator_mod.F90:193-215."""
+    op = Operator(N=N)
+    op.O = np.zeros((N, N), dtype=np.complex128)
+    op.P = np.zeros(N, dtype=np.int32)
+    op.N_non_zero = N
+    return op
+
+
+def Op_set(op: Operator) -> None:
+    """Prog/Operator_mod.F90:259-473: validate, detect diagonal operators, diagonalise, order the
+    non-zero eigenvalues first, normalise det(U)=1.  (The exponential tables E_exp/M_exp are private
+    in ALF and are rebuilt on the C side from U, E, g -- Operator_mod.F90:400-470.)"""
+    if op.type < 0 or op.type > 4:
+        raise HamiltonianError(f"Op_set: Invalid operator type: {op.type}")
+    if np.any(op.P < 1):
+        raise HamiltonianError("Op_set: Projector index out of bounds")
+    N = op.N
+    O = op.O
+    tol = EPS_MACHINE
+    for i in range(N):
+        for j in range(i + 1, N):
+            dev = abs(O[i, j] - np.conj(O[j, i]))
+            if dev > tol * max(abs(O[i, j]), abs(O[j, i]), 1e-30):
+                raise HamiltonianError("Op_set: Operator matrix Op%O is not Hermitian.")
+        if abs(O[i, i].imag) > tol * max(abs(O[i, i]), 1e-30):
+            raise HamiltonianError("Op_set: complex diagonal element (not Hermitian).")
+    op.U = np.zeros((N, N), dtype=np.complex128)
+    op.E = np.zeros(N, dtype=np.float64)
+    if N > 1:
+        offdiag = O - np.diag(np.diag(O))
+        op.diag = not np.any(offdiag != 0)
+        if op.diag:
+            op.E[:] = np.real(np.diag(O))
+            op.U[:] = np.eye(N)
+            op.N_non_zero = N
+        else:
+            E, U = np.linalg.eigh(O)          # Diag -> ZHEEV, ascending eigenvalues
+            npz, nz = 0, 0
+            for i in range(N):
+                if abs(E[i]) > EPS_SMALL:
+                    op.U[:, npz] = U[:, i]
+                    op.E[npz] = E[i]
+                    npz += 1
+                else:
+                    op.U[:, N - 1 - nz] = U[:, i]
+                    op.E[N - 1 - nz] = E[i]
+                    nz += 1
+            op.N_non_zero = npz
+            Z = np.linalg.det(op.U)
+            if abs(Z) < 1e-30:
+                raise HamiltonianError("Op_set: Eigenvector matrix has near-zero determinant")
+            op.U[:, 0] = op.U[:, 0] / Z        # scale into SU(N)
+    else:
+        op.E[0] = O[0, 0].real
+        op.U[0, 0] = 1.0
+        op.N_non_zero = 1
+        op.diag = True
+
+
+# ----------------------------------------------------------------------------- lattice
+class Lattice:
+    """Square-type Bravais lattice, Libraries/Modules/lattices_v3_mod.F90:88-330 (Make_lattice):
+    unit cells inside the Wigner-Seitz cell of (L1_p, L2_p), enumerated i1 outer / i2 inner."""
+
+    def __init__(self, L1: int, L2: int):
+        self.L1, self.L2 = L1, L2
+
+        def rng(L):
+            # x.L <= L^2/2 + 0  and  x.L >= -L^2/2 + Zero  (upper edge included, lower excluded)
+            return [i for i in range(-L, L + 1) if (i * L <= L * L / 2.0 + EPS_SMALL) and (i * L >= -L * L / 2.0 + EPS_SMALL)]
+
+        r1, r2 = rng(L1), rng(L2)
+        self.list = []
+        self.invlist = {}
+        for i1 in r1:
+            for i2 in r2:
+                self.list.append((i1, i2))
+                self.invlist[(i1, i2)] = len(self.list)      # 1-based
+        self.N = len(self.list)
+        self._r1, self._r2 = r1, r2
+
+    def _wrap(self, i, r, L):
+        lo = r[0]
+        return (i - lo) % L + lo
+
+    def nnlist(self, I: int, n1: int, n2: int) -> int:
+        i1, i2 = self.list[I - 1]
+        return self.invlist[(self._wrap(i1 + n1, self._r1, self.L1), self._wrap(i2 + n2, self._r2, self.L2))]
+
+
+# ----------------------------------------------------------------------------- model container
+@dataclass
+class Model:
+    """What ``Hamiltonian_main`` exposes publicly to the sweep (Prog/Hamiltonian_main_mod.F90:181-197)."""
+    name: str
+    Ndim: int
+    N_FL: int
+    N_SUN: int
+    Ltrot: int
+    Dtau: float
+    Symm: bool
+    Op_V: List[List[Operator]]          # Op_V[n][nf]
+    Op_T: List[List[Operator]]          # Op_T[nc][nf]
+    latt: Optional[Lattice] = None
+    params: dict = field(default_factory=dict)
+
+    @property
+    def n_opv(self):
+        return len(self.Op_V)
+
+    @property
+    def n_opt(self):
+        return len(self.Op_T)
+
+
+def _square_hopping_families(latt: Lattice, symm: bool):
+    """Set_Default_hopping_parameters_square (Predefined_Hop_mod.F90:331-360) + Symmetrize_Families (:1422-1495).
+    Returns list of (family members [(I, bond)], Prop_Fam)."""
+    fam = [[], [], [], []]
+    for I in range(1, latt.N + 1):
+        i1, i2 = latt.list[I - 1]
+        if (i1 + i2) % 2 == 0:
+            fam[0].append((I, 1)); fam[1].append((I, 2))
+        else:
+            fam[2].append((I, 1)); fam[3].append((I, 2))
+    prop = [1.0] * 4
+    if not symm:
+        return list(zip(fam, prop))
+    nfam_c = 4
+    order = list(range(nfam_c)) + list(range(nfam_c - 2, -1, -1))
+    lens = [len(f) for f in fam]
+    n_f_max = int(np.argmax(lens))            # first longest family (strict > in the reference)
+    if n_f_max != nfam_c - 1:
+        order[nfam_c - 1] = n_f_max
+        order[0] = nfam_c - 1
+        order[-1] = nfam_c - 1
+    props = [0.5] * (2 * nfam_c - 1)
+    props[nfam_c - 1] = 1.0
+    return [(fam[k], props[i]) for i, k in enumerate(order)]
+
+
+def hubbard_square(L1: int, L2: int, beta: float, dtau: float = 0.1, U: float = 4.0, t: float = 1.0, mu: float = 0.0,
+                   Mz: bool = True, checkerboard: bool = True, symm: bool = True, N_SUN: int = 2) -> Model:
+    """Hubbard model on the square lattice as set up by Hamiltonian_Hubbard_smod.F90 (Ham_Set :207-330,
+    Ham_Hop, Ham_V :477-542) with the shipped defaults (Scripts_and_Parameters_files/Start/parameters)."""
+    latt = Lattice(L1, L2)
+    Ndim = latt.N
+    Ltrot = int(round(beta / dtau))
+    N_FL = 2 if Mz else 1
+    n_sun = N_SUN // 2 if N_FL == 2 else N_SUN
+    # bonds: (no_I, no_J, n_1, n_2) ; List(1) = (1,1,0,1), List(2) = (1,1,1,0) ; T = -t ; T_loc = -mu
+    bonds = {1: (0, 1), 2: (1, 0)}
+    Op_T: List[List[Operator]] = []
+    if checkerboard:
+        fams = _square_hopping_families(latt, symm)
+        mult = 4                                   # Multiplicity of orbital 1 (Predefined_Hop_mod.F90:1773-1781)
+        for members, prop in fams:
+            for (I, nb) in members:
+                n1, n2 = bonds[nb]
+                J = latt.nnlist(I, n1, n2)
+                row = []
+                for nf in range(N_FL):
+                    op = Op_make(2)
+                    op.P[0], op.P[1] = I, J
+                    op.O[0, 1] = -t
+                    op.O[1, 0] = -t
+                    op.O[0, 0] = -mu / mult
+                    op.O[1, 1] = -mu / mult
+                    op.g = -dtau * prop
+                    Op_set(op)
+                    row.append(op)
+                Op_T.append(row)
+    else:
+        row = []
+        for nf in range(N_FL):
+            op = Op_make(Ndim)
+            for I in range(1, latt.N + 1):
+                for nb in (1, 2):
+                    n1, n2 = bonds[nb]
+                    J = latt.nnlist(I, n1, n2)
+                    op.O[I - 1, J - 1] = -t
+                    op.O[J - 1, I - 1] = -t
+                op.O[I - 1, I - 1] = -mu
+            op.P[:] = np.arange(1, Ndim + 1)
+            op.g = -dtau
+            Op_set(op)
+            row.append(op)
+        Op_T.append(row)
+    Op_V: List[List[Operator]] = []
+    if abs(U) > EPS_SMALL:
+        for I in range(1, latt.N + 1):
+            if Mz:
+                # Predefined_Int_U_MZ (Predefined_Int_mod.F90:107-133); Ham_U_vec/N_SUN with N_SUN already halved
+                Ueff = U / float(n_sun)
+                ops = []
+                for sgn in (+1.0, -1.0):
+                    op = Op_make(1)
+                    op.P[0] = I
+                    op.O[0, 0] = 1.0
+                    op.g = sgn * np.sqrt(complex(dtau * Ueff / 2.0, 0.0))
+                    op.alpha = -0.5
+                    op.type = 2
+                    Op_set(op)
+                    ops.append(op)
+                Op_V.append(ops)
+            else:
+                # Predefined_Int_U_SUN (Predefined_Int_mod.F90:59-77)
+                op = Op_make(1)
+                op.P[0] = I
+                op.O[0, 0] = 1.0
+                op.alpha = -0.5
+                op.g = np.sqrt(complex(-dtau * U / float(N_FL * n_sun), 0.0))
+                op.type = 2
+                Op_set(op)
+                Op_V.append([op])
+    return Model(name="Hubbard", Ndim=Ndim, N_FL=N_FL, N_SUN=n_sun, Ltrot=Ltrot, Dtau=dtau, Symm=bool(symm and checkerboard),
+                 Op_V=Op_V, Op_T=Op_T, latt=latt,
+                 params=dict(L1=L1, L2=L2, beta=beta, dtau=dtau, U=U, t=t, mu=mu, Mz=Mz, checkerboard=checkerboard, symm=symm))
+
+
+def hubbard_chain(L: int, beta: float, dtau: float, U: float = 4.0, t: float = 1.0, Mz: bool = True, symm: bool = True) -> Model:
+    """N_leg_ladder with L2=1 and Checkerboard=.false. as in testsuite/test_vs_ed/test_specs.yaml:24-56
+    (dense hopping matrix, periodic chain; with Symm the half-step similarity is applied before measuring)."""
+    Ndim = L
+    Ltrot = int(round(beta / dtau))
+    N_FL = 2 if Mz else 1
+    row = []
+    for nf in range(N_FL):
+        op = Op_make(Ndim)
+        for I in range(L):
+            J = (I + 1) % L
+            if L == 2 and I == 1:
+                continue
+            op.O[I, J] += -t
+            op.O[J, I] += -t
+        op.P[:] = np.arange(1, Ndim + 1)
+        op.g = -dtau
+        Op_set(op)
+        row.append(op)
+    Op_V = []
+    for I in range(1, L + 1):
+        if Mz:
+            ops = []
+            for sgn in (+1.0, -1.0):
+                op = Op_make(1); op.P[0] = I; op.O[0, 0] = 1.0
+                op.g = sgn * np.sqrt(complex(dtau * U / 2.0, 0.0)); op.alpha = -0.5; op.type = 2
+                Op_set(op); ops.append(op)
+            Op_V.append(ops)
+        else:
+            op = Op_make(1); op.P[0] = I; op.O[0, 0] = 1.0; op.alpha = -0.5
+            op.g = np.sqrt(complex(-dtau * U / 2.0, 0.0)); op.type = 2
+            Op_set(op); Op_V.append([op])
+    return Model(name="Hubbard_chain", Ndim=Ndim, N_FL=N_FL, N_SUN=1 if Mz else 2, Ltrot=Ltrot, Dtau=dtau, Symm=symm,
+                 Op_V=Op_V, Op_T=[row], params=dict(L=L, beta=beta, dtau=dtau, U=U, t=t, Mz=Mz, symm=symm))
+
+
+def kondo_square(L1: int, L2: int, beta: float, dtau: float = 0.1, t: float = 1.0, J: float = 2.0, Uf: float = 1.0,
+                 Uc: float = 0.0, symm: bool = True, N_SUN: int = 2) -> Model:
+    """SU(N) Kondo lattice on the bilayer square lattice, Hamiltonian_Kondo_smod.F90:464-530: orbital 1 = conduction
+    (hops), orbital 2 = f (no hopping); vertices U_f (k=1, imaginary g: Predefined_Int_U_SUN, Ham_V :497-505) and
+    J_K (k=2 vertex, Predefined_Int_V_SUN with Ham_JK/2 for N_SUN=2, :507-514).  The conduction-layer hopping uses the
+    square-lattice checkerboard families here (the reference's bilayer family split, Predefined_Hop_mod.F90:1005-1040,
+    groups the same bonds differently; the sweep path only sees a list of 2x2 bond operators either way)."""
+    latt = Lattice(L1, L2)
+    Nc = latt.N
+    Ndim = 2 * Nc                                  # Invlist(I,no) = (I-1)*Norb + no (Predefined_Latt_mod.F90:250-260)
+    Ltrot = int(round(beta / dtau))
+    inv = lambda I, no: (I - 1) * 2 + no
+    bonds = {1: (0, 1), 2: (1, 0)}
+    fams = _square_hopping_families(latt, symm)
+    Op_T = []
+    for members, prop in fams:
+        for (I, nb) in members:
+            n1, n2 = bonds[nb]
+            Jn = latt.nnlist(I, n1, n2)
+            op = Op_make(2)
+            op.P[0], op.P[1] = inv(I, 1), inv(Jn, 1)
+            op.O[0, 1] = -t; op.O[1, 0] = -t
+            op.g = -dtau * prop
+            Op_set(op)
+            Op_T.append([op])
+    Op_V = []
+    for I in range(1, Nc + 1):                    # U_f on the f orbital
+        if abs(Uf) > EPS_SMALL:
+            op = Op_make(1); op.P[0] = inv(I, 2); op.O[0, 0] = 1.0; op.alpha = -0.5
+            op.g = np.sqrt(complex(-dtau * Uf / float(N_SUN), 0.0)); op.type = 2
+            Op_set(op); Op_V.append([op])
+    for I in range(1, Nc + 1):                    # N_SUN == 2: Predefined_Int_V_SUN(OP, I1, I2, N_SUN, DTAU, Ham_JK/2)
+        op = Op_make(2)
+        op.P[0], op.P[1] = inv(I, 1), inv(I, 2)
+        op.O[0, 1] = 1.0; op.O[1, 0] = 1.0
+        op.g = np.sqrt(complex(dtau * (J / 2.0) / float(N_SUN), 0.0)); op.alpha = 0.0; op.type = 2
+        Op_set(op); Op_V.append([op])
+    return Model(name="Kondo", Ndim=Ndim, N_FL=1, N_SUN=N_SUN, Ltrot=Ltrot, Dtau=dtau, Symm=symm, Op_V=Op_V, Op_T=Op_T, latt=latt,
+                 params=dict(L1=L1, L2=L2, beta=beta, dtau=dtau, t=t, J=J, Uf=Uf, symm=symm))
+
+
+def flatten_ops(model: Model):
+    """Flattened operator tables, one entry per Fortran-shim call into the C-ABI
+    (alf_b200_set_op_v / alf_b200_set_op_t)."""
+    out_v, out_t = [], []
+    for n, row in enumerate(model.Op_V):
+        for nf, op in enumerate(row):
+            out_v.append(dict(n=n + 1, nf=nf + 1, N=op.N, nnz=op.N_non_zero, diag=int(op.diag), type=op.type,
+                              P=np.ascontiguousarray(op.P, dtype=np.int32),
+                              U=np.asfortranarray(op.U, dtype=np.complex128),
+                              E=np.ascontiguousarray(op.E, dtype=np.float64), g=complex(op.g), alpha=complex(op.alpha)))
+    for nc, row in enumerate(model.Op_T):
+        for nf, op in enumerate(row):
+            out_t.append(dict(nc=nc + 1, nf=nf + 1, N=op.N, diag=int(op.diag),
+                              P=np.ascontiguousarray(op.P, dtype=np.int32),
+                              U=np.asfortranarray(op.U, dtype=np.complex128),
+                              E=np.ascontiguousarray(op.E, dtype=np.float64), g=complex(op.g)))
+    return out_v, out_t

@@ -1,0 +1,240 @@
+"""ctypes binding of the CPU oracle (oracle/alf_oracle.cpp).
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / --impl reference legs.  The product (alf_b200/) never imports this module.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = os.path.join(_HERE, "_build", "liboracle.so")
+_lib = None
+
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int)
+
+
+def build(force: bool = False) -> str:
+    if force or not os.path.exists(_LIB) or os.path.getmtime(_LIB) < os.path.getmtime(os.path.join(_HERE, "alf_oracle.cpp")):
+        subprocess.check_call(["make", "-C", _HERE, "-s"], stdout=subprocess.DEVNULL)
+    return _LIB
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        _lib = C.CDLL(_LIB)
+        _lib.orc_create.restype = C.c_void_p
+        _lib.orc_ranf.restype = C.c_double
+        _lib.orc_get_log.restype = C.c_long
+        _lib.orc_taum_get.restype = C.c_long
+        _lib.orc_eq_get.restype = C.c_long
+    return _lib
+
+
+def _d(a):
+    return a.ctypes.data_as(_dp)
+
+
+def _cplx(a):
+    return np.asfortranarray(a, dtype=np.complex128)
+
+
+class Oracle:
+    """One Markov chain of the reference algorithm (one MPI rank of ALF)."""
+
+    def __init__(self, model, nwrap: int = 10, stab3: bool = False):
+        from alf_b200.model import flatten_ops
+        L = lib()
+        self.m = model
+        self.N = model.Ndim
+        self.nwrap = nwrap
+        self.h = C.c_void_p(L.orc_create(model.Ndim, model.N_FL, model.N_SUN, model.Ltrot, nwrap, model.n_opv, model.n_opt,
+                                         int(model.Symm), int(stab3)))
+        ov, ot = flatten_ops(model)
+        for o in ov:
+            L.orc_set_op_v(self.h, o["n"], o["nf"], o["N"], o["nnz"], o["diag"], o["type"], o["P"].ctypes.data_as(_ip),
+                           _d(o["U"]), _d(o["E"]), C.c_double(o["g"].real), C.c_double(o["g"].imag),
+                           C.c_double(o["alpha"].real), C.c_double(o["alpha"].imag))
+        for o in ot:
+            L.orc_set_op_t(self.h, o["nc"], o["nf"], o["N"], o["diag"], o["P"].ctypes.data_as(_ip), _d(o["U"]), _d(o["E"]),
+                           C.c_double(o["g"].real), C.c_double(o["g"].imag))
+
+    def __del__(self):
+        try:
+            lib().orc_destroy(self.h)
+        except Exception:
+            pass
+
+    # --- RNG / fields
+    def ranset(self, seed: int):
+        lib().orc_ranset(self.h, int(seed))
+
+    def ranf(self) -> float:
+        return lib().orc_ranf(self.h)
+
+    def rng_state(self):
+        s = np.zeros(4, dtype=np.uint64)
+        lib().orc_get_rng_state(self.h, s.ctypes.data_as(C.c_void_p))
+        return s
+
+    def set_rng_state(self, s):
+        s = np.ascontiguousarray(s, dtype=np.uint64)
+        lib().orc_set_rng_state(self.h, s.ctypes.data_as(C.c_void_p))
+
+    def fields_set(self):
+        lib().orc_fields_set(self.h)
+
+    def get_fields(self):
+        f = np.zeros((self.m.Ltrot, self.m.n_opv), dtype=np.complex128)
+        lib().orc_get_fields(self.h, _d(f))
+        return f                      # f[nt-1, n-1]
+
+    def set_fields(self, f):
+        f = np.ascontiguousarray(f, dtype=np.complex128)
+        assert f.shape == (self.m.Ltrot, self.m.n_opv)
+        lib().orc_set_fields(self.h, _d(f))
+
+    # --- driver
+    def init(self):
+        lib().orc_init(self.h)
+
+    def sweep(self, ltau: int = 0):
+        lib().orc_sweep(self.h, int(ltau))
+
+    def green(self, nf: int):
+        g = np.zeros((self.N, self.N), dtype=np.complex128, order="F")
+        lib().orc_get_green(self.h, nf, _d(g))
+        return g
+
+    def set_green(self, nf: int, g):
+        g = _cplx(g)
+        lib().orc_set_green(self.h, nf, _d(g))
+
+    def phase(self) -> complex:
+        p = np.zeros(2)
+        lib().orc_get_phase(self.h, _d(p))
+        return complex(p[0], p[1])
+
+    def nstm(self):
+        return lib().orc_nstm(self.h)
+
+    def log(self, on=True):
+        lib().orc_log(self.h, int(on))
+
+    def get_log(self):
+        n = lib().orc_get_log(self.h, None, None, 0)
+        acc = np.zeros(n, dtype=np.uint8)
+        w = np.zeros(n, dtype=np.float64)
+        lib().orc_get_log(self.h, acc.ctypes.data_as(C.POINTER(C.c_uint8)), _d(w), n)
+        return acc, w
+
+    def control(self):
+        out = np.zeros(13)
+        lib().orc_get_control(self.h, _d(out))
+        keys = ["XMEANG", "XMAXG", "NCG", "XMAXP", "XMEAN_tau", "XMAX_tau", "NCG_tau", "NC_up", "ACC_up", "NC_eff_up",
+                "ACC_eff_up", "nan", "unstable"]
+        return dict(zip(keys, out))
+
+    def taum_capture(self, every=1):
+        lib().orc_taum_capture(self.h, int(every))
+
+    def taum_get(self):
+        n = lib().orc_taum_get(self.h, None, 0)
+        buf = np.zeros(n, dtype=np.complex128)
+        lib().orc_taum_get(self.h, _d(buf), n)
+        nn = self.N * self.N
+        ntau = n // (4 * self.m.N_FL * nn)
+        # [tau][which: GT0,G0T,G00,GTT][nf][col-major N*N]
+        return buf.reshape(ntau, 4, self.m.N_FL, self.N, self.N).transpose(0, 1, 2, 4, 3)
+
+    def eq_capture(self, on=True):
+        lib().orc_eq_capture(self.h, int(on))
+
+    def eq_get(self):
+        n = lib().orc_eq_get(self.h, None, 0)
+        buf = np.zeros(n, dtype=np.complex128)
+        lib().orc_eq_get(self.h, _d(buf), n)
+        nn = self.N * self.N
+        nv = n // (self.m.N_FL * nn)
+        return buf.reshape(nv, self.m.N_FL, self.N, self.N).transpose(0, 1, 3, 2)
+
+    # --- building blocks
+    def hop_apply(self, which: int, nf: int, A):
+        A = _cplx(A).copy(order="F")
+        lib().orc_hop_apply(self.h, which, nf, _d(A), A.shape[0], A.shape[1])
+        return A
+
+    def op_mmultR(self, n, nf, A, field, cop="n"):
+        A = _cplx(A).copy(order="F"); field = complex(field)
+        lib().orc_op_mmultR(self.h, n, nf, _d(A), A.shape[0], A.shape[1], C.c_double(field.real), C.c_double(field.imag), C.c_char(cop.encode()))
+        return A
+
+    def op_mmultL(self, n, nf, A, field, cop="n", sign=1):
+        A = _cplx(A).copy(order="F"); field = complex(field)
+        lib().orc_op_mmultL(self.h, n, nf, _d(A), A.shape[0], A.shape[1], C.c_double(field.real), C.c_double(field.imag), C.c_char(cop.encode()), int(sign))
+        return A
+
+    def op_wrapup(self, n, nf, A, field, ntype):
+        A = _cplx(A).copy(order="F"); field = complex(field)
+        lib().orc_op_wrapup(self.h, n, nf, _d(A), C.c_double(field.real), C.c_double(field.imag), int(ntype))
+        return A
+
+    def op_wrapdo(self, n, nf, A, field, ntype):
+        A = _cplx(A).copy(order="F"); field = complex(field)
+        lib().orc_op_wrapdo(self.h, n, nf, _d(A), C.c_double(field.real), C.c_double(field.imag), int(ntype))
+        return A
+
+    def wrapgrup(self, ntau):
+        lib().orc_wrapgrup(self.h, int(ntau))
+
+    def wrapgrdo(self, ntau):
+        lib().orc_wrapgrdo(self.h, int(ntau))
+
+    def propr(self, nf, A, nt):
+        A = _cplx(A).copy(order="F")
+        lib().orc_propr(self.h, nf, _d(A), int(nt))
+        return A
+
+    def get_udv(self, which, nst, nf):
+        """which: 0 udvl, 1 udvr, 2 udvst(nst)."""
+        U = np.zeros((self.N, self.N), dtype=np.complex128, order="F"); V = U.copy(order="F"); D = np.zeros(self.N, dtype=np.complex128)
+        lib().orc_get_udv(self.h, which, nst, nf, _d(U), _d(D), _d(V))
+        return U, D, V
+
+
+def qdrp(A):
+    A = _cplx(A).copy(order="F"); n, m = A.shape
+    D = np.zeros(m, dtype=np.complex128); ipvt = np.zeros(m, dtype=np.int32); tau = np.zeros(m, dtype=np.complex128)
+    lib().orc_qdrp(n, m, _d(A), _d(D), ipvt.ctypes.data_as(_ip), _d(tau))
+    return A, D, ipvt, tau
+
+
+def udv_decompose(U, D, V, side="r"):
+    U = _cplx(U).copy(order="F"); V = _cplx(V).copy(order="F"); D = np.ascontiguousarray(D, dtype=np.complex128).copy()
+    lib().orc_udv_decompose(U.shape[0], C.c_char(side.encode()), _d(U), _d(D), _d(V))
+    return U, D, V
+
+
+def cgr(UR, DR, VR, UL, DL, VL, nvar=1, stab3=False):
+    n = UR.shape[0]
+    G = np.zeros((n, n), dtype=np.complex128, order="F"); ph = np.zeros(2)
+    a = [_cplx(x) for x in (UR, VR, UL, VL)]
+    dr = np.ascontiguousarray(DR, dtype=np.complex128); dl = np.ascontiguousarray(DL, dtype=np.complex128)
+    lib().orc_cgr(n, int(nvar), int(stab3), _d(a[0]), _d(dr), _d(a[1]), _d(a[2]), _d(dl), _d(a[3]), _d(G), _d(ph))
+    return G, complex(ph[0], ph[1])
+
+
+def cgr2_2(U2, D2, V2, U1, D1, V1, stab3=False):
+    n = U2.shape[0]
+    outs = [np.zeros((n, n), dtype=np.complex128, order="F") for _ in range(4)]
+    a = [_cplx(x) for x in (U2, V2, U1, V1)]
+    d2 = np.ascontiguousarray(D2, dtype=np.complex128); d1 = np.ascontiguousarray(D1, dtype=np.complex128)
+    lib().orc_cgr2_2(n, int(stab3), _d(a[0]), _d(d2), _d(a[1]), _d(a[2]), _d(d1), _d(a[3]), *[_d(o) for o in outs])
+    return dict(GRT0=outs[0], GR00=outs[1], GRTT=outs[2], GR0T=outs[3])
