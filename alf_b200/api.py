@@ -1,0 +1,265 @@
+"""Python host binding of the C-ABI (include/alf_b200.h) via ctypes.
+
+This is the Python twin of the Fortran ISO_C_BINDING shim (alf_b200/fortran/alf_b200_shim.F90): it flattens the
+model's Operator tables exactly as the shim does and forwards every call to libalf_b200.so.  The CUDA library is
+the only implementation: if it is missing or no sm_100 device is present, construction fails loudly (no fallback).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from .model import Model, flatten_ops
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libalf_b200.so")
+_lib = None
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int)
+
+
+class AlfError(RuntimeError):
+    """Non-zero return code of the C-ABI (the Fortran shim maps these to Terminate_on_error)."""
+
+    def __init__(self, code, msg=""):
+        super().__init__(f"alf_b200 error {code}: {msg}")
+        self.code = code
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise AlfError(100, f"{LIB_PATH} not built (run `python -c 'import __graft_entry__ as g; g.build()'`); there is no CPU fallback")
+        _lib = C.CDLL(LIB_PATH)
+        _lib.alf_b200_last_error.restype = C.c_char_p
+        _lib.alf_b200_last_error.argtypes = [C.c_void_p]
+    return _lib
+
+
+def _d(a):
+    return a.ctypes.data_as(_dp)
+
+
+class AlfB200:
+    """All chains of one GPU: the batched replacement of the sequential-sweep branch of Prog/main.F90."""
+
+    def __init__(self, model: Model, n_chains: int, nwrap: int = 10, stab: int = 0, device: int = 0):
+        L = lib()
+        self.m, self.C, self.N, self.nwrap = model, n_chains, model.Ndim, nwrap
+        self.h = C.c_void_p()
+        rc = L.alf_b200_create(C.byref(self.h), model.Ndim, model.N_FL, model.N_SUN, model.Ltrot, nwrap, model.n_opv, model.n_opt,
+                               int(model.Symm), int(stab), int(n_chains), int(device))
+        if rc != 0:
+            raise AlfError(rc, "alf_b200_create failed (no sm_100 CUDA device?)")
+        ov, ot = flatten_ops(model)
+        for o in ov:
+            self._ck(L.alf_b200_set_op_v(self.h, o["n"], o["nf"], o["N"], o["nnz"], o["diag"], o["type"], o["P"].ctypes.data_as(_ip),
+                                         _d(o["U"]), _d(o["E"]), C.c_double(o["g"].real), C.c_double(o["g"].imag),
+                                         C.c_double(o["alpha"].real), C.c_double(o["alpha"].imag)))
+        for o in ot:
+            self._ck(L.alf_b200_set_op_t(self.h, o["nc"], o["nf"], o["N"], o["diag"], o["P"].ctypes.data_as(_ip), _d(o["U"]), _d(o["E"]),
+                                         C.c_double(o["g"].real), C.c_double(o["g"].imag)))
+        self._ck(L.alf_b200_finalize_model(self.h))
+
+    def _ck(self, rc):
+        if rc != 0:
+            msg = lib().alf_b200_last_error(self.h)
+            raise AlfError(rc, msg.decode() if msg else "")
+
+    def close(self):
+        if getattr(self, "h", None) is not None and self.h:
+            lib().alf_b200_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def is_complex(self):
+        return bool(lib().alf_b200_is_complex(self.h))
+
+    # ---- RNG / fields
+    def set_seeds(self, seeds):
+        s = np.ascontiguousarray(seeds, dtype=np.int32)
+        assert s.size == self.C
+        self._ck(lib().alf_b200_set_seeds(self.h, s.ctypes.data_as(C.POINTER(C.c_int32))))
+
+    def rng_state(self):
+        s = np.zeros((self.C, 4), dtype=np.uint64)
+        self._ck(lib().alf_b200_get_rng_state(self.h, s.ctypes.data_as(C.c_void_p)))
+        return s
+
+    def set_rng_state(self, s):
+        s = np.ascontiguousarray(s, dtype=np.uint64)
+        self._ck(lib().alf_b200_set_rng_state(self.h, s.ctypes.data_as(C.c_void_p)))
+
+    def fields_set(self):
+        self._ck(lib().alf_b200_fields_set(self.h))
+
+    def get_fields(self):
+        f = np.zeros((self.C, self.m.Ltrot, self.m.n_opv), dtype=np.complex128)
+        self._ck(lib().alf_b200_get_fields(self.h, _d(f)))
+        return f
+
+    def set_fields(self, f):
+        f = np.ascontiguousarray(f, dtype=np.complex128)
+        assert f.shape == (self.C, self.m.Ltrot, self.m.n_opv)
+        self._ck(lib().alf_b200_set_fields(self.h, _d(f)))
+
+    # ---- batched mode
+    def init_sweep(self):
+        self._ck(lib().alf_b200_init_sweep(self.h))
+
+    def sweep(self, n_sweeps=1, ltau=0):
+        self._ck(lib().alf_b200_sweep(self.h, int(n_sweeps), int(ltau)))
+
+    def sweep_host(self, n_sweeps, ltau, fields_in, fields_out, obs_out, control_out):
+        self._ck(lib().alf_b200_sweep_host(self.h, int(n_sweeps), int(ltau), _d(fields_in) if fields_in is not None else None,
+                                           _d(fields_out) if fields_out is not None else None,
+                                           _d(obs_out) if obs_out is not None else None, _d(control_out) if control_out is not None else None))
+
+    # ---- compat mode
+    def wrapgrup(self, ntau):
+        self._ck(lib().alf_b200_wrapgrup(self.h, int(ntau)))
+
+    def wrapgrdo(self, ntau):
+        self._ck(lib().alf_b200_wrapgrdo(self.h, int(ntau)))
+
+    def wrapur(self, ntau, ntau1):
+        self._ck(lib().alf_b200_wrapur(self.h, int(ntau), int(ntau1)))
+
+    def wrapul(self, ntau1, ntau):
+        self._ck(lib().alf_b200_wrapul(self.h, int(ntau1), int(ntau)))
+
+    def udv_reset(self, which, side):
+        self._ck(lib().alf_b200_udv_reset(self.h, int(which), C.c_char(side.encode())))
+
+    def cgr(self, nvar=1):
+        self._ck(lib().alf_b200_cgr(self.h, int(nvar)))
+
+    def tau_m(self):
+        self._ck(lib().alf_b200_tau_m(self.h))
+
+    # ---- results
+    def green(self, chain, nf, symmetrize=False):
+        g = np.zeros((self.N, self.N), dtype=np.complex128, order="F")
+        self._ck(lib().alf_b200_get_green(self.h, int(chain), int(nf), int(symmetrize), _d(g)))
+        return g
+
+    def set_green(self, chain, nf, g):
+        g = np.asfortranarray(g, dtype=np.complex128)
+        self._ck(lib().alf_b200_set_green(self.h, int(chain), int(nf), _d(g)))
+
+    def phase(self):
+        p = np.zeros(self.C, dtype=np.complex128)
+        self._ck(lib().alf_b200_get_phase(self.h, _d(p)))
+        return p
+
+    def get_udv(self, which, nst, chain, nf):
+        U = np.zeros((self.N, self.N), dtype=np.complex128, order="F"); V = U.copy(order="F"); D = np.zeros(self.N, dtype=np.complex128)
+        self._ck(lib().alf_b200_get_udv(self.h, int(which), int(nst), int(chain), int(nf), _d(U), _d(D), _d(V)))
+        return U, D, V
+
+    def control(self):
+        out = np.zeros(16)
+        self._ck(lib().alf_b200_get_control(self.h, _d(out)))
+        keys = ["XMEANG", "XMAXG", "NCG", "XMAXP", "XMEAN_tau", "XMAX_tau", "NCG_tau", "NC_up", "ACC_up", "NC_eff_up", "ACC_eff_up", "nan", "unstable"]
+        return dict(zip(keys, out))
+
+    def accept_log(self, enable=True):
+        self._ck(lib().alf_b200_accept_log(self.h, int(enable)))
+
+    def get_accept_log(self):
+        n = C.c_long(0)
+        cap = 2 * self.m.Ltrot * self.m.n_opv * self.C
+        out = np.full(cap, 255, dtype=np.uint8)
+        self._ck(lib().alf_b200_get_accept_log(self.h, out.ctypes.data_as(C.POINTER(C.c_uint8)), C.c_long(cap), C.byref(n)))
+        return out[: n.value * self.C].reshape(self.C, n.value)
+
+    def taum_capture(self, every=1):
+        self._ck(lib().alf_b200_taum_capture(self.h, int(every)))
+
+    def get_taum(self, chain):
+        n = C.c_long(0)
+        self._ck(lib().alf_b200_get_taum(self.h, int(chain), None, C.c_long(0), C.byref(n)))
+        buf = np.zeros(n.value, dtype=np.complex128)
+        self._ck(lib().alf_b200_get_taum(self.h, int(chain), _d(buf), C.c_long(n.value), C.byref(n)))
+        nn = self.N * self.N
+        ntau = n.value // (4 * self.m.N_FL * nn)
+        return buf.reshape(ntau, 4, self.m.N_FL, self.N, self.N).transpose(0, 1, 2, 4, 3)
+
+    def obs(self):
+        n = lib().alf_b200_obs_size(self.h)
+        out = np.zeros(n)
+        self._ck(lib().alf_b200_get_obs(self.h, _d(out)))
+        return out
+
+    def obs_reset(self):
+        self._ck(lib().alf_b200_obs_reset(self.h))
+
+    def obs_device_ptr(self):
+        p = _dp(); n = C.c_long(0)
+        self._ck(lib().alf_b200_obs_device_ptr(self.h, C.byref(p), C.byref(n)))
+        return C.cast(p, C.c_void_p).value, n.value
+
+    def hop_apply(self, which, nf, A):
+        A = np.asfortranarray(A, dtype=np.complex128).copy(order="F")
+        self._ck(lib().alf_b200_hop_apply(self.h, int(which), int(nf), _d(A)))
+        return A
+
+
+# ---- kernel-level test entry points -------------------------------------------------------------------------------
+def _chk(rc, what):
+    if rc != 0:
+        raise AlfError(rc, what)
+
+
+def test_gemm(A, B, ta=False, tb=False, is_complex=True, device=0):
+    A = np.ascontiguousarray(A, dtype=np.complex128); B = np.ascontiguousarray(B, dtype=np.complex128)
+    batch = A.shape[0]
+    # inputs are [batch, rows, cols] in numpy order -> convert each to column-major storage
+    Af = np.ascontiguousarray(A.transpose(0, 2, 1)); Bf = np.ascontiguousarray(B.transpose(0, 2, 1))
+    m = A.shape[2] if ta else A.shape[1]; k = A.shape[1] if ta else A.shape[2]; n = B.shape[1] if tb else B.shape[2]
+    Cc = np.zeros((batch, n, m), dtype=np.complex128)
+    _chk(lib().alf_b200_test_gemm(device, int(is_complex), int(ta), int(tb), m, n, k, batch, _d(Af), _d(Bf), _d(Cc)), "test_gemm")
+    return Cc.transpose(0, 2, 1)
+
+
+def test_qdrp(A, is_complex=True, device=0):
+    A = np.ascontiguousarray(A, dtype=np.complex128); batch, m, n = A.shape
+    Af = np.ascontiguousarray(A.transpose(0, 2, 1)).copy()
+    D = np.zeros((batch, n)); jp = np.zeros((batch, n), dtype=np.int32); tau = np.zeros((batch, n), dtype=np.complex128); ph = np.zeros((batch, 5))
+    _chk(lib().alf_b200_test_qdrp(device, int(is_complex), m, n, batch, _d(Af), _d(D), jp.ctypes.data_as(_ip), _d(tau), _d(ph)), "test_qdrp")
+    return Af.transpose(0, 2, 1), D, jp, tau, ph
+
+
+def test_udv_decompose(U, D, V, side="r", is_complex=True, device=0):
+    U = np.ascontiguousarray(U, dtype=np.complex128); V = np.ascontiguousarray(V, dtype=np.complex128); batch, n, _ = U.shape
+    Uf = np.ascontiguousarray(U.transpose(0, 2, 1)).copy(); Vf = np.ascontiguousarray(V.transpose(0, 2, 1)).copy()
+    Dc = np.ascontiguousarray(D, dtype=np.complex128).copy()
+    _chk(lib().alf_b200_test_udv_decompose(device, int(is_complex), n, batch, C.c_char(side.encode()), _d(Uf), _d(Dc), _d(Vf)), "test_udv")
+    return Uf.transpose(0, 2, 1), Dc, Vf.transpose(0, 2, 1)
+
+
+def test_cgr(UR, DR, VR, UL, DL, VL, detUR, detUL, nvar=1, stab=0, is_complex=True, device=0):
+    batch, n, _ = UR.shape
+    cm = lambda X: np.ascontiguousarray(np.asarray(X, dtype=np.complex128).transpose(0, 2, 1))
+    a = [cm(x) for x in (UR, VR, UL, VL)]
+    dr = np.ascontiguousarray(DR, dtype=np.complex128); dl = np.ascontiguousarray(DL, dtype=np.complex128)
+    d1 = np.ascontiguousarray(detUR, dtype=np.complex128); d2 = np.ascontiguousarray(detUL, dtype=np.complex128)
+    G = np.zeros((batch, n, n), dtype=np.complex128); ph = np.zeros(batch, dtype=np.complex128)
+    _chk(lib().alf_b200_test_cgr(device, int(is_complex), n, batch, int(nvar), int(stab), _d(a[0]), _d(dr), _d(a[1]), _d(a[2]), _d(dl), _d(a[3]),
+                                 _d(d1), _d(d2), _d(G), _d(ph)), "test_cgr")
+    return G.transpose(0, 2, 1), ph
+
+
+def fp64_peak(device=0):
+    a = C.c_double(0); b = C.c_double(0)
+    _chk(lib().alf_b200_fp64_peak(device, C.byref(a), C.byref(b)), "fp64_peak")
+    return a.value, b.value

@@ -1,0 +1,492 @@
+// Batched dense linear algebra for the stabilisation path, hand-written for sm_100a (no cuBLAS/cuSOLVER):
+//   k_gemm      -- C = op(A) op(B), register-tiled FP64 (replaces ZGEMM/ZTRMM/MMULT call sites,
+//                  Prog/cgr1_mod.F90:223-225,396,445; Prog/udv_state_mod.F90:569-572)
+//   k_qrp       -- column-pivoted Householder QR + split-off of D (replaces ZGEQP3 + QDRP_decompose,
+//                  Prog/QDRP_decompose_mod.F90:60-101; Pivot_phase :103-126)
+//   k_formq     -- explicit Q from the reflectors (replaces ZUNGQR, Prog/udv_state_mod.F90:576)
+//   k_trsm_lun  -- X = R^-1 B for upper-triangular R (replaces ZTRSM, Prog/cgr1_mod.F90:381)
+// One CTA works on one matrix (QR/formQ) or one tile / column panel of one matrix (GEMM/TRSM);
+// the batch (chains x flavors) is the grid's second dimension.
+#pragma once
+#include "alf_types.cuh"
+
+// ------------------------------------------------------------------------------------------------
+// GEMM: C[b] = op(A[b]) * op(B[b]);  TA/TB: 0 = as stored, 1 = conjugate transpose.
+// MASK: 1 -> A is upper triangular as stored (strict lower part read as 0), 2 -> same for B.
+// 64x64x16 tiles, 256 threads, 4x4 register micro-tiles.
+// ------------------------------------------------------------------------------------------------
+#define GEMM_BM 64
+#define GEMM_BN 64
+#define GEMM_BK 16
+#define GEMM_PAD 4
+
+template <typename T, int TA, int TB, int MASK>
+__global__ void __launch_bounds__(256) k_gemm(int M, int N, int K, const T* __restrict__ A, int lda, long sA,
+                                              const T* __restrict__ B, int ldb, long sB, T* __restrict__ C, int ldc, long sC) {
+  __shared__ T As[GEMM_BK][GEMM_BM + GEMM_PAD];
+  __shared__ T Bs[GEMM_BK][GEMM_BN + GEMM_PAD];
+  const int tiles_m = (M + GEMM_BM - 1) / GEMM_BM;
+  const int tm = blockIdx.x % tiles_m, tn = blockIdx.x / tiles_m;
+  const int b = blockIdx.y;
+  A += (long)b * sA; B += (long)b * sB; C += (long)b * sC;
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int m0 = tm * GEMM_BM, n0 = tn * GEMM_BN;
+  T acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = zero_<T>();
+
+  for (int k0 = 0; k0 < K; k0 += GEMM_BK) {
+    // ---- load A tile: As[k][m] = op(A)(m0+m, k0+k)
+    if (TA == 0) {
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        int m = tid & 63, k = (tid >> 6) + 4 * r;
+        int gm = m0 + m, gk = k0 + k;
+        T v = zero_<T>();
+        if (gm < M && gk < K && !(MASK == 1 && gm > gk)) v = A[gm + (long)gk * lda];
+        As[k][m] = v;
+      }
+    } else {
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        int k = tid & 15, m = (tid >> 4) + 16 * r;
+        int gm = m0 + m, gk = k0 + k;
+        T v = zero_<T>();
+        if (gm < M && gk < K && !(MASK == 1 && gk > gm)) v = conj_(A[gk + (long)gm * lda]);
+        As[k][m] = v;
+      }
+    }
+    // ---- load B tile: Bs[k][n] = op(B)(k0+k, n0+n)
+    if (TB == 0) {
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        int k = tid & 15, n = (tid >> 4) + 16 * r;
+        int gk = k0 + k, gn = n0 + n;
+        T v = zero_<T>();
+        if (gk < K && gn < N && !(MASK == 2 && gk > gn)) v = B[gk + (long)gn * ldb];
+        Bs[k][n] = v;
+      }
+    } else {
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        int n = tid & 63, k = (tid >> 6) + 4 * r;
+        int gk = k0 + k, gn = n0 + n;
+        T v = zero_<T>();
+        if (gk < K && gn < N && !(MASK == 2 && gn > gk)) v = conj_(B[gn + (long)gk * ldb]);
+        Bs[k][n] = v;
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < GEMM_BK; ++kk) {
+      T a[4], bb[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = As[kk][tx * 4 + i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) bb[j] = Bs[kk][ty * 4 + j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) fma_(acc[i][j], a[i], bb[j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    int gn = n0 + ty * 4 + j;
+    if (gn >= N) continue;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      int gm = m0 + tx * 4 + i;
+      if (gm < M) C[gm + (long)gn * ldc] = acc[i][j];
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Householder helpers.  A warp owns whole columns: lane l holds rows r0+l, r0+l+32, ... in registers,
+// so one reflector application reads and writes each trailing column exactly once.
+// C(r0:m, c) -= tauc * v * (v^H C(r0:m, c)),  v in shared memory with v[0] = 1.
+// If vn != nullptr the exact 2-norm of C(r0+1:m, c) is written to vn[c] (partial column norm for
+// the next pivot search; LAPACK down-dates and occasionally recomputes, we always recompute because
+// the column is already in registers).
+// ------------------------------------------------------------------------------------------------
+template <typename T, int MAXR>
+__device__ __forceinline__ void reflect_cols(T* __restrict__ A, int ld, int r0, int m, int c_begin, int c_end,
+                                             const T* __restrict__ v, T tauc, double* __restrict__ vn) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const int len = m - r0;
+  T vv[MAXR];
+#pragma unroll
+  for (int q = 0; q < MAXR; ++q) { int i = lane + 32 * q; vv[q] = (i < len) ? v[i] : zero_<T>(); }
+  for (int c = c_begin + warp; c < c_end; c += nwarps) {
+    T* col = A + (long)c * ld + r0;
+    T x[MAXR];
+    T w = zero_<T>();
+#pragma unroll
+    for (int q = 0; q < MAXR; ++q) {
+      int i = lane + 32 * q;
+      x[q] = (i < len) ? col[i] : zero_<T>();
+      fmac_(w, vv[q], x[q]);
+    }
+    w = warp_sum(w);
+    T s = tauc * w;
+    double nrm = 0.0;
+#pragma unroll
+    for (int q = 0; q < MAXR; ++q) {
+      int i = lane + 32 * q;
+      if (i < len) {
+        T y = x[q] - vv[q] * s;
+        col[i] = y;
+        if (i > 0) nrm += abs2_(y);
+      }
+    }
+    if (vn) {
+      nrm = warp_sum(nrm);
+      if (lane == 0) vn[c] = sqrt(nrm);
+    }
+  }
+}
+
+struct QrOut {           // per-matrix scalars produced by k_qrp
+  double perm_sign;      // parity of the pivot permutation (Pivot_phase)
+  cplx diag_phase;       // prod_i R_ii/|R_ii|
+  cplx detq;             // prod_i det(H_i) = prod_i (1 - tau_i v_i^H v_i)
+};
+
+// Column-pivoted Householder QR of an m x n matrix (m >= n), in place: reflectors below the diagonal,
+// R on and above it, then D(i) = |R(i,i)| and R(i,i:) /= D(i)  (QDRP_decompose_mod.F90:86-100).
+// jpvt[j] = original index of the column now at position j (0-based; LAPACK's JPVT minus 1).
+// If PIVOT == 0 the columns are taken in order (IPVT /= 0 "fixed" columns of ZGEQP3).
+template <typename T, int MAXR, int PIVOT>
+__device__ void qrp_device(T* __restrict__ A, int m, int n, int ld, T* __restrict__ tau, int* __restrict__ jpvt,
+                           double* __restrict__ D, QrOut* out, T* __restrict__ v_s, double* __restrict__ vn_s,
+                           int* __restrict__ ipv_s, double* __restrict__ red_s) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5, nthr = blockDim.x;
+  // initial column norms, warp per column
+  for (int c = warp; c < n; c += nwarps) {
+    double s = 0.0;
+    for (int i = lane; i < m; i += 32) s += abs2_(A[i + (long)c * ld]);
+    s = warp_sum(s);
+    if (lane == 0) { vn_s[c] = sqrt(s); ipv_s[c] = c; }
+  }
+  __syncthreads();
+  const int kmax = (m < n) ? m : n;
+  cplx detq = cplx(1.0, 0.0);
+  for (int j = 0; j < kmax; ++j) {
+    // ---- pivot: first index of the maximal partial norm in [j, n)
+    if (PIVOT) {
+      if (warp == 0) {
+        double best = -1.0; int bi = j;
+        for (int c = j + lane; c < n; c += 32) { double x = vn_s[c]; if (x > best) { best = x; bi = c; } }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          double ob = __shfl_xor_sync(0xffffffffu, best, o); int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+          if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+        }
+        if (lane == 0) red_s[0] = (double)bi;
+      }
+      __syncthreads();
+      const int p = (int)red_s[0];
+      if (p != j) {
+        for (int i = tid; i < m; i += nthr) { T t = A[i + (long)p * ld]; A[i + (long)p * ld] = A[i + (long)j * ld]; A[i + (long)j * ld] = t; }
+        if (tid == 0) { int t = ipv_s[p]; ipv_s[p] = ipv_s[j]; ipv_s[j] = t; vn_s[p] = vn_s[j]; }
+      }
+      __syncthreads();
+    }
+    // ---- generate the reflector for column j (ZLARFG, Libraries/libqrref/zlarfg.f:107-203; no safmin rescaling loop)
+    if (warp == 0) {
+      T* col = A + (long)j * ld + j;
+      const int len = m - j;
+      double xn2 = 0.0;
+      for (int i = 1 + lane; i < len; i += 32) xn2 += abs2_(col[i]);
+      xn2 = warp_sum(xn2);
+      T alpha = col[0];
+      T tj, scal; double beta;
+      if (xn2 == 0.0 && imag_(alpha) == 0.0) { tj = zero_<T>(); scal = zero_<T>(); beta = real_(alpha); }
+      else {
+        beta = -copysign(sqrt(abs2_(alpha) + xn2), real_(alpha));
+        tj = make_<T>((beta - real_(alpha)) / beta, -imag_(alpha) / beta);
+        scal = one_<T>() / (alpha - make_<T>(beta, 0.0));
+      }
+      for (int i = 1 + lane; i < len; i += 32) { T y = col[i] * scal; col[i] = y; v_s[i] = y; }
+      if (lane == 0) { v_s[0] = one_<T>(); col[0] = make_<T>(beta, 0.0); tau[j] = tj; }
+      if (abs2_(tj) != 0.0) {  // det(H_j) = 1 - 2 (tau/|tau|) (Re tau/|tau|)   (Prog/cgr1_mod.F90:338-347)
+        double X = abs_(tj); cplx z = cplx(real_(tj) / X, imag_(tj) / X);
+        cplx d = cplx(1.0, 0.0) - 2.0 * (real_(tj) / X) * z;
+        double ad = abs_(d); detq = detq * cplx(d.x / ad, d.y / ad);
+      }
+    }
+    __syncthreads();
+    // ---- apply H_j^H to the trailing columns and refresh their partial norms
+    {
+      T tauc = conj_(tau[j]);
+      if (abs2_(tauc) != 0.0) reflect_cols<T, MAXR>(A, ld, j, m, j + 1, n, v_s, tauc, PIVOT ? vn_s : nullptr);
+      else if (PIVOT) {  // H = I: norms of rows below j only
+        for (int c = j + 1 + warp; c < n; c += nwarps) {
+          double s = 0.0;
+          for (int i = j + 1 + lane; i < m; i += 32) s += abs2_(A[i + (long)c * ld]);
+          s = warp_sum(s);
+          if (lane == 0) vn_s[c] = sqrt(s);
+        }
+      }
+    }
+    __syncthreads();
+  }
+  // ---- D(i) = |R(i,i)|, R(i, i:) /= D(i); phases
+  for (int i = tid; i < kmax; i += nthr) { double x = abs_(A[i + (long)i * ld]); D[i] = x; red_s[i] = x; }
+  __syncthreads();
+  for (long e = tid; e < (long)kmax * n; e += nthr) {
+    int i = (int)(e % kmax), c = (int)(e / kmax);
+    if (c >= i) A[i + (long)c * ld] = A[i + (long)c * ld] * (1.0 / red_s[i]);
+  }
+  for (int c = tid; c < n; c += nthr) jpvt[c] = ipv_s[c];
+  __syncthreads();
+  if (tid == 0) {
+    cplx ph = cplx(1.0, 0.0);
+    for (int i = 0; i < kmax; ++i) { T r = A[i + (long)i * ld]; ph = ph * cplx(real_(r), imag_(r)); }
+    // permutation parity: cycles of even length flip the sign (QDRP_decompose_mod.F90:103-126)
+    double sg = 1.0;
+    for (int i = 0; i < n; ++i) vn_s[i] = 0.0;
+    for (int i = 0; i < n; ++i) if (vn_s[i] == 0.0) {
+      int next = i, L = 0;
+      while (vn_s[next] == 0.0) { ++L; vn_s[next] = 1.0; next = ipv_s[next]; }
+      if ((L & 1) == 0) sg = -sg;
+    }
+    out->perm_sign = sg; out->diag_phase = ph; out->detq = detq;
+  }
+  __syncthreads();
+}
+
+// dynamic smem layout: [optional matrix m*ld_s T] [v: m T] [vn: n double] [red: max(n,32) double] [ipv: n int]
+template <typename T, int MAXR, int PIVOT, int STAGE>
+__global__ void __launch_bounds__(512) k_qrp(T* __restrict__ A, int m, int n, int ld, long sA, T* __restrict__ tau, long sTau,
+                                             int* __restrict__ jpvt, long sP, double* __restrict__ D, long sD, QrOut* __restrict__ out) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int b = blockIdx.x;
+  A += (long)b * sA; tau += (long)b * sTau; jpvt += (long)b * sP; D += (long)b * sD;
+  T* p = reinterpret_cast<T*>(smem_raw);
+  T* As = nullptr; int lds = ld;
+  if (STAGE) { As = p; lds = m; p += (long)m * n; }
+  T* v_s = p; p += m;
+  double* vn_s = reinterpret_cast<double*>(p);
+  double* red_s = vn_s + n;
+  int* ipv_s = reinterpret_cast<int*>(red_s + (n > 32 ? n : 32));
+  if (STAGE) {
+    for (long e = threadIdx.x; e < (long)m * n; e += blockDim.x) { int i = (int)(e % m), c = (int)(e / m); As[i + (long)c * m] = A[i + (long)c * ld]; }
+    __syncthreads();
+    qrp_device<T, MAXR, PIVOT>(As, m, n, lds, tau, jpvt, D, out + b, v_s, vn_s, ipv_s, red_s);
+    for (long e = threadIdx.x; e < (long)m * n; e += blockDim.x) { int i = (int)(e % m), c = (int)(e / m); A[i + (long)c * ld] = As[i + (long)c * m]; }
+  } else {
+    qrp_device<T, MAXR, PIVOT>(A, m, n, ld, tau, jpvt, D, out + b, v_s, vn_s, ipv_s, red_s);
+  }
+}
+
+// Explicit Q (m x n, n reflectors) in place of the reflectors, backward accumulation (ZUNG2R order).
+// Optionally scales column 0 by `colscale[b]` afterwards (udv_state_mod.F90:578).
+template <typename T, int MAXR, int STAGE>
+__global__ void __launch_bounds__(512) k_formq(T* __restrict__ A, int m, int n, int ld, long sA, const T* __restrict__ tau, long sTau,
+                                               const cplx* __restrict__ colscale) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int b = blockIdx.x, tid = threadIdx.x, nthr = blockDim.x;
+  A += (long)b * sA; tau += (long)b * sTau;
+  T* p = reinterpret_cast<T*>(smem_raw);
+  T* W = A; int lw = ld;
+  if (STAGE) {
+    W = p; lw = m; p += (long)m * n;
+    for (long e = tid; e < (long)m * n; e += nthr) { int i = (int)(e % m), c = (int)(e / m); W[i + (long)c * m] = A[i + (long)c * ld]; }
+  }
+  T* v_s = p;
+  __syncthreads();
+  for (int j = n - 1; j >= 0; --j) {
+    const int len = m - j;
+    T* col = W + (long)j * lw + j;
+    for (int i = tid; i < len; i += nthr) v_s[i] = (i == 0) ? one_<T>() : col[i];
+    __syncthreads();
+    T tj = tau[j];
+    if (j < n - 1 && abs2_(tj) != 0.0) reflect_cols<T, MAXR>(W, lw, j, m, j + 1, n, v_s, tj, nullptr);
+    // column j of Q: e_j - tau_j v
+    for (int i = tid; i < m; i += nthr) {
+      T y;
+      if (i < j) y = zero_<T>();
+      else if (i == j) y = one_<T>() - tj;
+      else y = -(tj * v_s[i - j]);
+      W[i + (long)j * lw] = y;
+    }
+    __syncthreads();
+  }
+  if (colscale) {
+    cplx s = colscale[b]; T st = make_<T>(s.x, s.y);
+    for (int i = tid; i < m; i += nthr) W[i] = W[i] * st;
+    __syncthreads();
+  }
+  if (STAGE) {
+    for (long e = tid; e < (long)m * n; e += nthr) { int i = (int)(e % m), c = (int)(e / m); A[i + (long)c * ld] = W[i + (long)c * m]; }
+  }
+}
+
+// X = R^-1 B, R upper triangular n x n (as stored in a QR'd matrix, leading dimension ldr), B n x nrhs in place.
+// A CTA owns TRSM_COLS right-hand sides; each warp keeps its columns in registers (rows over lanes);
+// column i of R is staged through shared memory once per elimination step.
+// If dinv != nullptr, B(i,:) is first multiplied by 1/dinv[i]  (the "apply inverse of D" loop, cgr1_mod.F90:368-377).
+#define TRSM_WARPS 8
+#define TRSM_CPW 4
+#define TRSM_COLS (TRSM_WARPS * TRSM_CPW)
+template <typename T, int MAXR>
+__global__ void __launch_bounds__(TRSM_WARPS * 32) k_trsm_lun(const T* __restrict__ R, int ldr, long sR, T* __restrict__ B, int ldb, long sB,
+                                                             int n, int nrhs, const double* __restrict__ dinv, long sD) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  T* rcol = reinterpret_cast<T*>(smem_raw);        // n entries
+  const int b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  R += (long)b * sR; B += (long)b * sB;
+  if (dinv) dinv += (long)b * sD;
+  const int c0 = blockIdx.x * TRSM_COLS + warp * TRSM_CPW;
+  T x[TRSM_CPW][MAXR];
+#pragma unroll
+  for (int cc = 0; cc < TRSM_CPW; ++cc)
+#pragma unroll
+    for (int q = 0; q < MAXR; ++q) {
+      int i = lane + 32 * q, c = c0 + cc;
+      T v = zero_<T>();
+      if (i < n && c < nrhs) { v = B[i + (long)c * ldb]; if (dinv) v = v * (1.0 / dinv[i]); }
+      x[cc][q] = v;
+    }
+  for (int i = n - 1; i >= 0; --i) {
+    __syncthreads();
+    for (int k = tid; k <= i; k += blockDim.x) rcol[k] = R[k + (long)i * ldr];
+    __syncthreads();
+    const T rinv = one_<T>() / rcol[i];
+    const int qi = i >> 5, li = i & 31;
+#pragma unroll
+    for (int cc = 0; cc < TRSM_CPW; ++cc) {
+      T xi = zero_<T>();
+#pragma unroll
+      for (int q = 0; q < MAXR; ++q) if (q == qi) xi = x[cc][q];
+      xi = shfl_(xi, li) * rinv;
+#pragma unroll
+      for (int q = 0; q < MAXR; ++q) {
+        int k = lane + 32 * q;
+        if (k < i) x[cc][q] = x[cc][q] - rcol[k] * xi;
+        else if (k == i) x[cc][q] = xi;
+      }
+    }
+  }
+#pragma unroll
+  for (int cc = 0; cc < TRSM_CPW; ++cc)
+#pragma unroll
+    for (int q = 0; q < MAXR; ++q) {
+      int i = lane + 32 * q, c = c0 + cc;
+      if (i < n && c < nrhs) B[i + (long)c * ldb] = x[cc][q];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// element-wise helpers (all batched over blockIdx.y)
+// ------------------------------------------------------------------------------------------------
+// dst(i,j) = src(perm? ...) generic gather: MODE 0 copy, 1 rows gathered dst(i,:) = src(p[i],:), 2 cols gathered dst(:,j) = src(:,p[j]),
+// 3 rows scattered dst(p[i],:) = src(i,:), 4 conj-transpose dst(i,j) = conj(src(j,i)),
+// 5 rows scattered + conj-transpose: dst = (scatter_rows(src))^H  i.e. dst(j, p[i]) = conj(src(i,j))
+template <typename T, int MODE>
+__global__ void k_permcopy(T* __restrict__ dst, int ldd, long sDst, const T* __restrict__ src, int lds, long sSrc, int m, int n,
+                           const int* __restrict__ perm, long sP) {
+  const int b = blockIdx.y;
+  dst += (long)b * sDst; src += (long)b * sSrc;
+  if (perm) perm += (long)b * sP;
+  for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < (long)m * n; e += (long)gridDim.x * blockDim.x) {
+    int i = (int)(e % m), j = (int)(e / m);
+    T v = src[i + (long)j * lds];
+    if (MODE == 0) dst[i + (long)j * ldd] = v;
+    else if (MODE == 1) dst[i + (long)j * ldd] = src[perm[i] + (long)j * lds];
+    else if (MODE == 2) dst[i + (long)j * ldd] = src[i + (long)perm[j] * lds];
+    else if (MODE == 3) dst[perm[i] + (long)j * ldd] = v;
+    else if (MODE == 4) dst[j + (long)i * ldd] = conj_(v);
+    else if (MODE == 5) dst[j + (long)perm[i] * ldd] = conj_(v);
+  }
+}
+
+// A(:, j) *= d[j]   (udv_state_mod.F90:473-477)
+template <typename T>
+__global__ void k_colscale(T* __restrict__ A, int ld, long sA, int m, int n, const double* __restrict__ d, long sD) {
+  const int b = blockIdx.y; A += (long)b * sA; d += (long)b * sD;
+  for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < (long)m * n; e += (long)gridDim.x * blockDim.x) {
+    int i = (int)(e % m), j = (int)(e / m);
+    A[i + (long)j * ld] = A[i + (long)j * ld] * d[j];
+  }
+}
+// row 0 of A (first n entries) *= conj?(1/phase[b])   (udv_state_mod.F90:489-492)
+template <typename T>
+__global__ void k_row0scale(T* __restrict__ A, int ld, long sA, int n, const cplx* __restrict__ s) {
+  const int b = blockIdx.y; A += (long)b * sA;
+  T st = make_<T>(s[b].x, s[b].y);
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) A[(long)j * ld] = A[(long)j * ld] * st;
+}
+// identity / zero fill
+template <typename T>
+__global__ void k_set_identity(T* __restrict__ A, int ld, long sA, int m, int n) {
+  const int b = blockIdx.y; A += (long)b * sA;
+  for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < (long)m * n; e += (long)gridDim.x * blockDim.x) {
+    int i = (int)(e % m), j = (int)(e / m);
+    A[i + (long)j * ld] = (i == j) ? one_<T>() : zero_<T>();
+  }
+}
+__global__ void k_fill_double(double* p, long n, double v) {
+  for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long)gridDim.x * blockDim.x) p[e] = v;
+}
+__global__ void k_fill_cplx(cplx* p, long n, cplx v) {
+  for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long)gridDim.x * blockDim.x) p[e] = v;
+}
+
+// TPUP(i,j) = DR(i) * TPUP(i,j) * DL(j) + RHS(i,j)      (cgr1_mod.F90:233-236)
+// SEP = 1: scale-separated form of the STAB3 branch (cgr1_mod.F90:241-268)
+// CT = 1: the result is written conjugate-transposed (NVAR /= 1, cgr1_mod.F90:303-308)
+template <typename T, int SEP, int CT>
+__global__ void k_cgr_tpup(T* __restrict__ OUT, const T* __restrict__ TP, const T* __restrict__ RHS, long sM, int n,
+                           const double* __restrict__ DR, const double* __restrict__ DL, long sD) {
+  const int b = blockIdx.y; OUT += (long)b * sM; TP += (long)b * sM; RHS += (long)b * sM; DR += (long)b * sD; DL += (long)b * sD;
+  for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < (long)n * n; e += (long)gridDim.x * blockDim.x) {
+    int i = (int)(e % n), j = (int)(e / n);
+    double dr = DR[i], dl = DL[j];
+    T t = TP[e], r = RHS[e], o;
+    if (!SEP) o = (dr * t) * dl + r;
+    else {
+      if (dl <= 1.0) { if (dr <= 1.0) o = r + (dr * dl) * t; else o = (1.0 / dr) * r + dl * t; }
+      else { if (dr <= 1.0) o = (1.0 / dl) * r + dr * t; else o = (r * (1.0 / dr)) * (1.0 / dl) + t; }
+    }
+    if (CT) OUT[j + (long)i * n] = conj_(o); else OUT[e] = o;
+  }
+}
+// rows i with d[i] > 1 scaled by 1/d[i] (ROWS=1) or columns (ROWS=0): the D_+^-1 scalings of the STAB3 branch
+template <typename T, int ROWS>
+__global__ void k_sep_scale(T* __restrict__ A, long sA, int n, const double* __restrict__ d, long sD) {
+  const int b = blockIdx.y; A += (long)b * sA; d += (long)b * sD;
+  for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < (long)n * n; e += (long)gridDim.x * blockDim.x) {
+    int i = (int)(e % n), j = (int)(e / n);
+    double x = d[ROWS ? i : j];
+    if (x > 1.0) A[e] = A[e] * (1.0 / x);
+  }
+}
+
+// Control_PrecisionG / COMPARE (control_mod.F90:207-298, mymats_mod.F90:683-704): per matrix max and mean |A-B|, NaN flag.
+// out[b*3+0] = xmax, +1 = xmean, +2 = nan flag
+template <typename T>
+__global__ void __launch_bounds__(256) k_compare(const T* __restrict__ A, const T* __restrict__ B, long sM, long nelem, double* __restrict__ out) {
+  __shared__ double smax[8], ssum[8]; __shared__ int snan[8];
+  const int b = blockIdx.x; A += (long)b * sM; B += (long)b * sM;
+  double mx = 0.0, sm = 0.0; int nn = 0;
+  for (long e = threadIdx.x; e < nelem; e += blockDim.x) {
+    T a = A[e], c = B[e];
+    if (isnan_(a) || isnan_(c)) nn = 1;
+    double d = abs_(a - c);
+    mx = fmax(mx, d); sm += d;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o)); sm += __shfl_xor_sync(0xffffffffu, sm, o); nn |= __shfl_xor_sync(0xffffffffu, nn, o); }
+  if ((threadIdx.x & 31) == 0) { smax[threadIdx.x >> 5] = mx; ssum[threadIdx.x >> 5] = sm; snan[threadIdx.x >> 5] = nn; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) { mx = fmax(mx, smax[w]); sm += ssum[w]; nn |= snan[w]; }
+    out[b * 3 + 0] = mx; out[b * 3 + 1] = sm / (double)nelem; out[b * 3 + 2] = (double)nn;
+  }
+}

@@ -1,0 +1,163 @@
+// Host-side launch helpers for the batched linear algebra (decompose, CGR) shared by the sweep engine and the
+// kernel-level test entry points.
+#pragma once
+#include <cstdio>
+#include <stdexcept>
+#include <string>
+#include <vector>
+#include "alf_la.cuh"
+
+struct CudaError : std::runtime_error { using std::runtime_error::runtime_error; };
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { \
+  throw CudaError(std::string(#call) + " -> " + cudaGetErrorString(e_) + " at " + __FILE__ + ":" + std::to_string(__LINE__)); } } while (0)
+#define CKL() CK(cudaGetLastError())
+
+static inline int ew_blocks(long n) { long b = (n + 255) / 256; return (int)(b > 2048 ? 2048 : (b < 1 ? 1 : b)); }
+
+template <typename T>
+struct UdvDev {            // batch of UDV_State objects (Prog/udv_state_mod.F90:85-110), one per (chain, flavor)
+  T* U = nullptr; T* V = nullptr; double* D = nullptr; cplx* det = nullptr;   // det = det(U), tracked instead of DET_C(U_R^H U_L)
+};
+
+template <typename T>
+struct LaWork {
+  int N = 0, NM = 0; cudaStream_t st = 0;
+  T* W[4] = {nullptr, nullptr, nullptr, nullptr};
+  T* tau = nullptr; int* jpvt = nullptr; double* Dq = nullptr; QrOut* qrout = nullptr; cplx* sc_phase = nullptr; cplx* sc_beta = nullptr;
+  long n2() const { return (long)N * N; }
+  void alloc(int n, int nm, cudaStream_t s) {
+    N = n; NM = nm; st = s;
+    for (int i = 0; i < 4; ++i) CK(cudaMalloc(&W[i], sizeof(T) * n2() * NM));
+    CK(cudaMalloc(&tau, sizeof(T) * (long)N * NM)); CK(cudaMalloc(&jpvt, sizeof(int) * (long)N * NM));
+    CK(cudaMalloc(&Dq, sizeof(double) * (long)N * NM)); CK(cudaMalloc(&qrout, sizeof(QrOut) * NM));
+    CK(cudaMalloc(&sc_phase, sizeof(cplx) * NM)); CK(cudaMalloc(&sc_beta, sizeof(cplx) * NM));
+  }
+  void release() {
+    for (int i = 0; i < 4; ++i) if (W[i]) cudaFree(W[i]);
+    if (tau) cudaFree(tau); if (jpvt) cudaFree(jpvt); if (Dq) cudaFree(Dq); if (qrout) cudaFree(qrout);
+    if (sc_phase) cudaFree(sc_phase); if (sc_beta) cudaFree(sc_beta);
+    for (int i = 0; i < 4; ++i) W[i] = nullptr; tau = nullptr; jpvt = nullptr; Dq = nullptr; qrout = nullptr; sc_phase = sc_beta = nullptr;
+  }
+};
+
+template <typename T, int TA, int TB, int MASK>
+static void gemm(cudaStream_t st, int M, int N, int K, const T* A, int lda, long sA, const T* B, int ldb, long sB, T* C, int ldc, long sC, int batch) {
+  dim3 grid(((M + GEMM_BM - 1) / GEMM_BM) * ((N + GEMM_BN - 1) / GEMM_BN), batch);
+  k_gemm<T, TA, TB, MASK><<<grid, 256, 0, st>>>(M, N, K, A, lda, sA, B, ldb, sB, C, ldc, sC);
+  CKL();
+}
+
+static const size_t kSmemStageLimit = 200 * 1024;
+
+template <typename T, int PIVOT>
+static void launch_qrp(cudaStream_t st, T* A, int m, int n, int ld, long sA, T* tau, long sTau, int* jpvt, long sP, double* D, long sD, QrOut* out, int batch) {
+  size_t extra = sizeof(T) * m + sizeof(double) * (n + (n > 32 ? n : 32)) + sizeof(int) * n + 64;
+  size_t stage = sizeof(T) * (size_t)m * n;
+  bool do_stage = (stage + extra) <= kSmemStageLimit;
+  size_t smem = extra + (do_stage ? stage : 0);
+#define QRP_LAUNCH(MAXR, STG) do { \
+    CK(cudaFuncSetAttribute(k_qrp<T, MAXR, PIVOT, STG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    k_qrp<T, MAXR, PIVOT, STG><<<batch, 512, smem, st>>>(A, m, n, ld, sA, tau, sTau, jpvt, sP, D, sD, out); } while (0)
+#define QRP_DISPATCH(MAXR) do { if (do_stage) QRP_LAUNCH(MAXR, 1); else QRP_LAUNCH(MAXR, 0); } while (0)
+  if (m <= 64) QRP_DISPATCH(2); else if (m <= 128) QRP_DISPATCH(4); else if (m <= 288) QRP_DISPATCH(9); else if (m <= 576) QRP_DISPATCH(18);
+  else throw CudaError("k_qrp: matrices with more than 576 rows are not supported in this build");
+  CKL();
+#undef QRP_DISPATCH
+#undef QRP_LAUNCH
+}
+
+template <typename T>
+static void launch_formq(cudaStream_t st, T* A, int m, int n, int ld, long sA, const T* tau, long sTau, const cplx* colscale, int batch) {
+  size_t extra = sizeof(T) * m + 64;
+  size_t stage = sizeof(T) * (size_t)m * n;
+  bool do_stage = (stage + extra) <= kSmemStageLimit;
+  size_t smem = extra + (do_stage ? stage : 0);
+#define FQ_LAUNCH(MAXR, STG) do { \
+    CK(cudaFuncSetAttribute(k_formq<T, MAXR, STG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    k_formq<T, MAXR, STG><<<batch, 512, smem, st>>>(A, m, n, ld, sA, tau, sTau, colscale); } while (0)
+#define FQ_DISPATCH(MAXR) do { if (do_stage) FQ_LAUNCH(MAXR, 1); else FQ_LAUNCH(MAXR, 0); } while (0)
+  if (m <= 64) FQ_DISPATCH(2); else if (m <= 128) FQ_DISPATCH(4); else if (m <= 288) FQ_DISPATCH(9); else if (m <= 576) FQ_DISPATCH(18);
+  else throw CudaError("k_formq: matrices with more than 576 rows are not supported in this build");
+  CKL();
+#undef FQ_DISPATCH
+#undef FQ_LAUNCH
+}
+
+template <typename T>
+static void launch_trsm(cudaStream_t st, const T* R, int ldr, long sR, T* B, int ldb, long sB, int n, int nrhs, const double* dinv, long sD, int batch) {
+  dim3 grid((nrhs + TRSM_COLS - 1) / TRSM_COLS, batch);
+  size_t smem = sizeof(T) * n;
+  if (n <= 64) k_trsm_lun<T, 2><<<grid, TRSM_WARPS * 32, smem, st>>>(R, ldr, sR, B, ldb, sB, n, nrhs, dinv, sD);
+  else if (n <= 128) k_trsm_lun<T, 4><<<grid, TRSM_WARPS * 32, smem, st>>>(R, ldr, sR, B, ldb, sB, n, nrhs, dinv, sD);
+  else if (n <= 288) k_trsm_lun<T, 9><<<grid, TRSM_WARPS * 32, smem, st>>>(R, ldr, sR, B, ldb, sB, n, nrhs, dinv, sD);
+  else if (n <= 576) k_trsm_lun<T, 18><<<grid, TRSM_WARPS * 32, smem, st>>>(R, ldr, sR, B, ldb, sB, n, nrhs, dinv, sD);
+  else throw CudaError("k_trsm_lun: n > 576 not supported in this build");
+  CKL();
+}
+
+// phase bookkeeping of decompose (udv_state_mod.F90:480-492, 578): Phase = prod R_ii * sign(perm), conjugated for side L;
+// beta = 1/Phase scales row 1 of R, Phase scales column 1 of U.  det(U_new) = det(Q) * Phase.
+__global__ void k_decomp_phase(const QrOut* __restrict__ q, int side_l, cplx* __restrict__ ph, cplx* __restrict__ beta, cplx* __restrict__ det, int n) {
+  int b = blockIdx.x * blockDim.x + threadIdx.x; if (b >= n) return;
+  cplx p = q[b].perm_sign * q[b].diag_phase;
+  if (side_l) p = conj_(p);
+  ph[b] = p; beta[b] = cplx(1.0, 0.0) / p; det[b] = q[b].detq * p;
+}
+
+// decompose_UDV_state (Prog/udv_state_mod.F90:448-582, default branch) for a batch
+template <typename T>
+static void la_decompose(LaWork<T>& w, UdvDev<T>& s, char side) {
+  const int N = w.N, NM = w.NM; const long n2 = w.n2(); cudaStream_t st = w.st;
+  const bool left = (side == 'l' || side == 'L');
+  k_colscale<T><<<dim3(ew_blocks(n2), NM), 256, 0, st>>>(s.U, N, n2, N, N, s.D, N); CKL();
+  launch_qrp<T, 1>(st, s.U, N, N, N, n2, w.tau, N, w.jpvt, N, s.D, N, w.qrout, NM);
+  k_decomp_phase<<<(NM + 127) / 128, 128, 0, st>>>(w.qrout, left ? 1 : 0, w.sc_phase, w.sc_beta, s.det, NM); CKL();
+  k_row0scale<T><<<dim3((N + 255) / 256, NM), 256, 0, st>>>(s.U, N, n2, N, w.sc_beta); CKL();
+  if (!left) {
+    k_permcopy<T, 1><<<dim3(ew_blocks(n2), NM), 256, 0, st>>>(w.W[0], N, n2, s.V, N, n2, N, N, w.jpvt, N); CKL();
+    gemm<T, 0, 0, 1>(st, N, N, N, s.U, N, n2, w.W[0], N, n2, s.V, N, n2, NM);          // V = R * (P^T V)
+  } else {
+    k_permcopy<T, 2><<<dim3(ew_blocks(n2), NM), 256, 0, st>>>(w.W[0], N, n2, s.V, N, n2, N, N, w.jpvt, N); CKL();
+    gemm<T, 0, 1, 2>(st, N, N, N, w.W[0], N, n2, s.U, N, n2, s.V, N, n2, NM);          // V = (V P) * R^H
+  }
+  launch_formq<T>(st, s.U, N, N, N, n2, w.tau, N, w.sc_phase, NM);
+}
+
+// per-matrix phase factor of det(1 + B_R B_L) without Op_phase (Prog/cgr1_mod.F90:300-349)
+__global__ void k_cgr_z(const QrOut* __restrict__ q, const cplx* __restrict__ detR, const cplx* __restrict__ detL, int nvar, cplx* __restrict__ z, int n) {
+  int b = blockIdx.x * blockDim.x + threadIdx.x; if (b >= n) return;
+  cplx dp = q[b].diag_phase, dq = q[b].detq;
+  if (nvar != 1) { dp = conj_(dp); dq = conj_(dq); }
+  z[b] = ((detR[b] * conj_(detL[b])) * q[b].perm_sign) * (dp * dq);
+}
+
+// CGR (Prog/cgr1_mod.F90:176-447): G = (1 + B_R B_L)^-1 and the phase factor z per matrix.  stab = 3 selects the
+// scale-separated branch.  Gout must not alias any input.
+template <typename T>
+static void la_cgr(LaWork<T>& w, int nvar, int stab, const UdvDev<T>& R, const UdvDev<T>& L, T* Gout, cplx* z) {
+  const int N = w.N, NM = w.NM; const long n2 = w.n2(); cudaStream_t st = w.st;
+  dim3 eg(ew_blocks(n2), NM);
+  gemm<T, 1, 0, 0>(st, N, N, N, R.U, N, n2, L.U, N, n2, w.W[0], N, n2, NM);            // RHS = U_R^H U_L
+  gemm<T, 0, 0, 0>(st, N, N, N, R.V, N, n2, L.V, N, n2, w.W[1], N, n2, NM);            // TPUP = V_R V_L
+  if (stab == 3) { if (nvar == 1) k_cgr_tpup<T, 1, 0><<<eg, 256, 0, st>>>(w.W[2], w.W[1], w.W[0], n2, N, R.D, L.D, N);
+                   else k_cgr_tpup<T, 1, 1><<<eg, 256, 0, st>>>(w.W[2], w.W[1], w.W[0], n2, N, R.D, L.D, N); }
+  else { if (nvar == 1) k_cgr_tpup<T, 0, 0><<<eg, 256, 0, st>>>(w.W[2], w.W[1], w.W[0], n2, N, R.D, L.D, N);
+         else k_cgr_tpup<T, 0, 1><<<eg, 256, 0, st>>>(w.W[2], w.W[1], w.W[0], n2, N, R.D, L.D, N); }
+  CKL();
+  launch_qrp<T, 1>(st, w.W[2], N, N, N, n2, w.tau, N, w.jpvt, N, w.Dq, N, w.qrout, NM);
+  k_cgr_z<<<(NM + 127) / 128, 128, 0, st>>>(w.qrout, R.det, L.det, nvar, z, NM); CKL();
+  // explicit Q in W[1]
+  k_permcopy<T, 0><<<eg, 256, 0, st>>>(w.W[1], N, n2, w.W[2], N, n2, N, N, nullptr, 0); CKL();
+  launch_formq<T>(st, w.W[1], N, N, N, n2, w.tau, N, nullptr, NM);
+  // X0 = U_R^H (nvar 1) or U_L^H (nvar 2), with the D_+^-1 row scaling of the STAB3 branch
+  const UdvDev<T>& A0 = (nvar == 1) ? R : L;
+  const UdvDev<T>& A1 = (nvar == 1) ? L : R;
+  k_permcopy<T, 4><<<eg, 256, 0, st>>>(w.W[0], N, n2, A0.U, N, n2, N, N, nullptr, 0); CKL();
+  if (stab == 3) { k_sep_scale<T, 1><<<eg, 256, 0, st>>>(w.W[0], n2, N, A0.D, N); CKL(); }
+  gemm<T, 1, 0, 0>(st, N, N, N, w.W[1], N, n2, w.W[0], N, n2, w.W[3], N, n2, NM);      // X = Q^H X0
+  launch_trsm<T>(st, w.W[2], N, n2, w.W[3], N, n2, N, N, w.Dq, N, NM);                 // X = R^-1 D^-1 X
+  k_permcopy<T, 3><<<eg, 256, 0, st>>>(w.W[0], N, n2, w.W[3], N, n2, N, N, w.jpvt, N); CKL();   // X2 = P X
+  if (stab == 3) { k_sep_scale<T, 1><<<eg, 256, 0, st>>>(w.W[0], n2, N, A1.D, N); CKL(); }
+  if (nvar == 1) gemm<T, 0, 0, 0>(st, N, N, N, L.U, N, n2, w.W[0], N, n2, Gout, N, n2, NM);        // G = U_L X2
+  else gemm<T, 1, 1, 0>(st, N, N, N, w.W[0], N, n2, R.U, N, n2, Gout, N, n2, NM);                 // G = X2^H U_R^H
+}

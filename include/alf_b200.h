@@ -1,0 +1,121 @@
+/* alf_b200.h -- C-ABI of the B200-native auxiliary-field QMC sweep (drop-in for ALF's L2/L3 hot path).
+ *
+ * ALF has no FFI around this path: the seam is a set of Fortran module procedures that share module-global
+ * state.  A Fortran shim (alf_b200/fortran/alf_b200_shim.F90, shown in INTEGRATION.md) keeps those
+ * procedure names and forwards their bodies to the entry points below.  Plain pointers and sizes only; every
+ * function returns 0 on success and a non-zero ALF error code otherwise (mapped by the shim to
+ * Terminate_on_error, Libraries/Modules/runtime_error_mod.F90:56-68,81-130).  No global state: everything hangs
+ * off the opaque handle; one CUDA stream per handle; not re-entrant per handle (as the reference: one thread/rank).
+ *
+ * Conventions at the boundary (all as on the Fortran side):
+ *   - complex numbers are interleaved (re, im) doubles = complex(kind(0.d0));
+ *   - matrices are column-major with leading dimension = number of rows;
+ *   - index arrays (P, time slices nt, operator index n, flavor nf) are 1-BASED;
+ *   - "chain" = one Markov chain = one MPI rank of the reference; chains are 0-based (they have no Fortran analogue).
+ */
+#ifndef ALF_B200_H
+#define ALF_B200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct alf_b200_handle alf_b200_handle;
+
+/* error codes: Libraries/Modules/runtime_error_mod.F90:56-68 */
+enum {
+  ALF_OK = 0,
+  ALF_ERROR_GENERIC = 1,
+  ALF_ERROR_HAMILTONIAN = 2,
+  ALF_ERROR_FIELDS = 3,
+  ALF_ERROR_UNSTABLE_MATRIX = 4,   /* Control_PrecisionG threshold exceeded / NaN (control_mod.F90:219-283) */
+  ALF_ERROR_CUDA = 100,            /* CUDA runtime failure or no sm_100 device: there is NO CPU fallback */
+  ALF_ERROR_UNSUPPORTED = 101
+};
+
+/* ---- life cycle.  Replaces the allocations of Prog/main.F90:589-605 and Wrapgr_alloc (Wrapgr_mod.F90:70-78).
+ * ndim, n_fl, n_sun, ltrot, symm: public state of Hamiltonian_main (Prog/Hamiltonian_main_mod.F90:181-197);
+ * nwrap: VAR_QMC (Prog/QMC_runtime_var_mod.F90:73-79); n_opv = size(Op_V,1); n_opt = size(Op_T,1);
+ * n_chains: number of independent Markov chains advanced by every call; device: CUDA ordinal.
+ * stab: 0 = default CGR branch, 3 = scale-separated branch (-DSTAB3, configure.sh:332-357). */
+int alf_b200_create(alf_b200_handle** h, int ndim, int n_fl, int n_sun, int ltrot, int nwrap, int n_opv, int n_opt,
+                    int symm, int stab, int n_chains, int device);
+int alf_b200_destroy(alf_b200_handle* h);
+const char* alf_b200_last_error(const alf_b200_handle* h);
+
+/* ---- model tables.  One call per Op_V(n,nf) / Op_T(nc,nf) with the PUBLIC fields of type Operator
+ * (Prog/Operator_mod.F90:57-69).  M_exp/E_exp and Hop_mod's ExpOpT_vec are private in ALF, so finalize_model
+ * recomputes them exactly as Op_set/Op_exp do (Operator_mod.F90:400-529, OpTTypes_mod.F90:92-133,203-234),
+ * i.e. it replaces Hop_mod_init (Prog/Hop_mod.F90:118). */
+int alf_b200_set_op_v(alf_b200_handle* h, int n, int nf, int N, int n_non_zero, int diag, int type, const int* P,
+                      const double* U, const double* E, double g_re, double g_im, double alpha_re, double alpha_im);
+int alf_b200_set_op_t(alf_b200_handle* h, int nc, int nf, int N, int diag, const int* P, const double* U, const double* E,
+                      double g_re, double g_im);
+int alf_b200_finalize_model(alf_b200_handle* h);
+int alf_b200_is_complex(const alf_b200_handle* h);   /* 1 if the complex instantiation was selected */
+
+/* ---- random numbers and fields.  Replaces Ranset per rank (Libraries/Modules/random_wrap_mod.F90:52-80,
+ * Prog/Set_random_mod.F90:48-106) and Fields_set / nsigma%f access (Prog/Fields_mod.F90:588-610). */
+int alf_b200_set_seeds(alf_b200_handle* h, const int32_t* seeds /* n_chains */);
+int alf_b200_get_rng_state(alf_b200_handle* h, uint64_t* state /* n_chains*4 */);
+int alf_b200_set_rng_state(alf_b200_handle* h, const uint64_t* state);
+int alf_b200_fields_set(alf_b200_handle* h);                           /* random start, draws from each chain's stream */
+int alf_b200_set_fields(alf_b200_handle* h, const double* f /* complex [chain][nt][n] */);
+int alf_b200_get_fields(alf_b200_handle* h, double* f);
+
+/* ---- batched mode: the body of the get_sequential() branch of Prog/main.F90 for all chains of the handle. */
+int alf_b200_init_sweep(alf_b200_handle* h);                 /* main.F90:589-631: storage fill (WRAPUL), G(0) = CGR, Phase */
+int alf_b200_sweep(alf_b200_handle* h, int n_sweeps, int ltau);  /* main.F90:714-887 (+ TAU_M when ltau = 1) */
+/* end-to-end form with HOST buffers: upload fields -> n_sweeps sweeps -> download fields, observables, counters */
+int alf_b200_sweep_host(alf_b200_handle* h, int n_sweeps, int ltau, const double* fields_in, double* fields_out,
+                        double* obs_out /* alf_b200_obs_size() doubles */, double* control_out /* 16 doubles */);
+
+/* ---- compat mode: one reference routine per call, on all chains (argument meaning as in the reference). */
+int alf_b200_wrapgrup(alf_b200_handle* h, int ntau);          /* Prog/Wrapgr_mod.F90:81  (NTAU in 0..Ltrot-1) */
+int alf_b200_wrapgrdo(alf_b200_handle* h, int ntau);          /* Prog/Wrapgr_mod.F90:160 (NTAU in Ltrot..1)   */
+int alf_b200_wrapur(alf_b200_handle* h, int ntau, int ntau1); /* Prog/wrapur_mod.F90:37  on udvr */
+int alf_b200_wrapul(alf_b200_handle* h, int ntau1, int ntau); /* Prog/wrapul_mod.F90:36  on udvl */
+int alf_b200_udv_reset(alf_b200_handle* h, int which /*0 udvl,1 udvr*/, char side);   /* udv_state_mod.F90:224 */
+int alf_b200_cgr(alf_b200_handle* h, int nvar);               /* Prog/cgr1_mod.F90:36: GR, Phase from udvr, udvl */
+int alf_b200_tau_m(alf_b200_handle* h);                       /* Prog/tau_m_mod.F90:56 */
+
+/* ---- results */
+int alf_b200_get_green(alf_b200_handle* h, int chain, int nf, int symmetrize, double* out /* complex N*N */);
+int alf_b200_set_green(alf_b200_handle* h, int chain, int nf, const double* in);
+int alf_b200_get_phase(alf_b200_handle* h, double* out /* complex [chain] */);
+int alf_b200_get_udv(alf_b200_handle* h, int which /*0 udvl,1 udvr,2 udvst*/, int nst, int chain, int nf,
+                     double* U, double* D, double* V /* complex */);
+/* control accumulators (Prog/control_mod.F90:53-71), reduced over chains:
+ * [0] XMEANG sum [1] XMAXG [2] NCG [3] XMAXP [4] XMEAN_tau sum [5] XMAX_tau [6] NCG_tau [7] NC_up [8] ACC_up
+ * [9] NC_eff_up [10] ACC_eff_up [11] NaN flag [12] unstable flag (XMAX > 10) */
+int alf_b200_get_control(alf_b200_handle* h, double* out /* 16 */);
+int alf_b200_accept_log(alf_b200_handle* h, int enable);     /* record accept/reject per field visit (check 2) */
+int alf_b200_get_accept_log(alf_b200_handle* h, uint8_t* out, long cap, long* n_per_chain);
+int alf_b200_taum_capture(alf_b200_handle* h, int every);    /* keep GT0,G0T,G00,GTT handed to ObserT every k-th slice */
+int alf_b200_get_taum(alf_b200_handle* h, int chain, double* out, long cap_complex, long* n_complex);
+
+/* ---- device-side scalar observables accumulated where main.F90 calls ham%Obser (:757-773,:789-802).
+ * Layout: [0] N_meas, [1..2] sum phase/|Re phase| sign, then per chain-summed: Kin, Pot, Part, Ener (re,im each). */
+int alf_b200_obs_size(const alf_b200_handle* h);
+int alf_b200_obs_reset(alf_b200_handle* h);
+int alf_b200_obs_device_ptr(alf_b200_handle* h, double** dptr, long* n_doubles);  /* for the NCCL bin reduction */
+int alf_b200_get_obs(alf_b200_handle* h, double* out);
+
+/* ---- kernel-level entry points used by the parity tests (host arrays in, host arrays out; batch of matrices) */
+int alf_b200_test_qdrp(int device, int is_complex, int m, int n, int batch, double* A /* complex m*n*batch, in/out */,
+                       double* D /* n*batch */, int* jpvt /* n*batch, 1-based */, double* tau /* complex n*batch */,
+                       double* phases /* 5*batch: perm sign, diag phase re/im, detq re/im */);
+int alf_b200_test_udv_decompose(int device, int is_complex, int n, int batch, char side, double* U, double* D, double* V);
+int alf_b200_test_cgr(int device, int is_complex, int n, int batch, int nvar, int stab, const double* UR, const double* DR,
+                      const double* VR, const double* UL, const double* DL, const double* VL, const double* detUR,
+                      const double* detUL, double* G, double* phase);
+int alf_b200_test_gemm(int device, int is_complex, int ta, int tb, int m, int n, int k, int batch, const double* A,
+                       const double* B, double* C);
+int alf_b200_hop_apply(alf_b200_handle* h, int which /* 0 mmthr,1 mmthr_m1,2 mmthl,3 mmthl_m1,4 mmthlc,5 Symm */,
+                       int nf, double* A /* complex N*N, in/out */);
+int alf_b200_fp64_peak(int device, double* dfma_tflops, double* dmma_tflops);   /* roofline denominator microbenchmark */
+
+#ifdef __cplusplus
+}
+#endif
+#endif

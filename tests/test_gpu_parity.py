@@ -1,0 +1,231 @@
+"""GPU parity tests (-m gpu): every kernel and the full sweep, through the C-ABI, against the CPU oracle.
+Tolerances: 1e-10 relative Frobenius on freshly recomputed G (north_star check 1); accept/reject sequences and field
+configurations bit-exact (check 2)."""
+import numpy as np
+import pytest
+
+from alf_b200 import api
+from alf_b200.api import AlfB200
+from alf_b200.model import hubbard_square, hubbard_chain, kondo_square
+import oracle.oracle as O
+from oracle.oracle import Oracle
+from common import relF, SEEDS, TOL_G, config1, config2, config3
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("is_complex", [False, True])
+@pytest.mark.parametrize("ta,tb", [(0, 0), (1, 0), (0, 1), (1, 1)])
+@pytest.mark.parametrize("m,n,k", [(16, 16, 16), (64, 64, 64), (70, 33, 45), (256, 256, 256)])
+def test_gemm(is_complex, ta, tb, m, n, k):
+    rng = np.random.default_rng(0); batch = 3
+    def mk(r, c):
+        x = rng.normal(size=(batch, r, c)); return x + (1j * rng.normal(size=(batch, r, c)) if is_complex else 0)
+    A = mk(k, m) if ta else mk(m, k); B = mk(n, k) if tb else mk(k, n)
+    Cg = api.test_gemm(A, B, ta, tb, is_complex)
+    opA = A.conj().transpose(0, 2, 1) if ta else A; opB = B.conj().transpose(0, 2, 1) if tb else B
+    assert relF(Cg, opA @ opB) < 1e-14
+
+
+@pytest.mark.parametrize("is_complex", [False, True])
+@pytest.mark.parametrize("n", [5, 16, 50, 64, 100, 256])
+def test_qdrp_reconstruct(is_complex, n):
+    """A P = Q D R with unit-modulus diag(R) (20-qdrp.F90), pivots = descending |R_ii| D, and same D as LAPACK's ZGEQP3."""
+    rng = np.random.default_rng(n); batch = 2
+    A = rng.normal(size=(batch, n, n)) * np.exp(rng.normal(size=(batch, 1, n)) * 4)
+    if is_complex:
+        A = A + 1j * rng.normal(size=(batch, n, n))
+    if n == 50:
+        A[0] = np.array([[1.0 / (i + j + 1) for j in range(n)] for i in range(n)])
+    QR, D, jp, tau, ph = api.test_qdrp(A, is_complex)
+    for b in range(batch):
+        R = np.triu(QR[b]); Q = np.eye(n, dtype=complex)
+        for j in range(n):
+            v = np.zeros(n, complex); v[j] = 1; v[j + 1:] = QR[b][j + 1:, j]
+            Q = Q @ (np.eye(n) - tau[b, j] * np.outer(v, v.conj()))
+        assert relF(Q @ np.diag(D[b]) @ R, A[b][:, jp[b] - 1]) < 1e-12
+        assert relF(Q.conj().T @ Q, np.eye(n)) < 1e-12
+        assert np.all(np.abs(np.abs(np.diag(R)) - 1) < 1e-12)
+        _, Dref, _, _ = O.qdrp(A[b])
+        if n != 50:
+            assert relF(D[b], Dref.real) < 1e-8
+        sign = np.linalg.det(np.eye(n)[:, jp[b] - 1])
+        assert abs(sign - ph[b, 0]) < 1e-12
+        assert abs(np.linalg.det(Q) - complex(ph[b, 3], ph[b, 4])) < 1e-9
+
+
+@pytest.mark.parametrize("is_complex", [False, True])
+@pytest.mark.parametrize("side", ["r", "l"])
+@pytest.mark.parametrize("n", [16, 64, 256])
+def test_udv_decompose(is_complex, side, n):
+    """decompose: the product U D V (side r) / U D V^H (side l) is unchanged and matches the oracle's factorisation product."""
+    rng = np.random.default_rng(3 + n); batch = 2
+    U0 = rng.normal(size=(batch, n, n)) + (1j * rng.normal(size=(batch, n, n)) if is_complex else 0)
+    V0 = np.stack([np.linalg.qr(rng.normal(size=(n, n)) + (1j * rng.normal(size=(n, n)) if is_complex else 0))[0] for _ in range(batch)])
+    D0 = np.exp(rng.normal(size=(batch, n)) * 5)
+    U, D, V = api.test_udv_decompose(U0, D0, V0, side, is_complex)
+    for b in range(batch):
+        B0 = U0[b] @ np.diag(D0[b]) @ (V0[b] if side == "r" else V0[b].conj().T)
+        B1 = U[b] @ np.diag(D[b]) @ (V[b] if side == "r" else V[b].conj().T)
+        assert relF(B1, B0) < 1e-11
+        assert relF(U[b].conj().T @ U[b], np.eye(n)) < 1e-12
+        Uo, Do, Vo = O.udv_decompose(U0[b], D0[b], V0[b], side)
+        assert relF(D[b].real, Do.real) < 1e-8
+        assert abs(np.linalg.det(V[b]) / np.linalg.det(Vo) - 1) < 1e-8
+
+
+@pytest.mark.parametrize("is_complex", [False, True])
+@pytest.mark.parametrize("nvar", [1, 2])
+@pytest.mark.parametrize("stab", [0, 3])
+@pytest.mark.parametrize("n", [5, 16, 64])
+def test_cgr_kernel(is_complex, nvar, stab, n):
+    """CGR on UDV states with 20 orders of magnitude of scales: G and phase vs the oracle (15-cgr.F90 tolerances)."""
+    rng = np.random.default_rng(100 + n); batch = 2
+    UR, DR, VR, UL, DL, VL, dR, dL = [], [], [], [], [], [], [], []
+    for b in range(batch):
+        def mk(side):
+            U0 = rng.normal(size=(n, n)) + (1j * rng.normal(size=(n, n)) if is_complex else 0)
+            U0 = U0 * np.exp(np.linspace(-10, 10, n))[None, :]
+            return O.udv_decompose(U0, np.ones(n), np.eye(n), side)
+        a = mk("r"); c = mk("l")
+        UR.append(a[0]); DR.append(a[1]); VR.append(a[2]); UL.append(c[0]); DL.append(c[1]); VL.append(c[2])
+        dR.append(np.linalg.det(a[0])); dL.append(np.linalg.det(c[0]))
+    st = lambda x: np.stack(x)
+    G, ph = api.test_cgr(st(UR), st(DR), st(VR), st(UL), st(DL), st(VL), st(dR), st(dL), nvar, stab, is_complex)
+    for b in range(batch):
+        Go, pho = O.cgr(UR[b], DR[b], VR[b], UL[b], DL[b], VL[b], nvar=nvar, stab3=(stab == 3))
+        assert relF(G[b], Go) < TOL_G
+        assert abs(ph[b] - pho) < 1e-9
+
+
+def _hop_check(model, nf=1):
+    g = AlfB200(model, n_chains=2, nwrap=5)
+    o = Oracle(model, nwrap=5)
+    rng = np.random.default_rng(9)
+    A = rng.normal(size=(model.Ndim, model.Ndim)) + (1j * rng.normal(size=(model.Ndim, model.Ndim)) if g.is_complex else 0)
+    for which in range(6):
+        assert relF(g.hop_apply(which, nf, A), o.hop_apply(which, nf, A)) < 1e-13, which
+    g.close()
+
+
+def test_hop_checkerboard_symm():
+    _hop_check(config1())
+
+
+def test_hop_dense():
+    _hop_check(hubbard_square(4, 4, 1.0, checkerboard=False, symm=False))
+
+
+def test_hop_golden_26_path():
+    """The golden-vector operator (testsuite/Prog.tests/26-...) family goes through the dense-T GEMM path on the GPU."""
+    _hop_check(hubbard_chain(4, 1.0, 0.1, Mz=False, symm=True))
+
+
+def _run_parity(model, seeds, nwrap, n_sweeps=1, stab=0, check_udv=True):
+    C = len(seeds)
+    g = AlfB200(model, n_chains=C, nwrap=nwrap, stab=stab)
+    g.set_seeds(seeds); g.fields_set()
+    orcs = []
+    for s in seeds:
+        o = Oracle(model, nwrap=nwrap, stab3=(stab == 3)); o.ranset(s); o.fields_set(); orcs.append(o)
+    f = g.get_fields()
+    for c, o in enumerate(orcs):
+        assert np.array_equal(f[c], o.get_fields()), "Fields_set stream differs"
+    g.init_sweep()
+    for o in orcs:
+        o.init()
+    ph = g.phase()
+    for c, o in enumerate(orcs):
+        for nf in range(1, model.N_FL + 1):
+            assert relF(g.green(c, nf), o.green(nf)) < TOL_G, ("init", c, nf)
+        assert abs(ph[c] - o.phase()) < 1e-9
+        if check_udv:
+            U, D, V = g.get_udv(0, 0, c, 1); Uo, Do, Vo = o.get_udv(0, 0, 1)
+            assert relF(D.real, Do.real) < 1e-7        # scales of the stored left propagation
+    g.accept_log(True)
+    for o in orcs:
+        o.log(True)
+    for sw in range(n_sweeps):
+        g.sweep(1, 0)
+        for o in orcs:
+            o.sweep(0)
+    log = g.get_accept_log(); f = g.get_fields(); ph = g.phase(); st = g.rng_state()
+    for c, o in enumerate(orcs):
+        acc, _ = o.get_log()
+        assert log.shape[1] == acc.size
+        nbad = int(np.sum(acc != log[c]))
+        assert nbad == 0, f"chain {c}: {nbad} of {acc.size} accept/reject decisions differ (first at {np.argmax(acc != log[c])})"
+        assert np.array_equal(f[c], o.get_fields())
+        assert np.array_equal(st[c], o.rng_state())
+        for nf in range(1, model.N_FL + 1):
+            assert relF(g.green(c, nf), o.green(nf)) < TOL_G, ("sweep", c, nf)
+        assert abs(ph[c] - o.phase()) < 1e-9
+    cg = g.control(); tot = {k: 0.0 for k in ("NC_up", "ACC_up", "NCG")}
+    for o in orcs:
+        co = o.control()
+        for k in tot:
+            tot[k] += co[k]
+    assert cg["NC_up"] == tot["NC_up"] and cg["ACC_up"] == tot["ACC_up"] and cg["NCG"] == tot["NCG"]
+    assert cg["XMAXG"] < 1e-6 and cg["nan"] == 0 and cg["unstable"] == 0
+    g.close()
+    return cg
+
+
+def test_sweep_config1_real_mz():
+    """configs[0]: Hubbard 4x4 Mz, U=4, beta=5, dtau=0.1, Nwrap=10."""
+    _run_parity(config1(), SEEDS[:4], nwrap=10, n_sweeps=2)
+
+
+def test_sweep_config1_stab3():
+    _run_parity(config1(), SEEDS[:2], nwrap=10, n_sweeps=1, stab=3)
+
+
+def test_sweep_config1_su2_complex():
+    """configs[0], SU(2) variant: N_FL=1, imaginary coupling -> complex instantiation, non-trivial Op_phase."""
+    _run_parity(config1(Mz=False), SEEDS[:3], nwrap=10, n_sweeps=1)
+
+
+def test_sweep_dense_hopping_nonsymm():
+    _run_parity(hubbard_square(4, 4, 2.0, checkerboard=False, symm=False), SEEDS[:2], nwrap=5, n_sweeps=1)
+
+
+def test_sweep_ragged_stabilisation():
+    """Ltrot not a multiple of Nwrap (last interval shorter) and Nwrap > Ltrot (single interval)."""
+    _run_parity(hubbard_square(4, 4, 2.3, symm=False), SEEDS[:2], nwrap=7, n_sweeps=1)
+    _run_parity(hubbard_square(2, 2, 0.5), SEEDS[:2], nwrap=10, n_sweeps=1)
+
+
+def test_sweep_config2():
+    """configs[1]: Hubbard 8x8, beta=10 (N_dim=64), a few of the 256 chains."""
+    _run_parity(config2(), SEEDS[:3], nwrap=10, n_sweeps=1)
+
+
+def test_sweep_kondo_complex_k2():
+    """configs[3] family at test size: Kondo 4x4 bilayer (N_dim=32), rank-1 + rank-2 non-diagonal vertices, complex."""
+    _run_parity(kondo_square(4, 4, 2.0), SEEDS[:2], nwrap=5, n_sweeps=1, check_udv=False)
+
+
+def test_init_config3():
+    """configs[2]: Hubbard 16x16 beta=10 (N_dim=256): storage fill + CGR at tau=0 for 2 chains."""
+    model = config3(); seeds = SEEDS[:2]
+    g = AlfB200(model, n_chains=2, nwrap=10); g.set_seeds(seeds); g.fields_set(); g.init_sweep()
+    ph = g.phase()
+    for c, s in enumerate(seeds):
+        o = Oracle(model, nwrap=10); o.ranset(s); o.fields_set(); o.init()
+        for nf in (1, 2):
+            assert relF(g.green(c, nf), o.green(nf)) < TOL_G
+        assert abs(ph[c] - o.phase()) < 1e-9
+    g.close()
+
+
+def test_many_chains_are_independent():
+    """Chains are independent Markov chains: a batch of 40 gives the same per-chain results as batches of 1."""
+    model = hubbard_square(4, 4, 1.0); seeds = [1000 + 7 * i for i in range(40)]
+    g = AlfB200(model, n_chains=40, nwrap=5); g.set_seeds(seeds); g.fields_set(); g.init_sweep(); g.sweep(1, 0)
+    f = g.get_fields()
+    for c in (0, 17, 39):
+        g1 = AlfB200(model, n_chains=1, nwrap=5); g1.set_seeds([seeds[c]]); g1.fields_set(); g1.init_sweep(); g1.sweep(1, 0)
+        assert np.array_equal(g1.get_fields()[0], f[c])
+        assert relF(g1.green(0, 1), g.green(c, 1)) < 1e-13
+        g1.close()
+    g.close()
