@@ -172,12 +172,13 @@ class AlfB200:
         keys = ["XMEANG", "XMAXG", "NCG", "XMAXP", "XMEAN_tau", "XMAX_tau", "NCG_tau", "NC_up", "ACC_up", "NC_eff_up", "ACC_eff_up", "nan", "unstable"]
         return dict(zip(keys, out))
 
-    def accept_log(self, enable=True):
-        self._ck(lib().alf_b200_accept_log(self.h, int(enable)))
+    def accept_log(self, n_sweeps=1):
+        self._log_sweeps = int(n_sweeps)
+        self._ck(lib().alf_b200_accept_log(self.h, int(n_sweeps)))
 
     def get_accept_log(self):
         n = C.c_long(0)
-        cap = 2 * self.m.Ltrot * self.m.n_opv * self.C
+        cap = 2 * self.m.Ltrot * self.m.n_opv * self.C * max(1, getattr(self, '_log_sweeps', 1))
         out = np.full(cap, 255, dtype=np.uint8)
         self._ck(lib().alf_b200_get_accept_log(self.h, out.ctypes.data_as(C.POINTER(C.c_uint8)), C.c_long(cap), C.byref(n)))
         return out[: n.value * self.C].reshape(self.C, n.value)
@@ -194,6 +195,9 @@ class AlfB200:
         ntau = n.value // (4 * self.m.N_FL * nn)
         return buf.reshape(ntau, 4, self.m.N_FL, self.N, self.N).transpose(0, 1, 2, 4, 3)
 
+    def obs_size(self):
+        return int(lib().alf_b200_obs_size(self.h))
+
     def obs(self):
         n = lib().alf_b200_obs_size(self.h)
         out = np.zeros(n)
@@ -207,6 +211,22 @@ class AlfB200:
         p = _dp(); n = C.c_long(0)
         self._ck(lib().alf_b200_obs_device_ptr(self.h, C.byref(p), C.byref(n)))
         return C.cast(p, C.c_void_p).value, n.value
+
+    # ---- measurement support
+    KCATS = ["update", "ops_wrap", "qrp", "formq", "gemm", "trsm", "elementwise", "obs"]
+
+    def stream_ptr(self):
+        p = C.c_void_p()
+        self._ck(lib().alf_b200_get_stream(self.h, C.byref(p)))
+        return p.value or 0
+
+    def kernel_timing(self, mask=0):
+        self._ck(lib().alf_b200_kernel_timing(self.h, C.c_uint(mask)))
+
+    def kernel_stats(self):
+        ms = np.zeros(8); n = np.zeros(8, dtype=np.int64)
+        self._ck(lib().alf_b200_get_kernel_stats(self.h, _d(ms), n.ctypes.data_as(C.POINTER(C.c_long))))
+        return {k: (float(ms[i]), int(n[i])) for i, k in enumerate(self.KCATS)}
 
     def hop_apply(self, which, nf, A):
         A = np.asfortranarray(A, dtype=np.complex128).copy(order="F")

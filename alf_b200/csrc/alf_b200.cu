@@ -124,6 +124,8 @@ struct alf_b200_handle {
   std::unique_ptr<EngineBase> eng;
   std::string err;
   cudaStream_t stream = 0;
+  Prof prof;
+  int8_t* pin_fields = nullptr;      // pinned staging buffer of sweep_host
   // untyped device state shared with the engine
   int8_t* d_fields = nullptr; uint64_t* d_rng = nullptr; cplx* d_phase = nullptr; unsigned long long* d_counters = nullptr;
   double* d_ctl = nullptr;            // per chain: 0 XMEANG 1 XMAXG 2 NCG 3 XMAXP 4 XMEAN_tau 5 XMAX_tau 6 NCG_tau 7 flags(nan=1, unstable=2)
@@ -346,8 +348,8 @@ struct Engine : EngineBase {
     const int pw = side == 0 ? pw_l : pw_r;
     dim3 grid((N + pw - 1) / pw, NM);
     size_t smem = (size_t)N * (pw + 1) * sizeof(T);
-    if (side == 0) k_apply_ops<T, 0><<<grid, 256, smem, st>>>(Mx, n2, N, N, pw, md, F, mode, nt_a, nt_b, h->d_fields, L, M);
-    else k_apply_ops<T, 1><<<grid, 256, smem, st>>>(Mx, n2, N, N, pw, md, F, mode, nt_a, nt_b, h->d_fields, L, M);
+    if (side == 0) KL(KC_OPS, st, k_apply_ops<T, 0><<<grid, 256, smem, st>>>(Mx, n2, N, N, pw, md, F, mode, nt_a, nt_b, h->d_fields, L, M));
+    else KL(KC_OPS, st, k_apply_ops<T, 1><<<grid, 256, smem, st>>>(Mx, n2, N, N, pw, md, F, mode, nt_a, nt_b, h->d_fields, L, M));
     CKL();
   }
   // dense hopping: Mx <- E * Mx (left) or Mx * E (right), E per flavor (batch stride 0 inside a flavor is emulated per flavor)
@@ -369,9 +371,9 @@ struct Engine : EngineBase {
 
   void set_udv_identity(UdvDev<T>& u) {   // reset_UDV_state, udv_state_mod.F90:224-249
     dim3 eg(ew_blocks(n2), NM);
-    k_set_identity<T><<<eg, 256, 0, st>>>(u.U, N, n2, N, N); k_set_identity<T><<<eg, 256, 0, st>>>(u.V, N, n2, N, N);
-    k_fill_double<<<ew_blocks((long)N * NM), 256, 0, st>>>(u.D, (long)N * NM, 1.0);
-    k_fill_cplx<<<ew_blocks(NM), 256, 0, st>>>(u.det, NM, cplx(1.0, 0.0)); CKL();
+    KL(KC_EW, st, k_set_identity<T><<<eg, 256, 0, st>>>(u.U, N, n2, N, N)); KL(KC_EW, st, k_set_identity<T><<<eg, 256, 0, st>>>(u.V, N, n2, N, N));
+    KL(KC_EW, st, k_fill_double<<<ew_blocks((long)N * NM), 256, 0, st>>>(u.D, (long)N * NM, 1.0));
+    KL(KC_EW, st, k_fill_cplx<<<ew_blocks(NM), 256, 0, st>>>(u.det, NM, cplx(1.0, 0.0)));
   }
   void copy_udv(UdvDev<T>& dst, const UdvDev<T>& src) {   // assign_UDV_state, udv_state_mod.F90:300-330
     CK(cudaMemcpyAsync(dst.U, src.U, sizeof(T) * n2 * NM, cudaMemcpyDeviceToDevice, st));
@@ -399,13 +401,13 @@ struct Engine : EngineBase {
   void cgr_and_phase(int nvar, bool compare) {
     la_cgr<T>(w, nvar, h->stab, udvr, udvl, G2, d_z);
     if (compare) {
-      k_compare<T><<<NM, 256, 0, st>>>(G2, G, n2, n2, d_cmp); CKL();
-      k_ctl_accum<<<(C + 127) / 128, 128, 0, st>>>(d_cmp, F, h->d_ctl, 0, C); CKL();
+      KL(KC_EW, st, k_compare<T><<<NM, 256, 0, st>>>(G2, G, n2, n2, d_cmp));
+      KL(KC_EW, st, k_ctl_accum<<<(C + 127) / 128, 128, 0, st>>>(d_cmp, F, h->d_ctl, 0, C));
     }
     std::swap(G, G2);
     double* ang = nullptr;
-    if (h->is_complex) { k_op_phase<<<NM, 256, 0, st>>>(h->d_fields, d_angle_tab, F, M, L, d_angle); CKL(); ang = d_angle; }
-    k_phase_update<<<(C + 127) / 128, 128, 0, st>>>(d_z, ang, F, h->n_sun, h->d_phase, h->d_ctl, compare ? 1 : 0, C); CKL();
+    if (h->is_complex) { KL(KC_EW, st, k_op_phase<<<NM, 256, 0, st>>>(h->d_fields, d_angle_tab, F, M, L, d_angle)); ang = d_angle; }
+    KL(KC_EW, st, k_phase_update<<<(C + 127) / 128, 128, 0, st>>>(d_z, ang, F, h->n_sun, h->d_phase, h->d_ctl, compare ? 1 : 0, C));
   }
   void cgr_call(int nvar) override { cgr_and_phase(nvar, false); }
 
@@ -421,8 +423,8 @@ struct Engine : EngineBase {
   void launch_update(int up, int nt) {
     uint8_t* lg = nullptr;
     if (h->acclog_on && h->d_acclog && h->acclog_pos + M <= h->acclog_per_chain) { lg = h->d_acclog + (long)h->acclog_pos * C; h->acclog_pos += M; }
-    if (up) k_wrapgr<T, 1><<<C, 512, upd_smem, st>>>(G, N, F, h->n_sun, M, d_vops, ft, h->d_fields, L, nt, h->d_rng, h->d_phase, h->d_counters, KD, lg, 0);
-    else k_wrapgr<T, 0><<<C, 512, upd_smem, st>>>(G, N, F, h->n_sun, M, d_vops, ft, h->d_fields, L, nt, h->d_rng, h->d_phase, h->d_counters, KD, lg, 0);
+    if (up) KL(KC_UPDATE, st, k_wrapgr<T, 1><<<C, 512, upd_smem, st>>>(G, N, F, h->n_sun, M, d_vops, ft, h->d_fields, L, nt, h->d_rng, h->d_phase, h->d_counters, KD, lg, 0));
+    else KL(KC_UPDATE, st, k_wrapgr<T, 0><<<C, 512, upd_smem, st>>>(G, N, F, h->n_sun, M, d_vops, ft, h->d_fields, L, nt, h->d_rng, h->d_phase, h->d_counters, KD, lg, 0));
     CKL();
   }
 
@@ -582,9 +584,11 @@ __global__ void k_peak_dmma(double* out, int iters) {
 }
 
 // ================================================================================================ C-ABI
-#define API_BEGIN(h) if (!(h)) return ALF_ERROR_GENERIC; try { CK(cudaSetDevice((h)->device));
+#define API_BEGIN(h) if (!(h)) return ALF_ERROR_GENERIC; try { CK(cudaSetDevice((h)->device)); t_prof = &(h)->prof;
 #define API_END(h) } catch (const CudaError& e) { (h)->err = e.what(); return ALF_ERROR_CUDA; } \
   catch (const std::exception& e) { (h)->err = e.what(); return ALF_ERROR_GENERIC; } return ALF_OK;
+#define API_END_NORET(h) } catch (const CudaError& e) { (h)->err = e.what(); return ALF_ERROR_CUDA; } \
+  catch (const std::exception& e) { (h)->err = e.what(); return ALF_ERROR_GENERIC; }
 
 extern "C" {
 
@@ -613,6 +617,7 @@ int alf_b200_destroy(alf_b200_handle* h) {
   h->eng.reset();
   if (h->d_fields) cudaFree(h->d_fields); if (h->d_rng) cudaFree(h->d_rng); if (h->d_phase) cudaFree(h->d_phase);
   if (h->d_counters) cudaFree(h->d_counters); if (h->d_ctl) cudaFree(h->d_ctl); if (h->d_acclog) cudaFree(h->d_acclog); if (h->d_obs) cudaFree(h->d_obs);
+  if (h->pin_fields) cudaFreeHost(h->pin_fields);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
   return ALF_OK;
@@ -656,8 +661,8 @@ int alf_b200_finalize_model(alf_b200_handle* h) {
   CK(cudaMalloc(&h->d_ctl, sizeof(double) * 8 * C)); CK(cudaMemset(h->d_ctl, 0, sizeof(double) * 8 * C));
   h->obs_size = 16; CK(cudaMalloc(&h->d_obs, sizeof(double) * h->obs_size)); CK(cudaMemset(h->d_obs, 0, sizeof(double) * h->obs_size));
   { std::vector<int32_t> z(C, 0); int32_t* d; CK(cudaMalloc(&d, sizeof(int32_t) * C)); CK(cudaMemcpy(d, z.data(), sizeof(int32_t) * C, cudaMemcpyHostToDevice));
-    k_ranset<<<(int)((C + 127) / 128), 128, 0, h->stream>>>(h->d_rng, d, (int)C); CK(cudaStreamSynchronize(h->stream)); cudaFree(d); }
-  k_fill_cplx<<<ew_blocks(C), 256, 0, h->stream>>>(h->d_phase, C, cplx(1.0, 0.0)); CKL();
+    KL(KC_EW, h->stream, k_ranset<<<(int)((C + 127) / 128), 128, 0, h->stream>>>(h->d_rng, d, (int)C)); CK(cudaStreamSynchronize(h->stream)); cudaFree(d); }
+  KL(KC_EW, h->stream, k_fill_cplx<<<ew_blocks(C), 256, 0, h->stream>>>(h->d_phase, C, cplx(1.0, 0.0)));
   if (h->is_complex) h->eng.reset(new Engine<cplx>(h)); else h->eng.reset(new Engine<double>(h));
   CK(cudaStreamSynchronize(h->stream));
   h->finalized = true;
@@ -670,14 +675,14 @@ int alf_b200_is_complex(const alf_b200_handle* h) { return h && h->is_complex ? 
 int alf_b200_set_seeds(alf_b200_handle* h, const int32_t* seeds) {
   API_BEGIN(h) NEED_FINAL(h)
   int32_t* d; CK(cudaMalloc(&d, sizeof(int32_t) * h->n_chains)); CK(cudaMemcpy(d, seeds, sizeof(int32_t) * h->n_chains, cudaMemcpyHostToDevice));
-  k_ranset<<<(h->n_chains + 127) / 128, 128, 0, h->stream>>>(h->d_rng, d, h->n_chains); CKL(); CK(cudaStreamSynchronize(h->stream)); cudaFree(d);
+  KL(KC_EW, h->stream, k_ranset<<<(h->n_chains + 127) / 128, 128, 0, h->stream>>>(h->d_rng, d, h->n_chains)); CK(cudaStreamSynchronize(h->stream)); cudaFree(d);
   API_END(h)
 }
 int alf_b200_get_rng_state(alf_b200_handle* h, uint64_t* s) { API_BEGIN(h) NEED_FINAL(h) CK(cudaStreamSynchronize(h->stream)); CK(cudaMemcpy(s, h->d_rng, sizeof(uint64_t) * 4 * h->n_chains, cudaMemcpyDeviceToHost)); API_END(h) }
 int alf_b200_set_rng_state(alf_b200_handle* h, const uint64_t* s) { API_BEGIN(h) NEED_FINAL(h) CK(cudaStreamSynchronize(h->stream)); CK(cudaMemcpy(h->d_rng, s, sizeof(uint64_t) * 4 * h->n_chains, cudaMemcpyHostToDevice)); API_END(h) }
 int alf_b200_fields_set(alf_b200_handle* h) {
   API_BEGIN(h) NEED_FINAL(h)
-  k_fields_set<<<(h->n_chains + 63) / 64, 64, 0, h->stream>>>(h->d_fields, h->d_rng, h->n_chains, (long)h->ltrot * h->n_opv); CKL();
+  KL(KC_EW, h->stream, k_fields_set<<<(h->n_chains + 63) / 64, 64, 0, h->stream>>>(h->d_fields, h->d_rng, h->n_chains, (long)h->ltrot * h->n_opv));
   API_END(h)
 }
 int alf_b200_set_fields(alf_b200_handle* h, const double* f) {
@@ -706,10 +711,24 @@ int alf_b200_sweep(alf_b200_handle* h, int n_sweeps, int ltau) {
 int alf_b200_get_control(alf_b200_handle* h, double* out);
 int alf_b200_get_obs(alf_b200_handle* h, double* out);
 int alf_b200_sweep_host(alf_b200_handle* h, int n_sweeps, int ltau, const double* fields_in, double* fields_out, double* obs_out, double* control_out) {
+  {
+  API_BEGIN(h) NEED_FINAL(h)
+  // fields cross PCIe as one int8 per (chain, nt, n) through a pinned staging buffer (nsigma%f of discrete fields holds +-1, +-2 only)
+  const size_t n = (size_t)h->n_chains * h->ltrot * h->n_opv;
+  if (!h->pin_fields) CK(cudaHostAlloc((void**)&h->pin_fields, n ? n : 1, cudaHostAllocDefault));
+  if (fields_in) {
+    for (size_t i = 0; i < n; ++i) { long s = std::lround(fields_in[2 * i]); int t = h->types[i % h->n_opv];
+      if (s == 0 || std::labs(s) > t) { h->err = "sweep_host: field value outside the discrete range of its operator type"; return ALF_ERROR_FIELDS; } h->pin_fields[i] = (int8_t)s; }
+    CK(cudaMemcpyAsync(h->d_fields, h->pin_fields, n, cudaMemcpyHostToDevice, h->stream));
+  }
+  for (int s = 0; s < n_sweeps; ++s) h->eng->sweep(ltau);
+  if (fields_out) {
+    CK(cudaMemcpyAsync(h->pin_fields, h->d_fields, n, cudaMemcpyDeviceToHost, h->stream)); CK(cudaStreamSynchronize(h->stream));
+    for (size_t i = 0; i < n; ++i) { fields_out[2 * i] = (double)h->pin_fields[i]; fields_out[2 * i + 1] = 0.0; }
+  } else h->eng->sync();
+  API_END_NORET(h)
+  }
   int rc;
-  if (fields_in && (rc = alf_b200_set_fields(h, fields_in)) != ALF_OK) return rc;
-  if ((rc = alf_b200_sweep(h, n_sweeps, ltau)) != ALF_OK) return rc;
-  if (fields_out && (rc = alf_b200_get_fields(h, fields_out)) != ALF_OK) return rc;
   if (obs_out && (rc = alf_b200_get_obs(h, obs_out)) != ALF_OK) return rc;
   if (control_out && (rc = alf_b200_get_control(h, control_out)) != ALF_OK) return rc;
   return ALF_OK;
@@ -752,7 +771,9 @@ int alf_b200_get_control(alf_b200_handle* h, double* out) {
 int alf_b200_accept_log(alf_b200_handle* h, int enable) {
   API_BEGIN(h) NEED_FINAL(h)
   h->acclog_on = enable != 0; h->acclog_pos = 0;
-  if (enable && !h->d_acclog) { h->acclog_per_chain = 2L * h->ltrot * h->n_opv; CK(cudaMalloc(&h->d_acclog, (size_t)h->acclog_per_chain * h->n_chains)); }
+  const long want = 2L * h->ltrot * h->n_opv * (enable > 0 ? enable : 1);    // enable = number of sweeps to record
+  if (enable && h->d_acclog && want > h->acclog_per_chain) { CK(cudaFree(h->d_acclog)); h->d_acclog = nullptr; }
+  if (enable && !h->d_acclog) { h->acclog_per_chain = want; CK(cudaMalloc(&h->d_acclog, (size_t)h->acclog_per_chain * h->n_chains)); }
   if (h->d_acclog) CK(cudaMemset(h->d_acclog, 255, (size_t)h->acclog_per_chain * h->n_chains));
   API_END(h)
 }
@@ -780,6 +801,13 @@ int alf_b200_obs_reset(alf_b200_handle* h) { API_BEGIN(h) NEED_FINAL(h) CK(cudaM
 int alf_b200_obs_device_ptr(alf_b200_handle* h, double** p, long* n) { if (!h || !h->finalized) return ALF_ERROR_GENERIC; *p = h->d_obs; *n = h->obs_size; return ALF_OK; }
 int alf_b200_get_obs(alf_b200_handle* h, double* out) { API_BEGIN(h) NEED_FINAL(h) CK(cudaStreamSynchronize(h->stream)); CK(cudaMemcpy(out, h->d_obs, sizeof(double) * h->obs_size, cudaMemcpyDeviceToHost)); API_END(h) }
 
+int alf_b200_get_stream(alf_b200_handle* h, void** stream) { if (!h || !stream) return ALF_ERROR_GENERIC; *stream = (void*)h->stream; return ALF_OK; }
+int alf_b200_kernel_timing(alf_b200_handle* h, unsigned mask) { API_BEGIN(h) CK(cudaStreamSynchronize(h->stream)); h->prof.reset(); h->prof.timing_mask = mask; API_END(h) }
+int alf_b200_get_kernel_stats(alf_b200_handle* h, double* ms, long* launches) {
+  API_BEGIN(h) CK(cudaStreamSynchronize(h->stream)); h->prof.collect();
+  for (int c = 0; c < KC_COUNT; ++c) { if (ms) ms[c] = h->prof.ms[c]; if (launches) launches[c] = h->prof.launches[c]; }
+  API_END(h)
+}
 int alf_b200_hop_apply(alf_b200_handle* h, int which, int nf, double* A) { API_BEGIN(h) NEED_FINAL(h) h->eng->hop_apply(which, nf, reinterpret_cast<cd*>(A)); API_END(h) }
 
 // ---- kernel-level test entry points and FP64 peak microbenchmark

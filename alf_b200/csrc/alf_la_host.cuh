@@ -12,6 +12,34 @@ struct CudaError : std::runtime_error { using std::runtime_error::runtime_error;
   throw CudaError(std::string(#call) + " -> " + cudaGetErrorString(e_) + " at " + __FILE__ + ":" + std::to_string(__LINE__)); } } while (0)
 #define CKL() CK(cudaGetLastError())
 
+// ---- launch accounting: every kernel launch goes through a KScope so that bench.py can report gpu_launches and the
+// per-kernel device time (CUDA events on the handle's stream) its roofline entry needs.
+enum { KC_UPDATE = 0, KC_OPS, KC_QRP, KC_FORMQ, KC_GEMM, KC_TRSM, KC_EW, KC_OBS, KC_COUNT };
+struct Prof {
+  unsigned timing_mask = 0;                       // bit c set: record CUDA events around launches of category c
+  long launches[KC_COUNT] = {0}; double ms[KC_COUNT] = {0};
+  struct Rec { int cat; cudaEvent_t a, b; };
+  std::vector<Rec> recs; std::vector<cudaEvent_t> pool;
+  cudaEvent_t get() { if (!pool.empty()) { cudaEvent_t e = pool.back(); pool.pop_back(); return e; } cudaEvent_t e; cudaEventCreate(&e); return e; }
+  void collect() {                                // caller has synchronised the stream
+    for (auto& r : recs) { float t = 0.f; if (cudaEventElapsedTime(&t, r.a, r.b) == cudaSuccess) ms[r.cat] += t; pool.push_back(r.a); pool.push_back(r.b); }
+    recs.clear();
+  }
+  void reset() { collect(); for (int c = 0; c < KC_COUNT; ++c) { launches[c] = 0; ms[c] = 0.0; } }
+  ~Prof() { collect(); for (auto e : pool) cudaEventDestroy(e); }
+};
+static thread_local Prof* t_prof = nullptr;
+struct KScope {
+  Prof* p; int cat; cudaStream_t st; cudaEvent_t a, b; bool on = false;
+  KScope(int c, cudaStream_t s) : p(t_prof), cat(c), st(s) {
+    if (!p) return;
+    p->launches[c]++;
+    if (p->timing_mask & (1u << c)) { on = true; a = p->get(); b = p->get(); cudaEventRecord(a, st); }
+  }
+  ~KScope() { if (on) { cudaEventRecord(b, st); p->recs.push_back({cat, a, b}); } }
+};
+#define KL(CAT, ST, ...) do { KScope ks_(CAT, ST); __VA_ARGS__; CKL(); } while (0)
+
 static inline int ew_blocks(long n) { long b = (n + 255) / 256; return (int)(b > 2048 ? 2048 : (b < 1 ? 1 : b)); }
 
 template <typename T>
@@ -43,8 +71,7 @@ struct LaWork {
 template <typename T, int TA, int TB, int MASK>
 static void gemm(cudaStream_t st, int M, int N, int K, const T* A, int lda, long sA, const T* B, int ldb, long sB, T* C, int ldc, long sC, int batch) {
   dim3 grid(((M + GEMM_BM - 1) / GEMM_BM) * ((N + GEMM_BN - 1) / GEMM_BN), batch);
-  k_gemm<T, TA, TB, MASK><<<grid, 256, 0, st>>>(M, N, K, A, lda, sA, B, ldb, sB, C, ldc, sC);
-  CKL();
+  KL(KC_GEMM, st, k_gemm<T, TA, TB, MASK><<<grid, 256, 0, st>>>(M, N, K, A, lda, sA, B, ldb, sB, C, ldc, sC));
 }
 
 static const size_t kSmemStageLimit = 200 * 1024;
@@ -59,9 +86,10 @@ static void launch_qrp(cudaStream_t st, T* A, int m, int n, int ld, long sA, T* 
     CK(cudaFuncSetAttribute(k_qrp<T, MAXR, PIVOT, STG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
     k_qrp<T, MAXR, PIVOT, STG><<<batch, 512, smem, st>>>(A, m, n, ld, sA, tau, sTau, jpvt, sP, D, sD, out); } while (0)
 #define QRP_DISPATCH(MAXR) do { if (do_stage) QRP_LAUNCH(MAXR, 1); else QRP_LAUNCH(MAXR, 0); } while (0)
+  { KScope ks_(KC_QRP, st);
   if (m <= 64) QRP_DISPATCH(2); else if (m <= 128) QRP_DISPATCH(4); else if (m <= 288) QRP_DISPATCH(9); else if (m <= 576) QRP_DISPATCH(18);
   else throw CudaError("k_qrp: matrices with more than 576 rows are not supported in this build");
-  CKL();
+  CKL(); }
 #undef QRP_DISPATCH
 #undef QRP_LAUNCH
 }
@@ -76,9 +104,10 @@ static void launch_formq(cudaStream_t st, T* A, int m, int n, int ld, long sA, c
     CK(cudaFuncSetAttribute(k_formq<T, MAXR, STG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
     k_formq<T, MAXR, STG><<<batch, 512, smem, st>>>(A, m, n, ld, sA, tau, sTau, colscale); } while (0)
 #define FQ_DISPATCH(MAXR) do { if (do_stage) FQ_LAUNCH(MAXR, 1); else FQ_LAUNCH(MAXR, 0); } while (0)
+  { KScope ks_(KC_FORMQ, st);
   if (m <= 64) FQ_DISPATCH(2); else if (m <= 128) FQ_DISPATCH(4); else if (m <= 288) FQ_DISPATCH(9); else if (m <= 576) FQ_DISPATCH(18);
   else throw CudaError("k_formq: matrices with more than 576 rows are not supported in this build");
-  CKL();
+  CKL(); }
 #undef FQ_DISPATCH
 #undef FQ_LAUNCH
 }
@@ -87,6 +116,7 @@ template <typename T>
 static void launch_trsm(cudaStream_t st, const T* R, int ldr, long sR, T* B, int ldb, long sB, int n, int nrhs, const double* dinv, long sD, int batch) {
   dim3 grid((nrhs + TRSM_COLS - 1) / TRSM_COLS, batch);
   size_t smem = sizeof(T) * n;
+  KScope ks_(KC_TRSM, st);
   if (n <= 64) k_trsm_lun<T, 2><<<grid, TRSM_WARPS * 32, smem, st>>>(R, ldr, sR, B, ldb, sB, n, nrhs, dinv, sD);
   else if (n <= 128) k_trsm_lun<T, 4><<<grid, TRSM_WARPS * 32, smem, st>>>(R, ldr, sR, B, ldb, sB, n, nrhs, dinv, sD);
   else if (n <= 288) k_trsm_lun<T, 9><<<grid, TRSM_WARPS * 32, smem, st>>>(R, ldr, sR, B, ldb, sB, n, nrhs, dinv, sD);
@@ -109,15 +139,15 @@ template <typename T>
 static void la_decompose(LaWork<T>& w, UdvDev<T>& s, char side) {
   const int N = w.N, NM = w.NM; const long n2 = w.n2(); cudaStream_t st = w.st;
   const bool left = (side == 'l' || side == 'L');
-  k_colscale<T><<<dim3(ew_blocks(n2), NM), 256, 0, st>>>(s.U, N, n2, N, N, s.D, N); CKL();
+  KL(KC_EW, st, k_colscale<T><<<dim3(ew_blocks(n2), NM), 256, 0, st>>>(s.U, N, n2, N, N, s.D, N));
   launch_qrp<T, 1>(st, s.U, N, N, N, n2, w.tau, N, w.jpvt, N, s.D, N, w.qrout, NM);
-  k_decomp_phase<<<(NM + 127) / 128, 128, 0, st>>>(w.qrout, left ? 1 : 0, w.sc_phase, w.sc_beta, s.det, NM); CKL();
-  k_row0scale<T><<<dim3((N + 255) / 256, NM), 256, 0, st>>>(s.U, N, n2, N, w.sc_beta); CKL();
+  KL(KC_EW, st, k_decomp_phase<<<(NM + 127) / 128, 128, 0, st>>>(w.qrout, left ? 1 : 0, w.sc_phase, w.sc_beta, s.det, NM));
+  KL(KC_EW, st, k_row0scale<T><<<dim3((N + 255) / 256, NM), 256, 0, st>>>(s.U, N, n2, N, w.sc_beta));
   if (!left) {
-    k_permcopy<T, 1><<<dim3(ew_blocks(n2), NM), 256, 0, st>>>(w.W[0], N, n2, s.V, N, n2, N, N, w.jpvt, N); CKL();
+    KL(KC_EW, st, k_permcopy<T, 1><<<dim3(ew_blocks(n2), NM), 256, 0, st>>>(w.W[0], N, n2, s.V, N, n2, N, N, w.jpvt, N));
     gemm<T, 0, 0, 1>(st, N, N, N, s.U, N, n2, w.W[0], N, n2, s.V, N, n2, NM);          // V = R * (P^T V)
   } else {
-    k_permcopy<T, 2><<<dim3(ew_blocks(n2), NM), 256, 0, st>>>(w.W[0], N, n2, s.V, N, n2, N, N, w.jpvt, N); CKL();
+    KL(KC_EW, st, k_permcopy<T, 2><<<dim3(ew_blocks(n2), NM), 256, 0, st>>>(w.W[0], N, n2, s.V, N, n2, N, N, w.jpvt, N));
     gemm<T, 0, 1, 2>(st, N, N, N, w.W[0], N, n2, s.U, N, n2, s.V, N, n2, NM);          // V = (V P) * R^H
   }
   launch_formq<T>(st, s.U, N, N, N, n2, w.tau, N, w.sc_phase, NM);
@@ -139,25 +169,25 @@ static void la_cgr(LaWork<T>& w, int nvar, int stab, const UdvDev<T>& R, const U
   dim3 eg(ew_blocks(n2), NM);
   gemm<T, 1, 0, 0>(st, N, N, N, R.U, N, n2, L.U, N, n2, w.W[0], N, n2, NM);            // RHS = U_R^H U_L
   gemm<T, 0, 0, 0>(st, N, N, N, R.V, N, n2, L.V, N, n2, w.W[1], N, n2, NM);            // TPUP = V_R V_L
-  if (stab == 3) { if (nvar == 1) k_cgr_tpup<T, 1, 0><<<eg, 256, 0, st>>>(w.W[2], w.W[1], w.W[0], n2, N, R.D, L.D, N);
-                   else k_cgr_tpup<T, 1, 1><<<eg, 256, 0, st>>>(w.W[2], w.W[1], w.W[0], n2, N, R.D, L.D, N); }
-  else { if (nvar == 1) k_cgr_tpup<T, 0, 0><<<eg, 256, 0, st>>>(w.W[2], w.W[1], w.W[0], n2, N, R.D, L.D, N);
-         else k_cgr_tpup<T, 0, 1><<<eg, 256, 0, st>>>(w.W[2], w.W[1], w.W[0], n2, N, R.D, L.D, N); }
+  if (stab == 3) { if (nvar == 1) KL(KC_EW, st, k_cgr_tpup<T, 1, 0><<<eg, 256, 0, st>>>(w.W[2], w.W[1], w.W[0], n2, N, R.D, L.D, N));
+                   else KL(KC_EW, st, k_cgr_tpup<T, 1, 1><<<eg, 256, 0, st>>>(w.W[2], w.W[1], w.W[0], n2, N, R.D, L.D, N)); }
+  else { if (nvar == 1) KL(KC_EW, st, k_cgr_tpup<T, 0, 0><<<eg, 256, 0, st>>>(w.W[2], w.W[1], w.W[0], n2, N, R.D, L.D, N));
+         else KL(KC_EW, st, k_cgr_tpup<T, 0, 1><<<eg, 256, 0, st>>>(w.W[2], w.W[1], w.W[0], n2, N, R.D, L.D, N)); }
   CKL();
   launch_qrp<T, 1>(st, w.W[2], N, N, N, n2, w.tau, N, w.jpvt, N, w.Dq, N, w.qrout, NM);
-  k_cgr_z<<<(NM + 127) / 128, 128, 0, st>>>(w.qrout, R.det, L.det, nvar, z, NM); CKL();
+  KL(KC_EW, st, k_cgr_z<<<(NM + 127) / 128, 128, 0, st>>>(w.qrout, R.det, L.det, nvar, z, NM));
   // explicit Q in W[1]
-  k_permcopy<T, 0><<<eg, 256, 0, st>>>(w.W[1], N, n2, w.W[2], N, n2, N, N, nullptr, 0); CKL();
+  KL(KC_EW, st, k_permcopy<T, 0><<<eg, 256, 0, st>>>(w.W[1], N, n2, w.W[2], N, n2, N, N, nullptr, 0));
   launch_formq<T>(st, w.W[1], N, N, N, n2, w.tau, N, nullptr, NM);
   // X0 = U_R^H (nvar 1) or U_L^H (nvar 2), with the D_+^-1 row scaling of the STAB3 branch
   const UdvDev<T>& A0 = (nvar == 1) ? R : L;
   const UdvDev<T>& A1 = (nvar == 1) ? L : R;
-  k_permcopy<T, 4><<<eg, 256, 0, st>>>(w.W[0], N, n2, A0.U, N, n2, N, N, nullptr, 0); CKL();
-  if (stab == 3) { k_sep_scale<T, 1><<<eg, 256, 0, st>>>(w.W[0], n2, N, A0.D, N); CKL(); }
+  KL(KC_EW, st, k_permcopy<T, 4><<<eg, 256, 0, st>>>(w.W[0], N, n2, A0.U, N, n2, N, N, nullptr, 0));
+  if (stab == 3) { KL(KC_EW, st, k_sep_scale<T, 1><<<eg, 256, 0, st>>>(w.W[0], n2, N, A0.D, N)); }
   gemm<T, 1, 0, 0>(st, N, N, N, w.W[1], N, n2, w.W[0], N, n2, w.W[3], N, n2, NM);      // X = Q^H X0
   launch_trsm<T>(st, w.W[2], N, n2, w.W[3], N, n2, N, N, w.Dq, N, NM);                 // X = R^-1 D^-1 X
-  k_permcopy<T, 3><<<eg, 256, 0, st>>>(w.W[0], N, n2, w.W[3], N, n2, N, N, w.jpvt, N); CKL();   // X2 = P X
-  if (stab == 3) { k_sep_scale<T, 1><<<eg, 256, 0, st>>>(w.W[0], n2, N, A1.D, N); CKL(); }
+  KL(KC_EW, st, k_permcopy<T, 3><<<eg, 256, 0, st>>>(w.W[0], N, n2, w.W[3], N, n2, N, N, w.jpvt, N));   // X2 = P X
+  if (stab == 3) { KL(KC_EW, st, k_sep_scale<T, 1><<<eg, 256, 0, st>>>(w.W[0], n2, N, A1.D, N)); }
   if (nvar == 1) gemm<T, 0, 0, 0>(st, N, N, N, L.U, N, n2, w.W[0], N, n2, Gout, N, n2, NM);        // G = U_L X2
   else gemm<T, 1, 1, 0>(st, N, N, N, w.W[0], N, n2, R.U, N, n2, Gout, N, n2, NM);                 // G = X2^H U_R^H
 }

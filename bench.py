@@ -1,0 +1,284 @@
+#!/usr/bin/env python
+"""bench.py -- sweeps/sec of the auxiliary-field QMC sweep on the BASELINE.json headline workload.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path (one process per GPU under torchrun)
+    python bench.py --impl reference --gpus N --steps K ...   # CPU arm: the oracle (restatement of ALF, not ALF.out)
+
+A "step" is ONE SWEEP (up + down pass over all L_trot slices, main.F90:714-887, plus TAU_M when --ltau 1) of every
+chain resident on the GPU.  value = chain-sweeps per second summed over all ranks, timed with CUDA events on the
+handle's stream, max over ranks.  e2e = the same through alf_b200_sweep_host (host buffers in/out each step).
+The oracle is used here only as the CPU baseline (cpu_baseline / --impl reference), never on the measured GPU path.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "sweeps/sec on 16x16 Hubbard beta=10"
+UNIT = "sweeps/s"
+WORKLOADS = {
+    # name: (L1, L2, beta, dtau, U, nwrap, default chains per GPU)
+    "hubbard_16x16_beta10": (16, 16, 10.0, 0.1, 4.0, 10, 148),      # BASELINE.json configs[2] = the metric's configuration
+    "hubbard_8x8_beta10": (8, 8, 10.0, 0.1, 4.0, 10, 296),          # configs[1]
+    "hubbard_4x4_beta5": (4, 4, 5.0, 0.1, 4.0, 10, 296),            # configs[0]
+}
+
+
+def make_model(name):
+    from alf_b200.model import hubbard_square
+    L1, L2, beta, dtau, U, nwrap, chains = WORKLOADS[name]
+    return hubbard_square(L1, L2, beta=beta, dtau=dtau, U=U), nwrap, chains
+
+
+def chain_seed(global_chain):
+    """Deterministic stand-in for successive lines of the `seeds` file (Prog/Set_random_mod.F90:79-84)."""
+    x = (global_chain + 1) * 2654435761 % 2147483647
+    return int(x) or 1
+
+
+# ----------------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.path = index, None, None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv"); os.close(fd)
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        try:
+            for ln in open(self.path):
+                p = [x.strip() for x in ln.split(",")]
+                if len(p) < 9:
+                    continue
+                try:
+                    sm.append(float(p[1])); mx.append(float(p[2]))
+                except ValueError:
+                    continue
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            sm.sort()
+            out.update(sm_mhz=sm[len(sm) // 2], sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+# ----------------------------------------------------------------------------------------------- CPU arm
+def cpu_sample(workload, ltau, cores, seconds_target, steps, warmup):
+    """Times the oracle (one independent chain per host thread, OPENBLAS_NUM_THREADS=1 as Documentation/running.tex:352
+    advises) on a bounded sample: `seg` consecutive stabilisation intervals of the sweep per step (a sweep has 2*NSTM
+    (+NSTM with TAU_M) of them, equal in cost).  Returns per-step seconds and the sample description."""
+    os.environ.setdefault("OPENBLAS_NUM_THREADS", "1")
+    from oracle.oracle import Oracle
+    model, nwrap, _ = make_model(workload)
+    orcs = []
+    for c in range(cores):
+        o = Oracle(model, nwrap=nwrap); o.ranset(chain_seed(c)); o.fields_set(); orcs.append(o)
+
+    def par(fn):
+        th = [threading.Thread(target=fn, args=(o,)) for o in orcs]
+        [t.start() for t in th]; [t.join() for t in th]
+    par(lambda o: o.init())
+    nseg = orcs[0].n_segments(ltau)
+    pos = [0]
+
+    def run_segments(k):
+        lo = pos[0]
+        def work(o):
+            for i in range(lo, lo + k):
+                o.sweep_segment(i % nseg, ltau)
+        par(work); pos[0] = lo + k
+    t0 = time.perf_counter(); run_segments(1); t_seg = time.perf_counter() - t0        # calibration (also a warm-up)
+    seg = max(1, min(nseg, int(seconds_target / max(t_seg, 1e-6) / max(1, steps + warmup))))
+    for _ in range(warmup):
+        run_segments(seg)
+    times = []
+    for _ in range(steps):
+        t0 = time.perf_counter(); run_segments(seg); times.append(time.perf_counter() - t0)
+    return times, seg, nseg
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    cores = args.cpu_cores or (os.cpu_count() or 1)
+    times, seg, nseg = cpu_sample(args.workload, args.ltau, cores, 150.0, args.steps, args.warmup)
+    tot = sum(times)
+    value = cores * len(times) * (seg / nseg) / tot
+    sample = f"{seg} of {nseg} stabilisation intervals of one sweep per step, {cores} independent chains (1 per host thread)"
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * tot / len(times), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "c128 (complex f64, as ALF)",
+            "data": "synthetic", "config": {"workload": args.workload, "ltau": args.ltau, "chains": cores},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+                             "note": "oracle-CPU: C++ restatement of ALF calling the same LAPACK/BLAS routines (scipy OpenBLAS); gfortran is absent so ALF.out cannot be built"},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ----------------------------------------------------------------------------------------------- GPU arm
+def run_b200(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from alf_b200 import build as _b
+    if rank == 0:
+        _b.build()
+    if world > 1:
+        dist.barrier()
+    from alf_b200.api import AlfB200, fp64_peak
+    from alf_b200.parallel import reduce_bins
+
+    model, nwrap, chains_default = make_model(args.workload)
+    C = args.chains or chains_default
+    g = AlfB200(model, n_chains=C, nwrap=nwrap, device=local)
+    g.set_seeds([chain_seed(rank * C + c) for c in range(C)])
+    g.fields_set(); g.init_sweep()
+    stream = torch.cuda.ExternalStream(g.stream_ptr(), device=torch.device("cuda", local))
+    N, L, M, F = model.Ndim, model.Ltrot, model.n_opv, model.N_FL
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX); return float(t.item())
+
+    for _ in range(args.warmup):
+        g.sweep(1, args.ltau)
+    # ---- timed region 1: device-resident sweeps
+    g.kernel_timing(1 << 0)                      # CUDA events around the dominant kernel (k_wrapgr) only
+    c0 = g.control()
+    clocks = ClockSampler(local); clocks.start()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        g.sweep(1, args.ltau)
+    e1.record(stream)
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1))
+    clk = clocks.stop()
+    stats = g.kernel_stats(); c1 = g.control()
+    g.kernel_timing(0)
+    value = world * C * args.steps / (ms * 1e-3)
+
+    # ---- timed region 2: end to end through the C-ABI with host buffers (fields up, sweep, fields + observables + control down)
+    f_in = g.get_fields(); f_out = np.empty_like(f_in); obs = np.zeros(max(16, g.obs_size())); ctl = np.zeros(16)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        g.sweep_host(1, args.ltau, f_in, f_out, obs, ctl)
+        red = reduce_bins(g, obs, world)          # NCCL reduction of the bin accumulators (replaces MPI_REDUCE, observables_mod.F90:425-438)
+        f_in, f_out = f_out, f_in
+    barrier()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    e2e_value = world * C * args.steps / e2e_s
+    h2d = C * L * M                                # int8 per field through the pinned staging buffer
+    d2h = C * L * M + 8 * (len(obs) + 16)
+
+    # ---- roofline of the dominant kernel and CPU baseline (rank 0, N = 1 only for the latter)
+    upd_ms, upd_n = stats["update"]
+    acc = c1["ACC_up"] - c0["ACC_up"]
+    w = 16 if g.is_complex else 8
+    line = None
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0)); peak_src = "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+        dfma, dmma = fp64_peak(local)
+        alg_bytes_per_launch = (acc * F * 2.0 * w * N * N) / max(upd_n, 1)        # 2*w*N^2 per accepted rank-1 update and flavor
+        alg_flops_per_launch = (acc * F * 2.0 * (4 if g.is_complex else 1) * N * N) / max(upd_n, 1)
+        avg_s = upd_ms * 1e-3 / max(upd_n, 1)
+        achieved = alg_bytes_per_launch / avg_s / 1e9 if avg_s > 0 else 0.0
+        roof = {"kernel": "k_wrapgr (delayed-update slice kernel)", "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                "traffic": None, "peak_source": peak_src, "launches": upd_n, "avg_launch_ms": 1e3 * avg_s, "share_of_step": upd_ms / ms if ms > 0 else None,
+                "algorithmic_bytes_per_launch": alg_bytes_per_launch,
+                "note": "algorithmic bytes = the reference's rank-1 ZGERU traffic (SURVEY 8d); the kernel keeps the updates delayed in shared memory, so its real DRAM traffic is far lower and frac may exceed 1",
+                "fp64": {"achieved_tflops": alg_flops_per_launch / avg_s / 1e12 if avg_s > 0 else 0.0, "peak_tflops_dfma_measured": dfma, "peak_tflops_dmma_measured": dmma}}
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            cores = args.cpu_cores or (os.cpu_count() or 1)
+            times, seg, nseg = cpu_sample(args.workload, args.ltau, cores, 20.0, 1, 0)
+            cpu = {"value": cores * (seg / nseg) / times[0], "unit": UNIT, "cores": cores, "kind": "port",
+                   "sample": f"{seg} of {nseg} stabilisation intervals of one sweep, {cores} independent chains (1 per host thread), oracle-CPU (restatement of ALF, not ALF.out)"}
+        nl = sum(v[1] for v in stats.values())
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "c128" if g.is_complex else "f64", "data": "synthetic",
+                "config": {"workload": args.workload, "N_dim": N, "L_trot": L, "N_FL": F, "nwrap": nwrap, "ltau": args.ltau, "chains_per_gpu": C, "chains": world * C,
+                           "parallelism": f"chains sharded over {world} GPU(s), no data-path collective", "l2": "working set (G + UDV storage of all chains) exceeds L2"},
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+                "gpu_launches": nl, "kernel_launches": {k: v[1] for k, v in stats.items()},
+                "acceptance": acc / max(c1["NC_up"] - c0["NC_up"], 1), "precision_green_max": c1["XMAXG"],
+                "clocks": clk, "roofline": roof, "cpu_baseline": cpu}
+    g.close()
+    if world > 1:
+        dist.barrier(); dist.destroy_process_group()
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="hubbard_16x16_beta10", choices=sorted(WORKLOADS))
+    ap.add_argument("--chains", type=int, default=0, help="chains per GPU (default: per workload)")
+    ap.add_argument("--ltau", type=int, default=0)
+    ap.add_argument("--cpu-cores", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_b200(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

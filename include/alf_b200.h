@@ -89,7 +89,7 @@ int alf_b200_get_udv(alf_b200_handle* h, int which /*0 udvl,1 udvr,2 udvst*/, in
  * [0] XMEANG sum [1] XMAXG [2] NCG [3] XMAXP [4] XMEAN_tau sum [5] XMAX_tau [6] NCG_tau [7] NC_up [8] ACC_up
  * [9] NC_eff_up [10] ACC_eff_up [11] NaN flag [12] unstable flag (XMAX > 10) */
 int alf_b200_get_control(alf_b200_handle* h, double* out /* 16 */);
-int alf_b200_accept_log(alf_b200_handle* h, int enable);     /* record accept/reject per field visit (check 2) */
+int alf_b200_accept_log(alf_b200_handle* h, int n_sweeps);   /* record accept/reject per field visit for the next n_sweeps sweeps (check 2); 0 = off */
 int alf_b200_get_accept_log(alf_b200_handle* h, uint8_t* out, long cap, long* n_per_chain);
 int alf_b200_taum_capture(alf_b200_handle* h, int every);    /* keep GT0,G0T,G00,GTT handed to ObserT every k-th slice */
 int alf_b200_get_taum(alf_b200_handle* h, int chain, double* out, long cap_complex, long* n_complex);
@@ -113,6 +113,13 @@ int alf_b200_test_gemm(int device, int is_complex, int ta, int tb, int m, int n,
                        const double* B, double* C);
 int alf_b200_hop_apply(alf_b200_handle* h, int which /* 0 mmthr,1 mmthr_m1,2 mmthl,3 mmthl_m1,4 mmthlc,5 Symm */,
                        int nf, double* A /* complex N*N, in/out */);
+/* ---- measurement support (bench.py): the handle's CUDA stream (for CUDA-event timing on the launching stream), and per-kernel
+ * launch counts / device time.  Categories: 0 update (k_wrapgr) 1 op-list wrap (k_apply_ops) 2 pivoted QR 3 form-Q 4 GEMM 5 TRSM
+ * 6 element-wise 7 observables.  mask bit c = 1 records CUDA events around every launch of category c. */
+#define ALF_B200_NKCAT 8
+int alf_b200_get_stream(alf_b200_handle* h, void** stream);
+int alf_b200_kernel_timing(alf_b200_handle* h, unsigned mask);        /* resets the statistics */
+int alf_b200_get_kernel_stats(alf_b200_handle* h, double* ms /* 8 */, long* launches /* 8 */);
 int alf_b200_fp64_peak(int device, double* dfma_tflops, double* dmma_tflops);   /* roofline denominator microbenchmark */
 
 #ifdef __cplusplus

@@ -762,35 +762,42 @@ struct Oracle {
     Phase = Z;
   }
 
-  // ---- Prog/main.F90:714-887 : one sequential sweep
-  void sweep(int ltau) {
-    for (int nf = 0; nf < n_fl; ++nf) udvr[nf].reset('r');
-    int NST = 1;
-    for (int NTAU = 0; NTAU <= ltrot - 1; ++NTAU) {
-      int NTAU1 = NTAU + 1;
-      wrapgrup(NTAU);
-      if (NTAU1 == stab_nt[NST]) { wrapur(stab_nt[NST - 1], NTAU1, udvr); stabilise(NTAU1, NST, true); NST++; }
-      obser_hook(NTAU1);
-    }
-    for (int nf = 0; nf < n_fl; ++nf) udvl[nf].reset('l');
-    NST = nstm - 1;
-    for (int NTAU = ltrot; NTAU >= 1; --NTAU) {
-      int NTAU1 = NTAU - 1;
-      wrapgrdo(NTAU);
-      obser_hook(NTAU1);
-      if (NST >= 0 && stab_nt[NST] == NTAU1 && NTAU1 != 0) { wrapul(stab_nt[NST + 1], NTAU1, udvl); stabilise(NTAU1, NST, false); NST--; }
-    }
-    wrapul(stab_nt[1], stab_nt[0], udvl);
-    for (int nf = 0; nf < n_fl; ++nf) udvr[nf].reset('r');
-    cd ph = 1; std::vector<cd> Test((size_t)ndim * ndim);
-    for (int nf = 0; nf < n_fl; ++nf) {
-      Test = GR[nf]; cd Z1; cgr(Z1, 1, GR[nf].data(), udvr[nf], udvl[nf], stab3);
-      control_precisionG(GR[nf].data(), Test.data()); op_phase(Z1, nf); ph *= Z1;
-    }
-    cd Z = std::pow(ph, n_sun); double X = std::abs(Z - Phase); if (X > ctl.XMAXP) ctl.XMAXP = X; Phase = Z;
-    for (int nf = 0; nf < n_fl; ++nf) st(nstm, nf).reset('l');
-    if (ltau == 1) tau_m();
+  // ---- Prog/main.F90:714-887 : one sequential sweep, cut into its 2*NSTM (+NSTM with TAU_M) stabilisation intervals so that
+  // the CPU baseline of bench.py can time a bounded sample (sweep() = all segments in order, nothing else).
+  int n_segments(int ltau) const { return 2 * nstm + (ltau == 1 ? nstm : 0); }
+  void sweep_segment(int idx, int ltau) {
+    if (idx < nstm) {                                   // up sweep, main.F90:727-774
+      if (idx == 0) for (int nf = 0; nf < n_fl; ++nf) udvr[nf].reset('r');
+      const int NST = idx + 1;
+      for (int NTAU = stab_nt[NST - 1]; NTAU <= stab_nt[NST] - 1; ++NTAU) {
+        int NTAU1 = NTAU + 1;
+        wrapgrup(NTAU);
+        if (NTAU1 == stab_nt[NST]) { wrapur(stab_nt[NST - 1], NTAU1, udvr); stabilise(NTAU1, NST, true); }
+        obser_hook(NTAU1);
+      }
+    } else if (idx < 2 * nstm) {                        // down sweep, main.F90:786-834, and the slice-0 recompute :836-872
+      const int d = idx - nstm, hi = nstm - d;
+      if (d == 0) for (int nf = 0; nf < n_fl; ++nf) udvl[nf].reset('l');
+      for (int NTAU = stab_nt[hi]; NTAU >= stab_nt[hi - 1] + 1; --NTAU) {
+        int NTAU1 = NTAU - 1;
+        wrapgrdo(NTAU);
+        obser_hook(NTAU1);
+        if (hi - 1 >= 1 && stab_nt[hi - 1] == NTAU1) { wrapul(stab_nt[hi], NTAU1, udvl); stabilise(NTAU1, hi - 1, false); }
+      }
+      if (hi == 1) {
+        wrapul(stab_nt[1], stab_nt[0], udvl);
+        for (int nf = 0; nf < n_fl; ++nf) udvr[nf].reset('r');
+        cd ph = 1; std::vector<cd> Test((size_t)ndim * ndim);
+        for (int nf = 0; nf < n_fl; ++nf) {
+          Test = GR[nf]; cd Z1; cgr(Z1, 1, GR[nf].data(), udvr[nf], udvl[nf], stab3);
+          control_precisionG(GR[nf].data(), Test.data()); op_phase(Z1, nf); ph *= Z1;
+        }
+        cd Z = std::pow(ph, n_sun); double X = std::abs(Z - Phase); if (X > ctl.XMAXP) ctl.XMAXP = X; Phase = Z;
+        for (int nf = 0; nf < n_fl; ++nf) st(nstm, nf).reset('l');
+      }
+    } else if (ltau == 1) tau_m_segment(idx - 2 * nstm);
   }
+  void sweep(int ltau) { for (int i = 0; i < n_segments(ltau); ++i) sweep_segment(i, ltau); }
 
   // ---- Prog/tau_m_mod.F90:215-263
   void propr(std::vector<std::vector<cd>>& A, int nt) {
@@ -812,33 +819,36 @@ struct Oracle {
       taum_buf.insert(taum_buf.end(), tmp.begin(), tmp.end());
     }
   }
-  // ---- Prog/tau_m_mod.F90:56-211
-  void tau_m() {
+  // ---- Prog/tau_m_mod.F90:56-211, one stabilisation interval per call (state kept in tm_*)
+  std::vector<std::vector<cd>> tm_G00, tm_G0T, tm_GT0, tm_GTT; std::vector<UDV> tm_udvr;
+  void tau_m_segment(int t) {
     size_t n2 = (size_t)ndim * ndim;
-    std::vector<std::vector<cd>> G00(n_fl, std::vector<cd>(n2)), G0T = G00, GT0 = G00, GTT = G00;
-    for (int nf = 0; nf < n_fl; ++nf) for (int J = 0; J < ndim; ++J) for (int I = 0; I < ndim; ++I) {
-      cd Z = (I == J) ? 1.0 : 0.0; cd g = GR[nf][I + (size_t)J * ndim];
-      G00[nf][I + (size_t)J * ndim] = g; GT0[nf][I + (size_t)J * ndim] = g; GTT[nf][I + (size_t)J * ndim] = g; G0T[nf][I + (size_t)J * ndim] = -(Z - g);
+    if (t == 0) {
+      tm_G00.assign(n_fl, std::vector<cd>(n2)); tm_G0T = tm_G00; tm_GT0 = tm_G00; tm_GTT = tm_G00;
+      for (int nf = 0; nf < n_fl; ++nf) for (int J = 0; J < ndim; ++J) for (int I = 0; I < ndim; ++I) {
+        cd Z = (I == J) ? 1.0 : 0.0; cd g = GR[nf][I + (size_t)J * ndim];
+        tm_G00[nf][I + (size_t)J * ndim] = g; tm_GT0[nf][I + (size_t)J * ndim] = g; tm_GTT[nf][I + (size_t)J * ndim] = g; tm_G0T[nf][I + (size_t)J * ndim] = -(Z - g);
+      }
+      obsert_hook(0, tm_GT0, tm_G0T, tm_G00, tm_GTT);
+      tm_udvr.assign(n_fl, UDV()); for (int nf = 0; nf < n_fl; ++nf) { tm_udvr[nf].alloc(ndim); tm_udvr[nf].reset('r'); }
     }
-    obsert_hook(0, GT0, G0T, G00, GTT);
-    std::vector<UDV> udvr2(n_fl); for (int nf = 0; nf < n_fl; ++nf) { udvr2[nf].alloc(ndim); udvr2[nf].reset('r'); }
-    int NST = 1; std::vector<cd> HLP4(n2), HLP5(n2), HLP6(n2);
-    for (int NT = 0; NT <= ltrot - 1; ++NT) {
+    const int NST = t + 1; std::vector<cd> HLP4(n2), HLP5(n2), HLP6(n2);
+    for (int NT = stab_nt[NST - 1]; NT <= stab_nt[NST] - 1; ++NT) {
       int NT1 = NT + 1;
-      propr(GT0, NT1); proprm1(G0T, NT1); proprm1(GTT, NT1); propr(GTT, NT1);
-      obsert_hook(NT1, GT0, G0T, G00, GTT);
+      propr(tm_GT0, NT1); proprm1(tm_G0T, NT1); proprm1(tm_GTT, NT1); propr(tm_GTT, NT1);
+      obsert_hook(NT1, tm_GT0, tm_G0T, tm_G00, tm_GTT);
       if (stab_nt[NST] == NT1) {
-        wrapur(stab_nt[NST - 1], NT1, udvr2);
+        wrapur(stab_nt[NST - 1], NT1, tm_udvr);
         for (int nf = 0; nf < n_fl; ++nf) {
-          HLP4 = GTT[nf]; HLP5 = GT0[nf]; HLP6 = G0T[nf];
-          cgr2_2(GT0[nf].data(), G00[nf].data(), GTT[nf].data(), G0T[nf].data(), udvr2[nf], st(NST, nf), ndim, stab3);
-          control_precision_tau(GR[nf].data(), G00[nf].data()); control_precision_tau(HLP4.data(), GTT[nf].data());
-          control_precision_tau(HLP5.data(), GT0[nf].data()); control_precision_tau(HLP6.data(), G0T[nf].data());
+          HLP4 = tm_GTT[nf]; HLP5 = tm_GT0[nf]; HLP6 = tm_G0T[nf];
+          cgr2_2(tm_GT0[nf].data(), tm_G00[nf].data(), tm_GTT[nf].data(), tm_G0T[nf].data(), tm_udvr[nf], st(NST, nf), ndim, stab3);
+          control_precision_tau(GR[nf].data(), tm_G00[nf].data()); control_precision_tau(HLP4.data(), tm_GTT[nf].data());
+          control_precision_tau(HLP5.data(), tm_GT0[nf].data()); control_precision_tau(HLP6.data(), tm_G0T[nf].data());
         }
-        NST++;
       }
     }
   }
+  void tau_m() { for (int t = 0; t < nstm; ++t) tau_m_segment(t); }
 };
 
 }  // namespace
@@ -910,6 +920,8 @@ void orc_set_fields(void* h, const double* f) { Oracle* o = (Oracle*)h; for (siz
 void orc_get_fields(void* h, double* f) { Oracle* o = (Oracle*)h; for (size_t i = 0; i < o->f.size(); ++i) { f[2 * i] = o->f[i].real(); f[2 * i + 1] = o->f[i].imag(); } }
 void orc_init(void* h) { ((Oracle*)h)->init(); }
 void orc_sweep(void* h, int ltau) { ((Oracle*)h)->sweep(ltau); }
+int orc_n_segments(void* h, int ltau) { return ((Oracle*)h)->n_segments(ltau); }
+void orc_sweep_segment(void* h, int idx, int ltau) { ((Oracle*)h)->sweep_segment(idx, ltau); }
 void orc_get_green(void* h, int nf, double* out) { Oracle* o = (Oracle*)h; std::memcpy(out, o->GR[nf - 1].data(), sizeof(cd) * (size_t)o->ndim * o->ndim); }
 void orc_set_green(void* h, int nf, const double* in) { Oracle* o = (Oracle*)h; std::memcpy(o->GR[nf - 1].data(), in, sizeof(cd) * (size_t)o->ndim * o->ndim); }
 void orc_get_phase(void* h, double* ph) { Oracle* o = (Oracle*)h; ph[0] = o->Phase.real(); ph[1] = o->Phase.imag(); }

@@ -108,6 +108,13 @@ class Oracle:
     def sweep(self, ltau: int = 0):
         lib().orc_sweep(self.h, int(ltau))
 
+    def n_segments(self, ltau: int = 0) -> int:
+        return lib().orc_n_segments(self.h, int(ltau))
+
+    def sweep_segment(self, idx: int, ltau: int = 0):
+        """One stabilisation interval of the sweep (sweep() == all segments in order); bench.py's bounded CPU sample."""
+        lib().orc_sweep_segment(self.h, int(idx), int(ltau))
+
     def green(self, nf: int):
         g = np.zeros((self.N, self.N), dtype=np.complex128, order="F")
         lib().orc_get_green(self.h, nf, _d(g))

@@ -142,7 +142,7 @@ def _run_parity(model, seeds, nwrap, n_sweeps=1, stab=0, check_udv=True):
         if check_udv:
             U, D, V = g.get_udv(0, 0, c, 1); Uo, Do, Vo = o.get_udv(0, 0, 1)
             assert relF(D.real, Do.real) < 1e-7        # scales of the stored left propagation
-    g.accept_log(True)
+    g.accept_log(n_sweeps)
     for o in orcs:
         o.log(True)
     for sw in range(n_sweeps):
