@@ -1,0 +1,172 @@
+!  alf_b200_shim.F90 -- ISO_C_BINDING layer between ALF's unchanged Fortran (main.F90, Hamiltonian_main_mod,
+!  Operator_mod, Fields_mod) and libalf_b200.so (include/alf_b200.h).
+!
+!  NOT COMPILED IN THIS REPOSITORY'S CI: the build image has no Fortran compiler (SURVEY.md F2).  It is the binding a
+!  maintainer adds to Prog/ (see INTEGRATION.md); style follows ALF's only existing bind(c) code,
+!  Libraries/Modules/lattices_interface_mod.F90:51-118 (value ints, assumed-size arrays, 1-based indices converted
+!  on the C side).
+module alf_b200_shim
+  use iso_c_binding
+  use runtime_error_mod          ! Terminate_on_error, ERROR_* codes (Libraries/Modules/runtime_error_mod.F90:56-130)
+  use Operator_mod               ! type Operator (Prog/Operator_mod.F90:56-90)
+  use Fields_mod                 ! type Fields   (Prog/Fields_mod.F90:79-99)
+  implicit none
+  private
+  public :: alf_b200_attach, alf_b200_detach, alf_b200_batched_sweep, alf_b200_handle_ptr
+
+  type(c_ptr), save :: alf_b200_handle_ptr = c_null_ptr
+
+  interface
+     integer(c_int) function alf_b200_create(h, ndim, n_fl, n_sun, ltrot, nwrap, n_opv, n_opt, symm, stab, n_chains, device) &
+          bind(c, name="alf_b200_create")
+       import :: c_ptr, c_int
+       type(c_ptr), intent(out) :: h
+       integer(c_int), value :: ndim, n_fl, n_sun, ltrot, nwrap, n_opv, n_opt, symm, stab, n_chains, device
+     end function
+     integer(c_int) function alf_b200_destroy(h) bind(c, name="alf_b200_destroy")
+       import :: c_ptr, c_int
+       type(c_ptr), value :: h
+     end function
+     integer(c_int) function alf_b200_set_op_v(h, n, nf, nn, n_non_zero, diag, typ, P, U, E, g_re, g_im, a_re, a_im) &
+          bind(c, name="alf_b200_set_op_v")
+       import :: c_ptr, c_int, c_double
+       type(c_ptr), value :: h
+       integer(c_int), value :: n, nf, nn, n_non_zero, diag, typ
+       integer(c_int), intent(in) :: P(*)
+       complex(c_double_complex), intent(in) :: U(*)     ! interleaved (re,im) = what the C side reads as double[2*nn*nn]
+       real(c_double), intent(in) :: E(*)
+       real(c_double), value :: g_re, g_im, a_re, a_im
+     end function
+     integer(c_int) function alf_b200_set_op_t(h, nc, nf, nn, diag, P, U, E, g_re, g_im) bind(c, name="alf_b200_set_op_t")
+       import :: c_ptr, c_int, c_double, c_double_complex
+       type(c_ptr), value :: h
+       integer(c_int), value :: nc, nf, nn, diag
+       integer(c_int), intent(in) :: P(*)
+       complex(c_double_complex), intent(in) :: U(*)
+       real(c_double), intent(in) :: E(*)
+       real(c_double), value :: g_re, g_im
+     end function
+     integer(c_int) function alf_b200_finalize_model(h) bind(c, name="alf_b200_finalize_model")
+       import :: c_ptr, c_int
+       type(c_ptr), value :: h
+     end function
+     integer(c_int) function alf_b200_set_seeds(h, seeds) bind(c, name="alf_b200_set_seeds")
+       import :: c_ptr, c_int, c_int32_t
+       type(c_ptr), value :: h
+       integer(c_int32_t), intent(in) :: seeds(*)
+     end function
+     integer(c_int) function alf_b200_init_sweep(h) bind(c, name="alf_b200_init_sweep")
+       import :: c_ptr, c_int
+       type(c_ptr), value :: h
+     end function
+     integer(c_int) function alf_b200_sweep_host(h, n_sweeps, ltau, fields_in, fields_out, obs_out, control_out) &
+          bind(c, name="alf_b200_sweep_host")
+       import :: c_ptr, c_int, c_double_complex, c_double
+       type(c_ptr), value :: h
+       integer(c_int), value :: n_sweeps, ltau
+       complex(c_double_complex), intent(in)  :: fields_in(*)     ! [n + n_opv*(nt-1) + n_opv*ltrot*chain]  == nsigma%f(n,nt) per chain
+       complex(c_double_complex), intent(out) :: fields_out(*)
+       real(c_double), intent(out) :: obs_out(*), control_out(*)
+     end function
+     integer(c_int) function alf_b200_wrapur(h, ntau, ntau1) bind(c, name="alf_b200_wrapur")
+       import :: c_ptr, c_int
+       type(c_ptr), value :: h
+       integer(c_int), value :: ntau, ntau1
+     end function
+     integer(c_int) function alf_b200_wrapul(h, ntau1, ntau) bind(c, name="alf_b200_wrapul")
+       import :: c_ptr, c_int
+       type(c_ptr), value :: h
+       integer(c_int), value :: ntau1, ntau
+     end function
+     integer(c_int) function alf_b200_wrapgrup(h, ntau) bind(c, name="alf_b200_wrapgrup")
+       import :: c_ptr, c_int
+       type(c_ptr), value :: h
+       integer(c_int), value :: ntau
+     end function
+     integer(c_int) function alf_b200_wrapgrdo(h, ntau) bind(c, name="alf_b200_wrapgrdo")
+       import :: c_ptr, c_int
+       type(c_ptr), value :: h
+       integer(c_int), value :: ntau
+     end function
+     integer(c_int) function alf_b200_cgr(h, nvar) bind(c, name="alf_b200_cgr")
+       import :: c_ptr, c_int
+       type(c_ptr), value :: h
+       integer(c_int), value :: nvar
+     end function
+     integer(c_int) function alf_b200_tau_m(h) bind(c, name="alf_b200_tau_m")
+       import :: c_ptr, c_int
+       type(c_ptr), value :: h
+     end function
+     integer(c_int) function alf_b200_get_green(h, chain, nf, symmetrize, gout) bind(c, name="alf_b200_get_green")
+       import :: c_ptr, c_int, c_double_complex
+       type(c_ptr), value :: h
+       integer(c_int), value :: chain, nf, symmetrize
+       complex(c_double_complex), intent(out) :: gout(*)
+     end function
+     integer(c_int) function alf_b200_set_green(h, chain, nf, gin) bind(c, name="alf_b200_set_green")
+       import :: c_ptr, c_int, c_double_complex
+       type(c_ptr), value :: h
+       integer(c_int), value :: chain, nf
+       complex(c_double_complex), intent(in) :: gin(*)
+     end function
+     integer(c_int) function alf_b200_get_phase(h, ph) bind(c, name="alf_b200_get_phase")
+       import :: c_ptr, c_int, c_double_complex
+       type(c_ptr), value :: h
+       complex(c_double_complex), intent(out) :: ph(*)
+     end function
+  end interface
+
+contains
+
+  subroutine check(rc, file, line)        ! the C-ABI never aborts: map its return code to ALF's convention
+    integer(c_int), intent(in) :: rc
+    character(len=*), intent(in) :: file
+    integer, intent(in) :: line
+    if (rc /= 0) call Terminate_on_error(int(rc), file, line)
+  end subroutine
+
+  !> Called once after ham%Ham_set (Prog/main.F90:318-319): flattens the PUBLIC fields of Op_V / Op_T
+  !> (Prog/Operator_mod.F90:57-69) into the C tables.  M_exp/E_exp/ExpOpT_vec are private in ALF and are rebuilt by
+  !> alf_b200_finalize_model exactly as Op_set/Op_exp/Hop_mod_init do.
+  subroutine alf_b200_attach(Op_V, Op_T, Ndim, N_FL, N_SUN, Ltrot, Nwrap, Symm, n_chains, device, seeds)
+    type(Operator), intent(in) :: Op_V(:,:), Op_T(:,:)
+    integer, intent(in) :: Ndim, N_FL, N_SUN, Ltrot, Nwrap, n_chains, device
+    logical, intent(in) :: Symm
+    integer, intent(in) :: seeds(:)
+    integer :: n, nf, stab
+    stab = 0
+#if defined(STAB3)
+    stab = 3
+#endif
+    call check(alf_b200_create(alf_b200_handle_ptr, Ndim, N_FL, N_SUN, Ltrot, Nwrap, size(Op_V,1), size(Op_T,1), &
+         merge(1,0,Symm), stab, n_chains, device), __FILE__, __LINE__)
+    do nf = 1, N_FL
+       do n = 1, size(Op_V,1)
+          call check(alf_b200_set_op_v(alf_b200_handle_ptr, n, nf, Op_V(n,nf)%N, Op_V(n,nf)%N_non_zero, merge(1,0,Op_V(n,nf)%diag), &
+               Op_V(n,nf)%type, Op_V(n,nf)%P, Op_V(n,nf)%U, Op_V(n,nf)%E, dble(Op_V(n,nf)%g), aimag(Op_V(n,nf)%g), &
+               dble(Op_V(n,nf)%alpha), aimag(Op_V(n,nf)%alpha)), __FILE__, __LINE__)
+       enddo
+       do n = 1, size(Op_T,1)
+          call check(alf_b200_set_op_t(alf_b200_handle_ptr, n, nf, Op_T(n,nf)%N, merge(1,0,Op_T(n,nf)%diag), Op_T(n,nf)%P, &
+               Op_T(n,nf)%U, Op_T(n,nf)%E, dble(Op_T(n,nf)%g), aimag(Op_T(n,nf)%g)), __FILE__, __LINE__)
+       enddo
+    enddo
+    call check(alf_b200_finalize_model(alf_b200_handle_ptr), __FILE__, __LINE__)
+    call check(alf_b200_set_seeds(alf_b200_handle_ptr, int(seeds, c_int32_t)), __FILE__, __LINE__)
+  end subroutine
+
+  subroutine alf_b200_detach()
+    integer(c_int) :: rc
+    rc = alf_b200_destroy(alf_b200_handle_ptr); alf_b200_handle_ptr = c_null_ptr
+  end subroutine
+
+  !> Batched mode: replaces the body of the get_sequential() branch, Prog/main.F90:714-887 (+ TAU_M when Ltau == 1),
+  !> for all chains of the handle.  nsigma_all(:,:,c) is chain c's nsigma%f.
+  subroutine alf_b200_batched_sweep(nsigma_all, n_sweeps, ltau, obs, control)
+    complex(kind=kind(0.d0)), intent(inout) :: nsigma_all(:,:,:)
+    integer, intent(in) :: n_sweeps, ltau
+    real(kind=kind(0.d0)), intent(out) :: obs(:), control(16)
+    call check(alf_b200_sweep_host(alf_b200_handle_ptr, n_sweeps, ltau, nsigma_all, nsigma_all, obs, control), __FILE__, __LINE__)
+  end subroutine
+
+end module alf_b200_shim
