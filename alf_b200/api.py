@@ -195,6 +195,14 @@ class AlfB200:
         ntau = n.value // (4 * self.m.N_FL * nn)
         return buf.reshape(ntau, 4, self.m.N_FL, self.N, self.N).transpose(0, 1, 2, 4, 3)
 
+    def get_taum_fresh(self, chain):
+        n = C.c_long(0)
+        self._ck(lib().alf_b200_get_taum_fresh(self.h, int(chain), None, C.c_long(0), C.byref(n)))
+        buf = np.zeros(n.value, dtype=np.complex128)
+        self._ck(lib().alf_b200_get_taum_fresh(self.h, int(chain), _d(buf), C.c_long(n.value), C.byref(n)))
+        ns = n.value // (4 * self.m.N_FL * self.N * self.N)
+        return buf.reshape(ns, 4, self.m.N_FL, self.N, self.N).transpose(0, 1, 2, 4, 3)
+
     def obs_size(self):
         return int(lib().alf_b200_obs_size(self.h))
 
@@ -277,6 +285,17 @@ def test_cgr(UR, DR, VR, UL, DL, VL, detUR, detUL, nvar=1, stab=0, is_complex=Tr
     _chk(lib().alf_b200_test_cgr(device, int(is_complex), n, batch, int(nvar), int(stab), _d(a[0]), _d(dr), _d(a[1]), _d(a[2]), _d(dl), _d(a[3]),
                                  _d(d1), _d(d2), _d(G), _d(ph)), "test_cgr")
     return G.transpose(0, 2, 1), ph
+
+
+def test_cgr2_2(U2, D2, V2, U1, D1, V1, stab=0, is_complex=True, device=0):
+    batch, n, _ = U2.shape
+    cm = lambda X: np.ascontiguousarray(np.asarray(X, dtype=np.complex128).transpose(0, 2, 1))
+    a = [cm(x) for x in (U2, V2, U1, V1)]
+    d2 = np.ascontiguousarray(D2, dtype=np.complex128); d1 = np.ascontiguousarray(D1, dtype=np.complex128)
+    out = np.zeros((4, batch, n, n), dtype=np.complex128)
+    _chk(lib().alf_b200_test_cgr2_2(device, int(is_complex), n, batch, int(stab), _d(a[0]), _d(d2), _d(a[1]), _d(a[2]), _d(d1), _d(a[3]), _d(out)), "test_cgr2_2")
+    o = out.transpose(0, 1, 3, 2)
+    return dict(GRT0=o[0], GR00=o[1], GRTT=o[2], GR0T=o[3])
 
 
 def fp64_peak(device=0):

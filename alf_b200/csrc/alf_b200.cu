@@ -131,7 +131,7 @@ struct alf_b200_handle {
   double* d_ctl = nullptr;            // per chain: 0 XMEANG 1 XMAXG 2 NCG 3 XMAXP 4 XMEAN_tau 5 XMAX_tau 6 NCG_tau 7 flags(nan=1, unstable=2)
   uint8_t* d_acclog = nullptr; long acclog_per_chain = 0; long acclog_pos = 0; bool acclog_on = false;
   double* d_obs = nullptr; int obs_size = 0;
-  int taum_every = 0; std::vector<std::vector<cd>> taum_host;   // per chain captured matrices
+  int taum_every = 0; std::vector<std::vector<cd>> taum_host, taum_fresh_host;   // per chain captured matrices
   std::vector<int> types;            // operator type per n
 };
 
@@ -475,7 +475,69 @@ struct Engine : EngineBase {
     if (ltau == 1) tau_m();
   }
 
-  void tau_m() override { throw CudaError("TAU_M is not built yet in this revision"); }
+  // ---------------------------------------------------------------- TAU_M (Prog/tau_m_mod.F90:56-211) for all chains
+  LaWork<T> w2; bool w2_ready = false; T* tmN[4] = {nullptr, nullptr, nullptr, nullptr}; int* d_first = nullptr; T* capbuf = nullptr;
+  void taum_alloc() {
+    if (w2_ready) return;
+    w2.alloc(2 * N, NM, st);
+    GT0 = dalloc<T>(n2 * NM); G0T = dalloc<T>(n2 * NM); G00 = dalloc<T>(n2 * NM); GTT = dalloc<T>(n2 * NM);
+    for (int q = 0; q < 4; ++q) tmN[q] = dalloc<T>(n2 * NM);
+    udvr2 = alloc_udv(); d_first = dalloc<int>(NM); capbuf = dalloc<T>(n2 * NM);
+    w2_ready = true;
+  }
+  void taum_capture(int nt, bool fresh = false) {     // what ham%ObserT receives (tau_m_mod.F90:115-124,151-177); test support only
+    if (!h->taum_every) return;
+    if (!fresh && h->taum_every > 1 && (nt % h->taum_every) != 0) return;
+    std::vector<std::vector<cd>>& dst = fresh ? h->taum_fresh_host : h->taum_host;
+    if (dst.size() != (size_t)C) dst.assign(C, std::vector<cd>());
+    T* arr[4] = {GT0, G0T, G00, GTT};
+    std::vector<T> host(n2 * NM);
+    std::vector<std::vector<cd>> part(C, std::vector<cd>((size_t)4 * F * n2));
+    for (int q = 0; q < 4; ++q) {
+      CK(cudaMemcpyAsync(capbuf, arr[q], sizeof(T) * n2 * NM, cudaMemcpyDeviceToDevice, st));
+      if (h->symm && !fresh) hop_symm(capbuf);
+      CK(cudaMemcpyAsync(host.data(), capbuf, sizeof(T) * n2 * NM, cudaMemcpyDeviceToHost, st)); sync();
+      for (int c = 0; c < C; ++c) for (int f = 0; f < F; ++f) for (long i = 0; i < n2; ++i)
+        part[c][((size_t)q * F + f) * n2 + i] = from_T<T>(host[n2 * ((long)c * F + f) + i]);
+    }
+    for (int c = 0; c < C; ++c) dst[c].insert(dst[c].end(), part[c].begin(), part[c].end());
+  }
+  void compare_tau(const T* A, const T* B) {   // Control_Precision_tau, control_mod.F90:300-311
+    KL(KC_EW, st, k_compare<T><<<NM, 256, 0, st>>>(A, B, n2, n2, d_cmp));
+    KL(KC_EW, st, k_ctl_accum<<<(C + 127) / 128, 128, 0, st>>>(d_cmp, F, h->d_ctl, 1, C));
+  }
+  void tau_m() override {
+    taum_alloc();
+    const size_t bytes = sizeof(T) * n2 * NM; dim3 eg(ew_blocks(n2), NM);
+    CK(cudaMemcpyAsync(G00, G, bytes, cudaMemcpyDeviceToDevice, st)); CK(cudaMemcpyAsync(GT0, G, bytes, cudaMemcpyDeviceToDevice, st));
+    CK(cudaMemcpyAsync(GTT, G, bytes, cudaMemcpyDeviceToDevice, st));
+    KL(KC_EW, st, k_g0t_init<T><<<eg, 256, 0, st>>>(G0T, G, n2, N));
+    taum_capture(0);
+    set_udv_identity(udvr2);
+    int NST = 1;
+    for (int NT = 0; NT <= L - 1; ++NT) {
+      const int NT1 = NT + 1;
+      propr(GT0, NT1); proprm1(G0T, NT1); proprm1(GTT, NT1); propr(GTT, NT1);          // tau_m_mod.F90:141-149
+      taum_capture(NT1);
+      if (stab_nt[NST] == NT1) {
+        wrapur_on(udvr2, stab_nt[NST - 1], NT1);
+        la_cgr2_2<T>(w, w2, h->stab, udvr2, udvst[NST - 1], tmN[0], tmN[1], tmN[2], tmN[3], d_first);
+        compare_tau(G, tmN[1]); compare_tau(GTT, tmN[2]); compare_tau(GT0, tmN[0]); compare_tau(G0T, tmN[3]);
+        std::swap(GT0, tmN[0]); std::swap(G00, tmN[1]); std::swap(GTT, tmN[2]); std::swap(G0T, tmN[3]);
+        taum_capture(NT1, true);
+        NST++;
+      }
+    }
+  }
+  // PROPR / PROPRM1 (Prog/tau_m_mod.F90:215-263): A <- B(nt) A ;  A <- A B(nt)^-1
+  void propr(T* A, int nt) {
+    if (!dense_t) apply_ops(A, 0, MODE_WRAPUR, nt, nt);
+    else { dense_mult(A, 0, true); apply_ops(A, 0, MODE_WRAPUR, nt, nt); }
+  }
+  void proprm1(T* A, int nt) {
+    if (!dense_t) apply_ops(A, 1, MODE_PROPRM1, nt, nt);
+    else { dense_mult(A, 1, false); apply_ops(A, 1, MODE_PROPRM1, nt, nt); }
+  }
 
   // ---------------------------------------------------------------- host access
   void get_green(int chain, int nf, int symm, cd* out) override {
@@ -551,6 +613,19 @@ static void t_cgr(int n, int batch, int nvar, int stab, const double* UR, const 
   la_cgr<T>(w, nvar, stab, R, L, dG.p, dz.p); CK(cudaDeviceSynchronize());
   T2h<T>(dG.down(), G); auto z = dz.down(); for (int i = 0; i < batch; ++i) { phase[2 * i] = z[i].x; phase[2 * i + 1] = z[i].y; }
   w.release();
+}
+template <typename T>
+static void t_cgr22(int n, int batch, int stab, const double* U2, const double* D2, const double* V2, const double* U1, const double* D1, const double* V1, double* out4) {
+  const size_t n2 = (size_t)n * n; LaWork<T> w, w2; w.alloc(n, batch, 0); w2.alloc(2 * n, batch, 0);
+  DevBuf<T> dU2(n2 * batch), dV2(n2 * batch), dU1(n2 * batch), dV1(n2 * batch), g0(n2 * batch), g1(n2 * batch), g2(n2 * batch), g3(n2 * batch);
+  DevBuf<double> dD2((size_t)n * batch), dD1((size_t)n * batch); DevBuf<int> first(batch);
+  dU2.up(h2T<T>(U2, n2 * batch)); dV2.up(h2T<T>(V2, n2 * batch)); dU1.up(h2T<T>(U1, n2 * batch)); dV1.up(h2T<T>(V1, n2 * batch));
+  { std::vector<double> a((size_t)n * batch), b((size_t)n * batch); for (size_t i = 0; i < a.size(); ++i) { a[i] = D2[2 * i]; b[i] = D1[2 * i]; } dD2.up(a); dD1.up(b); }
+  UdvDev<T> u2, u1; u2.U = dU2.p; u2.V = dV2.p; u2.D = dD2.p; u1.U = dU1.p; u1.V = dV1.p; u1.D = dD1.p;
+  la_cgr2_2<T>(w, w2, stab, u2, u1, g0.p, g1.p, g2.p, g3.p, first.p); CK(cudaDeviceSynchronize());
+  DevBuf<T>* gs[4] = {&g0, &g1, &g2, &g3};
+  for (int q = 0; q < 4; ++q) T2h<T>(gs[q]->down(), out4 + 2 * q * n2 * batch);
+  w.release(); w2.release();
 }
 template <typename T>
 static void t_gemm(int ta, int tb, int m, int n, int k, int batch, const double* A, const double* B, double* Cc) {
@@ -788,11 +863,18 @@ int alf_b200_get_accept_log(alf_b200_handle* h, uint8_t* out, long cap, long* n_
   for (long c = 0; c < C; ++c) for (long v = 0; v < n / M; ++v) for (long s = 0; s < M; ++s) { long o = c * n + v * M + s; if (o < cap) out[o] = raw[(size_t)(v * M) * C + c * M + s]; }
   API_END(h)
 }
-int alf_b200_taum_capture(alf_b200_handle* h, int every) { if (!h) return ALF_ERROR_GENERIC; h->taum_every = every; h->taum_host.clear(); return ALF_OK; }
+int alf_b200_taum_capture(alf_b200_handle* h, int every) { if (!h) return ALF_ERROR_GENERIC; h->taum_every = every; h->taum_host.clear(); h->taum_fresh_host.clear(); return ALF_OK; }
 int alf_b200_get_taum(alf_b200_handle* h, int chain, double* out, long cap, long* n) {
   if (!h) return ALF_ERROR_GENERIC;
   if (chain < 0 || chain >= (int)h->taum_host.size()) { if (n) *n = 0; return ALF_OK; }
   const auto& v = h->taum_host[chain]; if (n) *n = (long)v.size();
+  if (out) std::memcpy(out, v.data(), sizeof(cd) * std::min<long>((long)v.size(), cap));
+  return ALF_OK;
+}
+int alf_b200_get_taum_fresh(alf_b200_handle* h, int chain, double* out, long cap, long* n) {
+  if (!h) return ALF_ERROR_GENERIC;
+  if (chain < 0 || chain >= (int)h->taum_fresh_host.size()) { if (n) *n = 0; return ALF_OK; }
+  const auto& v = h->taum_fresh_host[chain]; if (n) *n = (long)v.size();
   if (out) std::memcpy(out, v.data(), sizeof(cd) * std::min<long>((long)v.size(), cap));
   return ALF_OK;
 }
@@ -824,6 +906,11 @@ int alf_b200_test_cgr(int device, int is_complex, int n, int batch, int nvar, in
   try { CK(cudaSetDevice(device)); if (is_complex) t_cgr<cplx>(n, batch, nvar, stab, UR, DR, VR, UL, DL, VL, detUR, detUL, G, phase);
         else t_cgr<double>(n, batch, nvar, stab, UR, DR, VR, UL, DL, VL, detUR, detUL, G, phase); }
   catch (const std::exception& e) { fprintf(stderr, "alf_b200_test_cgr: %s\n", e.what()); return ALF_ERROR_CUDA; } return ALF_OK;
+}
+int alf_b200_test_cgr2_2(int device, int is_complex, int n, int batch, int stab, const double* U2, const double* D2, const double* V2,
+                         const double* U1, const double* D1, const double* V1, double* out4) {
+  try { CK(cudaSetDevice(device)); if (is_complex) t_cgr22<cplx>(n, batch, stab, U2, D2, V2, U1, D1, V1, out4); else t_cgr22<double>(n, batch, stab, U2, D2, V2, U1, D1, V1, out4); }
+  catch (const std::exception& e) { fprintf(stderr, "alf_b200_test_cgr2_2: %s\n", e.what()); return ALF_ERROR_CUDA; } return ALF_OK;
 }
 int alf_b200_test_gemm(int device, int is_complex, int ta, int tb, int m, int n, int k, int batch, const double* A, const double* B, double* C) {
   try { CK(cudaSetDevice(device)); if (is_complex) t_gemm<cplx>(ta, tb, m, n, k, batch, A, B, C); else t_gemm<double>(ta, tb, m, n, k, batch, A, B, C); }

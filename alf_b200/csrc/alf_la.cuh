@@ -334,7 +334,7 @@ __global__ void __launch_bounds__(512) k_formq(T* __restrict__ A, int m, int n, 
 #define TRSM_WARPS 8
 #define TRSM_CPW 4
 #define TRSM_COLS (TRSM_WARPS * TRSM_CPW)
-template <typename T, int MAXR>
+template <typename T, int MAXR, int LOWER = 0>
 __global__ void __launch_bounds__(TRSM_WARPS * 32) k_trsm_lun(const T* __restrict__ R, int ldr, long sR, T* __restrict__ B, int ldb, long sB,
                                                              int n, int nrhs, const double* __restrict__ dinv, long sD) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -353,9 +353,12 @@ __global__ void __launch_bounds__(TRSM_WARPS * 32) k_trsm_lun(const T* __restric
       if (i < n && c < nrhs) { v = B[i + (long)c * ldb]; if (dinv) v = v * (1.0 / dinv[i]); }
       x[cc][q] = v;
     }
-  for (int i = n - 1; i >= 0; --i) {
+  // LOWER = 0: back substitution with the upper triangle; LOWER = 1: forward substitution with the lower triangle (R holds L)
+  for (int ii = 0; ii < n; ++ii) {
+    const int i = LOWER ? ii : n - 1 - ii;
     __syncthreads();
-    for (int k = tid; k <= i; k += blockDim.x) rcol[k] = R[k + (long)i * ldr];
+    if (LOWER) { for (int k = i + tid; k < n; k += blockDim.x) rcol[k] = R[k + (long)i * ldr]; }
+    else { for (int k = tid; k <= i; k += blockDim.x) rcol[k] = R[k + (long)i * ldr]; }
     __syncthreads();
     const T rinv = one_<T>() / rcol[i];
     const int qi = i >> 5, li = i & 31;
@@ -368,7 +371,7 @@ __global__ void __launch_bounds__(TRSM_WARPS * 32) k_trsm_lun(const T* __restric
 #pragma unroll
       for (int q = 0; q < MAXR; ++q) {
         int k = lane + 32 * q;
-        if (k < i) x[cc][q] = x[cc][q] - rcol[k] * xi;
+        if (LOWER ? (k > i && k < n) : (k < i)) x[cc][q] = x[cc][q] - rcol[k] * xi;
         else if (k == i) x[cc][q] = xi;
       }
     }
@@ -465,6 +468,59 @@ __global__ void k_sep_scale(T* __restrict__ A, long sA, int n, const double* __r
     int i = (int)(e % n), j = (int)(e / n);
     double x = d[ROWS ? i : j];
     if (x > 1.0) A[e] = A[e] * (1.0 / x);
+  }
+}
+
+// A(i, :) *= 1/d[i]
+template <typename T>
+__global__ void k_rowscale_inv(T* __restrict__ A, int ld, long sA, int m, int n, const double* __restrict__ d, long sD) {
+  const int b = blockIdx.y; A += (long)b * sA; d += (long)b * sD;
+  for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < (long)m * n; e += (long)gridDim.x * blockDim.x) {
+    int i = (int)(e % m), j = (int)(e / m);
+    A[i + (long)j * ld] = A[i + (long)j * ld] * (1.0 / d[i]);
+  }
+}
+
+// CGR2_2 (Prog/cgr2_2_mod.F90:318-425): builds HLPB1 = HLPB2^H (input of the 2N x 2N pivoted QR) and the block-diagonal
+// right-hand side HLP = diag(UCT, VINV) of solve_extended_System (:155-191).  Per matrix the ordering of the blocks depends
+// on D1(1) > D2(1) (:371, :398); the choice is recorded in first[b] for get_blocks.  STAB3: D_+ scalings (:352-366).
+template <typename T, int STAB3>
+__global__ void k_cgr22_build(T* __restrict__ HLPB1, T* __restrict__ HLP, long s22, const T* __restrict__ V1INV, const T* __restrict__ U1,
+                              const double* __restrict__ D1, const T* __restrict__ U2, const T* __restrict__ V2, const double* __restrict__ D2,
+                              long sM, long sD, int N, int* __restrict__ first) {
+  const int b = blockIdx.y; const int N2 = 2 * N;
+  HLPB1 += (long)b * s22; HLP += (long)b * s22; V1INV += (long)b * sM; U1 += (long)b * sM; U2 += (long)b * sM; V2 += (long)b * sM; D1 += (long)b * sD; D2 += (long)b * sD;
+  const bool fst = D1[0] > D2[0];
+  if (blockIdx.x == 0 && threadIdx.x == 0) first[b] = fst ? 1 : 0;
+  for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < (long)N2 * N2; e += (long)gridDim.x * blockDim.x) {
+    const int I2 = (int)(e % N2), J2 = (int)(e / N2);
+    const int bi = I2 >= N, bj = J2 >= N, I = I2 - bi * N, J = J2 - bj * N;
+    // blocks of HLPB2 in the "first" ordering: (0,0) V1INV, (0,1) D1 U1^H, (1,0) -D2 V2, (1,1) U2^H ; otherwise both block rows and columns swap roles
+    const int kind = fst ? (bi * 2 + bj) : ((1 - bi) * 2 + (1 - bj));
+    T v, hl = zero_<T>();
+    const double d1 = D1[I], d2 = D2[I];
+    const double s1 = (STAB3 && d1 > 1.0) ? 1.0 / d1 : 1.0, m1 = (STAB3 && d1 > 1.0) ? 1.0 : d1;
+    const double s2 = (STAB3 && d2 > 1.0) ? 1.0 / d2 : 1.0, m2 = (STAB3 && d2 > 1.0) ? 1.0 : d2;
+    if (kind == 0) { v = V1INV[I + (long)J * N] * s1; hl = v; }
+    else if (kind == 1) v = m1 * conj_(U1[J + (long)I * N]);
+    else if (kind == 2) v = -(m2 * V2[I + (long)J * N]);
+    else { v = conj_(U2[J + (long)I * N]) * s2; hl = v; }
+    HLPB1[J2 + (long)I2 * N2] = conj_(v);
+    HLP[I2 + (long)J2 * N2] = hl;
+  }
+}
+// get_blocks (cgr2_2_mod.F90:55-72) with the ordering flag: first: (A,B,C,D) = (G00,G0T,GT0,GTT), else (GTT,GT0,G0T,G00)
+template <typename T>
+__global__ void k_cgr22_blocks(const T* __restrict__ INP, long s22, T* __restrict__ GT0, T* __restrict__ G00, T* __restrict__ GTT, T* __restrict__ G0T,
+                               long sM, int N, const int* __restrict__ first) {
+  const int b = blockIdx.y; const int N2 = 2 * N;
+  INP += (long)b * s22; GT0 += (long)b * sM; G00 += (long)b * sM; GTT += (long)b * sM; G0T += (long)b * sM;
+  const bool fst = first[b] != 0;
+  for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < (long)N * N; e += (long)gridDim.x * blockDim.x) {
+    const int I = (int)(e % N), J = (int)(e / N);
+    const T a = INP[I + (long)J * N2], d = INP[(I + N) + (long)(J + N) * N2], c = INP[(I + N) + (long)J * N2], bb = INP[I + (long)(J + N) * N2];
+    if (fst) { G00[e] = a; G0T[e] = bb; GT0[e] = c; GTT[e] = d; }
+    else { GTT[e] = a; GT0[e] = bb; G0T[e] = c; G00[e] = d; }
   }
 }
 

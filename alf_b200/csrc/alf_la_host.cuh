@@ -112,15 +112,15 @@ static void launch_formq(cudaStream_t st, T* A, int m, int n, int ld, long sA, c
 #undef FQ_LAUNCH
 }
 
-template <typename T>
+template <typename T, int LOWER = 0>
 static void launch_trsm(cudaStream_t st, const T* R, int ldr, long sR, T* B, int ldb, long sB, int n, int nrhs, const double* dinv, long sD, int batch) {
   dim3 grid((nrhs + TRSM_COLS - 1) / TRSM_COLS, batch);
   size_t smem = sizeof(T) * n;
   KScope ks_(KC_TRSM, st);
-  if (n <= 64) k_trsm_lun<T, 2><<<grid, TRSM_WARPS * 32, smem, st>>>(R, ldr, sR, B, ldb, sB, n, nrhs, dinv, sD);
-  else if (n <= 128) k_trsm_lun<T, 4><<<grid, TRSM_WARPS * 32, smem, st>>>(R, ldr, sR, B, ldb, sB, n, nrhs, dinv, sD);
-  else if (n <= 288) k_trsm_lun<T, 9><<<grid, TRSM_WARPS * 32, smem, st>>>(R, ldr, sR, B, ldb, sB, n, nrhs, dinv, sD);
-  else if (n <= 576) k_trsm_lun<T, 18><<<grid, TRSM_WARPS * 32, smem, st>>>(R, ldr, sR, B, ldb, sB, n, nrhs, dinv, sD);
+  if (n <= 64) k_trsm_lun<T, 2, LOWER><<<grid, TRSM_WARPS * 32, smem, st>>>(R, ldr, sR, B, ldb, sB, n, nrhs, dinv, sD);
+  else if (n <= 128) k_trsm_lun<T, 4, LOWER><<<grid, TRSM_WARPS * 32, smem, st>>>(R, ldr, sR, B, ldb, sB, n, nrhs, dinv, sD);
+  else if (n <= 288) k_trsm_lun<T, 9, LOWER><<<grid, TRSM_WARPS * 32, smem, st>>>(R, ldr, sR, B, ldb, sB, n, nrhs, dinv, sD);
+  else if (n <= 576) k_trsm_lun<T, 18, LOWER><<<grid, TRSM_WARPS * 32, smem, st>>>(R, ldr, sR, B, ldb, sB, n, nrhs, dinv, sD);
   else throw CudaError("k_trsm_lun: n > 576 not supported in this build");
   CKL();
 }
@@ -190,4 +190,42 @@ static void la_cgr(LaWork<T>& w, int nvar, int stab, const UdvDev<T>& R, const U
   if (stab == 3) { KL(KC_EW, st, k_sep_scale<T, 1><<<eg, 256, 0, st>>>(w.W[0], n2, N, A1.D, N)); }
   if (nvar == 1) gemm<T, 0, 0, 0>(st, N, N, N, L.U, N, n2, w.W[0], N, n2, Gout, N, n2, NM);        // G = U_L X2
   else gemm<T, 1, 1, 0>(st, N, N, N, w.W[0], N, n2, R.U, N, n2, Gout, N, n2, NM);                 // G = X2^H U_R^H
+}
+
+
+// A^-1 for a batch of well-conditioned N x N matrices (replaces INV = ZGETRF + ZGETRI, Libraries/Modules/mymats_mod.F90:546-580,
+// at its only hot-path call site, V1INV of CGR2_2, Prog/cgr2_2_mod.F90:349) through the pivoted QR already on the device:
+// A P = Q D R  =>  A^-1 = P R^-1 D^-1 Q^H.   A is destroyed; Ainv must not alias A.  Uses w.W[0], w.W[1].
+template <typename T>
+static void la_inverse(LaWork<T>& w, T* A, T* Ainv) {
+  const int N = w.N, NM = w.NM; const long n2 = w.n2(); cudaStream_t st = w.st; dim3 eg(ew_blocks(n2), NM);
+  launch_qrp<T, 1>(st, A, N, N, N, n2, w.tau, N, w.jpvt, N, w.Dq, N, w.qrout, NM);
+  KL(KC_EW, st, k_permcopy<T, 0><<<eg, 256, 0, st>>>(w.W[0], N, n2, A, N, n2, N, N, nullptr, 0));
+  launch_formq<T>(st, w.W[0], N, N, N, n2, w.tau, N, nullptr, NM);
+  KL(KC_EW, st, k_permcopy<T, 4><<<eg, 256, 0, st>>>(w.W[1], N, n2, w.W[0], N, n2, N, N, nullptr, 0));      // Q^H
+  launch_trsm<T>(st, A, N, n2, w.W[1], N, n2, N, N, w.Dq, N, NM);                                            // R^-1 D^-1 Q^H
+  KL(KC_EW, st, k_permcopy<T, 3><<<eg, 256, 0, st>>>(Ainv, N, n2, w.W[1], N, n2, N, N, w.jpvt, N));          // rows scattered by P
+}
+
+// CGR2_2 (Prog/cgr2_2_mod.F90:318-425) for a batch: w is the N-sized workspace, w2 the 2N-sized one (w2.NM == w.NM).
+// udv2 = right propagation (side R), udv1 = left propagation (side L).  Outputs must not alias inputs.
+template <typename T>
+static void la_cgr2_2(LaWork<T>& w, LaWork<T>& w2, int stab, const UdvDev<T>& udv2, const UdvDev<T>& udv1, T* GT0, T* G00, T* GTT, T* G0T, int* first) {
+  const int N = w.N, NM = w.NM, N2 = 2 * N; const long n2 = w.n2(), n22 = w2.n2(); cudaStream_t st = w.st;
+  dim3 eg(ew_blocks(n2), NM), eg2(ew_blocks(n22), NM);
+  // V1INV in w.W[3] (V1 copied to w.W[2] because la_inverse destroys its input)
+  KL(KC_EW, st, k_permcopy<T, 0><<<eg, 256, 0, st>>>(w.W[2], N, n2, udv1.V, N, n2, N, N, nullptr, 0));
+  la_inverse<T>(w, w.W[2], w.W[3]);
+  // HLPB1 = HLPB2^H in w2.W[0]; right-hand side HLP in w2.W[1]
+  if (stab == 3) KL(KC_EW, st, k_cgr22_build<T, 1><<<eg2, 256, 0, st>>>(w2.W[0], w2.W[1], n22, w.W[3], udv1.U, udv1.D, udv2.U, udv2.V, udv2.D, n2, N, N, first));
+  else KL(KC_EW, st, k_cgr22_build<T, 0><<<eg2, 256, 0, st>>>(w2.W[0], w2.W[1], n22, w.W[3], udv1.U, udv1.D, udv2.U, udv2.V, udv2.D, n2, N, N, first));
+  launch_qrp<T, 1>(st, w2.W[0], N2, N2, N2, n22, w2.tau, N2, w2.jpvt, N2, w2.Dq, N2, w2.qrout, NM);
+  // HLP <- P^T-row gather (ZLAPMR forward), L = R^H, HLP <- L^-1 HLP, rows / D3, HLP <- Q HLP
+  KL(KC_EW, st, k_permcopy<T, 1><<<eg2, 256, 0, st>>>(w2.W[2], N2, n22, w2.W[1], N2, n22, N2, N2, w2.jpvt, N2));
+  KL(KC_EW, st, k_permcopy<T, 4><<<eg2, 256, 0, st>>>(w2.W[3], N2, n22, w2.W[0], N2, n22, N2, N2, nullptr, 0));   // full conj-transpose; only its lower triangle (R^H) is read
+  launch_trsm<T, 1>(st, w2.W[3], N2, n22, w2.W[2], N2, n22, N2, N2, nullptr, 0, NM);
+  KL(KC_EW, st, k_rowscale_inv<T><<<eg2, 256, 0, st>>>(w2.W[2], N2, n22, N2, N2, w2.Dq, N2));
+  launch_formq<T>(st, w2.W[0], N2, N2, N2, n22, w2.tau, N2, nullptr, NM);
+  gemm<T, 0, 0, 0>(st, N2, N2, N2, w2.W[0], N2, n22, w2.W[2], N2, n22, w2.W[1], N2, n22, NM);
+  KL(KC_EW, st, k_cgr22_blocks<T><<<eg, 256, 0, st>>>(w2.W[1], n22, GT0, G00, GTT, G0T, n2, N, first));
 }

@@ -93,6 +93,8 @@ int alf_b200_accept_log(alf_b200_handle* h, int n_sweeps);   /* record accept/re
 int alf_b200_get_accept_log(alf_b200_handle* h, uint8_t* out, long cap, long* n_per_chain);
 int alf_b200_taum_capture(alf_b200_handle* h, int every);    /* keep GT0,G0T,G00,GTT handed to ObserT every k-th slice */
 int alf_b200_get_taum(alf_b200_handle* h, int chain, double* out, long cap_complex, long* n_complex);
+/* the four matrices right after every CGR2_2 of TAU_M (freshly recomputed; not symmetrised), same layout */
+int alf_b200_get_taum_fresh(alf_b200_handle* h, int chain, double* out, long cap_complex, long* n_complex);
 
 /* ---- device-side scalar observables accumulated where main.F90 calls ham%Obser (:757-773,:789-802).
  * Layout: [0] N_meas, [1..2] sum phase/|Re phase| sign, then per chain-summed: Kin, Pot, Part, Ener (re,im each). */
@@ -109,6 +111,10 @@ int alf_b200_test_udv_decompose(int device, int is_complex, int n, int batch, ch
 int alf_b200_test_cgr(int device, int is_complex, int n, int batch, int nvar, int stab, const double* UR, const double* DR,
                       const double* VR, const double* UL, const double* DL, const double* VL, const double* detUR,
                       const double* detUL, double* G, double* phase);
+/* CGR2_2 (Prog/cgr2_2_mod.F90:196): udv2 = right (side R), udv1 = left (side L) propagation; out4 = GRT0, GR00, GRTT, GR0T,
+ * each complex n*n*batch */
+int alf_b200_test_cgr2_2(int device, int is_complex, int n, int batch, int stab, const double* U2, const double* D2, const double* V2,
+                         const double* U1, const double* D1, const double* V1, double* out4);
 int alf_b200_test_gemm(int device, int is_complex, int ta, int tb, int m, int n, int k, int batch, const double* A,
                        const double* B, double* C);
 int alf_b200_hop_apply(alf_b200_handle* h, int which /* 0 mmthr,1 mmthr_m1,2 mmthl,3 mmthl_m1,4 mmthlc,5 Symm */,

@@ -820,7 +820,7 @@ struct Oracle {
     }
   }
   // ---- Prog/tau_m_mod.F90:56-211, one stabilisation interval per call (state kept in tm_*)
-  std::vector<std::vector<cd>> tm_G00, tm_G0T, tm_GT0, tm_GTT; std::vector<UDV> tm_udvr;
+  std::vector<std::vector<cd>> tm_G00, tm_G0T, tm_GT0, tm_GTT; std::vector<UDV> tm_udvr; std::vector<cd> taum_fresh;
   void tau_m_segment(int t) {
     size_t n2 = (size_t)ndim * ndim;
     if (t == 0) {
@@ -844,6 +844,10 @@ struct Oracle {
           cgr2_2(tm_GT0[nf].data(), tm_G00[nf].data(), tm_GTT[nf].data(), tm_G0T[nf].data(), tm_udvr[nf], st(NST, nf), ndim, stab3);
           control_precision_tau(GR[nf].data(), tm_G00[nf].data()); control_precision_tau(HLP4.data(), tm_GTT[nf].data());
           control_precision_tau(HLP5.data(), tm_GT0[nf].data()); control_precision_tau(HLP6.data(), tm_G0T[nf].data());
+        }
+        if (taum_capture) {   // test support: the freshly recomputed G(tau,0), G(0,tau), G(0,0), G(tau,tau) (north_star check 1)
+          std::vector<std::vector<cd>>* arr[4] = {&tm_GT0, &tm_G0T, &tm_G00, &tm_GTT};
+          for (int w = 0; w < 4; ++w) for (int nf = 0; nf < n_fl; ++nf) taum_fresh.insert(taum_fresh.end(), (*arr[w])[nf].begin(), (*arr[w])[nf].end());
         }
       }
     }
@@ -940,7 +944,12 @@ void orc_get_control(void* h, double* out) {
   out[6] = (double)c.NCG_tau; out[7] = (double)c.NC_up; out[8] = (double)c.ACC_up; out[9] = (double)c.NC_eff_up; out[10] = (double)c.ACC_eff_up;
   out[11] = c.nan_flag; out[12] = c.unstable_flag;
 }
-void orc_taum_capture(void* h, int every) { Oracle* o = (Oracle*)h; o->taum_capture = every; o->taum_buf.clear(); }
+void orc_taum_capture(void* h, int every) { Oracle* o = (Oracle*)h; o->taum_capture = every; o->taum_buf.clear(); o->taum_fresh.clear(); }
+long orc_taum_fresh_get(void* h, double* out, long cap_complex) {
+  Oracle* o = (Oracle*)h; long n = (long)o->taum_fresh.size();
+  if (out) std::memcpy(out, o->taum_fresh.data(), sizeof(cd) * (size_t)std::min(n, cap_complex));
+  return n;
+}
 long orc_taum_get(void* h, double* out, long cap_complex) {
   Oracle* o = (Oracle*)h; long n = (long)o->taum_buf.size();
   if (out) std::memcpy(out, o->taum_buf.data(), sizeof(cd) * std::min(n, cap_complex));

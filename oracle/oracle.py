@@ -34,6 +34,7 @@ def lib():
         _lib.orc_ranf.restype = C.c_double
         _lib.orc_get_log.restype = C.c_long
         _lib.orc_taum_get.restype = C.c_long
+        _lib.orc_taum_fresh_get.restype = C.c_long
         _lib.orc_eq_get.restype = C.c_long
     return _lib
 
@@ -160,6 +161,14 @@ class Oracle:
         ntau = n // (4 * self.m.N_FL * nn)
         # [tau][which: GT0,G0T,G00,GTT][nf][col-major N*N]
         return buf.reshape(ntau, 4, self.m.N_FL, self.N, self.N).transpose(0, 1, 2, 4, 3)
+
+    def taum_fresh_get(self):
+        """[stabilisation][which: GT0,G0T,G00,GTT][nf][N,N]: the matrices right after every CGR2_2 of TAU_M."""
+        n = lib().orc_taum_fresh_get(self.h, None, 0)
+        buf = np.zeros(n, dtype=np.complex128)
+        lib().orc_taum_fresh_get(self.h, _d(buf), n)
+        ns = n // (4 * self.m.N_FL * self.N * self.N)
+        return buf.reshape(ns, 4, self.m.N_FL, self.N, self.N).transpose(0, 1, 2, 4, 3)
 
     def eq_capture(self, on=True):
         lib().orc_eq_capture(self.h, int(on))

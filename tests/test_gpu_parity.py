@@ -229,3 +229,74 @@ def test_many_chains_are_independent():
         assert relF(g1.green(0, 1), g.green(c, 1)) < 1e-13
         g1.close()
     g.close()
+
+
+@pytest.mark.parametrize("is_complex", [False, True])
+@pytest.mark.parametrize("stab", [0, 3])
+@pytest.mark.parametrize("n", [5, 16, 64])
+def test_cgr2_2_kernel(is_complex, stab, n):
+    """CGR2_2 (Prog/cgr2_2_mod.F90:196) on UDV states with 20 orders of magnitude of scales vs the oracle; both block orderings
+    (D1(1) > D2(1) and the opposite) occur in the batch."""
+    rng = np.random.default_rng(200 + n); batch = 3
+    S2, S1 = [], []
+    for b in range(batch):
+        def mk(side, spread):
+            U0 = rng.normal(size=(n, n)) + (1j * rng.normal(size=(n, n)) if is_complex else 0)
+            U0 = U0 * np.exp(np.linspace(-spread, spread, n))[None, :]
+            return O.udv_decompose(U0, np.ones(n), np.eye(n), side)
+        S2.append(mk("r", 10 if b != 1 else 4)); S1.append(mk("l", 10 if b == 1 else 6))
+    st = lambda k, S: np.stack([s[k] for s in S])
+    out = api.test_cgr2_2(st(0, S2), st(1, S2), st(2, S2), st(0, S1), st(1, S1), st(2, S1), stab, is_complex)
+    orders = set()
+    for b in range(batch):
+        ref = O.cgr2_2(S2[b][0], S2[b][1], S2[b][2], S1[b][0], S1[b][1], S1[b][2], stab3=(stab == 3))
+        orders.add(bool(S1[b][1][0].real > S2[b][1][0].real))
+        for k in ("GRT0", "GR00", "GRTT", "GR0T"):
+            assert relF(out[k][b], ref[k]) < TOL_G, (k, b)
+    assert len(orders) == 2
+
+
+def _run_taum(model, seeds, nwrap, every=1):
+    C = len(seeds)
+    g = AlfB200(model, n_chains=C, nwrap=nwrap); g.set_seeds(seeds); g.fields_set(); g.init_sweep()
+    g.taum_capture(every); g.sweep(1, 1)
+    cg = g.control()
+    for c, s in enumerate(seeds):
+        o = Oracle(model, nwrap=nwrap); o.ranset(s); o.fields_set(); o.init(); o.taum_capture(every); o.sweep(1)
+        a = g.get_taum(c); b = o.taum_get()
+        assert a.shape == b.shape and a.shape[0] >= 2
+        # freshly recomputed G(tau,0), G(0,tau), G(0,0), G(tau,tau) after every CGR2_2: north_star check (1) at 1e-10
+        af = g.get_taum_fresh(c); bf = o.taum_fresh_get()
+        assert af.shape == bf.shape and af.shape[0] == o.nstm()
+        for ist in range(af.shape[0]):
+            for w in range(4):
+                for nf in range(model.N_FL):
+                    assert relF(af[ist, w, nf], bf[ist, w, nf]) < TOL_G, (c, ist, w, nf, relF(af[ist, w, nf], bf[ist, w, nf]))
+        # what ObserT receives at every slice (wrapped in between: drifts like the reference's own "Precision tau", monitored not matched)
+        for it in range(a.shape[0]):
+            for w in range(4):
+                for nf in range(model.N_FL):
+                    assert relF(a[it, w, nf], b[it, w, nf]) < 1e-7, (c, it, w, nf, relF(a[it, w, nf], b[it, w, nf]))
+        assert np.array_equal(g.get_fields()[c], o.get_fields())
+        co = o.control()
+        assert co["NCG_tau"] * C == cg["NCG_tau"]
+    assert cg["XMAX_tau"] < 1e-5
+    g.close()
+
+
+def test_taum_config1():
+    """configs[0] with Ltau=1: G(tau,0), G(0,tau), G(0,0), G(tau,tau) for every tau vs the oracle's TAU_M."""
+    _run_taum(config1(), SEEDS[:3], nwrap=10)
+
+
+def test_taum_su2_complex():
+    _run_taum(config1(Mz=False), SEEDS[:2], nwrap=10, every=5)
+
+
+def test_taum_ragged():
+    _run_taum(hubbard_square(4, 4, 2.3, symm=False), SEEDS[:2], nwrap=7)
+
+
+def test_taum_config2():
+    """configs[1] (N_dim = 64, beta = 10): 2N = 128 extended system."""
+    _run_taum(config2(), SEEDS[:2], nwrap=10, every=10)
