@@ -7,7 +7,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "csrc", "alf_b200.cu")
 LIB = os.path.join(HERE, "libalf_b200.so")
-DEPS = ["alf_b200.cu", "alf_types.cuh", "alf_la.cuh", "alf_la_host.cuh", "alf_ops.cuh", "alf_update.cuh", "alf_taum.cuh", "alf_obs.cuh"]
+DEPS = ["alf_b200.cu", "alf_types.cuh", "alf_la.cuh", "alf_la_host.cuh", "alf_ops.cuh", "alf_update.cuh", "alf_update_fast.cuh", "alf_taum.cuh", "alf_obs.cuh"]
 
 
 def needs_build() -> bool:

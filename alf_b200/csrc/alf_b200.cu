@@ -10,6 +10,7 @@
 #include "alf_la_host.cuh"
 #include "alf_ops.cuh"
 #include "alf_update.cuh"
+#include "alf_update_fast.cuh"
 
 typedef std::complex<double> cd;
 static const double kEpsMachine = 2.220446049250313e-16;
@@ -218,6 +219,7 @@ struct Engine : EngineBase {
   std::vector<void*> owned;     // device allocations of the op lists
   bool dense_t = false; T* d_dense[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // fwd, inv, c, half, halfinv (N*N*F each)
   int KD = 16; size_t upd_smem = 0; int pw_l = 32, pw_r = 32;
+  bool fast_upd = false; int KDf = 0, ldxf = 0, iptf = 1; size_t fast_smem = 0;   // k_wrapgr_fast (all vertices diagonal, k = 1)
   // tau_m work
   T *GT0 = nullptr, *G0T = nullptr, *G00 = nullptr, *GTT = nullptr, *TMPG = nullptr; UdvDev<T> udvr2;
 
@@ -251,6 +253,31 @@ struct Engine : EngineBase {
     upd_smem = per_kd * KD + fixed;
     CK(cudaFuncSetAttribute(k_wrapgr<T, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)upd_smem));
     CK(cudaFuncSetAttribute(k_wrapgr<T, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)upd_smem));
+    // fast slice kernel: every vertex is a diagonal single-site operator with a discrete field
+    fast_upd = M > 0;
+    for (auto& o : h->opv) if (!(o.N == 1 && o.nnz == 1 && o.diag && (o.type == 1 || o.type == 2))) fast_upd = false;
+    for (int f = 0; f < F && fast_upd; ++f) {      // every site carries at most one vertex (its DL/DR entries are 1 until its own visit)
+      std::vector<char> seen(N, 0);
+      for (int n = 0; n < M; ++n) { int p = h->opv[n + (size_t)M * f].P[0]; if (seen[p]) fast_upd = false; seen[p] = 1; }
+    }
+    if (getenv("ALF_B200_GENERIC_UPDATE")) fast_upd = false;
+    if (fast_upd) {
+      ldxf = N; while (ldxf % 16 != 4) ++ldxf;
+      const size_t fixedf = (size_t)(2 * F * N + 6 * F * M + F * ALF_WIN * (ALF_WIN + 1) + 2 * ALF_WIN * F * ALF_WIN + ALF_WIN * F) * sizeof(T) + (size_t)2 * M * 8 + (size_t)F * M * 4 + (size_t)3 * M + 64;
+      const size_t perkd = (size_t)2 * F * ldxf * sizeof(T);
+      const size_t avail = 227 * 1024 - 1024;
+      if (fixedf + 4 * perkd > avail || F * N > 4 * 512) fast_upd = false;
+      else {
+        KDf = (int)((avail - fixedf) / perkd); KDf = (KDf / 4) * 4; if (KDf > 64) KDf = 64;
+        if (const char* e = getenv("ALF_B200_KD")) { int v = atoi(e); if (v >= 4 && v <= KDf) KDf = (v / 4) * 4; }
+        fast_smem = fixedf + perkd * KDf;
+        iptf = (F * N + 511) / 512; if (iptf > 1) iptf = 4;
+#define FAST_ATTR(IPT) do { CK(cudaFuncSetAttribute(k_wrapgr_fast<T, 1, IPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast_smem)); \
+                            CK(cudaFuncSetAttribute(k_wrapgr_fast<T, 0, IPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast_smem)); } while (0)
+        if (iptf == 1) FAST_ATTR(1); else FAST_ATTR(4);
+#undef FAST_ATTR
+      }
+    }
     // panel widths of the op-list kernel
     pw_l = 32; while ((size_t)N * (pw_l + 1) * sizeof(T) > 200 * 1024 && pw_l > 4) pw_l /= 2;
     pw_r = pw_l;
@@ -259,6 +286,28 @@ struct Engine : EngineBase {
     CK(cudaFuncSetAttribute(k_apply_ops<T, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ops_smem));
   }
   ~Engine() { for (void* p : owned) cudaFree(p); w.release(); }
+  // Optional (ALF_B200_L2_PERSIST=1): persisting-L2 access window over the batch of Green functions.  Measured on B200 with
+  // 148 chains x 1 MB (slightly more than L2): the slice kernel got SLOWER (1.28 ms vs 1.05 ms), so it is off by default.
+  double l2_persist_frac = -1.0; size_t l2_persist_bytes = 0;
+  void l2_window(const void* base, size_t bytes) {
+    if (l2_persist_frac < 0.0) {
+      l2_persist_frac = 0.0;
+      if (getenv("ALF_B200_L2_PERSIST")) {
+        int dev = h->device, maxp = 0, maxw = 0;
+        cudaDeviceGetAttribute(&maxp, cudaDevAttrMaxPersistingL2CacheSize, dev); cudaDeviceGetAttribute(&maxw, cudaDevAttrMaxAccessPolicyWindowSize, dev);
+        if (maxp > 0 && maxw > 0 && cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)maxp) == cudaSuccess) { l2_persist_bytes = (size_t)maxp; l2_persist_frac = 1.0; l2_maxw = (size_t)maxw; }
+        cudaGetLastError();
+      }
+    }
+    if (l2_persist_frac <= 0.0) return;
+    cudaStreamAttrValue a; memset(&a, 0, sizeof(a));
+    const size_t nb = std::min(bytes, l2_maxw);
+    a.accessPolicyWindow.base_ptr = const_cast<void*>(base); a.accessPolicyWindow.num_bytes = nb;
+    a.accessPolicyWindow.hitRatio = (float)std::min(1.0, 0.9 * (double)l2_persist_bytes / (double)nb);
+    a.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting; a.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    if (cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &a) != cudaSuccess) { cudaGetLastError(); l2_persist_frac = 0.0; }
+  }
+  size_t l2_maxw = 0;
   void sync() override { CK(cudaStreamSynchronize(st)); }
 
   // ---------------------------------------------------------------- model tables (Hop_mod_init + Op_set tables)
@@ -405,6 +454,7 @@ struct Engine : EngineBase {
       KL(KC_EW, st, k_ctl_accum<<<(C + 127) / 128, 128, 0, st>>>(d_cmp, F, h->d_ctl, 0, C));
     }
     std::swap(G, G2);
+    l2_window(G, sizeof(T) * n2 * NM);
     double* ang = nullptr;
     if (h->is_complex) { KL(KC_EW, st, k_op_phase<<<NM, 256, 0, st>>>(h->d_fields, d_angle_tab, F, M, L, d_angle)); ang = d_angle; }
     KL(KC_EW, st, k_phase_update<<<(C + 127) / 128, 128, 0, st>>>(d_z, ang, F, h->n_sun, h->d_phase, h->d_ctl, compare ? 1 : 0, C));
@@ -423,6 +473,13 @@ struct Engine : EngineBase {
   void launch_update(int up, int nt) {
     uint8_t* lg = nullptr;
     if (h->acclog_on && h->d_acclog && h->acclog_pos + M <= h->acclog_per_chain) { lg = h->d_acclog + (long)h->acclog_pos * C; h->acclog_pos += M; }
+    if (fast_upd) {
+#define FAST_LAUNCH(UPV, IPT) KL(KC_UPDATE, st, k_wrapgr_fast<T, UPV, IPT><<<C, 512, fast_smem, st>>>(G, N, F, h->n_sun, M, d_vops, ft, h->d_fields, L, nt, h->d_rng, h->d_phase, h->d_counters, KDf, ldxf, lg))
+      if (up) { if (iptf == 1) FAST_LAUNCH(1, 1); else FAST_LAUNCH(1, 4); }
+      else { if (iptf == 1) FAST_LAUNCH(0, 1); else FAST_LAUNCH(0, 4); }
+#undef FAST_LAUNCH
+      return;
+    }
     if (up) KL(KC_UPDATE, st, k_wrapgr<T, 1><<<C, 512, upd_smem, st>>>(G, N, F, h->n_sun, M, d_vops, ft, h->d_fields, L, nt, h->d_rng, h->d_phase, h->d_counters, KD, lg, 0));
     else KL(KC_UPDATE, st, k_wrapgr<T, 0><<<C, 512, upd_smem, st>>>(G, N, F, h->n_sun, M, d_vops, ft, h->d_fields, L, nt, h->d_rng, h->d_phase, h->d_counters, KD, lg, 0));
     CKL();
