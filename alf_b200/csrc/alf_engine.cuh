@@ -1,0 +1,699 @@
+#pragma once
+// alf_engine.cuh -- handle, model tables and the sweep schedule, templated on the arithmetic type (instantiated for double in
+// alf_inst_real.cu and for cplx in alf_inst_cplx.cu; the C-ABI of include/alf_b200.h lives in alf_b200.cu).
+// The schedule mirrors Prog/main.F90:446-457,589-631,714-887; every chain of the handle follows the same
+// stabilisation schedule, so each reference routine becomes ONE batched launch sequence over (chain, flavor).
+// There is no CPU fallback: without a CUDA device every entry point fails with ALF_ERROR_CUDA.
+#include <complex>
+#include <cstring>
+#include <algorithm>
+#include <memory>
+#include "../../include/alf_b200.h"
+#include "alf_la_host.cuh"
+#include "alf_ops.cuh"
+#include "alf_update.cuh"
+#include "alf_update_fast.cuh"
+
+typedef std::complex<double> cd;
+static const double kEpsMachine = 2.220446049250313e-16;
+
+// ------------------------------------------------------------------------------------------------ host model
+struct HostOp {
+  int N = 0, nnz = 0, diag = 0, type = 0; bool set = false;
+  std::vector<int> P; std::vector<cd> U; std::vector<double> E; cd g = 0, alpha = 0;
+};
+
+static void host_op_exp(cd g, const HostOp& op, std::vector<cd>& Mat) {   // Prog/Operator_mod.F90:491-529 (Kahan summation)
+  const int N = op.N; Mat.assign((size_t)N * N, cd(0, 0));
+  if (op.diag) { for (int n = 0; n < N; ++n) Mat[n + (size_t)n * N] = std::exp(g * op.E[n]); return; }
+  std::vector<cd> c((size_t)N * N, cd(0, 0));
+  for (int n = 0; n < N; ++n) {
+    cd Z = std::exp(g * op.E[n]);
+    for (int J = 0; J < N; ++J) {
+      cd Z1 = Z * std::conj(op.U[J + (size_t)n * N]);
+      for (int I = 0; I < N; ++I) {
+        cd y = Z1 * op.U[I + (size_t)n * N] - c[I + (size_t)J * N];
+        cd t = Mat[I + (size_t)J * N] + y;
+        c[I + (size_t)J * N] = (t - Mat[I + (size_t)J * N]) - y;
+        Mat[I + (size_t)J * N] = t;
+      }
+    }
+  }
+}
+
+struct HostExpT { int N; std::vector<int> P; std::vector<cd> mat, invmat, mat12, invmat12; bool active; };
+
+static void host_expopt(const HostOp& op, HostExpT& e) {   // Prog/OpTTypes_mod.F90:92-133, 203-234
+  const int N = op.N; e.N = N; e.P = op.P;
+  host_op_exp(op.g, op, e.mat); host_op_exp(-op.g, op, e.invmat); host_op_exp(op.g / 2.0, op, e.mat12); host_op_exp(-op.g / 2.0, op, e.invmat12);
+  bool real = std::abs(op.g.imag()) == 0.0;
+  for (auto& u : op.U) if (u.imag() != 0.0) real = false;
+  auto sym = [&](std::vector<cd>& M) {
+    if (real) for (auto& z : M) z = cd(z.real(), 0.0);
+    for (int i = 0; i < N; ++i) for (int j = i; j < N; ++j) M[i + (size_t)j * N] = (M[i + (size_t)j * N] + std::conj(M[j + (size_t)i * N])) / 2.0;
+    for (int i = 0; i < N; ++i) for (int j = i + 1; j < N; ++j) M[j + (size_t)i * N] = std::conj(M[i + (size_t)j * N]);   // 'U' storage
+  };
+  sym(e.mat); sym(e.invmat); sym(e.mat12); sym(e.invmat12);
+  double g2 = real ? op.g.real() * op.g.real() : std::norm(op.g);
+  e.active = g2 > kEpsMachine;
+}
+
+static double phi_st(int type, int s) {   // Prog/Fields_mod.F90:270-279
+  if (type == 1) return (double)s;
+  switch (s) { case -2: return -std::sqrt(2.0 * (3.0 + std::sqrt(6.0))); case -1: return -std::sqrt(2.0 * (3.0 - std::sqrt(6.0)));
+               case 1: return std::sqrt(2.0 * (3.0 - std::sqrt(6.0))); case 2: return std::sqrt(2.0 * (3.0 + std::sqrt(6.0))); }
+  return 0.0;
+}
+static double gama_st(int type, int s) {   // Fields_mod.F90:281-287
+  if (type != 2) return 1.0;
+  if (s == -2 || s == 2) return 1.0 - std::sqrt(6.0) / 3.0;
+  if (s == -1 || s == 1) return 1.0 + std::sqrt(6.0) / 3.0;
+  return 1.0;
+}
+
+template <typename T> T to_T(cd z);
+template <> inline double to_T<double>(cd z) { return z.real(); }
+template <> inline cplx to_T<cplx>(cd z) { return cplx(z.real(), z.imag()); }
+template <typename T> cd from_T(T v);
+template <> inline cd from_T<double>(double v) { return cd(v, 0.0); }
+template <> inline cd from_T<cplx>(cplx v) { return cd(v.x, v.y); }
+
+// one operator list under construction
+struct ListBuild {
+  int nvar = 1; std::vector<int> k, P, fidx; std::vector<cd> mat;   // mat: per op nvar*KMAX*KMAX
+  void add(int kk, const int* p, int fi, const std::vector<std::vector<cd>>& mats /* nvar matrices kk x kk col-major */) {
+    k.push_back(kk); fidx.push_back(fi);
+    for (int a = 0; a < ALF_KMAX; ++a) P.push_back(a < kk ? p[a] : 0);
+    for (int v = 0; v < nvar; ++v) for (int b = 0; b < ALF_KMAX; ++b) for (int a = 0; a < ALF_KMAX; ++a)
+      mat.push_back((a < kk && b < kk) ? mats[v][a + (size_t)b * kk] : cd(0, 0));
+  }
+  // greedy levels: consecutive operators with pairwise disjoint support (keeps the sequential semantics exactly)
+  std::vector<int> levels(int ndim) const {
+    std::vector<int> ls; ls.push_back(0); std::vector<char> used(ndim, 0);
+    for (size_t o = 0; o < k.size(); ++o) {
+      bool clash = false;
+      for (int a = 0; a < k[o]; ++a) if (used[P[o * ALF_KMAX + a]]) clash = true;
+      if (clash) { ls.push_back((int)o); std::fill(used.begin(), used.end(), 0); }
+      for (int a = 0; a < k[o]; ++a) used[P[o * ALF_KMAX + a]] = 1;
+    }
+    ls.push_back((int)k.size());
+    return ls;
+  }
+};
+
+// ------------------------------------------------------------------------------------------------ engine
+struct EngineBase {
+  virtual ~EngineBase() {}
+  virtual void init_sweep() = 0;
+  virtual void sweep(int ltau) = 0;
+  virtual void wrapgrup(int ntau) = 0;
+  virtual void wrapgrdo(int ntau) = 0;
+  virtual void wrapur(int ntau, int ntau1) = 0;
+  virtual void wrapul(int ntau1, int ntau) = 0;
+  virtual void udv_reset(int which, char side) = 0;
+  virtual void cgr_call(int nvar) = 0;
+  virtual void tau_m() = 0;
+  virtual void get_green(int chain, int nf, int symm, cd* out) = 0;
+  virtual void set_green(int chain, int nf, const cd* in) = 0;
+  virtual void get_udv(int which, int nst, int chain, int nf, cd* U, cd* D, cd* V) = 0;
+  virtual void hop_apply(int which, int nf, cd* A) = 0;
+  virtual void sync() = 0;
+};
+
+struct alf_b200_handle {
+  int ndim, n_fl, n_sun, ltrot, nwrap, n_opv, n_opt, symm, stab, n_chains, device;
+  std::vector<HostOp> opv, opt;
+  bool finalized = false, is_complex = false;
+  std::unique_ptr<EngineBase> eng;
+  std::string err;
+  cudaStream_t stream = 0;
+  Prof prof;
+  int8_t* pin_fields = nullptr;      // pinned staging buffer of sweep_host
+  // untyped device state shared with the engine
+  int8_t* d_fields = nullptr; uint64_t* d_rng = nullptr; cplx* d_phase = nullptr; unsigned long long* d_counters = nullptr;
+  double* d_ctl = nullptr;            // per chain: 0 XMEANG 1 XMAXG 2 NCG 3 XMAXP 4 XMEAN_tau 5 XMAX_tau 6 NCG_tau 7 flags(nan=1, unstable=2)
+  uint8_t* d_acclog = nullptr; long acclog_per_chain = 0; long acclog_pos = 0; bool acclog_on = false;
+  double* d_obs = nullptr; int obs_size = 0;
+  int taum_every = 0; std::vector<std::vector<cd>> taum_host, taum_fresh_host;   // per chain captured matrices
+  std::vector<int> types;            // operator type per n
+};
+
+static __global__ void k_ranset(uint64_t* rng, const int32_t* seeds, int n) {   // Ranset: random_wrap_mod.F90:52-80 with K = 8, N = 1
+  int c = blockIdx.x * blockDim.x + threadIdx.x; if (c >= n) return;
+  int32_t iseed0 = seeds[c], iseed = iseed0; int nn = 1;
+  if (iseed == 0) { iseed = 8752143; nn = 0; }
+  uint32_t v[8];
+  for (int i = 1; i <= 8; ++i) {
+    if (i <= nn) v[i - 1] = (uint32_t)iseed0;
+    else { long long res = (long long)iseed; res = 62089911LL * res + 4349LL; iseed = (int32_t)(uint32_t)(unsigned long long)res; v[i - 1] = (uint32_t)iseed; }
+  }
+  uint64_t s[4];
+  for (int i = 0; i < 4; ++i) s[i] = ((uint64_t)v[2 * i + 1] << 32) | (uint64_t)v[2 * i];
+  if ((s[0] | s[1] | s[2] | s[3]) == 0) s[0] = 0x9E3779B97F4A7C15ULL;
+  for (int i = 0; i < 4; ++i) rng[c * 4 + i] = s[i];
+}
+
+// Fields_set (Prog/Fields_mod.F90:588-610) for types < 4: f = +1, set to -1 if ranf() > 0.5; n fastest, then nt.
+static __global__ void k_fields_set(int8_t* fields, uint64_t* rng, int n_chains, long per_chain) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x; if (c >= n_chains) return;
+  Xoshiro r; r.s0 = rng[c * 4]; r.s1 = rng[c * 4 + 1]; r.s2 = rng[c * 4 + 2]; r.s3 = rng[c * 4 + 3];
+  int8_t* f = fields + (long)c * per_chain;
+  for (long i = 0; i < per_chain; ++i) f[i] = (r.ranf() > 0.5) ? -1 : 1;
+  rng[c * 4] = r.s0; rng[c * 4 + 1] = r.s1; rng[c * 4 + 2] = r.s2; rng[c * 4 + 3] = r.s3;
+}
+
+// sum over (n, nt) of Im(g alpha phi(s)) per (chain, flavor)  -- Op_phase, Prog/Operator_mod.F90:160-181
+static __global__ void k_op_phase(const int8_t* __restrict__ fields, const double* __restrict__ angle_tab, int F, int n_opv, int Ltrot, double* __restrict__ out) {
+  __shared__ double red[8];
+  const int b = blockIdx.x, chain = b / F, f = b % F;
+  const int8_t* fl = fields + (long)chain * Ltrot * n_opv;
+  double s = 0.0;
+  for (long e = threadIdx.x; e < (long)Ltrot * n_opv; e += blockDim.x) { int n = (int)(e % n_opv); s += angle_tab[((long)n * F + f) * ALF_NVAR + fl[e] + 2]; }
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) { for (int w = 1; w < (int)(blockDim.x >> 5); ++w) s += red[w]; out[b] = s; }
+}
+
+// Phase = (prod_f z_f e^{i angle_f})^N_SUN ; Control_PrecisionP (control_mod.F90:314-320)
+static __global__ void k_phase_update(const cplx* __restrict__ z, const double* __restrict__ angle, int F, int n_sun, cplx* __restrict__ phase,
+                               double* __restrict__ ctl, int compare, int n_chains) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x; if (c >= n_chains) return;
+  cplx Z = cplx(1.0, 0.0);
+  for (int f = 0; f < F; ++f) { cplx zz = z[c * F + f]; if (angle) { double a = angle[c * F + f]; zz = zz * cplx(cos(a), sin(a)); } Z = Z * zz; }
+  cplx Zn = Z; for (int q = 1; q < n_sun; ++q) Zn = Zn * Z;
+  if (compare) { double x = abs_(Zn - phase[c]); if (x > ctl[c * 8 + 3]) ctl[c * 8 + 3] = x; }
+  phase[c] = Zn;
+}
+
+// fold k_compare output into the per-chain accumulators; which = 0: Control_PrecisionG, 1: Control_Precision_tau
+static __global__ void k_ctl_accum(const double* __restrict__ cmp, int F, double* __restrict__ ctl, int which, int n_chains) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x; if (c >= n_chains) return;
+  for (int f = 0; f < F; ++f) {
+    const double* o = cmp + (long)(c * F + f) * 3;
+    if (which == 0) {
+      ctl[c * 8 + 0] += o[1]; if (o[0] > ctl[c * 8 + 1]) ctl[c * 8 + 1] = o[0]; ctl[c * 8 + 2] += 1.0;
+      int flags = (int)ctl[c * 8 + 7]; if (o[2] != 0.0) flags |= 1; if (o[0] > 10.0) flags |= 2; ctl[c * 8 + 7] = (double)flags;
+    } else { ctl[c * 8 + 4] += o[1]; if (o[0] > ctl[c * 8 + 5]) ctl[c * 8 + 5] = o[0]; ctl[c * 8 + 6] += 1.0; }
+  }
+}
+
+// G0T = -(1 - G)  (tau_m_mod.F90:96-104)
+template <typename T>
+__global__ void k_g0t_init(T* __restrict__ G0T, const T* __restrict__ G, long sM, int n) {
+  const int b = blockIdx.y; G0T += (long)b * sM; G += (long)b * sM;
+  for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < (long)n * n; e += (long)gridDim.x * blockDim.x) {
+    int i = (int)(e % n), j = (int)(e / n);
+    G0T[e] = G[e] - ((i == j) ? one_<T>() : zero_<T>());
+  }
+}
+
+template <typename T>
+struct Engine : EngineBase {
+  alf_b200_handle* h;
+  int C, F, N, L, M, S, NM; long n2; cudaStream_t st;
+  std::vector<int> stab_nt;
+  T *G = nullptr, *G2 = nullptr;
+  UdvDev<T> udvl, udvr; std::vector<UdvDev<T>> udvst;
+  LaWork<T> w;
+  cplx* d_z = nullptr; double* d_angle = nullptr; double* d_angle_tab = nullptr; double* d_cmp = nullptr;
+  VopDev<T>* d_vops = nullptr; ModelDev md; FieldTabDev ft;
+  std::vector<void*> owned;     // device allocations of the op lists
+  bool dense_t = false; T* d_dense[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // fwd, inv, c, half, halfinv (N*N*F each)
+  int KD = 16; size_t upd_smem = 0; int pw_l = 32, pw_r = 32;
+  bool fast_upd = false; int KDf = 0, ldxf = 0, iptf = 1; size_t fast_smem = 0;   // k_wrapgr_fast (all vertices diagonal, k = 1)
+  // tau_m work
+  T *GT0 = nullptr, *G0T = nullptr, *G00 = nullptr, *GTT = nullptr, *TMPG = nullptr; UdvDev<T> udvr2;
+
+  template <typename X> X* dalloc(size_t n) { X* p = nullptr; CK(cudaMalloc(&p, sizeof(X) * (n ? n : 1))); owned.push_back(p); return p; }
+  template <typename X> X* dupload(const std::vector<X>& v) { X* p = dalloc<X>(v.size()); if (!v.empty()) CK(cudaMemcpy(p, v.data(), sizeof(X) * v.size(), cudaMemcpyHostToDevice)); return p; }
+  UdvDev<T> alloc_udv() { UdvDev<T> u; u.U = dalloc<T>(n2 * NM); u.V = dalloc<T>(n2 * NM); u.D = dalloc<double>((size_t)N * NM); u.det = dalloc<cplx>(NM); return u; }
+
+  OpListDev upload_list(const ListBuild& lb) {
+    OpListDev d; d.n_ops = (int)lb.k.size(); d.nvar = lb.nvar;
+    std::vector<int> ls = lb.levels(N); d.n_levels = (int)ls.size() - 1;
+    d.level_start = dupload(ls); d.k = dupload(lb.k); d.P = dupload(lb.P); d.fidx = dupload(lb.fidx);
+    std::vector<T> m(lb.mat.size()); for (size_t i = 0; i < m.size(); ++i) m[i] = to_T<T>(lb.mat[i]);
+    d.mat = dupload(m);
+    return d;
+  }
+
+  Engine(alf_b200_handle* hh) : h(hh) {
+    C = h->n_chains; F = h->n_fl; N = h->ndim; L = h->ltrot; M = h->n_opv; NM = C * F; n2 = (long)N * N; st = h->stream;
+    if (F > ALF_FMAX) throw CudaError("more than ALF_FMAX flavors");
+    S = (L % h->nwrap == 0) ? L / h->nwrap : L / h->nwrap + 1;                 // main.F90:446-457
+    stab_nt.assign(S + 1, 0); for (int n = 1; n < S; ++n) stab_nt[n] = h->nwrap * n; stab_nt[S] = L;
+    build_model();
+    G = dalloc<T>(n2 * NM); G2 = dalloc<T>(n2 * NM);
+    udvl = alloc_udv(); udvr = alloc_udv(); udvst.resize(S); for (int s = 0; s < S; ++s) udvst[s] = alloc_udv();
+    w.alloc(N, NM, st);
+    d_z = dalloc<cplx>(NM); d_angle = dalloc<double>(NM); d_cmp = dalloc<double>((size_t)NM * 3);
+    // update kernel configuration: as many delayed columns as fit in ~200 KB of shared memory
+    size_t per_kd = (size_t)F * 2 * (N + 2) * sizeof(T), fixed = (size_t)F * 3 * N * sizeof(T) + 256;
+    KD = (int)((200 * 1024 - fixed) / per_kd); if (KD > 32) KD = 32; if (KD < 4) throw CudaError("Ndim too large for the update kernel's shared-memory factors");
+    KD = (KD / 4) * 4;
+    upd_smem = per_kd * KD + fixed;
+    CK(cudaFuncSetAttribute(k_wrapgr<T, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)upd_smem));
+    CK(cudaFuncSetAttribute(k_wrapgr<T, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)upd_smem));
+    // fast slice kernel: every vertex is a diagonal single-site operator with a discrete field
+    fast_upd = M > 0;
+    for (auto& o : h->opv) if (!(o.N == 1 && o.nnz == 1 && o.diag && (o.type == 1 || o.type == 2))) fast_upd = false;
+    for (int f = 0; f < F && fast_upd; ++f) {      // every site carries at most one vertex (its DL/DR entries are 1 until its own visit)
+      std::vector<char> seen(N, 0);
+      for (int n = 0; n < M; ++n) { int p = h->opv[n + (size_t)M * f].P[0]; if (seen[p]) fast_upd = false; seen[p] = 1; }
+    }
+    if (getenv("ALF_B200_GENERIC_UPDATE")) fast_upd = false;
+    if (fast_upd) {
+      ldxf = N; while (ldxf % 16 != 4) ++ldxf;
+      const size_t fixedf = (size_t)(2 * F * N + 6 * F * M + F * ALF_WIN * (ALF_WIN + 1) + 2 * ALF_WIN * F * ALF_WIN + ALF_WIN * F) * sizeof(T) + (size_t)2 * M * 8 + (size_t)F * M * 4 + (size_t)3 * M + 64;
+      const size_t perkd = (size_t)2 * F * ldxf * sizeof(T);
+      const size_t avail = 227 * 1024 - 1024;
+      if (fixedf + 4 * perkd > avail || F * N > 4 * 512) fast_upd = false;
+      else {
+        KDf = (int)((avail - fixedf) / perkd); KDf = (KDf / 4) * 4; if (KDf > 64) KDf = 64;
+        if (const char* e = getenv("ALF_B200_KD")) { int v = atoi(e); if (v >= 4 && v <= KDf) KDf = (v / 4) * 4; }
+        fast_smem = fixedf + perkd * KDf;
+        iptf = (F * N + 511) / 512; if (iptf > 1) iptf = 4;
+#define FAST_ATTR(IPT) do { CK(cudaFuncSetAttribute(k_wrapgr_fast<T, 1, IPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast_smem)); \
+                            CK(cudaFuncSetAttribute(k_wrapgr_fast<T, 0, IPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast_smem)); } while (0)
+        if (iptf == 1) FAST_ATTR(1); else FAST_ATTR(4);
+#undef FAST_ATTR
+      }
+    }
+    // panel widths of the op-list kernel
+    pw_l = 32; while ((size_t)N * (pw_l + 1) * sizeof(T) > 200 * 1024 && pw_l > 4) pw_l /= 2;
+    pw_r = pw_l;
+    size_t ops_smem = (size_t)N * (pw_l + 1) * sizeof(T);
+    CK(cudaFuncSetAttribute(k_apply_ops<T, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ops_smem));
+    CK(cudaFuncSetAttribute(k_apply_ops<T, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ops_smem));
+  }
+  ~Engine() { for (void* p : owned) cudaFree(p); w.release(); }
+  // Optional (ALF_B200_L2_PERSIST=1): persisting-L2 access window over the batch of Green functions.  Measured on B200 with
+  // 148 chains x 1 MB (slightly more than L2): the slice kernel got SLOWER (1.28 ms vs 1.05 ms), so it is off by default.
+  double l2_persist_frac = -1.0; size_t l2_persist_bytes = 0;
+  void l2_window(const void* base, size_t bytes) {
+    if (l2_persist_frac < 0.0) {
+      l2_persist_frac = 0.0;
+      if (getenv("ALF_B200_L2_PERSIST")) {
+        int dev = h->device, maxp = 0, maxw = 0;
+        cudaDeviceGetAttribute(&maxp, cudaDevAttrMaxPersistingL2CacheSize, dev); cudaDeviceGetAttribute(&maxw, cudaDevAttrMaxAccessPolicyWindowSize, dev);
+        if (maxp > 0 && maxw > 0 && cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)maxp) == cudaSuccess) { l2_persist_bytes = (size_t)maxp; l2_persist_frac = 1.0; l2_maxw = (size_t)maxw; }
+        cudaGetLastError();
+      }
+    }
+    if (l2_persist_frac <= 0.0) return;
+    cudaStreamAttrValue a; memset(&a, 0, sizeof(a));
+    const size_t nb = std::min(bytes, l2_maxw);
+    a.accessPolicyWindow.base_ptr = const_cast<void*>(base); a.accessPolicyWindow.num_bytes = nb;
+    a.accessPolicyWindow.hitRatio = (float)std::min(1.0, 0.9 * (double)l2_persist_bytes / (double)nb);
+    a.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting; a.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    if (cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &a) != cudaSuccess) { cudaGetLastError(); l2_persist_frac = 0.0; }
+  }
+  size_t l2_maxw = 0;
+  void sync() override { CK(cudaStreamSynchronize(st)); }
+
+  // ---------------------------------------------------------------- model tables (Hop_mod_init + Op_set tables)
+  void build_model() {
+    // hopping
+    std::vector<HostExpT> ex((size_t)h->n_opt * F);
+    int maxk = 0;
+    for (int nc = 0; nc < h->n_opt; ++nc) for (int f = 0; f < F; ++f) { host_expopt(h->opt[nc + (size_t)h->n_opt * f], ex[nc + (size_t)h->n_opt * f]); maxk = std::max(maxk, h->opt[nc + (size_t)h->n_opt * f].N); }
+    dense_t = maxk > ALF_KMAX;
+    auto tr = [](const std::vector<cd>& A, int k) { std::vector<cd> B(A.size()); for (int i = 0; i < k; ++i) for (int j = 0; j < k; ++j) B[i + (size_t)j * k] = A[j + (size_t)i * k]; return B; };
+    auto one = [](const std::vector<cd>& m) { return std::vector<std::vector<cd>>(1, m); };
+    for (int f = 0; f < F; ++f) {
+      ListBuild fwd, inv, cc, half, rfwd, rinv, rhalfinv;
+      if (!dense_t) {
+        for (int nc = h->n_opt - 1; nc >= 0; --nc) { const HostExpT& e = ex[nc + (size_t)h->n_opt * f]; if (!e.active) continue;
+          fwd.add(e.N, e.P.data(), -1, one(e.mat)); half.add(e.N, e.P.data(), -1, one(e.mat12)); rinv.add(e.N, e.P.data(), -1, one(tr(e.invmat, e.N))); rhalfinv.add(e.N, e.P.data(), -1, one(tr(e.invmat12, e.N))); }
+        for (int nc = 0; nc < h->n_opt; ++nc) { const HostExpT& e = ex[nc + (size_t)h->n_opt * f]; if (!e.active) continue;
+          inv.add(e.N, e.P.data(), -1, one(e.invmat)); cc.add(e.N, e.P.data(), -1, one(e.mat)); rfwd.add(e.N, e.P.data(), -1, one(tr(e.mat, e.N))); }
+      }
+      md.lists[L_TL_FWD][f] = upload_list(fwd); md.lists[L_TL_INV][f] = upload_list(inv); md.lists[L_TL_C][f] = upload_list(cc);
+      md.lists[L_TL_HALF][f] = upload_list(half); md.lists[L_TR_FWD][f] = upload_list(rfwd); md.lists[L_TR_INV][f] = upload_list(rinv);
+      md.lists[L_TR_HALFINV][f] = upload_list(rhalfinv);
+    }
+    if (dense_t) {
+      // products of the (few) dense factors in the orders of Hop_mod.F90:143-250
+      for (int q = 0; q < 5; ++q) d_dense[q] = dalloc<T>(n2 * F);
+      for (int f = 0; f < F; ++f) {
+        auto eye = [&]() { std::vector<cd> I(n2, cd(0, 0)); for (int i = 0; i < N; ++i) I[i + (size_t)i * N] = 1; return I; };
+        auto lmul = [&](const std::vector<cd>& A, std::vector<cd>& X) { std::vector<cd> Y(n2, cd(0, 0)); for (int j = 0; j < N; ++j) for (int k = 0; k < N; ++k) { cd x = X[k + (size_t)j * N]; if (x == cd(0, 0)) continue; for (int i = 0; i < N; ++i) Y[i + (size_t)j * N] += A[i + (size_t)k * N] * x; } X.swap(Y); };
+        auto embed = [&](const HostExpT& e, const std::vector<cd>& m) { std::vector<cd> A = eye(); for (int a = 0; a < e.N; ++a) for (int b = 0; b < e.N; ++b) A[e.P[a] + (size_t)e.P[b] * N] = m[a + (size_t)b * e.N]; return A; };
+        std::vector<cd> Ef = eye(), Ei = eye(), Ec = eye(), Eh = eye(), Ehi = eye();
+        for (int nc = h->n_opt - 1; nc >= 0; --nc) { const HostExpT& e = ex[nc + (size_t)h->n_opt * f]; if (!e.active) continue; lmul(embed(e, e.mat), Ef); lmul(embed(e, e.mat12), Eh); }
+        for (int nc = 0; nc < h->n_opt; ++nc) { const HostExpT& e = ex[nc + (size_t)h->n_opt * f]; if (!e.active) continue; lmul(embed(e, e.invmat), Ei); lmul(embed(e, e.mat), Ec); }
+        // right products: In * inv_N ... inv_1  (mmthl_m1) equals Ei as a matrix; In * mat_1 ... mat_N equals Ef.  Half inverse:
+        { std::vector<cd> X = eye(); for (int nc = 0; nc < h->n_opt; ++nc) { const HostExpT& e = ex[nc + (size_t)h->n_opt * f]; if (!e.active) continue; lmul(embed(e, e.invmat12), X); } Ehi = X; }
+        std::vector<cd>* src[5] = {&Ef, &Ei, &Ec, &Eh, &Ehi};
+        for (int q = 0; q < 5; ++q) { std::vector<T> t(n2); for (long i = 0; i < n2; ++i) t[i] = to_T<T>((*src[q])[i]); CK(cudaMemcpy(d_dense[q] + n2 * f, t.data(), sizeof(T) * n2, cudaMemcpyHostToDevice)); }
+      }
+    }
+    // vertices
+    std::vector<VopDev<T>> vops((size_t)M * F);
+    std::vector<double> angle_tab((size_t)M * F * ALF_NVAR, 0.0);
+    for (int f = 0; f < F; ++f) {
+      ListBuild vn, vc, vri; vn.nvar = vc.nvar = vri.nvar = ALF_NVAR;
+      std::vector<std::vector<std::vector<cd>>> mexp(M);   // [n][var] k x k
+      for (int n = 0; n < M; ++n) {
+        const HostOp& op = h->opv[n + (size_t)M * f]; const int k = op.N;
+        if (k > ALF_KMAX) throw CudaError("interaction vertex with N > ALF_KMAX is not supported in this build");
+        VopDev<T>& v = vops[(size_t)n * F + f];
+        std::memset(&v, 0, sizeof(v));
+        v.k = k; v.nnz = op.nnz; v.diag = op.diag; v.type = op.type;
+        for (int a = 0; a < k; ++a) v.P[a] = op.P[a];
+        for (int a = 0; a < k; ++a) for (int b = 0; b < k; ++b) v.U[a + b * ALF_KMAX] = to_T<T>(op.U[a + (size_t)b * k]);
+        mexp[n].resize(ALF_NVAR);
+        for (int var = 0; var < ALF_NVAR; ++var) {
+          const int s = var - 2; const bool valid = (s != 0) && (std::abs(s) <= op.type);
+          const double ph = valid ? phi_st(op.type, s) : 0.0;
+          for (int a = 0; a < ALF_KMAX; ++a) v.E_exp[a][var] = to_T<T>((a < op.nnz && valid) ? std::exp(op.g * op.E[a] * ph) : cd(1, 0));
+          host_op_exp(op.g * ph, op, mexp[n][var]);
+          angle_tab[((size_t)n * F + f) * ALF_NVAR + var] = valid ? (op.g * op.alpha * ph).imag() : 0.0;
+          for (int var2 = 0; var2 < ALF_NVAR; ++var2) {
+            const int s2 = var2 - 2; const bool valid2 = (s2 != 0) && (std::abs(s2) <= op.type);
+            const double dphi = (valid && valid2) ? (phi_st(op.type, s2) - ph) : 0.0;
+            for (int a = 0; a < ALF_KMAX; ++a) v.delta[a][var][var2] = to_T<T>((a < op.nnz) ? std::exp(op.g * dphi * op.E[a]) - 1.0 : cd(0, 0));
+            v.expalpha[var][var2] = to_T<T>(std::exp(op.g * dphi * op.alpha));
+          }
+        }
+      }
+      auto ct = [](const std::vector<cd>& A, int k) { std::vector<cd> B(A.size()); for (int i = 0; i < k; ++i) for (int j = 0; j < k; ++j) B[i + (size_t)j * k] = std::conj(A[j + (size_t)i * k]); return B; };
+      for (int n = 0; n < M; ++n) { const HostOp& op = h->opv[n + (size_t)M * f]; if (std::abs(op.g) < kEpsMachine) continue;   // quick return, Operator_mod.F90:576,668
+        vn.add(op.N, op.P.data(), n, mexp[n]);
+        std::vector<std::vector<cd>> mi(ALF_NVAR); for (int var = 0; var < ALF_NVAR; ++var) mi[var] = tr(mexp[n][ALF_NVAR - 1 - var], op.N);   // exp(-phi g O)^T
+        vri.add(op.N, op.P.data(), n, mi); }
+      for (int n = M - 1; n >= 0; --n) { const HostOp& op = h->opv[n + (size_t)M * f]; if (std::abs(op.g) < kEpsMachine) continue;
+        std::vector<std::vector<cd>> mc(ALF_NVAR); for (int var = 0; var < ALF_NVAR; ++var) mc[var] = ct(mexp[n][var], op.N);
+        vc.add(op.N, op.P.data(), n, mc); }
+      md.lists[L_VL_N][f] = upload_list(vn); md.lists[L_VL_C][f] = upload_list(vc); md.lists[L_VR_INV][f] = upload_list(vri);
+    }
+    d_vops = dupload(vops); d_angle_tab = dupload(angle_tab);
+    for (int t = 0; t < 3; ++t) for (int var = 0; var < ALF_NVAR; ++var) ft.gama[t][var] = gama_st(t, var - 2);
+    const int fl[5][4] = {{0, -1, 1, 2}, {0, 1, 2, -2}, {0, 0, 0, 0}, {0, 2, -2, -1}, {0, -2, -1, 1}};   // Fields_mod.F90:289-301
+    for (int a = 0; a < 5; ++a) for (int b = 0; b < 4; ++b) ft.flip[a][b] = fl[a][b];
+  }
+
+  // ---------------------------------------------------------------- op-list launches
+  void apply_ops(T* Mx, int side, int mode, int nt_a, int nt_b) {
+    const int pw = side == 0 ? pw_l : pw_r;
+    dim3 grid((N + pw - 1) / pw, NM);
+    size_t smem = (size_t)N * (pw + 1) * sizeof(T);
+    if (side == 0) KL(KC_OPS, st, k_apply_ops<T, 0><<<grid, 256, smem, st>>>(Mx, n2, N, N, pw, md, F, mode, nt_a, nt_b, h->d_fields, L, M));
+    else KL(KC_OPS, st, k_apply_ops<T, 1><<<grid, 256, smem, st>>>(Mx, n2, N, N, pw, md, F, mode, nt_a, nt_b, h->d_fields, L, M));
+    CKL();
+  }
+  // dense hopping: Mx <- E * Mx (left) or Mx * E (right), E per flavor (batch stride 0 inside a flavor is emulated per flavor)
+  void dense_mult(T* Mx, int which, bool left) {
+    for (int f = 0; f < F; ++f) {
+      // matrices of flavor f are at b = c*F + f : stride F*n2 over chains
+      if (left) gemm<T, 0, 0, 0>(st, N, N, N, d_dense[which] + n2 * f, N, 0, Mx + n2 * f, N, n2 * F, w.W[3] + n2 * f, N, n2 * F, C);
+      else gemm<T, 0, 0, 0>(st, N, N, N, Mx + n2 * f, N, n2 * F, d_dense[which] + n2 * f, N, 0, w.W[3] + n2 * f, N, n2 * F, C);
+    }
+    CK(cudaMemcpyAsync(Mx, w.W[3], sizeof(T) * n2 * NM, cudaMemcpyDeviceToDevice, st));
+  }
+  // Hop_mod entry points on a batch of N x N matrices
+  void mmthr(T* Mx) { if (dense_t) dense_mult(Mx, 0, true); else apply_ops(Mx, 0, MODE_TL_FWD, 0, 0); }
+  void mmthr_m1(T* Mx) { if (dense_t) dense_mult(Mx, 1, true); else apply_ops(Mx, 0, MODE_TL_INV, 0, 0); }
+  void mmthl(T* Mx) { if (dense_t) dense_mult(Mx, 0, false); else apply_ops(Mx, 1, MODE_TR_FWD, 0, 0); }
+  void mmthl_m1(T* Mx) { if (dense_t) dense_mult(Mx, 1, false); else apply_ops(Mx, 1, MODE_TR_INV, 0, 0); }
+  void mmthlc(T* Mx) { if (dense_t) dense_mult(Mx, 2, true); else apply_ops(Mx, 0, MODE_TL_C, 0, 0); }
+  void hop_symm(T* Mx) { if (dense_t) { dense_mult(Mx, 3, true); dense_mult(Mx, 4, false); } else { apply_ops(Mx, 0, MODE_TL_HALF, 0, 0); apply_ops(Mx, 1, MODE_TR_HALFINV, 0, 0); } }
+
+  void set_udv_identity(UdvDev<T>& u) {   // reset_UDV_state, udv_state_mod.F90:224-249
+    dim3 eg(ew_blocks(n2), NM);
+    KL(KC_EW, st, k_set_identity<T><<<eg, 256, 0, st>>>(u.U, N, n2, N, N)); KL(KC_EW, st, k_set_identity<T><<<eg, 256, 0, st>>>(u.V, N, n2, N, N));
+    KL(KC_EW, st, k_fill_double<<<ew_blocks((long)N * NM), 256, 0, st>>>(u.D, (long)N * NM, 1.0));
+    KL(KC_EW, st, k_fill_cplx<<<ew_blocks(NM), 256, 0, st>>>(u.det, NM, cplx(1.0, 0.0)));
+  }
+  void copy_udv(UdvDev<T>& dst, const UdvDev<T>& src) {   // assign_UDV_state, udv_state_mod.F90:300-330
+    CK(cudaMemcpyAsync(dst.U, src.U, sizeof(T) * n2 * NM, cudaMemcpyDeviceToDevice, st));
+    CK(cudaMemcpyAsync(dst.V, src.V, sizeof(T) * n2 * NM, cudaMemcpyDeviceToDevice, st));
+    CK(cudaMemcpyAsync(dst.D, src.D, sizeof(double) * N * NM, cudaMemcpyDeviceToDevice, st));
+    CK(cudaMemcpyAsync(dst.det, src.det, sizeof(cplx) * NM, cudaMemcpyDeviceToDevice, st));
+  }
+  void udv_reset(int which, char side) override { (void)side; set_udv_identity(which == 0 ? udvl : udvr); }
+
+  // WRAPUR (Prog/wrapur_mod.F90:102-123) / WRAPUL (Prog/wrapul_mod.F90:108-129) on a batch
+  void wrapur_on(UdvDev<T>& u, int ntau, int ntau1) {
+    if (!dense_t) apply_ops(u.U, 0, MODE_WRAPUR, ntau + 1, ntau1);
+    else for (int nt = ntau + 1; nt <= ntau1; ++nt) { dense_mult(u.U, 0, true); apply_ops(u.U, 0, MODE_WRAPUR, nt, nt); }
+    la_decompose<T>(w, u, 'r');
+  }
+  void wrapul_on(UdvDev<T>& u, int ntau1, int ntau) {
+    if (!dense_t) apply_ops(u.U, 0, MODE_WRAPUL, ntau + 1, ntau1);
+    else for (int nt = ntau1; nt >= ntau + 1; --nt) { apply_ops(u.U, 0, MODE_WRAPUL, nt, nt); dense_mult(u.U, 2, true); }
+    la_decompose<T>(w, u, 'l');
+  }
+  void wrapur(int ntau, int ntau1) override { wrapur_on(udvr, ntau, ntau1); }
+  void wrapul(int ntau1, int ntau) override { wrapul_on(udvl, ntau1, ntau); }
+
+  // CGR + Op_phase + Control_PrecisionG/P  (main.F90:742-753)
+  void cgr_and_phase(int nvar, bool compare) {
+    la_cgr<T>(w, nvar, h->stab, udvr, udvl, G2, d_z);
+    if (compare) {
+      KL(KC_EW, st, k_compare<T><<<NM, 256, 0, st>>>(G2, G, n2, n2, d_cmp));
+      KL(KC_EW, st, k_ctl_accum<<<(C + 127) / 128, 128, 0, st>>>(d_cmp, F, h->d_ctl, 0, C));
+    }
+    std::swap(G, G2);
+    l2_window(G, sizeof(T) * n2 * NM);
+    double* ang = nullptr;
+    if (h->is_complex) { KL(KC_EW, st, k_op_phase<<<NM, 256, 0, st>>>(h->d_fields, d_angle_tab, F, M, L, d_angle)); ang = d_angle; }
+    KL(KC_EW, st, k_phase_update<<<(C + 127) / 128, 128, 0, st>>>(d_z, ang, F, h->n_sun, h->d_phase, h->d_ctl, compare ? 1 : 0, C));
+  }
+  void cgr_call(int nvar) override { cgr_and_phase(nvar, false); }
+
+  // WRAPGRUP / WRAPGRDO (Prog/Wrapgr_mod.F90:81-157, 160-243)
+  void wrapgrup(int ntau) override {
+    mmthr(G); mmthl_m1(G);
+    launch_update(1, ntau + 1);
+  }
+  void wrapgrdo(int ntau) override {
+    launch_update(0, ntau);
+    mmthl(G); mmthr_m1(G);
+  }
+  void launch_update(int up, int nt) {
+    uint8_t* lg = nullptr;
+    if (h->acclog_on && h->d_acclog && h->acclog_pos + M <= h->acclog_per_chain) { lg = h->d_acclog + (long)h->acclog_pos * C; h->acclog_pos += M; }
+    if (fast_upd) {
+#define FAST_LAUNCH(UPV, IPT) KL(KC_UPDATE, st, k_wrapgr_fast<T, UPV, IPT><<<C, 512, fast_smem, st>>>(G, N, F, h->n_sun, M, d_vops, ft, h->d_fields, L, nt, h->d_rng, h->d_phase, h->d_counters, KDf, ldxf, lg))
+      if (up) { if (iptf == 1) FAST_LAUNCH(1, 1); else FAST_LAUNCH(1, 4); }
+      else { if (iptf == 1) FAST_LAUNCH(0, 1); else FAST_LAUNCH(0, 4); }
+#undef FAST_LAUNCH
+      return;
+    }
+    if (up) KL(KC_UPDATE, st, k_wrapgr<T, 1><<<C, 512, upd_smem, st>>>(G, N, F, h->n_sun, M, d_vops, ft, h->d_fields, L, nt, h->d_rng, h->d_phase, h->d_counters, KD, lg, 0));
+    else KL(KC_UPDATE, st, k_wrapgr<T, 0><<<C, 512, upd_smem, st>>>(G, N, F, h->n_sun, M, d_vops, ft, h->d_fields, L, nt, h->d_rng, h->d_phase, h->d_counters, KD, lg, 0));
+    CKL();
+  }
+
+  // main.F90:589-631
+  void init_sweep() override {
+    set_udv_identity(udvl); set_udv_identity(udvr); set_udv_identity(udvst[S - 1]);
+    for (int NST = S - 1; NST >= 1; --NST) { wrapul_on(udvl, stab_nt[NST + 1], stab_nt[NST]); copy_udv(udvst[NST - 1], udvl); }
+    wrapul_on(udvl, stab_nt[1], 0);
+    cgr_and_phase(1, false);
+  }
+
+  void measure_hook(int ntau) { (void)ntau; }   // device-side Obser: see alf_obs (next row of SURVEY 8f)
+
+  // main.F90:714-887
+  void sweep(int ltau) override {
+    set_udv_identity(udvr);
+    int NST = 1;
+    for (int NTAU = 0; NTAU <= L - 1; ++NTAU) {
+      const int NTAU1 = NTAU + 1;
+      wrapgrup(NTAU);
+      if (NTAU1 == stab_nt[NST]) {
+        wrapur_on(udvr, stab_nt[NST - 1], NTAU1);
+        std::swap(udvl, udvst[NST - 1]);            // udvl = udvst(NST) (old udvl content is dead)
+        copy_udv(udvst[NST - 1], udvr);             // udvst(NST) = udvr
+        cgr_and_phase(NTAU1 > L / 2 ? 2 : 1, true);
+        NST++;
+      }
+      measure_hook(NTAU1);
+    }
+    set_udv_identity(udvl);
+    NST = S - 1;
+    for (int NTAU = L; NTAU >= 1; --NTAU) {
+      const int NTAU1 = NTAU - 1;
+      wrapgrdo(NTAU);
+      measure_hook(NTAU1);
+      if (NST >= 0 && stab_nt[NST] == NTAU1 && NTAU1 != 0) {
+        wrapul_on(udvl, stab_nt[NST + 1], NTAU1);
+        std::swap(udvr, udvst[NST - 1]);            // udvr = udvst(NST)
+        copy_udv(udvst[NST - 1], udvl);             // udvst(NST) = udvl
+        cgr_and_phase(NTAU1 > L / 2 ? 2 : 1, true);
+        NST--;
+      }
+    }
+    wrapul_on(udvl, stab_nt[1], stab_nt[0]);
+    set_udv_identity(udvr);
+    cgr_and_phase(1, true);
+    set_udv_identity(udvst[S - 1]);
+    if (ltau == 1) tau_m();
+  }
+
+  // ---------------------------------------------------------------- TAU_M (Prog/tau_m_mod.F90:56-211) for all chains
+  LaWork<T> w2; bool w2_ready = false; T* tmN[4] = {nullptr, nullptr, nullptr, nullptr}; int* d_first = nullptr; T* capbuf = nullptr;
+  void taum_alloc() {
+    if (w2_ready) return;
+    w2.alloc(2 * N, NM, st);
+    GT0 = dalloc<T>(n2 * NM); G0T = dalloc<T>(n2 * NM); G00 = dalloc<T>(n2 * NM); GTT = dalloc<T>(n2 * NM);
+    for (int q = 0; q < 4; ++q) tmN[q] = dalloc<T>(n2 * NM);
+    udvr2 = alloc_udv(); d_first = dalloc<int>(NM); capbuf = dalloc<T>(n2 * NM);
+    w2_ready = true;
+  }
+  void taum_capture(int nt, bool fresh = false) {     // what ham%ObserT receives (tau_m_mod.F90:115-124,151-177); test support only
+    if (!h->taum_every) return;
+    if (!fresh && h->taum_every > 1 && (nt % h->taum_every) != 0) return;
+    std::vector<std::vector<cd>>& dst = fresh ? h->taum_fresh_host : h->taum_host;
+    if (dst.size() != (size_t)C) dst.assign(C, std::vector<cd>());
+    T* arr[4] = {GT0, G0T, G00, GTT};
+    std::vector<T> host(n2 * NM);
+    std::vector<std::vector<cd>> part(C, std::vector<cd>((size_t)4 * F * n2));
+    for (int q = 0; q < 4; ++q) {
+      CK(cudaMemcpyAsync(capbuf, arr[q], sizeof(T) * n2 * NM, cudaMemcpyDeviceToDevice, st));
+      if (h->symm && !fresh) hop_symm(capbuf);
+      CK(cudaMemcpyAsync(host.data(), capbuf, sizeof(T) * n2 * NM, cudaMemcpyDeviceToHost, st)); sync();
+      for (int c = 0; c < C; ++c) for (int f = 0; f < F; ++f) for (long i = 0; i < n2; ++i)
+        part[c][((size_t)q * F + f) * n2 + i] = from_T<T>(host[n2 * ((long)c * F + f) + i]);
+    }
+    for (int c = 0; c < C; ++c) dst[c].insert(dst[c].end(), part[c].begin(), part[c].end());
+  }
+  void compare_tau(const T* A, const T* B) {   // Control_Precision_tau, control_mod.F90:300-311
+    KL(KC_EW, st, k_compare<T><<<NM, 256, 0, st>>>(A, B, n2, n2, d_cmp));
+    KL(KC_EW, st, k_ctl_accum<<<(C + 127) / 128, 128, 0, st>>>(d_cmp, F, h->d_ctl, 1, C));
+  }
+  void tau_m() override {
+    taum_alloc();
+    const size_t bytes = sizeof(T) * n2 * NM; dim3 eg(ew_blocks(n2), NM);
+    CK(cudaMemcpyAsync(G00, G, bytes, cudaMemcpyDeviceToDevice, st)); CK(cudaMemcpyAsync(GT0, G, bytes, cudaMemcpyDeviceToDevice, st));
+    CK(cudaMemcpyAsync(GTT, G, bytes, cudaMemcpyDeviceToDevice, st));
+    KL(KC_EW, st, k_g0t_init<T><<<eg, 256, 0, st>>>(G0T, G, n2, N));
+    taum_capture(0);
+    set_udv_identity(udvr2);
+    int NST = 1;
+    for (int NT = 0; NT <= L - 1; ++NT) {
+      const int NT1 = NT + 1;
+      propr(GT0, NT1); proprm1(G0T, NT1); proprm1(GTT, NT1); propr(GTT, NT1);          // tau_m_mod.F90:141-149
+      taum_capture(NT1);
+      if (stab_nt[NST] == NT1) {
+        wrapur_on(udvr2, stab_nt[NST - 1], NT1);
+        la_cgr2_2<T>(w, w2, h->stab, udvr2, udvst[NST - 1], tmN[0], tmN[1], tmN[2], tmN[3], d_first);
+        compare_tau(G, tmN[1]); compare_tau(GTT, tmN[2]); compare_tau(GT0, tmN[0]); compare_tau(G0T, tmN[3]);
+        std::swap(GT0, tmN[0]); std::swap(G00, tmN[1]); std::swap(GTT, tmN[2]); std::swap(G0T, tmN[3]);
+        taum_capture(NT1, true);
+        NST++;
+      }
+    }
+  }
+  // PROPR / PROPRM1 (Prog/tau_m_mod.F90:215-263): A <- B(nt) A ;  A <- A B(nt)^-1
+  void propr(T* A, int nt) {
+    if (!dense_t) apply_ops(A, 0, MODE_WRAPUR, nt, nt);
+    else { dense_mult(A, 0, true); apply_ops(A, 0, MODE_WRAPUR, nt, nt); }
+  }
+  void proprm1(T* A, int nt) {
+    if (!dense_t) apply_ops(A, 1, MODE_PROPRM1, nt, nt);
+    else { dense_mult(A, 1, false); apply_ops(A, 1, MODE_PROPRM1, nt, nt); }
+  }
+
+  // ---------------------------------------------------------------- host access
+  void get_green(int chain, int nf, int symm, cd* out) override {
+    const T* src = G + n2 * ((long)chain * F + (nf - 1));
+    std::vector<T> t(n2);
+    if (symm) {   // Hop_mod_Symm on a copy (main.F90:761-764): do it for the whole batch in W[3]... only this matrix is read back
+      CK(cudaMemcpyAsync(G2, G, sizeof(T) * n2 * NM, cudaMemcpyDeviceToDevice, st));
+      hop_symm(G2); src = G2 + n2 * ((long)chain * F + (nf - 1));
+    }
+    CK(cudaMemcpyAsync(t.data(), src, sizeof(T) * n2, cudaMemcpyDeviceToHost, st)); sync();
+    for (long i = 0; i < n2; ++i) out[i] = from_T<T>(t[i]);
+  }
+  void set_green(int chain, int nf, const cd* in) override {
+    std::vector<T> t(n2); for (long i = 0; i < n2; ++i) t[i] = to_T<T>(in[i]);
+    CK(cudaMemcpyAsync(G + n2 * ((long)chain * F + (nf - 1)), t.data(), sizeof(T) * n2, cudaMemcpyHostToDevice, st)); sync();
+  }
+  void get_udv(int which, int nst, int chain, int nf, cd* U, cd* D, cd* V) override {
+    UdvDev<T>& u = which == 0 ? udvl : which == 1 ? udvr : udvst[nst - 1];
+    const long b = (long)chain * F + (nf - 1);
+    std::vector<T> t(n2); std::vector<double> d(N);
+    CK(cudaMemcpyAsync(t.data(), u.U + n2 * b, sizeof(T) * n2, cudaMemcpyDeviceToHost, st)); sync(); for (long i = 0; i < n2; ++i) U[i] = from_T<T>(t[i]);
+    CK(cudaMemcpyAsync(t.data(), u.V + n2 * b, sizeof(T) * n2, cudaMemcpyDeviceToHost, st)); sync(); for (long i = 0; i < n2; ++i) V[i] = from_T<T>(t[i]);
+    CK(cudaMemcpyAsync(d.data(), u.D + (long)N * b, sizeof(double) * N, cudaMemcpyDeviceToHost, st)); sync(); for (int i = 0; i < N; ++i) D[i] = cd(d[i], 0.0);
+  }
+  void hop_apply(int which, int nf, cd* A) override {
+    // applies to matrix slot (chain 0, flavor nf) of scratch G2; the whole batch is processed (test entry point)
+    std::vector<T> t(n2); for (long i = 0; i < n2; ++i) t[i] = to_T<T>(A[i]);
+    CK(cudaMemsetAsync(G2, 0, sizeof(T) * n2 * NM, st));
+    CK(cudaMemcpyAsync(G2 + n2 * (nf - 1), t.data(), sizeof(T) * n2, cudaMemcpyHostToDevice, st));
+    switch (which) { case 0: mmthr(G2); break; case 1: mmthr_m1(G2); break; case 2: mmthl(G2); break; case 3: mmthl_m1(G2); break; case 4: mmthlc(G2); break; case 5: hop_symm(G2); break; }
+    CK(cudaMemcpyAsync(t.data(), G2 + n2 * (nf - 1), sizeof(T) * n2, cudaMemcpyDeviceToHost, st)); sync();
+    for (long i = 0; i < n2; ++i) A[i] = from_T<T>(t[i]);
+  }
+};
+
+// ---- kernel-level test helpers and the FP64 peak microbenchmark (templates must live outside extern "C")
+template <typename T> static std::vector<T> h2T(const double* src, size_t n) { std::vector<T> v(n); for (size_t i = 0; i < n; ++i) v[i] = to_T<T>(cd(src[2 * i], src[2 * i + 1])); return v; }
+template <typename T> static void T2h(const std::vector<T>& v, double* dst) { for (size_t i = 0; i < v.size(); ++i) { cd z = from_T<T>(v[i]); dst[2 * i] = z.real(); dst[2 * i + 1] = z.imag(); } }
+template <typename T> struct DevBuf { T* p = nullptr; size_t n = 0; DevBuf(size_t nn) : n(nn) { CK(cudaMalloc(&p, sizeof(T) * (nn ? nn : 1))); } ~DevBuf() { cudaFree(p); }
+  void up(const std::vector<T>& v) { CK(cudaMemcpy(p, v.data(), sizeof(T) * v.size(), cudaMemcpyHostToDevice)); } std::vector<T> down() { std::vector<T> v(n); CK(cudaMemcpy(v.data(), p, sizeof(T) * n, cudaMemcpyDeviceToHost)); return v; } };
+
+template <typename T>
+static void t_qdrp(int m, int n, int batch, double* A, double* D, int* jpvt, double* tau, double* phases) {
+  DevBuf<T> dA((size_t)m * n * batch), dtau((size_t)n * batch); DevBuf<int> dp((size_t)n * batch); DevBuf<double> dD((size_t)n * batch); DevBuf<QrOut> dq(batch);
+  dA.up(h2T<T>(A, dA.n));
+  launch_qrp<T, 1>(0, dA.p, m, n, m, (long)m * n, dtau.p, n, dp.p, n, dD.p, n, dq.p, batch);
+  CK(cudaDeviceSynchronize());
+  T2h<T>(dA.down(), A); T2h<T>(dtau.down(), tau);
+  auto d = dD.down(); std::copy(d.begin(), d.end(), D);
+  auto p = dp.down(); for (size_t i = 0; i < p.size(); ++i) jpvt[i] = p[i] + 1;
+  auto q = dq.down(); for (int b = 0; b < batch; ++b) { phases[5 * b] = q[b].perm_sign; phases[5 * b + 1] = q[b].diag_phase.x; phases[5 * b + 2] = q[b].diag_phase.y; phases[5 * b + 3] = q[b].detq.x; phases[5 * b + 4] = q[b].detq.y; }
+}
+template <typename T>
+static void t_udv(int n, int batch, char side, double* U, double* D, double* V) {
+  const size_t n2 = (size_t)n * n; LaWork<T> w; w.alloc(n, batch, 0);
+  DevBuf<T> dU(n2 * batch), dV(n2 * batch); DevBuf<double> dD((size_t)n * batch); DevBuf<cplx> ddet(batch);
+  dU.up(h2T<T>(U, dU.n)); dV.up(h2T<T>(V, dV.n)); { std::vector<double> d((size_t)n * batch); for (size_t i = 0; i < d.size(); ++i) d[i] = D[2 * i]; dD.up(d); }
+  UdvDev<T> s; s.U = dU.p; s.V = dV.p; s.D = dD.p; s.det = ddet.p;
+  la_decompose<T>(w, s, side); CK(cudaDeviceSynchronize());
+  T2h<T>(dU.down(), U); T2h<T>(dV.down(), V); auto d = dD.down(); for (size_t i = 0; i < d.size(); ++i) { D[2 * i] = d[i]; D[2 * i + 1] = 0.0; }
+  w.release();
+}
+template <typename T>
+static void t_cgr(int n, int batch, int nvar, int stab, const double* UR, const double* DR, const double* VR, const double* UL, const double* DL, const double* VL,
+                  const double* detUR, const double* detUL, double* G, double* phase) {
+  const size_t n2 = (size_t)n * n; LaWork<T> w; w.alloc(n, batch, 0);
+  DevBuf<T> dUR(n2 * batch), dVR(n2 * batch), dUL(n2 * batch), dVL(n2 * batch), dG(n2 * batch); DevBuf<double> dDR((size_t)n * batch), dDL((size_t)n * batch);
+  DevBuf<cplx> detR(batch), detL(batch), dz(batch);
+  dUR.up(h2T<T>(UR, n2 * batch)); dVR.up(h2T<T>(VR, n2 * batch)); dUL.up(h2T<T>(UL, n2 * batch)); dVL.up(h2T<T>(VL, n2 * batch));
+  { std::vector<double> a((size_t)n * batch), b((size_t)n * batch); for (size_t i = 0; i < a.size(); ++i) { a[i] = DR[2 * i]; b[i] = DL[2 * i]; } dDR.up(a); dDL.up(b); }
+  { std::vector<cplx> a(batch), b(batch); for (int i = 0; i < batch; ++i) { a[i] = cplx(detUR[2 * i], detUR[2 * i + 1]); b[i] = cplx(detUL[2 * i], detUL[2 * i + 1]); } detR.up(a); detL.up(b); }
+  UdvDev<T> R, L; R.U = dUR.p; R.V = dVR.p; R.D = dDR.p; R.det = detR.p; L.U = dUL.p; L.V = dVL.p; L.D = dDL.p; L.det = detL.p;
+  la_cgr<T>(w, nvar, stab, R, L, dG.p, dz.p); CK(cudaDeviceSynchronize());
+  T2h<T>(dG.down(), G); auto z = dz.down(); for (int i = 0; i < batch; ++i) { phase[2 * i] = z[i].x; phase[2 * i + 1] = z[i].y; }
+  w.release();
+}
+template <typename T>
+static void t_cgr22(int n, int batch, int stab, const double* U2, const double* D2, const double* V2, const double* U1, const double* D1, const double* V1, double* out4) {
+  const size_t n2 = (size_t)n * n; LaWork<T> w, w2; w.alloc(n, batch, 0); w2.alloc(2 * n, batch, 0);
+  DevBuf<T> dU2(n2 * batch), dV2(n2 * batch), dU1(n2 * batch), dV1(n2 * batch), g0(n2 * batch), g1(n2 * batch), g2(n2 * batch), g3(n2 * batch);
+  DevBuf<double> dD2((size_t)n * batch), dD1((size_t)n * batch); DevBuf<int> first(batch);
+  dU2.up(h2T<T>(U2, n2 * batch)); dV2.up(h2T<T>(V2, n2 * batch)); dU1.up(h2T<T>(U1, n2 * batch)); dV1.up(h2T<T>(V1, n2 * batch));
+  { std::vector<double> a((size_t)n * batch), b((size_t)n * batch); for (size_t i = 0; i < a.size(); ++i) { a[i] = D2[2 * i]; b[i] = D1[2 * i]; } dD2.up(a); dD1.up(b); }
+  UdvDev<T> u2, u1; u2.U = dU2.p; u2.V = dV2.p; u2.D = dD2.p; u1.U = dU1.p; u1.V = dV1.p; u1.D = dD1.p;
+  la_cgr2_2<T>(w, w2, stab, u2, u1, g0.p, g1.p, g2.p, g3.p, first.p); CK(cudaDeviceSynchronize());
+  DevBuf<T>* gs[4] = {&g0, &g1, &g2, &g3};
+  for (int q = 0; q < 4; ++q) T2h<T>(gs[q]->down(), out4 + 2 * q * n2 * batch);
+  w.release(); w2.release();
+}
+template <typename T>
+static void t_gemm(int ta, int tb, int m, int n, int k, int batch, const double* A, const double* B, double* Cc) {
+  const int ar = ta ? k : m, ac = ta ? m : k, br = tb ? n : k, bc = tb ? k : n;
+  DevBuf<T> dA((size_t)ar * ac * batch), dB((size_t)br * bc * batch), dC((size_t)m * n * batch);
+  dA.up(h2T<T>(A, dA.n)); dB.up(h2T<T>(B, dB.n));
+  if (!ta && !tb) gemm<T, 0, 0, 0>(0, m, n, k, dA.p, ar, (long)ar * ac, dB.p, br, (long)br * bc, dC.p, m, (long)m * n, batch);
+  else if (ta && !tb) gemm<T, 1, 0, 0>(0, m, n, k, dA.p, ar, (long)ar * ac, dB.p, br, (long)br * bc, dC.p, m, (long)m * n, batch);
+  else if (!ta && tb) gemm<T, 0, 1, 0>(0, m, n, k, dA.p, ar, (long)ar * ac, dB.p, br, (long)br * bc, dC.p, m, (long)m * n, batch);
+  else gemm<T, 1, 1, 0>(0, m, n, k, dA.p, ar, (long)ar * ac, dB.p, br, (long)br * bc, dC.p, m, (long)m * n, batch);
+  CK(cudaDeviceSynchronize()); T2h<T>(dC.down(), Cc);
+}

@@ -434,10 +434,10 @@ __global__ void k_set_identity(T* __restrict__ A, int ld, long sA, int m, int n)
     A[i + (long)j * ld] = (i == j) ? one_<T>() : zero_<T>();
   }
 }
-__global__ void k_fill_double(double* p, long n, double v) {
+static __global__ void k_fill_double(double* p, long n, double v) {
   for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long)gridDim.x * blockDim.x) p[e] = v;
 }
-__global__ void k_fill_cplx(cplx* p, long n, cplx v) {
+static __global__ void k_fill_cplx(cplx* p, long n, cplx v) {
   for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long)gridDim.x * blockDim.x) p[e] = v;
 }
 

@@ -28,7 +28,7 @@ struct Prof {
   void reset() { collect(); for (int c = 0; c < KC_COUNT; ++c) { launches[c] = 0; ms[c] = 0.0; } }
   ~Prof() { collect(); for (auto e : pool) cudaEventDestroy(e); }
 };
-static thread_local Prof* t_prof = nullptr;
+extern thread_local Prof* t_prof;     // defined in alf_b200.cu, set by every C-ABI entry point
 struct KScope {
   Prof* p; int cat; cudaStream_t st; cudaEvent_t a, b; bool on = false;
   KScope(int c, cudaStream_t s) : p(t_prof), cat(c), st(s) {
@@ -127,7 +127,7 @@ static void launch_trsm(cudaStream_t st, const T* R, int ldr, long sR, T* B, int
 
 // phase bookkeeping of decompose (udv_state_mod.F90:480-492, 578): Phase = prod R_ii * sign(perm), conjugated for side L;
 // beta = 1/Phase scales row 1 of R, Phase scales column 1 of U.  det(U_new) = det(Q) * Phase.
-__global__ void k_decomp_phase(const QrOut* __restrict__ q, int side_l, cplx* __restrict__ ph, cplx* __restrict__ beta, cplx* __restrict__ det, int n) {
+static __global__ void k_decomp_phase(const QrOut* __restrict__ q, int side_l, cplx* __restrict__ ph, cplx* __restrict__ beta, cplx* __restrict__ det, int n) {
   int b = blockIdx.x * blockDim.x + threadIdx.x; if (b >= n) return;
   cplx p = q[b].perm_sign * q[b].diag_phase;
   if (side_l) p = conj_(p);
@@ -154,7 +154,7 @@ static void la_decompose(LaWork<T>& w, UdvDev<T>& s, char side) {
 }
 
 // per-matrix phase factor of det(1 + B_R B_L) without Op_phase (Prog/cgr1_mod.F90:300-349)
-__global__ void k_cgr_z(const QrOut* __restrict__ q, const cplx* __restrict__ detR, const cplx* __restrict__ detL, int nvar, cplx* __restrict__ z, int n) {
+static __global__ void k_cgr_z(const QrOut* __restrict__ q, const cplx* __restrict__ detR, const cplx* __restrict__ detL, int nvar, cplx* __restrict__ z, int n) {
   int b = blockIdx.x * blockDim.x + threadIdx.x; if (b >= n) return;
   cplx dp = q[b].diag_phase, dq = q[b].detq;
   if (nvar != 1) { dp = conj_(dp); dq = conj_(dq); }

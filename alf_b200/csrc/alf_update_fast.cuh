@@ -27,7 +27,7 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
 // scaled G0 tile (32 independent loads per thread issued up front, so the HBM/L2 latency is paid once per tile), then
 // (-X) Y^T is accumulated with DMMA m8n8k4 and the tile is stored.  X, Y: [k][ldx] with rows nd .. nd4-1 zeroed by the caller
 // (nd4 = nd rounded up to 4); ldx % 16 == 4 makes the fragment loads bank-conflict free.
-__device__ __noinline__ void flush_g0(double* __restrict__ G0, int N, const double* __restrict__ X, const double* __restrict__ Y, int ldx, int nd4,
+static __device__ __noinline__ void flush_g0(double* __restrict__ G0, int N, const double* __restrict__ X, const double* __restrict__ Y, int ldx, int nd4,
                                       double* __restrict__ dl, double* __restrict__ dr) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
   const int tm = (N + 31) / 32, tiles = tm * tm;
@@ -76,7 +76,7 @@ __device__ __noinline__ void flush_g0(double* __restrict__ G0, int N, const doub
   for (int i = threadIdx.x; i < N; i += blockDim.x) { dl[i] = 1.0; dr[i] = 1.0; }
 }
 // complex: register-tiled FMA version of alf_update.cuh
-__device__ __noinline__ void flush_g0(cplx* __restrict__ G0, int N, const cplx* __restrict__ X, const cplx* __restrict__ Y, int ldx, int nd4,
+static __device__ __noinline__ void flush_g0(cplx* __restrict__ G0, int N, const cplx* __restrict__ X, const cplx* __restrict__ Y, int ldx, int nd4,
                                          cplx* __restrict__ dl, cplx* __restrict__ dr) {
   flush_flavor<cplx>(G0, N, X, Y, ldx, nd4, dl, dr);
 }
