@@ -267,6 +267,14 @@ def test_qdrp(A, is_complex=True, device=0):
     return Af.transpose(0, 2, 1), D, jp, tau, ph
 
 
+def test_qdrp_blocked(A, is_complex=True, device=0):
+    A = np.ascontiguousarray(A, dtype=np.complex128); batch, m, n = A.shape
+    Af = np.ascontiguousarray(A.transpose(0, 2, 1)).copy(); Q = np.zeros((batch, m, m), dtype=np.complex128)
+    D = np.zeros((batch, n)); jp = np.zeros((batch, n), dtype=np.int32); tau = np.zeros((batch, n), dtype=np.complex128); ph = np.zeros((batch, 5))
+    _chk(lib().alf_b200_test_qdrp_blocked(device, int(is_complex), m, n, batch, _d(Af), _d(D), jp.ctypes.data_as(_ip), _d(tau), _d(ph), _d(Q)), "test_qdrp_blocked")
+    return Af.transpose(0, 2, 1), D, jp, tau, ph, Q.transpose(0, 2, 1)
+
+
 def test_udv_decompose(U, D, V, side="r", is_complex=True, device=0):
     U = np.ascontiguousarray(U, dtype=np.complex128); V = np.ascontiguousarray(V, dtype=np.complex128); batch, n, _ = U.shape
     Uf = np.ascontiguousarray(U.transpose(0, 2, 1)).copy(); Vf = np.ascontiguousarray(V.transpose(0, 2, 1)).copy()

@@ -264,6 +264,10 @@ int alf_b200_test_qdrp(int device, int is_complex, int m, int n, int batch, doub
   try { CK(cudaSetDevice(device)); if (is_complex) alf_t_qdrp_cplx(m, n, batch, A, D, jpvt, tau, phases); else alf_t_qdrp_real(m, n, batch, A, D, jpvt, tau, phases); }
   catch (const std::exception& e) { fprintf(stderr, "alf_b200_test_qdrp: %s\n", e.what()); return ALF_ERROR_CUDA; } return ALF_OK;
 }
+int alf_b200_test_qdrp_blocked(int device, int is_complex, int m, int n, int batch, double* A, double* D, int* jpvt, double* tau, double* phases, double* Q) {
+  try { CK(cudaSetDevice(device)); if (is_complex) alf_t_qdrp_blk_cplx(m, n, batch, A, D, jpvt, tau, phases, Q); else alf_t_qdrp_blk_real(m, n, batch, A, D, jpvt, tau, phases, Q); }
+  catch (const std::exception& e) { fprintf(stderr, "alf_b200_test_qdrp_blocked: %s\n", e.what()); return ALF_ERROR_CUDA; } return ALF_OK;
+}
 int alf_b200_test_udv_decompose(int device, int is_complex, int n, int batch, char side, double* U, double* D, double* V) {
   try { CK(cudaSetDevice(device)); if (is_complex) alf_t_udv_cplx(n, batch, side, U, D, V); else alf_t_udv_real(n, batch, side, U, D, V); }
   catch (const std::exception& e) { fprintf(stderr, "alf_b200_test_udv_decompose: %s\n", e.what()); return ALF_ERROR_CUDA; } return ALF_OK;

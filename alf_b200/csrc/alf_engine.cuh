@@ -649,6 +649,21 @@ static void t_qdrp(int m, int n, int batch, double* A, double* D, int* jpvt, dou
   auto p = dp.down(); for (size_t i = 0; i < p.size(); ++i) jpvt[i] = p[i] + 1;
   auto q = dq.down(); for (int b = 0; b < batch; ++b) { phases[5 * b] = q[b].perm_sign; phases[5 * b + 1] = q[b].diag_phase.x; phases[5 * b + 2] = q[b].diag_phase.y; phases[5 * b + 3] = q[b].detq.x; phases[5 * b + 4] = q[b].detq.y; }
 }
+// blocked (windowed-pivoting) QR + explicit Q through the compact-WY application: returns QR-in-place, D, jpvt, tau, phases and Q
+template <typename T>
+static void t_qdrp_blk(int m, int n, int batch, double* A, double* D, int* jpvt, double* tau, double* phases, double* Q) {
+  DevBuf<T> dA((size_t)m * n * batch), dtau((size_t)n * batch), dQ((size_t)m * m * batch), dT((size_t)(n + 32) * 32 * batch); DevBuf<int> dp((size_t)n * batch); DevBuf<double> dD((size_t)n * batch); DevBuf<QrOut> dq(batch);
+  dA.up(h2T<T>(A, dA.n));
+  if (!qrblk_cfg<T>(m, n).ok) throw CudaError("blocked QR: matrix too large for shared memory");
+  launch_qrp_blk<T>(0, dA.p, m, n, m, (long)m * n, dtau.p, n, dp.p, n, dD.p, n, dq.p, dT.p, batch);
+  KL(KC_EW, 0, k_set_identity<T><<<dim3(ew_blocks((long)m * m), batch), 256>>>(dQ.p, m, (long)m * m, m, m));
+  launch_apply_q<T>(0, dA.p, m, n, m, (long)m * n, dT.p, dQ.p, m, (long)m * m, m, 1, true, batch);
+  CK(cudaDeviceSynchronize());
+  T2h<T>(dA.down(), A); T2h<T>(dtau.down(), tau); T2h<T>(dQ.down(), Q);
+  auto d = dD.down(); std::copy(d.begin(), d.end(), D);
+  auto p = dp.down(); for (size_t i = 0; i < p.size(); ++i) jpvt[i] = p[i] + 1;
+  auto q = dq.down(); for (int b = 0; b < batch; ++b) { phases[5 * b] = q[b].perm_sign; phases[5 * b + 1] = q[b].diag_phase.x; phases[5 * b + 2] = q[b].diag_phase.y; phases[5 * b + 3] = q[b].detq.x; phases[5 * b + 4] = q[b].detq.y; }
+}
 template <typename T>
 static void t_udv(int n, int batch, char side, double* U, double* D, double* V) {
   const size_t n2 = (size_t)n * n; LaWork<T> w; w.alloc(n, batch, 0);

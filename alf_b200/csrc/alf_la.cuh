@@ -425,6 +425,13 @@ __global__ void k_row0scale(T* __restrict__ A, int ld, long sA, int n, const cpl
   T st = make_<T>(s[b].x, s[b].y);
   for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) A[(long)j * ld] = A[(long)j * ld] * st;
 }
+// dst = src with column 0 multiplied by s[b]  (explicit Q of the blocked path -> U, udv_state_mod.F90:578)
+template <typename T>
+__global__ void k_copy_col0scale(T* __restrict__ dst, const T* __restrict__ src, long sM, int n, const cplx* __restrict__ s) {
+  const int b = blockIdx.y; dst += (long)b * sM; src += (long)b * sM;
+  const T st = make_<T>(s[b].x, s[b].y);
+  for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < (long)n * n; e += (long)gridDim.x * blockDim.x) dst[e] = (e < n) ? src[e] * st : src[e];
+}
 // identity / zero fill
 template <typename T>
 __global__ void k_set_identity(T* __restrict__ A, int ld, long sA, int m, int n) {

@@ -6,6 +6,7 @@
 #include <string>
 #include <vector>
 #include "alf_la.cuh"
+#include "alf_qrblk.cuh"
 
 struct CudaError : std::runtime_error { using std::runtime_error::runtime_error; };
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { \
@@ -52,6 +53,7 @@ struct LaWork {
   int N = 0, NM = 0; cudaStream_t st = 0;
   T* W[4] = {nullptr, nullptr, nullptr, nullptr};
   T* tau = nullptr; int* jpvt = nullptr; double* Dq = nullptr; QrOut* qrout = nullptr; cplx* sc_phase = nullptr; cplx* sc_beta = nullptr;
+  T* Tbuf = nullptr;      // compact-WY factors of the blocked QR: [matrix][panel][QRB_NB x QRB_NB]
   long n2() const { return (long)N * N; }
   void alloc(int n, int nm, cudaStream_t s) {
     N = n; NM = nm; st = s;
@@ -59,11 +61,12 @@ struct LaWork {
     CK(cudaMalloc(&tau, sizeof(T) * (long)N * NM)); CK(cudaMalloc(&jpvt, sizeof(int) * (long)N * NM));
     CK(cudaMalloc(&Dq, sizeof(double) * (long)N * NM)); CK(cudaMalloc(&qrout, sizeof(QrOut) * NM));
     CK(cudaMalloc(&sc_phase, sizeof(cplx) * NM)); CK(cudaMalloc(&sc_beta, sizeof(cplx) * NM));
+    CK(cudaMalloc(&Tbuf, sizeof(T) * (size_t)(N + 32) * 32 * NM));
   }
   void release() {
     for (int i = 0; i < 4; ++i) if (W[i]) cudaFree(W[i]);
     if (tau) cudaFree(tau); if (jpvt) cudaFree(jpvt); if (Dq) cudaFree(Dq); if (qrout) cudaFree(qrout);
-    if (sc_phase) cudaFree(sc_phase); if (sc_beta) cudaFree(sc_beta);
+    if (sc_phase) cudaFree(sc_phase); if (sc_beta) cudaFree(sc_beta); if (Tbuf) cudaFree(Tbuf); Tbuf = nullptr;
     for (int i = 0; i < 4; ++i) W[i] = nullptr; tau = nullptr; jpvt = nullptr; Dq = nullptr; qrout = nullptr; sc_phase = sc_beta = nullptr;
   }
 };
@@ -125,6 +128,52 @@ static void launch_trsm(cudaStream_t st, const T* R, int ldr, long sR, T* B, int
   CKL();
 }
 
+// ---- blocked path (matrices that do not fit one SM's shared memory): windowed pivoted QR + compact-WY application
+struct QrBlkCfg { int NB, TC; size_t smem; bool ok; };
+template <typename T>
+static QrBlkCfg qrblk_cfg(int m, int n) {
+  QrBlkCfg c; c.ok = false;
+  const int nbs[2] = {32, 16};
+  for (int i = 0; i < 2; ++i) { c.NB = nbs[i]; c.TC = 8; c.smem = qrblk_smem<T>(m, n, c.NB, c.TC); if (c.smem <= 226 * 1024) { c.ok = true; break; } }
+  return c;
+}
+static inline bool la_force_unblocked() { static int v = -1; if (v < 0) v = getenv("ALF_B200_UNBLOCKED_QR") ? 1 : 0; return v == 1; }
+// true if the matrix is factored by the blocked kernel (the whole-matrix-in-shared-memory kernel is kept for small matrices)
+template <typename T>
+static bool use_blocked_qr(int m, int n) {
+  if (la_force_unblocked()) return false;
+  size_t extra = sizeof(T) * m + sizeof(double) * (n + (n > 32 ? n : 32)) + sizeof(int) * n + 64;
+  return sizeof(T) * (size_t)m * n + extra > kSmemStageLimit && m <= 1024 && qrblk_cfg<T>(m, n).ok;
+}
+template <typename T>
+static void launch_qrp_blk(cudaStream_t st, T* A, int m, int n, int ld, long sA, T* tau, long sTau, int* jpvt, long sP, double* D, long sD, QrOut* out,
+                           T* Tbuf, int batch) {
+  const QrBlkCfg c = qrblk_cfg<T>(m, n);
+  CK(cudaFuncSetAttribute(k_qrp_blk<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem));
+  KL(KC_QRP, st, k_qrp_blk<T><<<batch, 512, c.smem, st>>>(A, m, n, ld, sA, tau, sTau, jpvt, sP, D, sD, out, Tbuf, (long)(n + 32) * 32, c.NB, c.TC));
+}
+// X <- Q^H X (mode 0) / Q X (mode 1); ident: X holds the identity on entry (mode 1 only: forms Q)
+template <typename T>
+static void launch_apply_q(cudaStream_t st, const T* QR, int m, int n, int ld, long sQ, const T* Tbuf, T* X, int ldx, long sX, int ncols, int mode, bool ident, int batch) {
+  const QrBlkCfg c = qrblk_cfg<T>(m, n);
+  const int cpc = 64; dim3 grid((ncols + cpc - 1) / cpc, batch);
+  const long sT = (long)(n + 32) * 32;
+  KScope ks_(KC_FORMQ, st);
+  if (mode == 0) { CK(cudaFuncSetAttribute(k_apply_q<T, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem));
+    k_apply_q<T, 0, 0><<<grid, 512, c.smem, st>>>(QR, m, n, ld, sQ, Tbuf, sT, X, ldx, sX, ncols, c.NB, c.TC, cpc); }
+  else if (ident) { CK(cudaFuncSetAttribute(k_apply_q<T, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem));
+    k_apply_q<T, 1, 1><<<grid, 512, c.smem, st>>>(QR, m, n, ld, sQ, Tbuf, sT, X, ldx, sX, ncols, c.NB, c.TC, cpc); }
+  else { CK(cudaFuncSetAttribute(k_apply_q<T, 1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem));
+    k_apply_q<T, 1, 0><<<grid, 512, c.smem, st>>>(QR, m, n, ld, sQ, Tbuf, sT, X, ldx, sX, ncols, c.NB, c.TC, cpc); }
+  CKL();
+}
+// pivoted QR dispatcher used by the sweep
+template <typename T>
+static void la_qrp(LaWork<T>& w, T* A, int m, int n, double* D) {
+  if (use_blocked_qr<T>(m, n)) launch_qrp_blk<T>(w.st, A, m, n, m, (long)m * n, w.tau, n, w.jpvt, n, D, n, w.qrout, w.Tbuf, w.NM);
+  else launch_qrp<T, 1>(w.st, A, m, n, m, (long)m * n, w.tau, n, w.jpvt, n, D, n, w.qrout, w.NM);
+}
+
 // phase bookkeeping of decompose (udv_state_mod.F90:480-492, 578): Phase = prod R_ii * sign(perm), conjugated for side L;
 // beta = 1/Phase scales row 1 of R, Phase scales column 1 of U.  det(U_new) = det(Q) * Phase.
 static __global__ void k_decomp_phase(const QrOut* __restrict__ q, int side_l, cplx* __restrict__ ph, cplx* __restrict__ beta, cplx* __restrict__ det, int n) {
@@ -140,7 +189,8 @@ static void la_decompose(LaWork<T>& w, UdvDev<T>& s, char side) {
   const int N = w.N, NM = w.NM; const long n2 = w.n2(); cudaStream_t st = w.st;
   const bool left = (side == 'l' || side == 'L');
   KL(KC_EW, st, k_colscale<T><<<dim3(ew_blocks(n2), NM), 256, 0, st>>>(s.U, N, n2, N, N, s.D, N));
-  launch_qrp<T, 1>(st, s.U, N, N, N, n2, w.tau, N, w.jpvt, N, s.D, N, w.qrout, NM);
+  const bool blk = use_blocked_qr<T>(N, N);
+  la_qrp<T>(w, s.U, N, N, s.D);
   KL(KC_EW, st, k_decomp_phase<<<(NM + 127) / 128, 128, 0, st>>>(w.qrout, left ? 1 : 0, w.sc_phase, w.sc_beta, s.det, NM));
   KL(KC_EW, st, k_row0scale<T><<<dim3((N + 255) / 256, NM), 256, 0, st>>>(s.U, N, n2, N, w.sc_beta));
   if (!left) {
@@ -150,7 +200,12 @@ static void la_decompose(LaWork<T>& w, UdvDev<T>& s, char side) {
     KL(KC_EW, st, k_permcopy<T, 2><<<dim3(ew_blocks(n2), NM), 256, 0, st>>>(w.W[0], N, n2, s.V, N, n2, N, N, w.jpvt, N));
     gemm<T, 0, 1, 2>(st, N, N, N, w.W[0], N, n2, s.U, N, n2, s.V, N, n2, NM);          // V = (V P) * R^H
   }
-  launch_formq<T>(st, s.U, N, N, N, n2, w.tau, N, w.sc_phase, NM);
+  if (!blk) launch_formq<T>(st, s.U, N, N, N, n2, w.tau, N, w.sc_phase, NM);
+  else {   // Q = H_1 ... H_n applied to the identity block-wise, then column 1 scaled by the phase (udv_state_mod.F90:576-578)
+    KL(KC_EW, st, k_set_identity<T><<<dim3(ew_blocks(n2), NM), 256, 0, st>>>(w.W[1], N, n2, N, N));
+    launch_apply_q<T>(st, s.U, N, N, N, n2, w.Tbuf, w.W[1], N, n2, N, 1, true, NM);
+    KL(KC_EW, st, k_copy_col0scale<T><<<dim3(ew_blocks(n2), NM), 256, 0, st>>>(s.U, w.W[1], n2, N, w.sc_phase));
+  }
 }
 
 // per-matrix phase factor of det(1 + B_R B_L) without Op_phase (Prog/cgr1_mod.F90:300-349)
@@ -174,17 +229,24 @@ static void la_cgr(LaWork<T>& w, int nvar, int stab, const UdvDev<T>& R, const U
   else { if (nvar == 1) KL(KC_EW, st, k_cgr_tpup<T, 0, 0><<<eg, 256, 0, st>>>(w.W[2], w.W[1], w.W[0], n2, N, R.D, L.D, N));
          else KL(KC_EW, st, k_cgr_tpup<T, 0, 1><<<eg, 256, 0, st>>>(w.W[2], w.W[1], w.W[0], n2, N, R.D, L.D, N)); }
   CKL();
-  launch_qrp<T, 1>(st, w.W[2], N, N, N, n2, w.tau, N, w.jpvt, N, w.Dq, N, w.qrout, NM);
+  const bool blk = use_blocked_qr<T>(N, N);
+  la_qrp<T>(w, w.W[2], N, N, w.Dq);
   KL(KC_EW, st, k_cgr_z<<<(NM + 127) / 128, 128, 0, st>>>(w.qrout, R.det, L.det, nvar, z, NM));
-  // explicit Q in W[1]
-  KL(KC_EW, st, k_permcopy<T, 0><<<eg, 256, 0, st>>>(w.W[1], N, n2, w.W[2], N, n2, N, N, nullptr, 0));
-  launch_formq<T>(st, w.W[1], N, N, N, n2, w.tau, N, nullptr, NM);
   // X0 = U_R^H (nvar 1) or U_L^H (nvar 2), with the D_+^-1 row scaling of the STAB3 branch
   const UdvDev<T>& A0 = (nvar == 1) ? R : L;
   const UdvDev<T>& A1 = (nvar == 1) ? L : R;
-  KL(KC_EW, st, k_permcopy<T, 4><<<eg, 256, 0, st>>>(w.W[0], N, n2, A0.U, N, n2, N, N, nullptr, 0));
-  if (stab == 3) { KL(KC_EW, st, k_sep_scale<T, 1><<<eg, 256, 0, st>>>(w.W[0], n2, N, A0.D, N)); }
-  gemm<T, 1, 0, 0>(st, N, N, N, w.W[1], N, n2, w.W[0], N, n2, w.W[3], N, n2, NM);      // X = Q^H X0
+  if (!blk) {
+    // explicit Q in W[1]
+    KL(KC_EW, st, k_permcopy<T, 0><<<eg, 256, 0, st>>>(w.W[1], N, n2, w.W[2], N, n2, N, N, nullptr, 0));
+    launch_formq<T>(st, w.W[1], N, N, N, n2, w.tau, N, nullptr, NM);
+    KL(KC_EW, st, k_permcopy<T, 4><<<eg, 256, 0, st>>>(w.W[0], N, n2, A0.U, N, n2, N, N, nullptr, 0));
+    if (stab == 3) { KL(KC_EW, st, k_sep_scale<T, 1><<<eg, 256, 0, st>>>(w.W[0], n2, N, A0.D, N)); }
+    gemm<T, 1, 0, 0>(st, N, N, N, w.W[1], N, n2, w.W[0], N, n2, w.W[3], N, n2, NM);      // X = Q^H X0
+  } else {   // ZUNMQR: the block reflectors are applied to X0 directly
+    KL(KC_EW, st, k_permcopy<T, 4><<<eg, 256, 0, st>>>(w.W[3], N, n2, A0.U, N, n2, N, N, nullptr, 0));
+    if (stab == 3) { KL(KC_EW, st, k_sep_scale<T, 1><<<eg, 256, 0, st>>>(w.W[3], n2, N, A0.D, N)); }
+    launch_apply_q<T>(st, w.W[2], N, N, N, n2, w.Tbuf, w.W[3], N, n2, N, 0, false, NM);
+  }
   launch_trsm<T>(st, w.W[2], N, n2, w.W[3], N, n2, N, N, w.Dq, N, NM);                 // X = R^-1 D^-1 X
   KL(KC_EW, st, k_permcopy<T, 3><<<eg, 256, 0, st>>>(w.W[0], N, n2, w.W[3], N, n2, N, N, w.jpvt, N));   // X2 = P X
   if (stab == 3) { KL(KC_EW, st, k_sep_scale<T, 1><<<eg, 256, 0, st>>>(w.W[0], n2, N, A1.D, N)); }
@@ -199,10 +261,15 @@ static void la_cgr(LaWork<T>& w, int nvar, int stab, const UdvDev<T>& R, const U
 template <typename T>
 static void la_inverse(LaWork<T>& w, T* A, T* Ainv) {
   const int N = w.N, NM = w.NM; const long n2 = w.n2(); cudaStream_t st = w.st; dim3 eg(ew_blocks(n2), NM);
-  launch_qrp<T, 1>(st, A, N, N, N, n2, w.tau, N, w.jpvt, N, w.Dq, N, w.qrout, NM);
-  KL(KC_EW, st, k_permcopy<T, 0><<<eg, 256, 0, st>>>(w.W[0], N, n2, A, N, n2, N, N, nullptr, 0));
-  launch_formq<T>(st, w.W[0], N, N, N, n2, w.tau, N, nullptr, NM);
-  KL(KC_EW, st, k_permcopy<T, 4><<<eg, 256, 0, st>>>(w.W[1], N, n2, w.W[0], N, n2, N, N, nullptr, 0));      // Q^H
+  la_qrp<T>(w, A, N, N, w.Dq);
+  if (!use_blocked_qr<T>(N, N)) {
+    KL(KC_EW, st, k_permcopy<T, 0><<<eg, 256, 0, st>>>(w.W[0], N, n2, A, N, n2, N, N, nullptr, 0));
+    launch_formq<T>(st, w.W[0], N, N, N, n2, w.tau, N, nullptr, NM);
+    KL(KC_EW, st, k_permcopy<T, 4><<<eg, 256, 0, st>>>(w.W[1], N, n2, w.W[0], N, n2, N, N, nullptr, 0));      // Q^H
+  } else {
+    KL(KC_EW, st, k_set_identity<T><<<eg, 256, 0, st>>>(w.W[1], N, n2, N, N));
+    launch_apply_q<T>(st, A, N, N, N, n2, w.Tbuf, w.W[1], N, n2, N, 0, false, NM);                            // Q^H
+  }
   launch_trsm<T>(st, A, N, n2, w.W[1], N, n2, N, N, w.Dq, N, NM);                                            // R^-1 D^-1 Q^H
   KL(KC_EW, st, k_permcopy<T, 3><<<eg, 256, 0, st>>>(Ainv, N, n2, w.W[1], N, n2, N, N, w.jpvt, N));          // rows scattered by P
 }
@@ -219,13 +286,18 @@ static void la_cgr2_2(LaWork<T>& w, LaWork<T>& w2, int stab, const UdvDev<T>& ud
   // HLPB1 = HLPB2^H in w2.W[0]; right-hand side HLP in w2.W[1]
   if (stab == 3) KL(KC_EW, st, k_cgr22_build<T, 1><<<eg2, 256, 0, st>>>(w2.W[0], w2.W[1], n22, w.W[3], udv1.U, udv1.D, udv2.U, udv2.V, udv2.D, n2, N, N, first));
   else KL(KC_EW, st, k_cgr22_build<T, 0><<<eg2, 256, 0, st>>>(w2.W[0], w2.W[1], n22, w.W[3], udv1.U, udv1.D, udv2.U, udv2.V, udv2.D, n2, N, N, first));
-  launch_qrp<T, 1>(st, w2.W[0], N2, N2, N2, n22, w2.tau, N2, w2.jpvt, N2, w2.Dq, N2, w2.qrout, NM);
+  la_qrp<T>(w2, w2.W[0], N2, N2, w2.Dq);
   // HLP <- P^T-row gather (ZLAPMR forward), L = R^H, HLP <- L^-1 HLP, rows / D3, HLP <- Q HLP
   KL(KC_EW, st, k_permcopy<T, 1><<<eg2, 256, 0, st>>>(w2.W[2], N2, n22, w2.W[1], N2, n22, N2, N2, w2.jpvt, N2));
   KL(KC_EW, st, k_permcopy<T, 4><<<eg2, 256, 0, st>>>(w2.W[3], N2, n22, w2.W[0], N2, n22, N2, N2, nullptr, 0));   // full conj-transpose; only its lower triangle (R^H) is read
   launch_trsm<T, 1>(st, w2.W[3], N2, n22, w2.W[2], N2, n22, N2, N2, nullptr, 0, NM);
   KL(KC_EW, st, k_rowscale_inv<T><<<eg2, 256, 0, st>>>(w2.W[2], N2, n22, N2, N2, w2.Dq, N2));
-  launch_formq<T>(st, w2.W[0], N2, N2, N2, n22, w2.tau, N2, nullptr, NM);
-  gemm<T, 0, 0, 0>(st, N2, N2, N2, w2.W[0], N2, n22, w2.W[2], N2, n22, w2.W[1], N2, n22, NM);
-  KL(KC_EW, st, k_cgr22_blocks<T><<<eg, 256, 0, st>>>(w2.W[1], n22, GT0, G00, GTT, G0T, n2, N, first));
+  if (!use_blocked_qr<T>(N2, N2)) {
+    launch_formq<T>(st, w2.W[0], N2, N2, N2, n22, w2.tau, N2, nullptr, NM);
+    gemm<T, 0, 0, 0>(st, N2, N2, N2, w2.W[0], N2, n22, w2.W[2], N2, n22, w2.W[1], N2, n22, NM);
+    KL(KC_EW, st, k_cgr22_blocks<T><<<eg, 256, 0, st>>>(w2.W[1], n22, GT0, G00, GTT, G0T, n2, N, first));
+  } else {
+    launch_apply_q<T>(st, w2.W[0], N2, N2, N2, n22, w2.Tbuf, w2.W[2], N2, n22, N2, 1, false, NM);             // HLP <- Q HLP (ZUNMQR 'L','N')
+    KL(KC_EW, st, k_cgr22_blocks<T><<<eg, 256, 0, st>>>(w2.W[2], n22, GT0, G00, GTT, G0T, n2, N, first));
+  }
 }

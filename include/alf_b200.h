@@ -107,6 +107,10 @@ int alf_b200_get_obs(alf_b200_handle* h, double* out);
 int alf_b200_test_qdrp(int device, int is_complex, int m, int n, int batch, double* A /* complex m*n*batch, in/out */,
                        double* D /* n*batch */, int* jpvt /* n*batch, 1-based */, double* tau /* complex n*batch */,
                        double* phases /* 5*batch: perm sign, diag phase re/im, detq re/im */);
+/* the blocked, windowed-pivoting QR used by the sweep for matrices beyond one SM's shared memory (alf_qrblk.cuh), plus the explicit
+ * Q (complex m*m*batch) formed through the compact-WY application (replaces ZUNGQR) */
+int alf_b200_test_qdrp_blocked(int device, int is_complex, int m, int n, int batch, double* A, double* D, int* jpvt, double* tau,
+                               double* phases, double* Q);
 int alf_b200_test_udv_decompose(int device, int is_complex, int n, int batch, char side, double* U, double* D, double* V);
 int alf_b200_test_cgr(int device, int is_complex, int n, int batch, int nvar, int stab, const double* UR, const double* DR,
                       const double* VR, const double* UL, const double* DL, const double* VL, const double* detUR,
