@@ -42,7 +42,7 @@ def reduce_control(ctl_vec, dst: int = 0):
     if not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
         return v.numpy()
     dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
-    s = v.to(dev); m = v.to(dev)
+    s = v.to(dev).clone(); m = v.to(dev).clone()        # .to() aliases on CPU: the two reductions need distinct buffers
     dist.reduce(s, dst=dst, op=dist.ReduceOp.SUM); dist.reduce(m, dst=dst, op=dist.ReduceOp.MAX)
     out = s.cpu().numpy()
     for i in (1, 3, 5, 11, 12):
