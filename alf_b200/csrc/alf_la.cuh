@@ -8,6 +8,7 @@
 // One CTA works on one matrix (QR/formQ) or one tile / column panel of one matrix (GEMM/TRSM);
 // the batch (chains x flavors) is the grid's second dimension.
 #pragma once
+#include <type_traits>
 #include "alf_types.cuh"
 
 // ------------------------------------------------------------------------------------------------
@@ -31,6 +32,9 @@ __global__ void __launch_bounds__(256) k_gemm(int M, int N, int K, const T* __re
   A += (long)b * sA; B += (long)b * sB; C += (long)b * sC;
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
   const int m0 = tm * GEMM_BM, n0 = tn * GEMM_BN;
+  constexpr bool kDmma = std::is_same<T, double>::value;     // real: FP64 tensor cores, warp tile 16 x 32 (2 x 4 fragments)
+  const int lane = tid & 31, warp = tid >> 5, fg = lane >> 2, fq = lane & 3;
+  const int wm = (warp & 3) * 16, wn = (warp >> 2) * 32;
   T acc[4][4];
 #pragma unroll
   for (int i = 0; i < 4; ++i)
@@ -79,28 +83,56 @@ __global__ void __launch_bounds__(256) k_gemm(int M, int N, int K, const T* __re
       }
     }
     __syncthreads();
+    if constexpr (kDmma) {
+      // acc[2*ia + (ib >> 1)][2 * (ib & 1) + h] <-> C(wm + 8 ia + fg, wn + 8 ib + 2 fq + h)
 #pragma unroll
-    for (int kk = 0; kk < GEMM_BK; ++kk) {
-      T a[4], bb[4];
+      for (int ks = 0; ks < GEMM_BK / 4; ++ks) {
+        double a[2], bb[4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) a[i] = As[kk][tx * 4 + i];
+        for (int ia = 0; ia < 2; ++ia) a[ia] = As[4 * ks + fq][wm + 8 * ia + fg];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) bb[j] = Bs[kk][ty * 4 + j];
+        for (int ib = 0; ib < 4; ++ib) bb[ib] = Bs[4 * ks + fq][wn + 8 * ib + fg];
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+        for (int ia = 0; ia < 2; ++ia)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) fma_(acc[i][j], a[i], bb[j]);
+          for (int ib = 0; ib < 4; ++ib) dmma884(acc[2 * ia + (ib >> 1)][2 * (ib & 1)], acc[2 * ia + (ib >> 1)][2 * (ib & 1) + 1], a[ia], bb[ib]);
+      }
+    } else {
+#pragma unroll
+      for (int kk = 0; kk < GEMM_BK; ++kk) {
+        T a[4], bb[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) a[i] = As[kk][tx * 4 + i];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) bb[j] = Bs[kk][ty * 4 + j];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) fma_(acc[i][j], a[i], bb[j]);
+      }
     }
     __syncthreads();
   }
+  if constexpr (kDmma) {
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    int gn = n0 + ty * 4 + j;
-    if (gn >= N) continue;
+    for (int ia = 0; ia < 2; ++ia)
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      int gm = m0 + tx * 4 + i;
-      if (gm < M) C[gm + (long)gn * ldc] = acc[i][j];
+      for (int ib = 0; ib < 4; ++ib)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int gm = m0 + wm + 8 * ia + fg, gn = n0 + wn + 8 * ib + 2 * fq + h;
+          if (gm < M && gn < N) C[gm + (long)gn * ldc] = acc[2 * ia + (ib >> 1)][2 * (ib & 1) + h];
+        }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int gn = n0 + ty * 4 + j;
+      if (gn >= N) continue;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        int gm = m0 + tx * 4 + i;
+        if (gm < M) C[gm + (long)gn * ldc] = acc[i][j];
+      }
     }
   }
 }
@@ -383,6 +415,124 @@ __global__ void __launch_bounds__(TRSM_WARPS * 32) k_trsm_lun(const T* __restric
       int i = lane + 32 * q, c = c0 + cc;
       if (i < n && c < nrhs) B[i + (long)c * ldb] = x[cc][q];
     }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Blocked triangular solve on the FP64 tensor cores (real matrices): X = R^-1 diag(dinv)^-1 B (LOWER = 0, back substitution,
+// strict lower part of the stored matrix ignored) or X = L^-1 B (LOWER = 1, forward substitution, strict upper part ignored).
+// Step 1 (k_tri_inv_blocks): the 32 x 32 diagonal blocks are inverted, one warp per block (lane j solves for column j).
+// Step 2 (k_trsm_blk): a CTA owns TRSMB_CW right-hand sides of one matrix in shared memory and sweeps the block rows:
+//   X_k = inv(R_kk) B_k ;  B_i -= R_ik X_k for the remaining block rows i     -- both as DMMA m8n8k4 products whose A operand
+//   (R, inv(R_kk)) is read from global memory / L2 directly in fragment layout and whose B operand is the X panel.
+// n is zero-padded to a multiple of 32 (identity on the padded diagonal).
+// ------------------------------------------------------------------------------------------------
+#define TRSMB_BS 32
+#define TRSMB_CW 32
+template <int LOWER>
+__global__ void __launch_bounds__(32) k_tri_inv_blocks(const double* __restrict__ R, int ldr, long sR, int n, double* __restrict__ Rinv, long sI) {
+  __shared__ double Rs[32][33];
+  __shared__ double Xs[32][33];      // Xs[k][j]: entry k of column j of the inverse
+  const int kb = blockIdx.x, b = blockIdx.y, lane = threadIdx.x, k0 = kb * 32;
+  R += (long)b * sR; Rinv += (long)b * sI + (long)kb * 1024;
+  for (int c = 0; c < 32; ++c) {
+    const int i = k0 + lane, j = k0 + c;
+    double v = (lane == c) ? 1.0 : 0.0;
+    if (i < n && j < n && (LOWER ? (i >= j) : (i <= j))) v = R[i + (long)j * ldr];
+    Rs[lane][c] = v;
+  }
+  for (int k = 0; k < 32; ++k) Xs[k][lane] = 0.0;
+  __syncwarp();
+  const int j = lane;
+  if (!LOWER) {
+    for (int i = 31; i >= 0; --i) {
+      double s = (i == j) ? 1.0 : 0.0;
+      for (int k = i + 1; k < 32; ++k) s = fma(-Rs[i][k], Xs[k][j], s);
+      Xs[i][j] = (i <= j) ? s / Rs[i][i] : 0.0;
+    }
+  } else {
+    for (int i = 0; i < 32; ++i) {
+      double s = (i == j) ? 1.0 : 0.0;
+      for (int k = 0; k < i; ++k) s = fma(-Rs[i][k], Xs[k][j], s);
+      Xs[i][j] = (i >= j) ? s / Rs[i][i] : 0.0;
+    }
+  }
+  __syncwarp();
+  for (int c = 0; c < 32; ++c) Rinv[lane + c * 32] = Xs[lane][c];      // column-major 32 x 32
+}
+
+template <int LOWER>
+__global__ void __launch_bounds__(256) k_trsm_blk(const double* __restrict__ R, int ldr, long sR, const double* __restrict__ Rinv, long sI,
+                                                  double* __restrict__ B, int ldb, long sB, int n, int nrhs, const double* __restrict__ dinv, long sD) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* Xs = reinterpret_cast<double*>(smem_raw);          // [TRSMB_CW][ldx], rows contiguous
+  const int b = blockIdx.y, tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = nthr >> 5;
+  const int g = lane >> 2, q = lane & 3;
+  R += (long)b * sR; Rinv += (long)b * sI; B += (long)b * sB;
+  if (dinv) dinv += (long)b * sD;
+  const int np = (n + 31) & ~31, nb = np >> 5, ldx = ld_pad(np);
+  const int c0 = blockIdx.x * TRSMB_CW;
+  for (int e = tid; e < np * TRSMB_CW; e += nthr) {
+    const int i = e % np, c = e / np;
+    double v = 0.0;
+    if (i < n && c0 + c < nrhs) { v = B[i + (long)(c0 + c) * ldb]; if (dinv) v = v * (1.0 / dinv[i]); }
+    Xs[i + c * ldx] = v;
+  }
+  __syncthreads();
+  for (int s = 0; s < nb; ++s) {
+    const int kb = LOWER ? s : nb - 1 - s, k0 = kb * 32;
+    // B fragments of the current block row of X: bf[ks][cb] = X(k0 + 4 ks + q, 8 cb + g)
+    double bf[8][4];
+#pragma unroll
+    for (int ks = 0; ks < 8; ++ks)
+#pragma unroll
+      for (int cb = 0; cb < 4; ++cb) bf[ks][cb] = Xs[(k0 + 4 * ks + q) + (8 * cb + g) * ldx];
+    // ---- X_k = inv(R_kk) B_k : 4 row tiles of 8 rows, warps 0..3
+    double acc[4][2];
+    if (warp < 4) {
+      double af[8];
+      const double* ri = Rinv + (long)kb * 1024 + (8 * warp + g);
+#pragma unroll
+      for (int ks = 0; ks < 8; ++ks) af[ks] = ri[(4 * ks + q) * 32];
+#pragma unroll
+      for (int cb = 0; cb < 4; ++cb) { acc[cb][0] = 0.0; acc[cb][1] = 0.0; }
+#pragma unroll
+      for (int ks = 0; ks < 8; ++ks)
+#pragma unroll
+        for (int cb = 0; cb < 4; ++cb) dmma884(acc[cb][0], acc[cb][1], af[ks], bf[ks][cb]);
+    }
+    __syncthreads();                     // every warp holds the old block row in bf
+    if (warp < 4) {
+#pragma unroll
+      for (int cb = 0; cb < 4; ++cb) { Xs[(k0 + 8 * warp + g) + (8 * cb + 2 * q) * ldx] = acc[cb][0]; Xs[(k0 + 8 * warp + g) + (8 * cb + 2 * q + 1) * ldx] = acc[cb][1]; }
+    }
+    __syncthreads();
+    if (s == nb - 1) break;
+#pragma unroll
+    for (int ks = 0; ks < 8; ++ks)
+#pragma unroll
+      for (int cb = 0; cb < 4; ++cb) bf[ks][cb] = Xs[(k0 + 4 * ks + q) + (8 * cb + g) * ldx];
+    // ---- B_i -= R_ik X_k for the block rows not yet solved: 8-row tiles over the warps
+    const int r_lo = LOWER ? (k0 + 32) : 0, r_hi = LOWER ? np : k0;
+    for (int i0 = r_lo + 8 * warp; i0 < r_hi; i0 += 8 * nw) {
+      double af[8];
+      const int i = i0 + g;
+#pragma unroll
+      for (int ks = 0; ks < 8; ++ks) { const int k = k0 + 4 * ks + q; af[ks] = (i < n && k < n) ? -R[i + (long)k * ldr] : 0.0; }
+#pragma unroll
+      for (int cb = 0; cb < 4; ++cb) { acc[cb][0] = Xs[i + (8 * cb + 2 * q) * ldx]; acc[cb][1] = Xs[i + (8 * cb + 2 * q + 1) * ldx]; }
+#pragma unroll
+      for (int ks = 0; ks < 8; ++ks)
+#pragma unroll
+        for (int cb = 0; cb < 4; ++cb) dmma884(acc[cb][0], acc[cb][1], af[ks], bf[ks][cb]);
+#pragma unroll
+      for (int cb = 0; cb < 4; ++cb) { Xs[i + (8 * cb + 2 * q) * ldx] = acc[cb][0]; Xs[i + (8 * cb + 2 * q + 1) * ldx] = acc[cb][1]; }
+    }
+    __syncthreads();
+  }
+  for (int e = tid; e < n * TRSMB_CW; e += nthr) {
+    const int i = e % n, c = e / n;
+    if (c0 + c < nrhs) B[i + (long)(c0 + c) * ldb] = Xs[i + c * ldx];
+  }
 }
 
 // ------------------------------------------------------------------------------------------------

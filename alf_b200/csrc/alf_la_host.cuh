@@ -4,6 +4,7 @@
 #include <cstdio>
 #include <stdexcept>
 #include <string>
+#include <type_traits>
 #include <vector>
 #include "alf_la.cuh"
 #include "alf_qrblk.cuh"
@@ -54,6 +55,8 @@ struct LaWork {
   T* W[4] = {nullptr, nullptr, nullptr, nullptr};
   T* tau = nullptr; int* jpvt = nullptr; double* Dq = nullptr; QrOut* qrout = nullptr; cplx* sc_phase = nullptr; cplx* sc_beta = nullptr;
   T* Tbuf = nullptr;      // compact-WY factors of the blocked QR: [matrix][panel][QRB_NB x QRB_NB]
+  double* Rinv = nullptr; // inverted 32 x 32 diagonal blocks of the blocked triangular solve: [matrix][(N + 32) * 32]
+  long sRinv() const { return (long)(N + 32) * 32; }
   long n2() const { return (long)N * N; }
   void alloc(int n, int nm, cudaStream_t s) {
     N = n; NM = nm; st = s;
@@ -62,11 +65,12 @@ struct LaWork {
     CK(cudaMalloc(&Dq, sizeof(double) * (long)N * NM)); CK(cudaMalloc(&qrout, sizeof(QrOut) * NM));
     CK(cudaMalloc(&sc_phase, sizeof(cplx) * NM)); CK(cudaMalloc(&sc_beta, sizeof(cplx) * NM));
     CK(cudaMalloc(&Tbuf, sizeof(T) * (size_t)(N + 32) * 32 * NM));
+    CK(cudaMalloc(&Rinv, sizeof(double) * (size_t)(N + 32) * 32 * NM));
   }
   void release() {
     for (int i = 0; i < 4; ++i) if (W[i]) cudaFree(W[i]);
     if (tau) cudaFree(tau); if (jpvt) cudaFree(jpvt); if (Dq) cudaFree(Dq); if (qrout) cudaFree(qrout);
-    if (sc_phase) cudaFree(sc_phase); if (sc_beta) cudaFree(sc_beta); if (Tbuf) cudaFree(Tbuf); Tbuf = nullptr;
+    if (sc_phase) cudaFree(sc_phase); if (sc_beta) cudaFree(sc_beta); if (Tbuf) cudaFree(Tbuf); Tbuf = nullptr; if (Rinv) cudaFree(Rinv); Rinv = nullptr;
     for (int i = 0; i < 4; ++i) W[i] = nullptr; tau = nullptr; jpvt = nullptr; Dq = nullptr; qrout = nullptr; sc_phase = sc_beta = nullptr;
   }
 };
@@ -115,8 +119,26 @@ static void launch_formq(cudaStream_t st, T* A, int m, int n, int ld, long sA, c
 #undef FQ_LAUNCH
 }
 
+// real matrices: blocked DMMA solve; rinv = workspace of ((n + 31) / 32) * 1024 doubles per matrix (stride sI)
+template <int LOWER>
+static void launch_trsm_blk(cudaStream_t st, const double* R, int ldr, long sR, double* B, int ldb, long sB, int n, int nrhs, const double* dinv, long sD,
+                            double* rinv, long sI, int batch) {
+  const int np = (n + 31) & ~31, nb = np / 32;
+  const size_t smem = sizeof(double) * (size_t)ld_pad(np) * TRSMB_CW;
+  KL(KC_TRSM, st, k_tri_inv_blocks<LOWER><<<dim3(nb, batch), 32, 0, st>>>(R, ldr, sR, n, rinv, sI));
+  CK(cudaFuncSetAttribute(k_trsm_blk<LOWER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  KL(KC_TRSM, st, k_trsm_blk<LOWER><<<dim3((nrhs + TRSMB_CW - 1) / TRSMB_CW, batch), 256, smem, st>>>(R, ldr, sR, rinv, sI, B, ldb, sB, n, nrhs, dinv, sD));
+}
+static inline bool la_force_old_trsm() { static int v = -1; if (v < 0) v = getenv("ALF_B200_OLD_TRSM") ? 1 : 0; return v == 1; }
+
 template <typename T, int LOWER = 0>
-static void launch_trsm(cudaStream_t st, const T* R, int ldr, long sR, T* B, int ldb, long sB, int n, int nrhs, const double* dinv, long sD, int batch) {
+static void launch_trsm(cudaStream_t st, const T* R, int ldr, long sR, T* B, int ldb, long sB, int n, int nrhs, const double* dinv, long sD, int batch,
+                        double* rinv = nullptr, long sI = 0) {
+  if constexpr (std::is_same<T, double>::value) {
+    if (rinv && !la_force_old_trsm() && sizeof(double) * (size_t)ld_pad((n + 31) & ~31) * TRSMB_CW <= 220 * 1024) {
+      launch_trsm_blk<LOWER>(st, R, ldr, sR, B, ldb, sB, n, nrhs, dinv, sD, rinv, sI, batch); return;
+    }
+  }
   dim3 grid((nrhs + TRSM_COLS - 1) / TRSM_COLS, batch);
   size_t smem = sizeof(T) * n;
   KScope ks_(KC_TRSM, st);
@@ -247,7 +269,7 @@ static void la_cgr(LaWork<T>& w, int nvar, int stab, const UdvDev<T>& R, const U
     if (stab == 3) { KL(KC_EW, st, k_sep_scale<T, 1><<<eg, 256, 0, st>>>(w.W[3], n2, N, A0.D, N)); }
     launch_apply_q<T>(st, w.W[2], N, N, N, n2, w.Tbuf, w.W[3], N, n2, N, 0, false, NM);
   }
-  launch_trsm<T>(st, w.W[2], N, n2, w.W[3], N, n2, N, N, w.Dq, N, NM);                 // X = R^-1 D^-1 X
+  launch_trsm<T>(st, w.W[2], N, n2, w.W[3], N, n2, N, N, w.Dq, N, NM, w.Rinv, w.sRinv());                 // X = R^-1 D^-1 X
   KL(KC_EW, st, k_permcopy<T, 3><<<eg, 256, 0, st>>>(w.W[0], N, n2, w.W[3], N, n2, N, N, w.jpvt, N));   // X2 = P X
   if (stab == 3) { KL(KC_EW, st, k_sep_scale<T, 1><<<eg, 256, 0, st>>>(w.W[0], n2, N, A1.D, N)); }
   if (nvar == 1) gemm<T, 0, 0, 0>(st, N, N, N, L.U, N, n2, w.W[0], N, n2, Gout, N, n2, NM);        // G = U_L X2
@@ -270,7 +292,7 @@ static void la_inverse(LaWork<T>& w, T* A, T* Ainv) {
     KL(KC_EW, st, k_set_identity<T><<<eg, 256, 0, st>>>(w.W[1], N, n2, N, N));
     launch_apply_q<T>(st, A, N, N, N, n2, w.Tbuf, w.W[1], N, n2, N, 0, false, NM);                            // Q^H
   }
-  launch_trsm<T>(st, A, N, n2, w.W[1], N, n2, N, N, w.Dq, N, NM);                                            // R^-1 D^-1 Q^H
+  launch_trsm<T>(st, A, N, n2, w.W[1], N, n2, N, N, w.Dq, N, NM, w.Rinv, w.sRinv());                                            // R^-1 D^-1 Q^H
   KL(KC_EW, st, k_permcopy<T, 3><<<eg, 256, 0, st>>>(Ainv, N, n2, w.W[1], N, n2, N, N, w.jpvt, N));          // rows scattered by P
 }
 
@@ -290,7 +312,7 @@ static void la_cgr2_2(LaWork<T>& w, LaWork<T>& w2, int stab, const UdvDev<T>& ud
   // HLP <- P^T-row gather (ZLAPMR forward), L = R^H, HLP <- L^-1 HLP, rows / D3, HLP <- Q HLP
   KL(KC_EW, st, k_permcopy<T, 1><<<eg2, 256, 0, st>>>(w2.W[2], N2, n22, w2.W[1], N2, n22, N2, N2, w2.jpvt, N2));
   KL(KC_EW, st, k_permcopy<T, 4><<<eg2, 256, 0, st>>>(w2.W[3], N2, n22, w2.W[0], N2, n22, N2, N2, nullptr, 0));   // full conj-transpose; only its lower triangle (R^H) is read
-  launch_trsm<T, 1>(st, w2.W[3], N2, n22, w2.W[2], N2, n22, N2, N2, nullptr, 0, NM);
+  launch_trsm<T, 1>(st, w2.W[3], N2, n22, w2.W[2], N2, n22, N2, N2, nullptr, 0, NM, w2.Rinv, w2.sRinv());
   KL(KC_EW, st, k_rowscale_inv<T><<<eg2, 256, 0, st>>>(w2.W[2], N2, n22, N2, N2, w2.Dq, N2));
   if (!use_blocked_qr<T>(N2, N2)) {
     launch_formq<T>(st, w2.W[0], N2, N2, N2, n22, w2.tau, N2, nullptr, NM);

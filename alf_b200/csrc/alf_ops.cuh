@@ -9,7 +9,7 @@
 // ALL requested time slices to it, and writes it back: one HBM read + one write of the matrix per wrap
 // (2*w*N^2 bytes) instead of one per operator.  Operators with disjoint support are grouped in
 // "levels" on the host (checkerboard families are levels by construction); inside a level every (operator, lane)
-// pair is an independent work item, levels are separated by __syncthreads().
+// pair is an independent work item, levels are separated by __syncthreads().  See k_apply_ops below for the mapping.
 #pragma once
 #include "alf_types.cuh"
 
@@ -19,7 +19,7 @@
 
 struct OpListDev {
   int n_ops, n_levels, nvar;        // nvar = 1: fixed matrices (hopping); nvar = 5: field dependent (vertices)
-  const int* level_start;           // n_levels + 1
+  const int* level_start;           // n_levels + 1  (levels are cut into chunks of <= OPS_CH operators)
   const int* k;                     // n_ops
   const int* P;                     // n_ops * ALF_KMAX   (0-based)
   const int* fidx;                  // n_ops : field index n (0-based) or -1
@@ -45,100 +45,157 @@ struct ModelDev {
   OpListDev lists[L_COUNT][ALF_FMAX];
 };
 
+// Every launch executes a "program": for each requested time slice, up to two operator lists in a fixed order.  The lists are
+// cut on the host into CHUNKS of at most OPS_CH operators with pairwise disjoint support (checkerboard families are such
+// sets by construction; longer ones are split), so inside a chunk every (operator, panel lane) pair is independent work.
+//  * lanes of a warp = the 32 columns (rows) of the panel, a warp walks over the operators of the chunk: the operator
+//    descriptor is warp-uniform and comes from shared memory (broadcast), the data accesses S[P * ldp + lane] are conflict free;
+//  * the descriptors of chunk t+1 (support, k, and the k x k matrix of the field value found in nsigma for vertex lists) are
+//    fetched from global memory into registers while chunk t is processed and land in the other half of a double buffer:
+//    one block-wide barrier per chunk.
+#define OPS_CH 64            // operators per chunk
+#define OPS_PW 32            // panel width = warp size
+#define OPS_MPT 4            // descriptor-matrix entries prefetched per thread: OPS_CH * KMAX^2 / 256
+
 template <typename T>
-__device__ __forceinline__ void apply_list(T* __restrict__ S, int ldp, int pw, const OpListDev& L, const int8_t* __restrict__ fld) {
-  const T* mats = reinterpret_cast<const T*>(L.mat);
-  const int tid = threadIdx.x, nthr = blockDim.x;
-  for (int lv = 0; lv < L.n_levels; ++lv) {
-    const int a0 = L.level_start[lv], a1 = L.level_start[lv + 1];
-    const int work = (a1 - a0) * pw;
-    for (int idx = tid; idx < work; idx += nthr) {
-      const int o = a0 + idx / pw, lane = idx % pw;
-      const int k = L.k[o];
-      int var = 0;
-      if (L.nvar > 1) var = (int)fld[L.fidx[o]] + 2;
-      const T* A = mats + ((long)o * L.nvar + var) * (ALF_KMAX * ALF_KMAX);
-      const int* P = L.P + o * ALF_KMAX;
-      if (k == 1) {
-        T* p = S + (long)P[0] * ldp + lane;
-        *p = A[0] * (*p);
-      } else if (k == 2) {
-        T* p0 = S + (long)P[0] * ldp + lane; T* p1 = S + (long)P[1] * ldp + lane;
-        T v0 = *p0, v1 = *p1;
-        *p0 = A[0] * v0 + A[ALF_KMAX] * v1;
-        *p1 = A[1] * v0 + A[ALF_KMAX + 1] * v1;
+struct OpsDesc { T* dM[2]; int* dP[2]; int* dK[2]; };
+
+template <typename T>
+__device__ __forceinline__ void ops_process_chunk(T* __restrict__ S, int ldp, bool lane_ok, int cnt, const int* __restrict__ dP, const int* __restrict__ dK,
+                                                  const T* __restrict__ dM, int lk) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const int kk = 1 << lk, ms = 1 << (2 * lk);
+  for (int o = warp; o < cnt; o += 2 * nw) {
+    const int o2 = o + nw; const bool two = o2 < cnt;
+    const int k = dK[o], k2 = two ? dK[o2] : 0;
+    if (k == 2 && (k2 == 2 || !two)) {       // common case (bond operators): two independent operators in flight
+      const int4 P = reinterpret_cast<const int4*>(dP)[o]; const T* A = dM + o * ms;
+      const int4 Q = reinterpret_cast<const int4*>(dP)[two ? o2 : o]; const T* Bm = dM + (two ? o2 : o) * ms;
+      T* p0 = S + (long)P.x * ldp + lane; T* p1 = S + (long)P.y * ldp + lane;
+      T* q0 = S + (long)Q.x * ldp + lane; T* q1 = S + (long)Q.y * ldp + lane;
+      const T a00 = A[0], a10 = A[1], a01 = A[kk], a11 = A[kk + 1];
+      const T b00 = Bm[0], b10 = Bm[1], b01 = Bm[kk], b11 = Bm[kk + 1];
+      if (lane_ok) {
+        const T v0 = *p0, v1 = *p1, w0 = *q0, w1 = *q1;
+        *p0 = a00 * v0 + a01 * v1; *p1 = a10 * v0 + a11 * v1;
+        if (two) { *q0 = b00 * w0 + b01 * w1; *q1 = b10 * w0 + b11 * w1; }
+      }
+      continue;
+    }
+    for (int h = 0; h < (two ? 2 : 1); ++h) {
+      const int oo = h ? o2 : o, kc = h ? k2 : k;
+      const int4 P = reinterpret_cast<const int4*>(dP)[oo]; const T* A = dM + oo * ms;
+      if (!lane_ok) continue;
+      if (kc == 1) { T* p = S + (long)P.x * ldp + lane; *p = A[0] * (*p); }
+      else if (kc == 2) {
+        T* p0 = S + (long)P.x * ldp + lane; T* p1 = S + (long)P.y * ldp + lane;
+        const T v0 = *p0, v1 = *p1;
+        *p0 = A[0] * v0 + A[kk] * v1; *p1 = A[1] * v0 + A[kk + 1] * v1;
       } else {
+        const int Pa[ALF_KMAX] = {P.x, P.y, P.z, P.w};
         T v[ALF_KMAX], r[ALF_KMAX];
 #pragma unroll
-        for (int a = 0; a < ALF_KMAX; ++a) v[a] = (a < k) ? S[(long)P[a] * ldp + lane] : zero_<T>();
+        for (int a = 0; a < ALF_KMAX; ++a) v[a] = (a < kc) ? S[(long)Pa[a] * ldp + lane] : zero_<T>();
 #pragma unroll
         for (int a = 0; a < ALF_KMAX; ++a) {
-          T s = zero_<T>();
+          T sacc = zero_<T>();
 #pragma unroll
-          for (int b = 0; b < ALF_KMAX; ++b) if (b < k) fma_(s, A[a + b * ALF_KMAX], v[b]);
-          r[a] = s;
+          for (int b = 0; b < ALF_KMAX; ++b) if (a < kc && b < kc) fma_(sacc, A[a + b * kk], v[b]);
+          r[a] = sacc;
         }
 #pragma unroll
-        for (int a = 0; a < ALF_KMAX; ++a) if (a < k) S[(long)P[a] * ldp + lane] = r[a];
+        for (int a = 0; a < ALF_KMAX; ++a) if (a < kc) S[(long)Pa[a] * ldp + lane] = r[a];
       }
     }
-    __syncthreads();
   }
 }
 
-// SIDE 0: panel of PW columns [c0, c0+PW) of M;  S[i][j] = M(i, c0+j)
-// SIDE 1: panel of PW rows    [r0, r0+PW) of M;  S[i][j] = M(r0+j, i)   (right multiplication = left on the transpose)
-// grid = (ceil(nvec/PW), n_matrices); matrix b belongs to chain b / F, flavor b % F.
+// SIDE 0: panel of OPS_PW columns [v0, v0+pw) of M;  S[i][j] = M(i, v0+j)
+// SIDE 1: panel of OPS_PW rows    [v0, v0+pw) of M;  S[i][j] = M(v0+j, i)   (right multiplication = left on the transpose)
+// grid = (ceil(nvec/OPS_PW), n_matrices); matrix b belongs to chain b / F, flavor b % F.  lk = log2 of the largest operator size.
 template <typename T, int SIDE>
-__global__ void __launch_bounds__(256) k_apply_ops(T* __restrict__ M, long sM, int N, int nvec, int pw_max, ModelDev md, int F, int mode,
-                                                   int nt_a, int nt_b, const int8_t* __restrict__ fields, int Ltrot, int n_opv) {
+__global__ void __launch_bounds__(256) k_apply_ops(T* __restrict__ M, long sM, int N, int nvec, ModelDev md, int F, int mode,
+                                                   int nt_a, int nt_b, const int8_t* __restrict__ fields, int Ltrot, int n_opv, int lk) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int ldp = OPS_PW + 1, ms = 1 << (2 * lk), kk = 1 << lk;
   T* S = reinterpret_cast<T*>(smem_raw);
+  T* dMb = S + (long)N * ldp;
+  int* dPb = reinterpret_cast<int*>(dMb + 2 * OPS_CH * ms);
+  int* dKb = dPb + 2 * OPS_CH * 4;
   const int b = blockIdx.y, chain = b / F, f = b % F;
   M += (long)b * sM;
-  const int v0 = blockIdx.x * pw_max;
-  const int pw = min(pw_max, nvec - v0);
-  const int ldp = pw_max + 1;
-  const int tid = threadIdx.x, nthr = blockDim.x;
-  // ---- stage
-  if (SIDE == 0) {
-    for (int e = tid; e < N * pw; e += nthr) { int i = e % N, j = e / N; S[(long)i * ldp + j] = M[i + (long)(v0 + j) * N]; }
-  } else {
-    for (int e = tid; e < N * pw; e += nthr) { int j = e % pw, i = e / pw; S[(long)i * ldp + j] = M[(v0 + j) + (long)i * N]; }
-  }
-  __syncthreads();
-  const int8_t* fbase = fields ? fields + (long)chain * Ltrot * n_opv : nullptr;
+  const int v0 = blockIdx.x * OPS_PW;
+  const int pw = min(OPS_PW, nvec - v0);
+  const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = nthr >> 5;
+  // ---- the program of this launch
+  int li0 = -1, li1 = -1, uf0 = 0, uf1 = 0, dir = 1;
   switch (mode) {
-    case MODE_WRAPUR:
-      for (int nt = nt_a; nt <= nt_b; ++nt) {
-        apply_list<T>(S, ldp, pw, md.lists[L_TL_FWD][f], nullptr);
-        apply_list<T>(S, ldp, pw, md.lists[L_VL_N][f], fbase + (long)(nt - 1) * n_opv);
+    case MODE_WRAPUR: li0 = L_TL_FWD; li1 = L_VL_N; uf1 = 1; break;
+    case MODE_WRAPUL: li0 = L_VL_C; uf0 = 1; li1 = L_TL_C; dir = -1; break;
+    case MODE_TL_FWD: li0 = L_TL_FWD; break;
+    case MODE_TL_INV: li0 = L_TL_INV; break;
+    case MODE_TL_C: li0 = L_TL_C; break;
+    case MODE_TL_HALF: li0 = L_TL_HALF; break;
+    case MODE_TR_FWD: li0 = L_TR_FWD; break;
+    case MODE_TR_INV: li0 = L_TR_INV; break;
+    case MODE_TR_HALFINV: li0 = L_TR_HALFINV; break;
+    case MODE_PROPRM1: li0 = L_TR_INV; li1 = L_VR_INV; uf1 = 1; break;
+  }
+  const OpListDev& La = md.lists[li0][f];
+  const OpListDev& Lb = md.lists[li1 >= 0 ? li1 : li0][f];
+  const int nch0 = La.n_levels, nch1 = (li1 >= 0) ? Lb.n_levels : 0, per = nch0 + nch1;
+  const int ns = (uf0 || uf1) ? (nt_b - nt_a + 1) : 1, total = ns * per;
+  const int8_t* fbase = fields ? fields + (long)chain * Ltrot * n_opv : nullptr;
+
+  // descriptor prefetch registers
+  int rk = 0; int4 rP = make_int4(0, 0, 0, 0); T rM[OPS_MPT]; int rcnt = 0;
+  auto fetch = [&](int t) {
+    const int sl = t / per, r = t - sl * per;
+    const bool second = r >= nch0;
+    const OpListDev& L = second ? Lb : La;
+    const int c = second ? r - nch0 : r;
+    const int a0 = L.level_start[c]; rcnt = L.level_start[c + 1] - a0;
+    const int nt = (dir > 0) ? nt_a + sl : nt_b - sl;
+    const int8_t* fld = ((second ? uf1 : uf0) && fbase) ? fbase + (long)(nt - 1) * n_opv : nullptr;
+    if (tid < rcnt) { rk = L.k[a0 + tid]; rP = reinterpret_cast<const int4*>(L.P)[a0 + tid]; }
+    const T* mats = reinterpret_cast<const T*>(L.mat);
+#pragma unroll
+    for (int u = 0; u < OPS_MPT; ++u) {
+      const int e = tid + u * 256;
+      if (e < rcnt * ms) {
+        const int o = e >> (2 * lk), rr = e & (ms - 1), a = rr & (kk - 1), bb = rr >> lk, og = a0 + o;
+        int var = 0;
+        if (L.nvar > 1) var = (int)fld[L.fidx[og]] + 2;
+        rM[u] = mats[((long)og * L.nvar + var) * (ALF_KMAX * ALF_KMAX) + a + bb * ALF_KMAX];
       }
-      break;
-    case MODE_WRAPUL:
-      for (int nt = nt_b; nt >= nt_a; --nt) {
-        apply_list<T>(S, ldp, pw, md.lists[L_VL_C][f], fbase + (long)(nt - 1) * n_opv);
-        apply_list<T>(S, ldp, pw, md.lists[L_TL_C][f], nullptr);
-      }
-      break;
-    case MODE_TL_FWD: apply_list<T>(S, ldp, pw, md.lists[L_TL_FWD][f], nullptr); break;
-    case MODE_TL_INV: apply_list<T>(S, ldp, pw, md.lists[L_TL_INV][f], nullptr); break;
-    case MODE_TL_C: apply_list<T>(S, ldp, pw, md.lists[L_TL_C][f], nullptr); break;
-    case MODE_TL_HALF: apply_list<T>(S, ldp, pw, md.lists[L_TL_HALF][f], nullptr); break;
-    case MODE_TR_FWD: apply_list<T>(S, ldp, pw, md.lists[L_TR_FWD][f], nullptr); break;
-    case MODE_TR_INV: apply_list<T>(S, ldp, pw, md.lists[L_TR_INV][f], nullptr); break;
-    case MODE_TR_HALFINV: apply_list<T>(S, ldp, pw, md.lists[L_TR_HALFINV][f], nullptr); break;
-    case MODE_PROPRM1:
-      for (int nt = nt_a; nt <= nt_b; ++nt) {
-        apply_list<T>(S, ldp, pw, md.lists[L_TR_INV][f], nullptr);
-        apply_list<T>(S, ldp, pw, md.lists[L_VR_INV][f], fbase + (long)(nt - 1) * n_opv);
-      }
-      break;
+    }
+  };
+  auto commit = [&](int buf) {
+    if (tid < rcnt) { dKb[buf * OPS_CH + tid] = rk; reinterpret_cast<int4*>(dPb)[buf * OPS_CH + tid] = rP; }
+#pragma unroll
+    for (int u = 0; u < OPS_MPT; ++u) { const int e = tid + u * 256; if (e < rcnt * ms) dMb[buf * OPS_CH * ms + e] = rM[u]; }
+  };
+  if (total > 0) fetch(0);
+  // ---- stage the panel
+  if (SIDE == 0) {
+    for (int j = warp; j < pw; j += nw) { const T* col = M + (long)(v0 + j) * N; for (int i = lane; i < N; i += 32) S[(long)i * ldp + j] = col[i]; }
+  } else {
+    if (lane < pw) for (int i = warp; i < N; i += nw) S[(long)i * ldp + lane] = M[(v0 + lane) + (long)i * N];
+  }
+  int cnt_cur = rcnt;
+  if (total > 0) commit(0);
+  __syncthreads();
+  for (int t = 0; t < total; ++t) {
+    if (t + 1 < total) fetch(t + 1);
+    const int buf = t & 1;
+    ops_process_chunk<T>(S, ldp, lane < pw, cnt_cur, dPb + buf * OPS_CH * 4, dKb + buf * OPS_CH, dMb + buf * OPS_CH * ms, lk);
+    if (t + 1 < total) { commit(buf ^ 1); cnt_cur = rcnt; }
+    __syncthreads();
   }
   // ---- write back
   if (SIDE == 0) {
-    for (int e = tid; e < N * pw; e += nthr) { int i = e % N, j = e / N; M[i + (long)(v0 + j) * N] = S[(long)i * ldp + j]; }
+    for (int j = warp; j < pw; j += nw) { T* col = M + (long)(v0 + j) * N; for (int i = lane; i < N; i += 32) col[i] = S[(long)i * ldp + j]; }
   } else {
-    for (int e = tid; e < N * pw; e += nthr) { int j = e % pw, i = e / pw; M[(v0 + j) + (long)i * N] = S[(long)i * ldp + j]; }
+    if (lane < pw) for (int i = warp; i < N; i += nw) M[(v0 + lane) + (long)i * N] = S[(long)i * ldp + lane];
   }
 }

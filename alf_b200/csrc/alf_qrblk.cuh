@@ -56,7 +56,6 @@ __device__ __forceinline__ void blk_gemm(int M, int N, int K, const cplx* __rest
   }
 }
 
-__host__ __device__ inline int ld_pad(int rows) { int l = rows; while (l % 16 != 4) ++l; return l; }   // conflict-free DMMA fragment loads
 
 // Shared-memory footprint (bytes) of the blocked kernels for an m-row matrix: V panel, column tile, W, W2, T, reflector, norms, ints.
 template <typename T>

@@ -69,6 +69,12 @@ __device__ __forceinline__ double shfl_(double v, int l) { return __shfl_sync(0x
 __device__ __forceinline__ cplx shfl_(cplx v, int l) {
   return cplx(__shfl_sync(0xffffffffu, v.x, l), __shfl_sync(0xffffffffu, v.y, l));
 }
+// FP64 tensor-core tile product D(8x8) += A(8x4, row) B(4x8, col).  Lane l (g = l >> 2, q = l & 3) holds A[g][q], B[q][g] and
+// C[g][2q], C[g][2q+1].
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+__host__ __device__ inline int ld_pad(int rows) { int l = rows; while (l % 16 != 4) ++l; return l; }   // conflict-free DMMA fragment loads
 template <typename T> __device__ __forceinline__ T warp_sum(T v) {
 #pragma unroll
   for (int m = 16; m > 0; m >>= 1) v = v + shfl_xor_(v, m);

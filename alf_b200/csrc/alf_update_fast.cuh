@@ -19,9 +19,6 @@
 #pragma once
 #include "alf_update.cuh"
 
-__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
-  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
-}
 
 // G0 <- DL G0 DR - X Y^T, then DL = DR = 1.  Real: warp tiles of 32 x 32; the accumulator fragments are INITIALISED with the
 // scaled G0 tile (32 independent loads per thread issued up front, so the HBM/L2 latency is paid once per tile), then
