@@ -88,13 +88,17 @@ struct ListBuild {
       mat.push_back((a < kk && b < kk) ? mats[v][a + (size_t)b * kk] : cd(0, 0));
   }
   // greedy levels: consecutive operators with pairwise disjoint support (keeps the sequential semantics exactly)
-  std::vector<int> levels(int ndim) const {
+  // (a level is additionally cut after max_ops operators: the kernel's descriptor buffers hold one chunk)
+  std::vector<int> levels(int ndim, int max_ops) const {
     std::vector<int> ls; ls.push_back(0); std::vector<char> used(ndim, 0);
+    if (k.empty()) return ls;                       // no chunk at all
+    int in_level = 0;
     for (size_t o = 0; o < k.size(); ++o) {
-      bool clash = false;
+      bool clash = in_level >= max_ops;
       for (int a = 0; a < k[o]; ++a) if (used[P[o * ALF_KMAX + a]]) clash = true;
-      if (clash) { ls.push_back((int)o); std::fill(used.begin(), used.end(), 0); }
+      if (clash) { ls.push_back((int)o); std::fill(used.begin(), used.end(), 0); in_level = 0; }
       for (int a = 0; a < k[o]; ++a) used[P[o * ALF_KMAX + a]] = 1;
+      ++in_level;
     }
     ls.push_back((int)k.size());
     return ls;
@@ -220,7 +224,7 @@ struct Engine : EngineBase {
   VopDev<T>* d_vops = nullptr; ModelDev md; FieldTabDev ft;
   std::vector<void*> owned;     // device allocations of the op lists
   bool dense_t = false; T* d_dense[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // fwd, inv, c, half, halfinv (N*N*F each)
-  int KD = 16; size_t upd_smem = 0; int pw_l = 32, pw_r = 32;
+  int KD = 16; size_t upd_smem = 0; int ops_lk = 0; size_t ops_smem = 0;   // ops_lk = log2 of the largest small-operator dimension
   bool fast_upd = false; int KDf = 0, ldxf = 0, iptf = 1; size_t fast_smem = 0;   // k_wrapgr_fast (all vertices diagonal, k = 1)
   // tau_m work
   T *GT0 = nullptr, *G0T = nullptr, *G00 = nullptr, *GTT = nullptr, *TMPG = nullptr; UdvDev<T> udvr2;
@@ -231,7 +235,8 @@ struct Engine : EngineBase {
 
   OpListDev upload_list(const ListBuild& lb) {
     OpListDev d; d.n_ops = (int)lb.k.size(); d.nvar = lb.nvar;
-    std::vector<int> ls = lb.levels(N); d.n_levels = (int)ls.size() - 1;
+    std::vector<int> ls = lb.levels(N, OPS_CH); d.n_levels = (int)ls.size() - 1;
+    for (int kk : lb.k) { while ((1 << ops_lk) < kk) ++ops_lk; }
     d.level_start = dupload(ls); d.k = dupload(lb.k); d.P = dupload(lb.P); d.fidx = dupload(lb.fidx);
     std::vector<T> m(lb.mat.size()); for (size_t i = 0; i < m.size(); ++i) m[i] = to_T<T>(lb.mat[i]);
     d.mat = dupload(m);
@@ -280,10 +285,9 @@ struct Engine : EngineBase {
 #undef FAST_ATTR
       }
     }
-    // panel widths of the op-list kernel
-    pw_l = 32; while ((size_t)N * (pw_l + 1) * sizeof(T) > 200 * 1024 && pw_l > 4) pw_l /= 2;
-    pw_r = pw_l;
-    size_t ops_smem = (size_t)N * (pw_l + 1) * sizeof(T);
+    // op-list kernel: panel of 32 columns (rows) + double-buffered operator descriptors
+    ops_smem = (((size_t)N * (OPS_PW + 1) + 1) & ~(size_t)1) * sizeof(T) + 2 * OPS_CH * ((sizeof(T) << (2 * ops_lk)) + 5 * sizeof(int));
+    if (ops_smem > 227 * 1024) throw CudaError("Ndim too large for the op-list kernel's shared-memory panel");
     CK(cudaFuncSetAttribute(k_apply_ops<T, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ops_smem));
     CK(cudaFuncSetAttribute(k_apply_ops<T, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ops_smem));
   }
@@ -396,11 +400,9 @@ struct Engine : EngineBase {
 
   // ---------------------------------------------------------------- op-list launches
   void apply_ops(T* Mx, int side, int mode, int nt_a, int nt_b) {
-    const int pw = side == 0 ? pw_l : pw_r;
-    dim3 grid((N + pw - 1) / pw, NM);
-    size_t smem = (size_t)N * (pw + 1) * sizeof(T);
-    if (side == 0) KL(KC_OPS, st, k_apply_ops<T, 0><<<grid, 256, smem, st>>>(Mx, n2, N, N, pw, md, F, mode, nt_a, nt_b, h->d_fields, L, M));
-    else KL(KC_OPS, st, k_apply_ops<T, 1><<<grid, 256, smem, st>>>(Mx, n2, N, N, pw, md, F, mode, nt_a, nt_b, h->d_fields, L, M));
+    dim3 grid((N + OPS_PW - 1) / OPS_PW, NM);
+    if (side == 0) KL(KC_OPS, st, k_apply_ops<T, 0><<<grid, 256, ops_smem, st>>>(Mx, n2, N, N, md, F, mode, nt_a, nt_b, h->d_fields, L, M, ops_lk));
+    else KL(KC_OPS, st, k_apply_ops<T, 1><<<grid, 256, ops_smem, st>>>(Mx, n2, N, N, md, F, mode, nt_a, nt_b, h->d_fields, L, M, ops_lk));
     CKL();
   }
   // dense hopping: Mx <- E * Mx (left) or Mx * E (right), E per flavor (batch stride 0 inside a flavor is emulated per flavor)

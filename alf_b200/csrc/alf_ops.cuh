@@ -119,7 +119,7 @@ __global__ void __launch_bounds__(256) k_apply_ops(T* __restrict__ M, long sM, i
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int ldp = OPS_PW + 1, ms = 1 << (2 * lk), kk = 1 << lk;
   T* S = reinterpret_cast<T*>(smem_raw);
-  T* dMb = S + (long)N * ldp;
+  T* dMb = S + (((long)N * ldp + 1) & ~1L);           // keeps the int4 descriptor arrays 16-byte aligned
   int* dPb = reinterpret_cast<int*>(dMb + 2 * OPS_CH * ms);
   int* dKb = dPb + 2 * OPS_CH * 4;
   const int b = blockIdx.y, chain = b / F, f = b % F;
