@@ -286,10 +286,12 @@ struct Engine : EngineBase {
       }
     }
     // op-list kernel: panel of 32 columns (rows) + double-buffered operator descriptors
-    ops_smem = (((size_t)N * (OPS_PW + 1) + 1) & ~(size_t)1) * sizeof(T) + 2 * OPS_CH * ((sizeof(T) << (2 * ops_lk)) + 5 * sizeof(int));
+    ops_smem = (((size_t)N * (OPS_PW + 1) + 1) & ~(size_t)1) * sizeof(T) + 2 * OPS_CH * ((sizeof(T) << (2 * ops_lk)) + 4 * sizeof(int));
     if (ops_smem > 227 * 1024) throw CudaError("Ndim too large for the op-list kernel's shared-memory panel");
-    CK(cudaFuncSetAttribute(k_apply_ops<T, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ops_smem));
-    CK(cudaFuncSetAttribute(k_apply_ops<T, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ops_smem));
+#define OPS_ATTR(LKV) do { CK(cudaFuncSetAttribute(k_apply_ops<T, 0, LKV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ops_smem)); \
+                            CK(cudaFuncSetAttribute(k_apply_ops<T, 1, LKV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ops_smem)); } while (0)
+    if (ops_lk == 0) OPS_ATTR(0); else if (ops_lk == 1) OPS_ATTR(1); else OPS_ATTR(2);
+#undef OPS_ATTR
   }
   ~Engine() { for (void* p : owned) cudaFree(p); w.release(); }
   // Optional (ALF_B200_L2_PERSIST=1): persisting-L2 access window over the batch of Green functions.  Measured on B200 with
@@ -401,8 +403,10 @@ struct Engine : EngineBase {
   // ---------------------------------------------------------------- op-list launches
   void apply_ops(T* Mx, int side, int mode, int nt_a, int nt_b) {
     dim3 grid((N + OPS_PW - 1) / OPS_PW, NM);
-    if (side == 0) KL(KC_OPS, st, k_apply_ops<T, 0><<<grid, 256, ops_smem, st>>>(Mx, n2, N, N, md, F, mode, nt_a, nt_b, h->d_fields, L, M, ops_lk));
-    else KL(KC_OPS, st, k_apply_ops<T, 1><<<grid, 256, ops_smem, st>>>(Mx, n2, N, N, md, F, mode, nt_a, nt_b, h->d_fields, L, M, ops_lk));
+#define OPS_LAUNCH(SD, LKV) KL(KC_OPS, st, k_apply_ops<T, SD, LKV><<<grid, 256, ops_smem, st>>>(Mx, n2, N, N, md, F, mode, nt_a, nt_b, h->d_fields, L, M))
+    if (side == 0) { if (ops_lk == 0) OPS_LAUNCH(0, 0); else if (ops_lk == 1) OPS_LAUNCH(0, 1); else OPS_LAUNCH(0, 2); }
+    else { if (ops_lk == 0) OPS_LAUNCH(1, 0); else if (ops_lk == 1) OPS_LAUNCH(1, 1); else OPS_LAUNCH(1, 2); }
+#undef OPS_LAUNCH
     CKL();
   }
   // dense hopping: Mx <- E * Mx (left) or Mx * E (right), E per flavor (batch stride 0 inside a flavor is emulated per flavor)

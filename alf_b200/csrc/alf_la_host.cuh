@@ -8,6 +8,7 @@
 #include <vector>
 #include "alf_la.cuh"
 #include "alf_qrblk.cuh"
+#include "alf_qrblk2.cuh"
 
 struct CudaError : std::runtime_error { using std::runtime_error::runtime_error; };
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { \
@@ -167,9 +168,22 @@ static bool use_blocked_qr(int m, int n) {
   size_t extra = sizeof(T) * m + sizeof(double) * (n + (n > 32 ? n : 32)) + sizeof(int) * n + 64;
   return sizeof(T) * (size_t)m * n + extra > kSmemStageLimit && m <= 1024 && qrblk_cfg<T>(m, n).ok;
 }
+static inline bool la_force_qr1() { static int v = -1; if (v < 0) v = getenv("ALF_B200_QR1") ? 1 : 0; return v == 1; }
+// real matrices with m >= n, m <= 576: register-resident panels + strip updates (alf_qrblk2.cuh)
+template <typename T> static bool use_qr2(int m, int n) { return std::is_same<T, double>::value && m >= n && m <= 576 && !la_force_qr1() && qr2_smem(m, n) <= 226 * 1024; }
 template <typename T>
 static void launch_qrp_blk(cudaStream_t st, T* A, int m, int n, int ld, long sA, T* tau, long sTau, int* jpvt, long sP, double* D, long sD, QrOut* out,
                            T* Tbuf, int batch) {
+  if constexpr (std::is_same<T, double>::value) {
+    if (use_qr2<T>(m, n)) {
+      const size_t smem = qr2_smem(m, n); const long sT = (long)(n + 32) * 32;
+#define QR2_LAUNCH(MAXR) do { CK(cudaFuncSetAttribute(k_qrp_reg<MAXR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        KL(KC_QRP, st, k_qrp_reg<MAXR><<<batch, 512, smem, st>>>(A, m, n, ld, sA, tau, sTau, jpvt, sP, D, sD, out, Tbuf, sT)); } while (0)
+      if (m <= 128) QR2_LAUNCH(4); else if (m <= 288) QR2_LAUNCH(9); else QR2_LAUNCH(18);
+#undef QR2_LAUNCH
+      return;
+    }
+  }
   const QrBlkCfg c = qrblk_cfg<T>(m, n);
   CK(cudaFuncSetAttribute(k_qrp_blk<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem));
   KL(KC_QRP, st, k_qrp_blk<T><<<batch, 512, c.smem, st>>>(A, m, n, ld, sA, tau, sTau, jpvt, sP, D, sD, out, Tbuf, (long)(n + 32) * 32, c.NB, c.TC));
@@ -177,6 +191,18 @@ static void launch_qrp_blk(cudaStream_t st, T* A, int m, int n, int ld, long sA,
 // X <- Q^H X (mode 0) / Q X (mode 1); ident: X holds the identity on entry (mode 1 only: forms Q)
 template <typename T>
 static void launch_apply_q(cudaStream_t st, const T* QR, int m, int n, int ld, long sQ, const T* Tbuf, T* X, int ldx, long sX, int ncols, int mode, bool ident, int batch) {
+  if constexpr (std::is_same<T, double>::value) {
+    if (use_qr2<T>(m, n)) {
+      const size_t smem = applyq2_smem(m); const int cpc2 = 128; dim3 grid2((ncols + cpc2 - 1) / cpc2, batch); const long sT2 = (long)(n + 32) * 32;
+      KScope ks_(KC_FORMQ, st);
+#define AQ2_LAUNCH(MD, ID) do { CK(cudaFuncSetAttribute(k_apply_q2<MD, ID>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        k_apply_q2<MD, ID><<<grid2, 512, smem, st>>>(QR, m, n, ld, sQ, Tbuf, sT2, X, ldx, sX, ncols, cpc2); } while (0)
+      if (mode == 0) AQ2_LAUNCH(0, 0); else if (ident) AQ2_LAUNCH(1, 1); else AQ2_LAUNCH(1, 0);
+#undef AQ2_LAUNCH
+      CKL();
+      return;
+    }
+  }
   const QrBlkCfg c = qrblk_cfg<T>(m, n);
   const int cpc = 64; dim3 grid((ncols + cpc - 1) / cpc, batch);
   const long sT = (long)(n + 32) * 32;

@@ -55,80 +55,75 @@ struct ModelDev {
 //    one block-wide barrier per chunk.
 #define OPS_CH 64            // operators per chunk
 #define OPS_PW 32            // panel width = warp size
-#define OPS_MPT 4            // descriptor-matrix entries prefetched per thread: OPS_CH * KMAX^2 / 256
 
-template <typename T>
-struct OpsDesc { T* dM[2]; int* dP[2]; int* dK[2]; };
-
-template <typename T>
-__device__ __forceinline__ void ops_process_chunk(T* __restrict__ S, int ldp, bool lane_ok, int cnt, const int* __restrict__ dP, const int* __restrict__ dK,
-                                                  const T* __restrict__ dM, int lk) {
+// Shared-memory descriptor of one operator: x = (k << 28) | element offset of row P[0] in the panel, y, z, w = offsets of P[1..3];
+// its k x k matrix sits in dM[o << 2 LK] with leading dimension 1 << LK.
+template <typename T, int LK>
+__device__ __forceinline__ void ops_process_chunk(T* __restrict__ S, bool lane_ok, int cnt, const int4* __restrict__ dP, const T* __restrict__ dM) {
+  constexpr int kk = 1 << LK, ms = 1 << (2 * LK);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  const int kk = 1 << lk, ms = 1 << (2 * lk);
+  T* Sl = S + lane;
   for (int o = warp; o < cnt; o += 2 * nw) {
-    const int o2 = o + nw; const bool two = o2 < cnt;
-    const int k = dK[o], k2 = two ? dK[o2] : 0;
-    if (k == 2 && (k2 == 2 || !two)) {       // common case (bond operators): two independent operators in flight
-      const int4 P = reinterpret_cast<const int4*>(dP)[o]; const T* A = dM + o * ms;
-      const int4 Q = reinterpret_cast<const int4*>(dP)[two ? o2 : o]; const T* Bm = dM + (two ? o2 : o) * ms;
-      T* p0 = S + (long)P.x * ldp + lane; T* p1 = S + (long)P.y * ldp + lane;
-      T* q0 = S + (long)Q.x * ldp + lane; T* q1 = S + (long)Q.y * ldp + lane;
+    const int o2 = (o + nw < cnt) ? o + nw : o;          // second operator of this iteration (same as the first if there is none)
+    const bool two = o2 != o;
+    const int4 P = dP[o], Q = dP[o2];
+    const int k = ((unsigned)P.x) >> 28, k2 = ((unsigned)Q.x) >> 28;
+    const int px = P.x & 0x0fffffff, qx = Q.x & 0x0fffffff;
+    const T* A = dM + o * ms; const T* Bm = dM + o2 * ms;
+    if (LK >= 1 && k == 2 && k2 == 2) {       // common case (bond operators): two independent operators in flight
       const T a00 = A[0], a10 = A[1], a01 = A[kk], a11 = A[kk + 1];
       const T b00 = Bm[0], b10 = Bm[1], b01 = Bm[kk], b11 = Bm[kk + 1];
       if (lane_ok) {
-        const T v0 = *p0, v1 = *p1, w0 = *q0, w1 = *q1;
-        *p0 = a00 * v0 + a01 * v1; *p1 = a10 * v0 + a11 * v1;
-        if (two) { *q0 = b00 * w0 + b01 * w1; *q1 = b10 * w0 + b11 * w1; }
+        const T v0 = Sl[px], v1 = Sl[P.y], w0 = Sl[qx], w1 = Sl[Q.y];
+        Sl[px] = a00 * v0 + a01 * v1; Sl[P.y] = a10 * v0 + a11 * v1;
+        if (two) { Sl[qx] = b00 * w0 + b01 * w1; Sl[Q.y] = b10 * w0 + b11 * w1; }
       }
       continue;
     }
+    if (k == 1 && k2 == 1) {                  // diagonal single-site vertices
+      const T a = A[0], bq = Bm[0];
+      if (lane_ok) { const T v0 = Sl[px], w0 = Sl[qx]; Sl[px] = a * v0; if (two) Sl[qx] = bq * w0; }
+      continue;
+    }
     for (int h = 0; h < (two ? 2 : 1); ++h) {
-      const int oo = h ? o2 : o, kc = h ? k2 : k;
-      const int4 P = reinterpret_cast<const int4*>(dP)[oo]; const T* A = dM + oo * ms;
+      const int4 PP = h ? Q : P; const int kc = h ? k2 : k; const T* AA = h ? Bm : A;
       if (!lane_ok) continue;
-      if (kc == 1) { T* p = S + (long)P.x * ldp + lane; *p = A[0] * (*p); }
-      else if (kc == 2) {
-        T* p0 = S + (long)P.x * ldp + lane; T* p1 = S + (long)P.y * ldp + lane;
-        const T v0 = *p0, v1 = *p1;
-        *p0 = A[0] * v0 + A[kk] * v1; *p1 = A[1] * v0 + A[kk + 1] * v1;
-      } else {
-        const int Pa[ALF_KMAX] = {P.x, P.y, P.z, P.w};
-        T v[ALF_KMAX], r[ALF_KMAX];
+      const int Pa[ALF_KMAX] = {PP.x & 0x0fffffff, PP.y, PP.z, PP.w};
+      T v[kk], r[kk];
 #pragma unroll
-        for (int a = 0; a < ALF_KMAX; ++a) v[a] = (a < kc) ? S[(long)Pa[a] * ldp + lane] : zero_<T>();
+      for (int a = 0; a < kk; ++a) v[a] = (a < kc) ? Sl[Pa[a]] : zero_<T>();
 #pragma unroll
-        for (int a = 0; a < ALF_KMAX; ++a) {
-          T sacc = zero_<T>();
+      for (int a = 0; a < kk; ++a) {
+        T sacc = zero_<T>();
 #pragma unroll
-          for (int b = 0; b < ALF_KMAX; ++b) if (a < kc && b < kc) fma_(sacc, A[a + b * kk], v[b]);
-          r[a] = sacc;
-        }
-#pragma unroll
-        for (int a = 0; a < ALF_KMAX; ++a) if (a < kc) S[(long)Pa[a] * ldp + lane] = r[a];
+        for (int bq = 0; bq < kk; ++bq) if (a < kc && bq < kc) fma_(sacc, AA[a + bq * kk], v[bq]);
+        r[a] = sacc;
       }
+#pragma unroll
+      for (int a = 0; a < kk; ++a) if (a < kc) Sl[Pa[a]] = r[a];
     }
   }
 }
 
 // SIDE 0: panel of OPS_PW columns [v0, v0+pw) of M;  S[i][j] = M(i, v0+j)
 // SIDE 1: panel of OPS_PW rows    [v0, v0+pw) of M;  S[i][j] = M(v0+j, i)   (right multiplication = left on the transpose)
-// grid = (ceil(nvec/OPS_PW), n_matrices); matrix b belongs to chain b / F, flavor b % F.  lk = log2 of the largest operator size.
-template <typename T, int SIDE>
+// grid = (ceil(nvec/OPS_PW), n_matrices); matrix b belongs to chain b / F, flavor b % F.  LK = log2 of the largest operator size.
+template <typename T, int SIDE, int LK>
 __global__ void __launch_bounds__(256) k_apply_ops(T* __restrict__ M, long sM, int N, int nvec, ModelDev md, int F, int mode,
-                                                   int nt_a, int nt_b, const int8_t* __restrict__ fields, int Ltrot, int n_opv, int lk) {
+                                                   int nt_a, int nt_b, const int8_t* __restrict__ fields, int Ltrot, int n_opv) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int ldp = OPS_PW + 1, ms = 1 << (2 * lk), kk = 1 << lk;
+  constexpr int ldp = OPS_PW + 1, ms = 1 << (2 * LK), kk = 1 << LK;
+  constexpr int MPT = (OPS_CH * ms + 255) / 256;       // descriptor-matrix entries prefetched per thread
   T* S = reinterpret_cast<T*>(smem_raw);
-  T* dMb = S + (((long)N * ldp + 1) & ~1L);           // keeps the int4 descriptor arrays 16-byte aligned
-  int* dPb = reinterpret_cast<int*>(dMb + 2 * OPS_CH * ms);
-  int* dKb = dPb + 2 * OPS_CH * 4;
+  T* dMb = S + ((N * ldp + 1) & ~1);                  // keeps the int4 descriptor arrays 16-byte aligned
+  int4* dPb = reinterpret_cast<int4*>(dMb + 2 * OPS_CH * ms);
   const int b = blockIdx.y, chain = b / F, f = b % F;
   M += (long)b * sM;
   const int v0 = blockIdx.x * OPS_PW;
   const int pw = min(OPS_PW, nvec - v0);
-  const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = nthr >> 5;
-  // ---- the program of this launch
-  int li0 = -1, li1 = -1, uf0 = 0, uf1 = 0, dir = 1;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+  // ---- the program of this launch: per slice, list a then list b
+  int li0 = 0, li1 = -1, uf0 = 0, uf1 = 0, dir = 1;
   switch (mode) {
     case MODE_WRAPUR: li0 = L_TL_FWD; li1 = L_VL_N; uf1 = 1; break;
     case MODE_WRAPUL: li0 = L_VL_C; uf0 = 1; li1 = L_TL_C; dir = -1; break;
@@ -141,61 +136,65 @@ __global__ void __launch_bounds__(256) k_apply_ops(T* __restrict__ M, long sM, i
     case MODE_TR_HALFINV: li0 = L_TR_HALFINV; break;
     case MODE_PROPRM1: li0 = L_TR_INV; li1 = L_VR_INV; uf1 = 1; break;
   }
-  const OpListDev& La = md.lists[li0][f];
-  const OpListDev& Lb = md.lists[li1 >= 0 ? li1 : li0][f];
+  const OpListDev La = md.lists[li0][f];
+  const OpListDev Lb = md.lists[li1 >= 0 ? li1 : li0][f];
   const int nch0 = La.n_levels, nch1 = (li1 >= 0) ? Lb.n_levels : 0, per = nch0 + nch1;
   const int ns = (uf0 || uf1) ? (nt_b - nt_a + 1) : 1, total = ns * per;
   const int8_t* fbase = fields ? fields + (long)chain * Ltrot * n_opv : nullptr;
 
-  // descriptor prefetch registers
-  int rk = 0; int4 rP = make_int4(0, 0, 0, 0); T rM[OPS_MPT]; int rcnt = 0;
-  auto fetch = [&](int t) {
-    const int sl = t / per, r = t - sl * per;
-    const bool second = r >= nch0;
+  // descriptor prefetch registers and the cursor (slice, chunk within the slice) of the NEXT fetch
+  int4 rP = make_int4(0, 0, 0, 0); T rM[MPT]; int rcnt = 0;
+  int f_sl = 0, f_r = 0;
+  auto fetch = [&]() {
+    const bool second = f_r >= nch0;
     const OpListDev& L = second ? Lb : La;
-    const int c = second ? r - nch0 : r;
+    const int c = second ? f_r - nch0 : f_r;
     const int a0 = L.level_start[c]; rcnt = L.level_start[c + 1] - a0;
-    const int nt = (dir > 0) ? nt_a + sl : nt_b - sl;
-    const int8_t* fld = ((second ? uf1 : uf0) && fbase) ? fbase + (long)(nt - 1) * n_opv : nullptr;
-    if (tid < rcnt) { rk = L.k[a0 + tid]; rP = reinterpret_cast<const int4*>(L.P)[a0 + tid]; }
+    const int nt = (dir > 0) ? nt_a + f_sl : nt_b - f_sl;
+    const int8_t* fld = ((second ? uf1 : uf0) && fbase) ? fbase + (nt - 1) * n_opv : nullptr;
+    if (tid < rcnt) {
+      const int4 p = reinterpret_cast<const int4*>(L.P)[a0 + tid];
+      rP = make_int4((p.x * ldp) | (L.k[a0 + tid] << 28), p.y * ldp, p.z * ldp, p.w * ldp);
+    }
     const T* mats = reinterpret_cast<const T*>(L.mat);
 #pragma unroll
-    for (int u = 0; u < OPS_MPT; ++u) {
+    for (int u = 0; u < MPT; ++u) {
       const int e = tid + u * 256;
       if (e < rcnt * ms) {
-        const int o = e >> (2 * lk), rr = e & (ms - 1), a = rr & (kk - 1), bb = rr >> lk, og = a0 + o;
+        const int o = e >> (2 * LK), rr = e & (ms - 1), a = rr & (kk - 1), bb = rr >> LK, og = a0 + o;
         int var = 0;
         if (L.nvar > 1) var = (int)fld[L.fidx[og]] + 2;
-        rM[u] = mats[((long)og * L.nvar + var) * (ALF_KMAX * ALF_KMAX) + a + bb * ALF_KMAX];
+        rM[u] = mats[(og * L.nvar + var) * (ALF_KMAX * ALF_KMAX) + a + bb * ALF_KMAX];
       }
     }
+    if (++f_r == per) { f_r = 0; ++f_sl; }
   };
   auto commit = [&](int buf) {
-    if (tid < rcnt) { dKb[buf * OPS_CH + tid] = rk; reinterpret_cast<int4*>(dPb)[buf * OPS_CH + tid] = rP; }
+    if (tid < rcnt) dPb[buf * OPS_CH + tid] = rP;
 #pragma unroll
-    for (int u = 0; u < OPS_MPT; ++u) { const int e = tid + u * 256; if (e < rcnt * ms) dMb[buf * OPS_CH * ms + e] = rM[u]; }
+    for (int u = 0; u < MPT; ++u) { const int e = tid + u * 256; if (e < rcnt * ms) dMb[buf * OPS_CH * ms + e] = rM[u]; }
   };
-  if (total > 0) fetch(0);
+  if (total > 0) fetch();
   // ---- stage the panel
   if (SIDE == 0) {
-    for (int j = warp; j < pw; j += nw) { const T* col = M + (long)(v0 + j) * N; for (int i = lane; i < N; i += 32) S[(long)i * ldp + j] = col[i]; }
+    for (int j = warp; j < pw; j += nw) { const T* col = M + (long)(v0 + j) * N; for (int i = lane; i < N; i += 32) S[i * ldp + j] = col[i]; }
   } else {
-    if (lane < pw) for (int i = warp; i < N; i += nw) S[(long)i * ldp + lane] = M[(v0 + lane) + (long)i * N];
+    if (lane < pw) { const T* src = M + v0 + lane; for (int i = warp; i < N; i += nw) S[i * ldp + lane] = src[(long)i * N]; }
   }
   int cnt_cur = rcnt;
   if (total > 0) commit(0);
   __syncthreads();
   for (int t = 0; t < total; ++t) {
-    if (t + 1 < total) fetch(t + 1);
+    if (t + 1 < total) fetch();
     const int buf = t & 1;
-    ops_process_chunk<T>(S, ldp, lane < pw, cnt_cur, dPb + buf * OPS_CH * 4, dKb + buf * OPS_CH, dMb + buf * OPS_CH * ms, lk);
+    ops_process_chunk<T, LK>(S, lane < pw, cnt_cur, dPb + buf * OPS_CH, dMb + buf * OPS_CH * ms);
     if (t + 1 < total) { commit(buf ^ 1); cnt_cur = rcnt; }
     __syncthreads();
   }
   // ---- write back
   if (SIDE == 0) {
-    for (int j = warp; j < pw; j += nw) { T* col = M + (long)(v0 + j) * N; for (int i = lane; i < N; i += 32) col[i] = S[(long)i * ldp + j]; }
+    for (int j = warp; j < pw; j += nw) { T* col = M + (long)(v0 + j) * N; for (int i = lane; i < N; i += 32) col[i] = S[i * ldp + j]; }
   } else {
-    if (lane < pw) for (int i = warp; i < N; i += nw) M[(v0 + lane) + (long)i * N] = S[(long)i * ldp + lane];
+    if (lane < pw) { T* dst = M + v0 + lane; for (int i = warp; i < N; i += nw) dst[(long)i * N] = S[i * ldp + lane]; }
   }
 }

@@ -1,0 +1,371 @@
+// Second-generation blocked pivoted QR for REAL matrices that do not fit one SM's shared memory (N = 256: 512 KB), and the
+// matching block-reflector application.  Same mathematics and the same outputs as k_qrp_blk / k_apply_q (alf_qrblk.cuh:
+// windowed column pivoting, compact-WY trailing update; replaces ZGEQP3 / ZUNGQR / ZUNMQR of Prog/QDRP_decompose_mod.F90:78-100,
+// Prog/udv_state_mod.F90:569-578, Prog/cgr1_mod.F90:350-445, Prog/cgr2_2_mod.F90:155-191), restructured around the two things the
+// ncu source view showed the first version waiting on (profiles/r1_ncu_stab_blockedqr.md): block-wide barriers in the panel
+// factorisation and in the 8-column tiles of the trailing update.
+//  * Panel factorisation: the 32 panel columns live in REGISTERS, two columns per warp (16 warps), lane l holding rows
+//    l, l+32, ...  Dot products and norms are warp-shuffle reductions, in-panel pivoting is a logical permutation (no data
+//    movement), the reflector is broadcast through shared memory: two barriers per column instead of five.
+//  * Trailing update / Q application: every warp owns an 8-column strip of the target and runs the whole chain
+//    W = V^T C, W2 = op(T) W, C -= V W2 on the FP64 tensor cores (DMMA m8n8k4) with C read from and written to global memory
+//    (L2) in fragment layout: no barrier inside the update, and the exact column norms for the next pivot window fall out of
+//    the accumulator registers.
+#pragma once
+#include "alf_qrblk.cuh"
+
+#define QR2_NB 32
+#define QR2_LDW 36
+#define QR2_WSC (QR2_LDW * 8)      // per-warp scratch: 32 x 8 block, leading dimension 36
+
+static size_t qr2_smem(int m, int n) {
+  const int mp = (m + 7) & ~7, ldv = ld_pad(mp);
+  return sizeof(double) * ((size_t)ldv * QR2_NB + 2 * QR2_LDW * QR2_NB + 16 * QR2_WSC + mp + 2 * QR2_NB + n) + sizeof(int) * (4 * (size_t)n + 64) + 64;
+}
+static size_t applyq2_smem(int m) {
+  const int mp = (m + 7) & ~7, ldv = ld_pad(mp);
+  return sizeof(double) * ((size_t)ldv * QR2_NB + QR2_LDW * QR2_NB + 16 * QR2_WSC) + 64;
+}
+
+// X(r0:m, strip) <- (I - V op(T) V^T) X(r0:m, strip) for the 8-column strips c_begin + 8 (warp + k nw) < c_end of this CTA.
+// Vs: (m - r0) x 32 explicit unit-lower trapezoid, zero padded to mvp rows and 32 columns; Ts: 32 x 32 upper triangular (ld 36).
+// CONJT = 1: op(T) = T^T (Q^T from the left), 0: op(T) = T.  vn != nullptr: 2-norm of X(r0 + nbk : m, c) -> vn[c].
+template <int CONJT>
+__device__ __forceinline__ void apply_panel_strips(double* __restrict__ X, int ldx, int r0, int m, int c_begin, int c_end, const double* __restrict__ Vs,
+                                                   int ldv, const double* __restrict__ Ts, int nbk, double* __restrict__ Wsc, double* __restrict__ vn) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const int g = lane >> 2, q = lane & 3;
+  const int mv = m - r0, mvp = (mv + 7) & ~7;
+  double* Wm = Wsc + warp * QR2_WSC;
+  for (int c0 = c_begin + 8 * warp; c0 < c_end; c0 += 8 * nw) {
+    // ---- W = V^T C  (32 x 8)
+    double w[4][2];
+#pragma unroll
+    for (int ib = 0; ib < 4; ++ib) { w[ib][0] = 0.0; w[ib][1] = 0.0; }
+    const bool colb = (c0 + g) < c_end;
+    const double* xb = X + (long)(c0 + g) * ldx + r0 + q;
+#pragma unroll 4
+    for (int ks = 0; ks < mvp / 4; ++ks) {
+      const int r = 4 * ks + q;
+      const double bv = (colb && r < mv) ? xb[4 * ks] : 0.0;
+      const double* vp = Vs + r + (long)g * ldv;
+#pragma unroll
+      for (int ib = 0; ib < 4; ++ib) dmma884(w[ib][0], w[ib][1], vp[(long)(8 * ib) * ldv], bv);
+    }
+#pragma unroll
+    for (int ib = 0; ib < 4; ++ib) { Wm[(8 * ib + g) + (2 * q) * QR2_LDW] = w[ib][0]; Wm[(8 * ib + g) + (2 * q + 1) * QR2_LDW] = w[ib][1]; }
+    __syncwarp();
+    // ---- W2 = op(T) W  (32 x 8)
+    double bw[8];
+#pragma unroll
+    for (int ks = 0; ks < 8; ++ks) bw[ks] = Wm[(4 * ks + q) + g * QR2_LDW];
+#pragma unroll
+    for (int ib = 0; ib < 4; ++ib) { w[ib][0] = 0.0; w[ib][1] = 0.0; }
+#pragma unroll
+    for (int ks = 0; ks < 8; ++ks)
+#pragma unroll
+      for (int ib = 0; ib < 4; ++ib) {
+        const double a = CONJT ? Ts[(4 * ks + q) + (8 * ib + g) * QR2_LDW] : Ts[(8 * ib + g) + (4 * ks + q) * QR2_LDW];
+        dmma884(w[ib][0], w[ib][1], a, bw[ks]);
+      }
+    __syncwarp();
+#pragma unroll
+    for (int ib = 0; ib < 4; ++ib) { Wm[(8 * ib + g) + (2 * q) * QR2_LDW] = -w[ib][0]; Wm[(8 * ib + g) + (2 * q + 1) * QR2_LDW] = -w[ib][1]; }
+    __syncwarp();
+#pragma unroll
+    for (int ks = 0; ks < 8; ++ks) bw[ks] = Wm[(4 * ks + q) + g * QR2_LDW];       // -W2 as B fragments
+    __syncwarp();
+    // ---- C -= V W2, 8 rows at a time; exact norms of the rows below the panel
+    const bool ca = (c0 + 2 * q) < c_end, cb2 = (c0 + 2 * q + 1) < c_end;
+    double* xc = X + (long)(c0 + 2 * q) * ldx + r0 + g;
+    double n0 = 0.0, n1 = 0.0;
+#pragma unroll 2
+    for (int rb = 0; rb < mvp / 8; ++rb) {
+      const int r = 8 * rb + g; const bool rok = r < mv;
+      double a0 = (rok && ca) ? xc[8 * rb] : 0.0, a1 = (rok && cb2) ? xc[8 * rb + ldx] : 0.0;
+      const double* vp = Vs + r + (long)q * ldv;
+#pragma unroll
+      for (int ks = 0; ks < 8; ++ks) dmma884(a0, a1, vp[(long)(4 * ks) * ldv], bw[ks]);
+      if (rok && ca) xc[8 * rb] = a0;
+      if (rok && cb2) xc[8 * rb + ldx] = a1;
+      if (r >= nbk) { n0 = fma(a0, a0, n0); n1 = fma(a1, a1, n1); }
+    }
+    if (vn) {
+      n0 += __shfl_xor_sync(0xffffffffu, n0, 4); n1 += __shfl_xor_sync(0xffffffffu, n1, 4);
+      n0 += __shfl_xor_sync(0xffffffffu, n0, 8); n1 += __shfl_xor_sync(0xffffffffu, n1, 8);
+      n0 += __shfl_xor_sync(0xffffffffu, n0, 16); n1 += __shfl_xor_sync(0xffffffffu, n1, 16);
+      if (g == 0) { if (ca) vn[c0 + 2 * q] = sqrt(n0); if (cb2) vn[c0 + 2 * q + 1] = sqrt(n1); }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------------
+// k_qrp_reg: windowed column-pivoted blocked Householder QR of an m x n real matrix (m >= n, m <= 32 MAXR), in place, then
+// D(i) = |R(i,i)|, R(i, i:) /= D(i).  One CTA of 512 threads per matrix.  Outputs as k_qrp_blk (Tbuf: 32 x 32 factor per panel).
+// ------------------------------------------------------------------------------------------------------------------------
+template <int MAXR>
+__global__ void __launch_bounds__(512, 1) k_qrp_reg(double* __restrict__ A, int m, int n, int ld, long sA, double* __restrict__ tau, long sTau,
+                                                    int* __restrict__ jpvt, long sP, double* __restrict__ D, long sD, QrOut* __restrict__ out,
+                                                    double* __restrict__ Tbuf, long sT) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr int NB = QR2_NB, LDW = QR2_LDW;
+  const int b = blockIdx.x, tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = nthr >> 5;
+  A += (long)b * sA; tau += (long)b * sTau; jpvt += (long)b * sP; D += (long)b * sD; Tbuf += (long)b * sT;
+  const int mp = (m + 7) & ~7, ldv = ld_pad(mp);
+  double* Vs = reinterpret_cast<double*>(smem_raw);
+  double* Ts = Vs + (long)ldv * NB;
+  double* Gs = Ts + LDW * NB;
+  double* Wsc = Gs + LDW * NB;
+  double* v_s = Wsc + 16 * QR2_WSC;
+  double* tau_s = v_s + mp;
+  double* pn = tau_s + NB;
+  double* vn = pn + NB;
+  int* ipv = reinterpret_cast<int*>(vn + n);
+  int* rank_s = ipv + n;
+  int* lista = rank_s + n;
+  int* listb = lista + n;
+  int* pos_slot = listb + n;          // [32] slot at logical panel position j; [32..63] scratch
+  __shared__ int s_na;
+  __shared__ double s_detq[2];
+
+  for (int c = warp; c < n; c += nw) {
+    double s = 0.0;
+    for (int i = lane; i < m; i += 32) { const double x = A[i + (long)c * ld]; s = fma(x, x, s); }
+    s = warp_sum(s);
+    if (lane == 0) { vn[c] = sqrt(s); ipv[c] = c; }
+  }
+  if (tid == 0) { s_detq[0] = 1.0; s_detq[1] = 0.0; }
+  __syncthreads();
+  const int kmax = n;                 // m >= n
+  for (int k0 = 0; k0 < kmax; k0 += NB) {
+    const int nbk = min(NB, kmax - k0), mv = m - k0, mvp = (mv + 7) & ~7;
+    // ---- (1) the nbk remaining columns of largest norm form the panel (rank by counting; ties -> lower index first)
+    for (int c = k0 + tid; c < n; c += nthr) {
+      const double x = vn[c]; int r = 0;
+      for (int c2 = k0; c2 < n; ++c2) { const double y = vn[c2]; r += (y > x || (y == x && c2 < c)) ? 1 : 0; }
+      rank_s[c] = r;
+    }
+    __syncthreads();
+    if (warp == 0) {      // lista: selected columns outside the panel range; listb: unselected columns inside it (same count)
+      int na = 0, nb2 = 0;
+      for (int c0 = k0; c0 < n; c0 += 32) {
+        const int c = c0 + lane; const bool in = c < n;
+        const bool sel = in && rank_s[c] < nbk, front = in && c < k0 + nbk;
+        const unsigned ma = __ballot_sync(0xffffffffu, sel && !front), mb = __ballot_sync(0xffffffffu, !sel && front);
+        if (sel && !front) lista[na + __popc(ma & ((1u << lane) - 1))] = c;
+        if (!sel && front) listb[nb2 + __popc(mb & ((1u << lane) - 1))] = c;
+        na += __popc(ma); nb2 += __popc(mb);
+      }
+      if (lane == 0) s_na = na;
+    }
+    __syncthreads();
+    // ---- (2) bring the selected columns into the panel range (column swaps in global memory)
+    const int na = s_na;
+    for (int pi = warp; pi < na; pi += nw) {
+      const int ca = lista[pi], cb = listb[pi];
+      for (int r = lane; r < m; r += 32) { const double x = A[r + (long)ca * ld], y = A[r + (long)cb * ld]; A[r + (long)ca * ld] = y; A[r + (long)cb * ld] = x; }
+      if (lane == 0) { const int t = ipv[ca]; ipv[ca] = ipv[cb]; ipv[cb] = t; vn[ca] = vn[cb]; }
+    }
+    __syncthreads();
+    // ---- (3) panel columns -> registers: warp w owns slots 2w, 2w+1; exact norms below row k0
+    double c0r[MAXR], c1r[MAXR];
+    const int s0 = 2 * warp, s1 = 2 * warp + 1;
+    {
+      double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+      for (int r = 0; r < MAXR; ++r) {
+        const int i = lane + 32 * r;
+        c0r[r] = (i < m && s0 < nbk) ? A[i + (long)(k0 + s0) * ld] : 0.0;
+        c1r[r] = (i < m && s1 < nbk) ? A[i + (long)(k0 + s1) * ld] : 0.0;
+        if (i >= k0) { a0 = fma(c0r[r], c0r[r], a0); a1 = fma(c1r[r], c1r[r], a1); }
+      }
+      a0 = warp_sum(a0); a1 = warp_sum(a1);
+      if (lane == 0) { pn[s0] = sqrt(a0); pn[s1] = sqrt(a1); }
+    }
+    __syncthreads();
+    // ---- (4) exact column-pivoted Householder QR of the panel, columns in registers
+    unsigned used = 0u;
+    for (int j = 0; j < nbk; ++j) {
+      const int prow = k0 + j;
+      int p;
+      {
+        double best = (lane < nbk && !((used >> lane) & 1u)) ? pn[lane] : -1.0; int bi = lane;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          const double ob = __shfl_xor_sync(0xffffffffu, best, o); const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+          if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+        }
+        p = bi;
+      }
+      used |= 1u << p;
+      if (tid == 0) pos_slot[j] = p;
+      if (warp == (p >> 1)) {
+        const int h = p & 1;
+        double xn2 = 0.0, al = 0.0;
+#pragma unroll
+        for (int r = 0; r < MAXR; ++r) {
+          const int i = lane + 32 * r; const double x = h ? c1r[r] : c0r[r];
+          if (i > prow) xn2 = fma(x, x, xn2);
+          if (i == prow) al = x;
+        }
+        xn2 = warp_sum(xn2);
+        const double alpha = __shfl_sync(0xffffffffu, al, prow & 31);
+        double tj, scal, beta;
+        if (xn2 == 0.0) { tj = 0.0; scal = 0.0; beta = alpha; }
+        else { beta = -copysign(sqrt(alpha * alpha + xn2), alpha); tj = (beta - alpha) / beta; scal = 1.0 / (alpha - beta); }
+#pragma unroll
+        for (int r = 0; r < MAXR; ++r) {
+          const int i = lane + 32 * r;
+          if (i < m) {
+            double x = h ? c1r[r] : c0r[r];
+            if (i > prow) { x *= scal; v_s[i] = x; }
+            else if (i == prow) { x = beta; v_s[i] = 1.0; }
+            if (h) c1r[r] = x; else c0r[r] = x;
+          }
+        }
+        if (lane == 0) {
+          tau_s[j] = tj;
+          if (tj != 0.0) { s_detq[0] = -s_detq[0]; s_detq[1] = -s_detq[1]; }      // det of a real reflector = -1 (Prog/cgr1_mod.F90:338-347)
+        }
+      }
+      __syncthreads();
+      {
+        const double tj = tau_s[j];
+        const bool do0 = (s0 < nbk) && !((used >> s0) & 1u), do1 = (s1 < nbk) && !((used >> s1) & 1u);
+        if (do0 || do1) {
+          double w0 = 0.0, w1 = 0.0;
+          if (tj != 0.0) {
+#pragma unroll
+            for (int r = 0; r < MAXR; ++r) {
+              const int i = lane + 32 * r;
+              if (i >= prow && i < m) { const double v = v_s[i]; w0 = fma(v, c0r[r], w0); w1 = fma(v, c1r[r], w1); }
+            }
+            w0 = warp_sum(w0) * tj; w1 = warp_sum(w1) * tj;
+          }
+          double q0 = 0.0, q1 = 0.0;
+#pragma unroll
+          for (int r = 0; r < MAXR; ++r) {
+            const int i = lane + 32 * r;
+            if (i >= prow && i < m) {
+              const double v = (tj != 0.0) ? v_s[i] : 0.0;
+              if (do0) c0r[r] = fma(-v, w0, c0r[r]);
+              if (do1) c1r[r] = fma(-v, w1, c1r[r]);
+              if (i > prow) { q0 = fma(c0r[r], c0r[r], q0); q1 = fma(c1r[r], c1r[r], q1); }
+            }
+          }
+          q0 = warp_sum(q0); q1 = warp_sum(q1);
+          if (lane == 0) { if (do0) pn[s0] = sqrt(q0); if (do1) pn[s1] = sqrt(q1); }
+        }
+      }
+      __syncthreads();
+    }
+    // ---- (5) write the factored panel back at the logical positions; V panel (explicit unit lower trapezoid) -> shared memory
+    int pos0 = -1, pos1 = -1;
+    {
+      const int ps = (lane < nbk) ? pos_slot[lane] : -1;
+      const unsigned m0 = __ballot_sync(0xffffffffu, ps == s0), m1 = __ballot_sync(0xffffffffu, ps == s1);
+      if (m0) pos0 = __ffs(m0) - 1;
+      if (m1) pos1 = __ffs(m1) - 1;
+    }
+    for (int e = tid; e < (mvp - mv) * NB; e += nthr) { const int r = mv + e % (mvp - mv), c = e / (mvp - mv); Vs[r + (long)c * ldv] = 0.0; }
+    for (int e = tid; e < mvp * (NB - nbk); e += nthr) { const int r = e % mvp, c = nbk + e / mvp; Vs[r + (long)c * ldv] = 0.0; }
+#pragma unroll
+    for (int r = 0; r < MAXR; ++r) {
+      const int i = lane + 32 * r;
+      if (i < m) {
+        if (pos0 >= 0) {
+          A[i + (long)(k0 + pos0) * ld] = c0r[r];
+          if (i >= k0) { const int rr = i - k0; Vs[rr + (long)pos0 * ldv] = (rr > pos0) ? c0r[r] : ((rr == pos0) ? 1.0 : 0.0); }
+        }
+        if (pos1 >= 0) {
+          A[i + (long)(k0 + pos1) * ld] = c1r[r];
+          if (i >= k0) { const int rr = i - k0; Vs[rr + (long)pos1 * ldv] = (rr > pos1) ? c1r[r] : ((rr == pos1) ? 1.0 : 0.0); }
+        }
+      }
+    }
+    if (lane == 0) { if (pos0 >= 0) lista[pos0] = ipv[k0 + s0]; if (pos1 >= 0) lista[pos1] = ipv[k0 + s1]; }
+    if (tid < nbk) tau[k0 + tid] = tau_s[tid];
+    if (tid >= nbk && tid < NB) tau_s[tid] = 0.0;
+    __syncthreads();
+    if (tid < nbk) ipv[k0 + tid] = lista[tid];
+    // ---- (6) Gram matrix of the reflectors, then the triangular factor T (ZLARFT forward / columnwise) by one warp
+    blk_gemm<1, 0>(NB, NB, mvp, Vs, ldv, Vs, ldv, Gs, LDW, 1.0);
+    __syncthreads();
+    if (warp == 0) {
+      double trow[NB];
+#pragma unroll
+      for (int l = 0; l < NB; ++l) trow[l] = 0.0;
+#pragma unroll
+      for (int j = 0; j < NB; ++j) {
+        const double tj = tau_s[j];
+        double x0 = 0.0, x1 = 0.0;
+#pragma unroll
+        for (int l = 0; l < j; ++l) { if (l & 1) x1 = fma(trow[l], Gs[l + j * LDW], x1); else x0 = fma(trow[l], Gs[l + j * LDW], x0); }
+        const double t = (lane < j) ? -tj * (x0 + x1) : ((lane == j) ? tj : 0.0);
+        trow[j] = t;
+        Ts[lane + j * LDW] = t;
+        Tbuf[(long)(k0 / NB) * NB * NB + lane + j * NB] = t;
+      }
+    }
+    __syncthreads();
+    // ---- (7) trailing update with exact recomputation of the remaining column norms
+    apply_panel_strips<1>(A, ld, k0, m, k0 + nbk, n, Vs, ldv, Ts, nbk, Wsc, vn);
+    __syncthreads();
+  }
+  // ---- D(i) = |R(i,i)|, R(i, i:) /= D(i); phases (QDRP_decompose_mod.F90:86-100, Pivot_phase :103-126)
+  for (int i = tid; i < kmax; i += nthr) { const double x = fabs(A[i + (long)i * ld]); D[i] = x; v_s[i] = x; }
+  __syncthreads();
+  for (int c = warp; c < n; c += nw) {
+    const int top = min(c, kmax - 1);
+    for (int i = lane; i <= top; i += 32) A[i + (long)c * ld] = A[i + (long)c * ld] * (1.0 / v_s[i]);
+  }
+  for (int c = tid; c < n; c += nthr) jpvt[c] = ipv[c];
+  __syncthreads();
+  if (warp == 0) {
+    // sign of prod R_ii (after the scaling R_ii = +-1)
+    int neg = 0;
+    for (int i = lane; i < kmax; i += 32) neg ^= (A[i + (long)i * ld] < 0.0) ? 1 : 0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) neg ^= __shfl_xor_sync(0xffffffffu, neg, o);
+    if (lane == 0) {
+      double sg = 1.0;      // permutation parity: cycles of even length flip the sign
+      for (int i = 0; i < n; ++i) rank_s[i] = 0;
+      for (int i = 0; i < n; ++i) if (rank_s[i] == 0) {
+        int next = i, L = 0;
+        while (rank_s[next] == 0) { ++L; rank_s[next] = 1; next = ipv[next]; }
+        if ((L & 1) == 0) sg = -sg;
+      }
+      out[b].perm_sign = sg; out[b].diag_phase = cplx(neg ? -1.0 : 1.0, 0.0); out[b].detq = cplx(s_detq[0], s_detq[1]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------------
+// k_apply_q2: X <- Q^T X (MODE 0: panels forward with T^T; ZUNMQR 'L','C') or X <- Q X (MODE 1: panels backward with T;
+// ZUNMQR 'L','N'; with X = 1 this is ZUNGQR).  grid = (column groups of cols_per_cta, batch), 512 threads.
+// ------------------------------------------------------------------------------------------------------------------------
+template <int MODE, int IDENT>
+__global__ void __launch_bounds__(512) k_apply_q2(const double* __restrict__ QR, int m, int n, int ld, long sQ, const double* __restrict__ Tbuf, long sT,
+                                                  double* __restrict__ X, int ldx, long sX, int ncols, int cols_per_cta) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr int NB = QR2_NB, LDW = QR2_LDW;
+  const int b = blockIdx.y, tid = threadIdx.x, nthr = blockDim.x;
+  QR += (long)b * sQ; Tbuf += (long)b * sT; X += (long)b * sX;
+  const int mp = (m + 7) & ~7, ldv = ld_pad(mp);
+  double* Vs = reinterpret_cast<double*>(smem_raw);
+  double* Ts = Vs + (long)ldv * NB;
+  double* Wsc = Ts + LDW * NB;
+  const int cb = blockIdx.x * cols_per_cta, ce = min(ncols, cb + cols_per_cta);
+  const int kmax = (m < n) ? m : n, npan = (kmax + NB - 1) / NB;
+  for (int pp = 0; pp < npan; ++pp) {
+    const int pi = MODE ? (npan - 1 - pp) : pp, k0 = pi * NB, nbk = min(NB, kmax - k0);
+    int c_lo = cb;
+    if (IDENT) c_lo = max(cb, k0 & ~7);
+    if (c_lo >= ce) continue;
+    load_vpanel<double>(QR, ld, m, k0, nbk, NB, Vs, ldv);
+    for (int e = tid; e < LDW * NB; e += nthr) { const int r = e % LDW, c = e / LDW; Ts[e] = (r < NB) ? Tbuf[(long)pi * NB * NB + r + (long)c * NB] : 0.0; }
+    __syncthreads();
+    apply_panel_strips<MODE ? 0 : 1>(X, ldx, k0, m, c_lo, ce, Vs, ldv, Ts, nbk, Wsc, nullptr);
+    __syncthreads();
+  }
+}
