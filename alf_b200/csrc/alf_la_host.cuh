@@ -170,16 +170,21 @@ static bool use_blocked_qr(int m, int n) {
 }
 static inline bool la_force_qr1() { static int v = -1; if (v < 0) v = getenv("ALF_B200_QR1") ? 1 : 0; return v == 1; }
 // real matrices with m >= n, m <= 576: register-resident panels + strip updates (alf_qrblk2.cuh)
-template <typename T> static bool use_qr2(int m, int n) { return std::is_same<T, double>::value && m >= n && m <= 576 && !la_force_qr1() && qr2_smem(m, n) <= 226 * 1024; }
+template <typename T> static bool use_qr2(int m, int n) { return std::is_same<T, double>::value && m >= n && m <= 576 && !la_force_qr1() && qr2_smem(m, n, 16) <= 226 * 1024; }
 template <typename T>
 static void launch_qrp_blk(cudaStream_t st, T* A, int m, int n, int ld, long sA, T* tau, long sTau, int* jpvt, long sP, double* D, long sD, QrOut* out,
                            T* Tbuf, int batch) {
   if constexpr (std::is_same<T, double>::value) {
     if (use_qr2<T>(m, n)) {
-      const size_t smem = qr2_smem(m, n); const long sT = (long)(n + 32) * 32;
-#define QR2_LAUNCH(MAXR) do { CK(cudaFuncSetAttribute(k_qrp_reg<MAXR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        KL(KC_QRP, st, k_qrp_reg<MAXR><<<batch, 512, smem, st>>>(A, m, n, ld, sA, tau, sTau, jpvt, sP, D, sD, out, Tbuf, sT)); } while (0)
-      if (m <= 128) QR2_LAUNCH(4); else if (m <= 288) QR2_LAUNCH(9); else QR2_LAUNCH(18);
+      const long sT = (long)(n + 32) * 32;
+      // one CTA of 16 warps per matrix.  Two CTAs of 8 warps per SM (ALF_B200_QR_TWO_CTA=1) measured slower on B200:
+      // 1.94 ms vs 1.72 ms per batch of 296 256x256 matrices.
+      const bool two = m <= 288 && qr2_smem(m, n, 8) + 1024 <= 113 * 1024 && getenv("ALF_B200_QR_TWO_CTA");
+      const size_t smem = qr2_smem(m, n, two ? 8 : 16);
+#define QR2_LAUNCH(MAXR, CPW) do { CK(cudaFuncSetAttribute(k_qrp_reg<MAXR, CPW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        KL(KC_QRP, st, k_qrp_reg<MAXR, CPW><<<batch, 32 * (QR2_NB / CPW), smem, st>>>(A, m, n, ld, sA, tau, sTau, jpvt, sP, D, sD, out, Tbuf, sT)); } while (0)
+      if (two) { if (m <= 128) QR2_LAUNCH(4, 4); else QR2_LAUNCH(9, 4); }
+      else { if (m <= 128) QR2_LAUNCH(4, 2); else if (m <= 288) QR2_LAUNCH(9, 2); else QR2_LAUNCH(18, 2); }
 #undef QR2_LAUNCH
       return;
     }
@@ -193,10 +198,10 @@ template <typename T>
 static void launch_apply_q(cudaStream_t st, const T* QR, int m, int n, int ld, long sQ, const T* Tbuf, T* X, int ldx, long sX, int ncols, int mode, bool ident, int batch) {
   if constexpr (std::is_same<T, double>::value) {
     if (use_qr2<T>(m, n)) {
-      const size_t smem = applyq2_smem(m); const int cpc2 = 128; dim3 grid2((ncols + cpc2 - 1) / cpc2, batch); const long sT2 = (long)(n + 32) * 32;
+      const size_t smem = applyq2_smem(m, 8); const int cpc2 = 64; dim3 grid2((ncols + cpc2 - 1) / cpc2, batch); const long sT2 = (long)(n + 32) * 32;
       KScope ks_(KC_FORMQ, st);
 #define AQ2_LAUNCH(MD, ID) do { CK(cudaFuncSetAttribute(k_apply_q2<MD, ID>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        k_apply_q2<MD, ID><<<grid2, 512, smem, st>>>(QR, m, n, ld, sQ, Tbuf, sT2, X, ldx, sX, ncols, cpc2); } while (0)
+        k_apply_q2<MD, ID><<<grid2, 256, smem, st>>>(QR, m, n, ld, sQ, Tbuf, sT2, X, ldx, sX, ncols, cpc2); } while (0)
       if (mode == 0) AQ2_LAUNCH(0, 0); else if (ident) AQ2_LAUNCH(1, 1); else AQ2_LAUNCH(1, 0);
 #undef AQ2_LAUNCH
       CKL();

@@ -18,13 +18,15 @@
 #define QR2_LDW 36
 #define QR2_WSC (QR2_LDW * 8)      // per-warp scratch: 32 x 8 block, leading dimension 36
 
-static size_t qr2_smem(int m, int n) {
+// nw = warps per CTA.  The Gram matrix of the panel aliases the per-warp scratch (used in disjoint phases).
+static size_t qr2_smem(int m, int n, int nw) {
   const int mp = (m + 7) & ~7, ldv = ld_pad(mp);
-  return sizeof(double) * ((size_t)ldv * QR2_NB + 2 * QR2_LDW * QR2_NB + 16 * QR2_WSC + mp + 2 * QR2_NB + n) + sizeof(int) * (4 * (size_t)n + 64) + 64;
+  const size_t wsc = (size_t)nw * QR2_WSC > (size_t)QR2_LDW * QR2_NB ? (size_t)nw * QR2_WSC : (size_t)QR2_LDW * QR2_NB;
+  return sizeof(double) * ((size_t)ldv * QR2_NB + QR2_LDW * QR2_NB + wsc + mp + 2 * QR2_NB + n) + sizeof(int) * (4 * (size_t)n + 64) + 64;
 }
-static size_t applyq2_smem(int m) {
+static size_t applyq2_smem(int m, int nw) {
   const int mp = (m + 7) & ~7, ldv = ld_pad(mp);
-  return sizeof(double) * ((size_t)ldv * QR2_NB + QR2_LDW * QR2_NB + 16 * QR2_WSC) + 64;
+  return sizeof(double) * ((size_t)ldv * QR2_NB + QR2_LDW * QR2_NB + (size_t)nw * QR2_WSC) + 64;
 }
 
 // X(r0:m, strip) <- (I - V op(T) V^T) X(r0:m, strip) for the 8-column strips c_begin + 8 (warp + k nw) < c_end of this CTA.
@@ -101,10 +103,10 @@ __device__ __forceinline__ void apply_panel_strips(double* __restrict__ X, int l
 
 // ------------------------------------------------------------------------------------------------------------------------
 // k_qrp_reg: windowed column-pivoted blocked Householder QR of an m x n real matrix (m >= n, m <= 32 MAXR), in place, then
-// D(i) = |R(i,i)|, R(i, i:) /= D(i).  One CTA of 512 threads per matrix.  Outputs as k_qrp_blk (Tbuf: 32 x 32 factor per panel).
+// D(i) = |R(i,i)|, R(i, i:) /= D(i).  One CTA per matrix.  Outputs as k_qrp_blk (Tbuf: 32 x 32 factor per panel).
 // ------------------------------------------------------------------------------------------------------------------------
-template <int MAXR>
-__global__ void __launch_bounds__(512, 1) k_qrp_reg(double* __restrict__ A, int m, int n, int ld, long sA, double* __restrict__ tau, long sTau,
+template <int MAXR, int CPW>      // CPW = panel columns per warp: 2 -> 16 warps (one CTA per SM), 4 -> 8 warps (two CTAs per SM)
+__global__ void __launch_bounds__(32 * (QR2_NB / CPW), CPW == 4 ? 2 : 1) k_qrp_reg(double* __restrict__ A, int m, int n, int ld, long sA, double* __restrict__ tau, long sTau,
                                                     int* __restrict__ jpvt, long sP, double* __restrict__ D, long sD, QrOut* __restrict__ out,
                                                     double* __restrict__ Tbuf, long sT) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -114,9 +116,9 @@ __global__ void __launch_bounds__(512, 1) k_qrp_reg(double* __restrict__ A, int 
   const int mp = (m + 7) & ~7, ldv = ld_pad(mp);
   double* Vs = reinterpret_cast<double*>(smem_raw);
   double* Ts = Vs + (long)ldv * NB;
-  double* Gs = Ts + LDW * NB;
-  double* Wsc = Gs + LDW * NB;
-  double* v_s = Wsc + 16 * QR2_WSC;
+  double* Wsc = Ts + LDW * NB;
+  double* Gs = Wsc;                   // Gram matrix: dead before the first strip update of the panel
+  double* v_s = Wsc + ((nw * QR2_WSC > LDW * NB) ? nw * QR2_WSC : LDW * NB);
   double* tau_s = v_s + mp;
   double* pn = tau_s + NB;
   double* vn = pn + NB;
@@ -167,20 +169,24 @@ __global__ void __launch_bounds__(512, 1) k_qrp_reg(double* __restrict__ A, int 
       if (lane == 0) { const int t = ipv[ca]; ipv[ca] = ipv[cb]; ipv[cb] = t; vn[ca] = vn[cb]; }
     }
     __syncthreads();
-    // ---- (3) panel columns -> registers: warp w owns slots 2w, 2w+1; exact norms below row k0
-    double c0r[MAXR], c1r[MAXR];
-    const int s0 = 2 * warp, s1 = 2 * warp + 1;
+    // ---- (3) panel columns -> registers: warp w owns slots CPW w .. CPW w + CPW - 1; exact norms below row k0
+    double cr[CPW][MAXR];
+    const int sb = CPW * warp;
     {
-      double a0 = 0.0, a1 = 0.0;
+      double a[CPW];
+#pragma unroll
+      for (int h = 0; h < CPW; ++h) a[h] = 0.0;
 #pragma unroll
       for (int r = 0; r < MAXR; ++r) {
         const int i = lane + 32 * r;
-        c0r[r] = (i < m && s0 < nbk) ? A[i + (long)(k0 + s0) * ld] : 0.0;
-        c1r[r] = (i < m && s1 < nbk) ? A[i + (long)(k0 + s1) * ld] : 0.0;
-        if (i >= k0) { a0 = fma(c0r[r], c0r[r], a0); a1 = fma(c1r[r], c1r[r], a1); }
+#pragma unroll
+        for (int h = 0; h < CPW; ++h) {
+          cr[h][r] = (i < m && sb + h < nbk) ? A[i + (long)(k0 + sb + h) * ld] : 0.0;
+          if (i >= k0) a[h] = fma(cr[h][r], cr[h][r], a[h]);
+        }
       }
-      a0 = warp_sum(a0); a1 = warp_sum(a1);
-      if (lane == 0) { pn[s0] = sqrt(a0); pn[s1] = sqrt(a1); }
+#pragma unroll
+      for (int h = 0; h < CPW; ++h) { a[h] = warp_sum(a[h]); if (lane == 0) pn[sb + h] = sqrt(a[h]); }
     }
     __syncthreads();
     // ---- (4) exact column-pivoted Householder QR of the panel, columns in registers
@@ -199,12 +205,15 @@ __global__ void __launch_bounds__(512, 1) k_qrp_reg(double* __restrict__ A, int 
       }
       used |= 1u << p;
       if (tid == 0) pos_slot[j] = p;
-      if (warp == (p >> 1)) {
-        const int h = p & 1;
+      if (warp == p / CPW) {
+        const int hp = p % CPW;
         double xn2 = 0.0, al = 0.0;
 #pragma unroll
         for (int r = 0; r < MAXR; ++r) {
-          const int i = lane + 32 * r; const double x = h ? c1r[r] : c0r[r];
+          const int i = lane + 32 * r;
+          double x = cr[0][r];
+#pragma unroll
+          for (int h = 1; h < CPW; ++h) if (h == hp) x = cr[h][r];
           if (i > prow) xn2 = fma(x, x, xn2);
           if (i == prow) al = x;
         }
@@ -216,11 +225,13 @@ __global__ void __launch_bounds__(512, 1) k_qrp_reg(double* __restrict__ A, int 
 #pragma unroll
         for (int r = 0; r < MAXR; ++r) {
           const int i = lane + 32 * r;
-          if (i < m) {
-            double x = h ? c1r[r] : c0r[r];
-            if (i > prow) { x *= scal; v_s[i] = x; }
-            else if (i == prow) { x = beta; v_s[i] = 1.0; }
-            if (h) c1r[r] = x; else c0r[r] = x;
+          if (i < m && i >= prow) {
+            double x = cr[0][r];
+#pragma unroll
+            for (int h = 1; h < CPW; ++h) if (h == hp) x = cr[h][r];
+            if (i > prow) { x *= scal; v_s[i] = x; } else { x = beta; v_s[i] = 1.0; }
+#pragma unroll
+            for (int h = 0; h < CPW; ++h) if (h == hp) cr[h][r] = x;
           }
         }
         if (lane == 0) {
@@ -231,41 +242,60 @@ __global__ void __launch_bounds__(512, 1) k_qrp_reg(double* __restrict__ A, int 
       __syncthreads();
       {
         const double tj = tau_s[j];
-        const bool do0 = (s0 < nbk) && !((used >> s0) & 1u), do1 = (s1 < nbk) && !((used >> s1) & 1u);
-        if (do0 || do1) {
-          double w0 = 0.0, w1 = 0.0;
+        bool doh[CPW]; bool any = false;
+#pragma unroll
+        for (int h = 0; h < CPW; ++h) { doh[h] = (sb + h < nbk) && !((used >> (sb + h)) & 1u); any = any || doh[h]; }
+        if (any) {
+          double w[CPW], qn[CPW];
+#pragma unroll
+          for (int h = 0; h < CPW; ++h) { w[h] = 0.0; qn[h] = 0.0; }
           if (tj != 0.0) {
 #pragma unroll
             for (int r = 0; r < MAXR; ++r) {
               const int i = lane + 32 * r;
-              if (i >= prow && i < m) { const double v = v_s[i]; w0 = fma(v, c0r[r], w0); w1 = fma(v, c1r[r], w1); }
+              if (i >= prow && i < m) {
+                const double v = v_s[i];
+#pragma unroll
+                for (int h = 0; h < CPW; ++h) w[h] = fma(v, cr[h][r], w[h]);
+              }
             }
-            w0 = warp_sum(w0) * tj; w1 = warp_sum(w1) * tj;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+              for (int h = 0; h < CPW; ++h) w[h] += __shfl_xor_sync(0xffffffffu, w[h], o);
+#pragma unroll
+            for (int h = 0; h < CPW; ++h) w[h] *= tj;
           }
-          double q0 = 0.0, q1 = 0.0;
 #pragma unroll
           for (int r = 0; r < MAXR; ++r) {
             const int i = lane + 32 * r;
             if (i >= prow && i < m) {
               const double v = (tj != 0.0) ? v_s[i] : 0.0;
-              if (do0) c0r[r] = fma(-v, w0, c0r[r]);
-              if (do1) c1r[r] = fma(-v, w1, c1r[r]);
-              if (i > prow) { q0 = fma(c0r[r], c0r[r], q0); q1 = fma(c1r[r], c1r[r], q1); }
+#pragma unroll
+              for (int h = 0; h < CPW; ++h) {
+                if (doh[h]) cr[h][r] = fma(-v, w[h], cr[h][r]);
+                if (i > prow) qn[h] = fma(cr[h][r], cr[h][r], qn[h]);
+              }
             }
           }
-          q0 = warp_sum(q0); q1 = warp_sum(q1);
-          if (lane == 0) { if (do0) pn[s0] = sqrt(q0); if (do1) pn[s1] = sqrt(q1); }
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+            for (int h = 0; h < CPW; ++h) qn[h] += __shfl_xor_sync(0xffffffffu, qn[h], o);
+          if (lane == 0) {
+#pragma unroll
+            for (int h = 0; h < CPW; ++h) if (doh[h]) pn[sb + h] = sqrt(qn[h]);
+          }
         }
       }
       __syncthreads();
     }
     // ---- (5) write the factored panel back at the logical positions; V panel (explicit unit lower trapezoid) -> shared memory
-    int pos0 = -1, pos1 = -1;
+    int pos[CPW];
     {
       const int ps = (lane < nbk) ? pos_slot[lane] : -1;
-      const unsigned m0 = __ballot_sync(0xffffffffu, ps == s0), m1 = __ballot_sync(0xffffffffu, ps == s1);
-      if (m0) pos0 = __ffs(m0) - 1;
-      if (m1) pos1 = __ffs(m1) - 1;
+#pragma unroll
+      for (int h = 0; h < CPW; ++h) { const unsigned mk = __ballot_sync(0xffffffffu, ps == sb + h); pos[h] = mk ? (__ffs(mk) - 1) : -1; }
     }
     for (int e = tid; e < (mvp - mv) * NB; e += nthr) { const int r = mv + e % (mvp - mv), c = e / (mvp - mv); Vs[r + (long)c * ldv] = 0.0; }
     for (int e = tid; e < mvp * (NB - nbk); e += nthr) { const int r = e % mvp, c = nbk + e / mvp; Vs[r + (long)c * ldv] = 0.0; }
@@ -273,17 +303,17 @@ __global__ void __launch_bounds__(512, 1) k_qrp_reg(double* __restrict__ A, int 
     for (int r = 0; r < MAXR; ++r) {
       const int i = lane + 32 * r;
       if (i < m) {
-        if (pos0 >= 0) {
-          A[i + (long)(k0 + pos0) * ld] = c0r[r];
-          if (i >= k0) { const int rr = i - k0; Vs[rr + (long)pos0 * ldv] = (rr > pos0) ? c0r[r] : ((rr == pos0) ? 1.0 : 0.0); }
-        }
-        if (pos1 >= 0) {
-          A[i + (long)(k0 + pos1) * ld] = c1r[r];
-          if (i >= k0) { const int rr = i - k0; Vs[rr + (long)pos1 * ldv] = (rr > pos1) ? c1r[r] : ((rr == pos1) ? 1.0 : 0.0); }
+#pragma unroll
+        for (int h = 0; h < CPW; ++h) if (pos[h] >= 0) {
+          A[i + (long)(k0 + pos[h]) * ld] = cr[h][r];
+          if (i >= k0) { const int rr = i - k0; Vs[rr + (long)pos[h] * ldv] = (rr > pos[h]) ? cr[h][r] : ((rr == pos[h]) ? 1.0 : 0.0); }
         }
       }
     }
-    if (lane == 0) { if (pos0 >= 0) lista[pos0] = ipv[k0 + s0]; if (pos1 >= 0) lista[pos1] = ipv[k0 + s1]; }
+    if (lane == 0) {
+#pragma unroll
+      for (int h = 0; h < CPW; ++h) if (pos[h] >= 0) lista[pos[h]] = ipv[k0 + sb + h];
+    }
     if (tid < nbk) tau[k0 + tid] = tau_s[tid];
     if (tid >= nbk && tid < NB) tau_s[tid] = 0.0;
     __syncthreads();
@@ -342,10 +372,10 @@ __global__ void __launch_bounds__(512, 1) k_qrp_reg(double* __restrict__ A, int 
 
 // ------------------------------------------------------------------------------------------------------------------------
 // k_apply_q2: X <- Q^T X (MODE 0: panels forward with T^T; ZUNMQR 'L','C') or X <- Q X (MODE 1: panels backward with T;
-// ZUNMQR 'L','N'; with X = 1 this is ZUNGQR).  grid = (column groups of cols_per_cta, batch), 512 threads.
+// ZUNMQR 'L','N'; with X = 1 this is ZUNGQR).  grid = (column groups of cols_per_cta, batch), 256 threads, two CTAs per SM.
 // ------------------------------------------------------------------------------------------------------------------------
 template <int MODE, int IDENT>
-__global__ void __launch_bounds__(512) k_apply_q2(const double* __restrict__ QR, int m, int n, int ld, long sQ, const double* __restrict__ Tbuf, long sT,
+__global__ void __launch_bounds__(256, 2) k_apply_q2(const double* __restrict__ QR, int m, int n, int ld, long sQ, const double* __restrict__ Tbuf, long sT,
                                                   double* __restrict__ X, int ldx, long sX, int ncols, int cols_per_cta) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int NB = QR2_NB, LDW = QR2_LDW;

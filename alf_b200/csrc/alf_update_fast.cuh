@@ -24,12 +24,15 @@
 // scaled G0 tile (32 independent loads per thread issued up front, so the HBM/L2 latency is paid once per tile), then
 // (-X) Y^T is accumulated with DMMA m8n8k4 and the tile is stored.  X, Y: [k][ldx] with rows nd .. nd4-1 zeroed by the caller
 // (nd4 = nd rounded up to 4); ldx % 16 == 4 makes the fragment loads bank-conflict free.
+// rev = 1 walks the tiles in the opposite order: consecutive flushes alternate, so the tiles written last by one flush (still
+// in L2: the batch of Green functions is only slightly larger than the 126 MB L2) are the first ones the next flush reads.
 static __device__ __noinline__ void flush_g0(double* __restrict__ G0, int N, const double* __restrict__ X, const double* __restrict__ Y, int ldx, int nd4,
-                                      double* __restrict__ dl, double* __restrict__ dr) {
+                                      double* __restrict__ dl, double* __restrict__ dr, int rev) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
   const int tm = (N + 31) / 32, tiles = tm * tm;
   const int g = lane >> 2, q = lane & 3;
-  for (int t = warp; t < tiles; t += nw) {
+  for (int tt = warp; tt < tiles; tt += nw) {
+    const int t = rev ? tiles - 1 - tt : tt;
     const int i0 = (t % tm) * 32, j0 = (t / tm) * 32;
     double c[4][4][2];
 #pragma unroll
@@ -74,7 +77,7 @@ static __device__ __noinline__ void flush_g0(double* __restrict__ G0, int N, con
 }
 // complex: register-tiled FMA version of alf_update.cuh
 static __device__ __noinline__ void flush_g0(cplx* __restrict__ G0, int N, const cplx* __restrict__ X, const cplx* __restrict__ Y, int ldx, int nd4,
-                                         cplx* __restrict__ dl, cplx* __restrict__ dr) {
+                                         cplx* __restrict__ dl, cplx* __restrict__ dr, int) {
   flush_flavor<cplx>(G0, N, X, Y, ldx, nd4, dl, dr);
 }
 
@@ -175,6 +178,7 @@ __global__ void __launch_bounds__(512, 1) k_wrapgr_fast(T* __restrict__ G, int N
   cplx ph = phase[chain];
   unsigned long long n_acc = 0;
   int nd = 0;
+  int flush_rev = (nt + (UP ? 0 : 1)) & 1;      // alternate the tile order between consecutive flushes (also across slices)
 
   auto do_flush = [&]() {
     const int nd4 = (nd + 3) & ~3;
@@ -183,8 +187,11 @@ __global__ void __launch_bounds__(512, 1) k_wrapgr_fast(T* __restrict__ G, int N
       Xs[((long)f * KD + nd) * ldx + r] = zero_<T>(); Ys[((long)f * KD + nd) * ldx + r] = zero_<T>();
     }
     __syncthreads();
-    for (int f = 0; f < F; ++f)
-      flush_g0(Gc + (long)f * N * N, N, Xs + (long)f * KD * ldx, Ys + (long)f * KD * ldx, ldx, nd4, dl + f * N, dr + f * N);
+    for (int ff = 0; ff < F; ++ff) {
+      const int f = flush_rev ? F - 1 - ff : ff;
+      flush_g0(Gc + (long)f * N * N, N, Xs + (long)f * KD * ldx, Ys + (long)f * KD * ldx, ldx, nd4, dl + f * N, dr + f * N, flush_rev);
+    }
+    flush_rev ^= 1;
     nd = 0;
     __syncthreads();
   };
