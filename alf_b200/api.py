@@ -62,6 +62,11 @@ class AlfB200:
         for o in ot:
             self._ck(L.alf_b200_set_op_t(self.h, o["nc"], o["nf"], o["N"], o["diag"], o["P"].ctypes.data_as(_ip), _d(o["U"]), _d(o["E"]),
                                          C.c_double(o["g"].real), C.c_double(o["g"].imag)))
+        if getattr(model, "Projector", False):
+            self._ck(L.alf_b200_set_projector(self.h, int(model.Thtrot), int(model.N_part)))
+            for nf in range(model.N_FL):
+                pl = np.asfortranarray(model.WF_L[nf], dtype=np.complex128); pr = np.asfortranarray(model.WF_R[nf], dtype=np.complex128)
+                self._ck(L.alf_b200_set_trial_wf(self.h, nf + 1, _d(pl), _d(pr)))
         self._ck(L.alf_b200_finalize_model(self.h))
 
     def _ck(self, rc):
@@ -145,6 +150,9 @@ class AlfB200:
 
     def tau_m(self):
         self._ck(lib().alf_b200_tau_m(self.h))
+
+    def tau_p(self, nst_in):
+        self._ck(lib().alf_b200_tau_p(self.h, int(nst_in)))
 
     # ---- results
     def green(self, chain, nf, symmetrize=False):
@@ -292,6 +300,15 @@ def test_cgr(UR, DR, VR, UL, DL, VL, detUR, detUL, nvar=1, stab=0, is_complex=Tr
     G = np.zeros((batch, n, n), dtype=np.complex128); ph = np.zeros(batch, dtype=np.complex128)
     _chk(lib().alf_b200_test_cgr(device, int(is_complex), n, batch, int(nvar), int(stab), _d(a[0]), _d(dr), _d(a[1]), _d(a[2]), _d(dl), _d(a[3]),
                                  _d(d1), _d(d2), _d(G), _d(ph)), "test_cgr")
+    return G.transpose(0, 2, 1), ph
+
+
+def test_cgrp(UR, UL, is_complex=True, device=0):
+    """UR, UL: [batch, n, n_part]; returns G [batch, n, n] and the phases."""
+    UR = np.asarray(UR, dtype=np.complex128); UL = np.asarray(UL, dtype=np.complex128); batch, n, npart = UR.shape
+    a = np.ascontiguousarray(UR.transpose(0, 2, 1)); b = np.ascontiguousarray(UL.transpose(0, 2, 1))
+    G = np.zeros((batch, n, n), dtype=np.complex128); ph = np.zeros(batch, dtype=np.complex128)
+    _chk(lib().alf_b200_test_cgrp(device, int(is_complex), n, npart, batch, _d(a), _d(b), _d(G), _d(ph)), "test_cgrp")
     return G.transpose(0, 2, 1), ph
 
 

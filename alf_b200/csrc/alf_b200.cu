@@ -56,6 +56,7 @@ int alf_b200_create(alf_b200_handle** out, int ndim, int n_fl, int n_sun, int lt
 int alf_b200_destroy(alf_b200_handle* h) {
   if (!h) return ALF_OK;
   cudaSetDevice(h->device);
+  if (t_prof == &h->prof) t_prof = nullptr;          // the launch-accounting pointer must not outlive its handle
   h->eng.reset();
   if (h->d_fields) cudaFree(h->d_fields); if (h->d_rng) cudaFree(h->d_rng); if (h->d_phase) cudaFree(h->d_phase);
   if (h->d_counters) cudaFree(h->d_counters); if (h->d_ctl) cudaFree(h->d_ctl); if (h->d_acclog) cudaFree(h->d_acclog); if (h->d_obs) cudaFree(h->d_obs);
@@ -86,6 +87,22 @@ int alf_b200_set_op_t(alf_b200_handle* h, int nc, int nf, int N, int diag, const
   return fill_host_op(h->opt[(nc - 1) + (size_t)h->n_opt * (nf - 1)], N, N, diag, 0, P, U, E, g_re, g_im, 0, 0, h->ndim);
 }
 
+// projective algorithm: Thtrot and the number of particles per flavor, then one trial wave function pair per flavor
+// (WF_L(nf)%P, WF_R(nf)%P: Ndim x N_part, column-major complex; Prog/main.F90:366-376, 596-599)
+int alf_b200_set_projector(alf_b200_handle* h, int thtrot, int n_part) {
+  if (!h || h->finalized || thtrot < 0 || n_part < 1 || n_part > h->ndim) return ALF_ERROR_HAMILTONIAN;
+  h->projector = true; h->thtrot = thtrot; h->n_part = n_part;
+  h->wf_l.assign(h->n_fl, std::vector<cd>()); h->wf_r.assign(h->n_fl, std::vector<cd>());
+  return ALF_OK;
+}
+int alf_b200_set_trial_wf(alf_b200_handle* h, int nf, const double* PL, const double* PR) {
+  if (!h || h->finalized || !h->projector || nf < 1 || nf > h->n_fl || !PL || !PR) return ALF_ERROR_HAMILTONIAN;
+  const size_t n = (size_t)h->ndim * h->n_part;
+  h->wf_l[nf - 1].resize(n); h->wf_r[nf - 1].resize(n);
+  for (size_t i = 0; i < n; ++i) { h->wf_l[nf - 1][i] = cd(PL[2 * i], PL[2 * i + 1]); h->wf_r[nf - 1][i] = cd(PR[2 * i], PR[2 * i + 1]); }
+  return ALF_OK;
+}
+
 int alf_b200_finalize_model(alf_b200_handle* h) {
   API_BEGIN(h)
   for (auto& o : h->opv) if (!o.set) { h->err = "finalize_model: an Op_V entry was never set"; return ALF_ERROR_HAMILTONIAN; }
@@ -95,6 +112,14 @@ int alf_b200_finalize_model(alf_b200_handle* h) {
   bool cplx_needed = false;
   for (auto& o : h->opt) { if (o.g.imag() != 0.0) cplx_needed = true; for (auto& u : o.U) if (u.imag() != 0.0) cplx_needed = true; }
   for (auto& o : h->opv) { if (o.g.imag() != 0.0 || (o.g * o.alpha).imag() != 0.0) cplx_needed = true; for (auto& u : o.U) if (u.imag() != 0.0) cplx_needed = true; }
+  if (h->projector) {
+    for (int f = 0; f < h->n_fl; ++f) {
+      if (h->wf_l[f].size() != (size_t)h->ndim * h->n_part || h->wf_r[f].size() != (size_t)h->ndim * h->n_part) {
+        h->err = "Projector is selected but there are no trial wave functions!"; return ALF_ERROR_HAMILTONIAN; }      // main.F90:366-372
+      for (auto& z : h->wf_l[f]) if (z.imag() != 0.0) cplx_needed = true;
+      for (auto& z : h->wf_r[f]) if (z.imag() != 0.0) cplx_needed = true;
+    }
+  }
   h->is_complex = cplx_needed;
   const long C = h->n_chains;
   CK(cudaMalloc(&h->d_fields, (size_t)C * h->ltrot * std::max(1, h->n_opv))); CK(cudaMemset(h->d_fields, 1, (size_t)C * h->ltrot * std::max(1, h->n_opv)));
@@ -183,6 +208,7 @@ int alf_b200_wrapul(alf_b200_handle* h, int ntau1, int ntau) { API_BEGIN(h) NEED
 int alf_b200_udv_reset(alf_b200_handle* h, int which, char side) { API_BEGIN(h) NEED_FINAL(h) h->eng->udv_reset(which, side); h->eng->sync(); API_END(h) }
 int alf_b200_cgr(alf_b200_handle* h, int nvar) { API_BEGIN(h) NEED_FINAL(h) h->eng->cgr_call(nvar); h->eng->sync(); API_END(h) }
 int alf_b200_tau_m(alf_b200_handle* h) { API_BEGIN(h) NEED_FINAL(h) h->eng->tau_m(); h->eng->sync(); API_END(h) }
+int alf_b200_tau_p(alf_b200_handle* h, int nst_in) { API_BEGIN(h) NEED_FINAL(h) if (nst_in < 0) return ALF_ERROR_GENERIC; h->eng->tau_p(nst_in); h->eng->sync(); API_END(h) }
 
 int alf_b200_get_green(alf_b200_handle* h, int chain, int nf, int symmetrize, double* out) {
   API_BEGIN(h) NEED_FINAL(h) if (chain < 0 || chain >= h->n_chains || nf < 1 || nf > h->n_fl) return ALF_ERROR_GENERIC;
@@ -261,30 +287,34 @@ int alf_b200_hop_apply(alf_b200_handle* h, int which, int nf, double* A) { API_B
 
 // ---- kernel-level test entry points and FP64 peak microbenchmark
 int alf_b200_test_qdrp(int device, int is_complex, int m, int n, int batch, double* A, double* D, int* jpvt, double* tau, double* phases) {
-  try { CK(cudaSetDevice(device)); if (is_complex) alf_t_qdrp_cplx(m, n, batch, A, D, jpvt, tau, phases); else alf_t_qdrp_real(m, n, batch, A, D, jpvt, tau, phases); }
+  try { t_prof = nullptr; CK(cudaSetDevice(device)); if (is_complex) alf_t_qdrp_cplx(m, n, batch, A, D, jpvt, tau, phases); else alf_t_qdrp_real(m, n, batch, A, D, jpvt, tau, phases); }
   catch (const std::exception& e) { fprintf(stderr, "alf_b200_test_qdrp: %s\n", e.what()); return ALF_ERROR_CUDA; } return ALF_OK;
 }
 int alf_b200_test_qdrp_blocked(int device, int is_complex, int m, int n, int batch, double* A, double* D, int* jpvt, double* tau, double* phases, double* Q) {
-  try { CK(cudaSetDevice(device)); if (is_complex) alf_t_qdrp_blk_cplx(m, n, batch, A, D, jpvt, tau, phases, Q); else alf_t_qdrp_blk_real(m, n, batch, A, D, jpvt, tau, phases, Q); }
+  try { t_prof = nullptr; CK(cudaSetDevice(device)); if (is_complex) alf_t_qdrp_blk_cplx(m, n, batch, A, D, jpvt, tau, phases, Q); else alf_t_qdrp_blk_real(m, n, batch, A, D, jpvt, tau, phases, Q); }
   catch (const std::exception& e) { fprintf(stderr, "alf_b200_test_qdrp_blocked: %s\n", e.what()); return ALF_ERROR_CUDA; } return ALF_OK;
 }
 int alf_b200_test_udv_decompose(int device, int is_complex, int n, int batch, char side, double* U, double* D, double* V) {
-  try { CK(cudaSetDevice(device)); if (is_complex) alf_t_udv_cplx(n, batch, side, U, D, V); else alf_t_udv_real(n, batch, side, U, D, V); }
+  try { t_prof = nullptr; CK(cudaSetDevice(device)); if (is_complex) alf_t_udv_cplx(n, batch, side, U, D, V); else alf_t_udv_real(n, batch, side, U, D, V); }
   catch (const std::exception& e) { fprintf(stderr, "alf_b200_test_udv_decompose: %s\n", e.what()); return ALF_ERROR_CUDA; } return ALF_OK;
 }
 int alf_b200_test_cgr(int device, int is_complex, int n, int batch, int nvar, int stab, const double* UR, const double* DR, const double* VR,
                       const double* UL, const double* DL, const double* VL, const double* detUR, const double* detUL, double* G, double* phase) {
-  try { CK(cudaSetDevice(device)); if (is_complex) alf_t_cgr_cplx(n, batch, nvar, stab, UR, DR, VR, UL, DL, VL, detUR, detUL, G, phase);
+  try { t_prof = nullptr; CK(cudaSetDevice(device)); if (is_complex) alf_t_cgr_cplx(n, batch, nvar, stab, UR, DR, VR, UL, DL, VL, detUR, detUL, G, phase);
         else alf_t_cgr_real(n, batch, nvar, stab, UR, DR, VR, UL, DL, VL, detUR, detUL, G, phase); }
   catch (const std::exception& e) { fprintf(stderr, "alf_b200_test_cgr: %s\n", e.what()); return ALF_ERROR_CUDA; } return ALF_OK;
 }
+int alf_b200_test_cgrp(int device, int is_complex, int n, int n_part, int batch, const double* UR, const double* UL, double* G, double* phase) {
+  try { t_prof = nullptr; CK(cudaSetDevice(device)); if (is_complex) alf_t_cgrp_cplx(n, n_part, batch, UR, UL, G, phase); else alf_t_cgrp_real(n, n_part, batch, UR, UL, G, phase); }
+  catch (const std::exception& e) { fprintf(stderr, "alf_b200_test_cgrp: %s\n", e.what()); return ALF_ERROR_CUDA; } return ALF_OK;
+}
 int alf_b200_test_cgr2_2(int device, int is_complex, int n, int batch, int stab, const double* U2, const double* D2, const double* V2,
                          const double* U1, const double* D1, const double* V1, double* out4) {
-  try { CK(cudaSetDevice(device)); if (is_complex) alf_t_cgr22_cplx(n, batch, stab, U2, D2, V2, U1, D1, V1, out4); else alf_t_cgr22_real(n, batch, stab, U2, D2, V2, U1, D1, V1, out4); }
+  try { t_prof = nullptr; CK(cudaSetDevice(device)); if (is_complex) alf_t_cgr22_cplx(n, batch, stab, U2, D2, V2, U1, D1, V1, out4); else alf_t_cgr22_real(n, batch, stab, U2, D2, V2, U1, D1, V1, out4); }
   catch (const std::exception& e) { fprintf(stderr, "alf_b200_test_cgr2_2: %s\n", e.what()); return ALF_ERROR_CUDA; } return ALF_OK;
 }
 int alf_b200_test_gemm(int device, int is_complex, int ta, int tb, int m, int n, int k, int batch, const double* A, const double* B, double* C) {
-  try { CK(cudaSetDevice(device)); if (is_complex) alf_t_gemm_cplx(ta, tb, m, n, k, batch, A, B, C); else alf_t_gemm_real(ta, tb, m, n, k, batch, A, B, C); }
+  try { t_prof = nullptr; CK(cudaSetDevice(device)); if (is_complex) alf_t_gemm_cplx(ta, tb, m, n, k, batch, A, B, C); else alf_t_gemm_real(ta, tb, m, n, k, batch, A, B, C); }
   catch (const std::exception& e) { fprintf(stderr, "alf_b200_test_gemm: %s\n", e.what()); return ALF_ERROR_CUDA; } return ALF_OK;
 }
 

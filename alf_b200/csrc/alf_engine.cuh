@@ -117,6 +117,7 @@ struct EngineBase {
   virtual void udv_reset(int which, char side) = 0;
   virtual void cgr_call(int nvar) = 0;
   virtual void tau_m() = 0;
+  virtual void tau_p(int nst_in) = 0;
   virtual void get_green(int chain, int nf, int symm, cd* out) = 0;
   virtual void set_green(int chain, int nf, const cd* in) = 0;
   virtual void get_udv(int which, int nst, int chain, int nf, cd* U, cd* D, cd* V) = 0;
@@ -140,6 +141,8 @@ struct alf_b200_handle {
   double* d_obs = nullptr; int obs_size = 0;
   int taum_every = 0; std::vector<std::vector<cd>> taum_host, taum_fresh_host;   // per chain captured matrices
   std::vector<int> types;            // operator type per n
+  // projective algorithm (Prog/Hamiltonian_main_mod.F90:181-197: Projector, Thtrot, WF_L, WF_R)
+  bool projector = false; int thtrot = 0, n_part = 0; std::vector<std::vector<cd>> wf_l, wf_r;   // per flavor, Ndim x N_part column-major
 };
 
 static __global__ void k_ranset(uint64_t* rng, const int32_t* seeds, int n) {   // Ranset: random_wrap_mod.F90:52-80 with K = 8, N = 1
@@ -212,6 +215,22 @@ __global__ void k_g0t_init(T* __restrict__ G0T, const T* __restrict__ G, long sM
   }
 }
 
+// reset_UDV_state with a trial wave function (udv_state_mod.F90:320-345): U(:, 1:N_part) = P of the matrix's flavor
+template <typename T>
+__global__ void k_set_wf(T* __restrict__ U, long sM, const T* __restrict__ wf, int F, int N, int NP) {
+  const int b = blockIdx.y, f = b % F; U += (long)b * sM; wf += (long)f * N * NP;
+  for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < (long)N * NP; e += (long)gridDim.x * blockDim.x) U[e] = wf[e];
+}
+// dst = alpha * src + beta * 1
+template <typename T>
+__global__ void k_axpb_identity(T* __restrict__ dst, const T* __restrict__ src, long sM, int n, double alpha, double beta) {
+  const int b = blockIdx.y; dst += (long)b * sM; src += (long)b * sM;
+  for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < (long)n * n; e += (long)gridDim.x * blockDim.x) {
+    const int i = (int)(e % n), j = (int)(e / n);
+    dst[e] = alpha * src[e] + ((i == j) ? make_<T>(beta, 0.0) : zero_<T>());
+  }
+}
+
 template <typename T>
 struct Engine : EngineBase {
   alf_b200_handle* h;
@@ -228,6 +247,8 @@ struct Engine : EngineBase {
   bool fast_upd = false; int KDf = 0, ldxf = 0, iptf = 1; size_t fast_smem = 0;   // k_wrapgr_fast (all vertices diagonal, k = 1)
   // tau_m work
   T *GT0 = nullptr, *G0T = nullptr, *G00 = nullptr, *GTT = nullptr, *TMPG = nullptr; UdvDev<T> udvr2;
+  // projective algorithm
+  bool proj = false; int NP = 0, thtrot = 0; T *d_wfl = nullptr, *d_wfr = nullptr; LaWork<T> wp;
 
   template <typename X> X* dalloc(size_t n) { X* p = nullptr; CK(cudaMalloc(&p, sizeof(X) * (n ? n : 1))); owned.push_back(p); return p; }
   template <typename X> X* dupload(const std::vector<X>& v) { X* p = dalloc<X>(v.size()); if (!v.empty()) CK(cudaMemcpy(p, v.data(), sizeof(X) * v.size(), cudaMemcpyHostToDevice)); return p; }
@@ -252,6 +273,14 @@ struct Engine : EngineBase {
     G = dalloc<T>(n2 * NM); G2 = dalloc<T>(n2 * NM);
     udvl = alloc_udv(); udvr = alloc_udv(); udvst.resize(S); for (int s = 0; s < S; ++s) udvst[s] = alloc_udv();
     w.alloc(N, NM, st);
+    proj = h->projector; NP = proj ? h->n_part : N; thtrot = h->thtrot;
+    if (proj) {
+      if (NP < 1 || NP > N) throw CudaError("projector: illegal number of particles (0 < N_part <= Ndim)");
+      wp.alloc(NP, NM, st);
+      std::vector<T> a((size_t)F * N * NP), b2((size_t)F * N * NP);
+      for (int f = 0; f < F; ++f) for (long i = 0; i < (long)N * NP; ++i) { a[(size_t)f * N * NP + i] = to_T<T>(h->wf_l[f][i]); b2[(size_t)f * N * NP + i] = to_T<T>(h->wf_r[f][i]); }
+      d_wfl = dupload(a); d_wfr = dupload(b2);
+    }
     d_z = dalloc<cplx>(NM); d_angle = dalloc<double>(NM); d_cmp = dalloc<double>((size_t)NM * 3);
     // update kernel configuration: as many delayed columns as fit in ~200 KB of shared memory
     size_t per_kd = (size_t)F * 2 * (N + 2) * sizeof(T), fixed = (size_t)F * 3 * N * sizeof(T) + 256;
@@ -293,7 +322,7 @@ struct Engine : EngineBase {
     if (ops_lk == 0) OPS_ATTR(0); else if (ops_lk == 1) OPS_ATTR(1); else OPS_ATTR(2);
 #undef OPS_ATTR
   }
-  ~Engine() { for (void* p : owned) cudaFree(p); w.release(); }
+  ~Engine() { for (void* p : owned) cudaFree(p); w.release(); if (proj) wp.release(); if (w2_ready) w2.release(); }
   // Optional (ALF_B200_L2_PERSIST=1): persisting-L2 access window over the batch of Green functions.  Measured on B200 with
   // 148 chains x 1 MB (slightly more than L2): the slice kernel got SLOWER (1.28 ms vs 1.05 ms), so it is off by default.
   double l2_persist_frac = -1.0; size_t l2_persist_bytes = 0;
@@ -401,9 +430,10 @@ struct Engine : EngineBase {
   }
 
   // ---------------------------------------------------------------- op-list launches
-  void apply_ops(T* Mx, int side, int mode, int nt_a, int nt_b) {
-    dim3 grid((N + OPS_PW - 1) / OPS_PW, NM);
-#define OPS_LAUNCH(SD, LKV) KL(KC_OPS, st, k_apply_ops<T, SD, LKV><<<grid, 256, ops_smem, st>>>(Mx, n2, N, N, md, F, mode, nt_a, nt_b, h->d_fields, L, M))
+  void apply_ops(T* Mx, int side, int mode, int nt_a, int nt_b, int nvec = -1) {     // nvec: number of columns (side 0) / rows (side 1)
+    if (nvec < 0) nvec = N;
+    dim3 grid((nvec + OPS_PW - 1) / OPS_PW, NM);
+#define OPS_LAUNCH(SD, LKV) KL(KC_OPS, st, k_apply_ops<T, SD, LKV><<<grid, 256, ops_smem, st>>>(Mx, n2, N, nvec, md, F, mode, nt_a, nt_b, h->d_fields, L, M))
     if (side == 0) { if (ops_lk == 0) OPS_LAUNCH(0, 0); else if (ops_lk == 1) OPS_LAUNCH(0, 1); else OPS_LAUNCH(0, 2); }
     else { if (ops_lk == 0) OPS_LAUNCH(1, 0); else if (ops_lk == 1) OPS_LAUNCH(1, 1); else OPS_LAUNCH(1, 2); }
 #undef OPS_LAUNCH
@@ -438,25 +468,34 @@ struct Engine : EngineBase {
     CK(cudaMemcpyAsync(dst.D, src.D, sizeof(double) * N * NM, cudaMemcpyDeviceToDevice, st));
     CK(cudaMemcpyAsync(dst.det, src.det, sizeof(cplx) * NM, cudaMemcpyDeviceToDevice, st));
   }
-  void udv_reset(int which, char side) override { (void)side; set_udv_identity(which == 0 ? udvl : udvr); }
+  // reset_UDV_state: identity (finite temperature) or the trial wave function of the given side (projector)
+  void reset_udv(UdvDev<T>& u, char side) {
+    if (!proj) { set_udv_identity(u); return; }
+    KL(KC_EW, st, k_set_wf<T><<<dim3(ew_blocks((long)N * NP), NM), 256, 0, st>>>(u.U, n2, (side == 'l' || side == 'L') ? d_wfl : d_wfr, F, N, NP));
+    KL(KC_EW, st, k_fill_double<<<ew_blocks((long)N * NM), 256, 0, st>>>(u.D, (long)N * NM, 1.0));
+    KL(KC_EW, st, k_fill_cplx<<<ew_blocks(NM), 256, 0, st>>>(u.det, NM, cplx(1.0, 0.0)));
+  }
+  void decompose(UdvDev<T>& u, char side) { if (proj) la_decompose_proj<T>(w, u, side, NP); else la_decompose<T>(w, u, side); }
+  void udv_reset(int which, char side) override { reset_udv(which == 0 ? udvl : udvr, side); }
 
   // WRAPUR (Prog/wrapur_mod.F90:102-123) / WRAPUL (Prog/wrapul_mod.F90:108-129) on a batch
   void wrapur_on(UdvDev<T>& u, int ntau, int ntau1) {
-    if (!dense_t) apply_ops(u.U, 0, MODE_WRAPUR, ntau + 1, ntau1);
-    else for (int nt = ntau + 1; nt <= ntau1; ++nt) { dense_mult(u.U, 0, true); apply_ops(u.U, 0, MODE_WRAPUR, nt, nt); }
-    la_decompose<T>(w, u, 'r');
+    if (!dense_t) apply_ops(u.U, 0, MODE_WRAPUR, ntau + 1, ntau1, NP);
+    else for (int nt = ntau + 1; nt <= ntau1; ++nt) { dense_mult(u.U, 0, true); apply_ops(u.U, 0, MODE_WRAPUR, nt, nt, NP); }
+    decompose(u, 'r');
   }
   void wrapul_on(UdvDev<T>& u, int ntau1, int ntau) {
-    if (!dense_t) apply_ops(u.U, 0, MODE_WRAPUL, ntau + 1, ntau1);
-    else for (int nt = ntau1; nt >= ntau + 1; --nt) { apply_ops(u.U, 0, MODE_WRAPUL, nt, nt); dense_mult(u.U, 2, true); }
-    la_decompose<T>(w, u, 'l');
+    if (!dense_t) apply_ops(u.U, 0, MODE_WRAPUL, ntau + 1, ntau1, NP);
+    else for (int nt = ntau1; nt >= ntau + 1; --nt) { apply_ops(u.U, 0, MODE_WRAPUL, nt, nt, NP); dense_mult(u.U, 2, true); }
+    decompose(u, 'l');
   }
   void wrapur(int ntau, int ntau1) override { wrapur_on(udvr, ntau, ntau1); }
   void wrapul(int ntau1, int ntau) override { wrapul_on(udvl, ntau1, ntau); }
 
   // CGR + Op_phase + Control_PrecisionG/P  (main.F90:742-753)
   void cgr_and_phase(int nvar, bool compare) {
-    la_cgr<T>(w, nvar, h->stab, udvr, udvl, G2, d_z);
+    if (proj) la_cgrp<T>(w, wp, udvr, udvl, G2, d_z);      // cgr1_mod.F90:207-211
+    else la_cgr<T>(w, nvar, h->stab, udvr, udvl, G2, d_z);
     if (compare) {
       KL(KC_EW, st, k_compare<T><<<NM, 256, 0, st>>>(G2, G, n2, n2, d_cmp));
       KL(KC_EW, st, k_ctl_accum<<<(C + 127) / 128, 128, 0, st>>>(d_cmp, F, h->d_ctl, 0, C));
@@ -495,7 +534,7 @@ struct Engine : EngineBase {
 
   // main.F90:589-631
   void init_sweep() override {
-    set_udv_identity(udvl); set_udv_identity(udvr); set_udv_identity(udvst[S - 1]);
+    reset_udv(udvl, 'l'); reset_udv(udvr, 'r'); reset_udv(udvst[S - 1], 'l');
     for (int NST = S - 1; NST >= 1; --NST) { wrapul_on(udvl, stab_nt[NST + 1], stab_nt[NST]); copy_udv(udvst[NST - 1], udvl); }
     wrapul_on(udvl, stab_nt[1], 0);
     cgr_and_phase(1, false);
@@ -505,7 +544,7 @@ struct Engine : EngineBase {
 
   // main.F90:714-887
   void sweep(int ltau) override {
-    set_udv_identity(udvr);
+    reset_udv(udvr, 'r');
     int NST = 1;
     for (int NTAU = 0; NTAU <= L - 1; ++NTAU) {
       const int NTAU1 = NTAU + 1;
@@ -519,7 +558,7 @@ struct Engine : EngineBase {
       }
       measure_hook(NTAU1);
     }
-    set_udv_identity(udvl);
+    reset_udv(udvl, 'l');
     NST = S - 1;
     for (int NTAU = L; NTAU >= 1; --NTAU) {
       const int NTAU1 = NTAU - 1;
@@ -530,25 +569,28 @@ struct Engine : EngineBase {
         std::swap(udvr, udvst[NST - 1]);            // udvr = udvst(NST)
         copy_udv(udvst[NST - 1], udvl);             // udvst(NST) = udvl
         cgr_and_phase(NTAU1 > L / 2 ? 2 : 1, true);
+        if (ltau == 1 && proj && stab_nt[NST] <= thtrot + 1 && thtrot + 1 < stab_nt[NST + 1]) tau_p(NST);     // main.F90:829-831
         NST--;
       }
     }
     wrapul_on(udvl, stab_nt[1], stab_nt[0]);
-    set_udv_identity(udvr);
+    reset_udv(udvr, 'r');
     cgr_and_phase(1, true);
-    set_udv_identity(udvst[S - 1]);
-    if (ltau == 1) tau_m();
+    reset_udv(udvst[S - 1], 'l');
+    if (ltau == 1 && !proj) tau_m();
+    if (ltau == 1 && proj && stab_nt[1] > thtrot + 1) tau_p(0);                                              // main.F90:884-886
   }
 
   // ---------------------------------------------------------------- TAU_M (Prog/tau_m_mod.F90:56-211) for all chains
   LaWork<T> w2; bool w2_ready = false; T* tmN[4] = {nullptr, nullptr, nullptr, nullptr}; int* d_first = nullptr; T* capbuf = nullptr;
+  bool taum_ready = false;
   void taum_alloc() {
-    if (w2_ready) return;
-    w2.alloc(2 * N, NM, st);
+    if (taum_ready) return;
+    if (!proj) { w2.alloc(2 * N, NM, st); w2_ready = true; }
     GT0 = dalloc<T>(n2 * NM); G0T = dalloc<T>(n2 * NM); G00 = dalloc<T>(n2 * NM); GTT = dalloc<T>(n2 * NM);
     for (int q = 0; q < 4; ++q) tmN[q] = dalloc<T>(n2 * NM);
     udvr2 = alloc_udv(); d_first = dalloc<int>(NM); capbuf = dalloc<T>(n2 * NM);
-    w2_ready = true;
+    taum_ready = true;
   }
   void taum_capture(int nt, bool fresh = false) {     // what ham%ObserT receives (tau_m_mod.F90:115-124,151-177); test support only
     if (!h->taum_every) return;
@@ -594,6 +636,48 @@ struct Engine : EngineBase {
       }
     }
   }
+  // ---------------------------------------------------------------- Tau_p (Prog/tau_p_mod.F90:74-336, sequential update path) for all chains
+  void tau_p(int NST_IN) override {
+    if (!proj) throw CudaError("tau_p: the handle was not set up for the projective algorithm");
+    taum_alloc();
+    const size_t bytes = sizeof(T) * n2 * NM; dim3 eg(ew_blocks(n2), NM);
+    copy_udv(udvr2, udvr);                                     // udvr_local
+    CK(cudaMemcpyAsync(GTT, G, bytes, cudaMemcpyDeviceToDevice, st));
+    int NT_ST = NST_IN;
+    T* GRUP = tmN[0];
+    auto restab = [&]() {                                      // Wrapur + CGRP + Control_Precision_tau (:131-142, :198-208)
+      wrapur_on(udvr2, stab_nt[NT_ST], stab_nt[NT_ST + 1]);
+      la_cgrp<T>(w, wp, udvr2, udvst[NT_ST], GRUP, d_z);       // udvst(nt_st + 1) in the reference's 1-based numbering
+      compare_tau(GTT, GRUP);
+    };
+    for (int NT = stab_nt[NT_ST] + 1; NT <= thtrot + 1; ++NT) {
+      proprm1(GTT, NT); propr(GTT, NT);
+      if (NT_ST + 1 <= S && NT == stab_nt[NT_ST + 1]) { restab(); CK(cudaMemcpyAsync(GTT, GRUP, bytes, cudaMemcpyDeviceToDevice, st)); NT_ST++; }
+    }
+    CK(cudaMemcpyAsync(G00, GTT, bytes, cudaMemcpyDeviceToDevice, st)); CK(cudaMemcpyAsync(GT0, GTT, bytes, cudaMemcpyDeviceToDevice, st));
+    KL(KC_EW, st, k_g0t_init<T><<<eg, 256, 0, st>>>(G0T, GTT, n2, N));                     // G0T = GTT - 1
+    taum_capture(0);
+    int NCHECK = 0;
+    for (int NT = thtrot + 1; NT <= L - thtrot; ++NT) {
+      const int NTAU = NT - thtrot - 1;
+      if (NT_ST + 1 <= S && NT == stab_nt[NT_ST + 1] && NTAU != 0) {
+        restab(); NT_ST++; NCHECK++;
+        CK(cudaMemcpyAsync(GTT, GRUP, bytes, cudaMemcpyDeviceToDevice, st));
+        gemm<T, 0, 0, 0>(st, N, N, N, GRUP, N, n2, GT0, N, n2, tmN[1], N, n2, NM); std::swap(GT0, tmN[1]);          // GT0 = G GT0
+        KL(KC_EW, st, k_axpb_identity<T><<<eg, 256, 0, st>>>(tmN[2], GRUP, n2, N, -1.0, 1.0));                    // 1 - G
+        gemm<T, 0, 0, 0>(st, N, N, N, G0T, N, n2, tmN[2], N, n2, tmN[1], N, n2, NM); std::swap(G0T, tmN[1]);        // G0T = G0T (1 - G)
+        taum_capture(NT, true);
+      }
+      const int NT1 = NT + 1;
+      propr(GT0, NT1); proprm1(G0T, NT1); proprm1(GTT, NT1); propr(GTT, NT1);
+      taum_capture(NTAU + 1);
+    }
+    if (NCHECK == 0 && NT_ST + 1 <= S) {                       // fallback check of the reference (:262-279)
+      for (int NT = L - thtrot + 2; NT <= stab_nt[NT_ST + 1]; ++NT) { proprm1(GTT, NT); propr(GTT, NT); }
+      restab(); NT_ST++;
+    }
+  }
+
   // PROPR / PROPRM1 (Prog/tau_m_mod.F90:215-263): A <- B(nt) A ;  A <- A B(nt)^-1
   void propr(T* A, int nt) {
     if (!dense_t) apply_ops(A, 0, MODE_WRAPUR, nt, nt);
@@ -693,6 +777,22 @@ static void t_cgr(int n, int batch, int nvar, int stab, const double* UR, const 
   la_cgr<T>(w, nvar, stab, R, L, dG.p, dz.p); CK(cudaDeviceSynchronize());
   T2h<T>(dG.down(), G); auto z = dz.down(); for (int i = 0; i < batch; ++i) { phase[2 * i] = z[i].x; phase[2 * i + 1] = z[i].y; }
   w.release();
+}
+template <typename T>
+static void t_cgrp(int n, int np, int batch, const double* UR, const double* UL, double* G, double* phase) {
+  const size_t n2 = (size_t)n * n; LaWork<T> w, wp; w.alloc(n, batch, 0); wp.alloc(np, batch, 0);
+  DevBuf<T> dUR(n2 * batch), dUL(n2 * batch), dG(n2 * batch); DevBuf<cplx> dz(batch);
+  // inputs are n x np per matrix; the device layout keeps the leading dimension n inside an n x n slot
+  std::vector<T> a(n2 * batch, zero_<T>()), b(n2 * batch, zero_<T>());
+  for (int q = 0; q < batch; ++q) for (size_t i = 0; i < (size_t)n * np; ++i) {
+    const size_t src = (size_t)q * n * np + i;
+    a[(size_t)q * n2 + i] = to_T<T>(cd(UR[2 * src], UR[2 * src + 1])); b[(size_t)q * n2 + i] = to_T<T>(cd(UL[2 * src], UL[2 * src + 1]));
+  }
+  dUR.up(a); dUL.up(b);
+  UdvDev<T> R, L; R.U = dUR.p; L.U = dUL.p;
+  la_cgrp<T>(w, wp, R, L, dG.p, dz.p); CK(cudaDeviceSynchronize());
+  T2h<T>(dG.down(), G); auto z = dz.down(); for (int i = 0; i < batch; ++i) { phase[2 * i] = z[i].x; phase[2 * i + 1] = z[i].y; }
+  w.release(); wp.release();
 }
 template <typename T>
 static void t_cgr22(int n, int batch, int stab, const double* U2, const double* D2, const double* V2, const double* U1, const double* D1, const double* V1, double* out4) {

@@ -461,7 +461,7 @@ __global__ void __launch_bounds__(32) k_tri_inv_blocks(const double* __restrict_
 }
 
 template <int LOWER>
-__global__ void __launch_bounds__(256) k_trsm_blk(const double* __restrict__ R, int ldr, long sR, const double* __restrict__ Rinv, long sI,
+__global__ void __launch_bounds__(512) k_trsm_blk(const double* __restrict__ R, int ldr, long sR, const double* __restrict__ Rinv, long sI,
                                                   double* __restrict__ B, int ldb, long sB, int n, int nrhs, const double* __restrict__ dinv, long sD) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* Xs = reinterpret_cast<double*>(smem_raw);          // [TRSMB_CW][ldx], rows contiguous
@@ -577,10 +577,10 @@ __global__ void k_row0scale(T* __restrict__ A, int ld, long sA, int n, const cpl
 }
 // dst = src with column 0 multiplied by s[b]  (explicit Q of the blocked path -> U, udv_state_mod.F90:578)
 template <typename T>
-__global__ void k_copy_col0scale(T* __restrict__ dst, const T* __restrict__ src, long sM, int n, const cplx* __restrict__ s) {
+__global__ void k_copy_col0scale(T* __restrict__ dst, const T* __restrict__ src, long sM, int n, const cplx* __restrict__ s, long count) {
   const int b = blockIdx.y; dst += (long)b * sM; src += (long)b * sM;
   const T st = make_<T>(s[b].x, s[b].y);
-  for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < (long)n * n; e += (long)gridDim.x * blockDim.x) dst[e] = (e < n) ? src[e] * st : src[e];
+  for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < count; e += (long)gridDim.x * blockDim.x) dst[e] = (e < n) ? src[e] * st : src[e];
 }
 // identity / zero fill
 template <typename T>

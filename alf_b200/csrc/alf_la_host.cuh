@@ -128,7 +128,8 @@ static void launch_trsm_blk(cudaStream_t st, const double* R, int ldr, long sR, 
   const size_t smem = sizeof(double) * (size_t)ld_pad(np) * TRSMB_CW;
   KL(KC_TRSM, st, k_tri_inv_blocks<LOWER><<<dim3(nb, batch), 32, 0, st>>>(R, ldr, sR, n, rinv, sI));
   CK(cudaFuncSetAttribute(k_trsm_blk<LOWER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  KL(KC_TRSM, st, k_trsm_blk<LOWER><<<dim3((nrhs + TRSMB_CW - 1) / TRSMB_CW, batch), 256, smem, st>>>(R, ldr, sR, rinv, sI, B, ldb, sB, n, nrhs, dinv, sD));
+  const int nthr = (2 * (smem + 1024) <= 227 * 1024) ? 256 : 512;      // one resident CTA per SM only: give it 16 warps
+  KL(KC_TRSM, st, k_trsm_blk<LOWER><<<dim3((nrhs + TRSMB_CW - 1) / TRSMB_CW, batch), nthr, smem, st>>>(R, ldr, sR, rinv, sI, B, ldb, sB, n, nrhs, dinv, sD));
 }
 static inline bool la_force_old_trsm() { static int v = -1; if (v < 0) v = getenv("ALF_B200_OLD_TRSM") ? 1 : 0; return v == 1; }
 
@@ -198,11 +199,14 @@ template <typename T>
 static void launch_apply_q(cudaStream_t st, const T* QR, int m, int n, int ld, long sQ, const T* Tbuf, T* X, int ldx, long sX, int ncols, int mode, bool ident, int batch) {
   if constexpr (std::is_same<T, double>::value) {
     if (use_qr2<T>(m, n)) {
-      const size_t smem = applyq2_smem(m, 8); const int cpc2 = 64; dim3 grid2((ncols + cpc2 - 1) / cpc2, batch); const long sT2 = (long)(n + 32) * 32;
+      const bool small = applyq2_smem(m, 8) + 1024 <= 113 * 1024;        // two 8-warp CTAs per SM, else one 16-warp CTA
+      const size_t smem = applyq2_smem(m, small ? 8 : 16); const int cpc2 = small ? 64 : 128; dim3 grid2((ncols + cpc2 - 1) / cpc2, batch);
+      const long sT2 = (long)(n + 32) * 32;
       KScope ks_(KC_FORMQ, st);
-#define AQ2_LAUNCH(MD, ID) do { CK(cudaFuncSetAttribute(k_apply_q2<MD, ID>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        k_apply_q2<MD, ID><<<grid2, 256, smem, st>>>(QR, m, n, ld, sQ, Tbuf, sT2, X, ldx, sX, ncols, cpc2); } while (0)
-      if (mode == 0) AQ2_LAUNCH(0, 0); else if (ident) AQ2_LAUNCH(1, 1); else AQ2_LAUNCH(1, 0);
+#define AQ2_LAUNCH(MD, ID, NT) do { CK(cudaFuncSetAttribute(k_apply_q2<MD, ID, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        k_apply_q2<MD, ID, NT><<<grid2, NT, smem, st>>>(QR, m, n, ld, sQ, Tbuf, sT2, X, ldx, sX, ncols, cpc2); } while (0)
+      if (small) { if (mode == 0) AQ2_LAUNCH(0, 0, 256); else if (ident) AQ2_LAUNCH(1, 1, 256); else AQ2_LAUNCH(1, 0, 256); }
+      else { if (mode == 0) AQ2_LAUNCH(0, 0, 512); else if (ident) AQ2_LAUNCH(1, 1, 512); else AQ2_LAUNCH(1, 0, 512); }
 #undef AQ2_LAUNCH
       CKL();
       return;
@@ -225,6 +229,13 @@ template <typename T>
 static void la_qrp(LaWork<T>& w, T* A, int m, int n, double* D) {
   if (use_blocked_qr<T>(m, n)) launch_qrp_blk<T>(w.st, A, m, n, m, (long)m * n, w.tau, n, w.jpvt, n, D, n, w.qrout, w.Tbuf, w.NM);
   else launch_qrp<T, 1>(w.st, A, m, n, m, (long)m * n, w.tau, n, w.jpvt, n, D, n, w.qrout, w.NM);
+}
+
+// pivoted QR of m x n matrices stored with leading dimension ld and batch stride sA (tau / jpvt strides = w.N, D stride sD)
+template <typename T>
+static void la_qrp_gen(LaWork<T>& w, T* A, int m, int n, int ld, long sA, double* D, long sD) {
+  if (use_blocked_qr<T>(m, n)) launch_qrp_blk<T>(w.st, A, m, n, ld, sA, w.tau, w.N, w.jpvt, w.N, D, sD, w.qrout, w.Tbuf, w.NM);
+  else launch_qrp<T, 1>(w.st, A, m, n, ld, sA, w.tau, w.N, w.jpvt, w.N, D, sD, w.qrout, w.NM);
 }
 
 // phase bookkeeping of decompose (udv_state_mod.F90:480-492, 578): Phase = prod R_ii * sign(perm), conjugated for side L;
@@ -257,7 +268,38 @@ static void la_decompose(LaWork<T>& w, UdvDev<T>& s, char side) {
   else {   // Q = H_1 ... H_n applied to the identity block-wise, then column 1 scaled by the phase (udv_state_mod.F90:576-578)
     KL(KC_EW, st, k_set_identity<T><<<dim3(ew_blocks(n2), NM), 256, 0, st>>>(w.W[1], N, n2, N, N));
     launch_apply_q<T>(st, s.U, N, N, N, n2, w.Tbuf, w.W[1], N, n2, N, 1, true, NM);
-    KL(KC_EW, st, k_copy_col0scale<T><<<dim3(ew_blocks(n2), NM), 256, 0, st>>>(s.U, w.W[1], n2, N, w.sc_phase));
+    KL(KC_EW, st, k_copy_col0scale<T><<<dim3(ew_blocks(n2), NM), 256, 0, st>>>(s.U, w.W[1], n2, N, w.sc_phase, n2));
+  }
+}
+
+// decompose_UDV_state for the projective algorithm (no V: udv_state_mod.F90:473-493,576-578): U (N x N_part, leading dimension N)
+// <- Q of the pivoted QR, first column scaled by the phase; D <- |R_ii|.
+template <typename T>
+static void la_decompose_proj(LaWork<T>& w, UdvDev<T>& s, char side, int NP) {
+  const int N = w.N, NM = w.NM; const long n2 = w.n2(); cudaStream_t st = w.st;
+  const bool left = (side == 'l' || side == 'L');
+  const bool blk = use_blocked_qr<T>(N, NP);
+  la_qrp_gen<T>(w, s.U, N, NP, N, n2, s.D, N);
+  KL(KC_EW, st, k_decomp_phase<<<(NM + 127) / 128, 128, 0, st>>>(w.qrout, left ? 1 : 0, w.sc_phase, w.sc_beta, s.det, NM));
+  if (!blk) launch_formq<T>(st, s.U, N, NP, N, n2, w.tau, N, w.sc_phase, NM);
+  else {
+    KL(KC_EW, st, k_set_identity<T><<<dim3(ew_blocks((long)N * NP), NM), 256, 0, st>>>(w.W[1], N, n2, N, NP));
+    launch_apply_q<T>(st, s.U, N, NP, N, n2, w.Tbuf, w.W[1], N, n2, NP, 1, true, NM);
+    KL(KC_EW, st, k_copy_col0scale<T><<<dim3(ew_blocks((long)N * NP), NM), 256, 0, st>>>(s.U, w.W[1], n2, N, w.sc_phase, (long)N * NP));
+  }
+}
+
+// phase of det(U_L^H U_R) from its pivoted QR: det(Q) prod R_ii/|R_ii| sign(P)   (CGRP, Prog/cgr1_mod.F90:497-506)
+static __global__ void k_cgrp_z(const QrOut* __restrict__ q, cplx* __restrict__ z, int n) {
+  int b = blockIdx.x * blockDim.x + threadIdx.x; if (b >= n) return;
+  z[b] = (q[b].detq * q[b].diag_phase) * q[b].perm_sign;
+}
+template <typename T>
+__global__ void k_one_minus(T* __restrict__ G, long sM, int n) {
+  const int b = blockIdx.y; G += (long)b * sM;
+  for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < (long)n * n; e += (long)gridDim.x * blockDim.x) {
+    const int i = (int)(e % n), j = (int)(e / n);
+    G[e] = ((i == j) ? one_<T>() : zero_<T>()) - G[e];
   }
 }
 
@@ -325,6 +367,19 @@ static void la_inverse(LaWork<T>& w, T* A, T* Ainv) {
   }
   launch_trsm<T>(st, A, N, n2, w.W[1], N, n2, N, N, w.Dq, N, NM, w.Rinv, w.sRinv());                                            // R^-1 D^-1 Q^H
   KL(KC_EW, st, k_permcopy<T, 3><<<eg, 256, 0, st>>>(Ainv, N, n2, w.W[1], N, n2, N, N, w.jpvt, N));          // rows scattered by P
+}
+
+// CGRP (Prog/cgr1_mod.F90:464-515) for a batch: G = 1 - U_R (U_L^H U_R)^-1 U_L^H and z = phase of det(U_L^H U_R).
+// w: N-sized workspace, wp: N_part-sized workspace.  The LU of the reference is replaced by the pivoted QR already on the device.
+template <typename T>
+static void la_cgrp(LaWork<T>& w, LaWork<T>& wp, const UdvDev<T>& R, const UdvDev<T>& L, T* Gout, cplx* z) {
+  const int N = w.N, NP = wp.N, NM = w.NM; const long n2 = w.n2(), np2 = wp.n2(); cudaStream_t st = w.st;
+  gemm<T, 1, 0, 0>(st, NP, NP, N, L.U, N, n2, R.U, N, n2, wp.W[2], NP, np2, NM);                   // S = U_L^H U_R
+  la_inverse<T>(wp, wp.W[2], wp.W[3]);                                                             // S^-1
+  KL(KC_EW, st, k_cgrp_z<<<(NM + 127) / 128, 128, 0, st>>>(wp.qrout, z, NM));
+  gemm<T, 0, 1, 0>(st, NP, N, NP, wp.W[3], NP, np2, L.U, N, n2, w.W[0], NP, (long)NP * N, NM);      // rMat = S^-1 U_L^H
+  gemm<T, 0, 0, 0>(st, N, N, NP, R.U, N, n2, w.W[0], NP, (long)NP * N, Gout, N, n2, NM);            // U_R rMat
+  KL(KC_EW, st, k_one_minus<T><<<dim3(ew_blocks(n2), NM), 256, 0, st>>>(Gout, n2, N));
 }
 
 // CGR2_2 (Prog/cgr2_2_mod.F90:318-425) for a batch: w is the N-sized workspace, w2 the 2N-sized one (w2.NM == w.NM).

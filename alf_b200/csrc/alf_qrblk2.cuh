@@ -374,8 +374,8 @@ __global__ void __launch_bounds__(32 * (QR2_NB / CPW), CPW == 4 ? 2 : 1) k_qrp_r
 // k_apply_q2: X <- Q^T X (MODE 0: panels forward with T^T; ZUNMQR 'L','C') or X <- Q X (MODE 1: panels backward with T;
 // ZUNMQR 'L','N'; with X = 1 this is ZUNGQR).  grid = (column groups of cols_per_cta, batch), 256 threads, two CTAs per SM.
 // ------------------------------------------------------------------------------------------------------------------------
-template <int MODE, int IDENT>
-__global__ void __launch_bounds__(256, 2) k_apply_q2(const double* __restrict__ QR, int m, int n, int ld, long sQ, const double* __restrict__ Tbuf, long sT,
+template <int MODE, int IDENT, int NTHR>      // NTHR = 256: two CTAs per SM (m <= 288); 512: one CTA per SM for taller matrices
+__global__ void __launch_bounds__(NTHR, NTHR == 256 ? 2 : 1) k_apply_q2(const double* __restrict__ QR, int m, int n, int ld, long sQ, const double* __restrict__ Tbuf, long sT,
                                                   double* __restrict__ X, int ldx, long sX, int ncols, int cols_per_cta) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int NB = QR2_NB, LDW = QR2_LDW;

@@ -148,6 +148,15 @@ class Model:
     Op_T: List[List[Operator]]          # Op_T[nc][nf]
     latt: Optional[Lattice] = None
     params: dict = field(default_factory=dict)
+    # projective algorithm (Prog/Hamiltonian_main_mod.F90:181-197: Projector, Thtrot, WF_L, WF_R); Ltrot already includes 2*Thtrot
+    Projector: bool = False
+    Thtrot: int = 0
+    WF_L: Optional[List[np.ndarray]] = None     # per flavor, (Ndim, N_part) complex
+    WF_R: Optional[List[np.ndarray]] = None
+
+    @property
+    def N_part(self):
+        return 0 if not self.Projector else int(self.WF_L[0].shape[1])
 
     @property
     def n_opv(self):
@@ -184,13 +193,47 @@ def _square_hopping_families(latt: Lattice, symm: bool):
     return [(fam[k], props[i]) for i, k in enumerate(order)]
 
 
+def trial_wave_function_square(latt: Lattice, n_part: int, N_FL: int, kind: str = "flux", t: float = 1.0):
+    """Predefined_TrialWaveFunction for the square lattice (Prog/Predefined_Trial_mod.F90:112-398): the N_part lowest
+    single-particle states of a non-interacting H0 whose degeneracy at the Fermi level is lifted.
+    kind = "flux": ALF's choice, a twist Phi_X = 0.01 of the boundary condition along L1 (complex orbitals);
+    kind = "dimer": a real alternative (bond dimerisation delta = 0.01 along L1) that keeps the sweep in real arithmetic.
+    Returns (WF_L, WF_R, degeneracy gap E(N_part+1) - E(N_part))."""
+    N = latt.N
+    H = np.zeros((N, N), dtype=np.complex128)
+    for I in range(1, N + 1):
+        i1, i2 = latt.list[I - 1]
+        for (n1, n2) in ((0, 1), (1, 0)):
+            J = latt.nnlist(I, n1, n2)
+            amp = -t
+            if n1 == 1:
+                if kind == "flux":
+                    amp = -t * np.exp(2j * np.pi * 0.01 / latt.L1)
+                elif kind == "dimer":
+                    amp = -t * (1.0 + 0.01 * (-1) ** (i1 % 2))
+            H[I - 1, J - 1] += amp
+            H[J - 1, I - 1] += np.conj(amp)
+    E, Uv = np.linalg.eigh(H)
+    P = np.asfortranarray(Uv[:, :n_part])
+    if kind == "dimer":
+        P = np.asfortranarray(P.real.astype(np.complex128))
+    return [P.copy(order="F") for _ in range(N_FL)], [P.copy(order="F") for _ in range(N_FL)], float(E[n_part] - E[n_part - 1])
+
+
 def hubbard_square(L1: int, L2: int, beta: float, dtau: float = 0.1, U: float = 4.0, t: float = 1.0, mu: float = 0.0,
-                   Mz: bool = True, checkerboard: bool = True, symm: bool = True, N_SUN: int = 2) -> Model:
+                   Mz: bool = True, checkerboard: bool = True, symm: bool = True, N_SUN: int = 2,
+                   projector: bool = False, theta: float = 10.0, trial: str = "flux") -> Model:
     """Hubbard model on the square lattice as set up by Hamiltonian_Hubbard_smod.F90 (Ham_Set :207-330,
-    Ham_Hop, Ham_V :477-542) with the shipped defaults (Scripts_and_Parameters_files/Start/parameters)."""
+    Ham_Hop, Ham_V :477-542) with the shipped defaults (Scripts_and_Parameters_files/Start/parameters).
+    projector=True: the projective algorithm (:236-239 Thtrot = nint(theta/dtau), Ltrot += 2 Thtrot; Ham_Trial :455-470,
+    N_part = Ndim/2)."""
     latt = Lattice(L1, L2)
     Ndim = latt.N
     Ltrot = int(round(beta / dtau))
+    Thtrot = 0
+    if projector:
+        Thtrot = int(round(theta / dtau))
+        Ltrot = Ltrot + 2 * Thtrot
     N_FL = 2 if Mz else 1
     n_sun = N_SUN // 2 if N_FL == 2 else N_SUN
     # bonds: (no_I, no_J, n_1, n_2) ; List(1) = (1,1,0,1), List(2) = (1,1,1,0) ; T = -t ; T_loc = -mu
@@ -258,9 +301,14 @@ def hubbard_square(L1: int, L2: int, beta: float, dtau: float = 0.1, U: float = 
                 op.type = 2
                 Op_set(op)
                 Op_V.append([op])
-    return Model(name="Hubbard", Ndim=Ndim, N_FL=N_FL, N_SUN=n_sun, Ltrot=Ltrot, Dtau=dtau, Symm=bool(symm and checkerboard),
-                 Op_V=Op_V, Op_T=Op_T, latt=latt,
-                 params=dict(L1=L1, L2=L2, beta=beta, dtau=dtau, U=U, t=t, mu=mu, Mz=Mz, checkerboard=checkerboard, symm=symm))
+    m = Model(name="Hubbard", Ndim=Ndim, N_FL=N_FL, N_SUN=n_sun, Ltrot=Ltrot, Dtau=dtau, Symm=bool(symm and checkerboard),
+              Op_V=Op_V, Op_T=Op_T, latt=latt,
+              params=dict(L1=L1, L2=L2, beta=beta, dtau=dtau, U=U, t=t, mu=mu, Mz=Mz, checkerboard=checkerboard, symm=symm,
+                          projector=projector, theta=theta, trial=trial))
+    if projector:
+        m.Projector, m.Thtrot = True, Thtrot
+        m.WF_L, m.WF_R, m.params["wf_degen"] = trial_wave_function_square(latt, Ndim // 2, N_FL, trial, t)
+    return m
 
 
 def hubbard_chain(L: int, beta: float, dtau: float, U: float = 4.0, t: float = 1.0, Mz: bool = True, symm: bool = True) -> Model:

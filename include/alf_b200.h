@@ -51,6 +51,12 @@ int alf_b200_set_op_v(alf_b200_handle* h, int n, int nf, int N, int n_non_zero, 
                       const double* U, const double* E, double g_re, double g_im, double alpha_re, double alpha_im);
 int alf_b200_set_op_t(alf_b200_handle* h, int nc, int nf, int N, int diag, const int* P, const double* U, const double* E,
                       double g_re, double g_im);
+/* Projective algorithm (Projector = .T.): Thtrot and N_part, then WF_L(nf)%P / WF_R(nf)%P (Ndim x N_part, column-major
+ * complex) per flavor -- the public module variables read by Prog/main.F90:366-376,596-599.  Call before finalize_model;
+ * UDV_State then carries U(Ndim, N_part) without V (Prog/udv_state_mod.F90:131-150), CGR dispatches to CGRP
+ * (Prog/cgr1_mod.F90:207-211, 464-515) and the sweep calls Tau_p instead of TAU_M (Prog/main.F90:829-831, 884-886). */
+int alf_b200_set_projector(alf_b200_handle* h, int thtrot, int n_part);
+int alf_b200_set_trial_wf(alf_b200_handle* h, int nf, const double* P_L, const double* P_R);
 int alf_b200_finalize_model(alf_b200_handle* h);
 int alf_b200_is_complex(const alf_b200_handle* h);   /* 1 if the complex instantiation was selected */
 
@@ -78,6 +84,7 @@ int alf_b200_wrapul(alf_b200_handle* h, int ntau1, int ntau); /* Prog/wrapul_mod
 int alf_b200_udv_reset(alf_b200_handle* h, int which /*0 udvl,1 udvr*/, char side);   /* udv_state_mod.F90:224 */
 int alf_b200_cgr(alf_b200_handle* h, int nvar);               /* Prog/cgr1_mod.F90:36: GR, Phase from udvr, udvl */
 int alf_b200_tau_m(alf_b200_handle* h);                       /* Prog/tau_m_mod.F90:56 */
+int alf_b200_tau_p(alf_b200_handle* h, int nst_in);           /* Prog/tau_p_mod.F90:74 (projector; udvr, udvst, GR as in main.F90:829) */
 
 /* ---- results */
 int alf_b200_get_green(alf_b200_handle* h, int chain, int nf, int symmetrize, double* out /* complex N*N */);
@@ -117,6 +124,8 @@ int alf_b200_test_cgr(int device, int is_complex, int n, int batch, int nvar, in
                       const double* detUL, double* G, double* phase);
 /* CGR2_2 (Prog/cgr2_2_mod.F90:196): udv2 = right (side R), udv1 = left (side L) propagation; out4 = GRT0, GR00, GRTT, GR0T,
  * each complex n*n*batch */
+/* CGRP (Prog/cgr1_mod.F90:464) on explicit U_R, U_L (n x n_part each): G (n x n) and the phase of det(U_L^H U_R) */
+int alf_b200_test_cgrp(int device, int is_complex, int n, int n_part, int batch, const double* UR, const double* UL, double* G, double* phase);
 int alf_b200_test_cgr2_2(int device, int is_complex, int n, int batch, int stab, const double* U2, const double* D2, const double* V2,
                          const double* U1, const double* D1, const double* V1, double* out4);
 int alf_b200_test_gemm(int device, int is_complex, int ta, int tb, int m, int n, int k, int batch, const double* A,

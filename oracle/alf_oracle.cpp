@@ -246,10 +246,17 @@ void expopt_init(ExpOpT& e, const Op& op) {
 struct UDV {  // Prog/udv_state_mod.F90:85-110
   int ndim = 0, npart = 0; char side = 'r'; bool hasV = true;
   std::vector<cd> U, V, D;
-  void alloc(int n) { ndim = n; npart = n; U.assign((size_t)n * n, 0); V.assign((size_t)n * n, 0); D.assign(n, 0); }
+  void alloc(int n) { ndim = n; npart = n; hasV = true; U.assign((size_t)n * n, 0); V.assign((size_t)n * n, 0); D.assign(n, 0); }
+  void alloc(int n, int n_part) {  // projector: U(ndim, N_part), no V (udv_state_mod.F90:131-150)
+    ndim = n; npart = n_part; hasV = false; U.assign((size_t)n * n_part, 0); V.clear(); D.assign(n_part, 0);
+  }
   void reset(char s) {  // udv_state_mod.F90:224-249
     side = s; std::fill(U.begin(), U.end(), cd(0)); std::fill(V.begin(), V.end(), cd(0));
     for (int i = 0; i < ndim; ++i) { U[i + (size_t)i * ndim] = 1; V[i + (size_t)i * ndim] = 1; D[i] = 1; }
+  }
+  void reset(char s, const std::vector<cd>& P, int n_part) {  // udv_state_mod.F90:320-345 with a trial wave function
+    if ((int)P.size() != ndim * n_part || npart != n_part || hasV) alloc(ndim, n_part);
+    side = s; U = P; for (int i = 0; i < npart; ++i) D[i] = 1;
   }
 };
 
@@ -315,7 +322,9 @@ void inv_c(const std::vector<cd>& A, std::vector<cd>& Ainv, int N) {  // mymats_
 
 // Prog/cgr1_mod.F90:176-447.  stab3 = false: default branch (:223-236); stab3 = true: the
 // scale-separated STAB3 branch (:238-268, :353-362, :386-394, :401-409, :434-441).
+void cgrp(cd& phase, cd* GRUP, const UDV& udvr, const UDV& udvl);
 void cgr(cd& PHASE, int NVAR, cd* GRUP, const UDV& udvr, const UDV& udvl, bool stab3) {
+  if (!udvl.hasV) { cgrp(PHASE, GRUP, udvr, udvl); return; }      // cgr1_mod.F90:207-211
   int N = udvl.ndim; cd alpha = 1, beta = 0;
   std::vector<cd> TPUP((size_t)N * N), RHS((size_t)N * N), DUP(N), TAU(N), WORK; std::vector<int> IPVT(N, 0);
   int LWORK = 0, info;
@@ -384,6 +393,24 @@ void cgr(cd& PHASE, int NVAR, cd* GRUP, const UDV& udvr, const UDV& udvl, bool s
 }
 
 // Prog/cgr2_2_mod.F90:55-72 (get_blocks), :155-191 (solve_extended_System), :318-425 (CGR2_2)
+// Prog/cgr1_mod.F90:464-515 : projector Green function  G = 1 - U_R (U_L^H U_R)^-1 U_L^H  and the phase of det(U_L^H U_R)
+void cgrp(cd& phase, cd* GRUP, const UDV& udvr, const UDV& udvl) {
+  int Ndim = udvl.ndim, N_part = udvl.npart, info; cd alpha = 1, beta = 0;
+  std::vector<cd> sMat((size_t)N_part * N_part), rMat((size_t)N_part * Ndim); std::vector<int> ipiv(N_part);
+  scipy_zgemm_("C", "N", &N_part, &N_part, &Ndim, &alpha, const_cast<cd*>(udvl.U.data()), &Ndim, const_cast<cd*>(udvr.U.data()), &Ndim, &beta, sMat.data(), &N_part);
+  scipy_zgetrf_(&N_part, &N_part, sMat.data(), &N_part, ipiv.data(), &info);
+  phase = 1;
+  for (int n = 0; n < N_part; ++n) {
+    cd d = sMat[n + (size_t)n * N_part];
+    if (ipiv[n] != n + 1) phase = -phase * d / std::abs(d); else phase = phase * d / std::abs(d);
+  }
+  for (int j = 0; j < Ndim; ++j) for (int i = 0; i < N_part; ++i) rMat[i + (size_t)j * N_part] = std::conj(udvl.U[j + (size_t)i * Ndim]);
+  scipy_zgetrs_("N", &N_part, &Ndim, sMat.data(), &N_part, ipiv.data(), rMat.data(), &N_part, &info);
+  alpha = -1;
+  scipy_zgemm_("N", "N", &Ndim, &Ndim, &N_part, &alpha, const_cast<cd*>(udvr.U.data()), &Ndim, rMat.data(), &N_part, &beta, GRUP, &Ndim);
+  for (int n = 0; n < Ndim; ++n) GRUP[n + (size_t)n * Ndim] += cd(1, 0);
+}
+
 void get_blocks(cd* A, cd* B, cd* C, cd* D, const cd* INP, int LQ) {
   int L2 = 2 * LQ;
   for (int I = 0; I < LQ; ++I) for (int J = 0; J < LQ; ++J) {
@@ -475,6 +502,10 @@ struct Oracle {
   std::vector<cd> taum_buf; int taum_capture = 0;       // [nt][which(GT0,G0T,G00,GTT)][nf][N*N]
   // equal-time capture (G handed to ham%Obser)
   bool propose_s0 = false;
+  // projective algorithm (Prog/main.F90:366-376, Hamiltonian_main_mod.F90:181-197): trial wave functions and Thtrot
+  bool projector = false; int thtrot = 0, n_part = 0; std::vector<std::vector<cd>> WF_L, WF_R;
+  void reset_udv(UDV& u, char side, int nf) { if (projector) u.reset(side, side == 'l' ? WF_L[nf] : WF_R[nf], n_part); else u.reset(side); }
+  int wcols(const UDV& u) const { return u.npart; }
 
   cd& fld(int n, int nt) { return f[n + (size_t)n_opv * (nt - 1)]; }
   Op& OpV(int n, int nf) { return opv[n + (size_t)n_opv * nf]; }
@@ -572,8 +603,8 @@ struct Oracle {
   void wrapur(int NTAU, int NTAU1, std::vector<UDV>& udv) {
     for (int nf = 0; nf < n_fl; ++nf) {
       for (int NT = NTAU + 1; NT <= NTAU1; ++NT) {
-        mmthr(udv[nf].U.data(), ndim, ndim, nf);
-        for (int n = 0; n < n_opv; ++n) op_mmultR(udv[nf].U.data(), ndim, ndim, OpV(n, nf), fld(n, NT), 'n');
+        mmthr(udv[nf].U.data(), ndim, udv[nf].npart, nf);
+        for (int n = 0; n < n_opv; ++n) op_mmultR(udv[nf].U.data(), ndim, udv[nf].npart, OpV(n, nf), fld(n, NT), 'n');
       }
       udv_decompose(udv[nf]);
     }
@@ -582,8 +613,8 @@ struct Oracle {
   void wrapul(int NTAU1, int NTAU, std::vector<UDV>& udv) {
     for (int nf = 0; nf < n_fl; ++nf) {
       for (int NT = NTAU1; NT >= NTAU + 1; --NT) {
-        for (int n = n_opv - 1; n >= 0; --n) op_mmultR(udv[nf].U.data(), ndim, ndim, OpV(n, nf), fld(n, NT), 'c');
-        mmthlc(udv[nf].U.data(), ndim, ndim, nf);
+        for (int n = n_opv - 1; n >= 0; --n) op_mmultR(udv[nf].U.data(), ndim, udv[nf].npart, OpV(n, nf), fld(n, NT), 'c');
+        mmthlc(udv[nf].U.data(), ndim, udv[nf].npart, nf);
       }
       udv_decompose(udv[nf]);
     }
@@ -724,7 +755,8 @@ struct Oracle {
     udvl.assign(n_fl, UDV()); udvr.assign(n_fl, UDV()); udvst.assign((size_t)nstm * n_fl, UDV());
     for (int nf = 0; nf < n_fl; ++nf) {
       for (int n = 1; n <= nstm; ++n) st(n, nf).alloc(ndim);
-      udvl[nf].alloc(ndim); udvl[nf].reset('l'); udvr[nf].alloc(ndim); udvr[nf].reset('r'); st(nstm, nf).reset('l');
+      udvl[nf].alloc(ndim); udvr[nf].alloc(ndim);
+      reset_udv(udvl[nf], 'l', nf); reset_udv(udvr[nf], 'r', nf); reset_udv(st(nstm, nf), 'l', nf);
     }
     for (int NST = nstm - 1; NST >= 1; --NST) {
       wrapul(stab_nt[NST + 1], stab_nt[NST], udvl);
@@ -764,10 +796,10 @@ struct Oracle {
 
   // ---- Prog/main.F90:714-887 : one sequential sweep, cut into its 2*NSTM (+NSTM with TAU_M) stabilisation intervals so that
   // the CPU baseline of bench.py can time a bounded sample (sweep() = all segments in order, nothing else).
-  int n_segments(int ltau) const { return 2 * nstm + (ltau == 1 ? nstm : 0); }
+  int n_segments(int ltau) const { return 2 * nstm + ((ltau == 1 && !projector) ? nstm : 0); }
   void sweep_segment(int idx, int ltau) {
     if (idx < nstm) {                                   // up sweep, main.F90:727-774
-      if (idx == 0) for (int nf = 0; nf < n_fl; ++nf) udvr[nf].reset('r');
+      if (idx == 0) for (int nf = 0; nf < n_fl; ++nf) reset_udv(udvr[nf], 'r', nf);
       const int NST = idx + 1;
       for (int NTAU = stab_nt[NST - 1]; NTAU <= stab_nt[NST] - 1; ++NTAU) {
         int NTAU1 = NTAU + 1;
@@ -777,25 +809,30 @@ struct Oracle {
       }
     } else if (idx < 2 * nstm) {                        // down sweep, main.F90:786-834, and the slice-0 recompute :836-872
       const int d = idx - nstm, hi = nstm - d;
-      if (d == 0) for (int nf = 0; nf < n_fl; ++nf) udvl[nf].reset('l');
+      if (d == 0) for (int nf = 0; nf < n_fl; ++nf) reset_udv(udvl[nf], 'l', nf);
       for (int NTAU = stab_nt[hi]; NTAU >= stab_nt[hi - 1] + 1; --NTAU) {
         int NTAU1 = NTAU - 1;
         wrapgrdo(NTAU);
         obser_hook(NTAU1);
-        if (hi - 1 >= 1 && stab_nt[hi - 1] == NTAU1) { wrapul(stab_nt[hi], NTAU1, udvl); stabilise(NTAU1, hi - 1, false); }
+        if (hi - 1 >= 1 && stab_nt[hi - 1] == NTAU1) {
+          wrapul(stab_nt[hi], NTAU1, udvl); stabilise(NTAU1, hi - 1, false);
+          const int NST = hi - 1;     // main.F90:829-831
+          if (ltau == 1 && projector && stab_nt[NST] <= thtrot + 1 && thtrot + 1 < stab_nt[NST + 1]) tau_p(NST);
+        }
       }
       if (hi == 1) {
         wrapul(stab_nt[1], stab_nt[0], udvl);
-        for (int nf = 0; nf < n_fl; ++nf) udvr[nf].reset('r');
+        for (int nf = 0; nf < n_fl; ++nf) reset_udv(udvr[nf], 'r', nf);
         cd ph = 1; std::vector<cd> Test((size_t)ndim * ndim);
         for (int nf = 0; nf < n_fl; ++nf) {
           Test = GR[nf]; cd Z1; cgr(Z1, 1, GR[nf].data(), udvr[nf], udvl[nf], stab3);
           control_precisionG(GR[nf].data(), Test.data()); op_phase(Z1, nf); ph *= Z1;
         }
         cd Z = std::pow(ph, n_sun); double X = std::abs(Z - Phase); if (X > ctl.XMAXP) ctl.XMAXP = X; Phase = Z;
-        for (int nf = 0; nf < n_fl; ++nf) st(nstm, nf).reset('l');
+        for (int nf = 0; nf < n_fl; ++nf) reset_udv(st(nstm, nf), 'l', nf);
+        if (ltau == 1 && projector && stab_nt[1] > thtrot + 1) tau_p(0);      // main.F90:884-886
       }
-    } else if (ltau == 1) tau_m_segment(idx - 2 * nstm);
+    } else if (ltau == 1 && !projector) tau_m_segment(idx - 2 * nstm);
   }
   void sweep(int ltau) { for (int i = 0; i < n_segments(ltau); ++i) sweep_segment(i, ltau); }
 
@@ -853,6 +890,52 @@ struct Oracle {
     }
   }
   void tau_m() { for (int t = 0; t < nstm; ++t) tau_m_segment(t); }
+
+  // ---- Prog/tau_p_mod.F90:74-336 (sequential update path; the Langevin/HMC branches are out of scope)
+  void tau_p(int NST_IN) {
+    const size_t n2 = (size_t)ndim * ndim;
+    std::vector<UDV> udvr_local = udvr;
+    std::vector<std::vector<cd>> GTT = GR, GRUP(n_fl, std::vector<cd>(n2)), GRUPB, G00, G0T, GT0; std::vector<cd> TEMP(n2);
+    int NT_ST = NST_IN; cd DetZ; cd one = 1, zero = 0; int N = ndim;
+    auto restab = [&]() {
+      wrapur(stab_nt[NT_ST], stab_nt[NT_ST + 1], udvr_local);
+      for (int nf = 0; nf < n_fl; ++nf) cgrp(DetZ, GRUP[nf].data(), udvr_local[nf], st(NT_ST + 1, nf));
+      for (int nf = 0; nf < n_fl; ++nf) control_precision_tau(GTT[nf].data(), GRUP[nf].data());
+    };
+    for (int NT = stab_nt[NT_ST] + 1; NT <= thtrot + 1; ++NT) {
+      proprm1(GTT, NT); propr(GTT, NT);
+      if (NT_ST + 1 <= nstm && NT == stab_nt[NT_ST + 1]) { restab(); GTT = GRUP; NT_ST++; }
+    }
+    GRUPB = GTT;
+    for (int nf = 0; nf < n_fl; ++nf) for (int I = 0; I < ndim; ++I) GRUPB[nf][I + (size_t)I * ndim] -= 1.0;
+    G00 = GTT; GT0 = GTT; G0T = GRUPB;
+    obsert_hook(0, GT0, G0T, G00, GTT);
+    int NCHECK = 0;
+    for (int NT = thtrot + 1; NT <= ltrot - thtrot; ++NT) {
+      const int NTAU = NT - thtrot - 1;
+      if (NT_ST + 1 <= nstm && NT == stab_nt[NT_ST + 1] && NTAU != 0) {
+        restab(); NT_ST++; NCHECK++;
+        GTT = GRUP;
+        for (int nf = 0; nf < n_fl; ++nf) {
+          GRUPB[nf] = GRUP[nf]; for (auto& z : GRUPB[nf]) z = -z;
+          for (int I = 0; I < ndim; ++I) GRUPB[nf][I + (size_t)I * ndim] += 1.0;
+          scipy_zgemm_("N", "N", &N, &N, &N, &one, GRUP[nf].data(), &N, GT0[nf].data(), &N, &zero, TEMP.data(), &N); GT0[nf] = TEMP;
+          scipy_zgemm_("N", "N", &N, &N, &N, &one, G0T[nf].data(), &N, GRUPB[nf].data(), &N, &zero, TEMP.data(), &N); G0T[nf] = TEMP;
+        }
+        if (taum_capture) {   // test support: the freshly recomputed G(tau,tau) and the re-anchored G(tau,0), G(0,tau)
+          std::vector<std::vector<cd>>* arr[4] = {&GT0, &G0T, &G00, &GTT};
+          for (int w = 0; w < 4; ++w) for (int nf = 0; nf < n_fl; ++nf) taum_fresh.insert(taum_fresh.end(), (*arr[w])[nf].begin(), (*arr[w])[nf].end());
+        }
+      }
+      const int NT1 = NT + 1;
+      propr(GT0, NT1); proprm1(G0T, NT1); proprm1(GTT, NT1); propr(GTT, NT1);
+      obsert_hook(NTAU + 1, GT0, G0T, G00, GTT);
+    }
+    if (NCHECK == 0 && NT_ST + 1 <= nstm) {
+      for (int NT = ltrot - thtrot + 2; NT <= stab_nt[NT_ST + 1]; ++NT) { proprm1(GTT, NT); propr(GTT, NT); }
+      restab(); NT_ST++;
+    }
+  }
 };
 
 }  // namespace
@@ -872,6 +955,20 @@ void* orc_create(int ndim, int n_fl, int n_sun, int ltrot, int nwrap, int n_opv,
   return o;
 }
 void orc_destroy(void* h) { delete (Oracle*)h; }
+// projective algorithm: Thtrot and the trial wave functions P_L, P_R (Ndim x N_part, column-major complex) of flavor nf (1-based)
+void orc_set_projector(void* h, int thtrot, int n_part) {
+  Oracle* o = (Oracle*)h; o->projector = true; o->thtrot = thtrot; o->n_part = n_part;
+  o->WF_L.assign(o->n_fl, std::vector<cd>((size_t)o->ndim * n_part)); o->WF_R = o->WF_L;
+}
+void orc_set_trial_wf(void* h, int nf, const double* PL, const double* PR) {
+  Oracle* o = (Oracle*)h; size_t n = (size_t)o->ndim * o->n_part;
+  for (size_t i = 0; i < n; ++i) { o->WF_L[nf - 1][i] = cd(PL[2 * i], PL[2 * i + 1]); o->WF_R[nf - 1][i] = cd(PR[2 * i], PR[2 * i + 1]); }
+}
+void orc_cgrp(int ndim, int n_part, const double* UR, const double* UL, double* G, double* phase) {
+  UDV r, l; r.alloc(ndim, n_part); l.alloc(ndim, n_part); r.side = 'r'; l.side = 'l';
+  std::memcpy(r.U.data(), UR, sizeof(cd) * (size_t)ndim * n_part); std::memcpy(l.U.data(), UL, sizeof(cd) * (size_t)ndim * n_part);
+  cd ph; cgrp(ph, reinterpret_cast<cd*>(G), r, l); phase[0] = ph.real(); phase[1] = ph.imag();
+}
 
 static void fill_op(Op& op, int N, int nnz, int diag, int type, const int* P, const double* U, const double* E,
                     double g_re, double g_im, double a_re, double a_im) {

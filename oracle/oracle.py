@@ -67,6 +67,11 @@ class Oracle:
             L.orc_set_op_t(self.h, o["nc"], o["nf"], o["N"], o["diag"], o["P"].ctypes.data_as(_ip), _d(o["U"]), _d(o["E"]),
                            C.c_double(o["g"].real), C.c_double(o["g"].imag))
 
+        if getattr(model, "Projector", False):
+            L.orc_set_projector(self.h, int(model.Thtrot), int(model.N_part))
+            for nf in range(model.N_FL):
+                L.orc_set_trial_wf(self.h, nf + 1, _d(_cplx(model.WF_L[nf])), _d(_cplx(model.WF_R[nf])))
+
     def __del__(self):
         try:
             lib().orc_destroy(self.h)
@@ -254,3 +259,11 @@ def cgr2_2(U2, D2, V2, U1, D1, V1, stab3=False):
     d2 = np.ascontiguousarray(D2, dtype=np.complex128); d1 = np.ascontiguousarray(D1, dtype=np.complex128)
     lib().orc_cgr2_2(n, int(stab3), _d(a[0]), _d(d2), _d(a[1]), _d(a[2]), _d(d1), _d(a[3]), *[_d(o) for o in outs])
     return dict(GRT0=outs[0], GR00=outs[1], GRTT=outs[2], GR0T=outs[3])
+
+
+def cgrp(UR, UL):
+    """CGRP (Prog/cgr1_mod.F90:464-515) on explicit N x N_part matrices; returns (G, phase)."""
+    UR = _cplx(UR); UL = _cplx(UL); n, npart = UR.shape
+    G = np.zeros((n, n), dtype=np.complex128, order="F"); ph = np.zeros(2)
+    lib().orc_cgrp(int(n), int(npart), _d(UR), _d(UL), _d(G), _d(ph))
+    return G, complex(ph[0], ph[1])

@@ -325,3 +325,94 @@ def test_qdrp_blocked_reconstruct(is_complex, n):
         sign = np.linalg.det(np.eye(n)[:, jp[b] - 1])
         assert abs(sign - ph[b, 0]) < 1e-12
         assert abs(np.linalg.det(Q[b]) - complex(ph[b, 3], ph[b, 4])) < 1e-8
+
+
+# ---------------------------------------------------------------------------------- projective algorithm (CGRP, Tau_p)
+@pytest.mark.gpu
+@pytest.mark.parametrize("is_complex", [False, True])
+@pytest.mark.parametrize("n,npart", [(5, 2), (16, 8), (64, 32), (256, 128)])
+def test_cgrp_kernel(is_complex, n, npart):
+    """CGRP on the device (QR-based inverse instead of LU) against the oracle's ZGETRF/ZGETRS restatement (testsuite 23-cgrp)."""
+    from oracle.oracle import cgrp
+    rng = np.random.default_rng(1000 + n)
+    UR = rng.normal(size=(2, n, npart)); UL = rng.normal(size=(2, n, npart))
+    if is_complex:
+        UR = UR + 1j * rng.normal(size=UR.shape); UL = UL + 1j * rng.normal(size=UL.shape)
+    UR = np.linalg.qr(UR)[0]; UL = np.linalg.qr(UL)[0]       # column-orthonormal, as decompose leaves them
+    G, ph = api.test_cgrp(UR, UL, is_complex)
+    for b in range(2):
+        Go, pho = cgrp(UR[b], UL[b])
+        assert relF(G[b], Go) < TOL_G
+        assert abs(ph[b] - pho) < 1e-9
+
+
+def _run_projector(model, seeds, nwrap, ltau):
+    C = len(seeds)
+    g = AlfB200(model, n_chains=C, nwrap=nwrap); g.set_seeds(seeds); g.fields_set()
+    orcs = []
+    for s in seeds:
+        o = Oracle(model, nwrap=nwrap); o.ranset(s); o.fields_set(); orcs.append(o)
+    g.init_sweep()
+    for o in orcs:
+        o.init()
+    ph = g.phase()
+    for c, o in enumerate(orcs):
+        for nf in range(1, model.N_FL + 1):
+            assert relF(g.green(c, nf), o.green(nf)) < TOL_G, ("init", c, nf)
+        assert abs(ph[c] - o.phase()) < 1e-9
+    g.accept_log(1)
+    if ltau:
+        g.taum_capture(1)
+    for o in orcs:
+        o.log(True)
+        if ltau:
+            o.taum_capture(1)
+    g.sweep(1, ltau)
+    for o in orcs:
+        o.sweep(ltau)
+    log = g.get_accept_log(); f = g.get_fields(); ph = g.phase()
+    for c, o in enumerate(orcs):
+        acc, _ = o.get_log()
+        assert np.array_equal(acc, log[c]), f"chain {c}: accept/reject sequence differs"
+        assert np.array_equal(f[c], o.get_fields())
+        for nf in range(1, model.N_FL + 1):
+            assert relF(g.green(c, nf), o.green(nf)) < TOL_G, ("sweep", c, nf)
+        assert abs(ph[c] - o.phase()) < 1e-9
+        if ltau:
+            a, b = g.get_taum(c), o.taum_get()
+            assert a.shape == b.shape and a.shape[0] == model.Ltrot - 2 * model.Thtrot + 1
+            assert relF(a, b) < 1e-8                      # propagated (wrapped) time-displaced blocks handed to ObserT
+            af, bf = g.get_taum_fresh(c), o.taum_fresh_get()
+            assert af.shape == bf.shape
+            if af.size:
+                assert relF(af[:, 3], bf[:, 3]) < TOL_G   # G(tau,tau) freshly recomputed by CGRP
+                assert relF(af, bf) < 1e-8
+    cg = g.control()
+    assert cg["XMAXG"] < 1e-6 and cg["nan"] == 0 and cg["unstable"] == 0
+    if ltau:
+        assert cg["NCG_tau"] == sum(o.control()["NCG_tau"] for o in orcs) and cg["XMAX_tau"] < 1e-6
+    g.close()
+
+
+@pytest.mark.gpu
+def test_projector_sweep_complex_trial():
+    """Hubbard 4x4, projective algorithm with ALF's flux-twisted trial wave function (complex arithmetic)."""
+    _run_projector(hubbard_square(4, 4, 1.0, 0.1, 4.0, projector=True, theta=0.5), SEEDS[:2], nwrap=5, ltau=0)
+
+
+@pytest.mark.gpu
+def test_projector_sweep_real_trial_taup():
+    """Real trial wave function (real instantiation), Tau_p called inside the down sweep (Stab_nt(NST) <= Thtrot+1 < Stab_nt(NST+1))."""
+    _run_projector(hubbard_square(4, 4, 1.0, 0.1, 4.0, projector=True, theta=0.6, trial="dimer"), SEEDS[:2], nwrap=4, ltau=1)
+
+
+@pytest.mark.gpu
+def test_projector_taup_after_sweep_complex():
+    """Nwrap > Thtrot+1: Tau_p runs after the sweep with NST_IN = 0 (main.F90:884-886); SU(2) flavor-symmetric model, complex."""
+    _run_projector(hubbard_square(4, 4, 0.8, 0.1, 4.0, Mz=False, projector=True, theta=0.3), SEEDS[:2], nwrap=6, ltau=1)
+
+
+@pytest.mark.gpu
+def test_projector_config_like_8x8():
+    """8x8 Hubbard projector (N_dim = 64, N_part = 32), the size class of BASELINE configs[4]'s projective runs."""
+    _run_projector(hubbard_square(8, 8, 1.0, 0.1, 4.0, projector=True, theta=1.0, trial="dimer"), SEEDS[:2], nwrap=10, ltau=1)

@@ -253,3 +253,47 @@ def test_cabi_library_exports_all_symbols():
     import torch
     if not torch.cuda.is_available():
         assert lib.alf_b200_create(ctypes.byref(h), 16, 2, 1, 50, 10, 16, 56, 1, 0, 4, 0) == 100
+
+
+# ---------------------------------------------------------------------------------- projective algorithm (CGRP, Tau_p)
+def test_cgrp_vs_direct():
+    """CGRP (Prog/cgr1_mod.F90:464-515): G = 1 - U_R (U_L^H U_R)^-1 U_L^H and the phase of det(U_L^H U_R); inputs in the
+    spirit of testsuite/Prog.tests/23-cgrp.F90 (N = 5) plus a random complex case."""
+    from oracle.oracle import cgrp
+    rng = np.random.default_rng(23)
+    for n, npart in ((5, 2), (12, 6), (16, 16)):
+        UR = rng.normal(size=(n, npart)) + 1j * rng.normal(size=(n, npart))
+        UL = rng.normal(size=(n, npart)) + 1j * rng.normal(size=(n, npart))
+        G, ph = cgrp(UR, UL)
+        S = UL.conj().T @ UR
+        assert relF(G, np.eye(n) - UR @ np.linalg.solve(S, UL.conj().T)) < 1e-11
+        d = np.linalg.det(S)
+        assert abs(ph - d / abs(d)) < 1e-11
+
+
+@pytest.mark.parametrize("trial,Mz", [("flux", True), ("dimer", True), ("flux", False)])
+def test_projector_green_vs_bruteforce(trial, Mz):
+    """Projective sweep of the oracle against dense products: G(0) = 1 - P_R (P_L^H B_L..B_1 P_R)^-1 P_L^H B_L..B_1."""
+    m = hubbard_square(4, 4, 0.4, 0.1, 4.0, Mz=Mz, projector=True, theta=0.3, trial=trial)
+    assert m.Projector and m.Thtrot == 3 and m.Ltrot == 10 and m.N_part == 8
+    o = Oracle(m, nwrap=4); o.ranset(4711); o.fields_set(); f = o.get_fields(); o.init()
+
+    def Bmat(nf, nt):
+        B = np.eye(m.Ndim, dtype=complex)
+        for nc in range(m.n_opt - 1, -1, -1):
+            op = m.Op_T[nc][nf]; B = sl.expm(op.g * dense_op(op, m.Ndim)) @ B
+        for n in range(m.n_opv):
+            op = m.Op_V[n][nf]; B = sl.expm(op.g * phi(op, round(f[nt, n].real)) * dense_op(op, m.Ndim)) @ B
+        return B
+    for nf in range(m.N_FL):
+        Bt = np.eye(m.Ndim, dtype=complex)
+        for nt in range(m.Ltrot):
+            Bt = Bmat(nf, nt) @ Bt
+        PL, PR = m.WF_L[nf], m.WF_R[nf]
+        left = PL.conj().T @ Bt
+        G0 = np.eye(m.Ndim) - PR @ np.linalg.solve(left @ PR, left)
+        assert relF(o.green(nf + 1), G0) < 1e-10
+    # one sweep with Tau_p: wrapped and recomputed Green functions stay consistent (Control_PrecisionG / _tau)
+    o.sweep(1)
+    c = o.control()
+    assert c["XMAXG"] < 1e-8 and c["XMAX_tau"] < 1e-8 and c["NCG_tau"] > 0 and c["nan"] == 0
