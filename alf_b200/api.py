@@ -244,6 +244,11 @@ class AlfB200:
         self._ck(lib().alf_b200_get_kernel_stats(self.h, _d(ms), n.ctypes.data_as(C.POINTER(C.c_long))))
         return {k: (float(ms[i]), int(n[i])) for i, k in enumerate(self.KCATS)}
 
+    def kernel_flops(self):
+        fl = np.zeros(8)
+        self._ck(lib().alf_b200_get_kernel_flops(self.h, _d(fl)))
+        return {k: float(fl[i]) for i, k in enumerate(self.KCATS)}
+
     def hop_apply(self, which, nf, A):
         A = np.asfortranarray(A, dtype=np.complex128).copy(order="F")
         self._ck(lib().alf_b200_hop_apply(self.h, int(which), int(nf), _d(A)))

@@ -283,6 +283,9 @@ int alf_b200_get_kernel_stats(alf_b200_handle* h, double* ms, long* launches) {
   for (int c = 0; c < KC_COUNT; ++c) { if (ms) ms[c] = h->prof.ms[c]; if (launches) launches[c] = h->prof.launches[c]; }
   API_END(h)
 }
+int alf_b200_get_kernel_flops(alf_b200_handle* h, double* flops) {
+  API_BEGIN(h) for (int c = 0; c < KC_COUNT; ++c) flops[c] = h->prof.flops[c]; API_END(h)
+}
 int alf_b200_hop_apply(alf_b200_handle* h, int which, int nf, double* A) { API_BEGIN(h) NEED_FINAL(h) h->eng->hop_apply(which, nf, reinterpret_cast<cd*>(A)); API_END(h) }
 
 // ---- kernel-level test entry points and FP64 peak microbenchmark

@@ -21,6 +21,8 @@ enum { KC_UPDATE = 0, KC_OPS, KC_QRP, KC_FORMQ, KC_GEMM, KC_TRSM, KC_EW, KC_OBS,
 struct Prof {
   unsigned timing_mask = 0;                       // bit c set: record CUDA events around launches of category c
   long launches[KC_COUNT] = {0}; double ms[KC_COUNT] = {0};
+  double flops[KC_COUNT] = {0};                    // algorithmic FP64 flops of the dense kernels (real flops; a complex FMA counts 8)
+  void add_flops(int c, double f) { flops[c] += f; }
   struct Rec { int cat; cudaEvent_t a, b; };
   std::vector<Rec> recs; std::vector<cudaEvent_t> pool;
   cudaEvent_t get() { if (!pool.empty()) { cudaEvent_t e = pool.back(); pool.pop_back(); return e; } cudaEvent_t e; cudaEventCreate(&e); return e; }
@@ -28,7 +30,7 @@ struct Prof {
     for (auto& r : recs) { float t = 0.f; if (cudaEventElapsedTime(&t, r.a, r.b) == cudaSuccess) ms[r.cat] += t; pool.push_back(r.a); pool.push_back(r.b); }
     recs.clear();
   }
-  void reset() { collect(); for (int c = 0; c < KC_COUNT; ++c) { launches[c] = 0; ms[c] = 0.0; } }
+  void reset() { collect(); for (int c = 0; c < KC_COUNT; ++c) { launches[c] = 0; ms[c] = 0.0; flops[c] = 0.0; } }
   ~Prof() { collect(); for (auto e : pool) cudaEventDestroy(e); }
 };
 extern thread_local Prof* t_prof;     // defined in alf_b200.cu, set by every C-ABI entry point
@@ -42,6 +44,8 @@ struct KScope {
   ~KScope() { if (on) { cudaEventRecord(b, st); p->recs.push_back({cat, a, b}); } }
 };
 #define KL(CAT, ST, ...) do { KScope ks_(CAT, ST); __VA_ARGS__; CKL(); } while (0)
+template <typename T> static inline double flop_scale() { return std::is_same<T, double>::value ? 1.0 : 4.0; }
+static inline void count_flops(int cat, double f) { if (t_prof) t_prof->add_flops(cat, f); }
 
 static inline int ew_blocks(long n) { long b = (n + 255) / 256; return (int)(b > 2048 ? 2048 : (b < 1 ? 1 : b)); }
 
@@ -79,6 +83,7 @@ struct LaWork {
 template <typename T, int TA, int TB, int MASK>
 static void gemm(cudaStream_t st, int M, int N, int K, const T* A, int lda, long sA, const T* B, int ldb, long sB, T* C, int ldc, long sC, int batch) {
   dim3 grid(((M + GEMM_BM - 1) / GEMM_BM) * ((N + GEMM_BN - 1) / GEMM_BN), batch);
+  count_flops(KC_GEMM, flop_scale<T>() * 2.0 * M * N * K * batch * (MASK ? 0.5 : 1.0));
   KL(KC_GEMM, st, k_gemm<T, TA, TB, MASK><<<grid, 256, 0, st>>>(M, N, K, A, lda, sA, B, ldb, sB, C, ldc, sC));
 }
 
@@ -94,6 +99,7 @@ static void launch_qrp(cudaStream_t st, T* A, int m, int n, int ld, long sA, T* 
     CK(cudaFuncSetAttribute(k_qrp<T, MAXR, PIVOT, STG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
     k_qrp<T, MAXR, PIVOT, STG><<<batch, 512, smem, st>>>(A, m, n, ld, sA, tau, sTau, jpvt, sP, D, sD, out); } while (0)
 #define QRP_DISPATCH(MAXR) do { if (do_stage) QRP_LAUNCH(MAXR, 1); else QRP_LAUNCH(MAXR, 0); } while (0)
+  count_flops(KC_QRP, flop_scale<T>() * (2.0 * m * n * n - 2.0 * n * n * n / 3.0) * batch);
   { KScope ks_(KC_QRP, st);
   if (m <= 64) QRP_DISPATCH(2); else if (m <= 128) QRP_DISPATCH(4); else if (m <= 288) QRP_DISPATCH(9); else if (m <= 576) QRP_DISPATCH(18);
   else throw CudaError("k_qrp: matrices with more than 576 rows are not supported in this build");
@@ -112,6 +118,7 @@ static void launch_formq(cudaStream_t st, T* A, int m, int n, int ld, long sA, c
     CK(cudaFuncSetAttribute(k_formq<T, MAXR, STG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
     k_formq<T, MAXR, STG><<<batch, 512, smem, st>>>(A, m, n, ld, sA, tau, sTau, colscale); } while (0)
 #define FQ_DISPATCH(MAXR) do { if (do_stage) FQ_LAUNCH(MAXR, 1); else FQ_LAUNCH(MAXR, 0); } while (0)
+  count_flops(KC_FORMQ, flop_scale<T>() * (2.0 * m * n * n - 2.0 * n * n * n / 3.0) * batch);
   { KScope ks_(KC_FORMQ, st);
   if (m <= 64) FQ_DISPATCH(2); else if (m <= 128) FQ_DISPATCH(4); else if (m <= 288) FQ_DISPATCH(9); else if (m <= 576) FQ_DISPATCH(18);
   else throw CudaError("k_formq: matrices with more than 576 rows are not supported in this build");
@@ -125,6 +132,7 @@ template <int LOWER>
 static void launch_trsm_blk(cudaStream_t st, const double* R, int ldr, long sR, double* B, int ldb, long sB, int n, int nrhs, const double* dinv, long sD,
                             double* rinv, long sI, int batch) {
   const int np = (n + 31) & ~31, nb = np / 32;
+  count_flops(KC_TRSM, 1.0 * n * n * nrhs * batch);
   const size_t smem = sizeof(double) * (size_t)ld_pad(np) * TRSMB_CW;
   KL(KC_TRSM, st, k_tri_inv_blocks<LOWER><<<dim3(nb, batch), 32, 0, st>>>(R, ldr, sR, n, rinv, sI));
   CK(cudaFuncSetAttribute(k_trsm_blk<LOWER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -142,6 +150,7 @@ static void launch_trsm(cudaStream_t st, const T* R, int ldr, long sR, T* B, int
     }
   }
   dim3 grid((nrhs + TRSM_COLS - 1) / TRSM_COLS, batch);
+  count_flops(KC_TRSM, flop_scale<T>() * n * n * nrhs * batch);
   size_t smem = sizeof(T) * n;
   KScope ks_(KC_TRSM, st);
   if (n <= 64) k_trsm_lun<T, 2, LOWER><<<grid, TRSM_WARPS * 32, smem, st>>>(R, ldr, sR, B, ldb, sB, n, nrhs, dinv, sD);
@@ -175,6 +184,7 @@ template <typename T> static bool use_qr2(int m, int n) { return std::is_same<T,
 template <typename T>
 static void launch_qrp_blk(cudaStream_t st, T* A, int m, int n, int ld, long sA, T* tau, long sTau, int* jpvt, long sP, double* D, long sD, QrOut* out,
                            T* Tbuf, int batch) {
+  count_flops(KC_QRP, flop_scale<T>() * (2.0 * m * n * n - 2.0 * n * n * n / 3.0) * batch);
   if constexpr (std::is_same<T, double>::value) {
     if (use_qr2<T>(m, n)) {
       const long sT = (long)(n + 32) * 32;
@@ -197,6 +207,8 @@ static void launch_qrp_blk(cudaStream_t st, T* A, int m, int n, int ld, long sA,
 // X <- Q^H X (mode 0) / Q X (mode 1); ident: X holds the identity on entry (mode 1 only: forms Q)
 template <typename T>
 static void launch_apply_q(cudaStream_t st, const T* QR, int m, int n, int ld, long sQ, const T* Tbuf, T* X, int ldx, long sX, int ncols, int mode, bool ident, int batch) {
+  // ZUNMQR count 4 m n ncols - 2 n^2 ncols; forming Q from the identity (ZUNGQR) touches half of it
+  count_flops(KC_FORMQ, flop_scale<T>() * (4.0 * m * n * ncols - 2.0 * n * n * ncols) * (ident ? 0.5 : 1.0) * batch);
   if constexpr (std::is_same<T, double>::value) {
     if (use_qr2<T>(m, n)) {
       const bool small = applyq2_smem(m, 8) + 1024 <= 113 * 1024;        // two 8-warp CTAs per SM, else one 16-warp CTA

@@ -26,25 +26,30 @@
 // (nd4 = nd rounded up to 4); ldx % 16 == 4 makes the fragment loads bank-conflict free.
 // rev = 1 walks the tiles in the opposite order: consecutive flushes alternate, so the tiles written last by one flush (still
 // in L2: the batch of Green functions is only slightly larger than the 126 MB L2) are the first ones the next flush reads.
+// Warp tiles are 32 x 16 and software-pipelined two deep: the 16 loads of the next tile are in flight while the current one
+// is scaled, updated and stored, so every warp keeps HBM requests outstanding for the whole flush.
 static __device__ __noinline__ void flush_g0(double* __restrict__ G0, int N, const double* __restrict__ X, const double* __restrict__ Y, int ldx, int nd4,
                                       double* __restrict__ dl, double* __restrict__ dr, int rev) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-  const int tm = (N + 31) / 32, tiles = tm * tm;
+  const int tm = (N + 31) / 32, tn = (N + 15) / 16, tiles = tm * tn;
   const int g = lane >> 2, q = lane & 3;
-  for (int tt = warp; tt < tiles; tt += nw) {
+  auto load = [&](int tt, double (&c)[4][2][2]) {
     const int t = rev ? tiles - 1 - tt : tt;
-    const int i0 = (t % tm) * 32, j0 = (t / tm) * 32;
-    double c[4][4][2];
+    const int i0 = (t % tm) * 32, j0 = (t / tm) * 16;
 #pragma unroll
-    for (int b = 0; b < 4; ++b)
+    for (int b = 0; b < 2; ++b)
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         const int j = j0 + 8 * b + 2 * q + h;
 #pragma unroll
         for (int a = 0; a < 4; ++a) { const int i = i0 + 8 * a + g; c[a][b][h] = (i < N && j < N) ? G0[i + (long)j * N] : 0.0; }
       }
+  };
+  auto finish = [&](int tt, double (&c)[4][2][2]) {
+    const int t = rev ? tiles - 1 - tt : tt;
+    const int i0 = (t % tm) * 32, j0 = (t / tm) * 16;
 #pragma unroll
-    for (int b = 0; b < 4; ++b)
+    for (int b = 0; b < 2; ++b)
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         const int j = j0 + 8 * b + 2 * q + h; const double drj = (j < N) ? dr[j] : 0.0;
@@ -52,25 +57,41 @@ static __device__ __noinline__ void flush_g0(double* __restrict__ G0, int N, con
         for (int a = 0; a < 4; ++a) { const int i = i0 + 8 * a + g; c[a][b][h] = ((i < N ? dl[i] : 0.0) * c[a][b][h]) * drj; }
       }
     for (int k0 = 0; k0 < nd4; k0 += 4) {
-      double av[4], bv[4];
+      double av[4], bv[2];
       const double* xk = X + (long)(k0 + q) * ldx; const double* yk = Y + (long)(k0 + q) * ldx;
 #pragma unroll
       for (int a = 0; a < 4; ++a) { const int i = i0 + 8 * a + g; av[a] = (i < N) ? -xk[i] : 0.0; }
 #pragma unroll
-      for (int b = 0; b < 4; ++b) { const int j = j0 + 8 * b + g; bv[b] = (j < N) ? yk[j] : 0.0; }
+      for (int b = 0; b < 2; ++b) { const int j = j0 + 8 * b + g; bv[b] = (j < N) ? yk[j] : 0.0; }
 #pragma unroll
       for (int a = 0; a < 4; ++a)
 #pragma unroll
-        for (int b = 0; b < 4; ++b) dmma884(c[a][b][0], c[a][b][1], av[a], bv[b]);
+        for (int b = 0; b < 2; ++b) dmma884(c[a][b][0], c[a][b][1], av[a], bv[b]);
     }
 #pragma unroll
-    for (int b = 0; b < 4; ++b)
+    for (int b = 0; b < 2; ++b)
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         const int j = j0 + 8 * b + 2 * q + h;
 #pragma unroll
         for (int a = 0; a < 4; ++a) { const int i = i0 + 8 * a + g; if (i < N && j < N) G0[i + (long)j * N] = c[a][b][h]; }
       }
+  };
+  double cA[4][2][2], cB[4][2][2];
+  int tt = warp;
+  if (tt < tiles) {
+    load(tt, cA);
+    while (true) {
+      const int t1 = tt + nw;
+      if (t1 < tiles) load(t1, cB);
+      finish(tt, cA);
+      if (t1 >= tiles) break;
+      const int t2 = t1 + nw;
+      if (t2 < tiles) load(t2, cA);
+      finish(t1, cB);
+      if (t2 >= tiles) break;
+      tt = t2;
+    }
   }
   __syncthreads();
   for (int i = threadIdx.x; i < N; i += blockDim.x) { dl[i] = 1.0; dr[i] = 1.0; }

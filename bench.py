@@ -4,7 +4,8 @@
     python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path (one process per GPU under torchrun)
     python bench.py --impl reference --gpus N --steps K ...   # CPU arm: the oracle (restatement of ALF, not ALF.out)
 
-A "step" is ONE SWEEP (up + down pass over all L_trot slices, main.F90:714-887, plus TAU_M when --ltau 1) of every
+A "step" is ONE SWEEP (up + down pass over all L_trot slices, main.F90:714-887, plus TAU_M: --ltau 1 is the default because
+BASELINE.json's headline configuration measures time-displaced Green functions) of every
 chain resident on the GPU.  value = chain-sweeps per second summed over all ranks, timed with CUDA events on the
 handle's stream, max over ranks.  e2e = the same through alf_b200_sweep_host (host buffers in/out each step).
 The oracle is used here only as the CPU baseline (cpu_baseline / --impl reference), never on the measured GPU path.
@@ -218,6 +219,22 @@ def run_b200(args):
     h2d = C * L * M                                # int8 per field through the pinned staging buffer
     d2h = C * L * M + 8 * (len(obs) + 16)
 
+    # ---- un-timed extra passes (rank-local, after both timed regions): per-category device time + algorithmic FP64 flops of the
+    # dense kernels (CUDA events around every launch perturb the step, so they are kept out of the timed regions), and the same
+    # sweep without the time-displaced part for reference
+    g.kernel_timing(0xff)
+    g.sweep(1, args.ltau)
+    cat_stats = g.kernel_stats(); cat_flops = g.kernel_flops()
+    g.kernel_timing(0)
+    eq_only = None
+    if args.ltau:
+        barrier()
+        q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        q0.record(stream); g.sweep(1, 0); q1.record(stream)
+        barrier()
+        eq_ms = max_over_ranks(q0.elapsed_time(q1))
+        eq_only = {"value": world * C / (eq_ms * 1e-3), "unit": UNIT, "ms_per_step": eq_ms, "steps": 1, "note": "same chains, sweep without TAU_M (ltau = 0)"}
+
     # ---- roofline of the dominant kernel and CPU baseline (rank 0, N = 1 only for the latter)
     upd_ms, upd_n = stats["update"]
     acc = c1["ACC_up"] - c0["ACC_up"]
@@ -231,14 +248,27 @@ def run_b200(args):
             pass
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0)); peak_src = "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
         dfma, dmma = fp64_peak(local)
+        traffic = None; traffic_src = None
+        try:   # dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the committed ncu --set full capture of this kernel
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r1_ncu_update_kernel.json")))
+            if tj.get("workload") == args.workload and tj.get("chains") == C:
+                traffic = float(tj["dram_bytes_per_launch"]); traffic_src = tj.get("source")
+        except Exception:
+            pass
+        fp64_kernels = {}
+        for cat in ("gemm", "qrp", "formq", "trsm"):
+            cms, cn = cat_stats[cat]
+            if cn and cms > 0:
+                tf = cat_flops[cat] / (cms * 1e-3) / 1e12
+                fp64_kernels[cat] = {"launches": cn, "ms": cms, "tflops": tf, "frac_of_dmma_peak": tf / dmma if dmma else None}
         alg_bytes_per_launch = (acc * F * 2.0 * w * N * N) / max(upd_n, 1)        # 2*w*N^2 per accepted rank-1 update and flavor
         alg_flops_per_launch = (acc * F * 2.0 * (4 if g.is_complex else 1) * N * N) / max(upd_n, 1)
         avg_s = upd_ms * 1e-3 / max(upd_n, 1)
         achieved = alg_bytes_per_launch / avg_s / 1e9 if avg_s > 0 else 0.0
         roof = {"kernel": "k_wrapgr (delayed-update slice kernel)", "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                "traffic": None, "peak_source": peak_src, "launches": upd_n, "avg_launch_ms": 1e3 * avg_s, "share_of_step": upd_ms / ms if ms > 0 else None,
+                "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "launches": upd_n, "avg_launch_ms": 1e3 * avg_s, "share_of_step": upd_ms / ms if ms > 0 else None,
                 "algorithmic_bytes_per_launch": alg_bytes_per_launch,
-                "note": "algorithmic bytes = the reference's rank-1 ZGERU traffic (SURVEY 8d); the kernel keeps the updates delayed in shared memory, so its real DRAM traffic is far lower and frac may exceed 1",
+                "note": "algorithmic bytes = SURVEY 8d's figure for the reference algorithm (2*w*N^2 per accepted rank-1 ZGERU update and flavor); this kernel keeps accepted updates as delayed factors in shared memory and rewrites G once per KD accepts, so its DRAM traffic (see traffic) is ~20x below the algorithmic bytes and frac exceeds 1 by design",
                 "fp64": {"achieved_tflops": alg_flops_per_launch / avg_s / 1e12 if avg_s > 0 else 0.0, "peak_tflops_dfma_measured": dfma, "peak_tflops_dmma_measured": dmma}}
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
@@ -254,7 +284,9 @@ def run_b200(args):
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
                 "gpu_launches": nl, "kernel_launches": {k: v[1] for k, v in stats.items()},
                 "acceptance": acc / max(c1["NC_up"] - c0["NC_up"], 1), "precision_green_max": c1["XMAXG"],
-                "clocks": clk, "roofline": roof, "cpu_baseline": cpu}
+                "clocks": clk, "roofline": roof, "cpu_baseline": cpu,
+                "fp64_kernels": fp64_kernels, "fp64_peak_measured": {"dfma_tflops": dfma, "dmma_tflops": dmma},
+                "breakdown_ms_per_sweep": {k: round(v[0], 3) for k, v in cat_stats.items()}, "equal_time_only": eq_only}
     g.close()
     if world > 1:
         dist.barrier(); dist.destroy_process_group()
@@ -271,7 +303,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="hubbard_16x16_beta10", choices=sorted(WORKLOADS))
     ap.add_argument("--chains", type=int, default=0, help="chains per GPU (default: per workload)")
-    ap.add_argument("--ltau", type=int, default=0)
+    ap.add_argument("--ltau", type=int, default=1, help="1: the sweep includes TAU_M (BASELINE configs[2]: time-displaced Green functions); 0: equal-time only")
     ap.add_argument("--cpu-cores", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

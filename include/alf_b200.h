@@ -139,6 +139,7 @@ int alf_b200_hop_apply(alf_b200_handle* h, int which /* 0 mmthr,1 mmthr_m1,2 mmt
 int alf_b200_get_stream(alf_b200_handle* h, void** stream);
 int alf_b200_kernel_timing(alf_b200_handle* h, unsigned mask);        /* resets the statistics */
 int alf_b200_get_kernel_stats(alf_b200_handle* h, double* ms /* 8 */, long* launches /* 8 */);
+int alf_b200_get_kernel_flops(alf_b200_handle* h, double* flops /* 8: algorithmic FP64 flops per kernel category since the last reset */);
 int alf_b200_fp64_peak(int device, double* dfma_tflops, double* dmma_tflops);   /* roofline denominator microbenchmark */
 
 #ifdef __cplusplus
