@@ -81,10 +81,12 @@ __device__ __forceinline__ void apply_panel_strips(double* __restrict__ X, int l
     const bool ca = (c0 + 2 * q) < c_end, cb2 = (c0 + 2 * q + 1) < c_end;
     double* xc = X + (long)(c0 + 2 * q) * ldx + r0 + g;
     double n0 = 0.0, n1 = 0.0;
-#pragma unroll 2
-    for (int rb = 0; rb < mvp / 8; ++rb) {
+    const int nrb = mvp / 8;
+    double p0 = (g < mv && ca) ? xc[0] : 0.0, p1 = (g < mv && cb2) ? xc[ldx] : 0.0;       // row block 0, prefetched
+    for (int rb = 0; rb < nrb; ++rb) {
       const int r = 8 * rb + g; const bool rok = r < mv;
-      double a0 = (rok && ca) ? xc[8 * rb] : 0.0, a1 = (rok && cb2) ? xc[8 * rb + ldx] : 0.0;
+      double a0 = p0, a1 = p1;
+      if (rb + 1 < nrb) { const bool nok = r + 8 < mv; p0 = (nok && ca) ? xc[8 * rb + 8] : 0.0; p1 = (nok && cb2) ? xc[8 * rb + 8 + ldx] : 0.0; }
       const double* vp = Vs + r + (long)q * ldv;
 #pragma unroll
       for (int ks = 0; ks < 8; ++ks) dmma884(a0, a1, vp[(long)(4 * ks) * ldv], bw[ks]);
@@ -207,21 +209,22 @@ __global__ void __launch_bounds__(32 * (QR2_NB / CPW), CPW == 4 ? 2 : 1) k_qrp_r
       if (tid == 0) pos_slot[j] = p;
       if (warp == p / CPW) {
         const int hp = p % CPW;
-        double xn2 = 0.0, al = 0.0;
+        // The 2-norm of the pivot column below row prow - 1 is already known (pn, exact, from the previous step's update), so
+        // beta = -sign(alpha) pn needs no reduction on the critical path.  pn == 0: H = I (ZLARFG's xnorm == 0, alpha == 0 case).
+        double al = 0.0;
 #pragma unroll
         for (int r = 0; r < MAXR; ++r) {
           const int i = lane + 32 * r;
           double x = cr[0][r];
 #pragma unroll
           for (int h = 1; h < CPW; ++h) if (h == hp) x = cr[h][r];
-          if (i > prow) xn2 = fma(x, x, xn2);
           if (i == prow) al = x;
         }
-        xn2 = warp_sum(xn2);
         const double alpha = __shfl_sync(0xffffffffu, al, prow & 31);
+        const double cn = pn[p];
         double tj, scal, beta;
-        if (xn2 == 0.0) { tj = 0.0; scal = 0.0; beta = alpha; }
-        else { beta = -copysign(sqrt(alpha * alpha + xn2), alpha); tj = (beta - alpha) / beta; scal = 1.0 / (alpha - beta); }
+        if (cn == 0.0) { tj = 0.0; scal = 0.0; beta = alpha; }
+        else { beta = -copysign(cn, alpha); tj = (beta - alpha) / beta; scal = 1.0 / (alpha - beta); }
 #pragma unroll
         for (int r = 0; r < MAXR; ++r) {
           const int i = lane + 32 * r;
