@@ -205,6 +205,27 @@ static __global__ void k_ctl_accum(const double* __restrict__ cmp, int F, double
   }
 }
 
+// Model-independent scalar measurement at one time slice, where main.F90:757-773,789-802 call ham%Obser: per chain
+// ZP = Phase/Re(Phase), ZS = sign(Re Phase) (Hamiltonian_Hubbard_smod.F90:577-580) and the particle number
+// Part = N_SUN sum_nf sum_i (1 - G(i,i,nf)) -- a trace, hence identical for G and the symmetrised G~ = Hop_mod_Symm(G).
+// obs: [0] N_meas (chain-slices), [1] sum ZS, [2..3] sum Part ZP ZS (re, im)
+template <typename T>
+__global__ void __launch_bounds__(128) k_obs_scalar(const T* __restrict__ G, long sM, int N, int F, int n_sun, const cplx* __restrict__ phase, double* __restrict__ obs) {
+  __shared__ double red[2][4];
+  const int c = blockIdx.x;
+  cplx tr = cplx(0.0, 0.0);
+  for (int e = threadIdx.x; e < F * N; e += blockDim.x) { const int f = e / N, i = e % N; const T g = G[((long)c * F + f) * sM + i + (long)i * N]; tr = tr + cplx(1.0 - real_(g), -imag_(g)); }
+  double a = warp_sum(tr.x), b = warp_sum(tr.y);
+  if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = a; red[1][threadIdx.x >> 5] = b; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    a = red[0][0] + red[0][1] + red[0][2] + red[0][3]; b = red[1][0] + red[1][1] + red[1][2] + red[1][3];
+    const cplx ph = phase[c]; const double zs = (ph.x >= 0.0) ? 1.0 : -1.0; const cplx zp = cplx(1.0, ph.y / ph.x);
+    const cplx v = (cplx(a * n_sun, b * n_sun) * zp) * zs;
+    atomicAdd(obs + 0, 1.0); atomicAdd(obs + 1, zs); atomicAdd(obs + 2, v.x); atomicAdd(obs + 3, v.y);
+  }
+}
+
 // G0T = -(1 - G)  (tau_m_mod.F90:96-104)
 template <typename T>
 __global__ void k_g0t_init(T* __restrict__ G0T, const T* __restrict__ G, long sM, int n) {
@@ -540,7 +561,12 @@ struct Engine : EngineBase {
     cgr_and_phase(1, false);
   }
 
-  void measure_hook(int ntau) { (void)ntau; }   // device-side Obser: see alf_obs (next row of SURVEY 8f)
+  // where main.F90:757-773 / 789-802 call ham%Obser: NTAU1 in [LOBS_ST, LOBS_EN] (defaults of QMC_runtime_var_mod.F90:156-189)
+  void measure_hook(int ntau1) {
+    const int lobs_st = proj ? thtrot + 1 : 1, lobs_en = proj ? L - thtrot : L;
+    if (ntau1 < lobs_st || ntau1 > lobs_en) return;
+    KL(KC_OBS, st, k_obs_scalar<T><<<C, 128, 0, st>>>(G, n2, N, F, h->n_sun, h->d_phase, h->d_obs));
+  }
 
   // main.F90:714-887
   void sweep(int ltau) override {

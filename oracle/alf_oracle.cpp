@@ -769,7 +769,15 @@ struct Oracle {
   }
 
   std::vector<cd> eq_capture; int eq_capture_on = 0;   // G handed to ham%Obser: [visit][nf][N*N]
-  void obser_hook(int /*ntau*/) {
+  double obs_scal[4] = {0, 0, 0, 0};   // [0] N_meas, [1] sum ZS, [2..3] sum Part ZP ZS  (same model-independent scalars as the device)
+  void obser_hook(int ntau1) {
+    const int lobs_st = projector ? thtrot + 1 : 1, lobs_en = projector ? ltrot - thtrot : ltrot;   // QMC_runtime_var_mod.F90:156-189
+    if (ntau1 < lobs_st || ntau1 > lobs_en) return;
+    {   // ZP, ZS, Part as in Hamiltonian_Hubbard_smod.F90:577-580, 606-612 (a trace: the same for G and Hop_mod_Symm(G))
+      cd tr = 0; for (int nf = 0; nf < n_fl; ++nf) for (int i = 0; i < ndim; ++i) tr += cd(1, 0) - GR[nf][i + (size_t)i * ndim];
+      cd ZP = Phase / Phase.real(); double ZS = Phase.real() >= 0 ? 1.0 : -1.0; cd v = tr * (double)n_sun * ZP * ZS;
+      obs_scal[0] += 1; obs_scal[1] += ZS; obs_scal[2] += v.real(); obs_scal[3] += v.imag();
+    }
     if (!eq_capture_on) return;
     std::vector<cd> tmp((size_t)ndim * ndim);
     for (int nf = 0; nf < n_fl; ++nf) {
@@ -1052,6 +1060,7 @@ long orc_taum_get(void* h, double* out, long cap_complex) {
   if (out) std::memcpy(out, o->taum_buf.data(), sizeof(cd) * std::min(n, cap_complex));
   return n;
 }
+void orc_get_obs(void* h, double* out) { Oracle* o = (Oracle*)h; for (int i = 0; i < 4; ++i) out[i] = o->obs_scal[i]; }
 void orc_eq_capture(void* h, int on) { Oracle* o = (Oracle*)h; o->eq_capture_on = on; o->eq_capture.clear(); }
 long orc_eq_get(void* h, double* out, long cap_complex) {
   Oracle* o = (Oracle*)h; long n = (long)o->eq_capture.size();

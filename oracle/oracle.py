@@ -175,6 +175,12 @@ class Oracle:
         ns = n // (4 * self.m.N_FL * self.N * self.N)
         return buf.reshape(ns, 4, self.m.N_FL, self.N, self.N).transpose(0, 1, 2, 4, 3)
 
+    def obs(self):
+        """[N_meas, sum sign, Re/Im sum Part ZP ZS] accumulated where main.F90 calls ham%Obser."""
+        out = np.zeros(4)
+        lib().orc_get_obs(self.h, _d(out))
+        return out
+
     def eq_capture(self, on=True):
         lib().orc_eq_capture(self.h, int(on))
 

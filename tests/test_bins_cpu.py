@@ -1,0 +1,27 @@
+"""`_scal` bin records in ALF's text layout (Prog/observables_mod.F90:864-868) and the normalisation of Print_bin_Vec (:788-806)."""
+import numpy as np
+
+from alf_b200.bins import _e, format_scal_record, print_bin_vec, read_scal
+
+
+def test_fortran_e_descriptor():
+    assert _e(1.0, 25) == " 0.10000000000000000E+001"
+    assert _e(-0.5, 25) == "-0.50000000000000000E+000"
+    assert _e(0.0, 26) == "  0.00000000000000000E+000"
+    assert _e(-2.0 ** -10, 25) == "-0.97656250000000000E-003"
+    assert _e(0.99999999999999999999, 25) == " 0.10000000000000000E+001"
+    assert float(_e(0.1 + 0.2, 25)) == 0.1 + 0.2          # 17 significant digits round-trip a double
+    assert len(_e(123456.789, 25)) == 25 and len(_e(-1e-300, 26)) == 26
+
+
+def test_scal_record_layout_and_roundtrip(tmp_path):
+    rec = format_scal_record([1.5 - 2.0j, 0.25j], 0.875)
+    assert rec.startswith("         3 ( 0.15") and rec.count("(") == 2 and len(rec) == 10 + 2 * (2 + 25 + 1 + 25 + 1) + 26
+    p = str(tmp_path / "Part_scal")
+    # two bins: accumulators summed over 4 chains with 199 measurements per chain
+    for k in range(2):
+        print_bin_vec(p, [4 * 199 * (16.0 + k) + 0.0j], 4 * 199 * 1.0, 199, 4, description=["Particle number"])
+    obs, sign = read_scal(p)
+    assert obs.shape == (2, 1) and np.allclose(obs[:, 0], [16.0, 17.0]) and np.allclose(sign, 1.0)
+    info = open(p + "_info").read()
+    assert "====== Analysis Mode ======" in info and "identity" in info and "Particle number" in info

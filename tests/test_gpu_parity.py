@@ -160,6 +160,10 @@ def _run_parity(model, seeds, nwrap, n_sweeps=1, stab=0, check_udv=True):
         for nf in range(1, model.N_FL + 1):
             assert relF(g.green(c, nf), o.green(nf)) < TOL_G, ("sweep", c, nf)
         assert abs(ph[c] - o.phase()) < 1e-9
+    # device-side scalar observables (N_meas, <sign>, particle number) accumulated where main.F90 calls ham%Obser
+    ob = g.obs()[:4]; oo = sum(o.obs() for o in orcs)
+    assert ob[0] == oo[0] and ob[1] == oo[1] and ob[0] == len(seeds) * n_sweeps * (2 * model.Ltrot - 1)
+    assert abs(ob[2] - oo[2]) <= 1e-9 * abs(oo[2]) + 1e-9 and abs(ob[3] - oo[3]) <= 1e-8
     cg = g.control(); tot = {k: 0.0 for k in ("NC_up", "ACC_up", "NCG")}
     for o in orcs:
         co = o.control()
@@ -387,6 +391,8 @@ def _run_projector(model, seeds, nwrap, ltau):
             if af.size:
                 assert relF(af[:, 3], bf[:, 3]) < TOL_G   # G(tau,tau) freshly recomputed by CGRP
                 assert relF(af, bf) < 1e-8
+    ob = g.obs()[:4]; oo = sum(o.obs() for o in orcs)      # measured only inside [Thtrot+1, Ltrot-Thtrot]
+    assert ob[0] == oo[0] and ob[1] == oo[1] and ob[0] > 0 and abs(ob[2] - oo[2]) <= 1e-9 * abs(oo[2]) + 1e-9
     cg = g.control()
     assert cg["XMAXG"] < 1e-6 and cg["nan"] == 0 and cg["unstable"] == 0
     if ltau:
