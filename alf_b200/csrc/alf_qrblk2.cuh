@@ -2,7 +2,7 @@
 // matching block-reflector application.  Same mathematics and the same outputs as k_qrp_blk / k_apply_q (alf_qrblk.cuh:
 // windowed column pivoting, compact-WY trailing update; replaces ZGEQP3 / ZUNGQR / ZUNMQR of Prog/QDRP_decompose_mod.F90:78-100,
 // Prog/udv_state_mod.F90:569-578, Prog/cgr1_mod.F90:350-445, Prog/cgr2_2_mod.F90:155-191), restructured around the two things the
-// ncu source view showed the first version waiting on (profiles/r1_ncu_stab_blockedqr.md): block-wide barriers in the panel
+// ncu source view showed the first version waiting on (profiles/r1_ncu_stab.md): block-wide barriers in the panel
 // factorisation and in the 8-column tiles of the trailing update.
 //  * Panel factorisation: the 32 panel columns live in REGISTERS, two columns per warp (16 warps), lane l holding rows
 //    l, l+32, ...  Dot products and norms are warp-shuffle reductions, in-panel pivoting is a logical permutation (no data
