@@ -154,6 +154,29 @@ class AlfB200:
     def tau_p(self, nst_in):
         self._ck(lib().alf_b200_tau_p(self.h, int(nst_in)))
 
+    # ---- global-in-slice moves (Wrapgr_PlaceGR / Wrapgr_Random_update)
+    def wrapgr_set_position(self, m):
+        self._ck(lib().alf_b200_wrapgr_set_position(self.h, int(m)))
+
+    def wrapgr_get_position(self):
+        m = np.zeros(self.C, dtype=np.int32)
+        self._ck(lib().alf_b200_wrapgr_get_position(self.h, m.ctypes.data_as(_ip)))
+        return m
+
+    def wrapgr_placegr(self, m1, ntau):
+        self._ck(lib().alf_b200_wrapgr_placegr(self.h, int(m1), int(ntau)))
+
+    def wrapgr_random_update(self, ntau, flip_length, flip_list, flip_value, t0_ratio, s0_ratio, place_to=-1):
+        """flip_length, t0_ratio, s0_ratio: [chain, move]; flip_list (1-based), flip_value: [chain, move, maxlen]."""
+        fl = np.ascontiguousarray(flip_length, dtype=np.int32); C_, nm = fl.shape
+        li = np.ascontiguousarray(flip_list, dtype=np.int32); fv = np.ascontiguousarray(flip_value, dtype=np.complex128)
+        t0 = np.ascontiguousarray(t0_ratio, dtype=np.float64); s0 = np.ascontiguousarray(s0_ratio, dtype=np.float64)
+        assert C_ == self.C and li.shape == fv.shape == (C_, nm, li.shape[2])
+        acc = np.zeros((C_, nm), dtype=np.uint8)
+        self._ck(lib().alf_b200_wrapgr_random_update(self.h, int(ntau), int(nm), int(li.shape[2]), fl.ctypes.data_as(_ip), li.ctypes.data_as(_ip), _d(fv),
+                                                     _d(t0), _d(s0), acc.ctypes.data_as(C.POINTER(C.c_uint8)), int(place_to)))
+        return acc
+
     # ---- results
     def green(self, chain, nf, symmetrize=False):
         g = np.zeros((self.N, self.N), dtype=np.complex128, order="F")

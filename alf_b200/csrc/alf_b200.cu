@@ -210,6 +210,36 @@ int alf_b200_cgr(alf_b200_handle* h, int nvar) { API_BEGIN(h) NEED_FINAL(h) h->e
 int alf_b200_tau_m(alf_b200_handle* h) { API_BEGIN(h) NEED_FINAL(h) h->eng->tau_m(); h->eng->sync(); API_END(h) }
 int alf_b200_tau_p(alf_b200_handle* h, int nst_in) { API_BEGIN(h) NEED_FINAL(h) if (nst_in < 0) return ALF_ERROR_GENERIC; h->eng->tau_p(nst_in); h->eng->sync(); API_END(h) }
 
+// ---- global-in-slice moves: Wrapgr_PlaceGR / Wrapgr_Random_update (Prog/Wrapgr_mod.F90:247-433) with host-supplied proposals
+int alf_b200_wrapgr_set_position(alf_b200_handle* h, int m) { API_BEGIN(h) NEED_FINAL(h) if (m < 0 || m > h->n_opv) return ALF_ERROR_GENERIC; h->eng->gm_set_position(m); API_END(h) }
+int alf_b200_wrapgr_get_position(alf_b200_handle* h, int* m) { API_BEGIN(h) NEED_FINAL(h) h->eng->gm_get_position(m); API_END(h) }
+int alf_b200_wrapgr_placegr(alf_b200_handle* h, int m1, int ntau) {
+  API_BEGIN(h) NEED_FINAL(h) if (m1 < 0 || m1 > h->n_opv || ntau < 1 || ntau > h->ltrot) return ALF_ERROR_GENERIC;
+  h->eng->gm_random_update(ntau, 0, 1, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, m1); API_END(h)
+}
+int alf_b200_wrapgr_random_update(alf_b200_handle* h, int ntau, int n_moves, int maxlen, const int* flip_length, const int* flip_list, const double* flip_value,
+                                  const double* t0_ratio, const double* s0_ratio, uint8_t* accepted, int place_to) {
+  API_BEGIN(h) NEED_FINAL(h)
+  if (ntau < 1 || ntau > h->ltrot || n_moves < 0 || maxlen < 1 || maxlen > ALF_GM_MAXLEN || place_to > h->n_opv) return ALF_ERROR_GENERIC;
+  const size_t np = (size_t)h->n_chains * n_moves;
+  std::vector<int> l0(np * maxlen, 0); std::vector<int8_t> v8(np * maxlen, 1);
+  for (size_t p = 0; p < np; ++p) {
+    const int len = flip_length[p];
+    if (len < 0 || len > maxlen) { h->err = "wrapgr_random_update: Flip_length out of range"; return ALF_ERROR_GENERIC; }
+    std::vector<std::pair<int, long>> e(len);
+    for (int c = 0; c < len; ++c) {
+      const int n = flip_list[p * maxlen + c]; const long s = std::lround(flip_value[2 * (p * maxlen + c)]);
+      if (n < 1 || n > h->n_opv) { h->err = "wrapgr_random_update: Flip_list entry outside 1..size(Op_V,1)"; return ALF_ERROR_GENERIC; }
+      if (s == 0 || std::labs(s) > h->types[n - 1]) { h->err = "wrapgr_random_update: Flip_value outside the discrete range of its operator type"; return ALF_ERROR_FIELDS; }
+      e[c] = std::make_pair(n - 1, s);
+    }
+    std::stable_sort(e.begin(), e.end(), [](const std::pair<int, long>& a, const std::pair<int, long>& b) { return a.first < b.first; });   // Wrapgr_sort
+    for (int c = 0; c < len; ++c) { l0[p * maxlen + c] = e[c].first; v8[p * maxlen + c] = (int8_t)e[c].second; }
+  }
+  h->eng->gm_random_update(ntau, n_moves, maxlen, flip_length, l0.data(), v8.data(), t0_ratio, s0_ratio, accepted, place_to);
+  API_END(h)
+}
+
 int alf_b200_get_green(alf_b200_handle* h, int chain, int nf, int symmetrize, double* out) {
   API_BEGIN(h) NEED_FINAL(h) if (chain < 0 || chain >= h->n_chains || nf < 1 || nf > h->n_fl) return ALF_ERROR_GENERIC;
   h->eng->get_green(chain, nf, symmetrize, reinterpret_cast<cd*>(out)); API_END(h)

@@ -13,6 +13,7 @@
 #include "alf_ops.cuh"
 #include "alf_update.cuh"
 #include "alf_update_fast.cuh"
+#include "alf_global_move.cuh"
 
 typedef std::complex<double> cd;
 static const double kEpsMachine = 2.220446049250313e-16;
@@ -118,6 +119,10 @@ struct EngineBase {
   virtual void cgr_call(int nvar) = 0;
   virtual void tau_m() = 0;
   virtual void tau_p(int nst_in) = 0;
+  virtual void gm_set_position(int m) = 0;
+  virtual void gm_get_position(int* m) = 0;
+  virtual void gm_random_update(int ntau, int n_moves, int maxlen, const int* len, const int* list0, const int8_t* val, const double* t0, const double* s0,
+                                uint8_t* acc_out, int place_to) = 0;
   virtual void get_green(int chain, int nf, int symm, cd* out) = 0;
   virtual void set_green(int chain, int nf, const cd* in) = 0;
   virtual void get_udv(int which, int nst, int chain, int nf, cd* U, cd* D, cd* V) = 0;
@@ -702,6 +707,32 @@ struct Engine : EngineBase {
       for (int NT = L - thtrot + 2; NT <= stab_nt[NT_ST + 1]; ++NT) { proprm1(GTT, NT); propr(GTT, NT); }
       restab(); NT_ST++;
     }
+  }
+
+  // ---------------------------------------------------------------- global-in-slice moves (Prog/Wrapgr_mod.F90:247-433)
+  int* d_mpos = nullptr;
+  void gm_alloc() { if (!d_mpos) { d_mpos = dalloc<int>(C); CK(cudaMemsetAsync(d_mpos, 0, sizeof(int) * C, st)); } }
+  void gm_set_position(int m) override { gm_alloc(); std::vector<int> v(C, m); CK(cudaMemcpyAsync(d_mpos, v.data(), sizeof(int) * C, cudaMemcpyHostToDevice, st)); sync(); }
+  void gm_get_position(int* m) override { gm_alloc(); sync(); CK(cudaMemcpy(m, d_mpos, sizeof(int) * C, cudaMemcpyDeviceToHost)); }
+  void gm_random_update(int ntau, int n_moves, int maxlen, const int* len, const int* list0, const int8_t* val, const double* t0, const double* s0,
+                        uint8_t* acc_out, int place_to) override {
+    gm_alloc();
+    const size_t np = (size_t)C * std::max(n_moves, 1), nl = np * std::max(maxlen, 1);
+    int *d_len = nullptr, *d_list = nullptr; int8_t* d_val = nullptr; double *d_t0 = nullptr, *d_s0 = nullptr; uint8_t* d_acc = nullptr;
+    CK(cudaMalloc(&d_len, sizeof(int) * np)); CK(cudaMalloc(&d_list, sizeof(int) * nl)); CK(cudaMalloc(&d_val, nl));
+    CK(cudaMalloc(&d_t0, sizeof(double) * np)); CK(cudaMalloc(&d_s0, sizeof(double) * np)); CK(cudaMalloc(&d_acc, np));
+    if (n_moves > 0) {
+      CK(cudaMemcpyAsync(d_len, len, sizeof(int) * np, cudaMemcpyHostToDevice, st)); CK(cudaMemcpyAsync(d_list, list0, sizeof(int) * nl, cudaMemcpyHostToDevice, st));
+      CK(cudaMemcpyAsync(d_val, val, nl, cudaMemcpyHostToDevice, st)); CK(cudaMemcpyAsync(d_t0, t0, sizeof(double) * np, cudaMemcpyHostToDevice, st));
+      CK(cudaMemcpyAsync(d_s0, s0, sizeof(double) * np, cudaMemcpyHostToDevice, st));
+    }
+    const size_t smem = sizeof(T) * ((size_t)3 * N + 2 * ALF_KMAX * ALF_KMAX) + 64;
+    CK(cudaFuncSetAttribute(k_random_update<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    KL(KC_UPDATE, st, k_random_update<T><<<C, 512, smem, st>>>(G, G2, N, F, h->n_sun, M, d_vops, ft, h->d_fields, L, ntau, h->d_rng, h->d_phase, h->d_counters, d_mpos,
+                                                               n_moves, std::max(maxlen, 1), d_len, d_list, d_val, d_t0, d_s0, d_acc, place_to));
+    if (acc_out && n_moves > 0) { CK(cudaMemcpyAsync(acc_out, d_acc, np, cudaMemcpyDeviceToHost, st)); }
+    sync();
+    cudaFree(d_len); cudaFree(d_list); cudaFree(d_val); cudaFree(d_t0); cudaFree(d_s0); cudaFree(d_acc);
   }
 
   // PROPR / PROPRM1 (Prog/tau_m_mod.F90:215-263): A <- B(nt) A ;  A <- A B(nt)^-1

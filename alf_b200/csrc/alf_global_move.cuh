@@ -1,0 +1,174 @@
+// Global-in-slice moves on the device: Wrapgr_PlaceGR and Wrapgr_Random_update (Prog/Wrapgr_mod.F90:247-433) with
+// Upgrade2 in its "Intermediate" / "Final" modes (Prog/upgrade_mod.F90:203-222) for every chain of the handle.
+//
+// ham%Global_move_tau is a plugin callback (it proposes Flip_list, Flip_value, T0_Proposal_ratio, S0_ratio); the host
+// evaluates it and hands the proposals of all chains to this kernel, which performs everything the reference does with
+// them: sort order is expected on input (the C-ABI sorts, Wrapgr_sort :437-480), then per flip PlaceGR to n - 1,
+// Op_Wrapup N_type 1, Upgrade2, Op_Wrapup N_type 2, the Metropolis test on the accumulated ratio with the chain's own
+// random stream, and on rejection of a multi-field move the rollback of G (GR_st) and of the fields.
+//
+// One CTA per chain.  Moves are rare and touch few fields, so G is updated in place in global memory (rank-1 updates per
+// non-zero eigen-direction: the same Sherman-Morrison sequence as upgrade_mod.F90:225-285); no delayed factors here.
+#pragma once
+#include "alf_update.cuh"
+
+template <typename T>
+__device__ __forceinline__ void gm_similarity(T* __restrict__ Gf, int N, const VopDev<T>* op, int s, int mode, T* ones, T* AL_s, T* AR_s) {
+  // mode 0: Op_Wrapup N_type 1 (AL = diag(e) U^H, AR = U diag(1/e)); 1: Op_Wrapup N_type 2 (AL = U, AR = U^H)
+  // mode 2: Op_Wrapdo N_type 2 (AL = U^H, AR = U);                    3: Op_Wrapdo N_type 1 (AL = U diag(1/e), AR = diag(e) U^H)
+  const int k = op->k;
+  if (op->diag && (mode == 1 || mode == 2)) return;                 // U = 1: nothing to rotate
+  if (threadIdx.x < ALF_KMAX * ALF_KMAX) {
+    const int a = threadIdx.x % ALF_KMAX, b = threadIdx.x / ALF_KMAX;
+    T al = zero_<T>(), ar = zero_<T>();
+    if (a < k && b < k) {
+      const T ea = op->E_exp[a][s + 2], eb = op->E_exp[b][s + 2];
+      const T uab = op->U[a + b * ALF_KMAX], uba_c = conj_(op->U[b + a * ALF_KMAX]);
+      if (mode == 0) { al = ea * uba_c; ar = uab * (one_<T>() / eb); }
+      else if (mode == 1) { al = uab; ar = uba_c; }
+      else if (mode == 2) { al = uba_c; ar = uab; }
+      else { al = uab * (one_<T>() / eb); ar = ea * uba_c; }
+    }
+    AL_s[a + b * ALF_KMAX] = al; AR_s[a + b * ALF_KMAX] = ar;
+  }
+  __syncthreads();
+  T AL[ALF_KMAX * ALF_KMAX], AR[ALF_KMAX * ALF_KMAX];
+#pragma unroll
+  for (int e = 0; e < ALF_KMAX * ALF_KMAX; ++e) { AL[e] = AL_s[e]; AR[e] = AR_s[e]; }
+  similarity_immediate<T>(Gf, N, nullptr, nullptr, 0, 0, ones, ones, op->P, k, AL, AR);
+}
+
+// proposals: [chain][move]: length, t0 ratio, s0 ratio; [chain][move][maxlen]: 0-based op index (ascending), new field value
+template <typename T>
+__global__ void __launch_bounds__(512, 1) k_random_update(T* __restrict__ G, T* __restrict__ Gst, int N, int F, int n_sun, int M, const VopDev<T>* __restrict__ vops,
+                                                          FieldTabDev ft, int8_t* __restrict__ fields, int Ltrot, int nt, uint64_t* __restrict__ rng,
+                                                          cplx* __restrict__ phase, unsigned long long* __restrict__ counters, int* __restrict__ mpos,
+                                                          int n_moves, int maxlen, const int* __restrict__ flip_len, const int* __restrict__ flip_list,
+                                                          const int8_t* __restrict__ flip_val, const double* __restrict__ t0r, const double* __restrict__ s0r,
+                                                          uint8_t* __restrict__ acc_out, int place_to /* >= 0: final PlaceGR target, -1: none */) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  T* ones = reinterpret_cast<T*>(smem_raw);        // N
+  T* col = ones + N;                               // N
+  T* row = col + N;                                // N
+  T* AL_s = row + N; T* AR_s = AL_s + ALF_KMAX * ALF_KMAX;
+  __shared__ int s_acc; __shared__ T s_xf; __shared__ double s_prev[2];
+  const int chain = blockIdx.x, tid = threadIdx.x, nthr = blockDim.x;
+  T* Gc = G + (long)chain * F * N * N; T* Gs = Gst + (long)chain * F * N * N;
+  int8_t* fld = fields + ((long)chain * Ltrot + (nt - 1)) * M;
+  for (int i = tid; i < N; i += nthr) ones[i] = one_<T>();
+  __syncthreads();
+  int m = mpos[chain];
+  Xoshiro r; cplx ph = phase[chain];
+  r.s0 = rng[chain * 4 + 0]; r.s1 = rng[chain * 4 + 1]; r.s2 = rng[chain * 4 + 2]; r.s3 = rng[chain * 4 + 3];    // every thread keeps a copy; thread 0's is stored
+  unsigned long long n_acc = 0, n_prop = 0;
+
+  auto place = [&](int m1) {                       // Wrapgr_PlaceGR (:247-312)
+    if (m1 > m) {
+      for (int n = m; n < m1; ++n) { const int s = fld[n];
+        for (int f = 0; f < F; ++f) gm_similarity<T>(Gc + (long)f * N * N, N, vops + (long)n * F + f, s, 0, ones, AL_s, AR_s);
+        for (int f = 0; f < F; ++f) gm_similarity<T>(Gc + (long)f * N * N, N, vops + (long)n * F + f, s, 1, ones, AL_s, AR_s); }
+    } else {
+      for (int n = m - 1; n >= m1; --n) { const int s = fld[n];
+        for (int f = 0; f < F; ++f) gm_similarity<T>(Gc + (long)f * N * N, N, vops + (long)n * F + f, s, 2, ones, AL_s, AR_s);
+        for (int f = 0; f < F; ++f) gm_similarity<T>(Gc + (long)f * N * N, N, vops + (long)n * F + f, s, 3, ones, AL_s, AR_s); }
+    }
+    m = m1;
+  };
+
+  for (int mv = 0; mv < n_moves; ++mv) {
+    const long pi = (long)chain * n_moves + mv;
+    const int len = flip_len[pi]; const double T0 = t0r[pi], S0 = s0r[pi];
+    const int* fl = flip_list + pi * maxlen; const int8_t* fv = flip_val + pi * maxlen;
+    if (!(T0 > 10e-8) || len <= 0) { if (acc_out && tid == 0) acc_out[pi] = 2; continue; }
+    cplx prev = cplx(1.0, 0.0);
+    int acc = 0;
+    int8_t old_vals[ALF_GM_MAXLEN];
+    for (int c = 0; c < len; ++c) old_vals[c] = fld[fl[c]];
+    for (int c = 0; c < len; ++c) {
+      const int n = fl[c];
+      place(n);                                    // reference: PlaceGR(m, n - 1) with 1-based n
+      if (c == 0 && len > 1) { for (long e = tid; e < (long)F * N * N; e += nthr) Gs[e] = Gc[e]; }
+      const int s_old = fld[n], s_new = fv[c];
+      const VopDev<T>* op0 = vops + (long)n * F;
+      for (int f = 0; f < F; ++f) gm_similarity<T>(Gc + (long)f * N * N, N, op0 + f, s_old, 0, ones, AL_s, AR_s);
+      // ---- Upgrade2: ratio (every thread computes it redundantly from global G; k <= 4)
+      cplx ratiotot = cplx(1.0, 0.0);
+      for (int f = 0; f < F; ++f) {
+        const VopDev<T>* op = op0 + f; const int nz = op->nnz;
+        T Mat[ALF_KMAX][ALF_KMAX];
+        for (int q = 0; q < ALF_KMAX; ++q) for (int w = 0; w < ALF_KMAX; ++w) Mat[q][w] = zero_<T>();
+        for (int w = 0; w < nz; ++w) {
+          const T d = op->delta[w][s_old + 2][s_new + 2];
+          for (int q = 0; q < nz; ++q) Mat[q][w] = -(d * Gc[(long)f * N * N + op->P[q] + (long)op->P[w] * N]);
+          Mat[w][w] = Mat[w][w] + (d + one_<T>());
+        }
+        T D;
+        if (nz == 0) D = one_<T>();
+        else if (nz == 1) D = Mat[0][0];
+        else if (nz == 2) {
+          T s1 = Mat[0][0] * Mat[1][1], s2 = Mat[1][0] * Mat[0][1];
+          if (abs_(s1) > abs_(s2)) D = s1 * (one_<T>() - s2 / s1); else D = s2 * (s1 / s2 - one_<T>());
+        } else {
+          D = one_<T>();
+          for (int cc = 0; cc < nz; ++cc) {
+            int pv = cc; double best = abs_(Mat[cc][cc]);
+            for (int q = cc + 1; q < nz; ++q) if (abs_(Mat[q][cc]) > best) { best = abs_(Mat[q][cc]); pv = q; }
+            if (pv != cc) { for (int q = 0; q < nz; ++q) { T t = Mat[cc][q]; Mat[cc][q] = Mat[pv][q]; Mat[pv][q] = t; } D = -D; }
+            D = D * Mat[cc][cc];
+            for (int q = cc + 1; q < nz; ++q) { T l = Mat[q][cc] / Mat[cc][cc]; for (int w = cc; w < nz; ++w) Mat[q][w] = Mat[q][w] - l * Mat[cc][w]; }
+          }
+        }
+        const T rf = D * op->expalpha[s_old + 2][s_new + 2];
+        ratiotot = ratiotot * cplx(real_(rf), imag_(rf));
+      }
+      cplx rt = ratiotot;
+      for (int q = 1; q < n_sun; ++q) rt = rt * ratiotot;
+      const int type = op0->type;
+      rt = rt * (ft.gama[type][s_new + 2] / ft.gama[type][s_old + 2]);
+      const bool fin = (c == len - 1);
+      double weight;
+      if (fin) { rt = rt * prev; const cplx pr = ph * rt; weight = S0 * T0 * fabs(pr.x / ph.x); }
+      else { weight = 1.5; prev = prev * rt; }
+      const double u = r.ranf();
+      const int toggle = (weight > u) ? 1 : 0;
+      if (fin) { n_prop++; acc = toggle; if (toggle) { n_acc++; const double ar = abs_(rt); ph = ph * cplx(rt.x / ar, rt.y / ar); } }
+      __syncthreads();
+      if (toggle) {
+        // rank-1 updates over the non-zero eigen-directions (upgrade_mod.F90:225-285 in sequential Sherman-Morrison form)
+        const int nzmax = op0->nnz;
+        for (int a = 0; a < nzmax; ++a) for (int f = 0; f < F; ++f) {
+          const VopDev<T>* op = op0 + f;
+          if (a >= op->nnz) continue;
+          T* Gf = Gc + (long)f * N * N; const int p = op->P[a];
+          for (int i = tid; i < N; i += nthr) { col[i] = Gf[i + (long)p * N]; row[i] = Gf[p + (long)i * N]; }
+          __syncthreads();
+          const T d = op->delta[a][s_old + 2][s_new + 2];
+          const T xf = d / (one_<T>() + (one_<T>() - col[p]) * d);
+          for (long e = tid; e < (long)N * N; e += nthr) {
+            const int i = (int)(e % N), j = (int)(e / N);
+            const T y = ((j == p) ? one_<T>() : zero_<T>()) - row[j];
+            Gf[e] = Gf[e] - (xf * col[i]) * y;
+          }
+          __syncthreads();
+        }
+        if (tid == 0) fld[n] = (int8_t)s_new;
+        __syncthreads();
+      }
+      for (int f = 0; f < F; ++f) gm_similarity<T>(Gc + (long)f * N * N, N, op0 + f, s_old, 1, ones, AL_s, AR_s);
+      m = n + 1;                                   // reference: m = n (1-based)
+    }
+    if (!acc && len > 1) {                         // rollback (:421-427)
+      for (long e = tid; e < (long)F * N * N; e += nthr) Gc[e] = Gs[e];
+      if (tid == 0) for (int c = 0; c + 1 < len; ++c) fld[fl[c]] = old_vals[c];
+      m = fl[0];
+      __syncthreads();
+    }
+    if (acc_out && tid == 0) acc_out[pi] = (uint8_t)acc;
+  }
+  if (place_to >= 0) place(place_to);
+  if (tid == 0) {
+    mpos[chain] = m; phase[chain] = ph;
+    rng[chain * 4 + 0] = r.s0; rng[chain * 4 + 1] = r.s1; rng[chain * 4 + 2] = r.s2; rng[chain * 4 + 3] = r.s3;
+    counters[chain * 4 + 0] += n_prop; counters[chain * 4 + 1] += n_acc; counters[chain * 4 + 2] += n_prop; counters[chain * 4 + 3] += n_acc;
+  }
+}

@@ -16,6 +16,7 @@
 #define ALF_KMAX 4           // largest small-operator dimension handled by the op lists (bond ops: 2)
 #define ALF_NVAR 5           // field values sp = -2..2 -> table index sp+2 (types 1 and 2)
 #define ALF_FMAX 4           // max number of computed flavors
+#define ALF_GM_MAXLEN 16      // longest Flip_list of one global-in-slice move (Wrapgr_Random_update)
 
 struct OpListDev {
   int n_ops, n_levels, nvar;        // nvar = 1: fixed matrices (hopping); nvar = 5: field dependent (vertices)

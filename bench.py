@@ -32,12 +32,15 @@ WORKLOADS = {
     "hubbard_16x16_beta10": (16, 16, 10.0, 0.1, 4.0, 10, 148),      # BASELINE.json configs[2] = the metric's configuration
     "hubbard_8x8_beta10": (8, 8, 10.0, 0.1, 4.0, 10, 296),          # configs[1]
     "hubbard_4x4_beta5": (4, 4, 5.0, 0.1, 4.0, 10, 296),            # configs[0]
+    "kondo_12x12_beta20": (12, 12, 20.0, 0.1, None, 5, 148),        # configs[3]: SU(2) Kondo lattice, N_dim = 288, complex, Nwrap = 5
 }
 
 
 def make_model(name):
-    from alf_b200.model import hubbard_square
+    from alf_b200.model import hubbard_square, kondo_square
     L1, L2, beta, dtau, U, nwrap, chains = WORKLOADS[name]
+    if name.startswith("kondo"):
+        return kondo_square(L1, L2, beta=beta, dtau=dtau), nwrap, chains
     return hubbard_square(L1, L2, beta=beta, dtau=dtau, U=U), nwrap, chains
 
 

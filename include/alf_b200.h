@@ -86,6 +86,21 @@ int alf_b200_cgr(alf_b200_handle* h, int nvar);               /* Prog/cgr1_mod.F
 int alf_b200_tau_m(alf_b200_handle* h);                       /* Prog/tau_m_mod.F90:56 */
 int alf_b200_tau_p(alf_b200_handle* h, int nst_in);           /* Prog/tau_p_mod.F90:74 (projector; udvr, udvst, GR as in main.F90:829) */
 
+/* Global-in-slice moves (N_Global_tau > 0), Prog/Wrapgr_mod.F90:247-433.  ham%Global_move_tau stays a host plugin callback:
+ * its outputs (Flip_length, Flip_list (1-based), Flip_value, T0_Proposal_ratio, S0_ratio) are passed for every chain and every
+ * one of the n_moves proposals ([chain][move], lists [chain][move][maxlen], maxlen <= 16); the device sorts the lists
+ * (Wrapgr_sort), runs PlaceGR / Op_Wrapup / Upgrade2 ("Intermediate", "Final") with the chain's own random stream and rolls
+ * back rejected multi-field moves (GR_st).  The operator position m of GR inside the slice is per-chain device state:
+ * set it after WRAPGRUP (m = size(Op_V,1)) or before WRAPGRDO's sequential part; place_to >= 0 appends the final
+ * Wrapgr_PlaceGR(GR, m, place_to, ntau) of WRAPGRUP/WRAPGRDO (:148-153, :190-195). */
+int alf_b200_wrapgr_set_position(alf_b200_handle* h, int m);
+int alf_b200_wrapgr_get_position(alf_b200_handle* h, int* m /* [chain] */);
+int alf_b200_wrapgr_placegr(alf_b200_handle* h, int m1, int ntau);            /* Wrapgr_PlaceGR, Prog/Wrapgr_mod.F90:247 */
+int alf_b200_wrapgr_random_update(alf_b200_handle* h, int ntau, int n_moves, int maxlen, const int* flip_length, const int* flip_list,
+                                  const double* flip_value /* complex */, const double* t0_proposal_ratio, const double* s0_ratio,
+                                  uint8_t* accepted /* [chain][move]: 1 accepted, 0 rejected, 2 not proposed (T0 ratio <= 1e-7); may be NULL */,
+                                  int place_to);                             /* Wrapgr_Random_update, Prog/Wrapgr_mod.F90:317 */
+
 /* ---- results */
 int alf_b200_get_green(alf_b200_handle* h, int chain, int nf, int symmetrize, double* out /* complex N*N */);
 int alf_b200_set_green(alf_b200_handle* h, int chain, int nf, const double* in);

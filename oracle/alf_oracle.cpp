@@ -634,8 +634,11 @@ struct Oracle {
     xmean /= (double)n2; ctl.NCG_tau++; if (xmax > ctl.XMAX_tau) ctl.XMAX_tau = xmax; ctl.XMEAN_tau += xmean;
   }
 
-  // ---- Prog/upgrade_mod.F90:105-302 (mode "Final")
+  // ---- Prog/upgrade_mod.F90:105-302; final = true: mode "Final", false: mode "Intermediate" (Prev_Ratiotot accumulates)
   bool upgrade2(int n_op, int nt, cd Hs_new, cd Prev_Ratiotot, double S0_ratio, double T0_proposal_ratio) {
+    cd prev = Prev_Ratiotot; return upgrade2m(n_op, nt, Hs_new, prev, S0_ratio, T0_proposal_ratio, true);
+  }
+  bool upgrade2m(int n_op, int nt, cd Hs_new, cd& Prev_Ratiotot, double S0_ratio, double T0_proposal_ratio, bool final) {
     int op_dim = 0; for (int nf = 0; nf < n_fl; ++nf) op_dim = std::max(op_dim, OpV(n_op, nf).nnz);
     int type = OpV(n_op, 0).type;
     std::vector<cd> Mat(op_dim * op_dim), Delta((size_t)op_dim * n_fl), Ratio(n_fl);
@@ -661,14 +664,15 @@ struct Oracle {
     }
     cd Ratiotot = 1.0; for (int nf = 0; nf < n_fl; ++nf) Ratiotot *= Ratio[nf];
     Ratiotot = std::pow(Ratiotot, (double)n_sun) * ft.gama(type, Hs_new) / ft.gama(type, fld(n_op, nt));
-    Ratiotot = Ratiotot * Prev_Ratiotot;
-    double Weight = S0_ratio * T0_proposal_ratio * std::abs((Phase * Ratiotot).real() / Phase.real());
+    double Weight;
+    if (final) { Ratiotot = Ratiotot * Prev_Ratiotot; Weight = S0_ratio * T0_proposal_ratio * std::abs((Phase * Ratiotot).real() / Phase.real()); }
+    else { Weight = 1.5; Prev_Ratiotot = Prev_Ratiotot * Ratiotot; }
     bool toggle = false;
     double r = rng.ranf();
-    if (log_on) ratio_log.push_back(Weight);
+    if (log_on && final) ratio_log.push_back(Weight);
     if (Weight > r) {
       toggle = true;
-      Phase = Phase * Ratiotot / std::sqrt(Ratiotot * std::conj(Ratiotot));
+      if (final) Phase = Phase * Ratiotot / std::sqrt(Ratiotot * std::conj(Ratiotot));
       for (int nf = 0; nf < n_fl; ++nf) {
         const Op& op = OpV(n_op, nf); cd* G = GR[nf].data(); int od = op.nnz; int Nd = ndim;
         if (od <= 0) continue;
@@ -705,9 +709,49 @@ struct Oracle {
       }
       fld(n_op, nt) = Hs_new;
     }
-    ctl.NC_up++; ctl.NC_eff_up++; if (toggle) { ctl.ACC_up++; ctl.ACC_eff_up++; }
-    if (log_on) acc_log.push_back(toggle ? 1 : 0);
+    if (final) { ctl.NC_up++; ctl.NC_eff_up++; if (toggle) { ctl.ACC_up++; ctl.ACC_eff_up++; } }
+    if (log_on && final) acc_log.push_back(toggle ? 1 : 0);
     return toggle;
+  }
+
+  // ---- Prog/Wrapgr_mod.F90:247-312 : move GR between operator positions m -> m1 inside time slice ntau (m, m1 in 0..n_opv)
+  void wrapgr_placegr(int m, int m1, int ntau) {
+    if (m1 > m) {
+      for (int n = m + 1; n <= m1; ++n) { cd HS = fld(n - 1, ntau);
+        for (int nf = 0; nf < n_fl; ++nf) op_wrapup(GR[nf].data(), OpV(n - 1, nf), HS, 1);
+        for (int nf = 0; nf < n_fl; ++nf) op_wrapup(GR[nf].data(), OpV(n - 1, nf), HS, 2); }
+    } else if (m1 < m) {
+      for (int n = m; n >= m1 + 1; --n) { cd HS = fld(n - 1, ntau);
+        for (int nf = 0; nf < n_fl; ++nf) op_wrapdo(GR[nf].data(), OpV(n - 1, nf), HS, 2);
+        for (int nf = 0; nf < n_fl; ++nf) op_wrapdo(GR[nf].data(), OpV(n - 1, nf), HS, 1); }
+    }
+  }
+  // ---- Prog/Wrapgr_mod.F90:317-433 : ONE global-in-slice proposal (what ham%Global_move_tau returned is passed in).
+  // Flip_list is 1-based; returns the acceptance; m is updated as in the reference.
+  bool wrapgr_random_update_one(int& m, int ntau, double T0_Proposal_ratio, double S0_ratio, std::vector<int> Flip_list, std::vector<cd> Flip_value) {
+    const double Zero = 10e-8; bool Acc = false; const int Flip_length = (int)Flip_list.size();
+    if (!(T0_Proposal_ratio > Zero)) return false;
+    for (;;) { int swaps = 0;                               // wrapgr_sort (:437-480)
+      for (int nc = 0; nc + 1 < Flip_length; ++nc) if (Flip_list[nc] > Flip_list[nc + 1]) { std::swap(Flip_list[nc], Flip_list[nc + 1]); std::swap(Flip_value[nc], Flip_value[nc + 1]); swaps++; }
+      if (!swaps) break; }
+    std::vector<cd> Flip_value_st(Flip_length);
+    for (int c = 0; c + 1 < Flip_length; ++c) Flip_value_st[c] = fld(Flip_list[c] - 1, ntau);
+    cd Prev_Ratiotot(1, 0); std::vector<std::vector<cd>> GR_st;
+    for (int c = 0; c < Flip_length; ++c) {
+      const int n = Flip_list[c];
+      wrapgr_placegr(m, n - 1, ntau);
+      if (c == 0 && Flip_length > 1) GR_st = GR;
+      cd HS_Field = fld(n - 1, ntau);
+      for (int nf = 0; nf < n_fl; ++nf) op_wrapup(GR[nf].data(), OpV(n - 1, nf), HS_Field, 1);
+      Acc = upgrade2m(n - 1, ntau, Flip_value[c], Prev_Ratiotot, S0_ratio, T0_Proposal_ratio, c == Flip_length - 1);
+      for (int nf = 0; nf < n_fl; ++nf) op_wrapup(GR[nf].data(), OpV(n - 1, nf), HS_Field, 2);
+      m = n;
+    }
+    if (!Acc && Flip_length > 1) {
+      GR = GR_st; m = Flip_list[0] - 1;
+      for (int c = 0; c + 1 < Flip_length; ++c) fld(Flip_list[c] - 1, ntau) = Flip_value_st[c];
+    }
+    return Acc;
   }
 
   double S0(int, int, cd) { return 1.0; }   // Hamiltonian_main_mod S0_base for non-Ising actions (Hubbard_smod.F90:870-885)
@@ -1087,6 +1131,13 @@ void orc_op_wrapup(void* h, int n, int nf, double* A, double f_re, double f_im, 
   Oracle* o = (Oracle*)h; o->op_wrapup((cd*)A, o->OpV(n - 1, nf - 1), cd(f_re, f_im), ntype); }
 void orc_op_wrapdo(void* h, int n, int nf, double* A, double f_re, double f_im, int ntype) {
   Oracle* o = (Oracle*)h; o->op_wrapdo((cd*)A, o->OpV(n - 1, nf - 1), cd(f_re, f_im), ntype); }
+void orc_wrapgr_placegr(void* h, int m, int m1, int ntau) { ((Oracle*)h)->wrapgr_placegr(m, m1, ntau); }
+// one proposal of Wrapgr_Random_update; flip_list 1-based, flip_value complex interleaved; returns acceptance, *m updated
+int orc_wrapgr_random_update(void* h, int* m, int ntau, double t0_ratio, double s0_ratio, int flip_length, const int* flip_list, const double* flip_value) {
+  std::vector<int> fl(flip_list, flip_list + flip_length); std::vector<cd> fv(flip_length);
+  for (int i = 0; i < flip_length; ++i) fv[i] = cd(flip_value[2 * i], flip_value[2 * i + 1]);
+  return ((Oracle*)h)->wrapgr_random_update_one(*m, ntau, t0_ratio, s0_ratio, fl, fv) ? 1 : 0;
+}
 void orc_wrapgrup(void* h, int ntau) { ((Oracle*)h)->wrapgrup(ntau); }
 void orc_wrapgrdo(void* h, int ntau) { ((Oracle*)h)->wrapgrdo(ntau); }
 

@@ -218,6 +218,18 @@ class Oracle:
         lib().orc_op_wrapdo(self.h, n, nf, _d(A), C.c_double(field.real), C.c_double(field.imag), int(ntype))
         return A
 
+    def wrapgr_placegr(self, m, m1, ntau):
+        """Wrapgr_PlaceGR (Prog/Wrapgr_mod.F90:247): move GR from operator position m to m1 inside slice ntau."""
+        lib().orc_wrapgr_placegr(self.h, int(m), int(m1), int(ntau))
+
+    def wrapgr_random_update(self, m, ntau, t0_ratio, s0_ratio, flip_list, flip_value):
+        """One proposal of Wrapgr_Random_update (:317); flip_list 1-based.  Returns (accepted, new m)."""
+        fl = np.ascontiguousarray(flip_list, dtype=np.int32); fv = np.ascontiguousarray(flip_value, dtype=np.complex128)
+        mm = C.c_int(int(m))
+        acc = lib().orc_wrapgr_random_update(self.h, C.byref(mm), int(ntau), C.c_double(t0_ratio), C.c_double(s0_ratio), int(fl.size),
+                                             fl.ctypes.data_as(_ip), _d(fv))
+        return bool(acc), mm.value
+
     def wrapgrup(self, ntau):
         lib().orc_wrapgrup(self.h, int(ntau))
 

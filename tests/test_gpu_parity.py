@@ -422,3 +422,65 @@ def test_projector_taup_after_sweep_complex():
 def test_projector_config_like_8x8():
     """8x8 Hubbard projector (N_dim = 64, N_part = 32), the size class of BASELINE configs[4]'s projective runs."""
     _run_projector(hubbard_square(8, 8, 1.0, 0.1, 4.0, projector=True, theta=1.0, trial="dimer"), SEEDS[:2], nwrap=10, ltau=1)
+
+
+# ---------------------------------------------------------------------------------- global-in-slice moves (a3)
+def _other_value(model, n, cur, rng):
+    """A new field value for operator n (1-based) different from the current one: type 1 -> flip, type 2 -> one of the other three."""
+    cur = int(round(cur.real))
+    if model.Op_V[n - 1][0].type == 1:
+        return complex(-cur)
+    return complex([x for x in (-2, -1, 1, 2) if x != cur][int(rng.integers(0, 3))])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("which", ["hubbard_mz", "hubbard_su2", "kondo"])
+def test_wrapgr_random_update_and_placegr(which):
+    """Wrapgr_Random_update / Wrapgr_PlaceGR (Prog/Wrapgr_mod.F90:247-433) with host-supplied proposals: single- and multi-field
+    moves, accepted and rejected (rollback of G and fields), T0_Proposal_ratio = 0 (not proposed), then PlaceGR back to size(Op_V,1)."""
+    model = {"hubbard_mz": lambda: hubbard_square(4, 4, 1.0), "hubbard_su2": lambda: hubbard_square(4, 4, 1.0, Mz=False),
+             "kondo": lambda: kondo_square(2, 2, 1.0)}[which]()
+    seeds = SEEDS[:3]; C = len(seeds); M = model.n_opv; ntau = 1; nmoves = 6; maxlen = 4
+    g = AlfB200(model, n_chains=C, nwrap=5); g.set_seeds(seeds); g.fields_set(); g.init_sweep()
+    orcs = []
+    for s in seeds:
+        o = Oracle(model, nwrap=5); o.ranset(s); o.fields_set(); o.init(); orcs.append(o)
+    g.wrapgrup(0)
+    for o in orcs:
+        o.wrapgrup(0)
+    g.wrapgr_set_position(M)
+    rng = np.random.default_rng(7)
+    flen = np.zeros((C, nmoves), dtype=np.int32); flist = np.ones((C, nmoves, maxlen), dtype=np.int32)
+    fval = np.ones((C, nmoves, maxlen), dtype=np.complex128); t0 = np.ones((C, nmoves)); s0 = np.ones((C, nmoves))
+    acc_ref = np.zeros((C, nmoves), dtype=np.uint8); m_ref = np.zeros(C, dtype=np.int32)
+    for c, o in enumerate(orcs):
+        m = M
+        for mv in range(nmoves):
+            L = int(rng.integers(1, maxlen + 1)); ns = rng.choice(np.arange(1, M + 1), size=L, replace=False)
+            f = o.get_fields()[ntau - 1]
+            vals = [_other_value(model, int(n), f[n - 1], rng) for n in ns]
+            flen[c, mv] = L; flist[c, mv, :L] = ns; fval[c, mv, :L] = vals
+            t0[c, mv] = 0.0 if mv == 2 else float(rng.uniform(0.5, 2.0)); s0[c, mv] = float(rng.uniform(0.5, 2.0))
+            if t0[c, mv] > 1e-7:
+                a, m = o.wrapgr_random_update(m, ntau, t0[c, mv], s0[c, mv], ns, vals)
+                acc_ref[c, mv] = 1 if a else 0
+            else:
+                acc_ref[c, mv] = 2
+        o.wrapgr_placegr(m, M, ntau); m_ref[c] = M
+    # NOTE: the oracle consumed the proposals sequentially with fields evolving; the device gets the same lists
+    acc = g.wrapgr_random_update(ntau, flen, flist, fval, t0, s0, place_to=M)
+    assert np.array_equal(acc, acc_ref), (acc, acc_ref)
+    assert 0 < int(np.sum(acc_ref == 1)) and int(np.sum(acc_ref == 0)) > 0          # both branches exercised
+    assert np.array_equal(g.wrapgr_get_position(), m_ref)
+    f = g.get_fields(); ph = g.phase(); st = g.rng_state()
+    for c, o in enumerate(orcs):
+        assert np.array_equal(f[c], o.get_fields())
+        assert np.array_equal(st[c], o.rng_state())
+        for nf in range(1, model.N_FL + 1):
+            assert relF(g.green(c, nf), o.green(nf)) < TOL_G, (c, nf)
+        assert abs(ph[c] - o.phase()) < 1e-9
+    # moving GR down to position 0 and back up is the identity on G
+    g.wrapgr_placegr(0, ntau); g.wrapgr_placegr(M, ntau)
+    for c, o in enumerate(orcs):
+        assert relF(g.green(c, 1), o.green(1)) < TOL_G
+    g.close()
