@@ -97,6 +97,42 @@ module alf_b200_shim
        import :: c_ptr, c_int
        type(c_ptr), value :: h
      end function
+     integer(c_int) function alf_b200_set_projector(h, thtrot, n_part) bind(c, name="alf_b200_set_projector")
+       import :: c_ptr, c_int
+       type(c_ptr), value :: h
+       integer(c_int), value :: thtrot, n_part
+     end function
+     integer(c_int) function alf_b200_set_trial_wf(h, nf, P_L, P_R) bind(c, name="alf_b200_set_trial_wf")
+       import :: c_ptr, c_int, c_double_complex
+       type(c_ptr), value :: h
+       integer(c_int), value :: nf
+       complex(c_double_complex), intent(in) :: P_L(*), P_R(*)      ! WF_L(nf)%P, WF_R(nf)%P  (Ndim x N_part)
+     end function
+     integer(c_int) function alf_b200_tau_p(h, nst_in) bind(c, name="alf_b200_tau_p")
+       import :: c_ptr, c_int
+       type(c_ptr), value :: h
+       integer(c_int), value :: nst_in
+     end function
+     integer(c_int) function alf_b200_wrapgr_set_position(h, m) bind(c, name="alf_b200_wrapgr_set_position")
+       import :: c_ptr, c_int
+       type(c_ptr), value :: h
+       integer(c_int), value :: m
+     end function
+     integer(c_int) function alf_b200_wrapgr_placegr(h, m1, ntau) bind(c, name="alf_b200_wrapgr_placegr")
+       import :: c_ptr, c_int
+       type(c_ptr), value :: h
+       integer(c_int), value :: m1, ntau
+     end function
+     integer(c_int) function alf_b200_wrapgr_random_update(h, ntau, n_moves, maxlen, flip_length, flip_list, flip_value, &
+          &                                                  t0_ratio, s0_ratio, accepted, place_to) bind(c, name="alf_b200_wrapgr_random_update")
+       import :: c_ptr, c_int, c_double, c_double_complex, c_int8_t
+       type(c_ptr), value :: h
+       integer(c_int), value :: ntau, n_moves, maxlen, place_to
+       integer(c_int), intent(in) :: flip_length(*), flip_list(*)     ! [chain][move], [chain][move][maxlen] (1-based operator indices)
+       complex(c_double_complex), intent(in) :: flip_value(*)
+       real(c_double), intent(in) :: t0_ratio(*), s0_ratio(*)
+       integer(c_int8_t), intent(out) :: accepted(*)
+     end function
      integer(c_int) function alf_b200_get_green(h, chain, nf, symmetrize, gout) bind(c, name="alf_b200_get_green")
        import :: c_ptr, c_int, c_double_complex
        type(c_ptr), value :: h
