@@ -202,7 +202,8 @@ static __global__ void k_phase_update(const cplx* __restrict__ z, const double* 
 static __global__ void k_ctl_accum(const double* __restrict__ cmp, int F, double* __restrict__ ctl, int which, int n_chains) {
   int c = blockIdx.x * blockDim.x + threadIdx.x; if (c >= n_chains) return;
   for (int f = 0; f < F; ++f) {
-    const double* o = cmp + (long)(c * F + f) * 3;
+    double o[3] = {0.0, 0.0, 0.0};                                   // fold the CMP_SPLIT parts of the matrix
+    for (int p = 0; p < CMP_SPLIT; ++p) { const double* q = cmp + ((long)(c * F + f) * CMP_SPLIT + p) * 3; o[0] = fmax(o[0], q[0]); o[1] += q[1]; if (q[2] != 0.0) o[2] = 1.0; }
     if (which == 0) {
       ctl[c * 8 + 0] += o[1]; if (o[0] > ctl[c * 8 + 1]) ctl[c * 8 + 1] = o[0]; ctl[c * 8 + 2] += 1.0;
       int flags = (int)ctl[c * 8 + 7]; if (o[2] != 0.0) flags |= 1; if (o[0] > 10.0) flags |= 2; ctl[c * 8 + 7] = (double)flags;
@@ -287,6 +288,16 @@ struct Engine : EngineBase {
     d.level_start = dupload(ls); d.k = dupload(lb.k); d.P = dupload(lb.P); d.fidx = dupload(lb.fidx);
     std::vector<T> m(lb.mat.size()); for (size_t i = 0; i < m.size(); ++i) m[i] = to_T<T>(lb.mat[i]);
     d.mat = dupload(m);
+    std::vector<unsigned char> uni(std::max(d.n_levels, 1), 0);
+    if (lb.nvar == 1) for (int c = 0; c < d.n_levels; ++c) {       // chunks whose operators all carry the same 2 x 2 matrix
+      bool u = true;
+      for (int o = ls[c]; o < ls[c + 1] && u; ++o) {
+        if (lb.k[o] != 2) u = false;
+        for (int e = 0; e < ALF_KMAX * ALF_KMAX && u; ++e) if (lb.mat[(size_t)o * ALF_KMAX * ALF_KMAX + e] != lb.mat[(size_t)ls[c] * ALF_KMAX * ALF_KMAX + e]) u = false;
+      }
+      uni[c] = u ? 1 : 0;
+    }
+    d.uniform = dupload(uni);
     return d;
   }
 
@@ -307,7 +318,7 @@ struct Engine : EngineBase {
       for (int f = 0; f < F; ++f) for (long i = 0; i < (long)N * NP; ++i) { a[(size_t)f * N * NP + i] = to_T<T>(h->wf_l[f][i]); b2[(size_t)f * N * NP + i] = to_T<T>(h->wf_r[f][i]); }
       d_wfl = dupload(a); d_wfr = dupload(b2);
     }
-    d_z = dalloc<cplx>(NM); d_angle = dalloc<double>(NM); d_cmp = dalloc<double>((size_t)NM * 3);
+    d_z = dalloc<cplx>(NM); d_angle = dalloc<double>(NM); d_cmp = dalloc<double>((size_t)NM * 3 * CMP_SPLIT);
     // update kernel configuration: as many delayed columns as fit in ~200 KB of shared memory
     size_t per_kd = (size_t)F * 2 * (N + 2) * sizeof(T), fixed = (size_t)F * 3 * N * sizeof(T) + 256;
     KD = (int)((200 * 1024 - fixed) / per_kd); if (KD > 32) KD = 32; if (KD < 4) throw CudaError("Ndim too large for the update kernel's shared-memory factors");
@@ -523,7 +534,7 @@ struct Engine : EngineBase {
     if (proj) la_cgrp<T>(w, wp, udvr, udvl, G2, d_z);      // cgr1_mod.F90:207-211
     else la_cgr<T>(w, nvar, h->stab, udvr, udvl, G2, d_z);
     if (compare) {
-      KL(KC_EW, st, k_compare<T><<<NM, 256, 0, st>>>(G2, G, n2, n2, d_cmp));
+      KL(KC_EW, st, k_compare<T><<<dim3(NM, CMP_SPLIT), 256, 0, st>>>(G2, G, n2, n2, d_cmp));
       KL(KC_EW, st, k_ctl_accum<<<(C + 127) / 128, 128, 0, st>>>(d_cmp, F, h->d_ctl, 0, C));
     }
     std::swap(G, G2);
@@ -641,7 +652,7 @@ struct Engine : EngineBase {
     for (int c = 0; c < C; ++c) dst[c].insert(dst[c].end(), part[c].begin(), part[c].end());
   }
   void compare_tau(const T* A, const T* B) {   // Control_Precision_tau, control_mod.F90:300-311
-    KL(KC_EW, st, k_compare<T><<<NM, 256, 0, st>>>(A, B, n2, n2, d_cmp));
+    KL(KC_EW, st, k_compare<T><<<dim3(NM, CMP_SPLIT), 256, 0, st>>>(A, B, n2, n2, d_cmp));
     KL(KC_EW, st, k_ctl_accum<<<(C + 127) / 128, 128, 0, st>>>(d_cmp, F, h->d_ctl, 1, C));
   }
   void tau_m() override {

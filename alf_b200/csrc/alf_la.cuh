@@ -559,6 +559,18 @@ __global__ void k_permcopy(T* __restrict__ dst, int ldd, long sDst, const T* __r
   }
 }
 
+// dst = src^H for n x n matrices through 32 x 32 shared-memory tiles (both sides coalesced); grid = (tiles^2, batch), 256 threads
+template <typename T>
+__global__ void __launch_bounds__(256) k_transpose_conj(T* __restrict__ dst, int ldd, long sDst, const T* __restrict__ src, int lds, long sSrc, int n) {
+  __shared__ T tile[32][33];
+  const int b = blockIdx.y, nt = (n + 31) / 32, ti = blockIdx.x % nt, tj = blockIdx.x / nt;
+  dst += (long)b * sDst; src += (long)b * sSrc;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int c = ty; c < 32; c += 8) { const int i = ti * 32 + tx, j = tj * 32 + c; if (i < n && j < n) tile[c][tx] = src[i + (long)j * lds]; }
+  __syncthreads();
+  for (int c = ty; c < 32; c += 8) { const int i = tj * 32 + tx, j = ti * 32 + c; if (i < n && j < n) dst[i + (long)j * ldd] = conj_(tile[tx][c]); }
+}
+
 // A(:, j) *= d[j]   (udv_state_mod.F90:473-477)
 template <typename T>
 __global__ void k_colscale(T* __restrict__ A, int ld, long sA, int m, int n, const double* __restrict__ d, long sD) {
@@ -682,13 +694,15 @@ __global__ void k_cgr22_blocks(const T* __restrict__ INP, long s22, T* __restric
 }
 
 // Control_PrecisionG / COMPARE (control_mod.F90:207-298, mymats_mod.F90:683-704): per matrix max and mean |A-B|, NaN flag.
-// out[b*3+0] = xmax, +1 = xmean, +2 = nan flag
+// The matrix is split over CMP_SPLIT CTAs (grid = (matrices, CMP_SPLIT)); slot (b, part): out[(b*CMP_SPLIT+part)*3 + 0] = xmax of the
+// part, +1 = its sum of |A-B| divided by nelem (the parts add up to xmean), +2 = nan flag.  k_ctl_accum folds the parts.
+#define CMP_SPLIT 8
 template <typename T>
 __global__ void __launch_bounds__(256) k_compare(const T* __restrict__ A, const T* __restrict__ B, long sM, long nelem, double* __restrict__ out) {
   __shared__ double smax[8], ssum[8]; __shared__ int snan[8];
   const int b = blockIdx.x; A += (long)b * sM; B += (long)b * sM;
   double mx = 0.0, sm = 0.0; int nn = 0;
-  for (long e = threadIdx.x; e < nelem; e += blockDim.x) {
+  for (long e = (long)blockIdx.y * blockDim.x + threadIdx.x; e < nelem; e += (long)blockDim.x * gridDim.y) {
     T a = A[e], c = B[e];
     if (isnan_(a) || isnan_(c)) nn = 1;
     double d = abs_(a - c);
@@ -700,6 +714,7 @@ __global__ void __launch_bounds__(256) k_compare(const T* __restrict__ A, const 
   __syncthreads();
   if (threadIdx.x == 0) {
     for (int w = 1; w < (int)(blockDim.x >> 5); ++w) { mx = fmax(mx, smax[w]); sm += ssum[w]; nn |= snan[w]; }
-    out[b * 3 + 0] = mx; out[b * 3 + 1] = sm / (double)nelem; out[b * 3 + 2] = (double)nn;
+    double* o = out + ((long)b * gridDim.y + blockIdx.y) * 3;
+    o[0] = mx; o[1] = sm / (double)nelem; o[2] = (double)nn;
   }
 }

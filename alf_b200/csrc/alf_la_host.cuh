@@ -346,11 +346,11 @@ static void la_cgr(LaWork<T>& w, int nvar, int stab, const UdvDev<T>& R, const U
     // explicit Q in W[1]
     KL(KC_EW, st, k_permcopy<T, 0><<<eg, 256, 0, st>>>(w.W[1], N, n2, w.W[2], N, n2, N, N, nullptr, 0));
     launch_formq<T>(st, w.W[1], N, N, N, n2, w.tau, N, nullptr, NM);
-    KL(KC_EW, st, k_permcopy<T, 4><<<eg, 256, 0, st>>>(w.W[0], N, n2, A0.U, N, n2, N, N, nullptr, 0));
+    KL(KC_EW, st, k_transpose_conj<T><<<dim3(((N + 31) / 32) * ((N + 31) / 32), NM), 256, 0, st>>>(w.W[0], N, n2, A0.U, N, n2, N));
     if (stab == 3) { KL(KC_EW, st, k_sep_scale<T, 1><<<eg, 256, 0, st>>>(w.W[0], n2, N, A0.D, N)); }
     gemm<T, 1, 0, 0>(st, N, N, N, w.W[1], N, n2, w.W[0], N, n2, w.W[3], N, n2, NM);      // X = Q^H X0
   } else {   // ZUNMQR: the block reflectors are applied to X0 directly
-    KL(KC_EW, st, k_permcopy<T, 4><<<eg, 256, 0, st>>>(w.W[3], N, n2, A0.U, N, n2, N, N, nullptr, 0));
+    KL(KC_EW, st, k_transpose_conj<T><<<dim3(((N + 31) / 32) * ((N + 31) / 32), NM), 256, 0, st>>>(w.W[3], N, n2, A0.U, N, n2, N));
     if (stab == 3) { KL(KC_EW, st, k_sep_scale<T, 1><<<eg, 256, 0, st>>>(w.W[3], n2, N, A0.D, N)); }
     launch_apply_q<T>(st, w.W[2], N, N, N, n2, w.Tbuf, w.W[3], N, n2, N, 0, false, NM);
   }
@@ -372,7 +372,7 @@ static void la_inverse(LaWork<T>& w, T* A, T* Ainv) {
   if (!use_blocked_qr<T>(N, N)) {
     KL(KC_EW, st, k_permcopy<T, 0><<<eg, 256, 0, st>>>(w.W[0], N, n2, A, N, n2, N, N, nullptr, 0));
     launch_formq<T>(st, w.W[0], N, N, N, n2, w.tau, N, nullptr, NM);
-    KL(KC_EW, st, k_permcopy<T, 4><<<eg, 256, 0, st>>>(w.W[1], N, n2, w.W[0], N, n2, N, N, nullptr, 0));      // Q^H
+    KL(KC_EW, st, k_transpose_conj<T><<<dim3(((N + 31) / 32) * ((N + 31) / 32), NM), 256, 0, st>>>(w.W[1], N, n2, w.W[0], N, n2, N));      // Q^H
   } else {
     KL(KC_EW, st, k_set_identity<T><<<eg, 256, 0, st>>>(w.W[1], N, n2, N, N));
     launch_apply_q<T>(st, A, N, N, N, n2, w.Tbuf, w.W[1], N, n2, N, 0, false, NM);                            // Q^H
@@ -409,7 +409,7 @@ static void la_cgr2_2(LaWork<T>& w, LaWork<T>& w2, int stab, const UdvDev<T>& ud
   la_qrp<T>(w2, w2.W[0], N2, N2, w2.Dq);
   // HLP <- P^T-row gather (ZLAPMR forward), L = R^H, HLP <- L^-1 HLP, rows / D3, HLP <- Q HLP
   KL(KC_EW, st, k_permcopy<T, 1><<<eg2, 256, 0, st>>>(w2.W[2], N2, n22, w2.W[1], N2, n22, N2, N2, w2.jpvt, N2));
-  KL(KC_EW, st, k_permcopy<T, 4><<<eg2, 256, 0, st>>>(w2.W[3], N2, n22, w2.W[0], N2, n22, N2, N2, nullptr, 0));   // full conj-transpose; only its lower triangle (R^H) is read
+  KL(KC_EW, st, k_transpose_conj<T><<<dim3(((N2 + 31) / 32) * ((N2 + 31) / 32), NM), 256, 0, st>>>(w2.W[3], N2, n22, w2.W[0], N2, n22, N2));   // full conj-transpose; only its lower triangle (R^H) is read
   launch_trsm<T, 1>(st, w2.W[3], N2, n22, w2.W[2], N2, n22, N2, N2, nullptr, 0, NM, w2.Rinv, w2.sRinv());
   KL(KC_EW, st, k_rowscale_inv<T><<<eg2, 256, 0, st>>>(w2.W[2], N2, n22, N2, N2, w2.Dq, N2));
   if (!use_blocked_qr<T>(N2, N2)) {

@@ -25,6 +25,7 @@ struct OpListDev {
   const int* P;                     // n_ops * ALF_KMAX   (0-based)
   const int* fidx;                  // n_ops : field index n (0-based) or -1
   const void* mat;                  // n_ops * nvar * KMAX*KMAX entries of T, column-major a + b*KMAX
+  const unsigned char* uniform;     // n_levels: 1 if every operator of the chunk is a k = 2 operator with one and the same matrix
 };
 
 enum {  // which operator lists a launch applies (per slice nt in [nt_a, nt_b])
@@ -60,10 +61,24 @@ struct ModelDev {
 // Shared-memory descriptor of one operator: x = (k << 28) | element offset of row P[0] in the panel, y, z, w = offsets of P[1..3];
 // its k x k matrix sits in dM[o << 2 LK] with leading dimension 1 << LK.
 template <typename T, int LK>
-__device__ __forceinline__ void ops_process_chunk(T* __restrict__ S, bool lane_ok, int cnt, const int4* __restrict__ dP, const T* __restrict__ dM) {
+__device__ __forceinline__ void ops_process_chunk(T* __restrict__ S, bool lane_ok, int cnt, const int4* __restrict__ dP, const T* __restrict__ dM, bool uniform) {
   constexpr int kk = 1 << LK, ms = 1 << (2 * LK);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
   T* Sl = S + lane;
+  if (LK >= 1 && uniform) {                   // translation-invariant checkerboard family: one matrix for the whole chunk
+    const T a00 = dM[0], a10 = dM[1], a01 = dM[kk], a11 = dM[kk + 1];
+    for (int o = warp; o < cnt; o += 2 * nw) {
+      const int o2 = (o + nw < cnt) ? o + nw : o;
+      const int4 P = dP[o], Q = dP[o2];
+      const int px = P.x & 0x0fffffff, qx = Q.x & 0x0fffffff;
+      if (lane_ok) {
+        const T v0 = Sl[px], v1 = Sl[P.y], w0 = Sl[qx], w1 = Sl[Q.y];
+        Sl[px] = a00 * v0 + a01 * v1; Sl[P.y] = a10 * v0 + a11 * v1;
+        if (o2 != o) { Sl[qx] = a00 * w0 + a01 * w1; Sl[Q.y] = a10 * w0 + a11 * w1; }
+      }
+    }
+    return;
+  }
   for (int o = warp; o < cnt; o += 2 * nw) {
     const int o2 = (o + nw < cnt) ? o + nw : o;          // second operator of this iteration (same as the first if there is none)
     const bool two = o2 != o;
@@ -144,13 +159,13 @@ __global__ void __launch_bounds__(256) k_apply_ops(T* __restrict__ M, long sM, i
   const int8_t* fbase = fields ? fields + (long)chain * Ltrot * n_opv : nullptr;
 
   // descriptor prefetch registers and the cursor (slice, chunk within the slice) of the NEXT fetch
-  int4 rP = make_int4(0, 0, 0, 0); T rM[MPT]; int rcnt = 0;
+  int4 rP = make_int4(0, 0, 0, 0); T rM[MPT]; int rcnt = 0; bool runi = false;
   int f_sl = 0, f_r = 0;
   auto fetch = [&]() {
     const bool second = f_r >= nch0;
     const OpListDev& L = second ? Lb : La;
     const int c = second ? f_r - nch0 : f_r;
-    const int a0 = L.level_start[c]; rcnt = L.level_start[c + 1] - a0;
+    const int a0 = L.level_start[c]; rcnt = L.level_start[c + 1] - a0; runi = L.uniform[c] != 0;
     const int nt = (dir > 0) ? nt_a + f_sl : nt_b - f_sl;
     const int8_t* fld = ((second ? uf1 : uf0) && fbase) ? fbase + (nt - 1) * n_opv : nullptr;
     if (tid < rcnt) {
@@ -182,14 +197,14 @@ __global__ void __launch_bounds__(256) k_apply_ops(T* __restrict__ M, long sM, i
   } else {
     if (lane < pw) { const T* src = M + v0 + lane; for (int i = warp; i < N; i += nw) S[i * ldp + lane] = src[(long)i * N]; }
   }
-  int cnt_cur = rcnt;
+  int cnt_cur = rcnt; bool uni_cur = runi;
   if (total > 0) commit(0);
   __syncthreads();
   for (int t = 0; t < total; ++t) {
     if (t + 1 < total) fetch();
     const int buf = t & 1;
-    ops_process_chunk<T, LK>(S, lane < pw, cnt_cur, dPb + buf * OPS_CH, dMb + buf * OPS_CH * ms);
-    if (t + 1 < total) { commit(buf ^ 1); cnt_cur = rcnt; }
+    ops_process_chunk<T, LK>(S, lane < pw, cnt_cur, dPb + buf * OPS_CH, dMb + buf * OPS_CH * ms, uni_cur);
+    if (t + 1 < total) { commit(buf ^ 1); cnt_cur = rcnt; uni_cur = runi; }
     __syncthreads();
   }
   // ---- write back
