@@ -525,3 +525,35 @@ def test_ed_energy_two_site_gpu():
     ob = g.obs()
     assert abs(ob[2] / ob[0] - 2.0) < 0.02           # half filling: <N> = 2 (particle-hole symmetry), accumulated on the device over all slices
     g.close()
+
+
+@pytest.mark.gpu
+def test_first_sweep_config3_baseline_size():
+    """BASELINE configs[2] size (Hubbard 16x16, beta = 10, N_dim = 256, 51200 decisions per chain-sweep): the accept/reject sequence of
+    the first sweep is identical to the oracle's, the fields agree bit for bit, the freshly recomputed G agrees to 1e-10 and the
+    precision monitors (Control_PrecisionG) are of the same size as the oracle's (the windowed pivoting costs no accuracy)."""
+    import threading
+    model = config3(); seeds = SEEDS[:2]; C = len(seeds)
+    g = AlfB200(model, n_chains=C, nwrap=10); g.set_seeds(seeds); g.fields_set(); g.init_sweep(); g.accept_log(1)
+    orcs = []
+    for s in seeds:
+        o = Oracle(model, nwrap=10); o.ranset(s); o.fields_set(); orcs.append(o)
+
+    def work(o):
+        o.init(); o.log(True); o.sweep(0)
+    th = [threading.Thread(target=work, args=(o,)) for o in orcs]
+    [t.start() for t in th]; [t.join() for t in th]
+    g.sweep(1, 0)
+    log = g.get_accept_log(); f = g.get_fields(); ph = g.phase(); xmax_o = 0.0
+    for c, o in enumerate(orcs):
+        acc, _ = o.get_log()
+        assert acc.size == 2 * model.Ltrot * model.n_opv == log.shape[1]
+        assert np.array_equal(acc, log[c]), f"chain {c}: first mismatch at decision {int(np.argmax(acc != log[c]))}"
+        assert np.array_equal(f[c], o.get_fields())
+        for nf in (1, 2):
+            assert relF(g.green(c, nf), o.green(nf)) < TOL_G
+        assert abs(ph[c] - o.phase()) < 1e-9
+        xmax_o = max(xmax_o, o.control()["XMAXG"])
+    cg = g.control()
+    assert cg["XMAXG"] < 10 * xmax_o + 1e-9 and cg["nan"] == 0 and cg["unstable"] == 0
+    g.close()
