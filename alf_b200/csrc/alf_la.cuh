@@ -33,6 +33,12 @@ __global__ void __launch_bounds__(256) k_gemm(int M, int N, int K, const T* __re
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
   const int m0 = tm * GEMM_BM, n0 = tn * GEMM_BN;
   constexpr bool kDmma = std::is_same<T, double>::value;     // real: FP64 tensor cores, warp tile 16 x 32 (2 x 4 fragments)
+  constexpr bool kCplxDmma = !kDmma;                          // complex: the same tiling on split real / imaginary accumulators
+  double cre[2][4][2], cim[2][4][2];
+#pragma unroll
+  for (int ia = 0; ia < 2; ++ia)
+#pragma unroll
+    for (int ib = 0; ib < 4; ++ib) { cre[ia][ib][0] = cre[ia][ib][1] = 0.0; cim[ia][ib][0] = cim[ia][ib][1] = 0.0; }
   const int lane = tid & 31, warp = tid >> 5, fg = lane >> 2, fq = lane & 3;
   const int wm = (warp & 3) * 16, wn = (warp >> 2) * 32;
   T acc[4][4];
@@ -83,7 +89,24 @@ __global__ void __launch_bounds__(256) k_gemm(int M, int N, int K, const T* __re
       }
     }
     __syncthreads();
-    if constexpr (kDmma) {
+    if constexpr (kCplxDmma) {
+      // complex product as four real DMMA products per fragment pair: re += ar br - ai bi ; im += ar bi + ai br
+#pragma unroll
+      for (int ks = 0; ks < GEMM_BK / 4; ++ks) {
+        cplx a[2], bb[4];
+#pragma unroll
+        for (int ia = 0; ia < 2; ++ia) a[ia] = As[4 * ks + fq][wm + 8 * ia + fg];
+#pragma unroll
+        for (int ib = 0; ib < 4; ++ib) bb[ib] = Bs[4 * ks + fq][wn + 8 * ib + fg];
+#pragma unroll
+        for (int ia = 0; ia < 2; ++ia)
+#pragma unroll
+          for (int ib = 0; ib < 4; ++ib) {
+            dmma884(cre[ia][ib][0], cre[ia][ib][1], a[ia].x, bb[ib].x); dmma884(cre[ia][ib][0], cre[ia][ib][1], -a[ia].y, bb[ib].y);
+            dmma884(cim[ia][ib][0], cim[ia][ib][1], a[ia].x, bb[ib].y); dmma884(cim[ia][ib][0], cim[ia][ib][1], a[ia].y, bb[ib].x);
+          }
+      }
+    } else if constexpr (kDmma) {
       // acc[2*ia + (ib >> 1)][2 * (ib & 1) + h] <-> C(wm + 8 ia + fg, wn + 8 ib + 2 fq + h)
 #pragma unroll
       for (int ks = 0; ks < GEMM_BK / 4; ++ks) {
@@ -113,7 +136,17 @@ __global__ void __launch_bounds__(256) k_gemm(int M, int N, int K, const T* __re
     }
     __syncthreads();
   }
-  if constexpr (kDmma) {
+  if constexpr (kCplxDmma) {
+#pragma unroll
+    for (int ia = 0; ia < 2; ++ia)
+#pragma unroll
+      for (int ib = 0; ib < 4; ++ib)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int gm = m0 + wm + 8 * ia + fg, gn = n0 + wn + 8 * ib + 2 * fq + h;
+          if (gm < M && gn < N) C[gm + (long)gn * ldc] = make_<T>(cre[ia][ib][h], cim[ia][ib][h]);
+        }
+  } else if constexpr (kDmma) {
 #pragma unroll
     for (int ia = 0; ia < 2; ++ia)
 #pragma unroll
@@ -530,6 +563,125 @@ __global__ void __launch_bounds__(512) k_trsm_blk(const double* __restrict__ R, 
     __syncthreads();
   }
   for (int e = tid; e < n * TRSMB_CW; e += nthr) {
+    const int i = e % n, c = e / n;
+    if (c0 + c < nrhs) B[i + (long)(c0 + c) * ldb] = Xs[i + c * ldx];
+  }
+}
+
+// ---- complex variant of the blocked solve: 16 right-hand sides per CTA, complex products as four real DMMA products
+#define TRSMB_CWC 16
+template <int LOWER>
+__global__ void __launch_bounds__(32) k_tri_inv_blocks_c(const cplx* __restrict__ R, int ldr, long sR, int n, cplx* __restrict__ Rinv, long sI) {
+  __shared__ cplx Rs[32][33];
+  __shared__ cplx Xs[32][33];
+  const int kb = blockIdx.x, b = blockIdx.y, lane = threadIdx.x, k0 = kb * 32;
+  R += (long)b * sR; Rinv += (long)b * sI + (long)kb * 1024;
+  for (int c = 0; c < 32; ++c) {
+    const int i = k0 + lane, j = k0 + c;
+    cplx v = (lane == c) ? cplx(1.0, 0.0) : cplx(0.0, 0.0);
+    if (i < n && j < n && (LOWER ? (i >= j) : (i <= j))) v = R[i + (long)j * ldr];
+    Rs[lane][c] = v;
+  }
+  for (int k = 0; k < 32; ++k) Xs[k][lane] = cplx(0.0, 0.0);
+  __syncwarp();
+  const int j = lane;
+  if (!LOWER) {
+    for (int i = 31; i >= 0; --i) {
+      cplx s = (i == j) ? cplx(1.0, 0.0) : cplx(0.0, 0.0);
+      for (int k = i + 1; k < 32; ++k) s = s - Rs[i][k] * Xs[k][j];
+      Xs[i][j] = (i <= j) ? s / Rs[i][i] : cplx(0.0, 0.0);
+    }
+  } else {
+    for (int i = 0; i < 32; ++i) {
+      cplx s = (i == j) ? cplx(1.0, 0.0) : cplx(0.0, 0.0);
+      for (int k = 0; k < i; ++k) s = s - Rs[i][k] * Xs[k][j];
+      Xs[i][j] = (i >= j) ? s / Rs[i][i] : cplx(0.0, 0.0);
+    }
+  }
+  __syncwarp();
+  for (int c = 0; c < 32; ++c) Rinv[lane + c * 32] = Xs[lane][c];
+}
+
+__device__ __forceinline__ void cmma(double (&re)[2], double (&im)[2], cplx a, cplx b) {
+  dmma884(re[0], re[1], a.x, b.x); dmma884(re[0], re[1], -a.y, b.y);
+  dmma884(im[0], im[1], a.x, b.y); dmma884(im[0], im[1], a.y, b.x);
+}
+
+template <int LOWER>
+__global__ void __launch_bounds__(512) k_trsm_blk_c(const cplx* __restrict__ R, int ldr, long sR, const cplx* __restrict__ Rinv, long sI,
+                                                    cplx* __restrict__ B, int ldb, long sB, int n, int nrhs, const double* __restrict__ dinv, long sD) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  cplx* Xs = reinterpret_cast<cplx*>(smem_raw);          // [TRSMB_CWC][ldx]
+  const int b = blockIdx.y, tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = nthr >> 5;
+  const int g = lane >> 2, q = lane & 3;
+  R += (long)b * sR; Rinv += (long)b * sI; B += (long)b * sB;
+  if (dinv) dinv += (long)b * sD;
+  const int np = (n + 31) & ~31, nb = np >> 5, ldx = np + 1;
+  const int c0 = blockIdx.x * TRSMB_CWC;
+  for (int e = tid; e < np * TRSMB_CWC; e += nthr) {
+    const int i = e % np, c = e / np;
+    cplx v = cplx(0.0, 0.0);
+    if (i < n && c0 + c < nrhs) { v = B[i + (long)(c0 + c) * ldb]; if (dinv) v = v * (1.0 / dinv[i]); }
+    Xs[i + c * ldx] = v;
+  }
+  __syncthreads();
+  for (int s = 0; s < nb; ++s) {
+    const int kb = LOWER ? s : nb - 1 - s, k0 = kb * 32;
+    cplx bf[8][2];
+#pragma unroll
+    for (int ks = 0; ks < 8; ++ks)
+#pragma unroll
+      for (int cb = 0; cb < 2; ++cb) bf[ks][cb] = Xs[(k0 + 4 * ks + q) + (8 * cb + g) * ldx];
+    double are[2][2], aim[2][2];
+    if (warp < 4) {
+      cplx af[8];
+      const cplx* ri = Rinv + (long)kb * 1024 + (8 * warp + g);
+#pragma unroll
+      for (int ks = 0; ks < 8; ++ks) af[ks] = ri[(4 * ks + q) * 32];
+#pragma unroll
+      for (int cb = 0; cb < 2; ++cb) { are[cb][0] = are[cb][1] = 0.0; aim[cb][0] = aim[cb][1] = 0.0; }
+#pragma unroll
+      for (int ks = 0; ks < 8; ++ks)
+#pragma unroll
+        for (int cb = 0; cb < 2; ++cb) cmma(are[cb], aim[cb], af[ks], bf[ks][cb]);
+    }
+    __syncthreads();
+    if (warp < 4) {
+#pragma unroll
+      for (int cb = 0; cb < 2; ++cb) {
+        Xs[(k0 + 8 * warp + g) + (8 * cb + 2 * q) * ldx] = cplx(are[cb][0], aim[cb][0]);
+        Xs[(k0 + 8 * warp + g) + (8 * cb + 2 * q + 1) * ldx] = cplx(are[cb][1], aim[cb][1]);
+      }
+    }
+    __syncthreads();
+    if (s == nb - 1) break;
+#pragma unroll
+    for (int ks = 0; ks < 8; ++ks)
+#pragma unroll
+      for (int cb = 0; cb < 2; ++cb) bf[ks][cb] = Xs[(k0 + 4 * ks + q) + (8 * cb + g) * ldx];
+    const int r_lo = LOWER ? (k0 + 32) : 0, r_hi = LOWER ? np : k0;
+    for (int i0 = r_lo + 8 * warp; i0 < r_hi; i0 += 8 * nw) {
+      cplx af[8];
+      const int i = i0 + g;
+#pragma unroll
+      for (int ks = 0; ks < 8; ++ks) { const int k = k0 + 4 * ks + q; af[ks] = (i < n && k < n) ? -R[i + (long)k * ldr] : cplx(0.0, 0.0); }
+#pragma unroll
+      for (int cb = 0; cb < 2; ++cb) {
+        const cplx x0 = Xs[i + (8 * cb + 2 * q) * ldx], x1 = Xs[i + (8 * cb + 2 * q + 1) * ldx];
+        are[cb][0] = x0.x; aim[cb][0] = x0.y; are[cb][1] = x1.x; aim[cb][1] = x1.y;
+      }
+#pragma unroll
+      for (int ks = 0; ks < 8; ++ks)
+#pragma unroll
+        for (int cb = 0; cb < 2; ++cb) cmma(are[cb], aim[cb], af[ks], bf[ks][cb]);
+#pragma unroll
+      for (int cb = 0; cb < 2; ++cb) {
+        Xs[i + (8 * cb + 2 * q) * ldx] = cplx(are[cb][0], aim[cb][0]); Xs[i + (8 * cb + 2 * q + 1) * ldx] = cplx(are[cb][1], aim[cb][1]);
+      }
+    }
+    __syncthreads();
+  }
+  for (int e = tid; e < n * TRSMB_CWC; e += nthr) {
     const int i = e % n, c = e / n;
     if (c0 + c < nrhs) B[i + (long)(c0 + c) * ldb] = Xs[i + c * ldx];
   }

@@ -60,7 +60,7 @@ struct LaWork {
   T* W[4] = {nullptr, nullptr, nullptr, nullptr};
   T* tau = nullptr; int* jpvt = nullptr; double* Dq = nullptr; QrOut* qrout = nullptr; cplx* sc_phase = nullptr; cplx* sc_beta = nullptr;
   T* Tbuf = nullptr;      // compact-WY factors of the blocked QR: [matrix][panel][QRB_NB x QRB_NB]
-  double* Rinv = nullptr; // inverted 32 x 32 diagonal blocks of the blocked triangular solve: [matrix][(N + 32) * 32]
+  T* Rinv = nullptr;      // inverted 32 x 32 diagonal blocks of the blocked triangular solve: [matrix][(N + 32) * 32]
   long sRinv() const { return (long)(N + 32) * 32; }
   long n2() const { return (long)N * N; }
   void alloc(int n, int nm, cudaStream_t s) {
@@ -70,7 +70,7 @@ struct LaWork {
     CK(cudaMalloc(&Dq, sizeof(double) * (long)N * NM)); CK(cudaMalloc(&qrout, sizeof(QrOut) * NM));
     CK(cudaMalloc(&sc_phase, sizeof(cplx) * NM)); CK(cudaMalloc(&sc_beta, sizeof(cplx) * NM));
     CK(cudaMalloc(&Tbuf, sizeof(T) * (size_t)(N + 32) * 32 * NM));
-    CK(cudaMalloc(&Rinv, sizeof(double) * (size_t)(N + 32) * 32 * NM));
+    CK(cudaMalloc(&Rinv, sizeof(T) * (size_t)(N + 32) * 32 * NM));
   }
   void release() {
     for (int i = 0; i < 4; ++i) if (W[i]) cudaFree(W[i]);
@@ -139,14 +139,29 @@ static void launch_trsm_blk(cudaStream_t st, const double* R, int ldr, long sR, 
   const int nthr = (2 * (smem + 1024) <= 227 * 1024) ? 256 : 512;      // one resident CTA per SM only: give it 16 warps
   KL(KC_TRSM, st, k_trsm_blk<LOWER><<<dim3((nrhs + TRSMB_CW - 1) / TRSMB_CW, batch), nthr, smem, st>>>(R, ldr, sR, rinv, sI, B, ldb, sB, n, nrhs, dinv, sD));
 }
+template <int LOWER>
+static void launch_trsm_blk_c(cudaStream_t st, const cplx* R, int ldr, long sR, cplx* B, int ldb, long sB, int n, int nrhs, const double* dinv, long sD,
+                              cplx* rinv, long sI, int batch) {
+  const int np = (n + 31) & ~31, nb = np / 32;
+  count_flops(KC_TRSM, 4.0 * n * n * nrhs * batch);
+  const size_t smem = sizeof(cplx) * (size_t)(np + 1) * TRSMB_CWC;
+  KL(KC_TRSM, st, k_tri_inv_blocks_c<LOWER><<<dim3(nb, batch), 32, 0, st>>>(R, ldr, sR, n, rinv, sI));
+  CK(cudaFuncSetAttribute(k_trsm_blk_c<LOWER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int nthr = (2 * (smem + 1024) <= 227 * 1024) ? 256 : 512;
+  KL(KC_TRSM, st, k_trsm_blk_c<LOWER><<<dim3((nrhs + TRSMB_CWC - 1) / TRSMB_CWC, batch), nthr, smem, st>>>(R, ldr, sR, rinv, sI, B, ldb, sB, n, nrhs, dinv, sD));
+}
 static inline bool la_force_old_trsm() { static int v = -1; if (v < 0) v = getenv("ALF_B200_OLD_TRSM") ? 1 : 0; return v == 1; }
 
 template <typename T, int LOWER = 0>
 static void launch_trsm(cudaStream_t st, const T* R, int ldr, long sR, T* B, int ldb, long sB, int n, int nrhs, const double* dinv, long sD, int batch,
-                        double* rinv = nullptr, long sI = 0) {
+                        T* rinv = nullptr, long sI = 0) {
   if constexpr (std::is_same<T, double>::value) {
     if (rinv && !la_force_old_trsm() && sizeof(double) * (size_t)ld_pad((n + 31) & ~31) * TRSMB_CW <= 220 * 1024) {
       launch_trsm_blk<LOWER>(st, R, ldr, sR, B, ldb, sB, n, nrhs, dinv, sD, rinv, sI, batch); return;
+    }
+  } else {
+    if (rinv && !la_force_old_trsm() && sizeof(cplx) * (size_t)(((n + 31) & ~31) + 1) * TRSMB_CWC <= 220 * 1024) {
+      launch_trsm_blk_c<LOWER>(st, R, ldr, sR, B, ldb, sB, n, nrhs, dinv, sD, rinv, sI, batch); return;
     }
   }
   dim3 grid((nrhs + TRSM_COLS - 1) / TRSM_COLS, batch);

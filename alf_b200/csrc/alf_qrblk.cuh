@@ -43,19 +43,29 @@ __device__ __forceinline__ void blk_gemm(int M, int N, int K, const double* __re
     if (ACC) { cp[0] += alpha * c0; cp[ldc] += alpha * c1; } else { cp[0] = alpha * c0; cp[ldc] = alpha * c1; }
   }
 }
-// complex fallback (plain FMA; the headline models are real)
+// complex: the same 8 x 8 output blocks, each complex product as four real DMMA products on split accumulators
 template <int TA, int ACC>
 __device__ __forceinline__ void blk_gemm(int M, int N, int K, const cplx* __restrict__ A, int lda, const cplx* __restrict__ B, int ldb,
                                          cplx* __restrict__ C, int ldc, double alpha) {
-  for (int e = threadIdx.x; e < M * N; e += blockDim.x) {
-    const int i = e % M, j = e / M;
-    cplx s = cplx(0.0, 0.0);
-    if (TA) for (int k = 0; k < K; ++k) fmac_(s, A[k + (long)i * lda], B[k + (long)j * ldb]);
-    else for (int k = 0; k < K; ++k) fma_(s, A[i + (long)k * lda], B[k + (long)j * ldb]);
-    if (ACC) C[i + (long)j * ldc] = C[i + (long)j * ldc] + alpha * s; else C[i + (long)j * ldc] = alpha * s;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  const int g = lane >> 2, q = lane & 3;
+  const int mb = M >> 3, nb = N >> 3;
+  for (int blk = warp; blk < mb * nb; blk += nw) {
+    const int i0 = (blk % mb) * 8, j0 = (blk / mb) * 8;
+    double r0 = 0.0, r1 = 0.0, m0 = 0.0, m1 = 0.0;
+    const cplx* bp = B + (long)(j0 + g) * ldb + q;
+    for (int k0 = 0; k0 < K; k0 += 4) {
+      cplx a = TA ? A[(long)(i0 + g) * lda + q + k0] : A[(i0 + g) + (long)(q + k0) * lda];
+      if (TA) a.y = -a.y;                                 // op(A) = A^H
+      const cplx b = bp[k0];
+      dmma884(r0, r1, a.x, b.x); dmma884(r0, r1, -a.y, b.y);
+      dmma884(m0, m1, a.x, b.y); dmma884(m0, m1, a.y, b.x);
+    }
+    cplx* cp = C + (i0 + g) + (long)(j0 + 2 * q) * ldc;
+    if (ACC) { cp[0] = cp[0] + cplx(alpha * r0, alpha * m0); cp[ldc] = cp[ldc] + cplx(alpha * r1, alpha * m1); }
+    else { cp[0] = cplx(alpha * r0, alpha * m0); cp[ldc] = cplx(alpha * r1, alpha * m1); }
   }
 }
-
 
 // Shared-memory footprint (bytes) of the blocked kernels for an m-row matrix: V panel, column tile, W, W2, T, reflector, norms, ints.
 template <typename T>
