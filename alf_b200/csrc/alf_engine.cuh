@@ -271,7 +271,13 @@ struct Engine : EngineBase {
   std::vector<void*> owned;     // device allocations of the op lists
   bool dense_t = false; T* d_dense[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // fwd, inv, c, half, halfinv (N*N*F each)
   int KD = 16; size_t upd_smem = 0; int ops_lk = 0; size_t ops_smem = 0;   // ops_lk = log2 of the largest small-operator dimension
-  bool fast_upd = false; int KDf = 0, ldxf = 0, iptf = 1; size_t fast_smem = 0;   // k_wrapgr_fast (all vertices diagonal, k = 1)
+  bool fast_upd = false; int KDf = 0, ldxf = 0, iptf = 1; size_t fast_smem = 0;   // k_wrapgr_fast (groups of diagonal / diagonalisable vertices)
+  // The vertices of a slice are visited in GROUPS of consecutive vertices with pairwise disjoint supports:
+  //   kind 1: diagonal single-site vertices (k = 1)                        -> windowed fast kernel
+  //   kind 2: k = 2 vertices, rotated as a whole into their eigenbasis      -> fast kernel in pair mode between two op-list rotations
+  //   kind 0: anything else (k > 2, repeated sites)                         -> per-visit kernel k_wrapgr
+  struct VGroup { int n0 = 0, cnt = 0, kind = 0; OpListDev rot[4][ALF_FMAX]; };   // rot: in-left U^H, in-right U, out-left U, out-right U^H
+  std::vector<VGroup> groups;
   // tau_m work
   T *GT0 = nullptr, *G0T = nullptr, *G00 = nullptr, *GTT = nullptr, *TMPG = nullptr; UdvDev<T> udvr2;
   // projective algorithm
@@ -326,29 +332,67 @@ struct Engine : EngineBase {
     upd_smem = per_kd * KD + fixed;
     CK(cudaFuncSetAttribute(k_wrapgr<T, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)upd_smem));
     CK(cudaFuncSetAttribute(k_wrapgr<T, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)upd_smem));
-    // fast slice kernel: every vertex is a diagonal single-site operator with a discrete field
-    fast_upd = M > 0;
-    for (auto& o : h->opv) if (!(o.N == 1 && o.nnz == 1 && o.diag && (o.type == 1 || o.type == 2))) fast_upd = false;
-    for (int f = 0; f < F && fast_upd; ++f) {      // every site carries at most one vertex (its DL/DR entries are 1 until its own visit)
-      std::vector<char> seen(N, 0);
-      for (int n = 0; n < M; ++n) { int p = h->opv[n + (size_t)M * f].P[0]; if (seen[p]) fast_upd = false; seen[p] = 1; }
-    }
-    if (getenv("ALF_B200_GENERIC_UPDATE")) fast_upd = false;
-    if (fast_upd) {
-      ldxf = N; while (ldxf % 16 != 4) ++ldxf;
-      const size_t fixedf = (size_t)(2 * F * N + 6 * F * M + F * ALF_WIN * (ALF_WIN + 1) + 2 * ALF_WIN * F * ALF_WIN + ALF_WIN * F) * sizeof(T) + (size_t)2 * M * 8 + (size_t)F * M * 4 + (size_t)3 * M + 64;
-      const size_t perkd = (size_t)2 * F * ldxf * sizeof(T);
-      const size_t avail = 227 * 1024 - 1024;
-      if (fixedf + 4 * perkd > avail || F * N > 4 * 512) fast_upd = false;
-      else {
-        KDf = (int)((avail - fixedf) / perkd); KDf = (KDf / 4) * 4; if (KDf > 64) KDf = 64;
-        if (const char* e = getenv("ALF_B200_KD")) { int v = atoi(e); if (v >= 4 && v <= KDf) KDf = (v / 4) * 4; }
-        fast_smem = fixedf + perkd * KDf;
-        iptf = (F * N + 511) / 512; if (iptf > 1) iptf = 4;
-#define FAST_ATTR(IPT) do { CK(cudaFuncSetAttribute(k_wrapgr_fast<T, 1, IPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast_smem)); \
-                            CK(cudaFuncSetAttribute(k_wrapgr_fast<T, 0, IPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast_smem)); } while (0)
-        if (iptf == 1) FAST_ATTR(1); else FAST_ATTR(4);
+    // vertex groups (see VGroup): greedy over n = 1 .. M
+    {
+      auto kind_of = [&](int n) {
+        int kd = -1;
+        for (int f = 0; f < F; ++f) {
+          const HostOp& o = h->opv[n + (size_t)M * f]; int kf = 0;
+          if (o.type == 1 || o.type == 2) {
+            if (o.N == 1 && o.nnz == 1 && o.diag) kf = 1;
+            else if (o.N == 2 && o.nnz >= 1 && o.nnz <= 2) kf = 2;
+          }
+          if (kd < 0) kd = kf; else if (kd != kf) kd = 0;
+        }
+        if (getenv("ALF_B200_GENERIC_UPDATE")) kd = 0;
+        return kd;
+      };
+      std::vector<std::vector<char>> seen(F, std::vector<char>(N, 0));
+      for (int n = 0; n < M; ++n) {
+        const int kd = kind_of(n); bool clash = false;
+        for (int f = 0; f < F; ++f) { const HostOp& o = h->opv[n + (size_t)M * f]; for (int a = 0; a < o.N; ++a) if (seen[f][o.P[a]]) clash = true; }
+        if (groups.empty() || groups.back().kind != kd || (kd != 0 && clash)) {
+          VGroup g; g.n0 = n; g.kind = kd; groups.push_back(g);
+          for (int f = 0; f < F; ++f) std::fill(seen[f].begin(), seen[f].end(), 0);
+        }
+        groups.back().cnt++;
+        for (int f = 0; f < F; ++f) { const HostOp& o = h->opv[n + (size_t)M * f]; for (int a = 0; a < o.N; ++a) seen[f][o.P[a]] = 1; }
+      }
+      int mv_max = 0;                               // pseudo-visits of the largest fast group (sizes the kernel's per-visit tables)
+      for (auto& g : groups) if (g.kind) mv_max = std::max(mv_max, g.cnt * g.kind);
+      fast_upd = mv_max > 0;
+      if (fast_upd) {
+        ldxf = N; while (ldxf % 16 != 4) ++ldxf;
+        const size_t Mv = mv_max;
+        const size_t fixedf = (size_t)(2 * F * N + 6 * F * Mv + F * ALF_WIN * (ALF_WIN + 1) + 2 * ALF_WIN * F * ALF_WIN + ALF_WIN * F) * sizeof(T) + (size_t)2 * Mv * 8 + (size_t)F * Mv * 4 + (size_t)3 * Mv + 64;
+        const size_t perkd = (size_t)2 * F * ldxf * sizeof(T);
+        const size_t avail = 227 * 1024 - 1024;
+        if (fixedf + 4 * perkd > avail || F * N > 4 * 512) fast_upd = false;
+        else {
+          KDf = (int)((avail - fixedf) / perkd); KDf = (KDf / 4) * 4; if (KDf > 64) KDf = 64;
+          if (const char* e = getenv("ALF_B200_KD")) { int v = atoi(e); if (v >= 4 && v <= KDf) KDf = (v / 4) * 4; }
+          fast_smem = fixedf + perkd * KDf;
+          iptf = (F * N + 511) / 512; if (iptf > 1) iptf = 4;
+#define FAST_ATTR(IPT, PR) do { CK(cudaFuncSetAttribute(k_wrapgr_fast<T, 1, IPT, PR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast_smem)); \
+                                CK(cudaFuncSetAttribute(k_wrapgr_fast<T, 0, IPT, PR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast_smem)); } while (0)
+          if (iptf == 1) { FAST_ATTR(1, 0); FAST_ATTR(1, 1); } else { FAST_ATTR(4, 0); FAST_ATTR(4, 1); }
 #undef FAST_ATTR
+        }
+      }
+      if (!fast_upd) for (auto& g : groups) g.kind = 0;
+      // basis rotations of the pair groups as op lists: left matrices act on rows P, "right" lists act on the transpose (alf_ops.cuh)
+      for (auto& g : groups) if (g.kind == 2) {
+        for (int f = 0; f < F; ++f) {
+          ListBuild il, ir, ol, orr;
+          for (int n = g.n0; n < g.n0 + g.cnt; ++n) {
+            const HostOp& o = h->opv[n + (size_t)M * f];
+            std::vector<cd> U(4), UH(4), UT(4), UC(4);
+            for (int a = 0; a < 2; ++a) for (int b = 0; b < 2; ++b) { const cd u = o.U[a + (size_t)b * 2]; U[a + b * 2] = u; UH[b + a * 2] = std::conj(u); UT[b + a * 2] = u; UC[a + b * 2] = std::conj(u); }
+            il.add(2, o.P.data(), -1, {UH}); ir.add(2, o.P.data(), -1, {UT});      // G <- U^H G U
+            ol.add(2, o.P.data(), -1, {U}); orr.add(2, o.P.data(), -1, {UC});      // G <- U G U^H
+          }
+          g.rot[0][f] = upload_list(il); g.rot[1][f] = upload_list(ir); g.rot[2][f] = upload_list(ol); g.rot[3][f] = upload_list(orr);
+        }
       }
     }
     // op-list kernel: panel of 32 columns (rows) + double-buffered operator descriptors
@@ -467,8 +511,9 @@ struct Engine : EngineBase {
   }
 
   // ---------------------------------------------------------------- op-list launches
-  void apply_ops(T* Mx, int side, int mode, int nt_a, int nt_b, int nvec = -1) {     // nvec: number of columns (side 0) / rows (side 1)
+  void apply_ops(T* Mx, int side, int mode, int nt_a, int nt_b, int nvec = -1, const ModelDev* mdo = nullptr) {     // nvec: number of columns (side 0) / rows (side 1)
     if (nvec < 0) nvec = N;
+    const ModelDev& md = mdo ? *mdo : this->md;
     dim3 grid((nvec + OPS_PW - 1) / OPS_PW, NM);
 #define OPS_LAUNCH(SD, LKV) KL(KC_OPS, st, k_apply_ops<T, SD, LKV><<<grid, 256, ops_smem, st>>>(Mx, n2, N, nvec, md, F, mode, nt_a, nt_b, h->d_fields, L, M))
     if (side == 0) { if (ops_lk == 0) OPS_LAUNCH(0, 0); else if (ops_lk == 1) OPS_LAUNCH(0, 1); else OPS_LAUNCH(0, 2); }
@@ -554,19 +599,35 @@ struct Engine : EngineBase {
     launch_update(0, ntau);
     mmthl(G); mmthr_m1(G);
   }
+  void rotate_group(const VGroup& g, bool in) {     // G <- U^H G U (in) / U G U^H (out) for all vertices of a pair group
+    ModelDev m2 = md;
+    for (int f = 0; f < F; ++f) { m2.lists[L_TL_FWD][f] = g.rot[in ? 0 : 2][f]; m2.lists[L_TR_FWD][f] = g.rot[in ? 1 : 3][f]; }
+    apply_ops(G, 0, MODE_TL_FWD, 0, 0, -1, &m2); apply_ops(G, 1, MODE_TR_FWD, 0, 0, -1, &m2);
+  }
   void launch_update(int up, int nt) {
     uint8_t* lg = nullptr;
     if (h->acclog_on && h->d_acclog && h->acclog_pos + M <= h->acclog_per_chain) { lg = h->d_acclog + (long)h->acclog_pos * C; h->acclog_pos += M; }
-    if (fast_upd) {
-#define FAST_LAUNCH(UPV, IPT) KL(KC_UPDATE, st, k_wrapgr_fast<T, UPV, IPT><<<C, 512, fast_smem, st>>>(G, N, F, h->n_sun, M, d_vops, ft, h->d_fields, L, nt, h->d_rng, h->d_phase, h->d_counters, KDf, ldxf, lg))
-      if (up) { if (iptf == 1) FAST_LAUNCH(1, 1); else FAST_LAUNCH(1, 4); }
-      else { if (iptf == 1) FAST_LAUNCH(0, 1); else FAST_LAUNCH(0, 4); }
+    int off = 0;
+    for (int gi = 0; gi < (int)groups.size(); ++gi) {
+      const VGroup& g = groups[up ? gi : (int)groups.size() - 1 - gi];
+      if (g.kind == 0) {
+        if (up) KL(KC_UPDATE, st, k_wrapgr<T, 1><<<C, 512, upd_smem, st>>>(G, N, F, h->n_sun, g.n0, g.cnt, M, off, d_vops, ft, h->d_fields, L, nt, h->d_rng, h->d_phase, h->d_counters, KD, lg, 0));
+        else KL(KC_UPDATE, st, k_wrapgr<T, 0><<<C, 512, upd_smem, st>>>(G, N, F, h->n_sun, g.n0, g.cnt, M, off, d_vops, ft, h->d_fields, L, nt, h->d_rng, h->d_phase, h->d_counters, KD, lg, 0));
+      } else {
+        if (g.kind == 2) rotate_group(g, true);
+#define FAST_LAUNCH(UPV, IPT, PR) KL(KC_UPDATE, st, k_wrapgr_fast<T, UPV, IPT, PR><<<C, 512, fast_smem, st>>>(G, N, F, h->n_sun, g.n0, g.cnt, M, off, d_vops, ft, h->d_fields, L, nt, h->d_rng, h->d_phase, h->d_counters, KDf, ldxf, lg))
+        if (g.kind == 1) {
+          if (up) { if (iptf == 1) FAST_LAUNCH(1, 1, 0); else FAST_LAUNCH(1, 4, 0); }
+          else { if (iptf == 1) FAST_LAUNCH(0, 1, 0); else FAST_LAUNCH(0, 4, 0); }
+        } else {
+          if (up) { if (iptf == 1) FAST_LAUNCH(1, 1, 1); else FAST_LAUNCH(1, 4, 1); }
+          else { if (iptf == 1) FAST_LAUNCH(0, 1, 1); else FAST_LAUNCH(0, 4, 1); }
+        }
 #undef FAST_LAUNCH
-      return;
+        if (g.kind == 2) rotate_group(g, false);
+      }
+      off += g.cnt;
     }
-    if (up) KL(KC_UPDATE, st, k_wrapgr<T, 1><<<C, 512, upd_smem, st>>>(G, N, F, h->n_sun, M, d_vops, ft, h->d_fields, L, nt, h->d_rng, h->d_phase, h->d_counters, KD, lg, 0));
-    else KL(KC_UPDATE, st, k_wrapgr<T, 0><<<C, 512, upd_smem, st>>>(G, N, F, h->n_sun, M, d_vops, ft, h->d_fields, L, nt, h->d_rng, h->d_phase, h->d_counters, KD, lg, 0));
-    CKL();
   }
 
   // main.F90:589-631

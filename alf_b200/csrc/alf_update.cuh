@@ -132,10 +132,11 @@ __device__ __forceinline__ void similarity_immediate(T* __restrict__ G0, int N, 
 
 // dynamic smem: X[F][KD][ldx], Y[F][KD][ldx], dl[F][N], dr[F][N], gdiag[F][N] (all T)
 template <typename T, int UP>
-__global__ void __launch_bounds__(512, 1) k_wrapgr(T* __restrict__ G, int N, int F, int n_sun, int n_opv, const VopDev<T>* __restrict__ vops,
+__global__ void __launch_bounds__(512, 1) k_wrapgr(T* __restrict__ G, int N, int F, int n_sun, int n0, int cnt, int n_opv, int log_off,
+                                                   const VopDev<T>* __restrict__ vops,
                                                    FieldTabDev ft, int8_t* __restrict__ fields, int Ltrot, int nt, uint64_t* __restrict__ rng,
                                                    cplx* __restrict__ phase, unsigned long long* __restrict__ counters, int KD,
-                                                   uint8_t* __restrict__ acclog, int propose_s0) {
+                                                   uint8_t* __restrict__ acclog, int propose_s0) {   // visits the vertices n0 .. n0 + cnt - 1 of the slice
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ UpdCtl ctl[2];
   __shared__ T gpp_s[ALF_FMAX][ALF_KMAX][ALF_KMAX];
@@ -156,8 +157,8 @@ __global__ void __launch_bounds__(512, 1) k_wrapgr(T* __restrict__ G, int N, int
   int nd = 0;
   __syncthreads();
 
-  for (int step = 0; step < n_opv; ++step) {
-    const int n = UP ? step : (n_opv - 1 - step);
+  for (int step = 0; step < cnt; ++step) {
+    const int n = UP ? n0 + step : (n0 + cnt - 1 - step);
     const VopDev<T>* op0 = vops + (long)n * F;
     const int k = op0->k, isdiag = op0->diag, type = op0->type;
     const int s_old = (int)fld[n];
@@ -261,8 +262,8 @@ __global__ void __launch_bounds__(512, 1) k_wrapgr(T* __restrict__ G, int N, int
             const double ar = abs_(rt);
             ph = ph * cplx(rt.x / ar, rt.y / ar);
           }
-          if (acclog) acclog[(long)chain * n_opv + step] = (uint8_t)acc;
-        } else if (acclog) acclog[(long)chain * n_opv + step] = 2;
+          if (acclog) acclog[(long)chain * n_opv + log_off + step] = (uint8_t)acc;
+        } else if (acclog) acclog[(long)chain * n_opv + log_off + step] = 2;
         cb->accept = acc; cb->s_new = s_new;
         if (acc) fld[n] = (int8_t)s_new;
       }
@@ -367,7 +368,7 @@ __global__ void __launch_bounds__(512, 1) k_wrapgr(T* __restrict__ G, int N, int
     phase[chain] = ph;
     counters[chain * 4 + 0] += n_prop;   // NC_up
     counters[chain * 4 + 1] += n_acc;    // ACC_up
-    counters[chain * 4 + 2] += (unsigned long long)n_opv;   // NC_eff_up
+    counters[chain * 4 + 2] += (unsigned long long)cnt;     // NC_eff_up
     counters[chain * 4 + 3] += n_acc;    // ACC_eff_up
   }
 }

@@ -111,10 +111,18 @@ __device__ __forceinline__ void upd_phase(cplx& ph, cplx rt) { const double ar =
 #define ALF_WIN 16          // visits per window
 #define ALF_CH 8            // accepted flips whose G0 column/row are in flight at once in the bulk phase
 
-template <typename T, int UP, int IPT>
-__global__ void __launch_bounds__(512, 1) k_wrapgr_fast(T* __restrict__ G, int N, int F, int n_sun, int M, const VopDev<T>* __restrict__ vops, FieldTabDev ft,
+// The kernel visits the vertices n0 .. n0 + cnt - 1 of the slice (a GROUP of vertices with pairwise disjoint supports; Mtot =
+// size(Op_V,1) is the stride of the field array and of the accept log, log_off the number of vertices visited before the group).
+// PAIR = 1: the vertices are k = 2 operators that are DIAGONAL in the basis the Green function has been rotated to (the caller
+// applies U^dagger . U of the whole group before and U . U^dagger after, alf_engine.cuh); each vertex then is a pair of
+// consecutive single-site "pseudo-visits": the Metropolis decision is taken once with the 2 x 2 determinant of
+// upgrade_mod.F90:178-188, the two rank-1 updates follow (second one with the G already updated by the first).
+template <typename T, int UP, int IPT, int PAIR>
+__global__ void __launch_bounds__(512, 1) k_wrapgr_fast(T* __restrict__ G, int N, int F, int n_sun, int n0, int cnt, int Mtot, int log_off,
+                                                        const VopDev<T>* __restrict__ vops, FieldTabDev ft,
                                                         int8_t* __restrict__ fields, int Ltrot, int nt, uint64_t* __restrict__ rng, cplx* __restrict__ phase,
                                                         unsigned long long* __restrict__ counters, int KD, int ldx, uint8_t* __restrict__ acclog) {
+  const int M = PAIR ? 2 * cnt : cnt;                 // pseudo-visits (one site each)
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ int win_nvis, win_nacc;
   __shared__ int acc_vis[ALF_WIN];
@@ -144,27 +152,29 @@ __global__ void __launch_bounds__(512, 1) k_wrapgr_fast(T* __restrict__ G, int N
   int8_t* st_type = st_snew + M;
 
   T* Gc = G + (long)chain * F * N * N;
-  int8_t* fld = fields + ((long)chain * Ltrot + (nt - 1)) * M;
+  int8_t* fld = fields + ((long)chain * Ltrot + (nt - 1)) * Mtot;
+  auto vertex_of = [&](int s) { const int pv = PAIR ? (s >> 1) : s; return UP ? n0 + pv : n0 + cnt - 1 - pv; };
   const int items = F * N;
 
   // ---- prologue A: field values, types, sites; DL = DR = 1
   for (int s = tid; s < M; s += nthr) {
-    const int n = UP ? s : (M - 1 - s);
+    const int n = vertex_of(s), a = PAIR ? (s & 1) : 0;
     st_sold[s] = fld[n]; st_type[s] = (int8_t)vops[(long)n * F].type;
-    for (int f = 0; f < F; ++f) st_p[f * M + s] = vops[(long)n * F + f].P[0];
+    for (int f = 0; f < F; ++f) st_p[f * M + s] = vops[(long)n * F + f].P[a];
   }
   for (int e = tid; e < items; e += nthr) { dl[e] = one_<T>(); dr[e] = one_<T>(); }
   __syncthreads();
   // ---- prologue B: the chain's random stream for this slice, in the reference's order
   if (tid == 0) {
     Xoshiro r; r.s0 = rng[chain * 4 + 0]; r.s1 = rng[chain * 4 + 1]; r.s2 = rng[chain * 4 + 2]; r.s3 = rng[chain * 4 + 3];
-    for (int s = 0; s < M; ++s) {
+    for (int s = 0; s < M; s += (PAIR ? 2 : 1)) {
       const int so = st_sold[s];
       int sn;
       if (st_type[s] == 1) sn = -so; else sn = ft.flip[so + 2][r.nranf(3)];      // Fields_mod.F90:173-217
       (void)r.ranf();                                                              // proposal draw: T0_proposal = 1.5 > ranf() always (Wrapgr_mod.F90:133)
       st_u[s] = r.ranf();                                                          // acceptance draw (upgrade_mod.F90:222)
       st_snew[s] = (int8_t)sn;
+      if (PAIR) { st_u[s + 1] = st_u[s]; st_snew[s + 1] = (int8_t)sn; }
     }
     rng[chain * 4 + 0] = r.s0; rng[chain * 4 + 1] = r.s1; rng[chain * 4 + 2] = r.s2; rng[chain * 4 + 3] = r.s3;
   }
@@ -186,11 +196,13 @@ __global__ void __launch_bounds__(512, 1) k_wrapgr_fast(T* __restrict__ G, int N
   __syncthreads();
   // ---- prologue C: per-visit tables
   for (int e = tid; e < F * M; e += nthr) {
-    const int f = e / M, s = e % M; const int n = UP ? s : (M - 1 - s);
+    const int f = e / M, s = e % M; const int n = vertex_of(s), a = PAIR ? (s & 1) : 0;
     const VopDev<T>* op = vops + (long)n * F + f;
     const int so = st_sold[s] + 2, sn = st_snew[s] + 2;
-    const T d = op->delta[0][so][sn], ea = op->expalpha[so][sn];
-    st_d[e] = d; st_c1[e] = (d + one_<T>()) * ea; st_c2[e] = d * ea; st_eold[e] = op->E_exp[0][so]; st_enew[e] = op->E_exp[0][sn];
+    const T d = op->delta[a][so][sn], ea = op->expalpha[so][sn];
+    st_d[e] = d; st_eold[e] = op->E_exp[a][so]; st_enew[e] = op->E_exp[a][sn];
+    if (PAIR) { st_c1[e] = ea; st_c2[e] = zero_<T>(); }                           // the pair's ratio is a 2 x 2 determinant times exp(g dphi alpha)
+    else { st_c1[e] = (d + one_<T>()) * ea; st_c2[e] = d * ea; }
     st_eoldi[e] = one_<T>() / st_eold[e];
     if (f == 0) { const int ty = st_type[s]; st_gr[s] = ft.gama[ty][sn] / ft.gama[ty][so]; }
   }
@@ -243,25 +255,42 @@ __global__ void __launch_bounds__(512, 1) k_wrapgr_fast(T* __restrict__ G, int N
     // ---- (b) one warp: the window's Metropolis decisions on the small block (Upgrade2 for rank-1 vertices).  This is the only
     // sequential part of the slice, so it is written for latency: per visit 1 shared load + a handful of dependent FP64 ops.
     if (warp == 0) {
-      int nacc = 0, v = 0;
+      int nacc = 0, v = 0, pair_acc = 0;
       for (; v < Wn && nacc < cap; ++v) {
         const int s = v0 + v;
         T g[ALF_FMAX];
-        T rfp = one_<T>();
-        for (int f = 0; f < F; ++f) { g[f] = Gw[(f * W + v) * LW + v]; rfp = rfp * (st_c1[f * M + s] - st_c2[f * M + s] * g[f]); }
-        T rtT = rfp;
-        for (int q = 1; q < n_sun; ++q) rtT = rtT * rfp;
-        rtT = rtT * st_gr[s];
-        const double weight = upd_weight(ph, rtT);
-        const int acc = (weight > st_u[s]) ? 1 : 0;
-        if (lane == 0) {
-          acc_flag[v] = (int8_t)acc;
-          if (acc) { fld[UP ? s : (M - 1 - s)] = st_snew[s]; acc_vis[nacc] = v; }
-          if (acclog) acclog[(long)chain * M + s] = (uint8_t)acc;
-        }
+        int acc;
+        const bool decide = !PAIR || !(v & 1);
+        if (PAIR && decide && nacc + 2 > cap) break;                 // both factors of a pair go into the same batch
+        for (int f = 0; f < F; ++f) g[f] = Gw[(f * W + v) * LW + v];
+        if (decide) {
+          T rfp = one_<T>();
+          if (!PAIR) { for (int f = 0; f < F; ++f) rfp = rfp * (st_c1[f * M + s] - st_c2[f * M + s] * g[f]); }
+          else {
+            for (int f = 0; f < F; ++f) {     // Mat(n,m) = delta_nm (1 + d_m) - d_m G(P_n, P_m); 2 x 2 determinant as in upgrade_mod.F90:178-188
+              const T d0 = st_d[f * M + s], d1 = st_d[f * M + s + 1];
+              const T m00 = (d0 + one_<T>()) - d0 * g[f], m11 = (d1 + one_<T>()) - d1 * Gw[(f * W + v + 1) * LW + v + 1];
+              const T m10 = -(d0 * Gw[(f * W + v + 1) * LW + v]), m01 = -(d1 * Gw[(f * W + v) * LW + v + 1]);
+              const T s1 = m00 * m11, s2 = m10 * m01;
+              const T D = (abs_(s1) > abs_(s2)) ? s1 * (one_<T>() - s2 / s1) : s2 * (s1 / s2 - one_<T>());
+              rfp = rfp * (D * st_c1[f * M + s]);
+            }
+          }
+          T rtT = rfp;
+          for (int q = 1; q < n_sun; ++q) rtT = rtT * rfp;
+          rtT = rtT * st_gr[s];
+          const double weight = upd_weight(ph, rtT);
+          acc = (weight > st_u[s]) ? 1 : 0;
+          pair_acc = acc;
+          if (lane == 0) {
+            acc_flag[v] = (int8_t)acc; if (PAIR) acc_flag[v + 1] = (int8_t)acc;
+            if (acc) fld[vertex_of(s)] = st_snew[s];
+            if (acclog) acclog[(long)chain * Mtot + log_off + (PAIR ? (s >> 1) : s)] = (uint8_t)acc;
+          }
+          if (acc) { n_acc++; upd_phase(ph, rtT); }
+        } else acc = pair_acc;
+        if (lane == 0 && acc) acc_vis[nacc] = v;
         if (acc) {
-          n_acc++;
-          upd_phase(ph, rtT);
           // the new factor on the window's sites (in the frame of this visit: UP applies Op_Wrapup N_type 1 to row / column v first),
           // then the rank-1 update of the entries that later visits of the window still read
           T yb[(ALF_FMAX * W + 31) / 32];
@@ -393,9 +422,9 @@ __global__ void __launch_bounds__(512, 1) k_wrapgr_fast(T* __restrict__ G, int N
   do_flush();
   if (tid == 0) {
     phase[chain] = ph;
-    counters[chain * 4 + 0] += (unsigned long long)M;   // NC_up
+    counters[chain * 4 + 0] += (unsigned long long)cnt; // NC_up
     counters[chain * 4 + 1] += n_acc;                   // ACC_up
-    counters[chain * 4 + 2] += (unsigned long long)M;   // NC_eff_up
+    counters[chain * 4 + 2] += (unsigned long long)cnt; // NC_eff_up
     counters[chain * 4 + 3] += n_acc;                   // ACC_eff_up
   }
 }
