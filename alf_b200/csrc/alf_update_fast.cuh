@@ -97,9 +97,55 @@ static __device__ __noinline__ void flush_g0(double* __restrict__ G0, int N, con
   for (int i = threadIdx.x; i < N; i += blockDim.x) { dl[i] = 1.0; dr[i] = 1.0; }
 }
 // complex: register-tiled FMA version of alf_update.cuh
+// complex: the same 32 x 16 warp tiles on split real / imaginary accumulators, every complex product as four real DMMA products
 static __device__ __noinline__ void flush_g0(cplx* __restrict__ G0, int N, const cplx* __restrict__ X, const cplx* __restrict__ Y, int ldx, int nd4,
-                                         cplx* __restrict__ dl, cplx* __restrict__ dr, int) {
-  flush_flavor<cplx>(G0, N, X, Y, ldx, nd4, dl, dr);
+                                         cplx* __restrict__ dl, cplx* __restrict__ dr, int rev) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  const int tm = (N + 31) / 32, tn = (N + 15) / 16, tiles = tm * tn;
+  const int g = lane >> 2, q = lane & 3;
+  for (int tt = warp; tt < tiles; tt += nw) {
+    const int t = rev ? tiles - 1 - tt : tt;
+    const int i0 = (t % tm) * 32, j0 = (t / tm) * 16;
+    double cr[4][2][2], ci[4][2][2];
+#pragma unroll
+    for (int b = 0; b < 2; ++b)
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int j = j0 + 8 * b + 2 * q + h; const cplx drj = (j < N) ? dr[j] : cplx(0.0, 0.0);
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+          const int i = i0 + 8 * a + g;
+          cplx v = cplx(0.0, 0.0);
+          if (i < N && j < N) v = (dl[i] * G0[i + (long)j * N]) * drj;
+          cr[a][b][h] = v.x; ci[a][b][h] = v.y;
+        }
+      }
+    for (int k0 = 0; k0 < nd4; k0 += 4) {
+      cplx av[4], bv[2];
+      const cplx* xk = X + (long)(k0 + q) * ldx; const cplx* yk = Y + (long)(k0 + q) * ldx;
+#pragma unroll
+      for (int a = 0; a < 4; ++a) { const int i = i0 + 8 * a + g; av[a] = (i < N) ? -xk[i] : cplx(0.0, 0.0); }
+#pragma unroll
+      for (int b = 0; b < 2; ++b) { const int j = j0 + 8 * b + g; bv[b] = (j < N) ? yk[j] : cplx(0.0, 0.0); }
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {
+          dmma884(cr[a][b][0], cr[a][b][1], av[a].x, bv[b].x); dmma884(cr[a][b][0], cr[a][b][1], -av[a].y, bv[b].y);
+          dmma884(ci[a][b][0], ci[a][b][1], av[a].x, bv[b].y); dmma884(ci[a][b][0], ci[a][b][1], av[a].y, bv[b].x);
+        }
+    }
+#pragma unroll
+    for (int b = 0; b < 2; ++b)
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int j = j0 + 8 * b + 2 * q + h;
+#pragma unroll
+        for (int a = 0; a < 4; ++a) { const int i = i0 + 8 * a + g; if (i < N && j < N) G0[i + (long)j * N] = cplx(cr[a][b][h], ci[a][b][h]); }
+      }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < N; i += blockDim.x) { dl[i] = cplx(1.0, 0.0); dr[i] = cplx(1.0, 0.0); }
 }
 
 // Weight = |Re(Phase R) / Re(Phase)| (upgrade_mod.F90:210); for real arithmetic Phase = +-1 and the weight is |R|.
