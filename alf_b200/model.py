@@ -348,7 +348,7 @@ def hubbard_chain(L: int, beta: float, dtau: float, U: float = 4.0, t: float = 1
 
 
 def kondo_square(L1: int, L2: int, beta: float, dtau: float = 0.1, t: float = 1.0, J: float = 2.0, Uf: float = 1.0,
-                 Uc: float = 0.0, symm: bool = True, N_SUN: int = 2) -> Model:
+                 Uc: float = 0.0, symm: bool = True, N_SUN: int = 2, jk_vertex: str = "hop") -> Model:
     """SU(N) Kondo lattice on the bilayer square lattice, Hamiltonian_Kondo_smod.F90:464-530: orbital 1 = conduction
     (hops), orbital 2 = f (no hopping); vertices U_f (k=1, imaginary g: Predefined_Int_U_SUN, Ham_V :497-505) and
     J_K (k=2 vertex, Predefined_Int_V_SUN with Ham_JK/2 for N_SUN=2, :507-514).  The conduction-layer hopping uses the
@@ -382,6 +382,8 @@ def kondo_square(L1: int, L2: int, beta: float, dtau: float = 0.1, t: float = 1.
         op = Op_make(2)
         op.P[0], op.P[1] = inv(I, 1), inv(I, 2)
         op.O[0, 1] = 1.0; op.O[1, 0] = 1.0
+        if jk_vertex == "bond_density":          # test variant: (c^dag + f^dag)(c + f), eigenvalues (2, 0): a k = 2 vertex with ONE non-zero eigenvalue
+            op.O[0, 0] = 1.0; op.O[1, 1] = 1.0
         op.g = np.sqrt(complex(dtau * (J / 2.0) / float(N_SUN), 0.0)); op.alpha = 0.0; op.type = 2
         Op_set(op); Op_V.append([op])
     return Model(name="Kondo", Ndim=Ndim, N_FL=1, N_SUN=N_SUN, Ltrot=Ltrot, Dtau=dtau, Symm=symm, Op_V=Op_V, Op_T=Op_T, latt=latt,

@@ -557,3 +557,21 @@ def test_first_sweep_config3_baseline_size():
     cg = g.control()
     assert cg["XMAXG"] < 10 * xmax_o + 1e-9 and cg["nan"] == 0 and cg["unstable"] == 0
     g.close()
+
+
+# ---------------------------------------------------------------------------------- slice-kernel variants
+@pytest.mark.gpu
+def test_sweep_k2_vertex_with_one_nonzero_eigenvalue():
+    """Pair mode of the fast slice kernel with N_non_zero = 1 < k = 2 (second rank-1 factor vanishes)."""
+    m = kondo_square(2, 2, 1.0, jk_vertex="bond_density")
+    assert any(op[0].N == 2 and op[0].N_non_zero == 1 for op in m.Op_V)
+    _run_parity(m, SEEDS[:2], nwrap=5, n_sweeps=1, check_udv=False)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("which", ["hubbard", "kondo"])
+def test_sweep_generic_slice_kernel(which, monkeypatch):
+    """ALF_B200_GENERIC_UPDATE=1 routes every vertex through the per-visit kernel k_wrapgr (the path of k > 2 vertices)."""
+    monkeypatch.setenv("ALF_B200_GENERIC_UPDATE", "1")
+    model = hubbard_square(4, 4, 1.0) if which == "hubbard" else kondo_square(2, 2, 1.0)
+    _run_parity(model, SEEDS[:2], nwrap=5, n_sweeps=1, check_udv=False)
