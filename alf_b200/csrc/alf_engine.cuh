@@ -790,9 +790,11 @@ struct Engine : EngineBase {
                         uint8_t* acc_out, int place_to) override {
     gm_alloc();
     const size_t np = (size_t)C * std::max(n_moves, 1), nl = np * std::max(maxlen, 1);
-    int *d_len = nullptr, *d_list = nullptr; int8_t* d_val = nullptr; double *d_t0 = nullptr, *d_s0 = nullptr; uint8_t* d_acc = nullptr;
-    CK(cudaMalloc(&d_len, sizeof(int) * np)); CK(cudaMalloc(&d_list, sizeof(int) * nl)); CK(cudaMalloc(&d_val, nl));
-    CK(cudaMalloc(&d_t0, sizeof(double) * np)); CK(cudaMalloc(&d_s0, sizeof(double) * np)); CK(cudaMalloc(&d_acc, np));
+    struct Scratch { void* p = nullptr; ~Scratch() { if (p) cudaFree(p); } };       // freed on every exit path, including exceptions
+    Scratch b_len, b_list, b_val, b_t0, b_s0, b_acc;
+    CK(cudaMalloc(&b_len.p, sizeof(int) * np)); CK(cudaMalloc(&b_list.p, sizeof(int) * nl)); CK(cudaMalloc(&b_val.p, nl));
+    CK(cudaMalloc(&b_t0.p, sizeof(double) * np)); CK(cudaMalloc(&b_s0.p, sizeof(double) * np)); CK(cudaMalloc(&b_acc.p, np));
+    int *d_len = (int*)b_len.p, *d_list = (int*)b_list.p; int8_t* d_val = (int8_t*)b_val.p; double *d_t0 = (double*)b_t0.p, *d_s0 = (double*)b_s0.p; uint8_t* d_acc = (uint8_t*)b_acc.p;
     if (n_moves > 0) {
       CK(cudaMemcpyAsync(d_len, len, sizeof(int) * np, cudaMemcpyHostToDevice, st)); CK(cudaMemcpyAsync(d_list, list0, sizeof(int) * nl, cudaMemcpyHostToDevice, st));
       CK(cudaMemcpyAsync(d_val, val, nl, cudaMemcpyHostToDevice, st)); CK(cudaMemcpyAsync(d_t0, t0, sizeof(double) * np, cudaMemcpyHostToDevice, st));
@@ -804,7 +806,6 @@ struct Engine : EngineBase {
                                                                n_moves, std::max(maxlen, 1), d_len, d_list, d_val, d_t0, d_s0, d_acc, place_to));
     if (acc_out && n_moves > 0) { CK(cudaMemcpyAsync(acc_out, d_acc, np, cudaMemcpyDeviceToHost, st)); }
     sync();
-    cudaFree(d_len); cudaFree(d_list); cudaFree(d_val); cudaFree(d_t0); cudaFree(d_s0); cudaFree(d_acc);
   }
 
   // PROPR / PROPRM1 (Prog/tau_m_mod.F90:215-263): A <- B(nt) A ;  A <- A B(nt)^-1

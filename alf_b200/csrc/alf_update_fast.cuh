@@ -1,4 +1,5 @@
-// Fast slice kernel for models whose interaction vertices are all diagonal single-site operators (k = 1: every Hubbard variant):
+// Fast slice kernel for GROUPS of interaction vertices with pairwise disjoint supports that are diagonal single-site operators
+// (k = 1: every Hubbard variant, Kondo U_f) or, in pair mode, k = 2 operators in their eigenbasis (Kondo J_K; see the kernel's header):
 // same semantics as k_wrapgr (alf_update.cuh) = the n-loop of WRAPGRUP / WRAPGRDO (Prog/Wrapgr_mod.F90:115-146, 191-237) with
 // Op_Wrapup/Op_Wrapdo (Prog/Operator_mod.F90:743-951), Fields%flip (Prog/Fields_mod.F90:173-217), Upgrade2
 // (Prog/upgrade_mod.F90:105-302) and the counters of Prog/control_mod.F90:164-176 -- restructured around what is sequential.
