@@ -158,53 +158,70 @@ __global__ void __launch_bounds__(256) k_apply_ops(T* __restrict__ M, long sM, i
   const int ns = (uf0 || uf1) ? (nt_b - nt_a + 1) : 1, total = ns * per;
   const int8_t* fbase = fields ? fields + (long)chain * Ltrot * n_opv : nullptr;
 
-  // descriptor prefetch registers and the cursor (slice, chunk within the slice) of the NEXT fetch
-  int4 rP = make_int4(0, 0, 0, 0); T rM[MPT]; int rcnt = 0; bool runi = false;
-  int f_sl = 0, f_r = 0;
-  auto fetch = [&]() {
-    const bool second = f_r >= nch0;
-    const OpListDev& L = second ? Lb : La;
-    const int c = second ? f_r - nch0 : f_r;
-    const int a0 = L.level_start[c]; rcnt = L.level_start[c + 1] - a0; runi = L.uniform[c] != 0;
+  // Descriptor prefetch, two chunks deep: the chunk boundaries ("meta": first operator, count, uniform flag, field slice) of chunk
+  // t + 3 and the operator data of chunk t + 2 are requested from global memory while chunk t is processed, and the data of chunk
+  // t + 1 (requested one step earlier) is committed to the other half of the shared-memory double buffer afterwards.
+  struct Pref { int4 rP; T rM[MPT]; int rcnt; bool runi; };
+  Pref pf0, pf1; pf0.rcnt = pf1.rcnt = 0; pf0.runi = pf1.runi = false;
+  int f_sl = 0, f_r = 0, f_n = 0;                     // cursor of the next meta load
+  bool m_second = false; int m_a0 = 0, m_cnt = 0; bool m_uni = false; const int8_t* m_fld = nullptr;
+  auto meta_load = [&]() {
+    if (f_n >= total) { m_cnt = 0; return; }
+    m_second = f_r >= nch0;
+    const OpListDev& L = m_second ? Lb : La;
+    const int c = m_second ? f_r - nch0 : f_r;
+    m_a0 = L.level_start[c]; m_cnt = L.level_start[c + 1] - m_a0; m_uni = L.uniform[c] != 0;
     const int nt = (dir > 0) ? nt_a + f_sl : nt_b - f_sl;
-    const int8_t* fld = ((second ? uf1 : uf0) && fbase) ? fbase + (nt - 1) * n_opv : nullptr;
-    if (tid < rcnt) {
-      const int4 p = reinterpret_cast<const int4*>(L.P)[a0 + tid];
-      rP = make_int4((p.x * ldp) | (L.k[a0 + tid] << 28), p.y * ldp, p.z * ldp, p.w * ldp);
+    m_fld = ((m_second ? uf1 : uf0) && fbase) ? fbase + (nt - 1) * n_opv : nullptr;
+    ++f_n; if (++f_r == per) { f_r = 0; ++f_sl; }
+  };
+  auto data_issue = [&](Pref& pf) {                   // uses the meta registers loaded one step earlier
+    const OpListDev& L = m_second ? Lb : La;
+    pf.rcnt = m_cnt; pf.runi = m_uni;
+    if (tid < m_cnt) {
+      const int4 p = reinterpret_cast<const int4*>(L.P)[m_a0 + tid];
+      pf.rP = make_int4((p.x * ldp) | (L.k[m_a0 + tid] << 28), p.y * ldp, p.z * ldp, p.w * ldp);
     }
     const T* mats = reinterpret_cast<const T*>(L.mat);
 #pragma unroll
     for (int u = 0; u < MPT; ++u) {
       const int e = tid + u * 256;
-      if (e < rcnt * ms) {
-        const int o = e >> (2 * LK), rr = e & (ms - 1), a = rr & (kk - 1), bb = rr >> LK, og = a0 + o;
+      if (e < m_cnt * ms) {
+        const int o = e >> (2 * LK), rr = e & (ms - 1), a = rr & (kk - 1), bb = rr >> LK, og = m_a0 + o;
         int var = 0;
-        if (L.nvar > 1) var = (int)fld[L.fidx[og]] + 2;
-        rM[u] = mats[(og * L.nvar + var) * (ALF_KMAX * ALF_KMAX) + a + bb * ALF_KMAX];
+        if (L.nvar > 1) var = (int)m_fld[L.fidx[og]] + 2;
+        pf.rM[u] = mats[(og * L.nvar + var) * (ALF_KMAX * ALF_KMAX) + a + bb * ALF_KMAX];
       }
     }
-    if (++f_r == per) { f_r = 0; ++f_sl; }
   };
-  auto commit = [&](int buf) {
-    if (tid < rcnt) dPb[buf * OPS_CH + tid] = rP;
+  auto commit = [&](const Pref& pf, int buf) {
+    if (tid < pf.rcnt) dPb[buf * OPS_CH + tid] = pf.rP;
 #pragma unroll
-    for (int u = 0; u < MPT; ++u) { const int e = tid + u * 256; if (e < rcnt * ms) dMb[buf * OPS_CH * ms + e] = rM[u]; }
+    for (int u = 0; u < MPT; ++u) { const int e = tid + u * 256; if (e < pf.rcnt * ms) dMb[buf * OPS_CH * ms + e] = pf.rM[u]; }
   };
-  if (total > 0) fetch();
+  meta_load();
+  if (total > 0) { data_issue(pf0); meta_load(); }
+  if (total > 1) { data_issue(pf1); meta_load(); }
   // ---- stage the panel
   if (SIDE == 0) {
     for (int j = warp; j < pw; j += nw) { const T* col = M + (long)(v0 + j) * N; for (int i = lane; i < N; i += 32) S[i * ldp + j] = col[i]; }
   } else {
     if (lane < pw) { const T* src = M + v0 + lane; for (int i = warp; i < N; i += nw) S[i * ldp + lane] = src[(long)i * N]; }
   }
-  int cnt_cur = rcnt; bool uni_cur = runi;
-  if (total > 0) commit(0);
+  int cnt_cur = pf0.rcnt; bool uni_cur = pf0.runi;
+  if (total > 0) commit(pf0, 0);
   __syncthreads();
-  for (int t = 0; t < total; ++t) {
-    if (t + 1 < total) fetch();
-    const int buf = t & 1;
-    ops_process_chunk<T, LK>(S, lane < pw, cnt_cur, dPb + buf * OPS_CH, dMb + buf * OPS_CH * ms, uni_cur);
-    if (t + 1 < total) { commit(buf ^ 1); cnt_cur = rcnt; uni_cur = runi; }
+  for (int t = 0; t < total; t += 2) {
+    // even step: chunk t sits in buffer 0; pf0 is free, pf1 carries chunk t + 1, the meta registers describe chunk t + 2
+    if (t + 2 < total) { data_issue(pf0); meta_load(); }
+    ops_process_chunk<T, LK>(S, lane < pw, cnt_cur, dPb, dMb, uni_cur);
+    if (t + 1 < total) { commit(pf1, 1); cnt_cur = pf1.rcnt; uni_cur = pf1.runi; }
+    __syncthreads();
+    if (t + 1 >= total) break;
+    // odd step: chunk t + 1 in buffer 1; pf1 is free, pf0 carries chunk t + 2, the meta registers describe chunk t + 3
+    if (t + 3 < total) { data_issue(pf1); meta_load(); }
+    ops_process_chunk<T, LK>(S, lane < pw, cnt_cur, dPb + OPS_CH, dMb + OPS_CH * ms, uni_cur);
+    if (t + 2 < total) { commit(pf0, 0); cnt_cur = pf0.rcnt; uni_cur = pf0.runi; }
     __syncthreads();
   }
   // ---- write back
