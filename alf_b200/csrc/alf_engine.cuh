@@ -310,6 +310,7 @@ struct Engine : EngineBase {
   Engine(alf_b200_handle* hh) : h(hh) {
     C = h->n_chains; F = h->n_fl; N = h->ndim; L = h->ltrot; M = h->n_opv; NM = C * F; n2 = (long)N * N; st = h->stream;
     if (F > ALF_FMAX) throw CudaError("more than ALF_FMAX flavors");
+    if (N > 576) throw CudaError("Ndim > 576 is not supported in this build (QR / TRSM kernels hold <= 18 rows per lane; TAU_M needs 2 Ndim <= 576)");
     S = (L % h->nwrap == 0) ? L / h->nwrap : L / h->nwrap + 1;                 // main.F90:446-457
     stab_nt.assign(S + 1, 0); for (int n = 1; n < S; ++n) stab_nt[n] = h->nwrap * n; stab_nt[S] = L;
     build_model();

@@ -575,3 +575,38 @@ def test_sweep_generic_slice_kernel(which, monkeypatch):
     monkeypatch.setenv("ALF_B200_GENERIC_UPDATE", "1")
     model = hubbard_square(4, 4, 1.0) if which == "hubbard" else kondo_square(2, 2, 1.0)
     _run_parity(model, SEEDS[:2], nwrap=5, n_sweeps=1, check_udv=False)
+
+
+@pytest.mark.gpu
+def test_free_fermions_no_vertices():
+    """Edge case: U = 0 leaves size(Op_V,1) = 0 (empty field loop).  G(0) must be the free-fermion (1 + prod e^{-dtau T})^-1 exactly and a
+    sweep (with TAU_M) must leave it unchanged; also the oracle agrees."""
+    import scipy.linalg as sl
+    model = hubbard_square(4, 4, 1.0, U=0.0, checkerboard=False, symm=False)
+    assert model.n_opv == 0
+    g = AlfB200(model, n_chains=2, nwrap=5); g.set_seeds([1, 2]); g.fields_set(); g.init_sweep()
+    op = model.Op_T[0][0]
+    Tm = np.zeros((model.Ndim, model.Ndim), dtype=complex)
+    for a in range(op.N):
+        for b in range(op.N):
+            Tm[op.P[a] - 1, op.P[b] - 1] = op.O[a, b]
+    B = np.linalg.matrix_power(sl.expm(op.g * Tm), model.Ltrot)
+    Gex = np.linalg.inv(np.eye(model.Ndim) + B)
+    for c in range(2):
+        for nf in (1, 2):
+            assert relF(g.green(c, nf), Gex) < 1e-12
+    g.sweep(1, 1)
+    for c in range(2):
+        assert relF(g.green(c, 1), Gex) < 1e-12
+    cg = g.control()
+    assert cg["NC_up"] == 0 and cg["XMAXG"] < 1e-12 and cg["XMAX_tau"] < 1e-10 and cg["nan"] == 0
+    g.close()
+
+
+@pytest.mark.gpu
+def test_too_large_ndim_fails_loudly():
+    """Sizes outside what the kernels support are refused at finalize_model with an error code and a message (no silent fallback)."""
+    from alf_b200.api import AlfError
+    with pytest.raises(AlfError) as ei:
+        AlfB200(hubbard_square(26, 24, 0.2, U=0.0, checkerboard=True), n_chains=1, nwrap=2)
+    assert "not supported" in str(ei.value)
