@@ -269,6 +269,7 @@ __device__ void qrp_device(T* __restrict__ A, int m, int n, int ld, T* __restric
       for (int i = 1 + lane; i < len; i += 32) xn2 += abs2_(col[i]);
       xn2 = warp_sum(xn2);
       T alpha = col[0];
+      __syncwarp();                      // every lane has read the pivot entry before lane 0 overwrites it with beta (racecheck)
       T tj, scal; double beta;
       if (xn2 == 0.0 && imag_(alpha) == 0.0) { tj = zero_<T>(); scal = zero_<T>(); beta = real_(alpha); }
       else {
@@ -493,17 +494,23 @@ __global__ void __launch_bounds__(32) k_tri_inv_blocks(const double* __restrict_
   for (int c = 0; c < 32; ++c) Rinv[lane + c * 32] = Xs[lane][c];      // column-major 32 x 32
 }
 
+// zero_cols_from / zero_rows (LOWER only): right-hand sides c >= zero_cols_from are known to vanish in rows < zero_rows (block-diagonal
+// right-hand side of solve_extended_System), so their forward substitution starts at block row zero_rows / 32.
+// dout != nullptr: X(i,:) is divided by dout[i] on the way out (the "apply inverse of D" loop of cgr2_2_mod.F90:183-188).
 template <int LOWER>
 __global__ void __launch_bounds__(512) k_trsm_blk(const double* __restrict__ R, int ldr, long sR, const double* __restrict__ Rinv, long sI,
-                                                  double* __restrict__ B, int ldb, long sB, int n, int nrhs, const double* __restrict__ dinv, long sD) {
+                                                  double* __restrict__ B, int ldb, long sB, int n, int nrhs, const double* __restrict__ dinv, long sD,
+                                                  int zero_cols_from, int zero_rows, const double* __restrict__ dout) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* Xs = reinterpret_cast<double*>(smem_raw);          // [TRSMB_CW][ldx], rows contiguous
   const int b = blockIdx.y, tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = nthr >> 5;
   const int g = lane >> 2, q = lane & 3;
   R += (long)b * sR; Rinv += (long)b * sI; B += (long)b * sB;
   if (dinv) dinv += (long)b * sD;
+  if (dout) dout += (long)b * sD;
   const int np = (n + 31) & ~31, nb = np >> 5, ldx = ld_pad(np);
   const int c0 = blockIdx.x * TRSMB_CW;
+  const int s_begin = (LOWER && zero_rows > 0 && c0 >= zero_cols_from) ? (zero_rows >> 5) : 0;
   for (int e = tid; e < np * TRSMB_CW; e += nthr) {
     const int i = e % np, c = e / np;
     double v = 0.0;
@@ -511,7 +518,7 @@ __global__ void __launch_bounds__(512) k_trsm_blk(const double* __restrict__ R, 
     Xs[i + c * ldx] = v;
   }
   __syncthreads();
-  for (int s = 0; s < nb; ++s) {
+  for (int s = s_begin; s < nb; ++s) {
     const int kb = LOWER ? s : nb - 1 - s, k0 = kb * 32;
     // B fragments of the current block row of X: bf[ks][cb] = X(k0 + 4 ks + q, 8 cb + g)
     double bf[8][4];
@@ -564,7 +571,7 @@ __global__ void __launch_bounds__(512) k_trsm_blk(const double* __restrict__ R, 
   }
   for (int e = tid; e < n * TRSMB_CW; e += nthr) {
     const int i = e % n, c = e / n;
-    if (c0 + c < nrhs) B[i + (long)(c0 + c) * ldb] = Xs[i + c * ldx];
+    if (c0 + c < nrhs) B[i + (long)(c0 + c) * ldb] = dout ? Xs[i + c * ldx] * (1.0 / dout[i]) : Xs[i + c * ldx];
   }
 }
 

@@ -130,14 +130,14 @@ static void launch_formq(cudaStream_t st, T* A, int m, int n, int ld, long sA, c
 // real matrices: blocked DMMA solve; rinv = workspace of ((n + 31) / 32) * 1024 doubles per matrix (stride sI)
 template <int LOWER>
 static void launch_trsm_blk(cudaStream_t st, const double* R, int ldr, long sR, double* B, int ldb, long sB, int n, int nrhs, const double* dinv, long sD,
-                            double* rinv, long sI, int batch) {
+                            double* rinv, long sI, int batch, int zero_cols_from = 0, int zero_rows = 0, const double* dout = nullptr) {
   const int np = (n + 31) & ~31, nb = np / 32;
   count_flops(KC_TRSM, 1.0 * n * n * nrhs * batch);
   const size_t smem = sizeof(double) * (size_t)ld_pad(np) * TRSMB_CW;
   KL(KC_TRSM, st, k_tri_inv_blocks<LOWER><<<dim3(nb, batch), 32, 0, st>>>(R, ldr, sR, n, rinv, sI));
   CK(cudaFuncSetAttribute(k_trsm_blk<LOWER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int nthr = (2 * (smem + 1024) <= 227 * 1024) ? 256 : 512;      // one resident CTA per SM only: give it 16 warps
-  KL(KC_TRSM, st, k_trsm_blk<LOWER><<<dim3((nrhs + TRSMB_CW - 1) / TRSMB_CW, batch), nthr, smem, st>>>(R, ldr, sR, rinv, sI, B, ldb, sB, n, nrhs, dinv, sD));
+  KL(KC_TRSM, st, k_trsm_blk<LOWER><<<dim3((nrhs + TRSMB_CW - 1) / TRSMB_CW, batch), nthr, smem, st>>>(R, ldr, sR, rinv, sI, B, ldb, sB, n, nrhs, dinv, sD, zero_cols_from, zero_rows, dout));
 }
 template <int LOWER>
 static void launch_trsm_blk_c(cudaStream_t st, const cplx* R, int ldr, long sR, cplx* B, int ldb, long sB, int n, int nrhs, const double* dinv, long sD,
@@ -425,8 +425,19 @@ static void la_cgr2_2(LaWork<T>& w, LaWork<T>& w2, int stab, const UdvDev<T>& ud
   // HLP <- P^T-row gather (ZLAPMR forward), L = R^H, HLP <- L^-1 HLP, rows / D3, HLP <- Q HLP
   KL(KC_EW, st, k_permcopy<T, 1><<<eg2, 256, 0, st>>>(w2.W[2], N2, n22, w2.W[1], N2, n22, N2, N2, w2.jpvt, N2));
   KL(KC_EW, st, k_transpose_conj<T><<<dim3(((N2 + 31) / 32) * ((N2 + 31) / 32), NM), 256, 0, st>>>(w2.W[3], N2, n22, w2.W[0], N2, n22, N2));   // full conj-transpose; only its lower triangle (R^H) is read
-  launch_trsm<T, 1>(st, w2.W[3], N2, n22, w2.W[2], N2, n22, N2, N2, nullptr, 0, NM, w2.Rinv, w2.sRinv());
-  KL(KC_EW, st, k_rowscale_inv<T><<<eg2, 256, 0, st>>>(w2.W[2], N2, n22, N2, N2, w2.Dq, N2));
+  bool fused = false;
+  if constexpr (std::is_same<T, double>::value) {
+    if (!la_force_old_trsm() && sizeof(double) * (size_t)ld_pad(N2) * TRSMB_CW <= 220 * 1024) {
+      // the division by D3 rides on the write-back (the row permutation has destroyed the block-diagonal zero pattern of HLP,
+      // so no block rows can be skipped: zero_rows = 0)
+      launch_trsm_blk<1>(st, w2.W[3], N2, n22, w2.W[2], N2, n22, N2, N2, nullptr, N2, w2.Rinv, w2.sRinv(), NM, 0, 0, w2.Dq);
+      fused = true;
+    }
+  }
+  if (!fused) {
+    launch_trsm<T, 1>(st, w2.W[3], N2, n22, w2.W[2], N2, n22, N2, N2, nullptr, 0, NM, w2.Rinv, w2.sRinv());
+    KL(KC_EW, st, k_rowscale_inv<T><<<eg2, 256, 0, st>>>(w2.W[2], N2, n22, N2, N2, w2.Dq, N2));
+  }
   if (!use_blocked_qr<T>(N2, N2)) {
     launch_formq<T>(st, w2.W[0], N2, N2, N2, n22, w2.tau, N2, nullptr, NM);
     gemm<T, 0, 0, 0>(st, N2, N2, N2, w2.W[0], N2, n22, w2.W[2], N2, n22, w2.W[1], N2, n22, NM);

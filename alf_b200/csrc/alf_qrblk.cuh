@@ -237,6 +237,7 @@ __global__ void __launch_bounds__(512) k_qrp_blk(T* __restrict__ A, int m, int n
         for (int i = 1 + lane; i < len; i += 32) xn2 += abs2_(col[i]);
         xn2 = warp_sum(xn2);
         const T alpha = col[0];
+        __syncwarp();                    // every lane has read the pivot entry before lane 0 overwrites it with beta
         T tj, scal; double beta;
         if (xn2 == 0.0 && imag_(alpha) == 0.0) { tj = zero_<T>(); scal = zero_<T>(); beta = real_(alpha); }
         else {
