@@ -1,0 +1,13 @@
+"""Small-case driver for compute-sanitizer (memcheck / racecheck / synccheck): one sweep incl. TAU_M / Tau_p of Hubbard 4x4,
+Kondo 2x2 and a projector run with 2 chains each, the blocked QR at 256 and CGR2_2 at 64."""
+import sys, os
+sys.path.insert(0, os.getcwd()); sys.path.insert(0, os.path.join(os.getcwd(), "tests"))
+import numpy as np
+from alf_b200.api import AlfB200
+from alf_b200 import api
+from alf_b200.model import hubbard_square, kondo_square
+for model, nw in ((hubbard_square(4, 4, 0.6), 3), (kondo_square(2, 2, 0.4), 2), (hubbard_square(4, 4, 0.4, projector=True, theta=0.2, trial="dimer"), 2)):
+    g = AlfB200(model, n_chains=2, nwrap=nw); g.set_seeds([5, 6]); g.fields_set(); g.init_sweep(); g.sweep(1, 1); print(model.name, g.control()["XMAXG"]); g.close()
+rng = np.random.default_rng(0)
+A = rng.normal(size=(1, 256, 256)); api.test_qdrp_blocked(A, False); print("qr256 ok")
+U = np.linalg.qr(rng.normal(size=(1, 64, 64)))[0]; api.test_cgr2_2(U, np.ones((1, 64)), U, U, np.ones((1, 64)), U, 0, False); print("cgr22 ok")
