@@ -174,11 +174,15 @@ def run_b200(args):
     from alf_b200.parallel import reduce_bins
 
     model, nwrap, chains_default = make_model(args.workload)
-    C = args.chains or chains_default
-    g = AlfB200(model, n_chains=C, nwrap=nwrap, device=local)
-    g.set_seeds([chain_seed(rank * C + c) for c in range(C)])
-    g.fields_set(); g.init_sweep()
-    stream = torch.cuda.ExternalStream(g.stream_ptr(), device=torch.device("cuda", local))
+    C = args.chains or chains_default                  # chains per handle
+    H = max(1, args.handles)                           # handles (= CUDA streams, each driven by one host thread) per GPU
+    gs, streams = [], []
+    for k in range(H):
+        gk = AlfB200(model, n_chains=C, nwrap=nwrap, device=local)
+        gk.set_seeds([chain_seed((rank * H + k) * C + c) for c in range(C)])
+        gk.fields_set(); gk.init_sweep()
+        gs.append(gk); streams.append(torch.cuda.ExternalStream(gk.stream_ptr(), device=torch.device("cuda", local)))
+    g = gs[0]
     N, L, M, F = model.Ndim, model.Ltrot, model.n_opv, model.N_FL
 
     def barrier():
@@ -191,58 +195,79 @@ def run_b200(args):
             return x
         t = torch.tensor([x], dtype=torch.float64, device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX); return float(t.item())
 
-    for _ in range(args.warmup):
-        g.sweep(1, args.ltau)
+    def on_all(fn):
+        """fn(k) for every handle, one host thread per handle (the C-ABI is re-entrant across handles; ctypes drops the GIL)."""
+        if H == 1:
+            fn(0); return
+        errs = []
+        def wrap(k):
+            try:
+                torch.cuda.set_device(local); fn(k)
+            except Exception as e:      # noqa: BLE001
+                errs.append(e)
+        th = [threading.Thread(target=wrap, args=(k,)) for k in range(H)]
+        [t.start() for t in th]; [t.join() for t in th]
+        if errs:
+            raise errs[0]
+
+    def timed(fn):
+        """Device time of fn over all handles: first start event to last end event (CUDA events on each handle's stream)."""
+        barrier()
+        ev0 = [torch.cuda.Event(enable_timing=True) for _ in range(H)]; ev1 = [torch.cuda.Event(enable_timing=True) for _ in range(H)]
+        for k in range(H):
+            ev0[k].record(streams[k])                  # all streams idle here
+        def body(k):
+            fn(k); ev1[k].record(streams[k])           # fn returns after its stream has drained
+        on_all(body)
+        barrier()
+        return max_over_ranks(max(ev0[a].elapsed_time(ev1[b]) for a in range(H) for b in range(H)))
+
+    on_all(lambda k: gs[k].sweep(args.warmup, args.ltau) if args.warmup > 0 else None)
     # ---- timed region 1: device-resident sweeps
-    g.kernel_timing(1 << 0)                      # CUDA events around the dominant kernel (k_wrapgr) only
-    c0 = g.control()
+    for gk in gs:
+        gk.kernel_timing(1 << 0)                 # CUDA events around the dominant kernel (k_wrapgr_fast) only
+    c0 = [gk.control() for gk in gs]
     clocks = ClockSampler(local); clocks.start()
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    for _ in range(args.steps):
-        g.sweep(1, args.ltau)
-    e1.record(stream)
-    barrier()
-    ms = max_over_ranks(e0.elapsed_time(e1))
+    ms = timed(lambda k: [gs[k].sweep(1, args.ltau) for _ in range(args.steps)])
     clk = clocks.stop()
-    stats = g.kernel_stats(); c1 = g.control()
-    g.kernel_timing(0)
-    value = world * C * args.steps / (ms * 1e-3)
+    stats_all = [gk.kernel_stats() for gk in gs]; c1 = [gk.control() for gk in gs]
+    stats = {key: (sum(st[key][0] for st in stats_all), sum(st[key][1] for st in stats_all)) for key in stats_all[0]}
+    for gk in gs:
+        gk.kernel_timing(0)
+    value = world * H * C * args.steps / (ms * 1e-3)
 
     # ---- timed region 2: end to end through the C-ABI with host buffers (fields up, sweep, fields + observables + control down)
-    f_in = g.get_fields(); f_out = np.empty_like(f_in); obs = np.zeros(max(16, g.obs_size())); ctl = np.zeros(16)
+    f_in = [gk.get_fields() for gk in gs]; f_out = [np.empty_like(x) for x in f_in]
+    obs = [np.zeros(max(16, gk.obs_size())) for gk in gs]; ctl = [np.zeros(16) for _ in gs]
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        g.sweep_host(1, args.ltau, f_in, f_out, obs, ctl)
-        red = reduce_bins(g, obs, world)          # NCCL reduction of the bin accumulators (replaces MPI_REDUCE, observables_mod.F90:425-438)
+        on_all(lambda k: gs[k].sweep_host(1, args.ltau, f_in[k], f_out[k], obs[k], ctl[k]))
+        for k in range(H):
+            red = reduce_bins(gs[k], obs[k], world)   # NCCL reduction of the bin accumulators (replaces MPI_REDUCE, observables_mod.F90:425-438)
         f_in, f_out = f_out, f_in
     barrier()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
-    e2e_value = world * C * args.steps / e2e_s
-    h2d = C * L * M                                # int8 per field through the pinned staging buffer
-    d2h = C * L * M + 8 * (len(obs) + 16)
+    e2e_value = world * H * C * args.steps / e2e_s
+    h2d = world * H * C * L * M                    # int8 per field through the pinned staging buffers, all ranks
+    d2h = world * H * (C * L * M + 8 * (len(obs[0]) + 16))
 
     # ---- un-timed extra passes (rank-local, after both timed regions): per-category device time + algorithmic FP64 flops of the
-    # dense kernels (CUDA events around every launch perturb the step, so they are kept out of the timed regions), and the same
-    # sweep without the time-displaced part for reference
+    # dense kernels on ONE handle running alone (CUDA events around every launch perturb the step, so they are kept out of the timed
+    # regions), and the same sweep without the time-displaced part for reference
     g.kernel_timing(0xff)
     g.sweep(1, args.ltau)
     cat_stats = g.kernel_stats(); cat_flops = g.kernel_flops()
     g.kernel_timing(0)
     eq_only = None
     if args.ltau:
-        barrier()
-        q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        q0.record(stream); g.sweep(1, 0); q1.record(stream)
-        barrier()
-        eq_ms = max_over_ranks(q0.elapsed_time(q1))
-        eq_only = {"value": world * C / (eq_ms * 1e-3), "unit": UNIT, "ms_per_step": eq_ms, "steps": 1, "note": "same chains, sweep without TAU_M (ltau = 0)"}
+        eq_ms = timed(lambda k: gs[k].sweep(1, 0))
+        eq_only = {"value": world * H * C / (eq_ms * 1e-3), "unit": UNIT, "ms_per_step": eq_ms, "steps": 1, "note": "same chains, sweep without TAU_M (ltau = 0)"}
 
     # ---- roofline of the dominant kernel and CPU baseline (rank 0, N = 1 only for the latter)
     upd_ms, upd_n = stats["update"]
-    acc = c1["ACC_up"] - c0["ACC_up"]
+    acc = sum(b["ACC_up"] - a["ACC_up"] for a, b in zip(c0, c1))
+    nprop = sum(b["NC_up"] - a["NC_up"] for a, b in zip(c0, c1))
     w = 16 if g.is_complex else 8
     line = None
     if rank == 0:
@@ -271,7 +296,7 @@ def run_b200(args):
         avg_s = upd_ms * 1e-3 / max(upd_n, 1)
         achieved = alg_bytes_per_launch / avg_s / 1e9 if avg_s > 0 else 0.0
         roof = {"kernel": "k_wrapgr (delayed-update slice kernel)", "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "launches": upd_n, "avg_launch_ms": 1e3 * avg_s, "share_of_step": upd_ms / ms if ms > 0 else None,
+                "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "launches": upd_n, "avg_launch_ms": 1e3 * avg_s, "share_of_step": upd_ms / (H * ms) if ms > 0 else None,
                 "algorithmic_bytes_per_launch": alg_bytes_per_launch,
                 "note": "algorithmic bytes = SURVEY 8d's figure for the reference algorithm (2*w*N^2 per accepted rank-1 ZGERU update and flavor); this kernel keeps accepted updates as delayed factors in shared memory and rewrites G once per KD accepts, so its DRAM traffic (see traffic) is ~20x below the algorithmic bytes and frac exceeds 1 by design",
                 "fp64": {"achieved_tflops": alg_flops_per_launch / avg_s / 1e12 if avg_s > 0 else 0.0, "peak_tflops_dfma_measured": dfma, "peak_tflops_dmma_measured": dmma}}
@@ -284,15 +309,18 @@ def run_b200(args):
         nl = sum(v[1] for v in stats.values())
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "c128" if g.is_complex else "f64", "data": "synthetic",
-                "config": {"workload": args.workload, "N_dim": N, "L_trot": L, "N_FL": F, "nwrap": nwrap, "ltau": args.ltau, "chains_per_gpu": C, "chains": world * C,
-                           "parallelism": f"chains sharded over {world} GPU(s), no data-path collective", "l2": "working set (G + UDV storage of all chains) exceeds L2"},
+                "config": {"workload": args.workload, "N_dim": N, "L_trot": L, "N_FL": F, "nwrap": nwrap, "ltau": args.ltau, "chains_per_gpu": H * C, "chains": world * H * C,
+                           "handles_per_gpu": H, "chains_per_handle": C,
+                           "parallelism": f"chains sharded over {world} GPU(s) x {H} handle(s) (one CUDA stream and host thread each), no data-path collective",
+                           "l2": "working set (G + UDV storage of all chains) exceeds L2"},
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
                 "gpu_launches": nl, "kernel_launches": {k: v[1] for k, v in stats.items()},
-                "acceptance": acc / max(c1["NC_up"] - c0["NC_up"], 1), "precision_green_max": c1["XMAXG"],
+                "acceptance": acc / max(nprop, 1), "precision_green_max": max(c["XMAXG"] for c in c1),
                 "clocks": clk, "roofline": roof, "cpu_baseline": cpu,
                 "fp64_kernels": fp64_kernels, "fp64_peak_measured": {"dfma_tflops": dfma, "dmma_tflops": dmma},
                 "breakdown_ms_per_sweep": {k: round(v[0], 3) for k, v in cat_stats.items()}, "equal_time_only": eq_only}
-    g.close()
+    for gk in gs:
+        gk.close()
     if world > 1:
         dist.barrier(); dist.destroy_process_group()
     if rank == 0:
@@ -307,7 +335,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="hubbard_16x16_beta10", choices=sorted(WORKLOADS))
-    ap.add_argument("--chains", type=int, default=0, help="chains per GPU (default: per workload)")
+    ap.add_argument("--chains", type=int, default=0, help="chains per handle (default: per workload)")
+    ap.add_argument("--handles", type=int, default=2, help="handles per GPU, each with its own CUDA stream and host thread (measured: 2 x 148 chains "
+                    "overlap the latency-bound kernels of one handle with the throughput-bound ones of the other, +7 %% over 1 x 148)")
     ap.add_argument("--ltau", type=int, default=1, help="1: the sweep includes TAU_M (BASELINE configs[2]: time-displaced Green functions); 0: equal-time only")
     ap.add_argument("--cpu-cores", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
