@@ -159,6 +159,8 @@ def run_b200(args):
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback (use --impl reference for the CPU arm)")
+    # stdout carries exactly ONE JSON line: whatever libraries print there meanwhile (NCCL's version banner at 8 ranks) goes to stderr
+    sys.stdout.flush(); saved_stdout = os.dup(1); os.dup2(2, 1)
     torch.cuda.set_device(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
@@ -323,6 +325,7 @@ def run_b200(args):
         gk.close()
     if world > 1:
         dist.barrier(); dist.destroy_process_group()
+    sys.stdout.flush(); os.dup2(saved_stdout, 1); os.close(saved_stdout)
     if rank == 0:
         print(json.dumps(line), flush=True)
     return 0
