@@ -154,6 +154,25 @@ class AlfB200:
     def tau_p(self, nst_in):
         self._ck(lib().alf_b200_tau_p(self.h, int(nst_in)))
 
+    # ---- device-side time-displaced lattice observables (ObserT of the shipped Hamiltonians)
+    def obs_tau_enable(self, on=True):
+        n_unit, norb, cell, orb, imj = self.m.lattice_tables()
+        imj_f = np.ascontiguousarray(imj.T)                       # Fortran order: imj(I, J) at I-1 + (J-1) n_unit
+        self._ck(lib().alf_b200_set_lattice(self.h, int(n_unit), int(norb), cell.ctypes.data_as(_ip), orb.ctypes.data_as(_ip), imj_f.ctypes.data_as(_ip)))
+        self._ck(lib().alf_b200_obs_tau_enable(self.h, int(on)))
+
+    def obs_tau_reset(self):
+        self._ck(lib().alf_b200_obs_tau_reset(self.h))
+
+    def obs_tau(self):
+        """(acc[ch, nt, no_J, no_I, imj] complex, bg[which, nt, no] complex, N, sum of signs), summed over the chains of the handle."""
+        nch, ntau, norb, nu = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        self._ck(lib().alf_b200_obs_tau_dims(self.h, C.byref(nch), C.byref(ntau), C.byref(norb), C.byref(nu)))
+        acc = np.zeros((nch.value, ntau.value, norb.value, norb.value, nu.value), dtype=np.complex128)
+        bg = np.zeros((2, ntau.value, norb.value), dtype=np.complex128); cnt = np.zeros(2)
+        self._ck(lib().alf_b200_get_obs_tau(self.h, _d(acc), _d(bg), _d(cnt)))
+        return acc, bg, cnt[0], cnt[1]
+
     # ---- global-in-slice moves (Wrapgr_PlaceGR / Wrapgr_Random_update)
     def wrapgr_set_position(self, m):
         self._ck(lib().alf_b200_wrapgr_set_position(self.h, int(m)))

@@ -59,6 +59,7 @@ int alf_b200_destroy(alf_b200_handle* h) {
   if (t_prof == &h->prof) t_prof = nullptr;          // the launch-accounting pointer must not outlive its handle
   h->eng.reset();
   if (h->d_fields) cudaFree(h->d_fields); if (h->d_rng) cudaFree(h->d_rng); if (h->d_phase) cudaFree(h->d_phase);
+  if (h->d_obst_acc) cudaFree(h->d_obst_acc); if (h->d_obst_bg) cudaFree(h->d_obst_bg); if (h->d_obst_cnt) cudaFree(h->d_obst_cnt);
   if (h->d_counters) cudaFree(h->d_counters); if (h->d_ctl) cudaFree(h->d_ctl); if (h->d_acclog) cudaFree(h->d_acclog); if (h->d_obs) cudaFree(h->d_obs);
   if (h->pin_fields) cudaFreeHost(h->pin_fields);
   if (h->stream) cudaStreamDestroy(h->stream);
@@ -209,6 +210,52 @@ int alf_b200_udv_reset(alf_b200_handle* h, int which, char side) { API_BEGIN(h) 
 int alf_b200_cgr(alf_b200_handle* h, int nvar) { API_BEGIN(h) NEED_FINAL(h) h->eng->cgr_call(nvar); h->eng->sync(); API_END(h) }
 int alf_b200_tau_m(alf_b200_handle* h) { API_BEGIN(h) NEED_FINAL(h) h->eng->tau_m(); h->eng->sync(); API_END(h) }
 int alf_b200_tau_p(alf_b200_handle* h, int nst_in) { API_BEGIN(h) NEED_FINAL(h) if (nst_in < 0) return ALF_ERROR_GENERIC; h->eng->tau_p(nst_in); h->eng->sync(); API_END(h) }
+
+// ---- lattice tables and device-side time-displaced lattice observables (what ham%ObserT accumulates through Predefined_Obs_tau_*)
+int alf_b200_set_lattice(alf_b200_handle* h, int n_unit, int norb, const int* site_cell, const int* site_orb, const int* imj) {
+  if (!h || n_unit < 1 || norb < 1 || !site_cell || !site_orb || !imj) return ALF_ERROR_GENERIC;
+  h->n_unit = n_unit; h->norb = norb; h->site_cell.resize(h->ndim); h->site_orb.resize(h->ndim); h->imj.resize((size_t)n_unit * n_unit);
+  for (int i = 0; i < h->ndim; ++i) {
+    if (site_cell[i] > n_unit || (site_cell[i] > 0 && (site_orb[i] < 1 || site_orb[i] > norb))) { h->err = "set_lattice: List entry out of range"; return ALF_ERROR_GENERIC; }
+    h->site_cell[i] = site_cell[i] - 1; h->site_orb[i] = site_orb[i] - 1;      // List(I1,1) <= 0: site not in the list (skipped, Predefined_Obs_mod.F90:365)
+  }
+  for (size_t i = 0; i < h->imj.size(); ++i) { if (imj[i] < 1 || imj[i] > n_unit) { h->err = "set_lattice: imj entry out of range"; return ALF_ERROR_GENERIC; } h->imj[i] = imj[i] - 1; }
+  return ALF_OK;
+}
+static size_t obst_acc_len(const alf_b200_handle* h) { return (size_t)2 * OBST_NCH * h->obst_ntau * h->norb * h->norb * h->n_unit; }
+static size_t obst_bg_len(const alf_b200_handle* h) { return (size_t)2 * 2 * h->obst_ntau * h->norb; }
+int alf_b200_obs_tau_enable(alf_b200_handle* h, int on) {
+  API_BEGIN(h) NEED_FINAL(h)
+  if (on && !h->d_obst_acc) {
+    if (h->n_unit <= 0) { h->err = "obs_tau_enable: call alf_b200_set_lattice first"; return ALF_ERROR_GENERIC; }
+    h->obst_ntau = h->projector ? h->ltrot - 2 * h->thtrot + 1 : h->ltrot + 1;          // Ltau + 1 time points (Hubbard_smod.F90:628,666)
+    CK(cudaMalloc(&h->d_obst_acc, sizeof(double) * obst_acc_len(h))); CK(cudaMalloc(&h->d_obst_bg, sizeof(double) * obst_bg_len(h))); CK(cudaMalloc(&h->d_obst_cnt, sizeof(double) * 2));
+    CK(cudaMemsetAsync(h->d_obst_acc, 0, sizeof(double) * obst_acc_len(h), h->stream)); CK(cudaMemsetAsync(h->d_obst_bg, 0, sizeof(double) * obst_bg_len(h), h->stream));
+    CK(cudaMemsetAsync(h->d_obst_cnt, 0, sizeof(double) * 2, h->stream));
+    h->eng->obs_tau_setup();
+  }
+  h->obs_tau_on = on != 0;
+  API_END(h)
+}
+int alf_b200_obs_tau_reset(alf_b200_handle* h) {
+  API_BEGIN(h) NEED_FINAL(h) if (!h->d_obst_acc) return ALF_ERROR_GENERIC;
+  CK(cudaMemsetAsync(h->d_obst_acc, 0, sizeof(double) * obst_acc_len(h), h->stream)); CK(cudaMemsetAsync(h->d_obst_bg, 0, sizeof(double) * obst_bg_len(h), h->stream));
+  CK(cudaMemsetAsync(h->d_obst_cnt, 0, sizeof(double) * 2, h->stream));
+  API_END(h)
+}
+int alf_b200_obs_tau_dims(const alf_b200_handle* h, int* n_channels, int* ntau, int* norb, int* n_unit) {
+  if (!h || !h->d_obst_acc) return ALF_ERROR_GENERIC;
+  if (n_channels) *n_channels = OBST_NCH; if (ntau) *ntau = h->obst_ntau; if (norb) *norb = h->norb; if (n_unit) *n_unit = h->n_unit;
+  return ALF_OK;
+}
+int alf_b200_get_obs_tau(alf_b200_handle* h, double* acc, double* bg, double* cnt) {
+  API_BEGIN(h) NEED_FINAL(h) if (!h->d_obst_acc) return ALF_ERROR_GENERIC;
+  CK(cudaStreamSynchronize(h->stream));
+  if (acc) CK(cudaMemcpy(acc, h->d_obst_acc, sizeof(double) * obst_acc_len(h), cudaMemcpyDeviceToHost));
+  if (bg) CK(cudaMemcpy(bg, h->d_obst_bg, sizeof(double) * obst_bg_len(h), cudaMemcpyDeviceToHost));
+  if (cnt) CK(cudaMemcpy(cnt, h->d_obst_cnt, sizeof(double) * 2, cudaMemcpyDeviceToHost));
+  API_END(h)
+}
 
 // ---- global-in-slice moves: Wrapgr_PlaceGR / Wrapgr_Random_update (Prog/Wrapgr_mod.F90:247-433) with host-supplied proposals
 int alf_b200_wrapgr_set_position(alf_b200_handle* h, int m) { API_BEGIN(h) NEED_FINAL(h) if (m < 0 || m > h->n_opv) return ALF_ERROR_GENERIC; h->eng->gm_set_position(m); API_END(h) }

@@ -14,6 +14,7 @@
 #include "alf_update.cuh"
 #include "alf_update_fast.cuh"
 #include "alf_global_move.cuh"
+#include "alf_obs_tau.cuh"
 
 typedef std::complex<double> cd;
 static const double kEpsMachine = 2.220446049250313e-16;
@@ -119,6 +120,7 @@ struct EngineBase {
   virtual void cgr_call(int nvar) = 0;
   virtual void tau_m() = 0;
   virtual void tau_p(int nst_in) = 0;
+  virtual void obs_tau_setup() = 0;
   virtual void gm_set_position(int m) = 0;
   virtual void gm_get_position(int* m) = 0;
   virtual void gm_random_update(int ntau, int n_moves, int maxlen, const int* len, const int* list0, const int8_t* val, const double* t0, const double* s0,
@@ -146,6 +148,9 @@ struct alf_b200_handle {
   double* d_obs = nullptr; int obs_size = 0;
   int taum_every = 0; std::vector<std::vector<cd>> taum_host, taum_fresh_host;   // per chain captured matrices
   std::vector<int> types;            // operator type per n
+  // lattice tables for the device-side lattice observables (0-based; site -> unit cell / orbital, imj(I,J) column-major)
+  int n_unit = 0, norb = 1; std::vector<int> site_cell, site_orb, imj;
+  bool obs_tau_on = false; double *d_obst_acc = nullptr, *d_obst_bg = nullptr, *d_obst_cnt = nullptr; int obst_ntau = 0;
   // projective algorithm (Prog/Hamiltonian_main_mod.F90:181-197: Projector, Thtrot, WF_L, WF_R)
   bool projector = false; int thtrot = 0, n_part = 0; std::vector<std::vector<cd>> wf_l, wf_r;   // per flavor, Ndim x N_part column-major
 };
@@ -713,6 +718,30 @@ struct Engine : EngineBase {
     }
     for (int c = 0; c < C; ++c) dst[c].insert(dst[c].end(), part[c].begin(), part[c].end());
   }
+  // ---- device-side ObserT (alf_obs_tau.cuh): symmetrised copies of the four matrices, then one binning kernel per time point
+  LattDev lt; T* obsS[4] = {nullptr, nullptr, nullptr, nullptr}; size_t obst_smem = 0;
+  void obs_tau_setup() override {
+    if (lt.cell) return;
+    if (h->n_unit <= 0 || (int)h->site_cell.size() != N) throw CudaError("obs_tau: alf_b200_set_lattice has not been called");
+    if (F > 2) throw CudaError("obs_tau: more than two flavors are not supported");
+    lt.n_unit = h->n_unit; lt.norb = h->norb;
+    lt.cell = dupload(h->site_cell); lt.orb = dupload(h->site_orb); lt.imj = dupload(h->imj);
+    for (int q = 0; q < 4; ++q) obsS[q] = dalloc<T>(n2 * NM);
+    obst_smem = obs_tau_smem<T>(N, lt.n_unit, lt.norb);
+    if (obst_smem > 227 * 1024) throw CudaError("obs_tau: lattice too large for the shared-memory bins");
+    CK(cudaFuncSetAttribute(k_obs_tau<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)obst_smem));
+  }
+  void obsert(int nt_index) {      // where TAU_M / Tau_p call ham%ObserT(nt_index, GT0, G0T, G00, GTT, Phase): tau_m_mod.F90:115-124,151-177
+    if (!h->obs_tau_on || nt_index < 0 || nt_index >= h->obst_ntau) return;
+    obs_tau_setup();
+    const T* src[4] = {GT0, G0T, G00, GTT}; const T* use[4];
+    for (int q = 0; q < 4; ++q) {
+      if (h->symm) { CK(cudaMemcpyAsync(obsS[q], src[q], sizeof(T) * n2 * NM, cudaMemcpyDeviceToDevice, st)); hop_symm(obsS[q]); use[q] = obsS[q]; }
+      else use[q] = src[q];
+    }
+    KL(KC_OBS, st, k_obs_tau<T><<<C, 256, obst_smem, st>>>(use[0], use[1], use[2], use[3], n2, N, F, h->n_sun, h->d_phase, lt, nt_index, h->obst_ntau,
+                                                        h->d_obst_acc, h->d_obst_bg, h->d_obst_cnt));
+  }
   void compare_tau(const T* A, const T* B) {   // Control_Precision_tau, control_mod.F90:300-311
     KL(KC_EW, st, k_compare<T><<<dim3(NM, CMP_SPLIT), 256, 0, st>>>(A, B, n2, n2, d_cmp));
     KL(KC_EW, st, k_ctl_accum<<<(C + 127) / 128, 128, 0, st>>>(d_cmp, F, h->d_ctl, 1, C));
@@ -723,13 +752,13 @@ struct Engine : EngineBase {
     CK(cudaMemcpyAsync(G00, G, bytes, cudaMemcpyDeviceToDevice, st)); CK(cudaMemcpyAsync(GT0, G, bytes, cudaMemcpyDeviceToDevice, st));
     CK(cudaMemcpyAsync(GTT, G, bytes, cudaMemcpyDeviceToDevice, st));
     KL(KC_EW, st, k_g0t_init<T><<<eg, 256, 0, st>>>(G0T, G, n2, N));
-    taum_capture(0);
+    taum_capture(0); obsert(0);
     set_udv_identity(udvr2);
     int NST = 1;
     for (int NT = 0; NT <= L - 1; ++NT) {
       const int NT1 = NT + 1;
       propr(GT0, NT1); proprm1(G0T, NT1); proprm1(GTT, NT1); propr(GTT, NT1);          // tau_m_mod.F90:141-149
-      taum_capture(NT1);
+      taum_capture(NT1); obsert(NT1);
       if (stab_nt[NST] == NT1) {
         wrapur_on(udvr2, stab_nt[NST - 1], NT1);
         la_cgr2_2<T>(w, w2, h->stab, udvr2, udvst[NST - 1], tmN[0], tmN[1], tmN[2], tmN[3], d_first);
@@ -760,7 +789,7 @@ struct Engine : EngineBase {
     }
     CK(cudaMemcpyAsync(G00, GTT, bytes, cudaMemcpyDeviceToDevice, st)); CK(cudaMemcpyAsync(GT0, GTT, bytes, cudaMemcpyDeviceToDevice, st));
     KL(KC_EW, st, k_g0t_init<T><<<eg, 256, 0, st>>>(G0T, GTT, n2, N));                     // G0T = GTT - 1
-    taum_capture(0);
+    taum_capture(0); obsert(0);
     int NCHECK = 0;
     for (int NT = thtrot + 1; NT <= L - thtrot; ++NT) {
       const int NTAU = NT - thtrot - 1;
@@ -774,7 +803,7 @@ struct Engine : EngineBase {
       }
       const int NT1 = NT + 1;
       propr(GT0, NT1); proprm1(G0T, NT1); proprm1(GTT, NT1); propr(GTT, NT1);
-      taum_capture(NTAU + 1);
+      taum_capture(NTAU + 1); obsert(NTAU + 1);
     }
     if (NCHECK == 0 && NT_ST + 1 <= S) {                       // fallback check of the reference (:262-279)
       for (int NT = L - thtrot + 2; NT <= stab_nt[NT_ST + 1]; ++NT) { proprm1(GTT, NT); propr(GTT, NT); }

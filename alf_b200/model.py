@@ -128,6 +128,19 @@ class Lattice:
         lo = r[0]
         return (i - lo) % L + lo
 
+    def imj(self, I: int, J: int) -> int:
+        """Latt%imj(I, J): the lattice point r_I - r_J folded back (lattices_v3_mod.F90:316-330); 1-based."""
+        i1, i2 = self.list[I - 1]; j1, j2 = self.list[J - 1]
+        return self.invlist[(self._wrap(i1 - j1, self._r1, self.L1), self._wrap(i2 - j2, self._r2, self.L2))]
+
+    def imj_table(self) -> np.ndarray:
+        """imj as an (N, N) int32 array, [I-1, J-1] -> 1-based index of r_I - r_J."""
+        t = np.zeros((self.N, self.N), dtype=np.int32)
+        for I in range(1, self.N + 1):
+            for J in range(1, self.N + 1):
+                t[I - 1, J - 1] = self.imj(I, J)
+        return t
+
     def nnlist(self, I: int, n1: int, n2: int) -> int:
         i1, i2 = self.list[I - 1]
         return self.invlist[(self._wrap(i1 + n1, self._r1, self.L1), self._wrap(i2 + n2, self._r2, self.L2))]
@@ -153,6 +166,19 @@ class Model:
     Thtrot: int = 0
     WF_L: Optional[List[np.ndarray]] = None     # per flavor, (Ndim, N_part) complex
     WF_R: Optional[List[np.ndarray]] = None
+
+    # List(I1, 1:2) of the Hamiltonians (unit cell, orbital) per site, 1-based, and the number of orbitals per unit cell
+    # (Prog/Predefined_Latt_mod.F90:250-260); None -> one orbital per cell, site I1 = cell I1
+    site_cell: Optional[np.ndarray] = None
+    site_orb: Optional[np.ndarray] = None
+    n_orb: int = 1
+
+    def lattice_tables(self):
+        """(n_unit, n_orb, site_cell, site_orb, imj) as the C-ABI's alf_b200_set_lattice wants them (all 1-based)."""
+        n_unit = self.latt.N
+        cell = self.site_cell if self.site_cell is not None else np.arange(1, self.Ndim + 1, dtype=np.int32)
+        orb = self.site_orb if self.site_orb is not None else np.ones(self.Ndim, dtype=np.int32)
+        return n_unit, int(self.n_orb), np.ascontiguousarray(cell, dtype=np.int32), np.ascontiguousarray(orb, dtype=np.int32), self.latt.imj_table()
 
     @property
     def N_part(self):
@@ -386,8 +412,12 @@ def kondo_square(L1: int, L2: int, beta: float, dtau: float = 0.1, t: float = 1.
             op.O[0, 0] = 1.0; op.O[1, 1] = 1.0
         op.g = np.sqrt(complex(dtau * (J / 2.0) / float(N_SUN), 0.0)); op.alpha = 0.0; op.type = 2
         Op_set(op); Op_V.append([op])
-    return Model(name="Kondo", Ndim=Ndim, N_FL=1, N_SUN=N_SUN, Ltrot=Ltrot, Dtau=dtau, Symm=symm, Op_V=Op_V, Op_T=Op_T, latt=latt,
-                 params=dict(L1=L1, L2=L2, beta=beta, dtau=dtau, t=t, J=J, Uf=Uf, symm=symm))
+    m = Model(name="Kondo", Ndim=Ndim, N_FL=1, N_SUN=N_SUN, Ltrot=Ltrot, Dtau=dtau, Symm=symm, Op_V=Op_V, Op_T=Op_T, latt=latt,
+              params=dict(L1=L1, L2=L2, beta=beta, dtau=dtau, t=t, J=J, Uf=Uf, symm=symm))
+    m.n_orb = 2
+    m.site_cell = np.repeat(np.arange(1, Nc + 1, dtype=np.int32), 2)
+    m.site_orb = np.tile(np.array([1, 2], dtype=np.int32), Nc)
+    return m
 
 
 def flatten_ops(model: Model):

@@ -86,6 +86,19 @@ int alf_b200_cgr(alf_b200_handle* h, int nvar);               /* Prog/cgr1_mod.F
 int alf_b200_tau_m(alf_b200_handle* h);                       /* Prog/tau_m_mod.F90:56 */
 int alf_b200_tau_p(alf_b200_handle* h, int nst_in);           /* Prog/tau_p_mod.F90:74 (projector; udvr, udvst, GR as in main.F90:829) */
 
+/* Device-side time-displaced lattice observables: what ham%ObserT of the shipped Hamiltonians accumulates through
+ * Predefined_Obs_tau_Green / SpinMz / SpinSUN / Den_measure (Prog/Predefined_Obs_mod.F90:337-594) each time TAU_M / Tau_p reach a
+ * time point (tau_m_mod.F90:115-177, tau_p_mod.F90:173-250), with Hop_mod_Symm applied first when Symm (as the reference does).
+ * set_lattice: List(I1,1:2) (unit cell, orbital; 1-based; cell <= 0 = site not measured) and Latt%imj (n_unit x n_unit, column-major,
+ * 1-based; Libraries/Modules/lattices_v3_mod.F90:316-330).  Accumulators are sums over the chains of the handle:
+ * acc[ch][nt][no_J][no_I][imj] complex with ch = 0 Green, 1 SpinZ, 2 SpinXY (Mz only), 3 Den; bg[which][nt][no] complex (Obs_Latt0 of
+ * SpinZ, Den); cnt = {N (counted at nt = 0), sum of signs}.  ham%ObserT of other models stays a host callback (taum_capture). */
+int alf_b200_set_lattice(alf_b200_handle* h, int n_unit, int norb, const int* site_cell, const int* site_orb, const int* imj);
+int alf_b200_obs_tau_enable(alf_b200_handle* h, int on);
+int alf_b200_obs_tau_reset(alf_b200_handle* h);
+int alf_b200_obs_tau_dims(const alf_b200_handle* h, int* n_channels, int* ntau, int* norb, int* n_unit);
+int alf_b200_get_obs_tau(alf_b200_handle* h, double* acc, double* bg, double* cnt);
+
 /* Global-in-slice moves (N_Global_tau > 0), Prog/Wrapgr_mod.F90:247-433.  ham%Global_move_tau stays a host plugin callback:
  * its outputs (Flip_length, Flip_list (1-based), Flip_value, T0_Proposal_ratio, S0_ratio) are passed for every chain and every
  * one of the n_moves proposals ([chain][move], lists [chain][move][maxlen], maxlen <= 16); the device sorts the lists

@@ -897,8 +897,49 @@ struct Oracle {
     for (int nf = 0; nf < n_fl; ++nf) { mmthl_m1(A[nf].data(), ndim, ndim, nf);
       for (int n = 0; n < n_opv; ++n) op_mmultL(A[nf].data(), ndim, ndim, OpV(n, nf), fld(n, nt), 'n', -1); }
   }
+  // ---- what ham%ObserT of the shipped Hamiltonians accumulates: Predefined_Obs_tau_Green / SpinMz / SpinSUN / Den_measure
+  // (Prog/Predefined_Obs_mod.F90:337-594), same layout as the device: acc[ch][nt][no_J][no_I][imj], bg[which][nt][no]
+  int lat_n_unit = 0, lat_norb = 1, obst_ntau = 0; std::vector<int> lat_cell, lat_orb, lat_imj; bool obst_on = false;
+  std::vector<cd> obst_acc, obst_bg; double obst_cnt[2] = {0, 0};
+  void obst_measure(int NT, const std::vector<std::vector<cd>>& GT0, const std::vector<std::vector<cd>>& G0T,
+                    const std::vector<std::vector<cd>>& G00, const std::vector<std::vector<cd>>& GTT) {
+    const int N = ndim, nu = lat_n_unit, nb = lat_norb, nb2 = nb * nb;
+    cd ZP = Phase / Phase.real(); double ZSr = Phase.real() >= 0 ? 1.0 : -1.0; cd ZS = ZSr;
+    if (NT == 0) { obst_cnt[0] += 1; obst_cnt[1] += ZSr; }
+    auto A = [&](int ch, int no_I, int no_J, int imj) -> cd& { return obst_acc[(((size_t)ch * obst_ntau + NT) * nb2 + no_I + nb * no_J) * nu + imj]; };
+    for (int I1 = 0; I1 < N; ++I1) {
+      const int I = lat_cell[I1]; if (I < 0) continue; const int no_I = lat_orb[I1];
+      cd ZI = 0; for (int nf = 0; nf < n_fl; ++nf) ZI += cd(1, 0) - GTT[nf][I1 + (size_t)I1 * N];
+      ZI *= (double)n_sun;
+      for (int J1 = 0; J1 < N; ++J1) {
+        const int J = lat_cell[J1]; if (J < 0) continue; const int no_J = lat_orb[J1];
+        const int imj = lat_imj[I + (size_t)J * nu];
+        cd Zg = 0, Zd = 0, ZJ = 0;
+        for (int nf = 0; nf < n_fl; ++nf) { Zg += GT0[nf][I1 + (size_t)J1 * N]; Zd -= G0T[nf][J1 + (size_t)I1 * N] * GT0[nf][I1 + (size_t)J1 * N]; ZJ += cd(1, 0) - G00[nf][J1 + (size_t)J1 * N]; }
+        ZJ *= (double)n_sun;
+        A(0, no_I, no_J, imj) += Zg / (double)n_fl * ZP * ZS;
+        if (n_fl == 2) {
+          cd ZZ = (GTT[0][I1 + (size_t)I1 * N] - GTT[1][I1 + (size_t)I1 * N]) * (G00[0][J1 + (size_t)J1 * N] - G00[1][J1 + (size_t)J1 * N])
+                - G0T[0][J1 + (size_t)I1 * N] * GT0[0][I1 + (size_t)J1 * N] - G0T[1][J1 + (size_t)I1 * N] * GT0[1][I1 + (size_t)J1 * N];
+          cd ZXY = -G0T[0][J1 + (size_t)I1 * N] * GT0[1][I1 + (size_t)J1 * N] - G0T[1][J1 + (size_t)I1 * N] * GT0[0][I1 + (size_t)J1 * N];
+          A(1, no_I, no_J, imj) += ZZ * ZP * ZS; A(2, no_I, no_J, imj) += ZXY * ZP * ZS;
+        } else A(1, no_I, no_J, imj) += -(double)n_sun * G0T[0][J1 + (size_t)I1 * N] * GT0[0][I1 + (size_t)J1 * N] * ZP * ZS;
+        A(3, no_I, no_J, imj) += (ZI * ZJ + Zd * (double)n_sun) * ZP * ZS;
+      }
+      if (n_fl == 2) obst_bg[((size_t)0 * obst_ntau + NT) * nb + no_I] += (GTT[1][I1 + (size_t)I1 * N] - GTT[0][I1 + (size_t)I1 * N]) * ZP * ZS;
+      obst_bg[((size_t)1 * obst_ntau + NT) * nb + no_I] += ZI * ZP * ZS;
+    }
+  }
   void obsert_hook(int nt, std::vector<std::vector<cd>>& GT0, std::vector<std::vector<cd>>& G0T,
                    std::vector<std::vector<cd>>& G00, std::vector<std::vector<cd>>& GTT) {
+    if (obst_on && nt >= 0 && nt < obst_ntau) {
+      if (symm) {
+        std::vector<std::vector<cd>> s0 = GT0, s1 = G0T, s2 = G00, s3 = GTT;
+        for (int nf = 0; nf < n_fl; ++nf) { hop_symm(s0[nf].data(), GT0[nf].data(), nf); hop_symm(s1[nf].data(), G0T[nf].data(), nf);
+                                           hop_symm(s2[nf].data(), G00[nf].data(), nf); hop_symm(s3[nf].data(), GTT[nf].data(), nf); }
+        obst_measure(nt, s0, s1, s2, s3);
+      } else obst_measure(nt, GT0, G0T, G00, GTT);
+    }
     if (!taum_capture) return;
     if (taum_capture > 1 && (nt % taum_capture) != 0) return;
     std::vector<cd> tmp((size_t)ndim * ndim);
@@ -1103,6 +1144,19 @@ long orc_taum_get(void* h, double* out, long cap_complex) {
   Oracle* o = (Oracle*)h; long n = (long)o->taum_buf.size();
   if (out) std::memcpy(out, o->taum_buf.data(), sizeof(cd) * std::min(n, cap_complex));
   return n;
+}
+void orc_obs_tau_enable(void* h, int n_unit, int norb, const int* cell, const int* orb, const int* imj) {   // tables 1-based, imj column-major
+  Oracle* o = (Oracle*)h; o->lat_n_unit = n_unit; o->lat_norb = norb; o->lat_cell.resize(o->ndim); o->lat_orb.resize(o->ndim); o->lat_imj.resize((size_t)n_unit * n_unit);
+  for (int i = 0; i < o->ndim; ++i) { o->lat_cell[i] = cell[i] - 1; o->lat_orb[i] = orb[i] - 1; }
+  for (size_t i = 0; i < o->lat_imj.size(); ++i) o->lat_imj[i] = imj[i] - 1;
+  o->obst_ntau = o->projector ? o->ltrot - 2 * o->thtrot + 1 : o->ltrot + 1;
+  o->obst_acc.assign((size_t)4 * o->obst_ntau * norb * norb * n_unit, cd(0)); o->obst_bg.assign((size_t)2 * o->obst_ntau * norb, cd(0));
+  o->obst_cnt[0] = o->obst_cnt[1] = 0; o->obst_on = true;
+}
+int orc_obs_tau_ntau(void* h) { return ((Oracle*)h)->obst_ntau; }
+void orc_get_obs_tau(void* h, double* acc, double* bg, double* cnt) {
+  Oracle* o = (Oracle*)h; std::memcpy(acc, o->obst_acc.data(), sizeof(cd) * o->obst_acc.size()); std::memcpy(bg, o->obst_bg.data(), sizeof(cd) * o->obst_bg.size());
+  cnt[0] = o->obst_cnt[0]; cnt[1] = o->obst_cnt[1];
 }
 void orc_get_obs(void* h, double* out) { Oracle* o = (Oracle*)h; for (int i = 0; i < 4; ++i) out[i] = o->obs_scal[i]; }
 void orc_eq_capture(void* h, int on) { Oracle* o = (Oracle*)h; o->eq_capture_on = on; o->eq_capture.clear(); }

@@ -181,6 +181,17 @@ class Oracle:
         lib().orc_get_obs(self.h, _d(out))
         return out
 
+    def obs_tau_enable(self):
+        n_unit, norb, cell, orb, imj = self.m.lattice_tables()
+        imj_f = np.ascontiguousarray(imj.T)
+        lib().orc_obs_tau_enable(self.h, int(n_unit), int(norb), cell.ctypes.data_as(_ip), orb.ctypes.data_as(_ip), imj_f.ctypes.data_as(_ip))
+        self._obst_dims = (4, lib().orc_obs_tau_ntau(self.h), int(norb), int(norb), int(n_unit))
+
+    def obs_tau(self):
+        acc = np.zeros(self._obst_dims, dtype=np.complex128); bg = np.zeros((2, self._obst_dims[1], self._obst_dims[2]), dtype=np.complex128); cnt = np.zeros(2)
+        lib().orc_get_obs_tau(self.h, _d(acc), _d(bg), _d(cnt))
+        return acc, bg, cnt[0], cnt[1]
+
     def eq_capture(self, on=True):
         lib().orc_eq_capture(self.h, int(on))
 

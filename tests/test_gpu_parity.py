@@ -610,3 +610,35 @@ def test_too_large_ndim_fails_loudly():
     with pytest.raises(AlfError) as ei:
         AlfB200(hubbard_square(26, 24, 0.2, U=0.0, checkerboard=True), n_chains=1, nwrap=2)
     assert "not supported" in str(ei.value)
+
+
+# ---------------------------------------------------------------------------------- device-side ObserT (time-displaced lattice observables)
+@pytest.mark.gpu
+@pytest.mark.parametrize("which", ["hubbard_mz_symm", "hubbard_su2", "hubbard_mz_nosymm", "kondo", "projector"])
+def test_obs_tau_on_device(which):
+    """Green / SpinZ / SpinXY / Den time-displaced correlation functions and their backgrounds, accumulated on the device where TAU_M /
+    Tau_p call ham%ObserT (with Hop_mod_Symm when Symm), against the oracle's restatement of Predefined_Obs_tau_*_measure."""
+    model = {"hubbard_mz_symm": lambda: hubbard_square(4, 4, 0.8), "hubbard_su2": lambda: hubbard_square(4, 4, 0.8, Mz=False),
+             "hubbard_mz_nosymm": lambda: hubbard_square(4, 2, 0.6, symm=False), "kondo": lambda: kondo_square(2, 2, 0.6),
+             "projector": lambda: hubbard_square(4, 4, 0.6, projector=True, theta=0.3, trial="dimer")}[which]()
+    seeds = SEEDS[:2]; nwrap = 4
+    g = AlfB200(model, n_chains=len(seeds), nwrap=nwrap); g.set_seeds(seeds); g.fields_set(); g.init_sweep(); g.obs_tau_enable()
+    orcs = []
+    for s in seeds:
+        o = Oracle(model, nwrap=nwrap); o.ranset(s); o.fields_set(); o.init(); o.obs_tau_enable(); orcs.append(o)
+    for sw in range(2):
+        g.sweep(1, 1)
+        for o in orcs:
+            o.sweep(1)
+    acc, bg, n, sg = g.obs_tau()
+    ro = [o.obs_tau() for o in orcs]
+    acc_o = sum(r[0] for r in ro); bg_o = sum(r[1] for r in ro); n_o = sum(r[2] for r in ro); sg_o = sum(r[3] for r in ro)
+    assert n == n_o == 2 * len(seeds) and sg == sg_o
+    assert acc.shape == acc_o.shape and acc.shape[1] == model.Ltrot - 2 * model.Thtrot + 1
+    for ch in range(4):
+        if np.abs(acc_o[ch]).max() > 0:
+            assert relF(acc[ch], acc_o[ch]) < 1e-9, ch
+        else:
+            assert np.abs(acc[ch]).max() == 0
+    assert np.abs(bg - bg_o).max() < 1e-9 * max(1.0, np.abs(bg_o).max())
+    g.close()
