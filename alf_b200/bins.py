@@ -67,3 +67,82 @@ def read_scal(file_pr: str):
             rest = rest[b + 1:]
         obs.append(vals); sign.append(float(rest))
     return np.asarray(obs), np.asarray(sign)
+
+
+# ----------------------------------------------------------------------------------------------- lattice observables
+def fourier_r_to_k(x_r, latt):
+    """FT_R_to_K_C (Libraries/Modules/lattices_v3_mod.F90:847-876): X(k) = 1/N sum_r exp(-i k.r) X(r) on the k-points
+    k = m1 b1_p + m2 b2_p, b_p = 2 pi / L (square-type Bravais lattice with orthogonal unit vectors: listk enumerates like list)."""
+    pts = np.asarray(latt.list, dtype=np.float64)                      # (N, 2) integer coordinates of r and of k
+    kv = pts * np.array([2.0 * np.pi / latt.L1, 2.0 * np.pi / latt.L2])
+    phase = np.exp(-1j * (kv @ pts.T))                                 # [k, r]
+    return (phase @ np.asarray(x_r, dtype=np.complex128)) / latt.N, kv
+
+
+def print_bin_latt(name, obs_sum, bg_sum, sign_sum, n_meas_per_chain, n_chains, latt, dtau=None, channel="---"):
+    """Print_bin_Latt (Prog/observables_mod.F90:355-515), text layout (:494-512): appends one bin to `<name>_tau` (or `<name>_eq` if
+    there is a single time point).  obs_sum[nt, no, no1, r]: real-space accumulator summed over chains (Obs_Latt(imj, nt, no, no1));
+    bg_sum[no]: Obs_Latt0 summed over chains and time points; n_meas_per_chain = Obs%N."""
+    obs_sum = np.asarray(obs_sum, dtype=np.complex128); ntau, norb, _, ns = obs_sum.shape
+    assert ns == latt.N
+    suffix = "_eq" if ntau == 1 else "_tau"
+    file_pr = name + suffix
+    norm = float(n_meas_per_chain) * float(n_chains)
+    obs = obs_sum / norm                                               # Obs_Latt / N, averaged over ranks
+    bg = np.asarray(bg_sum, dtype=np.complex128) / (norm * ns * ntau)  # Obs_Latt0 / (N Ns Ntau)
+    ave_sign = float(sign_sum) / norm
+    info = file_pr + "_info"
+    if not os.path.exists(info):
+        with open(info, "w") as f:
+            f.write(f"{'Observable':>20s}: {os.path.basename(file_pr)}\n{'Channel':>20s}: {channel}\n{'Ntau':>20s}: {ntau:10d}\n")
+            f.write(f"{'dtau':>20s}: " + _e(dtau or 0.0, 26) + "\n       ====== Bravais Lattice ======\n")
+            f.write(f"{'Unit cells':>20s}: {latt.N:10d}\n{'L1':>20s}: " + _e(float(latt.L1), 26) + _e(0.0, 26) + "\n")
+            f.write(f"{'L2':>20s}: " + _e(0.0, 26) + _e(float(latt.L2), 26) + "\n")
+            f.write(f"{'a1':>20s}: " + _e(1.0, 26) + _e(0.0, 26) + f"\n{'a2':>20s}: " + _e(0.0, 26) + _e(1.0, 26) + "\n")
+            f.write("       ========= Unit cell =========\n" + f"{'Number of orbitals':>20s}: {norb:10d}\n")
+    lines = []
+    if ntau == 1:
+        lines.append(_e(ave_sign, 25) + f"{norb:11d}{latt.N:11d}")
+    else:
+        lines.append(_e(ave_sign, 25) + f"{norb:11d}{latt.N:11d}{ntau:11d}" + _e(dtau or 0.0, 26))
+    for no in range(norb):
+        lines.append("(" + _e(bg[no].real, 25) + "," + _e(bg[no].imag, 25) + ")")
+    xk = None
+    obs_k = np.zeros_like(obs)
+    for nt in range(ntau):
+        for no in range(norb):
+            for no1 in range(norb):
+                obs_k[nt, no, no1], xk = fourier_r_to_k(obs[nt, no, no1], latt)
+    for i in range(latt.N):
+        lines.append(_e(xk[i, 0], 25) + " " + _e(xk[i, 1], 25))
+        for nt in range(ntau):
+            for no in range(norb):
+                for no1 in range(norb):
+                    z = obs_k[nt, no, no1, i]
+                    lines.append("(" + _e(z.real, 25) + "," + _e(z.imag, 25) + ")")
+    with open(file_pr, "a") as f:
+        f.write("\n".join(lines) + "\n")
+    return file_pr
+
+
+def read_latt(file_pr):
+    """What Analysis/ana_mod.F90:57-220 (read_latt) does with a `_tau` / `_eq` file: returns a list of bins
+    (sign, bg[norb], k[N, 2], obs[k, nt, no, no1])."""
+    toks = open(file_pr).read().split("\n")
+    pos = 0; bins = []
+
+    def cplx(s):
+        a, b = s.strip()[1:-1].split(","); return complex(float(a), float(b))
+    while pos < len(toks) and toks[pos].strip():
+        hdr = toks[pos].split(); pos += 1
+        sign, norb, n = float(hdr[0]), int(hdr[1]), int(hdr[2]); ntau = int(hdr[3]) if len(hdr) > 3 else 1
+        bg = [cplx(toks[pos + k]) for k in range(norb)]; pos += norb
+        ks = np.zeros((n, 2)); obs = np.zeros((n, ntau, norb, norb), dtype=np.complex128)
+        for i in range(n):
+            ks[i] = [float(x) for x in toks[pos].split()]; pos += 1
+            for nt in range(ntau):
+                for no in range(norb):
+                    for no1 in range(norb):
+                        obs[i, nt, no, no1] = cplx(toks[pos]); pos += 1
+        bins.append((sign, np.array(bg), ks, obs))
+    return bins

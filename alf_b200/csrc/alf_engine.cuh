@@ -720,6 +720,7 @@ struct Engine : EngineBase {
   }
   // ---- device-side ObserT (alf_obs_tau.cuh): symmetrised copies of the four matrices, then one binning kernel per time point
   LattDev lt; T* obsS[4] = {nullptr, nullptr, nullptr, nullptr}; size_t obst_smem = 0;
+  const T* g00_sym_of = nullptr;     // which buffer obsS[2] is the symmetrised copy of (reset whenever G00's content is rewritten)
   void obs_tau_setup() override {
     if (lt.cell) return;
     if (h->n_unit <= 0 || (int)h->site_cell.size() != N) throw CudaError("obs_tau: alf_b200_set_lattice has not been called");
@@ -736,8 +737,11 @@ struct Engine : EngineBase {
     obs_tau_setup();
     const T* src[4] = {GT0, G0T, G00, GTT}; const T* use[4];
     for (int q = 0; q < 4; ++q) {
-      if (h->symm) { CK(cudaMemcpyAsync(obsS[q], src[q], sizeof(T) * n2 * NM, cudaMemcpyDeviceToDevice, st)); hop_symm(obsS[q]); use[q] = obsS[q]; }
-      else use[q] = src[q];
+      if (!h->symm) { use[q] = src[q]; continue; }
+      use[q] = obsS[q];
+      if (q == 2 && g00_sym_of == G00) continue;          // G(0,0) only changes at the stabilisation points: its symmetrised copy is reused
+      CK(cudaMemcpyAsync(obsS[q], src[q], sizeof(T) * n2 * NM, cudaMemcpyDeviceToDevice, st)); hop_symm(obsS[q]);
+      if (q == 2) g00_sym_of = G00;
     }
     KL(KC_OBS, st, k_obs_tau<T><<<C, 256, obst_smem, st>>>(use[0], use[1], use[2], use[3], n2, N, F, h->n_sun, h->d_phase, lt, nt_index, h->obst_ntau,
                                                         h->d_obst_acc, h->d_obst_bg, h->d_obst_cnt));
@@ -749,6 +753,7 @@ struct Engine : EngineBase {
   void tau_m() override {
     taum_alloc();
     const size_t bytes = sizeof(T) * n2 * NM; dim3 eg(ew_blocks(n2), NM);
+    g00_sym_of = nullptr;
     CK(cudaMemcpyAsync(G00, G, bytes, cudaMemcpyDeviceToDevice, st)); CK(cudaMemcpyAsync(GT0, G, bytes, cudaMemcpyDeviceToDevice, st));
     CK(cudaMemcpyAsync(GTT, G, bytes, cudaMemcpyDeviceToDevice, st));
     KL(KC_EW, st, k_g0t_init<T><<<eg, 256, 0, st>>>(G0T, G, n2, N));
@@ -763,7 +768,7 @@ struct Engine : EngineBase {
         wrapur_on(udvr2, stab_nt[NST - 1], NT1);
         la_cgr2_2<T>(w, w2, h->stab, udvr2, udvst[NST - 1], tmN[0], tmN[1], tmN[2], tmN[3], d_first);
         compare_tau(G, tmN[1]); compare_tau(GTT, tmN[2]); compare_tau(GT0, tmN[0]); compare_tau(G0T, tmN[3]);
-        std::swap(GT0, tmN[0]); std::swap(G00, tmN[1]); std::swap(GTT, tmN[2]); std::swap(G0T, tmN[3]);
+        std::swap(GT0, tmN[0]); std::swap(G00, tmN[1]); std::swap(GTT, tmN[2]); std::swap(G0T, tmN[3]); g00_sym_of = nullptr;
         taum_capture(NT1, true);
         NST++;
       }
@@ -787,6 +792,7 @@ struct Engine : EngineBase {
       proprm1(GTT, NT); propr(GTT, NT);
       if (NT_ST + 1 <= S && NT == stab_nt[NT_ST + 1]) { restab(); CK(cudaMemcpyAsync(GTT, GRUP, bytes, cudaMemcpyDeviceToDevice, st)); NT_ST++; }
     }
+    g00_sym_of = nullptr;
     CK(cudaMemcpyAsync(G00, GTT, bytes, cudaMemcpyDeviceToDevice, st)); CK(cudaMemcpyAsync(GT0, GTT, bytes, cudaMemcpyDeviceToDevice, st));
     KL(KC_EW, st, k_g0t_init<T><<<eg, 256, 0, st>>>(G0T, GTT, n2, N));                     // G0T = GTT - 1
     taum_capture(0); obsert(0);

@@ -261,6 +261,16 @@ def run_b200(args):
     g.sweep(1, args.ltau)
     cat_stats = g.kernel_stats(); cat_flops = g.kernel_flops()
     g.kernel_timing(0)
+    with_obsert = None
+    if args.ltau and args.obs_tau:           # the same sweep with the device-side ObserT (time-displaced Green / spin / density correlations) switched on
+        for gk in gs:
+            gk.obs_tau_enable(True)
+        on_all(lambda k: gs[k].sweep(1, args.ltau))
+        ot_ms = timed(lambda k: gs[k].sweep(1, args.ltau))
+        for gk in gs:
+            gk.obs_tau_enable(False)
+        with_obsert = {"value": world * H * C / (ot_ms * 1e-3), "unit": UNIT, "ms_per_step": ot_ms, "steps": 1,
+                       "note": "sweep + TAU_M + device-side ObserT: Hop_mod_Symm of GT0, G0T, G00, GTT and Predefined_Obs_tau_Green/SpinMz/Den at every time point"}
     eq_only = None
     if args.ltau:
         eq_ms = timed(lambda k: gs[k].sweep(1, 0))
@@ -320,7 +330,7 @@ def run_b200(args):
                 "acceptance": acc / max(nprop, 1), "precision_green_max": max(c["XMAXG"] for c in c1),
                 "clocks": clk, "roofline": roof, "cpu_baseline": cpu,
                 "fp64_kernels": fp64_kernels, "fp64_peak_measured": {"dfma_tflops": dfma, "dmma_tflops": dmma},
-                "breakdown_ms_per_sweep": {k: round(v[0], 3) for k, v in cat_stats.items()}, "equal_time_only": eq_only}
+                "breakdown_ms_per_sweep": {k: round(v[0], 3) for k, v in cat_stats.items()}, "equal_time_only": eq_only, "with_device_obsert": with_obsert}
     for gk in gs:
         gk.close()
     if world > 1:
@@ -344,6 +354,7 @@ def main():
     ap.add_argument("--ltau", type=int, default=1, help="1: the sweep includes TAU_M (BASELINE configs[2]: time-displaced Green functions); 0: equal-time only")
     ap.add_argument("--cpu-cores", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--obs-tau", type=int, default=1, help="also time one sweep with the device-side ObserT on (reported as with_device_obsert; not part of value)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

@@ -25,3 +25,32 @@ def test_scal_record_layout_and_roundtrip(tmp_path):
     assert obs.shape == (2, 1) and np.allclose(obs[:, 0], [16.0, 17.0]) and np.allclose(sign, 1.0)
     info = open(p + "_info").read()
     assert "====== Analysis Mode ======" in info and "identity" in info and "Particle number" in info
+
+
+def test_latt_bin_layout_fourier_and_roundtrip(tmp_path):
+    """`_tau` records (Prog/observables_mod.F90:494-512): header, backgrounds, then per k-point Ntau*Norb*Norb values; Fourier_R_to_K
+    convention X(k) = 1/N sum_r exp(-i k r) X(r) (lattices_v3_mod.F90:847-876)."""
+    from alf_b200.bins import fourier_r_to_k, print_bin_latt, read_latt
+    from alf_b200.model import Lattice
+    latt = Lattice(4, 2); ntau, norb, nchains, nmeas = 3, 1, 5, 2
+    r0 = latt.invlist[(0, 0)] - 1; r1 = latt.invlist[(1, 0)] - 1
+    x = np.zeros(latt.N, dtype=complex); x[r0] = 8.0
+    xk, kv = fourier_r_to_k(x, latt)
+    assert np.allclose(xk, 1.0)                                        # delta function at the origin -> constant 8 / N
+    x[:] = 0; x[r1] = 8.0
+    xk, kv = fourier_r_to_k(x, latt)
+    assert np.allclose(xk, np.exp(-1j * kv[:, 0]))                     # shifted by a_1: phase exp(-i k_x)
+    obs = np.zeros((ntau, norb, norb, latt.N), dtype=complex)
+    for nt in range(ntau):
+        obs[nt, 0, 0, r0] = 8.0 * (nt + 1) * nchains * nmeas           # accumulators are sums over chains and measurements
+    p = print_bin_latt(str(tmp_path / "Green"), obs, [2.0 * nchains * nmeas * latt.N * ntau], nchains * nmeas * 1.0, nmeas, nchains, latt, dtau=0.1)
+    p = print_bin_latt(str(tmp_path / "Green"), obs, [2.0 * nchains * nmeas * latt.N * ntau], nchains * nmeas * 1.0, nmeas, nchains, latt, dtau=0.1)
+    assert p.endswith("Green_tau")
+    first = open(p).readline()
+    assert len(first.rstrip("\n")) == 25 + 3 * 11 + 26 and first.split()[1:4] == ["1", "8", "3"]
+    bins = read_latt(p)
+    assert len(bins) == 2
+    sign, bg, ks, o = bins[1]
+    assert sign == 1.0 and np.allclose(bg, [2.0]) and o.shape == (8, 3, 1, 1)
+    assert np.allclose(o[:, :, 0, 0], np.array([1.0, 2.0, 3.0])[None, :])
+    assert "Unit cells" in open(p + "_info").read()
