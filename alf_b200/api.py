@@ -161,6 +161,18 @@ class AlfB200:
         self._ck(lib().alf_b200_set_lattice(self.h, int(n_unit), int(norb), cell.ctypes.data_as(_ip), orb.ctypes.data_as(_ip), imj_f.ctypes.data_as(_ip)))
         self._ck(lib().alf_b200_obs_tau_enable(self.h, int(on)))
 
+    def obs_eq_enable(self, on=True):
+        n_unit, norb, cell, orb, imj = self.m.lattice_tables()
+        imj_f = np.ascontiguousarray(imj.T)
+        self._ck(lib().alf_b200_set_lattice(self.h, int(n_unit), int(norb), cell.ctypes.data_as(_ip), orb.ctypes.data_as(_ip), imj_f.ctypes.data_as(_ip)))
+        self._ck(lib().alf_b200_obs_eq_enable(self.h, int(on)))
+
+    def obs_eq(self):
+        n_unit, norb = self.m.latt.N, self.m.n_orb
+        acc = np.zeros((4, 1, norb, norb, n_unit), dtype=np.complex128); bg = np.zeros((2, 1, norb), dtype=np.complex128); cnt = np.zeros(2)
+        self._ck(lib().alf_b200_get_obs_eq(self.h, _d(acc), _d(bg), _d(cnt)))
+        return acc, bg, cnt[0], cnt[1]
+
     def obs_tau_reset(self):
         self._ck(lib().alf_b200_obs_tau_reset(self.h))
 

@@ -59,6 +59,7 @@ int alf_b200_destroy(alf_b200_handle* h) {
   if (t_prof == &h->prof) t_prof = nullptr;          // the launch-accounting pointer must not outlive its handle
   h->eng.reset();
   if (h->d_fields) cudaFree(h->d_fields); if (h->d_rng) cudaFree(h->d_rng); if (h->d_phase) cudaFree(h->d_phase);
+  if (h->d_obse_acc) cudaFree(h->d_obse_acc); if (h->d_obse_bg) cudaFree(h->d_obse_bg); if (h->d_obse_cnt) cudaFree(h->d_obse_cnt);
   if (h->d_obst_acc) cudaFree(h->d_obst_acc); if (h->d_obst_bg) cudaFree(h->d_obst_bg); if (h->d_obst_cnt) cudaFree(h->d_obst_cnt);
   if (h->d_counters) cudaFree(h->d_counters); if (h->d_ctl) cudaFree(h->d_ctl); if (h->d_acclog) cudaFree(h->d_acclog); if (h->d_obs) cudaFree(h->d_obs);
   if (h->pin_fields) cudaFreeHost(h->pin_fields);
@@ -235,6 +236,29 @@ int alf_b200_obs_tau_enable(alf_b200_handle* h, int on) {
     h->eng->obs_tau_setup();
   }
   h->obs_tau_on = on != 0;
+  API_END(h)
+}
+// equal-time lattice observables (Predefined_Obs_eq_*), accumulated at every measured slice of the sweep
+int alf_b200_obs_eq_enable(alf_b200_handle* h, int on) {
+  API_BEGIN(h) NEED_FINAL(h)
+  if (on && !h->d_obse_acc) {
+    if (h->n_unit <= 0) { h->err = "obs_eq_enable: call alf_b200_set_lattice first"; return ALF_ERROR_GENERIC; }
+    const size_t na = (size_t)2 * OBST_NCH * h->norb * h->norb * h->n_unit, nb = (size_t)2 * 2 * h->norb;
+    CK(cudaMalloc(&h->d_obse_acc, sizeof(double) * na)); CK(cudaMalloc(&h->d_obse_bg, sizeof(double) * nb)); CK(cudaMalloc(&h->d_obse_cnt, sizeof(double) * 2));
+    CK(cudaMemsetAsync(h->d_obse_acc, 0, sizeof(double) * na, h->stream)); CK(cudaMemsetAsync(h->d_obse_bg, 0, sizeof(double) * nb, h->stream));
+    CK(cudaMemsetAsync(h->d_obse_cnt, 0, sizeof(double) * 2, h->stream));
+    h->eng->obs_tau_setup();
+  }
+  h->obs_eq_on = on != 0;
+  API_END(h)
+}
+int alf_b200_get_obs_eq(alf_b200_handle* h, double* acc, double* bg, double* cnt) {
+  API_BEGIN(h) NEED_FINAL(h) if (!h->d_obse_acc) return ALF_ERROR_GENERIC;
+  const size_t na = (size_t)2 * OBST_NCH * h->norb * h->norb * h->n_unit, nb = (size_t)2 * 2 * h->norb;
+  CK(cudaStreamSynchronize(h->stream));
+  if (acc) CK(cudaMemcpy(acc, h->d_obse_acc, sizeof(double) * na, cudaMemcpyDeviceToHost));
+  if (bg) CK(cudaMemcpy(bg, h->d_obse_bg, sizeof(double) * nb, cudaMemcpyDeviceToHost));
+  if (cnt) CK(cudaMemcpy(cnt, h->d_obse_cnt, sizeof(double) * 2, cudaMemcpyDeviceToHost));
   API_END(h)
 }
 int alf_b200_obs_tau_reset(alf_b200_handle* h) {

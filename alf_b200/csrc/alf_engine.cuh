@@ -151,6 +151,7 @@ struct alf_b200_handle {
   // lattice tables for the device-side lattice observables (0-based; site -> unit cell / orbital, imj(I,J) column-major)
   int n_unit = 0, norb = 1; std::vector<int> site_cell, site_orb, imj;
   bool obs_tau_on = false; double *d_obst_acc = nullptr, *d_obst_bg = nullptr, *d_obst_cnt = nullptr; int obst_ntau = 0;
+  bool obs_eq_on = false; double *d_obse_acc = nullptr, *d_obse_bg = nullptr, *d_obse_cnt = nullptr;      // equal-time lattice observables (one time point)
   // projective algorithm (Prog/Hamiltonian_main_mod.F90:181-197: Projector, Thtrot, WF_L, WF_R)
   bool projector = false; int thtrot = 0, n_part = 0; std::vector<std::vector<cd>> wf_l, wf_r;   // per flavor, Ndim x N_part column-major
 };
@@ -517,11 +518,12 @@ struct Engine : EngineBase {
   }
 
   // ---------------------------------------------------------------- op-list launches
-  void apply_ops(T* Mx, int side, int mode, int nt_a, int nt_b, int nvec = -1, const ModelDev* mdo = nullptr) {     // nvec: number of columns (side 0) / rows (side 1)
+  void apply_ops(T* Mx, int side, int mode, int nt_a, int nt_b, int nvec = -1, const ModelDev* mdo = nullptr, T* Mout = nullptr) {   // nvec: columns (side 0) / rows (side 1)
     if (nvec < 0) nvec = N;
+    if (!Mout) Mout = Mx;                          // in place unless a result buffer is given (full matrices only)
     const ModelDev& md = mdo ? *mdo : this->md;
     dim3 grid((nvec + OPS_PW - 1) / OPS_PW, NM);
-#define OPS_LAUNCH(SD, LKV) KL(KC_OPS, st, k_apply_ops<T, SD, LKV><<<grid, 256, ops_smem, st>>>(Mx, n2, N, nvec, md, F, mode, nt_a, nt_b, h->d_fields, L, M))
+#define OPS_LAUNCH(SD, LKV) KL(KC_OPS, st, k_apply_ops<T, SD, LKV><<<grid, 256, ops_smem, st>>>(Mx, n2, N, nvec, md, F, mode, nt_a, nt_b, h->d_fields, L, M, Mout))
     if (side == 0) { if (ops_lk == 0) OPS_LAUNCH(0, 0); else if (ops_lk == 1) OPS_LAUNCH(0, 1); else OPS_LAUNCH(0, 2); }
     else { if (ops_lk == 0) OPS_LAUNCH(1, 0); else if (ops_lk == 1) OPS_LAUNCH(1, 1); else OPS_LAUNCH(1, 2); }
 #undef OPS_LAUNCH
@@ -649,6 +651,17 @@ struct Engine : EngineBase {
     const int lobs_st = proj ? thtrot + 1 : 1, lobs_en = proj ? L - thtrot : L;
     if (ntau1 < lobs_st || ntau1 > lobs_en) return;
     KL(KC_OBS, st, k_obs_scalar<T><<<C, 128, 0, st>>>(G, n2, N, F, h->n_sun, h->d_phase, h->d_obs));
+    if (h->obs_eq_on) {      // equal-time lattice observables on the symmetrised G (main.F90:761-764 hands GR_Tilde to ham%Obser)
+      obs_tau_setup();
+      const T* gs = G;
+      if (h->symm) {
+        if (dense_t) { CK(cudaMemcpyAsync(obsS[0], G, sizeof(T) * n2 * NM, cudaMemcpyDeviceToDevice, st)); hop_symm(obsS[0]); }
+        else { apply_ops(G, 0, MODE_TL_HALF, 0, 0, -1, nullptr, obsS[0]); apply_ops(obsS[0], 1, MODE_TR_HALFINV, 0, 0); }
+        gs = obsS[0];
+      }
+      KL(KC_EW, st, k_g0t_init<T><<<dim3(ew_blocks(n2), NM), 256, 0, st>>>(obsS[1], gs, n2, N));      // G - 1
+      KL(KC_OBS, st, k_obs_tau<T, 1><<<C, 256, obst_smem, st>>>(gs, obsS[1], gs, gs, n2, N, F, h->n_sun, h->d_phase, lt, 0, 1, h->d_obse_acc, h->d_obse_bg, h->d_obse_cnt));
+    }
   }
 
   // main.F90:714-887
@@ -730,7 +743,8 @@ struct Engine : EngineBase {
     for (int q = 0; q < 4; ++q) obsS[q] = dalloc<T>(n2 * NM);
     obst_smem = obs_tau_smem<T>(N, lt.n_unit, lt.norb);
     if (obst_smem > 227 * 1024) throw CudaError("obs_tau: lattice too large for the shared-memory bins");
-    CK(cudaFuncSetAttribute(k_obs_tau<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)obst_smem));
+    CK(cudaFuncSetAttribute(k_obs_tau<T, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)obst_smem));
+    CK(cudaFuncSetAttribute(k_obs_tau<T, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)obst_smem));
   }
   void obsert(int nt_index) {      // where TAU_M / Tau_p call ham%ObserT(nt_index, GT0, G0T, G00, GTT, Phase): tau_m_mod.F90:115-124,151-177
     if (!h->obs_tau_on || nt_index < 0 || nt_index >= h->obst_ntau) return;
@@ -740,10 +754,13 @@ struct Engine : EngineBase {
       if (!h->symm) { use[q] = src[q]; continue; }
       use[q] = obsS[q];
       if (q == 2 && g00_sym_of == G00) continue;          // G(0,0) only changes at the stabilisation points: its symmetrised copy is reused
-      CK(cudaMemcpyAsync(obsS[q], src[q], sizeof(T) * n2 * NM, cudaMemcpyDeviceToDevice, st)); hop_symm(obsS[q]);
+      if (dense_t) { CK(cudaMemcpyAsync(obsS[q], src[q], sizeof(T) * n2 * NM, cudaMemcpyDeviceToDevice, st)); hop_symm(obsS[q]); }
+      else {     // Hop_mod_Symm out of place: the left half step reads the source and writes the copy, the right one works on the copy
+        apply_ops(const_cast<T*>(src[q]), 0, MODE_TL_HALF, 0, 0, -1, nullptr, obsS[q]); apply_ops(obsS[q], 1, MODE_TR_HALFINV, 0, 0);
+      }
       if (q == 2) g00_sym_of = G00;
     }
-    KL(KC_OBS, st, k_obs_tau<T><<<C, 256, obst_smem, st>>>(use[0], use[1], use[2], use[3], n2, N, F, h->n_sun, h->d_phase, lt, nt_index, h->obst_ntau,
+    KL(KC_OBS, st, k_obs_tau<T, 0><<<C, 256, obst_smem, st>>>(use[0], use[1], use[2], use[3], n2, N, F, h->n_sun, h->d_phase, lt, nt_index, h->obst_ntau,
                                                         h->d_obst_acc, h->d_obst_bg, h->d_obst_cnt));
   }
   void compare_tau(const T* A, const T* B) {   // Control_Precision_tau, control_mod.F90:300-311

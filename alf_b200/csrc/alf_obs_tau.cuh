@@ -18,7 +18,10 @@
 struct LattDev { int n_unit = 0, norb = 1; const int* cell = nullptr; const int* orb = nullptr; const int* imj = nullptr; };   // 0-based tables
 
 // acc: [ch][nt][no_J][no_I][imj] complex; bg: [2][nt][norb] complex; cnt: [0] N (chain-measurements at nt = 0), [1] sum ZS
-template <typename T>
+// EQ = 1: the equal-time variants Predefined_Obs_eq_Green / SpinMz / SpinSUN / Den_measure (Predefined_Obs_mod.F90:77-325) on the inputs
+// GT0 = GTT = G00 = G, G0T = G - 1 (so that -G0T(J1,I1) = GRC(I1,J1)): SpinZ, SpinXY and Den coincide with the formulas above; Green is
+// N_SUN sum_nf GRC(I1,J1,nf) and the SpinZ background GRC(I1,I1,2) - GRC(I1,I1,1) has the opposite sign.
+template <typename T, int EQ>
 __global__ void __launch_bounds__(256) k_obs_tau(const T* __restrict__ GT0, const T* __restrict__ G0T, const T* __restrict__ G00, const T* __restrict__ GTT,
                                                  long sM, int N, int F, int n_sun, const cplx* __restrict__ phase, LattDev lt, int nt, int ntau,
                                                  double* __restrict__ acc, double* __restrict__ bg, double* __restrict__ cnt) {
@@ -63,7 +66,8 @@ __global__ void __launch_bounds__(256) k_obs_tau(const T* __restrict__ GT0, cons
             zi = zi + (cplx(1.0, 0.0) - cplx(real_(a), imag_(a))); zj = zj + (cplx(1.0, 0.0) - cplx(real_(b), imag_(b)));
             zz = zz - g0t[f] * gt0[f]; gsum = gsum + gt0[f];
           }
-          v[0] = gsum * (1.0 / (double)F);
+          if (EQ) { cplx gc = cplx(0.0, 0.0); for (int f = 0; f < F && f < 2; ++f) gc = gc - g0t[f]; v[0] = gc * (double)n_sun; }
+          else v[0] = gsum * (1.0 / (double)F);
           if (F >= 2) {
             const T a1 = dTT[i], a2 = dTT[N + i], b1 = d00[j], b2 = d00[N + j];
             const cplx da = cplx(real_(a1) - real_(a2), imag_(a1) - imag_(a2)), db = cplx(real_(b1) - real_(b2), imag_(b1) - imag_(b2));
@@ -95,7 +99,7 @@ __global__ void __launch_bounds__(256) k_obs_tau(const T* __restrict__ GT0, cons
       cplx zi = cplx(0.0, 0.0);
       for (int f = 0; f < F && f < 2; ++f) { const T a = dTT[f * N + i]; zi = zi + (cplx(1.0, 0.0) - cplx(real_(a), imag_(a))); }
       bd = bd + zi * (double)n_sun;
-      if (F >= 2) { const T a1 = dTT[i], a2 = dTT[N + i]; bz = bz + cplx(real_(a2) - real_(a1), imag_(a2) - imag_(a1)); }
+      if (F >= 2) { const T a1 = dTT[i], a2 = dTT[N + i]; const cplx dd = cplx(real_(a2) - real_(a1), imag_(a2) - imag_(a1)); bz = EQ ? bz - dd : bz + dd; }
     }
     bz = bz * zpzs; bd = bd * zpzs;
     double* b0 = bg + 2 * ((size_t)(0 * ntau + nt) * norb + tid); double* b1 = bg + 2 * ((size_t)(1 * ntau + nt) * norb + tid);

@@ -125,8 +125,8 @@ __device__ __forceinline__ void ops_process_chunk(T* __restrict__ S, bool lane_o
 // SIDE 1: panel of OPS_PW rows    [v0, v0+pw) of M;  S[i][j] = M(v0+j, i)   (right multiplication = left on the transpose)
 // grid = (ceil(nvec/OPS_PW), n_matrices); matrix b belongs to chain b / F, flavor b % F.  LK = log2 of the largest operator size.
 template <typename T, int SIDE, int LK>
-__global__ void __launch_bounds__(256) k_apply_ops(T* __restrict__ M, long sM, int N, int nvec, ModelDev md, int F, int mode,
-                                                   int nt_a, int nt_b, const int8_t* __restrict__ fields, int Ltrot, int n_opv) {
+__global__ void __launch_bounds__(256) k_apply_ops(T* M, long sM, int N, int nvec, ModelDev md, int F, int mode,
+                                                   int nt_a, int nt_b, const int8_t* __restrict__ fields, int Ltrot, int n_opv, T* Mout) {   // Mout: result buffer (may be M)
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int ldp = OPS_PW + 1, ms = 1 << (2 * LK), kk = 1 << LK;
   constexpr int MPT = (OPS_CH * ms + 255) / 256;       // descriptor-matrix entries prefetched per thread
@@ -134,7 +134,7 @@ __global__ void __launch_bounds__(256) k_apply_ops(T* __restrict__ M, long sM, i
   T* dMb = S + ((N * ldp + 1) & ~1);                  // keeps the int4 descriptor arrays 16-byte aligned
   int4* dPb = reinterpret_cast<int4*>(dMb + 2 * OPS_CH * ms);
   const int b = blockIdx.y, chain = b / F, f = b % F;
-  M += (long)b * sM;
+  M += (long)b * sM; Mout += (long)b * sM;
   const int v0 = blockIdx.x * OPS_PW;
   const int pw = min(OPS_PW, nvec - v0);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
@@ -226,8 +226,8 @@ __global__ void __launch_bounds__(256) k_apply_ops(T* __restrict__ M, long sM, i
   }
   // ---- write back
   if (SIDE == 0) {
-    for (int j = warp; j < pw; j += nw) { T* col = M + (long)(v0 + j) * N; for (int i = lane; i < N; i += 32) col[i] = S[i * ldp + j]; }
+    for (int j = warp; j < pw; j += nw) { T* col = Mout + (long)(v0 + j) * N; for (int i = lane; i < N; i += 32) col[i] = S[i * ldp + j]; }
   } else {
-    if (lane < pw) { T* dst = M + v0 + lane; for (int i = warp; i < N; i += nw) dst[(long)i * N] = S[i * ldp + lane]; }
+    if (lane < pw) { T* dst = Mout + v0 + lane; for (int i = warp; i < N; i += nw) dst[(long)i * N] = S[i * ldp + lane]; }
   }
 }

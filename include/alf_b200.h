@@ -96,6 +96,11 @@ int alf_b200_tau_p(alf_b200_handle* h, int nst_in);           /* Prog/tau_p_mod.
 int alf_b200_set_lattice(alf_b200_handle* h, int n_unit, int norb, const int* site_cell, const int* site_orb, const int* imj);
 int alf_b200_obs_tau_enable(alf_b200_handle* h, int on);
 int alf_b200_obs_tau_reset(alf_b200_handle* h);
+/* equal-time variants (Predefined_Obs_eq_Green / SpinMz / SpinSUN / Den_measure, Predefined_Obs_mod.F90:77-325) accumulated at every
+ * measured slice of the sweep where main.F90:757-773,789-802 call ham%Obser; same layout with a single time point; cnt[0] counts
+ * chain-measurements */
+int alf_b200_obs_eq_enable(alf_b200_handle* h, int on);
+int alf_b200_get_obs_eq(alf_b200_handle* h, double* acc, double* bg, double* cnt);
 int alf_b200_obs_tau_dims(const alf_b200_handle* h, int* n_channels, int* ntau, int* norb, int* n_unit);
 int alf_b200_get_obs_tau(alf_b200_handle* h, double* acc, double* bg, double* cnt);
 

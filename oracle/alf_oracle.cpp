@@ -813,6 +813,7 @@ struct Oracle {
   }
 
   std::vector<cd> eq_capture; int eq_capture_on = 0;   // G handed to ham%Obser: [visit][nf][N*N]
+  bool obse_on = false; std::vector<cd> obse_acc, obse_bg; double obse_cnt[2] = {0, 0};      // equal-time lattice observables (lattice tables: obst_* below)
   double obs_scal[4] = {0, 0, 0, 0};   // [0] N_meas, [1] sum ZS, [2..3] sum Part ZP ZS  (same model-independent scalars as the device)
   void obser_hook(int ntau1) {
     const int lobs_st = projector ? thtrot + 1 : 1, lobs_en = projector ? ltrot - thtrot : ltrot;   // QMC_runtime_var_mod.F90:156-189
@@ -821,6 +822,39 @@ struct Oracle {
       cd tr = 0; for (int nf = 0; nf < n_fl; ++nf) for (int i = 0; i < ndim; ++i) tr += cd(1, 0) - GR[nf][i + (size_t)i * ndim];
       cd ZP = Phase / Phase.real(); double ZS = Phase.real() >= 0 ? 1.0 : -1.0; cd v = tr * (double)n_sun * ZP * ZS;
       obs_scal[0] += 1; obs_scal[1] += ZS; obs_scal[2] += v.real(); obs_scal[3] += v.imag();
+    }
+    if (obse_on) {   // Predefined_Obs_eq_Green / SpinMz / SpinSUN / Den_measure (Prog/Predefined_Obs_mod.F90:77-325) on GR_Tilde (main.F90:761-764)
+      const int N = ndim, nu = lat_n_unit, nb = lat_norb, nb2 = nb * nb;
+      std::vector<std::vector<cd>> GRt(n_fl, std::vector<cd>((size_t)N * N)), GRC = GRt;
+      for (int nf = 0; nf < n_fl; ++nf) {
+        if (symm) hop_symm(GRt[nf].data(), GR[nf].data(), nf); else GRt[nf] = GR[nf];
+        for (int I = 0; I < N; ++I) for (int J = 0; J < N; ++J) GRC[nf][I + (size_t)J * N] = ((I == J) ? cd(1, 0) : cd(0, 0)) - GRt[nf][J + (size_t)I * N];
+      }
+      cd ZP = Phase / Phase.real(); double ZSr = Phase.real() >= 0 ? 1.0 : -1.0; cd ZS = ZSr;
+      obse_cnt[0] += 1; obse_cnt[1] += ZSr;
+      auto A = [&](int ch, int no_I, int no_J, int imj) -> cd& { return obse_acc[((size_t)ch * nb2 + no_I + nb * no_J) * nu + imj]; };
+      for (int I1 = 0; I1 < N; ++I1) {
+        const int I = lat_cell[I1]; if (I < 0) continue; const int no_I = lat_orb[I1];
+        cd ZI = 0; for (int nf = 0; nf < n_fl; ++nf) ZI += GRC[nf][I1 + (size_t)I1 * N];
+        ZI *= (double)n_sun;
+        for (int J1 = 0; J1 < N; ++J1) {
+          const int J = lat_cell[J1]; if (J < 0) continue; const int no_J = lat_orb[J1];
+          const int imj = lat_imj[I + (size_t)J * nu]; const size_t ij = I1 + (size_t)J1 * N;
+          cd Zg = 0, Zd = 0, ZJ = 0;
+          for (int nf = 0; nf < n_fl; ++nf) { Zg += GRC[nf][ij]; Zd += GRC[nf][ij] * GRt[nf][ij]; ZJ += GRC[nf][J1 + (size_t)J1 * N]; }
+          ZJ *= (double)n_sun;
+          A(0, no_I, no_J, imj) += Zg * (double)n_sun * ZP * ZS;
+          if (n_fl == 2) {
+            cd ZXY = GRC[0][ij] * GRt[1][ij] + GRC[1][ij] * GRt[0][ij];
+            cd ZZ = GRC[0][ij] * GRt[0][ij] + GRC[1][ij] * GRt[1][ij]
+                  + (GRC[1][I1 + (size_t)I1 * N] - GRC[0][I1 + (size_t)I1 * N]) * (GRC[1][J1 + (size_t)J1 * N] - GRC[0][J1 + (size_t)J1 * N]);
+            A(1, no_I, no_J, imj) += ZZ * ZP * ZS; A(2, no_I, no_J, imj) += ZXY * ZP * ZS;
+          } else A(1, no_I, no_J, imj) += GRC[0][ij] * GRt[0][ij] * (double)n_sun * ZP * ZS;
+          A(3, no_I, no_J, imj) += (ZI * ZJ + Zd * (double)n_sun) * ZP * ZS;
+        }
+        if (n_fl == 2) obse_bg[(size_t)0 * nb + no_I] += (GRC[1][I1 + (size_t)I1 * N] - GRC[0][I1 + (size_t)I1 * N]) * ZP * ZS;
+        obse_bg[(size_t)1 * nb + no_I] += ZI * ZP * ZS;
+      }
     }
     if (!eq_capture_on) return;
     std::vector<cd> tmp((size_t)ndim * ndim);
@@ -1152,6 +1186,14 @@ void orc_obs_tau_enable(void* h, int n_unit, int norb, const int* cell, const in
   o->obst_ntau = o->projector ? o->ltrot - 2 * o->thtrot + 1 : o->ltrot + 1;
   o->obst_acc.assign((size_t)4 * o->obst_ntau * norb * norb * n_unit, cd(0)); o->obst_bg.assign((size_t)2 * o->obst_ntau * norb, cd(0));
   o->obst_cnt[0] = o->obst_cnt[1] = 0; o->obst_on = true;
+}
+void orc_obs_eq_enable(void* h) {      // after orc_obs_tau_enable (lattice tables)
+  Oracle* o = (Oracle*)h; o->obse_acc.assign((size_t)4 * o->lat_norb * o->lat_norb * o->lat_n_unit, cd(0)); o->obse_bg.assign((size_t)2 * o->lat_norb, cd(0));
+  o->obse_cnt[0] = o->obse_cnt[1] = 0; o->obse_on = true;
+}
+void orc_get_obs_eq(void* h, double* acc, double* bg, double* cnt) {
+  Oracle* o = (Oracle*)h; std::memcpy(acc, o->obse_acc.data(), sizeof(cd) * o->obse_acc.size()); std::memcpy(bg, o->obse_bg.data(), sizeof(cd) * o->obse_bg.size());
+  cnt[0] = o->obse_cnt[0]; cnt[1] = o->obse_cnt[1];
 }
 int orc_obs_tau_ntau(void* h) { return ((Oracle*)h)->obst_ntau; }
 void orc_get_obs_tau(void* h, double* acc, double* bg, double* cnt) {

@@ -187,6 +187,17 @@ class Oracle:
         lib().orc_obs_tau_enable(self.h, int(n_unit), int(norb), cell.ctypes.data_as(_ip), orb.ctypes.data_as(_ip), imj_f.ctypes.data_as(_ip))
         self._obst_dims = (4, lib().orc_obs_tau_ntau(self.h), int(norb), int(norb), int(n_unit))
 
+    def obs_eq_enable(self):
+        if not hasattr(self, "_obst_dims"):
+            self.obs_tau_enable()
+        lib().orc_obs_eq_enable(self.h)
+
+    def obs_eq(self):
+        d = self._obst_dims
+        acc = np.zeros((4, 1, d[2], d[3], d[4]), dtype=np.complex128); bg = np.zeros((2, 1, d[2]), dtype=np.complex128); cnt = np.zeros(2)
+        lib().orc_get_obs_eq(self.h, _d(acc), _d(bg), _d(cnt))
+        return acc, bg, cnt[0], cnt[1]
+
     def obs_tau(self):
         acc = np.zeros(self._obst_dims, dtype=np.complex128); bg = np.zeros((2, self._obst_dims[1], self._obst_dims[2]), dtype=np.complex128); cnt = np.zeros(2)
         lib().orc_get_obs_tau(self.h, _d(acc), _d(bg), _d(cnt))

@@ -642,3 +642,31 @@ def test_obs_tau_on_device(which):
             assert np.abs(acc[ch]).max() == 0
     assert np.abs(bg - bg_o).max() < 1e-9 * max(1.0, np.abs(bg_o).max())
     g.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("which", ["hubbard_mz_symm", "hubbard_su2", "kondo"])
+def test_obs_eq_on_device(which):
+    """Equal-time Green / SpinZ / SpinXY / Den correlation functions accumulated on the device at every measured slice (on the
+    symmetrised G, as main.F90:761-764 hands GR_Tilde to ham%Obser) against the oracle's restatement of Predefined_Obs_eq_*_measure."""
+    model = {"hubbard_mz_symm": lambda: hubbard_square(4, 4, 0.8), "hubbard_su2": lambda: hubbard_square(4, 4, 0.8, Mz=False),
+             "kondo": lambda: kondo_square(2, 2, 0.6)}[which]()
+    seeds = SEEDS[:2]; nwrap = 4
+    g = AlfB200(model, n_chains=len(seeds), nwrap=nwrap); g.set_seeds(seeds); g.fields_set(); g.init_sweep(); g.obs_eq_enable()
+    orcs = []
+    for s in seeds:
+        o = Oracle(model, nwrap=nwrap); o.ranset(s); o.fields_set(); o.init(); o.obs_eq_enable(); orcs.append(o)
+    g.sweep(1, 0)
+    for o in orcs:
+        o.sweep(0)
+    acc, bg, n, sg = g.obs_eq()
+    ro = [o.obs_eq() for o in orcs]
+    acc_o = sum(r[0] for r in ro); bg_o = sum(r[1] for r in ro)
+    assert n == sum(r[2] for r in ro) == len(seeds) * (2 * model.Ltrot - 1) and sg == sum(r[3] for r in ro)
+    for ch in range(4):
+        if np.abs(acc_o[ch]).max() > 0:
+            assert relF(acc[ch], acc_o[ch]) < 1e-9, ch
+        else:
+            assert np.abs(acc[ch]).max() == 0
+    assert np.abs(bg - bg_o).max() < 1e-9 * max(1.0, np.abs(bg_o).max())
+    g.close()
