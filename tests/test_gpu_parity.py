@@ -1,6 +1,8 @@
 """GPU parity tests (-m gpu): every kernel and the full sweep, through the C-ABI, against the CPU oracle.
 Tolerances: 1e-10 relative Frobenius on freshly recomputed G (north_star check 1); accept/reject sequences and field
 configurations bit-exact (check 2)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -670,3 +672,22 @@ def test_obs_eq_on_device(which):
             assert np.abs(acc[ch]).max() == 0
     assert np.abs(bg - bg_o).max() < 1e-9 * max(1.0, np.abs(bg_o).max())
     g.close()
+
+
+@pytest.mark.gpu
+def test_example_writes_alf_bin_files(tmp_path):
+    """examples/hubbard_bins.py: sweeps + device-side measurements + bin files in ALF's text layout that parse back (what Analysis reads)."""
+    import importlib.util
+    from alf_b200.bins import read_latt, read_scal
+    spec = importlib.util.spec_from_file_location("hubbard_bins", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "examples", "hubbard_bins.py"))
+    mod = importlib.util.module_from_spec(spec); spec.loader.exec_module(mod)
+    out = str(tmp_path / "run")
+    assert mod.main(["--L1", "4", "--L2", "2", "--beta", "1.0", "--chains", "8", "--bins", "2", "--sweeps", "3", "--warmup", "2", "--nwrap", "5", "--out", out]) == 0
+    obs, sign = read_scal(os.path.join(out, "Part_scal"))
+    assert obs.shape == (2, 1) and np.all(np.abs(obs[:, 0].real - 8.0) < 0.5) and np.allclose(sign, 1.0)      # half filling: <N> = 8 sites
+    for nm in ("Green", "SpinZ", "SpinXY", "Den"):
+        beq = read_latt(os.path.join(out, nm + "_eq")); btau = read_latt(os.path.join(out, nm + "_tau"))
+        assert len(beq) == 2 and len(btau) == 2 and beq[0][3].shape == (8, 1, 1, 1) and btau[0][3].shape == (8, 11, 1, 1)
+    # the k-sum of the k-space function is its r = 0 value: Green_eq(r = 0) = sum_i N_SUN sum_nf <c^dag_i c_i> = 8 particles at half filling
+    g_eq = read_latt(os.path.join(out, "Green_eq"))[1][3][:, 0, 0, 0]
+    assert abs(g_eq.sum().real - 8.0) < 0.5
