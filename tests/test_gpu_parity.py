@@ -691,3 +691,56 @@ def test_example_writes_alf_bin_files(tmp_path):
     # the k-sum of the k-space function is its r = 0 value: Green_eq(r = 0) = sum_i N_SUN sum_nf <c^dag_i c_i> = 8 particles at half filling
     g_eq = read_latt(os.path.join(out, "Green_eq"))[1][3][:, 0, 0, 0]
     assert abs(g_eq.sum().real - 8.0) < 0.5
+
+
+@pytest.mark.gpu
+def test_ed_correlations_plaquette_device_observables():
+    """Full chain of the device-side measurements against exact diagonalisation (testsuite/test_vs_ed in spirit): 2x2 Hubbard plaquette,
+    U = 4, beta = 2: equal-time spin and density correlation functions accumulated ON THE DEVICE over 64 chains vs the 256-state Fock space."""
+    beta, dtau, U = 2.0, 0.05, 4.0
+    m = hubbard_square(2, 2, beta, dtau, U)
+    N = m.Ndim
+    # single-particle hopping matrix exactly as the operator list defines it: sum over the checkerboard operators of O * (g / -dtau)
+    Tm = np.zeros((N, N))
+    for ops in m.Op_T:
+        op = ops[0]
+        for a in range(op.N):
+            for b in range(op.N):
+                Tm[op.P[a] - 1, op.P[b] - 1] += (op.O[a, b] * (op.g / (-dtau))).real
+    norb = 2 * N; dim = 2 ** norb
+
+    def cdag(i):
+        M = np.zeros((dim, dim))
+        for s in range(dim):
+            if not (s >> i) & 1:
+                M[s | (1 << i), s] = (-1) ** bin(s & ((1 << i) - 1)).count("1")
+        return M
+    cd_ = [cdag(i) for i in range(norb)]; c_ = [x.T for x in cd_]; n_ = [cd_[i] @ c_[i] for i in range(norb)]
+    H = np.zeros((dim, dim))
+    for sp in range(2):
+        for i in range(N):
+            for j in range(N):
+                if Tm[i, j] != 0.0:
+                    H += Tm[i, j] * cd_[sp * N + i] @ c_[sp * N + j]
+    I = np.eye(dim)
+    for i in range(N):
+        H += U * (n_[i] - 0.5 * I) @ (n_[N + i] - 0.5 * I)
+    w, v = np.linalg.eigh(H); p = np.exp(-beta * (w - w.min())); p /= p.sum()
+
+    def ev(Op):
+        return float(np.einsum("i,ji,jk,ki->", p, v, Op, v))
+    imj = m.latt.imj_table() - 1
+    spin_ed = np.zeros(N); den_ed = np.zeros(N)
+    for i in range(N):
+        for j in range(N):
+            mi, mj = n_[N + i] - n_[i], n_[N + j] - n_[j]
+            spin_ed[imj[i, j]] += ev(mi @ mj); den_ed[imj[i, j]] += ev((n_[i] + n_[N + i]) @ (n_[j] + n_[N + j]))
+    C = 64
+    g = AlfB200(m, n_chains=C, nwrap=10); g.set_seeds([31 + 101 * c for c in range(C)]); g.fields_set(); g.init_sweep()
+    g.sweep(30, 0); g.obs_eq_enable(True); g.sweep(150, 0)
+    acc, bg, n, sg = g.obs_eq()
+    spin = acc[1, 0, 0, 0].real / n; den = acc[3, 0, 0, 0].real / n
+    assert sg == n                                       # no sign problem at half filling
+    assert np.abs(spin - spin_ed).max() < 0.06 * max(1.0, np.abs(spin_ed).max()), (spin, spin_ed)
+    assert np.abs(den - den_ed).max() < 0.03 * max(1.0, np.abs(den_ed).max()), (den, den_ed)
+    g.close()
