@@ -133,6 +133,34 @@ module alf_b200_shim
        real(c_double), intent(in) :: t0_ratio(*), s0_ratio(*)
        integer(c_int8_t), intent(out) :: accepted(*)
      end function
+     integer(c_int) function alf_b200_set_lattice(h, n_unit, norb, site_cell, site_orb, imj) bind(c, name="alf_b200_set_lattice")
+       import :: c_ptr, c_int
+       type(c_ptr), value :: h
+       integer(c_int), value :: n_unit, norb
+       integer(c_int), intent(in) :: site_cell(*), site_orb(*), imj(*)     ! List(:,1), List(:,2), Latt%imj (column-major, 1-based)
+     end function
+     integer(c_int) function alf_b200_obs_tau_enable(h, on) bind(c, name="alf_b200_obs_tau_enable")
+       import :: c_ptr, c_int
+       type(c_ptr), value :: h
+       integer(c_int), value :: on
+     end function
+     integer(c_int) function alf_b200_obs_eq_enable(h, on) bind(c, name="alf_b200_obs_eq_enable")
+       import :: c_ptr, c_int
+       type(c_ptr), value :: h
+       integer(c_int), value :: on
+     end function
+     integer(c_int) function alf_b200_get_obs_tau(h, acc, bg, cnt) bind(c, name="alf_b200_get_obs_tau")
+       import :: c_ptr, c_int, c_double, c_double_complex
+       type(c_ptr), value :: h
+       complex(c_double_complex), intent(out) :: acc(*), bg(*)      ! Obs_Latt(imj, nt, no_I, no_J) per channel; Obs_Latt0
+       real(c_double), intent(out) :: cnt(2)                        ! N, sum of signs
+     end function
+     integer(c_int) function alf_b200_get_obs_eq(h, acc, bg, cnt) bind(c, name="alf_b200_get_obs_eq")
+       import :: c_ptr, c_int, c_double, c_double_complex
+       type(c_ptr), value :: h
+       complex(c_double_complex), intent(out) :: acc(*), bg(*)
+       real(c_double), intent(out) :: cnt(2)
+     end function
      integer(c_int) function alf_b200_get_green(h, chain, nf, symmetrize, gout) bind(c, name="alf_b200_get_green")
        import :: c_ptr, c_int, c_double_complex
        type(c_ptr), value :: h
