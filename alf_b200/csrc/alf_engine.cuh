@@ -337,8 +337,8 @@ struct Engine : EngineBase {
     KD = (int)((200 * 1024 - fixed) / per_kd); if (KD > 32) KD = 32; if (KD < 4) throw CudaError("Ndim too large for the update kernel's shared-memory factors");
     KD = (KD / 4) * 4;
     upd_smem = per_kd * KD + fixed;
-    CK(cudaFuncSetAttribute(k_wrapgr<T, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)upd_smem));
-    CK(cudaFuncSetAttribute(k_wrapgr<T, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)upd_smem));
+    CK(alf_raise_smem(k_wrapgr<T, 1>));
+    CK(alf_raise_smem(k_wrapgr<T, 0>));
     // vertex groups (see VGroup): greedy over n = 1 .. M
     {
       auto kind_of = [&](int n) {
@@ -380,8 +380,8 @@ struct Engine : EngineBase {
           if (const char* e = getenv("ALF_B200_KD")) { int v = atoi(e); if (v >= 4 && v <= KDf) KDf = (v / 4) * 4; }
           fast_smem = fixedf + perkd * KDf;
           iptf = (F * N + 511) / 512; if (iptf > 1) iptf = 4;
-#define FAST_ATTR(IPT, PR) do { CK(cudaFuncSetAttribute(k_wrapgr_fast<T, 1, IPT, PR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast_smem)); \
-                                CK(cudaFuncSetAttribute(k_wrapgr_fast<T, 0, IPT, PR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast_smem)); } while (0)
+#define FAST_ATTR(IPT, PR) do { CK(alf_raise_smem(k_wrapgr_fast<T, 1, IPT, PR>)); \
+                                CK(alf_raise_smem(k_wrapgr_fast<T, 0, IPT, PR>)); } while (0)
           if (iptf == 1) { FAST_ATTR(1, 0); FAST_ATTR(1, 1); } else { FAST_ATTR(4, 0); FAST_ATTR(4, 1); }
 #undef FAST_ATTR
         }
@@ -405,8 +405,8 @@ struct Engine : EngineBase {
     // op-list kernel: panel of 32 columns (rows) + double-buffered operator descriptors
     ops_smem = (((size_t)N * (OPS_PW + 1) + 1) & ~(size_t)1) * sizeof(T) + 2 * OPS_CH * ((sizeof(T) << (2 * ops_lk)) + 4 * sizeof(int));
     if (ops_smem > 227 * 1024) throw CudaError("Ndim too large for the op-list kernel's shared-memory panel");
-#define OPS_ATTR(LKV) do { CK(cudaFuncSetAttribute(k_apply_ops<T, 0, LKV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ops_smem)); \
-                            CK(cudaFuncSetAttribute(k_apply_ops<T, 1, LKV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ops_smem)); } while (0)
+#define OPS_ATTR(LKV) do { CK(alf_raise_smem(k_apply_ops<T, 0, LKV>)); \
+                            CK(alf_raise_smem(k_apply_ops<T, 1, LKV>)); } while (0)
     if (ops_lk == 0) OPS_ATTR(0); else if (ops_lk == 1) OPS_ATTR(1); else OPS_ATTR(2);
 #undef OPS_ATTR
   }
@@ -743,8 +743,8 @@ struct Engine : EngineBase {
     for (int q = 0; q < 4; ++q) obsS[q] = dalloc<T>(n2 * NM);
     obst_smem = obs_tau_smem<T>(N, lt.n_unit, lt.norb);
     if (obst_smem > 227 * 1024) throw CudaError("obs_tau: lattice too large for the shared-memory bins");
-    CK(cudaFuncSetAttribute(k_obs_tau<T, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)obst_smem));
-    CK(cudaFuncSetAttribute(k_obs_tau<T, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)obst_smem));
+    CK(alf_raise_smem(k_obs_tau<T, 0>));
+    CK(alf_raise_smem(k_obs_tau<T, 1>));
   }
   void obsert(int nt_index) {      // where TAU_M / Tau_p call ham%ObserT(nt_index, GT0, G0T, G00, GTT, Phase): tau_m_mod.F90:115-124,151-177
     if (!h->obs_tau_on || nt_index < 0 || nt_index >= h->obst_ntau) return;
@@ -854,7 +854,7 @@ struct Engine : EngineBase {
       CK(cudaMemcpyAsync(d_s0, s0, sizeof(double) * np, cudaMemcpyHostToDevice, st));
     }
     const size_t smem = sizeof(T) * ((size_t)3 * N + 2 * ALF_KMAX * ALF_KMAX) + 64;
-    CK(cudaFuncSetAttribute(k_random_update<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(alf_raise_smem(k_random_update<T>));
     KL(KC_UPDATE, st, k_random_update<T><<<C, 512, smem, st>>>(G, G2, N, F, h->n_sun, M, d_vops, ft, h->d_fields, L, ntau, h->d_rng, h->d_phase, h->d_counters, d_mpos,
                                                                n_moves, std::max(maxlen, 1), d_len, d_list, d_val, d_t0, d_s0, d_acc, place_to));
     if (acc_out && n_moves > 0) { CK(cudaMemcpyAsync(acc_out, d_acc, np, cudaMemcpyDeviceToHost, st)); }

@@ -2,6 +2,8 @@
 // kernel-level test entry points.
 #pragma once
 #include <cstdio>
+#include <mutex>
+#include <set>
 #include <stdexcept>
 #include <string>
 #include <type_traits>
@@ -14,6 +16,21 @@ struct CudaError : std::runtime_error { using std::runtime_error::runtime_error;
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { \
   throw CudaError(std::string(#call) + " -> " + cudaGetErrorString(e_) + " at " + __FILE__ + ":" + std::to_string(__LINE__)); } } while (0)
 #define CKL() CK(cudaGetLastError())
+
+// Opt-in dynamic shared memory: the attribute is per-function state shared by every handle of the process (two handles with
+// different models may launch the same kernel from two host threads), so it is raised once per device and function to the most
+// the function can ever get (227 KB opt-in limit minus its static shared memory) instead of to what one launch needs.
+template <class F>
+static cudaError_t alf_raise_smem(F* f) {
+  static std::mutex mu; static std::set<std::pair<int, const void*>> done;
+  int dev = 0; cudaError_t e = cudaGetDevice(&dev); if (e != cudaSuccess) return e;
+  std::lock_guard<std::mutex> lk(mu);
+  if (done.count({dev, (const void*)f})) return cudaSuccess;
+  cudaFuncAttributes a; e = cudaFuncGetAttributes(&a, f); if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, ALF_MAX_DYN_SMEM - (int)a.sharedSizeBytes);
+  if (e == cudaSuccess) done.insert({dev, (const void*)f});
+  return e;
+}
 
 // ---- launch accounting: every kernel launch goes through a KScope so that bench.py can report gpu_launches and the
 // per-kernel device time (CUDA events on the handle's stream) its roofline entry needs.
@@ -96,7 +113,7 @@ static void launch_qrp(cudaStream_t st, T* A, int m, int n, int ld, long sA, T* 
   bool do_stage = (stage + extra) <= kSmemStageLimit;
   size_t smem = extra + (do_stage ? stage : 0);
 #define QRP_LAUNCH(MAXR, STG) do { \
-    CK(cudaFuncSetAttribute(k_qrp<T, MAXR, PIVOT, STG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    CK(alf_raise_smem(k_qrp<T, MAXR, PIVOT, STG>)); \
     k_qrp<T, MAXR, PIVOT, STG><<<batch, 512, smem, st>>>(A, m, n, ld, sA, tau, sTau, jpvt, sP, D, sD, out); } while (0)
 #define QRP_DISPATCH(MAXR) do { if (do_stage) QRP_LAUNCH(MAXR, 1); else QRP_LAUNCH(MAXR, 0); } while (0)
   count_flops(KC_QRP, flop_scale<T>() * (2.0 * m * n * n - 2.0 * n * n * n / 3.0) * batch);
@@ -115,7 +132,7 @@ static void launch_formq(cudaStream_t st, T* A, int m, int n, int ld, long sA, c
   bool do_stage = (stage + extra) <= kSmemStageLimit;
   size_t smem = extra + (do_stage ? stage : 0);
 #define FQ_LAUNCH(MAXR, STG) do { \
-    CK(cudaFuncSetAttribute(k_formq<T, MAXR, STG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    CK(alf_raise_smem(k_formq<T, MAXR, STG>)); \
     k_formq<T, MAXR, STG><<<batch, 512, smem, st>>>(A, m, n, ld, sA, tau, sTau, colscale); } while (0)
 #define FQ_DISPATCH(MAXR) do { if (do_stage) FQ_LAUNCH(MAXR, 1); else FQ_LAUNCH(MAXR, 0); } while (0)
   count_flops(KC_FORMQ, flop_scale<T>() * (2.0 * m * n * n - 2.0 * n * n * n / 3.0) * batch);
@@ -135,7 +152,7 @@ static void launch_trsm_blk(cudaStream_t st, const double* R, int ldr, long sR, 
   count_flops(KC_TRSM, 1.0 * n * n * nrhs * batch);
   const size_t smem = sizeof(double) * (size_t)ld_pad(np) * TRSMB_CW;
   KL(KC_TRSM, st, k_tri_inv_blocks<LOWER><<<dim3(nb, batch), 32, 0, st>>>(R, ldr, sR, n, rinv, sI));
-  CK(cudaFuncSetAttribute(k_trsm_blk<LOWER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CK(alf_raise_smem(k_trsm_blk<LOWER>));
   const int nthr = (2 * (smem + 1024) <= 227 * 1024) ? 256 : 512;      // one resident CTA per SM only: give it 16 warps
   KL(KC_TRSM, st, k_trsm_blk<LOWER><<<dim3((nrhs + TRSMB_CW - 1) / TRSMB_CW, batch), nthr, smem, st>>>(R, ldr, sR, rinv, sI, B, ldb, sB, n, nrhs, dinv, sD, zero_cols_from, zero_rows, dout));
 }
@@ -146,7 +163,7 @@ static void launch_trsm_blk_c(cudaStream_t st, const cplx* R, int ldr, long sR, 
   count_flops(KC_TRSM, 4.0 * n * n * nrhs * batch);
   const size_t smem = sizeof(cplx) * (size_t)(np + 1) * TRSMB_CWC;
   KL(KC_TRSM, st, k_tri_inv_blocks_c<LOWER><<<dim3(nb, batch), 32, 0, st>>>(R, ldr, sR, n, rinv, sI));
-  CK(cudaFuncSetAttribute(k_trsm_blk_c<LOWER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CK(alf_raise_smem(k_trsm_blk_c<LOWER>));
   const int nthr = (2 * (smem + 1024) <= 227 * 1024) ? 256 : 512;
   KL(KC_TRSM, st, k_trsm_blk_c<LOWER><<<dim3((nrhs + TRSMB_CWC - 1) / TRSMB_CWC, batch), nthr, smem, st>>>(R, ldr, sR, rinv, sI, B, ldb, sB, n, nrhs, dinv, sD));
 }
@@ -207,7 +224,7 @@ static void launch_qrp_blk(cudaStream_t st, T* A, int m, int n, int ld, long sA,
       // 1.94 ms vs 1.72 ms per batch of 296 256x256 matrices.
       const bool two = m <= 288 && qr2_smem(m, n, 8) + 1024 <= 113 * 1024 && getenv("ALF_B200_QR_TWO_CTA");
       const size_t smem = qr2_smem(m, n, two ? 8 : 16);
-#define QR2_LAUNCH(MAXR, CPW) do { CK(cudaFuncSetAttribute(k_qrp_reg<MAXR, CPW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+#define QR2_LAUNCH(MAXR, CPW) do { CK(alf_raise_smem(k_qrp_reg<MAXR, CPW>)); \
         KL(KC_QRP, st, k_qrp_reg<MAXR, CPW><<<batch, 32 * (QR2_NB / CPW), smem, st>>>(A, m, n, ld, sA, tau, sTau, jpvt, sP, D, sD, out, Tbuf, sT)); } while (0)
       if (two) { if (m <= 128) QR2_LAUNCH(4, 4); else QR2_LAUNCH(9, 4); }
       else { if (m <= 128) QR2_LAUNCH(4, 2); else if (m <= 288) QR2_LAUNCH(9, 2); else QR2_LAUNCH(18, 2); }
@@ -216,7 +233,7 @@ static void launch_qrp_blk(cudaStream_t st, T* A, int m, int n, int ld, long sA,
     }
   }
   const QrBlkCfg c = qrblk_cfg<T>(m, n);
-  CK(cudaFuncSetAttribute(k_qrp_blk<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem));
+  CK(alf_raise_smem(k_qrp_blk<T>));
   KL(KC_QRP, st, k_qrp_blk<T><<<batch, 512, c.smem, st>>>(A, m, n, ld, sA, tau, sTau, jpvt, sP, D, sD, out, Tbuf, (long)(n + 32) * 32, c.NB, c.TC));
 }
 // X <- Q^H X (mode 0) / Q X (mode 1); ident: X holds the identity on entry (mode 1 only: forms Q)
@@ -230,7 +247,7 @@ static void launch_apply_q(cudaStream_t st, const T* QR, int m, int n, int ld, l
       const size_t smem = applyq2_smem(m, small ? 8 : 16); const int cpc2 = small ? 64 : 128; dim3 grid2((ncols + cpc2 - 1) / cpc2, batch);
       const long sT2 = (long)(n + 32) * 32;
       KScope ks_(KC_FORMQ, st);
-#define AQ2_LAUNCH(MD, ID, NT) do { CK(cudaFuncSetAttribute(k_apply_q2<MD, ID, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+#define AQ2_LAUNCH(MD, ID, NT) do { CK(alf_raise_smem(k_apply_q2<MD, ID, NT>)); \
         k_apply_q2<MD, ID, NT><<<grid2, NT, smem, st>>>(QR, m, n, ld, sQ, Tbuf, sT2, X, ldx, sX, ncols, cpc2); } while (0)
       if (small) { if (mode == 0) AQ2_LAUNCH(0, 0, 256); else if (ident) AQ2_LAUNCH(1, 1, 256); else AQ2_LAUNCH(1, 0, 256); }
       else { if (mode == 0) AQ2_LAUNCH(0, 0, 512); else if (ident) AQ2_LAUNCH(1, 1, 512); else AQ2_LAUNCH(1, 0, 512); }
@@ -243,11 +260,11 @@ static void launch_apply_q(cudaStream_t st, const T* QR, int m, int n, int ld, l
   const int cpc = 64; dim3 grid((ncols + cpc - 1) / cpc, batch);
   const long sT = (long)(n + 32) * 32;
   KScope ks_(KC_FORMQ, st);
-  if (mode == 0) { CK(cudaFuncSetAttribute(k_apply_q<T, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem));
+  if (mode == 0) { CK(alf_raise_smem(k_apply_q<T, 0, 0>));
     k_apply_q<T, 0, 0><<<grid, 512, c.smem, st>>>(QR, m, n, ld, sQ, Tbuf, sT, X, ldx, sX, ncols, c.NB, c.TC, cpc); }
-  else if (ident) { CK(cudaFuncSetAttribute(k_apply_q<T, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem));
+  else if (ident) { CK(alf_raise_smem(k_apply_q<T, 1, 1>));
     k_apply_q<T, 1, 1><<<grid, 512, c.smem, st>>>(QR, m, n, ld, sQ, Tbuf, sT, X, ldx, sX, ncols, c.NB, c.TC, cpc); }
-  else { CK(cudaFuncSetAttribute(k_apply_q<T, 1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem));
+  else { CK(alf_raise_smem(k_apply_q<T, 1, 0>));
     k_apply_q<T, 1, 0><<<grid, 512, c.smem, st>>>(QR, m, n, ld, sQ, Tbuf, sT, X, ldx, sX, ncols, c.NB, c.TC, cpc); }
   CKL();
 }

@@ -8,6 +8,9 @@
 #include <cmath>
 
 #define ALF_HD __host__ __device__ __forceinline__
+// cap for cudaFuncAttributeMaxDynamicSharedMemorySize (227 KB opt-in maximum of sm_100): the attribute is per-function state shared by
+// all handles of the process, so it is always raised to the maximum instead of the size one particular launch needs
+#define ALF_MAX_DYN_SMEM (227 * 1024)
 
 struct __align__(16) cplx {
   double x, y;

@@ -744,3 +744,34 @@ def test_ed_correlations_plaquette_device_observables():
     assert np.abs(spin - spin_ed).max() < 0.06 * max(1.0, np.abs(spin_ed).max()), (spin, spin_ed)
     assert np.abs(den - den_ed).max() < 0.03 * max(1.0, np.abs(den_ed).max()), (den, den_ed)
     g.close()
+
+
+@pytest.mark.gpu
+def test_handles_are_reentrant_across_threads():
+    """Two handles with DIFFERENT models (real Hubbard 8x8 with blocked kernels' small cousins, complex Kondo) advanced concurrently by two
+    host threads on their own streams give the same chains as the oracle: no shared state between handles (bench.py runs two per GPU)."""
+    import threading
+    models = [hubbard_square(8, 8, 1.0), kondo_square(2, 2, 0.6), hubbard_square(4, 4, 0.8, projector=True, theta=0.3, trial="dimer")]
+    seeds = SEEDS[:2]
+    gs = []
+    for m in models:
+        g = AlfB200(m, n_chains=len(seeds), nwrap=5); g.set_seeds(seeds); g.fields_set(); g.init_sweep(); gs.append(g)
+    errs = []
+
+    def run(g):
+        try:
+            g.sweep(2, 1)
+        except Exception as e:      # noqa: BLE001
+            errs.append(e)
+    th = [threading.Thread(target=run, args=(g,)) for g in gs]
+    [t.start() for t in th]; [t.join() for t in th]
+    assert not errs, errs
+    for m, g in zip(models, gs):
+        f = g.get_fields(); ph = g.phase()
+        for c, s in enumerate(seeds):
+            o = Oracle(m, nwrap=5); o.ranset(s); o.fields_set(); o.init(); o.sweep(1); o.sweep(1)
+            assert np.array_equal(f[c], o.get_fields()), m.name
+            for nf in range(1, m.N_FL + 1):
+                assert relF(g.green(c, nf), o.green(nf)) < TOL_G, m.name
+            assert abs(ph[c] - o.phase()) < 1e-9
+        g.close()
