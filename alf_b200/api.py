@@ -342,6 +342,15 @@ def test_qdrp_blocked(A, is_complex=True, device=0):
     return Af.transpose(0, 2, 1), D, jp, tau, ph, Q.transpose(0, 2, 1)
 
 
+def udv_wrap_pivot(A, is_complex=True, device=0):
+    """UDV_Wrap_Pivot(A, U, D, V, NCON, N1, N2) (Prog/UDV_WRAP_mod.F90:125-208) on a batch A[b] (N1 x N2): returns U, D, V with A = U D V."""
+    A = np.ascontiguousarray(A, dtype=np.complex128); batch, n1, n2 = A.shape
+    Af = np.ascontiguousarray(A.transpose(0, 2, 1)).copy()
+    Uf = np.zeros((batch, n2, n1), dtype=np.complex128); Vf = np.zeros((batch, n2, n2), dtype=np.complex128); D = np.zeros((batch, n2), dtype=np.complex128)
+    _chk(lib().alf_b200_udv_wrap_pivot(device, int(is_complex), n1, n2, batch, _d(Af), _d(Uf), _d(D), _d(Vf)), "udv_wrap_pivot")
+    return Uf.transpose(0, 2, 1), D, Vf.transpose(0, 2, 1)
+
+
 def test_udv_decompose(U, D, V, side="r", is_complex=True, device=0):
     U = np.ascontiguousarray(U, dtype=np.complex128); V = np.ascontiguousarray(V, dtype=np.complex128); batch, n, _ = U.shape
     Uf = np.ascontiguousarray(U.transpose(0, 2, 1)).copy(); Vf = np.ascontiguousarray(V.transpose(0, 2, 1)).copy()

@@ -402,6 +402,11 @@ int alf_b200_test_udv_decompose(int device, int is_complex, int n, int batch, ch
   try { t_prof = nullptr; CK(cudaSetDevice(device)); if (is_complex) alf_t_udv_cplx(n, batch, side, U, D, V); else alf_t_udv_real(n, batch, side, U, D, V); }
   catch (const std::exception& e) { fprintf(stderr, "alf_b200_test_udv_decompose: %s\n", e.what()); return ALF_ERROR_CUDA; } return ALF_OK;
 }
+int alf_b200_udv_wrap_pivot(int device, int is_complex, int n1, int n2, int batch, const double* A, double* U, double* D, double* V) {
+  if (n1 < 1 || n2 < 1 || n2 > n1 || n1 > 576 || batch < 1 || !A || !U || !D || !V) return ALF_ERROR_GENERIC;
+  try { t_prof = nullptr; CK(cudaSetDevice(device)); if (is_complex) alf_t_udv_wrap_pivot_cplx(n1, n2, batch, A, U, D, V); else alf_t_udv_wrap_pivot_real(n1, n2, batch, A, U, D, V); }
+  catch (const std::exception& e) { fprintf(stderr, "alf_b200_udv_wrap_pivot: %s\n", e.what()); return ALF_ERROR_CUDA; } return ALF_OK;
+}
 int alf_b200_test_cgr(int device, int is_complex, int n, int batch, int nvar, int stab, const double* UR, const double* DR, const double* VR,
                       const double* UL, const double* DL, const double* VL, const double* detUR, const double* detUL, double* G, double* phase) {
   try { t_prof = nullptr; CK(cudaSetDevice(device)); if (is_complex) alf_t_cgr_cplx(n, batch, nvar, stab, UR, DR, VR, UL, DL, VL, detUR, detUL, G, phase);

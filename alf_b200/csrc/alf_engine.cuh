@@ -15,6 +15,7 @@
 #include "alf_update_fast.cuh"
 #include "alf_global_move.cuh"
 #include "alf_obs_tau.cuh"
+#include "alf_udv_wrap.cuh"
 
 typedef std::complex<double> cd;
 static const double kEpsMachine = 2.220446049250313e-16;
@@ -936,6 +937,14 @@ static void t_qdrp_blk(int m, int n, int batch, double* A, double* D, int* jpvt,
   auto d = dD.down(); std::copy(d.begin(), d.end(), D);
   auto p = dp.down(); for (size_t i = 0; i < p.size(); ++i) jpvt[i] = p[i] + 1;
   auto q = dq.down(); for (int b = 0; b < batch; ++b) { phases[5 * b] = q[b].perm_sign; phases[5 * b + 1] = q[b].diag_phase.x; phases[5 * b + 2] = q[b].diag_phase.y; phases[5 * b + 3] = q[b].detq.x; phases[5 * b + 4] = q[b].detq.y; }
+}
+// UDV_Wrap_Pivot(A, U, D, V, NCON, N1, N2) on a batch of host matrices (complex layout at the boundary)
+template <typename T>
+static void t_udv_wrap_pivot(int n1, int n2, int batch, const double* A, double* U, double* D, double* V) {
+  DevBuf<T> dA((size_t)n1 * n2 * batch), dU((size_t)n1 * n2 * batch), dV((size_t)n2 * n2 * batch); DevBuf<double> dD((size_t)n2 * batch);
+  dA.up(h2T<T>(A, dA.n));
+  la_udv_wrap_pivot<T>(0, dA.p, dU.p, dD.p, dV.p, n1, n2, batch); CK(cudaDeviceSynchronize());
+  T2h<T>(dU.down(), U); T2h<T>(dV.down(), V); auto d = dD.down(); for (size_t i = 0; i < d.size(); ++i) { D[2 * i] = d[i]; D[2 * i + 1] = 0.0; }
 }
 template <typename T>
 static void t_udv(int n, int batch, char side, double* U, double* D, double* V) {

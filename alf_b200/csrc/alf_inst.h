@@ -11,6 +11,7 @@ struct alf_b200_handle; struct EngineBase;
                          const double* V1, double* out4); \
   void alf_t_qdrp_blk_##SUF(int m, int n, int batch, double* A, double* D, int* jpvt, double* tau, double* phases, double* Q); \
   void alf_t_cgrp_##SUF(int n, int n_part, int batch, const double* UR, const double* UL, double* G, double* phase); \
+  void alf_t_udv_wrap_pivot_##SUF(int n1, int n2, int batch, const double* A, double* U, double* D, double* V); \
   void alf_t_gemm_##SUF(int ta, int tb, int m, int n, int k, int batch, const double* A, const double* B, double* Cc);
 ALF_INST_DECL(real)
 ALF_INST_DECL(cplx)

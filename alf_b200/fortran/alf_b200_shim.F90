@@ -12,9 +12,10 @@ module alf_b200_shim
   use Fields_mod                 ! type Fields   (Prog/Fields_mod.F90:79-99)
   implicit none
   private
-  public :: alf_b200_attach, alf_b200_detach, alf_b200_batched_sweep, alf_b200_handle_ptr
+  public :: alf_b200_attach, alf_b200_detach, alf_b200_batched_sweep, alf_b200_handle_ptr, UDV_Wrap_Pivot
 
   type(c_ptr), save :: alf_b200_handle_ptr = c_null_ptr
+  integer(c_int), save :: alf_b200_device = 0      ! set by alf_b200_attach
 
   interface
      integer(c_int) function alf_b200_create(h, ndim, n_fl, n_sun, ltrot, nwrap, n_opv, n_opt, symm, stab, n_chains, device) &
@@ -178,6 +179,12 @@ module alf_b200_shim
        type(c_ptr), value :: h
        complex(c_double_complex), intent(out) :: ph(*)
      end function
+     integer(c_int) function alf_b200_udv_wrap_pivot(device, is_complex, n1, n2, batch, A, U, D, V) bind(c, name="alf_b200_udv_wrap_pivot")
+       import :: c_int, c_double_complex
+       integer(c_int), value :: device, is_complex, n1, n2, batch
+       complex(c_double_complex), intent(in) :: A(*)
+       complex(c_double_complex), intent(out) :: U(*), D(*), V(*)
+     end function
   end interface
 
 contains
@@ -198,6 +205,7 @@ contains
     logical, intent(in) :: Symm
     integer, intent(in) :: seeds(:)
     integer :: n, nf, stab
+    alf_b200_device = device
     stab = 0
 #if defined(STAB3)
     stab = 3
@@ -217,6 +225,19 @@ contains
     enddo
     call check(alf_b200_finalize_model(alf_b200_handle_ptr), __FILE__, __LINE__)
     call check(alf_b200_set_seeds(alf_b200_handle_ptr, int(seeds, c_int32_t)), __FILE__, __LINE__)
+  end subroutine
+
+  !> Same name and argument list as Prog/UDV_WRAP_mod.F90:125 (STAB1 / STAB2 builds call it from wrapur_mod.F90:96,
+  !> wrapul_mod.F90:98-102, cgr1_mod.F90:115,137); NCON only triggers a diagnostic print in the reference.
+  subroutine UDV_Wrap_Pivot(A, U, D, V, NCON, N1, N2)
+    complex(kind=kind(0.d0)), intent(in),    dimension(:,:) :: A
+    complex(kind=kind(0.d0)), intent(inout), dimension(:,:) :: U, V
+    complex(kind=kind(0.d0)), intent(inout), dimension(:)   :: D
+    integer, intent(in) :: NCON, N1, N2
+    complex(kind=kind(0.d0)) :: A1(N1,N2), U1(N1,N2), V1(N2,N2), D1(N2)
+    A1 = A(1:N1,1:N2)
+    call check(alf_b200_udv_wrap_pivot(alf_b200_device, 1, N1, N2, 1, A1, U1, D1, V1), __FILE__, __LINE__)
+    U(1:N1,1:N2) = U1; V(1:N2,1:N2) = V1; D(1:N2) = D1
   end subroutine
 
   subroutine alf_b200_detach()

@@ -143,6 +143,13 @@ int alf_b200_obs_reset(alf_b200_handle* h);
 int alf_b200_obs_device_ptr(alf_b200_handle* h, double** dptr, long* n_doubles);  /* for the NCCL bin reduction */
 int alf_b200_get_obs(alf_b200_handle* h, double* out);
 
+/* ---- UDV_Wrap_Pivot(A, U, D, V, NCON, N1, N2), Prog/UDV_WRAP_mod.F90:125-208 (default variant; the stabilisation of the STAB1 / STAB2
+ * builds: wrapur_mod.F90:96, wrapul_mod.F90:98-102, cgr1_mod.F90:115,137): norm-sorted, norm-scaled columns, unpivoted Householder QR
+ * (UDV_C, mymats_mod.F90:933), det V = 1.  A, U: complex n1*n2*batch, D: complex n2*batch, V: complex n2*n2*batch, A = U D V per matrix.
+ * NCON (a diagnostic print in the reference) has no counterpart.  UDV_Wrap (QR + SVD, :212) is only called from Global_mod.F90:926,
+ * outside the sweep, and is not provided. */
+int alf_b200_udv_wrap_pivot(int device, int is_complex, int n1, int n2, int batch, const double* A, double* U, double* D, double* V);
+
 /* ---- kernel-level entry points used by the parity tests (host arrays in, host arrays out; batch of matrices) */
 int alf_b200_test_qdrp(int device, int is_complex, int m, int n, int batch, double* A /* complex m*n*batch, in/out */,
                        double* D /* n*batch */, int* jpvt /* n*batch, 1-based */, double* tau /* complex n*batch */,

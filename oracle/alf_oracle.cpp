@@ -34,6 +34,7 @@ typedef std::complex<double> cd;
 extern "C" {
 void scipy_zgeqp3_(int*, int*, cd*, int*, int*, cd*, cd*, int*, double*, int*);
 void scipy_zungqr_(int*, int*, int*, cd*, int*, cd*, cd*, int*, int*);
+void scipy_zgeqrf_(int*, int*, cd*, int*, cd*, cd*, int*, int*);
 void scipy_zunmqr_(const char*, const char*, int*, int*, int*, cd*, int*, cd*, cd*, int*, cd*, int*, int*);
 void scipy_ztrsm_(const char*, const char*, const char*, const char*, int*, int*, cd*, cd*, int*, cd*, int*);
 void scipy_ztrmm_(const char*, const char*, const char*, const char*, int*, int*, cd*, cd*, int*, cd*, int*);
@@ -1267,6 +1268,45 @@ void orc_cgr2_2(int n, int stab3, const double* U2, const double* D2, const doub
                 double* GRT0, double* GR00, double* GRTT, double* GR0T) {
   UDV a, b; load_udv(a, n, 'r', U2, D2, V2); load_udv(b, n, 'l', U1, D1, V1);
   cgr2_2((cd*)GRT0, (cd*)GR00, (cd*)GRTT, (cd*)GR0T, a, b, n, stab3 != 0);
+}
+// UDV_C (Libraries/Modules/mymats_mod.F90:933-1039): A (LQ x NE) = U D V by unpivoted Householder QR (ZGEQRF + ZUNGQR); the sign of
+// det R is moved into U(:,1) / V(1,:), D = |Re R_ii|, V unit upper triangular.
+static void udv_c(int LQ, int NE, const cd* A, cd* U, cd* D, cd* V /* NE x NE */) {
+  std::vector<cd> TMP(A, A + (size_t)LQ * NE), TAU(NE), WORK(1); int info = 0, m1 = -1;
+  scipy_zgeqrf_(&LQ, &NE, TMP.data(), &LQ, TAU.data(), WORK.data(), &m1, &info);
+  int LWORK = (int)WORK[0].real(); WORK.resize(std::max(LWORK, 1));
+  scipy_zgeqrf_(&LQ, &NE, TMP.data(), &LQ, TAU.data(), WORK.data(), &LWORK, &info);
+  std::fill(V, V + (size_t)NE * NE, cd(0, 0));
+  for (int j = 0; j < NE; ++j) for (int i = 0; i <= j; ++i) V[i + (size_t)j * NE] = TMP[i + (size_t)j * LQ];     // ZLACPY 'U'
+  double DETV = 1.0; for (int i = 0; i < NE; ++i) DETV *= TMP[i + (size_t)i * LQ].real();
+  scipy_zungqr_(&LQ, &NE, &NE, TMP.data(), &LQ, TAU.data(), WORK.data(), &LWORK, &info);
+  std::copy(TMP.begin(), TMP.end(), U);
+  if (DETV < 0.0) { for (int i = 0; i < LQ; ++i) U[i] = -U[i]; for (int i = 0; i < NE; ++i) V[(size_t)i * NE] = -V[(size_t)i * NE]; }
+  for (int i = 0; i < NE; ++i) { double X = std::abs(V[i + (size_t)i * NE].real()); D[i] = cd(X, 0.0); X = 1.0 / X; for (int j = i; j < NE; ++j) V[i + (size_t)j * NE] *= X; }
+}
+// UDV_Wrap_Pivot, default (non-STAB1) variant (Prog/UDV_WRAP_mod.F90:125-208): columns sorted by decreasing norm and divided by
+// their squared norm, UDV_C, det V = 1 through the first row of V / first column of U, scaling and permutation undone in D and V.
+void orc_udv_wrap_pivot(int N1, int N2, const double* A_, double* U_, double* D_, double* V_) {
+  const cd* A = (const cd*)A_; cd* U = (cd*)U_; cd* D = (cd*)D_; cd* V = (cd*)V_;
+  std::vector<double> XNORM(N2), VHELP; std::vector<int> IVPT(N2), IVPTM1(N2);
+  for (int I = 0; I < N2; ++I) { double x = 0.0; for (int J = 0; J < N1; ++J) x += (A[J + (size_t)I * N1] * std::conj(A[J + (size_t)I * N1])).real(); XNORM[I] = x; }
+  VHELP = XNORM;
+  for (int I = 0; I < N2; ++I) {
+    double XMAX = VHELP[0]; int IMAX = 0;
+    for (int J = 1; J < N2; ++J) if (VHELP[J] > XMAX) { IMAX = J; XMAX = VHELP[J]; }
+    VHELP[IMAX] = -1.0; IVPTM1[IMAX] = I; IVPT[I] = IMAX;
+  }
+  std::vector<cd> A1((size_t)N1 * N2), V1((size_t)N2 * N2);
+  for (int I = 0; I < N2; ++I) { int K = IVPT[I]; for (int J = 0; J < N1; ++J) A1[J + (size_t)I * N1] = A[J + (size_t)K * N1] / cd(XNORM[K], 0.0); }
+  udv_c(N1, N2, A1.data(), U, D, V1.data());
+  cd Phase(1.0, 0.0); for (int i = 0; i < N2; ++i) Phase *= V1[i + (size_t)i * N2];
+  { std::vector<int> ip(N2); for (int i = 0; i < N2; ++i) ip[i] = IVPT[i] + 1; pivot_phase(Phase, ip.data(), N2); }
+  cd beta = 1.0 / Phase;
+  for (int j = 0; j < N2; ++j) V1[(size_t)j * N2] *= beta;
+  for (int i = 0; i < N1; ++i) U[i] *= Phase;
+  for (int I = 0; I < N2; ++I) D[I] *= XNORM[IVPT[I]];
+  for (int I = 0; I < N2 - 1; ++I) { double Z = 1.0 / XNORM[IVPT[I]]; for (int J = I + 1; J < N2; ++J) V1[I + (size_t)J * N2] *= XNORM[IVPT[J]] * Z; }
+  for (int J = 0; J < N2; ++J) for (int I = 0; I < N2; ++I) V[I + (size_t)J * N2] = V1[I + (size_t)IVPTM1[J] * N2];
 }
 // udv state access (for kernel-level parity: product U*D*V of a stored state)
 void orc_get_udv(void* h, int which, int nst, int nf, double* U, double* D, double* V) {

@@ -277,6 +277,14 @@ def qdrp(A):
     return A, D, ipvt, tau
 
 
+def udv_wrap_pivot(A):
+    """UDV_Wrap_Pivot (Prog/UDV_WRAP_mod.F90:125-208, default variant): A (N1 x N2) -> U (N1 x N2), D (N2), V (N2 x N2) with A = U D V."""
+    A = _cplx(A).copy(order="F"); n1, n2 = A.shape
+    U = np.zeros((n1, n2), dtype=np.complex128, order="F"); V = np.zeros((n2, n2), dtype=np.complex128, order="F"); D = np.zeros(n2, dtype=np.complex128)
+    lib().orc_udv_wrap_pivot(n1, n2, _d(A), _d(U), _d(D), _d(V))
+    return U, D, V
+
+
 def udv_decompose(U, D, V, side="r"):
     U = _cplx(U).copy(order="F"); V = _cplx(V).copy(order="F"); D = np.ascontiguousarray(D, dtype=np.complex128).copy()
     lib().orc_udv_decompose(U.shape[0], C.c_char(side.encode()), _d(U), _d(D), _d(V))

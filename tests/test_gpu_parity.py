@@ -76,6 +76,29 @@ def test_udv_decompose(is_complex, side, n):
         assert abs(np.linalg.det(V[b]) / np.linalg.det(Vo) - 1) < 1e-8
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("is_complex", [False, True])
+@pytest.mark.parametrize("shape", [(16, 16), (24, 9), (64, 64), (144, 72), (256, 256)])
+def test_udv_wrap_pivot(is_complex, shape):
+    """UDV_Wrap_Pivot (Prog/UDV_WRAP_mod.F90:125-208): U, D, V equal the oracle's (same norm sort, same Householder convention) and
+    satisfy the routine's contract A = U D V, U^H U = 1, D > 0, det V = 1 -- on graded products as in testsuite/Prog.tests/24-udv.F90."""
+    n1, n2 = shape; rng = np.random.default_rng(17 + n1); batch = 3
+    A = np.zeros((batch, n1, n2), dtype=np.complex128)
+    for b in range(batch):
+        X = np.eye(n1, n2, dtype=np.complex128)
+        for _ in range(3 + b):
+            X = ((4 * (rng.random((n1, n1)) - 0.5) + (2j * (rng.random((n1, n1)) - 0.5) if is_complex else 0)) / np.sqrt(n1)) @ X
+        A[b] = X * np.exp(np.linspace(-6, 6, n2))[rng.permutation(n2)][None, :]
+    U, D, V = api.udv_wrap_pivot(A, is_complex)
+    for b in range(batch):
+        assert relF(U[b] @ np.diag(D[b]) @ V[b], A[b]) < 1e-12
+        assert relF(U[b].conj().T @ U[b], np.eye(n2)) < 1e-12
+        assert np.all(D[b].real > 0)
+        sd, ld = np.linalg.slogdet(V[b]); assert abs(sd - 1) < 1e-8 and abs(ld) < 1e-8
+        Uo, Do, Vo = O.udv_wrap_pivot(A[b])
+        assert relF(D[b], Do) < 1e-10 and relF(U[b], Uo) < 1e-9 and relF(V[b], Vo) < 1e-9
+
+
 @pytest.mark.parametrize("is_complex", [False, True])
 @pytest.mark.parametrize("nvar", [1, 2])
 @pytest.mark.parametrize("stab", [0, 3])

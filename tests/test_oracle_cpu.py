@@ -117,6 +117,25 @@ def test_udv_decompose_invariants(side):
     assert abs(np.linalg.det(V) - 1) < 1e-10
 
 
+@pytest.mark.parametrize("shape", [(16, 16), (24, 9)])
+def test_udv_wrap_pivot_invariants(shape):
+    """UDV_Wrap_Pivot (Prog/UDV_WRAP_mod.F90:125-208) on the products of testsuite/Prog.tests/24-udv.F90 (entries 4(u-1/2) + 2i(u-1/2), ten
+    factors, N = 16) and on a rectangular (projector) matrix: A = U D V, U column-orthonormal, D > 0, det V = 1."""
+    rng = np.random.default_rng(4782347); n1, n2 = shape
+    A = np.eye(n1, n2, dtype=np.complex128)
+    for _ in range(10):
+        A = (4 * (rng.random((n1, n1)) - 0.5) + 2j * (rng.random((n1, n1)) - 0.5)) @ A
+        U, D, V = O.udv_wrap_pivot(A)
+        assert relF(U @ np.diag(D) @ V, A) < 1e-12
+        assert relF(U.conj().T @ U, np.eye(n2)) < 1e-12
+        assert np.all(D.real > 0) and np.all(D.imag == 0)
+        assert abs(np.linalg.det(V) - 1) < 1e-9
+        # V is an upper triangular matrix with unit-modulus diagonal up to the column permutation of the norm sort
+        order = np.argsort(-np.sum(np.abs(A) ** 2, axis=0), kind="stable")
+        Vp = V[:, order]
+        assert np.abs(np.tril(Vp, -1)).max() < 1e-13 and np.allclose(np.abs(np.diag(Vp)), 1.0)
+
+
 @pytest.mark.parametrize("nvar", [1, 2])
 @pytest.mark.parametrize("stab3", [False, True])
 def test_cgr_vs_direct_inverse(nvar, stab3):
