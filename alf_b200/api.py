@@ -67,6 +67,15 @@ class AlfB200:
             for nf in range(model.N_FL):
                 pl = np.asfortranarray(model.WF_L[nf], dtype=np.complex128); pr = np.asfortranarray(model.WF_R[nf], dtype=np.complex128)
                 self._ck(L.alf_b200_set_trial_wf(self.h, nf + 1, _d(pl), _d(pr)))
+        s0 = getattr(model, "s0_ising", None)
+        if s0 is not None or getattr(model, "propose_s0", False):
+            t = s0 if s0 is not None else dict(n_terms=0, op_start=np.zeros(model.n_opv + 1, np.int32), term_start=np.zeros(1, np.int32),
+                                               e_op=np.zeros(1, np.int32), e_dt=np.zeros(1, np.int32), w=np.zeros(2), open_bc=0)
+            arr = {k: np.ascontiguousarray(t[k], dtype=np.int32) for k in ("op_start", "term_start", "e_op", "e_dt")}
+            w = np.ascontiguousarray(t["w"], dtype=np.float64)
+            self._ck(L.alf_b200_set_s0_ising(self.h, int(t["n_terms"]), arr["op_start"].ctypes.data_as(_ip), arr["term_start"].ctypes.data_as(_ip),
+                                             arr["e_op"].ctypes.data_as(_ip), arr["e_dt"].ctypes.data_as(_ip), _d(w), int(t["open_bc"]),
+                                             int(bool(getattr(model, "propose_s0", False)))))
         self._ck(L.alf_b200_finalize_model(self.h))
 
     def _ck(self, rc):

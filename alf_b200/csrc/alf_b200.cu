@@ -91,6 +91,21 @@ int alf_b200_set_op_t(alf_b200_handle* h, int nc, int nf, int N, int diag, const
 
 // projective algorithm: Thtrot and the number of particles per flavor, then one trial wave function pair per flavor
 // (WF_L(nf)%P, WF_R(nf)%P: Ndim x N_part, column-major complex; Prog/main.F90:366-376, 596-599)
+int alf_b200_set_s0_ising(alf_b200_handle* h, int n_terms, const int* op_start, const int* term_start, const int* entry_op, const int* entry_dt,
+                          const double* w, int open_boundaries, int propose_s0) {
+  if (!h) return ALF_ERROR_GENERIC;
+  if (h->finalized) { h->err = "alf_b200_set_s0_ising must be called before alf_b200_finalize_model"; return ALF_ERROR_GENERIC; }
+  h->propose_s0 = propose_s0 ? 1 : 0;
+  if (n_terms <= 0) { h->s0_on = false; return ALF_OK; }
+  if (!op_start || !term_start || !entry_op || !entry_dt || !w || op_start[0] != 0 || op_start[h->n_opv] != n_terms || term_start[0] != 0) { h->err = "alf_b200_set_s0_ising: inconsistent tables"; return ALF_ERROR_GENERIC; }
+  const int ne = term_start[n_terms];
+  for (int e = 0; e < ne; ++e) if (entry_op[e] < 1 || entry_op[e] > h->n_opv || entry_dt[e] <= -h->ltrot || entry_dt[e] >= h->ltrot) { h->err = "alf_b200_set_s0_ising: entry out of range"; return ALF_ERROR_GENERIC; }
+  h->s0_on = true; h->s0_open_bc = open_boundaries ? 1 : 0;
+  h->s0_op_start.assign(op_start, op_start + h->n_opv + 1); h->s0_term_start.assign(term_start, term_start + n_terms + 1);
+  h->s0_e_op.resize(ne); for (int e = 0; e < ne; ++e) h->s0_e_op[e] = entry_op[e] - 1;
+  h->s0_e_dt.assign(entry_dt, entry_dt + ne); h->s0_w.assign(w, w + 2 * (size_t)n_terms);
+  return ALF_OK;
+}
 int alf_b200_set_projector(alf_b200_handle* h, int thtrot, int n_part) {
   if (!h || h->finalized || thtrot < 0 || n_part < 1 || n_part > h->ndim) return ALF_ERROR_HAMILTONIAN;
   h->projector = true; h->thtrot = thtrot; h->n_part = n_part;

@@ -153,6 +153,8 @@ struct alf_b200_handle {
   int n_unit = 0, norb = 1; std::vector<int> site_cell, site_orb, imj;
   bool obs_tau_on = false; double *d_obst_acc = nullptr, *d_obst_bg = nullptr, *d_obst_cnt = nullptr; int obst_ntau = 0;
   bool obs_eq_on = false; double *d_obse_acc = nullptr, *d_obse_bg = nullptr, *d_obse_cnt = nullptr;      // equal-time lattice observables (one time point)
+  // table-driven Ising action for ham%S0 (see S0TabDev) and main.F90's Propose_S0
+  bool s0_on = false; int s0_open_bc = 0, propose_s0 = 0; std::vector<int> s0_op_start, s0_term_start, s0_e_op, s0_e_dt; std::vector<double> s0_w;
   // projective algorithm (Prog/Hamiltonian_main_mod.F90:181-197: Projector, Thtrot, WF_L, WF_R)
   bool projector = false; int thtrot = 0, n_part = 0; std::vector<std::vector<cd>> wf_l, wf_r;   // per flavor, Ndim x N_part column-major
 };
@@ -285,6 +287,7 @@ struct Engine : EngineBase {
   //   kind 0: anything else (k > 2, repeated sites)                         -> per-visit kernel k_wrapgr
   struct VGroup { int n0 = 0, cnt = 0, kind = 0; OpListDev rot[4][ALF_FMAX]; };   // rot: in-left U^H, in-right U, out-left U, out-right U^H
   std::vector<VGroup> groups;
+  S0TabDev s0dev = {0, 0, nullptr, nullptr, nullptr, nullptr, nullptr};
   // tau_m work
   T *GT0 = nullptr, *G0T = nullptr, *G00 = nullptr, *GTT = nullptr, *TMPG = nullptr; UdvDev<T> udvr2;
   // projective algorithm
@@ -340,6 +343,10 @@ struct Engine : EngineBase {
     upd_smem = per_kd * KD + fixed;
     CK(alf_raise_smem(k_wrapgr<T, 1>));
     CK(alf_raise_smem(k_wrapgr<T, 0>));
+    if (h->s0_on) {
+      s0dev.on = 1; s0dev.open_bc = h->s0_open_bc; s0dev.op_start = dupload(h->s0_op_start); s0dev.term_start = dupload(h->s0_term_start);
+      s0dev.e_op = dupload(h->s0_e_op); s0dev.e_dt = dupload(h->s0_e_dt); s0dev.w = dupload(h->s0_w);
+    }
     // vertex groups (see VGroup): greedy over n = 1 .. M
     {
       auto kind_of = [&](int n) {
@@ -352,7 +359,7 @@ struct Engine : EngineBase {
           }
           if (kd < 0) kd = kf; else if (kd != kf) kd = 0;
         }
-        if (getenv("ALF_B200_GENERIC_UPDATE")) kd = 0;
+        if (getenv("ALF_B200_GENERIC_UPDATE") || h->s0_on || h->propose_s0) kd = 0;      // S0 tables / Propose_S0: per-visit kernel (draws depend on the data)
         return kd;
       };
       std::vector<std::vector<char>> seen(F, std::vector<char>(N, 0));
@@ -620,8 +627,8 @@ struct Engine : EngineBase {
     for (int gi = 0; gi < (int)groups.size(); ++gi) {
       const VGroup& g = groups[up ? gi : (int)groups.size() - 1 - gi];
       if (g.kind == 0) {
-        if (up) KL(KC_UPDATE, st, k_wrapgr<T, 1><<<C, 512, upd_smem, st>>>(G, N, F, h->n_sun, g.n0, g.cnt, M, off, d_vops, ft, h->d_fields, L, nt, h->d_rng, h->d_phase, h->d_counters, KD, lg, 0));
-        else KL(KC_UPDATE, st, k_wrapgr<T, 0><<<C, 512, upd_smem, st>>>(G, N, F, h->n_sun, g.n0, g.cnt, M, off, d_vops, ft, h->d_fields, L, nt, h->d_rng, h->d_phase, h->d_counters, KD, lg, 0));
+        if (up) KL(KC_UPDATE, st, k_wrapgr<T, 1><<<C, 512, upd_smem, st>>>(G, N, F, h->n_sun, g.n0, g.cnt, M, off, d_vops, ft, h->d_fields, L, nt, h->d_rng, h->d_phase, h->d_counters, KD, lg, h->propose_s0, s0dev));
+        else KL(KC_UPDATE, st, k_wrapgr<T, 0><<<C, 512, upd_smem, st>>>(G, N, F, h->n_sun, g.n0, g.cnt, M, off, d_vops, ft, h->d_fields, L, nt, h->d_rng, h->d_phase, h->d_counters, KD, lg, h->propose_s0, s0dev));
       } else {
         if (g.kind == 2) rotate_group(g, true);
 #define FAST_LAUNCH(UPV, IPT, PR) KL(KC_UPDATE, st, k_wrapgr_fast<T, UPV, IPT, PR><<<C, 512, fast_smem, st>>>(G, N, F, h->n_sun, g.n0, g.cnt, M, off, d_vops, ft, h->d_fields, L, nt, h->d_rng, h->d_phase, h->d_counters, KDf, ldxf, lg))

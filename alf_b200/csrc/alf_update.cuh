@@ -130,13 +130,32 @@ __device__ __forceinline__ void similarity_immediate(T* __restrict__ G0, int N, 
   __syncthreads();
 }
 
+// ham%S0(n, nt, Hs_new) of Ising actions as tables (Hamiltonian_Z2_Matter_smod.F90:439-512): term t of field n lists the (field, time offset)
+// pairs whose current product of +-1 fields indexes its flip ratio w[t][prod < 0 ? 0 : 1]; S0 is the product over the field's terms.  Time
+// offsets wrap periodically, or (open_bc, projective algorithm :465-472) terms that leave 1..Ltrot are dropped.  on == 0: S0 = 1 (S0_base).
+struct S0TabDev { int on, open_bc; const int* op_start; const int* term_start; const int* e_op; const int* e_dt; const double* w; };
+__device__ __forceinline__ double s0_eval(const S0TabDev& t, const int8_t* __restrict__ fchain, int n, int nt, int Ltrot, int n_opv) {
+  if (!t.on) return 1.0;
+  double S = 1.0;
+  for (int q = t.op_start[n]; q < t.op_start[n + 1]; ++q) {
+    int prod = 1; bool skip = false;
+    for (int e = t.term_start[q]; e < t.term_start[q + 1]; ++e) {
+      int nt1 = nt + t.e_dt[e];
+      if (nt1 > Ltrot || nt1 < 1) { if (t.open_bc) { skip = true; break; } nt1 = (nt1 > Ltrot) ? nt1 - Ltrot : nt1 + Ltrot; }
+      prod *= (fchain[(long)(nt1 - 1) * n_opv + t.e_op[e]] < 0) ? -1 : 1;
+    }
+    if (!skip) S *= t.w[2 * q + (prod > 0 ? 1 : 0)];
+  }
+  return S;
+}
+
 // dynamic smem: X[F][KD][ldx], Y[F][KD][ldx], dl[F][N], dr[F][N], gdiag[F][N] (all T)
 template <typename T, int UP>
 __global__ void __launch_bounds__(512, 1) k_wrapgr(T* __restrict__ G, int N, int F, int n_sun, int n0, int cnt, int n_opv, int log_off,
                                                    const VopDev<T>* __restrict__ vops,
                                                    FieldTabDev ft, int8_t* __restrict__ fields, int Ltrot, int nt, uint64_t* __restrict__ rng,
                                                    cplx* __restrict__ phase, unsigned long long* __restrict__ counters, int KD,
-                                                   uint8_t* __restrict__ acclog, int propose_s0) {   // visits the vertices n0 .. n0 + cnt - 1 of the slice
+                                                   uint8_t* __restrict__ acclog, int propose_s0, S0TabDev s0t) {   // visits the vertices n0 .. n0 + cnt - 1 of the slice
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ UpdCtl ctl[2];
   __shared__ T gpp_s[ALF_FMAX][ALF_KMAX][ALF_KMAX];
@@ -217,7 +236,7 @@ __global__ void __launch_bounds__(512, 1) k_wrapgr(T* __restrict__ G, int N, int
         // --- proposal: nsigma%flip (Fields_mod.F90:173-217), types 1 and 2
         int s_new;
         if (type == 1) s_new = -s_old; else s_new = ft.flip[s_old + 2][r.nranf(3)];
-        double S0_ratio = 1.0, T0_proposal = 1.5, T0_Proposal_ratio = 1.0;   // ham%S0 == 1 (S0_base), Propose_S0 only for type 1
+        double S0_ratio = s0_eval(s0t, fields + (long)chain * Ltrot * n_opv, n, nt, Ltrot, n_opv), T0_proposal = 1.5, T0_Proposal_ratio = 1.0;   // Propose_S0 only for type 1 (Wrapgr_mod.F90:127-132)
         if (propose_s0 && type == 1) { T0_proposal = 1.0 - 1.0 / (1.0 + S0_ratio); T0_Proposal_ratio = 1.0 / S0_ratio; }
         int acc = 0;
         if (T0_proposal > r.ranf()) {

@@ -167,6 +167,10 @@ class Model:
     WF_L: Optional[List[np.ndarray]] = None     # per flavor, (Ndim, N_part) complex
     WF_R: Optional[List[np.ndarray]] = None
 
+    # ham%S0 of Ising actions as tables (alf_b200_set_s0_ising) and main.F90's Propose_S0
+    s0_ising: Optional[dict] = None
+    propose_s0: bool = False
+
     # List(I1, 1:2) of the Hamiltonians (unit cell, orbital) per site, 1-based, and the number of orbitals per unit cell
     # (Prog/Predefined_Latt_mod.F90:250-260); None -> one orbital per cell, site I1 = cell I1
     site_cell: Optional[np.ndarray] = None
@@ -417,6 +421,83 @@ def kondo_square(L1: int, L2: int, beta: float, dtau: float = 0.1, t: float = 1.
     m.n_orb = 2
     m.site_cell = np.repeat(np.arange(1, Nc + 1, dtype=np.int32), 2)
     m.site_orb = np.tile(np.array([1, 2], dtype=np.int32), Nc)
+    return m
+
+
+def z2_gauge_square(L1: int, L2: int, beta: float, dtau: float = 0.1, t_z2: float = 1.0, g: float = 1.0, K: float = 1.0, chem: float = 0.0,
+                    U: float = 0.0, N_SUN: int = 2, propose_s0: bool = False) -> Model:
+    """The Z2-gauge sector of Hamiltonian_Z2_Matter_smod.F90 (Ham_T = 0, hence Ham_J = Ham_h = 0, :163-166): fermions hop only through
+    the Ising bond fields (Predefined_Int_Ising_SUN with Xi = -Ham_TZ2, Ham_V :335-346), optionally with Hubbard vertices first
+    (Ham_U, :329-333).  Field order as Setup_Ising_action_and_field_list (:738-795): for every site I with even Ix + Iy the bonds
+    (I, x), (I, y), (I - a_x, x), (I - a_y, y).  Op_T is the single dense operator of Ham_Hop (:274-296, Checkerboard = .false.,
+    zero hopping, chemical potential on the diagonal).  The Ising action S0 (:439-512) is handed over as tables: transverse-field
+    coupling DW_Ising_tau to the two neighbouring time slices (:474-479, :841-845) and the two plaquettes of the bond
+    DW_Ising_Flux(F1, F2) = exp(2 dtau K F1) exp(2 dtau K F2) (:481-506, :846-850).  All fields are visited sequentially
+    (Overide_global_tau_sampling_parameters :1330-1343: N_Global_tau = 0 without matter fields)."""
+    latt = Lattice(L1, L2)
+    if L1 == 1 or L2 == 1:
+        raise HamiltonianError("Ham_Latt: One dimensional systems are not included")
+    Ndim = latt.N
+    Ltrot = int(round(beta / dtau))
+    op = Op_make(Ndim)
+    for I in range(1, Ndim + 1):
+        op.O[I - 1, I - 1] = -chem
+    op.P[:] = np.arange(1, Ndim + 1); op.g = -dtau
+    Op_set(op)
+    Op_T = [[op]]
+    field_list = {}                 # (site, orientation, type) -> field index (1-based)
+    field_inv = []                  # field -> (site, orientation, type)
+    if abs(U) > EPS_SMALL:
+        for I in range(1, latt.N + 1):
+            field_inv.append((I, 3, 3)); field_list[(I, 3, 3)] = len(field_inv)
+    if abs(t_z2) > EPS_SMALL:
+        for I in range(1, latt.N + 1):
+            ix, iy = latt.list[I - 1]
+            if (ix + iy) % 2 == 0:
+                for (I1, no) in ((I, 1), (I, 2), (latt.nnlist(I, -1, 0), 1), (latt.nnlist(I, 0, -1), 2)):
+                    field_inv.append((I1, no, 1)); field_list[(I1, no, 1)] = len(field_inv)
+    Op_V = []
+    for (I, no, ty) in field_inv:
+        if ty == 3:                # Predefined_Int_U_SUN (Predefined_Int_mod.F90:59-77)
+            o = Op_make(1); o.P[0] = I; o.O[0, 0] = 1.0; o.alpha = -0.5
+            o.g = np.sqrt(complex(-dtau * U / float(N_SUN), 0.0)); o.type = 2
+        else:                      # Predefined_Int_Ising_SUN(OP, I, I1, DTAU, -Ham_TZ2) (Predefined_Int_mod.F90:264-283)
+            I1 = latt.nnlist(I, 1, 0) if no == 1 else latt.nnlist(I, 0, 1)
+            o = Op_make(2); o.P[0], o.P[1] = I, I1; o.O[0, 1] = 1.0; o.O[1, 0] = 1.0
+            o.g = complex(-dtau * (-t_z2), 0.0); o.alpha = 0.0; o.type = 1
+        Op_set(o); Op_V.append([o])
+    # ---- S0 tables
+    dw_tau = (1.0, 1.0)
+    if g > EPS_SMALL:
+        dw_tau = (1.0 / np.tanh(dtau * g), float(np.tanh(dtau * g)))          # (product -1, product +1)
+    dw_flux = (float(np.exp(-2.0 * dtau * K)), float(np.exp(2.0 * dtau * K)))
+    FL = lambda I, no: field_list[(I, no, 1)]
+    op_start, term_start, e_op, e_dt, w = [0], [0], [], [], []
+
+    def term(entries, tab):
+        for (m, dt) in entries:
+            e_op.append(m); e_dt.append(dt)
+        term_start.append(len(e_op)); w.extend(tab)
+    for n, (I1, no, ty) in enumerate(field_inv, start=1):
+        if ty == 1:
+            term([(n, 0), (n, 1)], dw_tau); term([(n, 0), (n, -1)], dw_tau)
+            if no == 1:
+                I2, I3 = latt.nnlist(I1, 0, 1), latt.nnlist(I1, 1, 0)
+                term([(n, 0), (FL(I1, 2), 0), (FL(I2, 1), 0), (FL(I3, 2), 0)], dw_flux)
+                I2, I3 = latt.nnlist(I1, 0, -1), latt.nnlist(I1, 1, -1)
+                term([(n, 0), (FL(I2, 1), 0), (FL(I2, 2), 0), (FL(I3, 2), 0)], dw_flux)
+            else:
+                I2, I3 = latt.nnlist(I1, -1, 0), latt.nnlist(I1, -1, 1)
+                term([(n, 0), (FL(I2, 1), 0), (FL(I2, 2), 0), (FL(I3, 1), 0)], dw_flux)
+                I2, I3 = latt.nnlist(I1, 0, 1), latt.nnlist(I1, 1, 0)
+                term([(n, 0), (FL(I1, 1), 0), (FL(I2, 1), 0), (FL(I3, 2), 0)], dw_flux)
+        op_start.append(len(term_start) - 1)
+    m = Model(name="Z2_Gauge", Ndim=Ndim, N_FL=1, N_SUN=N_SUN, Ltrot=Ltrot, Dtau=dtau, Symm=False, Op_V=Op_V, Op_T=Op_T, latt=latt,
+              params=dict(L1=L1, L2=L2, beta=beta, dtau=dtau, t_z2=t_z2, g=g, K=K, chem=chem, U=U))
+    m.s0_ising = dict(n_terms=len(term_start) - 1, op_start=np.array(op_start, np.int32), term_start=np.array(term_start, np.int32),
+                      e_op=np.array(e_op, np.int32), e_dt=np.array(e_dt, np.int32), w=np.array(w, np.float64), open_bc=0)
+    m.propose_s0 = bool(propose_s0)
+    m.params["field_inv"] = field_inv
     return m
 
 

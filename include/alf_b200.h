@@ -57,6 +57,15 @@ int alf_b200_set_op_t(alf_b200_handle* h, int nc, int nf, int N, int diag, const
  * (Prog/cgr1_mod.F90:207-211, 464-515) and the sweep calls Tau_p instead of TAU_M (Prog/main.F90:829-831, 884-886). */
 int alf_b200_set_projector(alf_b200_handle* h, int thtrot, int n_part);
 int alf_b200_set_trial_wf(alf_b200_handle* h, int nf, const double* P_L, const double* P_R);
+/* ham%S0 for Ising actions as tables (Prog/Hamiltonians/Hamiltonian_Z2_Matter_smod.F90:439-512, tables :841-857), and main.F90's
+ * Propose_S0 (Prog/Wrapgr_mod.F90:127-132).  Field n (1-based) owns the terms op_start[n-1] .. op_start[n]-1; term t lists the entries
+ * term_start[t] .. term_start[t+1]-1, each a (field entry_op, 1-based; time-slice offset entry_dt) pair; the product of the CURRENT +-1
+ * values of those fields selects the flip ratio w[2t] (product -1) or w[2t+1] (product +1); S0(n, nt) is the product over the field's
+ * terms (the field itself is listed where the coupling contains it, as in DW_Ising_tau(nsigma(n,nt)*nsigma(n,nt+1))).  Time offsets
+ * wrap periodically; open_boundaries = 1 drops terms that leave 1..Ltrot (projective algorithm, :465-472).  n_terms = 0: S0 = 1.
+ * Must be called before alf_b200_finalize_model.  With tables or Propose_S0 the slice is visited by the per-visit kernel. */
+int alf_b200_set_s0_ising(alf_b200_handle* h, int n_terms, const int* op_start /* n_opv+1 */, const int* term_start /* n_terms+1 */,
+                          const int* entry_op, const int* entry_dt, const double* w /* 2*n_terms */, int open_boundaries, int propose_s0);
 int alf_b200_finalize_model(alf_b200_handle* h);
 int alf_b200_is_complex(const alf_b200_handle* h);   /* 1 if the complex instantiation was selected */
 

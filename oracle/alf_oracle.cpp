@@ -755,7 +755,25 @@ struct Oracle {
     return Acc;
   }
 
-  double S0(int, int, cd) { return 1.0; }   // Hamiltonian_main_mod S0_base for non-Ising actions (Hubbard_smod.F90:870-885)
+  // ham%S0(n, nt, Hs_new): S0_base = 1 for non-Ising actions (Hamiltonian_main_mod.F90:259-280, Hubbard_smod.F90:870-885).  Ising actions
+  // (Hamiltonian_Z2_Matter_smod.F90:439-512) are products of tabulated flip ratios DW(s s'...) over the couplings the field takes part in:
+  // term t of field n carries the list of (field m, time offset dt) whose current product indexes its table w[t][prod = -1 | +1].
+  // Time offsets wrap periodically (finite temperature, :474-479) or, with open boundaries, terms leaving 1..Ltrot are dropped (projector, :465-472).
+  struct S0Tab { bool on = false, open_bc = false; std::vector<int> op_start, term_start, e_op, e_dt; std::vector<double> w; } s0tab;
+  double S0(int n, int nt, cd) {
+    if (!s0tab.on) return 1.0;
+    double S = 1.0;
+    for (int t = s0tab.op_start[n]; t < s0tab.op_start[n + 1]; ++t) {
+      int prod = 1; bool skip = false;
+      for (int e = s0tab.term_start[t]; e < s0tab.term_start[t + 1]; ++e) {
+        int nt1 = nt + s0tab.e_dt[e];
+        if (nt1 > ltrot || nt1 < 1) { if (s0tab.open_bc) { skip = true; break; } nt1 = (nt1 > ltrot) ? nt1 - ltrot : nt1 + ltrot; }
+        prod *= (fld(s0tab.e_op[e], nt1).real() < 0.0) ? -1 : 1;
+      }
+      if (!skip) S *= s0tab.w[2 * t + (prod > 0 ? 1 : 0)];
+    }
+    return S;
+  }
 
   // ---- Prog/Wrapgr_mod.F90:81-157
   void wrapgrup(int NTAU) {
@@ -1087,6 +1105,15 @@ void orc_destroy(void* h) { delete (Oracle*)h; }
 void orc_set_projector(void* h, int thtrot, int n_part) {
   Oracle* o = (Oracle*)h; o->projector = true; o->thtrot = thtrot; o->n_part = n_part;
   o->WF_L.assign(o->n_fl, std::vector<cd>((size_t)o->ndim * n_part)); o->WF_R = o->WF_L;
+}
+double orc_s0(void* h, int n, int nt) { return ((Oracle*)h)->S0(n - 1, nt, cd(0, 0)); }   // ham%S0(n, nt, .) on the current configuration
+void orc_set_propose_s0(void* h, int on) { ((Oracle*)h)->propose_s0 = on != 0; }
+// table-driven Ising action: op_start[n_opv + 1] -> terms of field n; term_start[n_terms + 1] -> entries; entry = (field, 1-based; dt); w = [n_terms][2]
+void orc_set_s0_ising(void* h, int n_terms, const int* op_start, const int* term_start, const int* e_op, const int* e_dt, const double* w, int open_bc, int propose_s0) {
+  Oracle* o = (Oracle*)h; auto& t = o->s0tab; t.on = true; t.open_bc = open_bc != 0; o->propose_s0 = propose_s0 != 0;
+  t.op_start.assign(op_start, op_start + o->n_opv + 1); t.term_start.assign(term_start, term_start + n_terms + 1);
+  const int ne = term_start[n_terms]; t.e_op.resize(ne); t.e_dt.assign(e_dt, e_dt + ne); for (int i = 0; i < ne; ++i) t.e_op[i] = e_op[i] - 1;
+  t.w.assign(w, w + 2 * (size_t)n_terms);
 }
 void orc_set_trial_wf(void* h, int nf, const double* PL, const double* PR) {
   Oracle* o = (Oracle*)h; size_t n = (size_t)o->ndim * o->n_part;

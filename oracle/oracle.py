@@ -32,6 +32,7 @@ def lib():
         _lib = C.CDLL(_LIB)
         _lib.orc_create.restype = C.c_void_p
         _lib.orc_ranf.restype = C.c_double
+        _lib.orc_s0.restype = C.c_double
         _lib.orc_get_log.restype = C.c_long
         _lib.orc_taum_get.restype = C.c_long
         _lib.orc_taum_fresh_get.restype = C.c_long
@@ -72,11 +73,28 @@ class Oracle:
             for nf in range(model.N_FL):
                 L.orc_set_trial_wf(self.h, nf + 1, _d(_cplx(model.WF_L[nf])), _d(_cplx(model.WF_R[nf])))
 
+        s0 = getattr(model, "s0_ising", None)
+        if s0 is not None or getattr(model, "propose_s0", False):
+            t = s0 if s0 is not None else dict(n_terms=0, op_start=np.zeros(model.n_opv + 1, np.int32), term_start=np.zeros(1, np.int32),
+                                               e_op=np.zeros(1, np.int32), e_dt=np.zeros(1, np.int32), w=np.zeros(2), open_bc=0)
+            arr = {k: np.ascontiguousarray(t[k], dtype=np.int32) for k in ("op_start", "term_start", "e_op", "e_dt")}
+            w = np.ascontiguousarray(t["w"], dtype=np.float64)
+            if int(t["n_terms"]) > 0:
+                L.orc_set_s0_ising(self.h, int(t["n_terms"]), arr["op_start"].ctypes.data_as(_ip), arr["term_start"].ctypes.data_as(_ip),
+                                   arr["e_op"].ctypes.data_as(_ip), arr["e_dt"].ctypes.data_as(_ip), _d(w), int(t["open_bc"]),
+                                   int(bool(getattr(model, "propose_s0", False))))
+            elif getattr(model, "propose_s0", False):
+                L.orc_set_propose_s0(self.h, 1)
+
     def __del__(self):
         try:
             lib().orc_destroy(self.h)
         except Exception:
             pass
+
+    def s0(self, n: int, nt: int) -> float:
+        """ham%S0(n, nt, flipped value) on the current configuration (1-based n, nt)."""
+        return lib().orc_s0(self.h, int(n), int(nt))
 
     # --- RNG / fields
     def ranset(self, seed: int):

@@ -54,3 +54,23 @@ def test_latt_bin_layout_fourier_and_roundtrip(tmp_path):
     assert sign == 1.0 and np.allclose(bg, [2.0]) and o.shape == (8, 3, 1, 1)
     assert np.allclose(o[:, :, 0, 0], np.array([1.0, 2.0, 3.0])[None, :])
     assert "Unit cells" in open(p + "_info").read()
+
+
+def test_conf_roundtrip_all_field_types(tmp_path):
+    """confout/confin text layout (Prog/Fields_mod.F90:631-662, 750-774): seed vector line, then one value per (I, NT), I fastest; integer for
+    types 1/2, real for type 3, complex for type 4.  Round trip is exact, and the file parses with the reference's record structure."""
+    from alf_b200 import conf
+    rng = np.random.default_rng(3); ltrot, types = 5, np.array([1, 2, 3, 4, 1, 3])
+    f = np.zeros((ltrot, types.size), dtype=np.complex128)
+    f[:, types == 1] = rng.choice([-1, 1], size=(ltrot, 2)); f[:, types == 2] = rng.choice([-2, -1, 1, 2], size=(ltrot, 1))
+    f[:, types == 3] = rng.normal(size=(ltrot, 2)); f[:, types == 4] = (rng.normal(size=(ltrot, 1)) + 1j * rng.normal(size=(ltrot, 1)))
+    state = rng.integers(0, 2**63, size=4, dtype=np.uint64) * np.uint64(2) + np.uint64(1)
+    sv = conf.state_to_seed_vec(state)
+    assert sv.dtype == np.int32 and sv.size == conf.SEED_LEN and np.array_equal(conf.seed_vec_to_state(sv), state)
+    p = str(tmp_path / conf.conf_name("confout", 3)); assert p.endswith("confout_3")
+    conf.write_conf(p, sv, f, types)
+    lines = open(p).read().splitlines()
+    assert len(lines) == 1 + ltrot * types.size and len(lines[0].split()) == conf.SEED_LEN
+    assert int(lines[1]) == int(f[0, 0].real) and lines[4].strip().startswith("(")          # I fastest: line 1 + I of slice 1
+    sv2, f2 = conf.read_conf(p, ltrot, types)
+    assert np.array_equal(sv2, sv) and np.array_equal(f2, f)

@@ -8,7 +8,7 @@ import pytest
 
 from alf_b200 import api
 from alf_b200.api import AlfB200
-from alf_b200.model import hubbard_square, hubbard_chain, kondo_square
+from alf_b200.model import hubbard_square, hubbard_chain, kondo_square, z2_gauge_square
 import oracle.oracle as O
 from oracle.oracle import Oracle
 from common import relF, SEEDS, TOL_G, config1, config2, config3
@@ -798,3 +798,48 @@ def test_handles_are_reentrant_across_threads():
                 assert relF(g.green(c, nf), o.green(nf)) < TOL_G, m.name
             assert abs(ph[c] - o.phase()) < 1e-9
         g.close()
+
+
+def test_confout_restart_continues_the_chain(tmp_path):
+    """Checkpoint / restart through ALF's confout_<rank> text files (Prog/Fields_mod.F90:631-662,750-774): a handle restarted from the
+    files written after sweep 1 reproduces sweep 2 of the uninterrupted run bit for bit (fields) and G to 1e-10."""
+    from alf_b200 import conf
+    m = hubbard_square(4, 4, 1.0); seeds = SEEDS[:3]
+    a = AlfB200(m, n_chains=3, nwrap=5); a.set_seeds(seeds); a.fields_set(); a.init_sweep(); a.sweep(1, 0)
+    files = conf.write_confs(a, str(tmp_path)); assert [os.path.basename(f) for f in files] == ["confout_0", "confout_1", "confout_2"]
+    a.sweep(1, 0)
+    for f in files:
+        os.rename(f, os.path.join(os.path.dirname(f), os.path.basename(f).replace("confout", "confin")))
+    b = AlfB200(m, n_chains=3, nwrap=5); b.set_seeds([1, 2, 3]); conf.read_confs(b, str(tmp_path)); b.init_sweep(); b.sweep(1, 0)
+    assert np.array_equal(a.get_fields(), b.get_fields()) and np.array_equal(a.rng_state(), b.rng_state())
+    for c in range(3):
+        for nf in (1, 2):
+            assert relF(b.green(c, nf), a.green(c, nf)) < TOL_G
+    a.close(); b.close()
+
+
+@pytest.mark.parametrize("variant", ["gauge", "gauge_propose_s0", "gauge_hubbard", "gauge_no_action"])
+def test_ising_action_s0_tables_sweep_parity(variant):
+    """ham%S0 as device-side tables: the Z2-gauge sector of Hamiltonian_Z2_Matter (Ising bond vertices, type 1, k = 2; Ising action
+    in time and on plaquettes; Hamiltonian_Z2_Matter_smod.F90:439-512) swept on the device gives the oracle's accept / reject / not-proposed
+    sequence, fields, G and phase -- also with main.F90's Propose_S0 (data-dependent number of random draws, Wrapgr_mod.F90:127-140) and
+    with Hubbard vertices mixed in."""
+    kw = dict(g=0.8, K=0.5)
+    if variant == "gauge_hubbard":
+        kw.update(U=2.0)
+    if variant == "gauge_no_action":
+        kw.update(g=0.0, K=0.0)
+    m = z2_gauge_square(4, 4, beta=1.0, dtau=0.1, propose_s0=(variant == "gauge_propose_s0"), **kw)
+    seeds = SEEDS[:3]
+    g = AlfB200(m, n_chains=len(seeds), nwrap=5); g.set_seeds(seeds); g.fields_set(); g.init_sweep(); g.accept_log(2); g.sweep(2, 0)
+    log = g.get_accept_log(); f = g.get_fields(); ph = g.phase()
+    for c, s in enumerate(seeds):
+        o = Oracle(m, nwrap=5); o.ranset(s); o.fields_set(); o.init(); o.log(True); o.sweep(0); o.sweep(0)
+        acc, _ = o.get_log()
+        assert np.array_equal(acc, log[c]), variant
+        if variant == "gauge_propose_s0":
+            assert (acc == 2).any() and (acc == 1).any()               # some visits are not proposed at all
+        assert np.array_equal(f[c], o.get_fields())
+        assert relF(g.green(c, 1), o.green(1)) < TOL_G
+        assert abs(ph[c] - o.phase()) < 1e-9
+    g.close()

@@ -316,3 +316,28 @@ def test_projector_green_vs_bruteforce(trial, Mz):
     o.sweep(1)
     c = o.control()
     assert c["XMAXG"] < 1e-8 and c["XMAX_tau"] < 1e-8 and c["NCG_tau"] > 0 and c["nan"] == 0
+
+
+def test_s0_tables_of_z2_gauge_model_match_the_ising_action():
+    """The Ising action of Hamiltonian_Z2_Matter_smod.F90 (gauge sector: transverse-field coupling in time, :841-845; plaquette flux term,
+    :846-850) evaluated by brute force: for random single flips the ratio of Boltzmann weights equals the table-driven S0(n, nt)
+    (:439-512) that the oracle and the CUDA path use."""
+    from alf_b200.model import z2_gauge_square
+    dtau, g, K = 0.1, 0.7, 0.4
+    m = z2_gauge_square(4, 4, beta=0.6, dtau=dtau, g=g, K=K)
+    o = Oracle(m, nwrap=3); o.ranset(77); o.fields_set()
+    f = o.get_fields().real.copy()                                     # (Ltrot, n_opv)
+    L, M = f.shape; latt = m.latt; inv = m.params["field_inv"]; FL = {(I, no): n for n, (I, no, ty) in enumerate(inv)}
+    gam = -0.5 * np.log(np.tanh(dtau * g))
+
+    def log_weight(c):
+        s = gam * np.sum(c * np.roll(c, -1, axis=0))
+        for I in range(1, latt.N + 1):                                   # plaquette with lower-left corner I
+            Ix, Iy = latt.nnlist(I, 1, 0), latt.nnlist(I, 0, 1)
+            s += -dtau * K * np.sum(c[:, FL[(I, 1)]] * c[:, FL[(I, 2)]] * c[:, FL[(Iy, 1)]] * c[:, FL[(Ix, 2)]])
+        return s
+    rng = np.random.default_rng(0); w0 = log_weight(f)
+    for _ in range(40):
+        n, nt = int(rng.integers(0, M)), int(rng.integers(0, L))
+        c = f.copy(); c[nt, n] = -c[nt, n]
+        assert abs(np.exp(log_weight(c) - w0) / o.s0(n + 1, nt + 1) - 1) < 1e-12, (n, nt)
