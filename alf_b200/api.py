@@ -76,6 +76,16 @@ class AlfB200:
             self._ck(L.alf_b200_set_s0_ising(self.h, int(t["n_terms"]), arr["op_start"].ctypes.data_as(_ip), arr["term_start"].ctypes.data_as(_ip),
                                              arr["e_op"].ctypes.data_as(_ip), arr["e_dt"].ctypes.data_as(_ip), _d(w), int(t["open_bc"]),
                                              int(bool(getattr(model, "propose_s0", False)))))
+        gt = getattr(model, "global_tau", None)
+        if gt is not None and (gt["n_global_tau"] > 0 or gt["nt_seq_end"] != model.n_opv):
+            self._ck(L.alf_b200_set_global_tau_sampling(self.h, int(gt["nt_seq_start"]), int(gt["nt_seq_end"]), int(gt["n_global_tau"])))
+        gm = getattr(model, "global_move_tau_ising", None)
+        if gm is not None:
+            a = {k: np.ascontiguousarray(gm[k], dtype=np.int32) for k in ("move_start", "move_fields", "op_start", "term_start", "e_op", "e_dt")}
+            w = np.ascontiguousarray(gm["w"], dtype=np.float64)
+            self._ck(L.alf_b200_set_global_move_tau_ising(self.h, int(gm["n_sites"]), a["move_start"].ctypes.data_as(_ip), a["move_fields"].ctypes.data_as(_ip),
+                                                          int(gm["n_terms"]), a["op_start"].ctypes.data_as(_ip), a["term_start"].ctypes.data_as(_ip),
+                                                          a["e_op"].ctypes.data_as(_ip), a["e_dt"].ctypes.data_as(_ip), _d(w), int(gm["open_bc"])))
         self._ck(L.alf_b200_finalize_model(self.h))
 
     def _ck(self, rc):

@@ -106,6 +106,37 @@ int alf_b200_set_s0_ising(alf_b200_handle* h, int n_terms, const int* op_start, 
   h->s0_e_dt.assign(entry_dt, entry_dt + ne); h->s0_w.assign(w, w + 2 * (size_t)n_terms);
   return ALF_OK;
 }
+int alf_b200_set_global_tau_sampling(alf_b200_handle* h, int nt_sequential_start, int nt_sequential_end, int n_global_tau) {
+  if (!h) return ALF_ERROR_GENERIC;
+  if (h->finalized) { h->err = "alf_b200_set_global_tau_sampling must be called before alf_b200_finalize_model"; return ALF_ERROR_GENERIC; }
+  if (nt_sequential_start < 1 || nt_sequential_end > h->n_opv || nt_sequential_start > nt_sequential_end + 1 || n_global_tau < 0) { h->err = "alf_b200_set_global_tau_sampling: illegal range"; return ALF_ERROR_GENERIC; }
+  h->nt_seq_start = nt_sequential_start; h->nt_seq_end = nt_sequential_end; h->n_global_tau = n_global_tau;
+  return ALF_OK;
+}
+int alf_b200_set_global_move_tau_ising(alf_b200_handle* h, int n_sites, const int* move_start, const int* move_fields, int n_terms, const int* site_term_start,
+                                       const int* term_start, const int* entry_op, const int* entry_dt, const double* w, int open_boundaries) {
+  if (!h) return ALF_ERROR_GENERIC;
+  if (h->finalized) { h->err = "alf_b200_set_global_move_tau_ising must be called before alf_b200_finalize_model"; return ALF_ERROR_GENERIC; }
+  if (n_sites < 1 || !move_start || !move_fields || n_terms < 0 || !site_term_start || !term_start || !w || move_start[0] != 0 || site_term_start[0] != 0 ||
+      site_term_start[n_sites] != n_terms || term_start[0] != 0) { h->err = "alf_b200_set_global_move_tau_ising: inconsistent tables"; return ALF_ERROR_GENERIC; }
+  for (int I = 0; I < n_sites; ++I) {
+    const int len = move_start[I + 1] - move_start[I];
+    if (len < 1 || len > ALF_GM_MAXLEN) { h->err = "alf_b200_set_global_move_tau_ising: a move flips between 1 and 16 fields"; return ALF_ERROR_GENERIC; }
+    for (int e = move_start[I]; e < move_start[I + 1]; ++e) {
+      if (move_fields[e] < 1 || move_fields[e] > h->n_opv || (e > move_start[I] && move_fields[e] <= move_fields[e - 1])) { h->err = "alf_b200_set_global_move_tau_ising: Flip_list must be ascending (Wrapgr_sort) and in range"; return ALF_ERROR_GENERIC; }
+      if (h->opv[(size_t)(move_fields[e] - 1)].type != 1) { h->err = "alf_b200_set_global_move_tau_ising: only Ising (type 1) fields"; return ALF_ERROR_UNSUPPORTED; }
+    }
+  }
+  const int ne = term_start[n_terms];
+  for (int e = 0; e < ne; ++e) if (entry_op[e] < 1 || entry_op[e] > h->n_opv || entry_dt[e] <= -h->ltrot || entry_dt[e] >= h->ltrot) { h->err = "alf_b200_set_global_move_tau_ising: entry out of range"; return ALF_ERROR_GENERIC; }
+  h->gmt_on = true; h->gmt_n_sites = n_sites; h->gmt_open_bc = open_boundaries ? 1 : 0;
+  h->gmt_move_start.assign(move_start, move_start + n_sites + 1); h->gmt_move_fields.resize(move_start[n_sites]);
+  for (int e = 0; e < move_start[n_sites]; ++e) h->gmt_move_fields[e] = move_fields[e] - 1;
+  h->gmt_op_start.assign(site_term_start, site_term_start + n_sites + 1); h->gmt_term_start.assign(term_start, term_start + n_terms + 1);
+  h->gmt_e_op.resize(ne); for (int e = 0; e < ne; ++e) h->gmt_e_op[e] = entry_op[e] - 1;
+  h->gmt_e_dt.assign(entry_dt, entry_dt + ne); h->gmt_w.assign(w, w + 2 * (size_t)n_terms);
+  return ALF_OK;
+}
 int alf_b200_set_projector(alf_b200_handle* h, int thtrot, int n_part) {
   if (!h || h->finalized || thtrot < 0 || n_part < 1 || n_part > h->ndim) return ALF_ERROR_HAMILTONIAN;
   h->projector = true; h->thtrot = thtrot; h->n_part = n_part;

@@ -155,6 +155,9 @@ struct alf_b200_handle {
   bool obs_eq_on = false; double *d_obse_acc = nullptr, *d_obse_bg = nullptr, *d_obse_cnt = nullptr;      // equal-time lattice observables (one time point)
   // table-driven Ising action for ham%S0 (see S0TabDev) and main.F90's Propose_S0
   bool s0_on = false; int s0_open_bc = 0, propose_s0 = 0; std::vector<int> s0_op_start, s0_term_start, s0_e_op, s0_e_dt; std::vector<double> s0_w;
+  // Nt_sequential_start / _end, N_Global_tau (Overide_global_tau_sampling_parameters) and ham%Global_move_tau as tables (see GmtDev)
+  int nt_seq_start = 1, nt_seq_end = -1, n_global_tau = 0;
+  bool gmt_on = false; int gmt_n_sites = 0, gmt_open_bc = 0; std::vector<int> gmt_move_start, gmt_move_fields, gmt_op_start, gmt_term_start, gmt_e_op, gmt_e_dt; std::vector<double> gmt_w;
   // projective algorithm (Prog/Hamiltonian_main_mod.F90:181-197: Projector, Thtrot, WF_L, WF_R)
   bool projector = false; int thtrot = 0, n_part = 0; std::vector<std::vector<cd>> wf_l, wf_r;   // per flavor, Ndim x N_part column-major
 };
@@ -241,6 +244,7 @@ __global__ void __launch_bounds__(128) k_obs_scalar(const T* __restrict__ G, lon
   }
 }
 
+static __global__ void k_fill_int(int* __restrict__ p, int n, int v) { const int i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) p[i] = v; }
 // G0T = -(1 - G)  (tau_m_mod.F90:96-104)
 template <typename T>
 __global__ void k_g0t_init(T* __restrict__ G0T, const T* __restrict__ G, long sM, int n) {
@@ -288,6 +292,8 @@ struct Engine : EngineBase {
   struct VGroup { int n0 = 0, cnt = 0, kind = 0; OpListDev rot[4][ALF_FMAX]; };   // rot: in-left U^H, in-right U, out-left U, out-right U^H
   std::vector<VGroup> groups;
   S0TabDev s0dev = {0, 0, nullptr, nullptr, nullptr, nullptr, nullptr};
+  GmtDev gmtdev = {0, 0, nullptr, nullptr, {0, 0, nullptr, nullptr, nullptr, nullptr, nullptr}};
+  int seq_lo = 0, seq_hi = 0;      // sequential visits: fields seq_lo .. seq_hi - 1 (0-based)
   // tau_m work
   T *GT0 = nullptr, *G0T = nullptr, *G00 = nullptr, *GTT = nullptr, *TMPG = nullptr; UdvDev<T> udvr2;
   // projective algorithm
@@ -347,6 +353,14 @@ struct Engine : EngineBase {
       s0dev.on = 1; s0dev.open_bc = h->s0_open_bc; s0dev.op_start = dupload(h->s0_op_start); s0dev.term_start = dupload(h->s0_term_start);
       s0dev.e_op = dupload(h->s0_e_op); s0dev.e_dt = dupload(h->s0_e_dt); s0dev.w = dupload(h->s0_w);
     }
+    seq_lo = h->nt_seq_start - 1; seq_hi = (h->nt_seq_end < 0) ? M : h->nt_seq_end;
+    if (seq_lo < 0 || seq_hi > M || seq_lo > seq_hi) throw CudaError("illegal Nt_sequential_start / Nt_sequential_end");
+    if ((seq_lo > 0 || seq_hi < M) && h->n_global_tau <= 0) throw CudaError("a restricted sequential range needs N_Global_tau > 0 (Wrapgr_mod.F90:148-153)");
+    if (h->gmt_on) {
+      gmtdev.on = 1; gmtdev.n_sites = h->gmt_n_sites; gmtdev.move_start = dupload(h->gmt_move_start); gmtdev.move_fields = dupload(h->gmt_move_fields);
+      gmtdev.terms.on = 1; gmtdev.terms.open_bc = h->gmt_open_bc; gmtdev.terms.op_start = dupload(h->gmt_op_start); gmtdev.terms.term_start = dupload(h->gmt_term_start);
+      gmtdev.terms.e_op = dupload(h->gmt_e_op); gmtdev.terms.e_dt = dupload(h->gmt_e_dt); gmtdev.terms.w = dupload(h->gmt_w);
+    }
     // vertex groups (see VGroup): greedy over n = 1 .. M
     {
       auto kind_of = [&](int n) {
@@ -366,7 +380,7 @@ struct Engine : EngineBase {
       for (int n = 0; n < M; ++n) {
         const int kd = kind_of(n); bool clash = false;
         for (int f = 0; f < F; ++f) { const HostOp& o = h->opv[n + (size_t)M * f]; for (int a = 0; a < o.N; ++a) if (seen[f][o.P[a]]) clash = true; }
-        if (groups.empty() || groups.back().kind != kd || (kd != 0 && clash)) {
+        if (groups.empty() || groups.back().kind != kd || (kd != 0 && clash) || n == seq_lo || n == seq_hi) {
           VGroup g; g.n0 = n; g.kind = kd; groups.push_back(g);
           for (int f = 0; f < F; ++f) std::fill(seen[f].begin(), seen[f].end(), 0);
         }
@@ -610,10 +624,20 @@ struct Engine : EngineBase {
   void wrapgrup(int ntau) override {
     mmthr(G); mmthl_m1(G);
     launch_update(1, ntau + 1);
+    if (h->n_global_tau > 0 && h->gmt_on) { gm_set_position(seq_hi); gm_device_moves(ntau + 1, M); }           // Wrapgr_mod.F90:148-153
   }
   void wrapgrdo(int ntau) override {
+    if (h->n_global_tau > 0 && h->gmt_on) { gm_set_position(M); gm_device_moves(ntau, seq_hi); }               // :189-194
     launch_update(0, ntau);
     mmthl(G); mmthr_m1(G);
+  }
+  // Wrapgr_Random_update with ham%Global_move_tau evaluated on the device from the tables, then Wrapgr_PlaceGR(GR, m, place_to, ntau)
+  void gm_device_moves(int ntau, int place_to) {
+    gm_alloc();
+    const size_t smem = sizeof(T) * ((size_t)3 * N + 2 * ALF_KMAX * ALF_KMAX) + 64;
+    CK(alf_raise_smem(k_random_update<T>));
+    KL(KC_UPDATE, st, k_random_update<T><<<C, 512, smem, st>>>(G, G2, N, F, h->n_sun, M, d_vops, ft, h->d_fields, L, ntau, h->d_rng, h->d_phase, h->d_counters, d_mpos,
+                                                               h->n_global_tau, 1, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, place_to, gmtdev));
   }
   void rotate_group(const VGroup& g, bool in) {     // G <- U^H G U (in) / U G U^H (out) for all vertices of a pair group
     ModelDev m2 = md;
@@ -626,6 +650,7 @@ struct Engine : EngineBase {
     int off = 0;
     for (int gi = 0; gi < (int)groups.size(); ++gi) {
       const VGroup& g = groups[up ? gi : (int)groups.size() - 1 - gi];
+      if (g.n0 < seq_lo || g.n0 >= seq_hi) continue;                  // not visited sequentially (Nt_sequential_start .. Nt_sequential_end)
       if (g.kind == 0) {
         if (up) KL(KC_UPDATE, st, k_wrapgr<T, 1><<<C, 512, upd_smem, st>>>(G, N, F, h->n_sun, g.n0, g.cnt, M, off, d_vops, ft, h->d_fields, L, nt, h->d_rng, h->d_phase, h->d_counters, KD, lg, h->propose_s0, s0dev));
         else KL(KC_UPDATE, st, k_wrapgr<T, 0><<<C, 512, upd_smem, st>>>(G, N, F, h->n_sun, g.n0, g.cnt, M, off, d_vops, ft, h->d_fields, L, nt, h->d_rng, h->d_phase, h->d_counters, KD, lg, h->propose_s0, s0dev));
@@ -845,7 +870,7 @@ struct Engine : EngineBase {
   // ---------------------------------------------------------------- global-in-slice moves (Prog/Wrapgr_mod.F90:247-433)
   int* d_mpos = nullptr;
   void gm_alloc() { if (!d_mpos) { d_mpos = dalloc<int>(C); CK(cudaMemsetAsync(d_mpos, 0, sizeof(int) * C, st)); } }
-  void gm_set_position(int m) override { gm_alloc(); std::vector<int> v(C, m); CK(cudaMemcpyAsync(d_mpos, v.data(), sizeof(int) * C, cudaMemcpyHostToDevice, st)); sync(); }
+  void gm_set_position(int m) override { gm_alloc(); KL(KC_EW, st, k_fill_int<<<ew_blocks(C), 256, 0, st>>>(d_mpos, C, m)); }
   void gm_get_position(int* m) override { gm_alloc(); sync(); CK(cudaMemcpy(m, d_mpos, sizeof(int) * C, cudaMemcpyDeviceToHost)); }
   void gm_random_update(int ntau, int n_moves, int maxlen, const int* len, const int* list0, const int8_t* val, const double* t0, const double* s0,
                         uint8_t* acc_out, int place_to) override {
@@ -864,7 +889,7 @@ struct Engine : EngineBase {
     const size_t smem = sizeof(T) * ((size_t)3 * N + 2 * ALF_KMAX * ALF_KMAX) + 64;
     CK(alf_raise_smem(k_random_update<T>));
     KL(KC_UPDATE, st, k_random_update<T><<<C, 512, smem, st>>>(G, G2, N, F, h->n_sun, M, d_vops, ft, h->d_fields, L, ntau, h->d_rng, h->d_phase, h->d_counters, d_mpos,
-                                                               n_moves, std::max(maxlen, 1), d_len, d_list, d_val, d_t0, d_s0, d_acc, place_to));
+                                                               n_moves, std::max(maxlen, 1), d_len, d_list, d_val, d_t0, d_s0, d_acc, place_to, GmtDev{0, 0, nullptr, nullptr, {0, 0, nullptr, nullptr, nullptr, nullptr, nullptr}}));
     if (acc_out && n_moves > 0) { CK(cudaMemcpyAsync(acc_out, d_acc, np, cudaMemcpyDeviceToHost, st)); }
     sync();
   }

@@ -38,6 +38,30 @@ __device__ __forceinline__ void gm_similarity(T* __restrict__ Gf, int N, const V
   similarity_immediate<T>(Gf, N, nullptr, nullptr, 0, 0, ones, ones, op->P, k, AL, AR);
 }
 
+// ham%Global_move_tau for Ising star moves as tables (Hamiltonian_Z2_Matter_smod.F90:535-643), evaluated on the device: a site
+// I = nranf(n_sites) is drawn from the chain's stream, the (ascending) fields move_fields[move_start[I] ..) are flipped, S0_Matter is the
+// product of the site's coupling terms (same form as S0TabDev: products of current +-1 fields at time offsets -> flip-ratio table),
+// T0_Proposal = 1 - 1/(1 + S0_Matter) is tested against one ranf() and T0_Proposal_ratio = 1/S0_Matter or 0 (:633-641).
+struct GmtDev { int on, n_sites; const int* move_start; const int* move_fields; S0TabDev terms; };
+
+// product over the owner's terms, evaluated by the whole CTA (one entry per thread and pass, parity through __syncthreads_count):
+// every thread returns the same value.  Must be called by all threads of the block.
+__device__ __forceinline__ double ising_terms_block(const S0TabDev& t, const int8_t* __restrict__ fchain, int owner, int nt, int Ltrot, int n_opv) {
+  double S = 1.0;
+  for (int q = t.op_start[owner]; q < t.op_start[owner + 1]; ++q) {
+    const int e0 = t.term_start[q], e1 = t.term_start[q + 1];
+    int neg = 0, out = 0;
+    for (int e = e0 + (int)threadIdx.x; e < e1; e += (int)blockDim.x) {
+      int nt1 = nt + t.e_dt[e];
+      if (nt1 > Ltrot || nt1 < 1) { if (t.open_bc) { out = 1; continue; } nt1 = (nt1 > Ltrot) ? nt1 - Ltrot : nt1 + Ltrot; }
+      neg ^= (fchain[(long)(nt1 - 1) * n_opv + t.e_op[e]] < 0) ? 1 : 0;
+    }
+    const int nneg = __syncthreads_count(neg), nout = __syncthreads_count(out);
+    if (!nout) S *= t.w[2 * q + ((nneg & 1) ? 0 : 1)];
+  }
+  return S;
+}
+
 // proposals: [chain][move]: length, t0 ratio, s0 ratio; [chain][move][maxlen]: 0-based op index (ascending), new field value
 template <typename T>
 __global__ void __launch_bounds__(512, 1) k_random_update(T* __restrict__ G, T* __restrict__ Gst, int N, int F, int n_sun, int M, const VopDev<T>* __restrict__ vops,
@@ -45,7 +69,7 @@ __global__ void __launch_bounds__(512, 1) k_random_update(T* __restrict__ G, T* 
                                                           cplx* __restrict__ phase, unsigned long long* __restrict__ counters, int* __restrict__ mpos,
                                                           int n_moves, int maxlen, const int* __restrict__ flip_len, const int* __restrict__ flip_list,
                                                           const int8_t* __restrict__ flip_val, const double* __restrict__ t0r, const double* __restrict__ s0r,
-                                                          uint8_t* __restrict__ acc_out, int place_to /* >= 0: final PlaceGR target, -1: none */) {
+                                                          uint8_t* __restrict__ acc_out, int place_to /* >= 0: final PlaceGR target, -1: none */, GmtDev gmt) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   T* ones = reinterpret_cast<T*>(smem_raw);        // N
   T* col = ones + N;                               // N
@@ -77,8 +101,16 @@ __global__ void __launch_bounds__(512, 1) k_random_update(T* __restrict__ G, T* 
 
   for (int mv = 0; mv < n_moves; ++mv) {
     const long pi = (long)chain * n_moves + mv;
-    const int len = flip_len[pi]; const double T0 = t0r[pi], S0 = s0r[pi];
-    const int* fl = flip_list + pi * maxlen; const int8_t* fv = flip_val + pi * maxlen;
+    int len; double T0, S0; const int* fl; const int8_t* fv; int8_t fv_dev[ALF_GM_MAXLEN];
+    if (gmt.on) {                                   // the proposal comes from the tables (every thread draws the same numbers)
+      const int I = r.nranf(gmt.n_sites) - 1;
+      fl = gmt.move_fields + gmt.move_start[I]; len = gmt.move_start[I + 1] - gmt.move_start[I];
+      for (int c = 0; c < len && c < ALF_GM_MAXLEN; ++c) fv_dev[c] = (int8_t)(-fld[fl[c]]);      // nsigma%flip of an Ising field (Fields_mod.F90:190)
+      fv = fv_dev;
+      S0 = ising_terms_block(gmt.terms, fields + (long)chain * Ltrot * M, I, nt, Ltrot, M);
+      const double T0_Proposal = 1.0 - 1.0 / (1.0 + S0);
+      T0 = (T0_Proposal > r.ranf()) ? 1.0 / S0 : 0.0;
+    } else { len = flip_len[pi]; T0 = t0r[pi]; S0 = s0r[pi]; fl = flip_list + pi * maxlen; fv = flip_val + pi * maxlen; }
     if (!(T0 > 10e-8) || len <= 0) { if (acc_out && tid == 0) acc_out[pi] = 2; continue; }
     cplx prev = cplx(1.0, 0.0);
     int acc = 0;

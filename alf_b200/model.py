@@ -170,6 +170,9 @@ class Model:
     # ham%S0 of Ising actions as tables (alf_b200_set_s0_ising) and main.F90's Propose_S0
     s0_ising: Optional[dict] = None
     propose_s0: bool = False
+    # Nt_sequential_start / _end, N_Global_tau (Hamiltonian_main_mod.F90 Overide_global_tau_sampling_parameters) and ham%Global_move_tau as tables
+    global_tau: Optional[dict] = None
+    global_move_tau_ising: Optional[dict] = None
 
     # List(I1, 1:2) of the Hamiltonians (unit cell, orbital) per site, 1-based, and the number of orbitals per unit cell
     # (Prog/Predefined_Latt_mod.F90:250-260); None -> one orbital per cell, site I1 = cell I1
@@ -424,21 +427,33 @@ def kondo_square(L1: int, L2: int, beta: float, dtau: float = 0.1, t: float = 1.
     return m
 
 
-def z2_gauge_square(L1: int, L2: int, beta: float, dtau: float = 0.1, t_z2: float = 1.0, g: float = 1.0, K: float = 1.0, chem: float = 0.0,
-                    U: float = 0.0, N_SUN: int = 2, propose_s0: bool = False) -> Model:
-    """The Z2-gauge sector of Hamiltonian_Z2_Matter_smod.F90 (Ham_T = 0, hence Ham_J = Ham_h = 0, :163-166): fermions hop only through
-    the Ising bond fields (Predefined_Int_Ising_SUN with Xi = -Ham_TZ2, Ham_V :335-346), optionally with Hubbard vertices first
-    (Ham_U, :329-333).  Field order as Setup_Ising_action_and_field_list (:738-795): for every site I with even Ix + Iy the bonds
-    (I, x), (I, y), (I - a_x, x), (I - a_y, y).  Op_T is the single dense operator of Ham_Hop (:274-296, Checkerboard = .false.,
-    zero hopping, chemical potential on the diagonal).  The Ising action S0 (:439-512) is handed over as tables: transverse-field
-    coupling DW_Ising_tau to the two neighbouring time slices (:474-479, :841-845) and the two plaquettes of the bond
-    DW_Ising_Flux(F1, F2) = exp(2 dtau K F1) exp(2 dtau K F2) (:481-506, :846-850).  All fields are visited sequentially
-    (Overide_global_tau_sampling_parameters :1330-1343: N_Global_tau = 0 without matter fields)."""
+def z2_matter_square(L1: int, L2: int, beta: float, dtau: float = 0.1, t: float = 1.0, t_z2: float = 1.0, chem: float = 0.0, U: float = 0.0,
+                     J: float = 1.0, K: float = 1.0, h: float = 1.0, g: float = 1.0, N_SUN: int = 2, propose_s0: bool = False,
+                     projector: bool = False, theta: float = 10.0, n_part: int = -1) -> Model:
+    """Hamiltonian_Z2_Matter_smod.F90 (Z2 lattice gauge theory coupled to fermions and Z2 matter on the square lattice) as Ham_Set builds it
+    (:143-240) with the shipped defaults of Scripts_and_Parameters_files/Start/parameters:156-167.
+      * Fields (Setup_Ising_action_and_field_list :738-832): [Hubbard, one per site, if U] + [Z2 gauge bonds, if t_z2] + [matter bonds and ONE
+        site matter field at site Latt%N, if t]; bonds are enumerated per site I of even Ix + Iy as (I,x), (I,y), (I - a_x, x), (I - a_y, y).
+      * Ham_V (:313-371): Predefined_Int_Ising_SUN bond vertices (type 1, k = 2) with Xi = -t_z2 / -t; the site matter field is a k = 1 operator
+        with g = 0 (no fermionic weight); Ham_Hop (:274-296): one dense Op_T carrying only the chemical potential.
+      * Ising action as tables: ham%S0 (:439-512) of the gauge fields = coupling to the matter bond field (DW_Ising_Matter), to the two
+        neighbouring time slices (DW_Ising_tau; only the existing neighbour(s) in the projective algorithm) and the two plaquettes
+        (DW_Ising_Flux); matter fields are not visited sequentially (Overide_global_tau_sampling_parameters :1330-1343) but through
+        N_Global_tau = Latt%N/4 star moves per slice, ham%Global_move_tau (:535-643): the four matter bonds around a random site (+ the site
+        field for I = Latt%N), S0_Matter = prod DW_Ising_Matter * DW_Matter_tau(tau_I(nt) tau_I(nt +- 1)) where the site variable tau_I is the
+        product of the bond fields along the walk of Hamiltonian_set_Z2_matter (:1288-1317) -- again a product of fields, hence a table term.
+      * projector=True: Thtrot = nint(theta/dtau), Ltrot += 2 Thtrot, N_part = L1 L2 / 2, trial wave function of Ham_Trial (:380-425)."""
     latt = Lattice(L1, L2)
     if L1 == 1 or L2 == 1:
         raise HamiltonianError("Ham_Latt: One dimensional systems are not included")
+    if abs(t) < EPS_SMALL:
+        J = 0.0; h = 0.0
+    if abs(t_z2) < EPS_SMALL:
+        J = 0.0; K = 0.0; g = 0.0
     Ndim = latt.N
     Ltrot = int(round(beta / dtau))
+    Thtrot = int(round(theta / dtau)) if projector else 0
+    Ltrot += 2 * Thtrot
     op = Op_make(Ndim)
     for I in range(1, Ndim + 1):
         op.O[I - 1, I - 1] = -chem
@@ -447,58 +462,134 @@ def z2_gauge_square(L1: int, L2: int, beta: float, dtau: float = 0.1, t_z2: floa
     Op_T = [[op]]
     field_list = {}                 # (site, orientation, type) -> field index (1-based)
     field_inv = []                  # field -> (site, orientation, type)
+
+    def add(I, no, ty):
+        field_inv.append((I, no, ty)); field_list[(I, no, ty)] = len(field_inv)
     if abs(U) > EPS_SMALL:
         for I in range(1, latt.N + 1):
-            field_inv.append((I, 3, 3)); field_list[(I, 3, 3)] = len(field_inv)
-    if abs(t_z2) > EPS_SMALL:
-        for I in range(1, latt.N + 1):
-            ix, iy = latt.list[I - 1]
-            if (ix + iy) % 2 == 0:
-                for (I1, no) in ((I, 1), (I, 2), (latt.nnlist(I, -1, 0), 1), (latt.nnlist(I, 0, -1), 2)):
-                    field_inv.append((I1, no, 1)); field_list[(I1, no, 1)] = len(field_inv)
+            add(I, 3, 3)
+    for ty, amp in ((1, t_z2), (2, t)):
+        if abs(amp) > EPS_SMALL:
+            for I in range(1, latt.N + 1):
+                ix, iy = latt.list[I - 1]
+                if (ix + iy) % 2 == 0:
+                    for (I1, no) in ((I, 1), (I, 2), (latt.nnlist(I, -1, 0), 1), (latt.nnlist(I, 0, -1), 2)):
+                        add(I1, no, ty)
+    if abs(t) > EPS_SMALL:
+        add(latt.N, 3, 4)
     Op_V = []
+    I1 = 1
     for (I, no, ty) in field_inv:
         if ty == 3:                # Predefined_Int_U_SUN (Predefined_Int_mod.F90:59-77)
             o = Op_make(1); o.P[0] = I; o.O[0, 0] = 1.0; o.alpha = -0.5
             o.g = np.sqrt(complex(-dtau * U / float(N_SUN), 0.0)); o.type = 2
-        else:                      # Predefined_Int_Ising_SUN(OP, I, I1, DTAU, -Ham_TZ2) (Predefined_Int_mod.F90:264-283)
+        elif ty in (1, 2):         # Predefined_Int_Ising_SUN(OP, I, I1, DTAU, -Ham_TZ2 | -Ham_T) (Predefined_Int_mod.F90:264-283)
             I1 = latt.nnlist(I, 1, 0) if no == 1 else latt.nnlist(I, 0, 1)
             o = Op_make(2); o.P[0], o.P[1] = I, I1; o.O[0, 1] = 1.0; o.O[1, 0] = 1.0
-            o.g = complex(-dtau * (-t_z2), 0.0); o.alpha = 0.0; o.type = 1
+            o.g = complex(-dtau * (-(t_z2 if ty == 1 else t)), 0.0); o.alpha = 0.0; o.type = 1
+        else:                      # site matter field (:358-367): P(1) = I1 is whatever the previous bond left there; g = 0
+            o = Op_make(1); o.P[0] = I1; o.O[0, 0] = 1.0; o.g = 0.0; o.alpha = 0.0; o.type = 1
         Op_set(o); Op_V.append([o])
-    # ---- S0 tables
-    dw_tau = (1.0, 1.0)
-    if g > EPS_SMALL:
-        dw_tau = (1.0 / np.tanh(dtau * g), float(np.tanh(dtau * g)))          # (product -1, product +1)
+    # ---- tables (product -1, product +1)
+    dw_tau = (1.0 / np.tanh(dtau * g), float(np.tanh(dtau * g))) if g > EPS_SMALL else (1.0, 1.0)
     dw_flux = (float(np.exp(-2.0 * dtau * K)), float(np.exp(2.0 * dtau * K)))
-    FL = lambda I, no: field_list[(I, no, 1)]
-    op_start, term_start, e_op, e_dt, w = [0], [0], [], [], []
+    dw_im = (float(np.exp(-2.0 * dtau * J)), float(np.exp(2.0 * dtau * J)))
+    dw_mtau = (1.0 / np.tanh(dtau * h), float(np.tanh(dtau * h))) if h > EPS_SMALL else (1.0, 1.0)
+    FL = lambda I, no, ty=1: field_list[(I, no, ty)]
 
-    def term(entries, tab):
-        for (m, dt) in entries:
-            e_op.append(m); e_dt.append(dt)
-        term_start.append(len(e_op)); w.extend(tab)
+    class Terms:
+        def __init__(self):
+            self.owner_start, self.term_start, self.e_op, self.e_dt, self.w = [0], [0], [], [], []
+
+        def term(self, entries, tab):
+            for (m_, dt) in entries:
+                self.e_op.append(m_); self.e_dt.append(dt)
+            self.term_start.append(len(self.e_op)); self.w.extend(tab)
+
+        def close_owner(self):
+            self.owner_start.append(len(self.term_start) - 1)
+
+        def table(self, open_bc):
+            return dict(n_terms=len(self.term_start) - 1, op_start=np.array(self.owner_start, np.int32), term_start=np.array(self.term_start, np.int32),
+                        e_op=np.array(self.e_op if self.e_op else [1], np.int32), e_dt=np.array(self.e_dt if self.e_dt else [0], np.int32),
+                        w=np.array(self.w if self.w else [1.0, 1.0], np.float64), open_bc=int(open_bc))
+    s0 = Terms()
     for n, (I1, no, ty) in enumerate(field_inv, start=1):
         if ty == 1:
-            term([(n, 0), (n, 1)], dw_tau); term([(n, 0), (n, -1)], dw_tau)
+            if abs(t) > EPS_SMALL:
+                s0.term([(n, 0), (FL(I1, no, 2), 0)], dw_im)
+            s0.term([(n, 0), (n, 1)], dw_tau); s0.term([(n, 0), (n, -1)], dw_tau)
             if no == 1:
                 I2, I3 = latt.nnlist(I1, 0, 1), latt.nnlist(I1, 1, 0)
-                term([(n, 0), (FL(I1, 2), 0), (FL(I2, 1), 0), (FL(I3, 2), 0)], dw_flux)
+                s0.term([(n, 0), (FL(I1, 2), 0), (FL(I2, 1), 0), (FL(I3, 2), 0)], dw_flux)
                 I2, I3 = latt.nnlist(I1, 0, -1), latt.nnlist(I1, 1, -1)
-                term([(n, 0), (FL(I2, 1), 0), (FL(I2, 2), 0), (FL(I3, 2), 0)], dw_flux)
+                s0.term([(n, 0), (FL(I2, 1), 0), (FL(I2, 2), 0), (FL(I3, 2), 0)], dw_flux)
             else:
                 I2, I3 = latt.nnlist(I1, -1, 0), latt.nnlist(I1, -1, 1)
-                term([(n, 0), (FL(I2, 1), 0), (FL(I2, 2), 0), (FL(I3, 1), 0)], dw_flux)
+                s0.term([(n, 0), (FL(I2, 1), 0), (FL(I2, 2), 0), (FL(I3, 1), 0)], dw_flux)
                 I2, I3 = latt.nnlist(I1, 0, 1), latt.nnlist(I1, 1, 0)
-                term([(n, 0), (FL(I1, 1), 0), (FL(I2, 1), 0), (FL(I3, 2), 0)], dw_flux)
-        op_start.append(len(term_start) - 1)
-    m = Model(name="Z2_Gauge", Ndim=Ndim, N_FL=1, N_SUN=N_SUN, Ltrot=Ltrot, Dtau=dtau, Symm=False, Op_V=Op_V, Op_T=Op_T, latt=latt,
-              params=dict(L1=L1, L2=L2, beta=beta, dtau=dtau, t_z2=t_z2, g=g, K=K, chem=chem, U=U))
-    m.s0_ising = dict(n_terms=len(term_start) - 1, op_start=np.array(op_start, np.int32), term_start=np.array(term_start, np.int32),
-                      e_op=np.array(e_op, np.int32), e_dt=np.array(e_dt, np.int32), w=np.array(w, np.float64), open_bc=0)
+                s0.term([(n, 0), (FL(I1, 1), 0), (FL(I2, 1), 0), (FL(I3, 2), 0)], dw_flux)
+        s0.close_owner()
+    m = Model(name="Z2_Matter", Ndim=Ndim, N_FL=1, N_SUN=N_SUN, Ltrot=Ltrot, Dtau=dtau, Symm=False, Op_V=Op_V, Op_T=Op_T, latt=latt,
+              params=dict(L1=L1, L2=L2, beta=beta, dtau=dtau, t=t, t_z2=t_z2, g=g, K=K, J=J, h=h, chem=chem, U=U, projector=projector, theta=theta))
+    if abs(t_z2) > EPS_SMALL:
+        m.s0_ising = s0.table(projector)
     m.propose_s0 = bool(propose_s0)
     m.params["field_inv"] = field_inv
+    # ---- Overide_global_tau_sampling_parameters (:1330-1343) and the star moves
+    nt_seq_end = (latt.N if abs(U) > EPS_SMALL else 0) + (2 * latt.N if abs(t_z2) > EPS_SMALL else 0)
+    m.global_tau = dict(nt_seq_start=1, nt_seq_end=nt_seq_end, n_global_tau=(latt.N // 4 if abs(t) > EPS_SMALL else 0))
+    if abs(t) > EPS_SMALL:
+        # tau_I as a set of fields: the walk of Hamiltonian_set_Z2_matter (:1303-1315), later assignments overwrite earlier ones
+        site_f = FL(latt.N, 3, 4)
+        sets = {latt.N: frozenset([site_f])}
+        I = latt.N
+        for _nx in range(L1):
+            for _ny in range(L2):
+                I1 = latt.nnlist(I, 0, 1); sets[I1] = sets[I] ^ frozenset([FL(I, 2, 2)]); I = I1
+            I1 = latt.nnlist(I, 1, 0); sets[I1] = sets[I] ^ frozenset([FL(I, 1, 2)]); I = I1
+        assert len(sets) == latt.N
+        gm = Terms(); move_start, move_fields = [0], []
+        for I in range(1, latt.N + 1):
+            bonds = [(I, 1), (I, 2), (latt.nnlist(I, -1, 0), 1), (latt.nnlist(I, 0, -1), 2)]
+            fl = [FL(b[0], b[1], 2) for b in bonds]
+            if abs(t_z2) > EPS_SMALL:
+                for b, n_op in zip(bonds, fl):
+                    gm.term([(n_op, 0), (FL(b[0], b[1], 1), 0)], dw_im)
+            path = sorted(sets[I])
+            gm.term([(f_, 0) for f_ in path] + [(f_, 1) for f_ in path], dw_mtau)       # tau_I(nt) tau_I(nt + 1)
+            gm.term([(f_, 0) for f_ in path] + [(f_, -1) for f_ in path], dw_mtau)      # tau_I(nt) tau_I(nt - 1)
+            gm.close_owner()
+            if I == latt.N:
+                fl = fl + [site_f]
+            move_fields.extend(sorted(fl)); move_start.append(len(move_fields))          # Wrapgr_sort: ascending field index
+        tb = gm.table(projector)
+        tb.update(n_sites=latt.N, move_start=np.array(move_start, np.int32), move_fields=np.array(move_fields, np.int32))
+        m.global_move_tau_ising = tb
+        m.params["tau_sets"] = sets
+    if projector:
+        npart = (L1 * L2) // 2 if n_part < 0 else n_part
+        H0 = np.zeros((Ndim, Ndim)); Delta = 0.01
+        for I in range(1, latt.N + 1):
+            ix, iy = latt.list[I - 1]
+            Ix = latt.nnlist(I, 1, 0)
+            H0[I - 1, Ix - 1] = H0[Ix - 1, I - 1] = -(1.0 + Delta * np.cos(np.pi * float(ix + iy)))
+            if L2 > 1:
+                Iy = latt.nnlist(I, 0, 1)
+                H0[I - 1, Iy - 1] = H0[Iy - 1, I - 1] = -(1.0 - Delta)
+        E0, U0 = np.linalg.eigh(H0)
+        P = np.asfortranarray(U0[:, :npart].astype(np.complex128))
+        m.Projector, m.Thtrot = True, Thtrot
+        m.WF_L, m.WF_R = [P.copy()], [P.copy()]
+        m.params["wf_degen"] = float(E0[npart] - E0[npart - 1])
     return m
+
+
+def z2_gauge_square(L1: int, L2: int, beta: float, dtau: float = 0.1, t_z2: float = 1.0, g: float = 1.0, K: float = 1.0, chem: float = 0.0,
+                    U: float = 0.0, N_SUN: int = 2, propose_s0: bool = False) -> Model:
+    """The Z2-gauge sector of Hamiltonian_Z2_Matter (Ham_T = 0, hence Ham_J = Ham_h = 0, :163-166): only the Ising bond fields the fermions
+    hop through (+ optional Hubbard vertices); all fields are visited sequentially, N_Global_tau = 0."""
+    return z2_matter_square(L1, L2, beta, dtau, t=0.0, t_z2=t_z2, chem=chem, U=U, J=0.0, K=K, h=0.0, g=g, N_SUN=N_SUN, propose_s0=propose_s0)
 
 
 def flatten_ops(model: Model):

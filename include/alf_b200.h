@@ -66,6 +66,20 @@ int alf_b200_set_trial_wf(alf_b200_handle* h, int nf, const double* P_L, const d
  * Must be called before alf_b200_finalize_model.  With tables or Propose_S0 the slice is visited by the per-visit kernel. */
 int alf_b200_set_s0_ising(alf_b200_handle* h, int n_terms, const int* op_start /* n_opv+1 */, const int* term_start /* n_terms+1 */,
                           const int* entry_op, const int* entry_dt, const double* w /* 2*n_terms */, int open_boundaries, int propose_s0);
+/* Nt_sequential_start, Nt_sequential_end, N_Global_tau of Prog/main.F90 (ham%Overide_global_tau_sampling_parameters): WRAPGRUP / WRAPGRDO visit
+ * the fields nt_sequential_start .. nt_sequential_end one by one and then (before, on the way down) make n_global_tau global-in-slice moves
+ * (Prog/Wrapgr_mod.F90:112-153, 189-194).  Defaults: 1, size(Op_V,1), 0.  Before alf_b200_finalize_model. */
+int alf_b200_set_global_tau_sampling(alf_b200_handle* h, int nt_sequential_start, int nt_sequential_end, int n_global_tau);
+/* The plugin callback ham%Global_move_tau for Ising "star" moves as tables (Prog/Hamiltonians/Hamiltonian_Z2_Matter_smod.F90:535-643), so that
+ * the batched sweep needs no host in the loop: per move a site I = nranf(n_sites) is drawn from the chain's stream; Flip_list =
+ * move_fields[move_start[I-1] .. move_start[I]-1] (1-based field indices, ascending = after Wrapgr_sort, at most 16, Ising fields only),
+ * Flip_value = the flipped fields; S0_ratio = product of the site's coupling terms (site_term_start / term_start / entry_op / entry_dt / w
+ * exactly as in alf_b200_set_s0_ising); T0_Proposal = 1 - 1/(1 + S0_ratio) is tested against one ranf() and T0_Proposal_ratio =
+ * 1/S0_ratio or 0 (:633-641).  Wrapgr_Random_update then proceeds on the device as in alf_b200_wrapgr_random_update.
+ * Before alf_b200_finalize_model. */
+int alf_b200_set_global_move_tau_ising(alf_b200_handle* h, int n_sites, const int* move_start /* n_sites+1 */, const int* move_fields, int n_terms,
+                                       const int* site_term_start /* n_sites+1 */, const int* term_start /* n_terms+1 */, const int* entry_op,
+                                       const int* entry_dt, const double* w /* 2*n_terms */, int open_boundaries);
 int alf_b200_finalize_model(alf_b200_handle* h);
 int alf_b200_is_complex(const alf_b200_handle* h);   /* 1 if the complex instantiation was selected */
 

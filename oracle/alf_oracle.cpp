@@ -760,26 +760,55 @@ struct Oracle {
   // term t of field n carries the list of (field m, time offset dt) whose current product indexes its table w[t][prod = -1 | +1].
   // Time offsets wrap periodically (finite temperature, :474-479) or, with open boundaries, terms leaving 1..Ltrot are dropped (projector, :465-472).
   struct S0Tab { bool on = false, open_bc = false; std::vector<int> op_start, term_start, e_op, e_dt; std::vector<double> w; } s0tab;
-  double S0(int n, int nt, cd) {
-    if (!s0tab.on) return 1.0;
+  double ising_terms(const S0Tab& tb, int owner, int nt) {
     double S = 1.0;
-    for (int t = s0tab.op_start[n]; t < s0tab.op_start[n + 1]; ++t) {
+    for (int t = tb.op_start[owner]; t < tb.op_start[owner + 1]; ++t) {
       int prod = 1; bool skip = false;
-      for (int e = s0tab.term_start[t]; e < s0tab.term_start[t + 1]; ++e) {
-        int nt1 = nt + s0tab.e_dt[e];
-        if (nt1 > ltrot || nt1 < 1) { if (s0tab.open_bc) { skip = true; break; } nt1 = (nt1 > ltrot) ? nt1 - ltrot : nt1 + ltrot; }
-        prod *= (fld(s0tab.e_op[e], nt1).real() < 0.0) ? -1 : 1;
+      for (int e = tb.term_start[t]; e < tb.term_start[t + 1]; ++e) {
+        int nt1 = nt + tb.e_dt[e];
+        if (nt1 > ltrot || nt1 < 1) { if (tb.open_bc) { skip = true; break; } nt1 = (nt1 > ltrot) ? nt1 - ltrot : nt1 + ltrot; }
+        prod *= (fld(tb.e_op[e], nt1).real() < 0.0) ? -1 : 1;
       }
-      if (!skip) S *= s0tab.w[2 * t + (prod > 0 ? 1 : 0)];
+      if (!skip) S *= tb.w[2 * t + (prod > 0 ? 1 : 0)];
     }
     return S;
+  }
+  double S0(int n, int nt, cd) { return s0tab.on ? ising_terms(s0tab, n, nt) : 1.0; }
+
+  // ham%Global_move_tau for Ising star moves as tables (Hamiltonian_Z2_Matter_smod.F90:535-643): a site I = nranf(n_sites) is drawn, the
+  // fields move_fields[move_start[I] ..) are flipped (Flip_value = nsigma%flip), S0_Matter is the product of the site's coupling terms
+  // (same table form as S0), T0_Proposal = 1 - 1/(1 + S0_Matter) is tested against one ranf() and T0_Proposal_ratio = 1/S0_Matter or 0.
+  // Overide_global_tau_sampling_parameters (:1330-1343): sequential visits Nt_sequential_start..end, then N_Global_tau such moves.
+  struct GmtTab { bool on = false; int n_sites = 0; std::vector<int> move_start, move_fields; S0Tab terms; } gmt;
+  int nt_seq_start = 1, nt_seq_end = -1, n_global_tau = 0;      // nt_seq_end < 0: all fields
+  std::vector<uint8_t> gm_log;                                  // per global move: 1 accepted, 0 rejected, 2 not proposed
+  int seq_end() const { return nt_seq_end < 0 ? n_opv : nt_seq_end; }
+  void global_move_tau(double& T0_Proposal_ratio, double& S0_ratio, std::vector<int>& Flip_list, std::vector<cd>& Flip_value, int ntau) {
+    const int I = rng.nranf(gmt.n_sites) - 1;
+    Flip_list.clear(); Flip_value.clear();
+    for (int e = gmt.move_start[I]; e < gmt.move_start[I + 1]; ++e) { const int n_op = gmt.move_fields[e]; Flip_list.push_back(n_op + 1);
+      Flip_value.push_back(ft.flip(OpV(n_op, 0).type, OpV(n_op, 0).flip_protocol, fld(n_op, ntau), rng)); }
+    const double S0_Matter = ising_terms(gmt.terms, I, ntau);
+    const double T0_Proposal = 1.0 - 1.0 / (1.0 + S0_Matter);
+    T0_Proposal_ratio = (T0_Proposal > rng.ranf()) ? 1.0 / S0_Matter : 0.0;
+    S0_ratio = S0_Matter;
+  }
+  void wrapgr_random_update(int& m, int ntau) {     // Prog/Wrapgr_mod.F90:317-433
+    for (int ng_c = 0; ng_c < n_global_tau; ++ng_c) {
+      double T0, S0r; std::vector<int> fl; std::vector<cd> fv;
+      global_move_tau(T0, S0r, fl, fv, ntau);
+      const size_t nlog = acc_log.size(), nrat = ratio_log.size();
+      const bool acc = wrapgr_random_update_one(m, ntau, T0, S0r, fl, fv);
+      acc_log.resize(nlog); ratio_log.resize(nrat);                 // the accept log records the sequential visits only
+      gm_log.push_back(T0 > 10e-8 ? (acc ? 1 : 0) : 2);
+    }
   }
 
   // ---- Prog/Wrapgr_mod.F90:81-157
   void wrapgrup(int NTAU) {
     int NTAU1 = NTAU + 1;
     for (int nf = 0; nf < n_fl; ++nf) { mmthr(GR[nf].data(), ndim, ndim, nf); mmthl_m1(GR[nf].data(), ndim, ndim, nf); }
-    for (int n = 0; n < n_opv; ++n) {
+    for (int n = nt_seq_start - 1; n < seq_end(); ++n) {
       cd HS_Field = fld(n, NTAU1);
       for (int nf = 0; nf < n_fl; ++nf) op_wrapup(GR[nf].data(), OpV(n, nf), HS_Field, 1);
       double T0_proposal = 1.5, T0_Proposal_ratio = 1.0;
@@ -790,10 +819,13 @@ struct Oracle {
       else { ctl.NC_eff_up++; if (log_on) acc_log.push_back(2); }
       for (int nf = 0; nf < n_fl; ++nf) op_wrapup(GR[nf].data(), OpV(n, nf), HS_Field, 2);
     }
+    if (n_global_tau > 0) { int m = seq_end(); wrapgr_random_update(m, NTAU1); wrapgr_placegr(m, n_opv, NTAU1); }      // :148-153
+    else if (seq_end() < n_opv || nt_seq_start > 1) throw std::runtime_error("Nt_sequential range without N_Global_tau");
   }
   // ---- Prog/Wrapgr_mod.F90:160-243
   void wrapgrdo(int NTAU) {
-    for (int n = n_opv - 1; n >= 0; --n) {
+    if (n_global_tau > 0) { int m = n_opv; wrapgr_random_update(m, NTAU); wrapgr_placegr(m, seq_end(), NTAU); }        // :189-194
+    for (int n = seq_end() - 1; n >= nt_seq_start - 1; --n) {
       cd HS_Field = fld(n, NTAU);
       for (int nf = 0; nf < n_fl; ++nf) op_wrapdo(GR[nf].data(), OpV(n, nf), HS_Field, 2);
       double T0_proposal = 1.5, T0_Proposal_ratio = 1.0;
@@ -1106,6 +1138,22 @@ void orc_set_projector(void* h, int thtrot, int n_part) {
   Oracle* o = (Oracle*)h; o->projector = true; o->thtrot = thtrot; o->n_part = n_part;
   o->WF_L.assign(o->n_fl, std::vector<cd>((size_t)o->ndim * n_part)); o->WF_R = o->WF_L;
 }
+static void load_terms(Oracle* o, Oracle::S0Tab& t, int n_owner, int n_terms, const int* op_start, const int* term_start, const int* e_op, const int* e_dt, const double* w, int open_bc) {
+  t.on = true; t.open_bc = open_bc != 0; t.op_start.assign(op_start, op_start + n_owner + 1); t.term_start.assign(term_start, term_start + n_terms + 1);
+  const int ne = term_start[n_terms]; t.e_op.resize(ne); t.e_dt.assign(e_dt, e_dt + ne); for (int i = 0; i < ne; ++i) t.e_op[i] = e_op[i] - 1;
+  t.w.assign(w, w + 2 * (size_t)n_terms);
+}
+void orc_set_global_tau_sampling(void* h, int nt_seq_start, int nt_seq_end, int n_global_tau) {
+  Oracle* o = (Oracle*)h; o->nt_seq_start = nt_seq_start; o->nt_seq_end = nt_seq_end; o->n_global_tau = n_global_tau;
+}
+void orc_set_global_move_tau_ising(void* h, int n_sites, const int* move_start, const int* move_fields, int n_terms, const int* site_term_start,
+                                   const int* term_start, const int* e_op, const int* e_dt, const double* w, int open_bc) {
+  Oracle* o = (Oracle*)h; o->gmt.on = true; o->gmt.n_sites = n_sites; o->gmt.move_start.assign(move_start, move_start + n_sites + 1);
+  o->gmt.move_fields.resize(move_start[n_sites]); for (int i = 0; i < move_start[n_sites]; ++i) o->gmt.move_fields[i] = move_fields[i] - 1;
+  load_terms(o, o->gmt.terms, n_sites, n_terms, site_term_start, term_start, e_op, e_dt, w, open_bc);
+}
+long orc_get_gm_log(void* h, uint8_t* out, long cap) { Oracle* o = (Oracle*)h; long n = (long)o->gm_log.size(); for (long i = 0; i < n && i < cap; ++i) out[i] = o->gm_log[i]; return n; }
+double orc_global_move_s0(void* h, int site, int nt) { Oracle* o = (Oracle*)h; return o->ising_terms(o->gmt.terms, site - 1, nt); }
 double orc_s0(void* h, int n, int nt) { return ((Oracle*)h)->S0(n - 1, nt, cd(0, 0)); }   // ham%S0(n, nt, .) on the current configuration
 void orc_set_propose_s0(void* h, int on) { ((Oracle*)h)->propose_s0 = on != 0; }
 // table-driven Ising action: op_start[n_opv + 1] -> terms of field n; term_start[n_terms + 1] -> entries; entry = (field, 1-based; dt); w = [n_terms][2]

@@ -33,6 +33,8 @@ def lib():
         _lib.orc_create.restype = C.c_void_p
         _lib.orc_ranf.restype = C.c_double
         _lib.orc_s0.restype = C.c_double
+        _lib.orc_global_move_s0.restype = C.c_double
+        _lib.orc_get_gm_log.restype = C.c_long
         _lib.orc_get_log.restype = C.c_long
         _lib.orc_taum_get.restype = C.c_long
         _lib.orc_taum_fresh_get.restype = C.c_long
@@ -86,11 +88,32 @@ class Oracle:
             elif getattr(model, "propose_s0", False):
                 L.orc_set_propose_s0(self.h, 1)
 
+        gt = getattr(model, "global_tau", None)
+        if gt is not None and (gt["n_global_tau"] > 0 or gt["nt_seq_end"] != model.n_opv):
+            L.orc_set_global_tau_sampling(self.h, int(gt["nt_seq_start"]), int(gt["nt_seq_end"]), int(gt["n_global_tau"]))
+        gm = getattr(model, "global_move_tau_ising", None)
+        if gm is not None:
+            a = {k: np.ascontiguousarray(gm[k], dtype=np.int32) for k in ("move_start", "move_fields", "op_start", "term_start", "e_op", "e_dt")}
+            w = np.ascontiguousarray(gm["w"], dtype=np.float64)
+            L.orc_set_global_move_tau_ising(self.h, int(gm["n_sites"]), a["move_start"].ctypes.data_as(_ip), a["move_fields"].ctypes.data_as(_ip), int(gm["n_terms"]),
+                                            a["op_start"].ctypes.data_as(_ip), a["term_start"].ctypes.data_as(_ip), a["e_op"].ctypes.data_as(_ip),
+                                            a["e_dt"].ctypes.data_as(_ip), _d(w), int(gm["open_bc"]))
+
     def __del__(self):
         try:
             lib().orc_destroy(self.h)
         except Exception:
             pass
+
+    def global_move_s0(self, site: int, nt: int) -> float:
+        """S0_Matter of ham%Global_move_tau for the star move at `site` on slice nt, current configuration (1-based)."""
+        return lib().orc_global_move_s0(self.h, int(site), int(nt))
+
+    def get_gm_log(self):
+        n = lib().orc_get_gm_log(self.h, None, 0)
+        out = np.zeros(max(n, 1), dtype=np.uint8)
+        lib().orc_get_gm_log(self.h, out.ctypes.data_as(C.POINTER(C.c_uint8)), n)
+        return out[:n]
 
     def s0(self, n: int, nt: int) -> float:
         """ham%S0(n, nt, flipped value) on the current configuration (1-based n, nt)."""

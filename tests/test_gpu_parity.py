@@ -8,7 +8,7 @@ import pytest
 
 from alf_b200 import api
 from alf_b200.api import AlfB200
-from alf_b200.model import hubbard_square, hubbard_chain, kondo_square, z2_gauge_square
+from alf_b200.model import hubbard_square, hubbard_chain, kondo_square, z2_gauge_square, z2_matter_square
 import oracle.oracle as O
 from oracle.oracle import Oracle
 from common import relF, SEEDS, TOL_G, config1, config2, config3
@@ -840,6 +840,34 @@ def test_ising_action_s0_tables_sweep_parity(variant):
         if variant == "gauge_propose_s0":
             assert (acc == 2).any() and (acc == 1).any()               # some visits are not proposed at all
         assert np.array_equal(f[c], o.get_fields())
+        assert relF(g.green(c, 1), o.green(1)) < TOL_G
+        assert abs(ph[c] - o.phase()) < 1e-9
+    g.close()
+
+
+@pytest.mark.parametrize("variant", ["finite_T", "projector", "matter_only", "with_hubbard"])
+def test_z2_matter_batched_sweep_parity(variant):
+    """BASELINE config 5 at test size: Hamiltonian_Z2_Matter (gauge + matter Ising bond vertices, Ising action, N_Global_tau = N/4 star moves per
+    slice through ham%Global_move_tau, restricted sequential range) swept entirely on the device -- S0 and Global_move_tau from tables, no host
+    in the loop -- reproduces the oracle: identical fields and random-number state after two sweeps (hence identical proposals, draws and
+    decisions of every sequential visit and every global move), G and phase within tolerance.  Finite temperature and projective algorithm."""
+    kw = dict(g=0.8, K=0.5, J=0.7, h=0.9)
+    if variant == "projector":
+        kw.update(projector=True, theta=0.5)
+    if variant == "matter_only":
+        kw.update(t_z2=0.0)
+    if variant == "with_hubbard":
+        kw.update(U=2.0)
+    m = z2_matter_square(4, 4, beta=0.5 if variant == "projector" else 1.0, dtau=0.1, **kw)
+    assert m.global_tau["n_global_tau"] == 4
+    seeds = SEEDS[:3]
+    g = AlfB200(m, n_chains=len(seeds), nwrap=5); g.set_seeds(seeds); g.fields_set(); g.init_sweep(); g.sweep(2, 0)
+    f = g.get_fields(); ph = g.phase(); rs = g.rng_state(); ctr = g.counters() if hasattr(g, "counters") else None
+    for c, s in enumerate(seeds):
+        o = Oracle(m, nwrap=5); o.ranset(s); o.fields_set(); o.init(); o.log(True); o.sweep(0); o.sweep(0)
+        gm = o.get_gm_log(); assert (gm == 1).any() and (gm == 2).any(), np.bincount(gm)
+        assert np.array_equal(f[c], o.get_fields()), variant
+        assert np.array_equal(rs[c], o.rng_state()), variant
         assert relF(g.green(c, 1), o.green(1)) < TOL_G
         assert abs(ph[c] - o.phase()) < 1e-9
     g.close()

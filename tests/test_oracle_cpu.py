@@ -341,3 +341,49 @@ def test_s0_tables_of_z2_gauge_model_match_the_ising_action():
         n, nt = int(rng.integers(0, M)), int(rng.integers(0, L))
         c = f.copy(); c[nt, n] = -c[nt, n]
         assert abs(np.exp(log_weight(c) - w0) / o.s0(n + 1, nt + 1) - 1) < 1e-12, (n, nt)
+
+
+@pytest.mark.parametrize("projector", [False, True])
+def test_z2_matter_tables_match_the_ising_action(projector):
+    """Full Hamiltonian_Z2_Matter action by brute force (gauge: time + flux + coupling to matter bonds; matter: tau_I(nt) tau_I(nt+1) with the site
+    variables of Hamiltonian_set_Z2_matter, :1288-1317, rebuilt here by walking the lattice): the Boltzmann-weight ratio of a single gauge flip
+    equals the table-driven S0(n, nt) (:439-512) and that of a star move equals S0_Matter of Global_move_tau (:535-643), with periodic
+    (finite temperature) and open (projective) boundaries in imaginary time."""
+    from alf_b200.model import z2_matter_square
+    dtau, g, K, J, h = 0.1, 0.7, 0.4, 0.6, 0.9
+    m = z2_matter_square(4, 4, beta=0.4, dtau=dtau, g=g, K=K, J=J, h=h, projector=projector, theta=0.2)
+    o = Oracle(m, nwrap=3); o.ranset(91); o.fields_set()
+    f = o.get_fields().real.copy(); L, M = f.shape; latt = m.latt; inv = m.params["field_inv"]
+    FL = {(I, no, ty): n for n, (I, no, ty) in enumerate(inv)}
+    assert M == 4 * latt.N + 1 and m.global_tau == dict(nt_seq_start=1, nt_seq_end=2 * latt.N, n_global_tau=latt.N // 4)
+    gg, gh = -0.5 * np.log(np.tanh(dtau * g)), -0.5 * np.log(np.tanh(dtau * h))
+
+    def tau(c):                                                         # Hamiltonian_set_Z2_matter on every slice
+        t = np.zeros((L, latt.N + 1)); t[:, latt.N] = c[:, FL[(latt.N, 3, 4)]]; I = latt.N
+        for _ in range(latt.L1):
+            for _ in range(latt.L2):
+                I1 = latt.nnlist(I, 0, 1); t[:, I1] = t[:, I] * c[:, FL[(I, 2, 2)]]; I = I1
+            I1 = latt.nnlist(I, 1, 0); t[:, I1] = t[:, I] * c[:, FL[(I, 1, 2)]]; I = I1
+        return t[:, 1:]
+
+    def log_weight(c):
+        pairs = (lambda a: a[:-1] * a[1:]) if projector else (lambda a: a * np.roll(a, -1, axis=0))
+        gauge = c[:, [FL[(I, no, 1)] for I in range(1, latt.N + 1) for no in (1, 2)]]
+        s = gg * np.sum(pairs(gauge)) + gh * np.sum(pairs(tau(c)))
+        for I in range(1, latt.N + 1):
+            Ix, Iy = latt.nnlist(I, 1, 0), latt.nnlist(I, 0, 1)
+            s += -dtau * K * np.sum(c[:, FL[(I, 1, 1)]] * c[:, FL[(I, 2, 1)]] * c[:, FL[(Iy, 1, 1)]] * c[:, FL[(Ix, 2, 1)]])
+            for no in (1, 2):
+                s += -dtau * J * np.sum(c[:, FL[(I, no, 1)]] * c[:, FL[(I, no, 2)]])
+        return s
+    rng = np.random.default_rng(1); w0 = log_weight(f)
+    for nt in list(rng.integers(0, L, size=12)) + [0, L - 1]:
+        n = int(rng.integers(0, 2 * latt.N))                             # a gauge field
+        c = f.copy(); c[nt, n] = -c[nt, n]
+        assert abs(np.exp(log_weight(c) - w0) / o.s0(n + 1, nt + 1) - 1) < 1e-11, (n, nt)
+        I = int(rng.integers(1, latt.N + 1)) if nt not in (0, L - 1) else latt.N
+        star = [FL[(I, 1, 2)], FL[(I, 2, 2)], FL[(latt.nnlist(I, -1, 0), 1, 2)], FL[(latt.nnlist(I, 0, -1), 2, 2)]] + ([FL[(latt.N, 3, 4)]] if I == latt.N else [])
+        c = f.copy(); c[nt, star] = -c[nt, star]
+        assert abs(np.exp(log_weight(c) - w0) / o.global_move_s0(I, nt + 1) - 1) < 1e-11, (I, nt)
+        gm = m.global_move_tau_ising
+        assert sorted(x + 1 for x in star) == list(gm["move_fields"][gm["move_start"][I - 1]:gm["move_start"][I]])
