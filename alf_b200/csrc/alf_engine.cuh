@@ -280,7 +280,7 @@ struct Engine : EngineBase {
   UdvDev<T> udvl, udvr; std::vector<UdvDev<T>> udvst;
   LaWork<T> w;
   cplx* d_z = nullptr; double* d_angle = nullptr; double* d_angle_tab = nullptr; double* d_cmp = nullptr;
-  VopDev<T>* d_vops = nullptr; ModelDev md; FieldTabDev ft;
+  VopDev<T>* d_vops = nullptr; T* d_place_tab = nullptr; int* d_place_pk = nullptr; ModelDev md; FieldTabDev ft;
   std::vector<void*> owned;     // device allocations of the op lists
   bool dense_t = false; T* d_dense[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // fwd, inv, c, half, halfinv (N*N*F each)
   int KD = 16; size_t upd_smem = 0; int ops_lk = 0; size_t ops_smem = 0;   // ops_lk = log2 of the largest small-operator dimension
@@ -293,6 +293,7 @@ struct Engine : EngineBase {
   std::vector<VGroup> groups;
   S0TabDev s0dev = {0, 0, nullptr, nullptr, nullptr, nullptr, nullptr};
   GmtDev gmtdev = {0, 0, nullptr, nullptr, {0, 0, nullptr, nullptr, nullptr, nullptr, nullptr}};
+  int stage_g = 0;                 // k_wrapgr keeps G in shared memory
   int seq_lo = 0, seq_hi = 0;      // sequential visits: fields seq_lo .. seq_hi - 1 (0-based)
   // tau_m work
   T *GT0 = nullptr, *G0T = nullptr, *G00 = nullptr, *GTT = nullptr, *TMPG = nullptr; UdvDev<T> udvr2;
@@ -344,7 +345,11 @@ struct Engine : EngineBase {
     d_z = dalloc<cplx>(NM); d_angle = dalloc<double>(NM); d_cmp = dalloc<double>((size_t)NM * 3 * CMP_SPLIT);
     // update kernel configuration: as many delayed columns as fit in ~200 KB of shared memory
     size_t per_kd = (size_t)F * 2 * (N + 2) * sizeof(T), fixed = (size_t)F * 3 * N * sizeof(T) + 256;
-    KD = (int)((200 * 1024 - fixed) / per_kd); if (KD > 32) KD = 32; if (KD < 4) throw CudaError("Ndim too large for the update kernel's shared-memory factors");
+    {   // small lattices: G itself in shared memory next to at least 8 delayed columns (per-visit kernel only)
+      const size_t gsz = sizeof(T) * (size_t)F * (N | 1) * N;
+      if (fixed + gsz + 8 * per_kd <= 224 * 1024 && !getenv("ALF_B200_NO_STAGE_G")) { stage_g = 1; fixed += gsz; }
+    }
+    KD = (int)(((stage_g ? 224 : 200) * 1024 - fixed) / per_kd); if (KD > 32) KD = 32; if (KD < 4) throw CudaError("Ndim too large for the update kernel's shared-memory factors");
     KD = (KD / 4) * 4;
     upd_smem = per_kd * KD + fixed;
     CK(alf_raise_smem(k_wrapgr<T, 1>));
@@ -534,6 +539,25 @@ struct Engine : EngineBase {
       md.lists[L_VL_N][f] = upload_list(vn); md.lists[L_VL_C][f] = upload_list(vc); md.lists[L_VR_INV][f] = upload_list(vri);
     }
     d_vops = dupload(vops); d_angle_tab = dupload(angle_tab);
+    {   // e^{+V_n(s)} and e^{-V_n(s)} per vertex and field value for Wrapgr_PlaceGR (gm_place_step)
+      std::vector<T> pt((size_t)M * F * ALF_NVAR * 2 * ALF_KMAX * ALF_KMAX, zero_<T>());
+      for (int f = 0; f < F; ++f) for (int n = 0; n < M; ++n) {
+        const HostOp& op = h->opv[n + (size_t)M * f]; const int k = op.N;
+        for (int var = 0; var < ALF_NVAR; ++var) {
+          const int sv = var - 2; const bool valid = (sv != 0) && (std::abs(sv) <= op.type);
+          const double ph = valid ? phi_st(op.type, sv) : 0.0;
+          std::vector<cd> Ep, Em; host_op_exp(op.g * ph, op, Ep); host_op_exp(-op.g * ph, op, Em);
+          T* dst = pt.data() + (((size_t)n * F + f) * ALF_NVAR + var) * 2 * ALF_KMAX * ALF_KMAX;
+          for (int a = 0; a < k; ++a) for (int b2 = 0; b2 < k; ++b2) { dst[a + b2 * ALF_KMAX] = to_T<T>(Ep[a + (size_t)b2 * k]); dst[ALF_KMAX * ALF_KMAX + a + b2 * ALF_KMAX] = to_T<T>(Em[a + (size_t)b2 * k]); }
+        }
+      }
+      d_place_tab = dupload(pt);
+      std::vector<int> pk((size_t)M * F * 8, 0);
+      for (int f = 0; f < F; ++f) for (int n = 0; n < M; ++n) { const HostOp& op = h->opv[n + (size_t)M * f];
+        for (int a = 0; a < op.N && a < ALF_KMAX; ++a) pk[((size_t)n * F + f) * 8 + a] = op.P[a];
+        pk[((size_t)n * F + f) * 8 + 4] = op.N; }
+      d_place_pk = dupload(pk);
+    }
     for (int t = 0; t < 3; ++t) for (int var = 0; var < ALF_NVAR; ++var) ft.gama[t][var] = gama_st(t, var - 2);
     const int fl[5][4] = {{0, -1, 1, 2}, {0, 1, 2, -2}, {0, 0, 0, 0}, {0, 2, -2, -1}, {0, -2, -1, 1}};   // Fields_mod.F90:289-301
     for (int a = 0; a < 5; ++a) for (int b = 0; b < 4; ++b) ft.flip[a][b] = fl[a][b];
@@ -634,10 +658,10 @@ struct Engine : EngineBase {
   // Wrapgr_Random_update with ham%Global_move_tau evaluated on the device from the tables, then Wrapgr_PlaceGR(GR, m, place_to, ntau)
   void gm_device_moves(int ntau, int place_to) {
     gm_alloc();
-    const size_t smem = sizeof(T) * ((size_t)3 * N + 2 * ALF_KMAX * ALF_KMAX) + 64;
+    const size_t smem = gm_smem();
     CK(alf_raise_smem(k_random_update<T>));
     KL(KC_UPDATE, st, k_random_update<T><<<C, 512, smem, st>>>(G, G2, N, F, h->n_sun, M, d_vops, ft, h->d_fields, L, ntau, h->d_rng, h->d_phase, h->d_counters, d_mpos,
-                                                               h->n_global_tau, 1, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, place_to, gmtdev));
+                                                               h->n_global_tau, 1, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, place_to, gmtdev, gm_stage, d_place_tab, d_place_pk, gm_stage_f));
   }
   void rotate_group(const VGroup& g, bool in) {     // G <- U^H G U (in) / U G U^H (out) for all vertices of a pair group
     ModelDev m2 = md;
@@ -652,8 +676,8 @@ struct Engine : EngineBase {
       const VGroup& g = groups[up ? gi : (int)groups.size() - 1 - gi];
       if (g.n0 < seq_lo || g.n0 >= seq_hi) continue;                  // not visited sequentially (Nt_sequential_start .. Nt_sequential_end)
       if (g.kind == 0) {
-        if (up) KL(KC_UPDATE, st, k_wrapgr<T, 1><<<C, 512, upd_smem, st>>>(G, N, F, h->n_sun, g.n0, g.cnt, M, off, d_vops, ft, h->d_fields, L, nt, h->d_rng, h->d_phase, h->d_counters, KD, lg, h->propose_s0, s0dev));
-        else KL(KC_UPDATE, st, k_wrapgr<T, 0><<<C, 512, upd_smem, st>>>(G, N, F, h->n_sun, g.n0, g.cnt, M, off, d_vops, ft, h->d_fields, L, nt, h->d_rng, h->d_phase, h->d_counters, KD, lg, h->propose_s0, s0dev));
+        if (up) KL(KC_UPDATE, st, k_wrapgr<T, 1><<<C, 512, upd_smem, st>>>(G, N, F, h->n_sun, g.n0, g.cnt, M, off, d_vops, ft, h->d_fields, L, nt, h->d_rng, h->d_phase, h->d_counters, KD, lg, h->propose_s0, s0dev, stage_g));
+        else KL(KC_UPDATE, st, k_wrapgr<T, 0><<<C, 512, upd_smem, st>>>(G, N, F, h->n_sun, g.n0, g.cnt, M, off, d_vops, ft, h->d_fields, L, nt, h->d_rng, h->d_phase, h->d_counters, KD, lg, h->propose_s0, s0dev, stage_g));
       } else {
         if (g.kind == 2) rotate_group(g, true);
 #define FAST_LAUNCH(UPV, IPT, PR) KL(KC_UPDATE, st, k_wrapgr_fast<T, UPV, IPT, PR><<<C, 512, fast_smem, st>>>(G, N, F, h->n_sun, g.n0, g.cnt, M, off, d_vops, ft, h->d_fields, L, nt, h->d_rng, h->d_phase, h->d_counters, KDf, ldxf, lg))
@@ -869,6 +893,15 @@ struct Engine : EngineBase {
 
   // ---------------------------------------------------------------- global-in-slice moves (Prog/Wrapgr_mod.F90:247-433)
   int* d_mpos = nullptr;
+  // shared memory of k_random_update; G is staged there when it fits (gm_stage)
+  int gm_stage = 0, gm_stage_f = 0;
+  size_t gm_smem() {
+    const size_t base = sizeof(T) * ((size_t)3 * N + 2 * ALF_KMAX * ALF_KMAX) + 64, staged = base + sizeof(T) * (size_t)F * (N | 1) * N;
+    gm_stage = (staged <= 220 * 1024 && !getenv("ALF_B200_NO_STAGE_G")) ? 1 : 0;
+    size_t sz = gm_stage ? staged : base;
+    gm_stage_f = (sz + (size_t)M + 16 <= 224 * 1024) ? 1 : 0;
+    return sz + (gm_stage_f ? (size_t)M + 16 : 0);
+  }
   void gm_alloc() { if (!d_mpos) { d_mpos = dalloc<int>(C); CK(cudaMemsetAsync(d_mpos, 0, sizeof(int) * C, st)); } }
   void gm_set_position(int m) override { gm_alloc(); KL(KC_EW, st, k_fill_int<<<ew_blocks(C), 256, 0, st>>>(d_mpos, C, m)); }
   void gm_get_position(int* m) override { gm_alloc(); sync(); CK(cudaMemcpy(m, d_mpos, sizeof(int) * C, cudaMemcpyDeviceToHost)); }
@@ -886,10 +919,10 @@ struct Engine : EngineBase {
       CK(cudaMemcpyAsync(d_val, val, nl, cudaMemcpyHostToDevice, st)); CK(cudaMemcpyAsync(d_t0, t0, sizeof(double) * np, cudaMemcpyHostToDevice, st));
       CK(cudaMemcpyAsync(d_s0, s0, sizeof(double) * np, cudaMemcpyHostToDevice, st));
     }
-    const size_t smem = sizeof(T) * ((size_t)3 * N + 2 * ALF_KMAX * ALF_KMAX) + 64;
+    const size_t smem = gm_smem();
     CK(alf_raise_smem(k_random_update<T>));
     KL(KC_UPDATE, st, k_random_update<T><<<C, 512, smem, st>>>(G, G2, N, F, h->n_sun, M, d_vops, ft, h->d_fields, L, ntau, h->d_rng, h->d_phase, h->d_counters, d_mpos,
-                                                               n_moves, std::max(maxlen, 1), d_len, d_list, d_val, d_t0, d_s0, d_acc, place_to, GmtDev{0, 0, nullptr, nullptr, {0, 0, nullptr, nullptr, nullptr, nullptr, nullptr}}));
+                                                               n_moves, std::max(maxlen, 1), d_len, d_list, d_val, d_t0, d_s0, d_acc, place_to, GmtDev{0, 0, nullptr, nullptr, {0, 0, nullptr, nullptr, nullptr, nullptr, nullptr}}, gm_stage, d_place_tab, d_place_pk, gm_stage_f));
     if (acc_out && n_moves > 0) { CK(cudaMemcpyAsync(acc_out, d_acc, np, cudaMemcpyDeviceToHost, st)); }
     sync();
   }

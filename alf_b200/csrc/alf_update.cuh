@@ -56,7 +56,7 @@ struct UpdCtl {                       // per-op broadcast block (double buffered
 
 // ---- G0 <- DL G0 DR - X Y^T for one flavor, then DL = DR = 1.  128 x 128 output tiles, 8 x 4 register micro-tiles.
 template <typename T>
-__device__ __forceinline__ void flush_flavor(T* __restrict__ G0, int N, const T* __restrict__ X, const T* __restrict__ Y, int ldx, int nd,
+__device__ __forceinline__ void flush_flavor(T* __restrict__ G0, int N, int ldg, const T* __restrict__ X, const T* __restrict__ Y, int ldx, int nd,
                                              T* __restrict__ dl, T* __restrict__ dr) {
   const int tid = threadIdx.x;
   const int tx = tid & 15, ty = tid >> 4;      // 16 x 32 threads
@@ -88,7 +88,7 @@ __device__ __forceinline__ void flush_flavor(T* __restrict__ G0, int N, const T*
 #pragma unroll
         for (int r = 0; r < 8; ++r) {
           const int i = ib + r;
-          if (i < N) { T g = G0[i + (long)j * N]; G0[i + (long)j * N] = (dl[i] * g) * drj - acc[r][c]; }
+          if (i < N) { T g = G0[i + (long)j * ldg]; G0[i + (long)j * ldg] = (dl[i] * g) * drj - acc[r][c]; }
         }
       }
     }
@@ -99,14 +99,14 @@ __device__ __forceinline__ void flush_flavor(T* __restrict__ G0, int N, const T*
 // Apply  G_cur <- AL * G_cur * AR  restricted to rows / columns P (k x k matrices) IMMEDIATELY to G0 (global) and to the
 // delayed factors: rows P of X by AL, rows P of Y by AR^T.  Pending diagonal factors on P are folded in first.
 template <typename T>
-__device__ __forceinline__ void similarity_immediate(T* __restrict__ G0, int N, T* __restrict__ X, T* __restrict__ Y, int ldx, int nd,
+__device__ __forceinline__ void similarity_immediate(T* __restrict__ G0, int N, int ldg, T* __restrict__ X, T* __restrict__ Y, int ldx, int nd,
                                                      T* __restrict__ dl, T* __restrict__ dr, const int* P, int k, const T* AL, const T* AR) {
   const int tid = threadIdx.x, nthr = blockDim.x;
   // rows: G0(P,:) <- AL * diag(dl_P) * G0(P,:)
   for (int j = tid; j < N; j += nthr) {
     T v[ALF_KMAX];
-    for (int a = 0; a < k; ++a) v[a] = dl[P[a]] * G0[P[a] + (long)j * N];
-    for (int a = 0; a < k; ++a) { T s = zero_<T>(); for (int b = 0; b < k; ++b) fma_(s, AL[a + b * ALF_KMAX], v[b]); G0[P[a] + (long)j * N] = s; }
+    for (int a = 0; a < k; ++a) v[a] = dl[P[a]] * G0[P[a] + (long)j * ldg];
+    for (int a = 0; a < k; ++a) { T s = zero_<T>(); for (int b = 0; b < k; ++b) fma_(s, AL[a + b * ALF_KMAX], v[b]); G0[P[a] + (long)j * ldg] = s; }
   }
   for (int kk = tid; kk < nd; kk += nthr) {
     T v[ALF_KMAX], w[ALF_KMAX];
@@ -122,8 +122,8 @@ __device__ __forceinline__ void similarity_immediate(T* __restrict__ G0, int N, 
   // columns: G0(:,P) <- G0(:,P) * diag(dr_P) * AR
   for (int i = tid; i < N; i += nthr) {
     T v[ALF_KMAX];
-    for (int a = 0; a < k; ++a) v[a] = G0[i + (long)P[a] * N] * dr[P[a]];
-    for (int a = 0; a < k; ++a) { T s = zero_<T>(); for (int b = 0; b < k; ++b) fma_(s, v[b], AR[b + a * ALF_KMAX]); G0[i + (long)P[a] * N] = s; }
+    for (int a = 0; a < k; ++a) v[a] = G0[i + (long)P[a] * ldg] * dr[P[a]];
+    for (int a = 0; a < k; ++a) { T s = zero_<T>(); for (int b = 0; b < k; ++b) fma_(s, v[b], AR[b + a * ALF_KMAX]); G0[i + (long)P[a] * ldg] = s; }
   }
   __syncthreads();
   for (int a = tid; a < k; a += nthr) dr[P[a]] = one_<T>();
@@ -155,7 +155,7 @@ __global__ void __launch_bounds__(512, 1) k_wrapgr(T* __restrict__ G, int N, int
                                                    const VopDev<T>* __restrict__ vops,
                                                    FieldTabDev ft, int8_t* __restrict__ fields, int Ltrot, int nt, uint64_t* __restrict__ rng,
                                                    cplx* __restrict__ phase, unsigned long long* __restrict__ counters, int KD,
-                                                   uint8_t* __restrict__ acclog, int propose_s0, S0TabDev s0t) {   // visits the vertices n0 .. n0 + cnt - 1 of the slice
+                                                   uint8_t* __restrict__ acclog, int propose_s0, S0TabDev s0t, int stage_g) {   // visits the vertices n0 .. n0 + cnt - 1 of the slice
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ UpdCtl ctl[2];
   __shared__ T gpp_s[ALF_FMAX][ALF_KMAX][ALF_KMAX];
@@ -168,9 +168,14 @@ __global__ void __launch_bounds__(512, 1) k_wrapgr(T* __restrict__ G, int N, int
   T* dl = Ys + (long)F * KD * ldx;
   T* dr = dl + (long)F * N;
   T* gdiag = dr + (long)F * N;
-  T* Gc = G + (long)chain * F * N * N;
+  T* Gglob = G + (long)chain * F * N * N;
+  // stage_g: the chain's G lives in shared memory for the whole slice (small lattices: every non-diagonal vertex applies its similarity
+  // transformation to G immediately, which is L2 latency per visit otherwise); odd leading dimension against bank conflicts of row accesses
+  const int ldg = stage_g ? (N | 1) : N; const long sG = (long)ldg * N;
+  T* Gc = stage_g ? (gdiag + (long)F * N) : Gglob;
+  if (stage_g) { for (long e = threadIdx.x; e < (long)F * N * N; e += blockDim.x) { const long fq = e / ((long)N * N), q = e - fq * N * N; Gc[fq * sG + (q % N) + (q / N) * ldg] = Gglob[e]; } __syncthreads(); }
   int8_t* fld = fields + ((long)chain * Ltrot + (nt - 1)) * n_opv;
-  for (int e = tid; e < F * N; e += nthr) { dl[e] = one_<T>(); dr[e] = one_<T>(); int f = e / N, i = e % N; gdiag[e] = Gc[(long)f * N * N + i + (long)i * N]; }
+  for (int e = tid; e < F * N; e += nthr) { dl[e] = one_<T>(); dr[e] = one_<T>(); int f = e / N, i = e % N; gdiag[e] = Gc[f * sG + i + (long)i * ldg]; }
   Xoshiro r; cplx ph; unsigned long long n_acc = 0, n_prop = 0;
   if (tid == 0) { r.s0 = rng[chain * 4 + 0]; r.s1 = rng[chain * 4 + 1]; r.s2 = rng[chain * 4 + 2]; r.s3 = rng[chain * 4 + 3]; ph = phase[chain]; }
   int nd = 0;
@@ -210,8 +215,8 @@ __global__ void __launch_bounds__(512, 1) k_wrapgr(T* __restrict__ G, int N, int
             AR[a + b * ALF_KMAX] = op->U[a + b * ALF_KMAX];
           }
         }
-        similarity_immediate<T>(Gc + (long)f * N * N, N, Xs + (long)f * KD * ldx, Ys + (long)f * KD * ldx, ldx, nd, dl + f * N, dr + f * N, op->P, k, AL, AR);
-        for (int a = tid; a < k; a += nthr) gdiag[f * N + op->P[a]] = Gc[(long)f * N * N + op->P[a] + (long)op->P[a] * N];
+        similarity_immediate<T>(Gc + f * sG, N, ldg, Xs + (long)f * KD * ldx, Ys + (long)f * KD * ldx, ldx, nd, dl + f * N, dr + f * N, op->P, k, AL, AR);
+        for (int a = tid; a < k; a += nthr) gdiag[f * N + op->P[a]] = Gc[f * sG + op->P[a] + (long)op->P[a] * ldg];
       }
       __syncthreads();
     }
@@ -226,7 +231,7 @@ __global__ void __launch_bounds__(512, 1) k_wrapgr(T* __restrict__ G, int N, int
           for (int kk = lane; kk < nd; kk += 32) fma_(s, Xs[((long)f * KD + kk) * ldx + pa], Ys[((long)f * KD + kk) * ldx + pb]);
           s = warp_sum(s);
           if (lane == 0) {
-            T g0 = (a == b) ? gdiag[f * N + pa] : Gc[(long)f * N * N + pa + (long)pb * N];
+            T g0 = (a == b) ? gdiag[f * N + pa] : Gc[f * sG + pa + (long)pb * ldg];
             gpp_s[f][a][b] = (dl[f * N + pa] * g0) * dr[f * N + pb] - s;
           }
         }
@@ -300,7 +305,7 @@ __global__ void __launch_bounds__(512, 1) k_wrapgr(T* __restrict__ G, int N, int
           if (a >= op->nnz) continue;
           const int p = op->P[a];
           T* X = Xs + (long)f * KD * ldx; T* Y = Ys + (long)f * KD * ldx;
-          const T* G0 = Gc + (long)f * N * N;
+          const T* G0 = Gc + f * sG;
           T xf;
           if (op->nnz == 1) xf = xfac_s[f];
           else {
@@ -310,7 +315,7 @@ __global__ void __launch_bounds__(512, 1) k_wrapgr(T* __restrict__ G, int N, int
               for (int kk = lane; kk < nd; kk += 32) fma_(s, X[(long)kk * ldx + p], Y[(long)kk * ldx + p]);
               s = warp_sum(s);
               if (lane == 0) {
-                T gpp = (dl[f * N + p] * G0[p + (long)p * N]) * dr[f * N + p] - s;
+                T gpp = (dl[f * N + p] * G0[p + (long)p * ldg]) * dr[f * N + p] - s;
                 T d = op->delta[a][s_old + 2][s_cur + 2];
                 bc_s[0] = d / (one_<T>() + (one_<T>() - gpp) * d);
               }
@@ -321,12 +326,12 @@ __global__ void __launch_bounds__(512, 1) k_wrapgr(T* __restrict__ G, int N, int
           const T dlp = dl[f * N + p], drp = dr[f * N + p];
           for (int t = tid; t < 2 * N; t += nthr) {
             if (t < N) {          // column p of G_cur  ->  X(:, nd) = xfac * G_cur(:, p)
-              T s = (dl[f * N + t] * G0[t + (long)p * N]) * drp;
+              T s = (dl[f * N + t] * G0[t + (long)p * ldg]) * drp;
               for (int kk = 0; kk < nd; ++kk) s = s - X[(long)kk * ldx + t] * Y[(long)kk * ldx + p];
               X[(long)nd * ldx + t] = xf * s;
             } else {              // row p of G_cur     ->  Y(:, nd) = e_p - G_cur(p, :)
               const int j = t - N;
-              T s = (dlp * G0[p + (long)j * N]) * dr[f * N + j];
+              T s = (dlp * G0[p + (long)j * ldg]) * dr[f * N + j];
               for (int kk = 0; kk < nd; ++kk) s = s - X[(long)kk * ldx + p] * Y[(long)kk * ldx + j];
               Y[(long)nd * ldx + j] = ((j == p) ? one_<T>() : zero_<T>()) - s;
             }
@@ -336,10 +341,10 @@ __global__ void __launch_bounds__(512, 1) k_wrapgr(T* __restrict__ G, int N, int
         nd += 1;
         if (nd == KD) {
           for (int f = 0; f < F; ++f)
-            flush_flavor<T>(Gc + (long)f * N * N, N, Xs + (long)f * KD * ldx, Ys + (long)f * KD * ldx, ldx, nd, dl + f * N, dr + f * N);
+            flush_flavor<T>(Gc + f * sG, N, ldg, Xs + (long)f * KD * ldx, Ys + (long)f * KD * ldx, ldx, nd, dl + f * N, dr + f * N);
           nd = 0;
           __syncthreads();
-          for (int e = tid; e < F * N; e += nthr) { int f = e / N, i = e % N; gdiag[e] = Gc[(long)f * N * N + i + (long)i * N]; }
+          for (int e = tid; e < F * N; e += nthr) { int f = e / N, i = e % N; gdiag[e] = Gc[f * sG + i + (long)i * ldg]; }
           __syncthreads();
         }
       }
@@ -372,8 +377,8 @@ __global__ void __launch_bounds__(512, 1) k_wrapgr(T* __restrict__ G, int N, int
             AR[a + b * ALF_KMAX] = ea * conj_(op->U[b + a * ALF_KMAX]);
           }
         }
-        similarity_immediate<T>(Gc + (long)f * N * N, N, Xs + (long)f * KD * ldx, Ys + (long)f * KD * ldx, ldx, nd, dl + f * N, dr + f * N, op->P, k, AL, AR);
-        for (int a = tid; a < k; a += nthr) gdiag[f * N + op->P[a]] = Gc[(long)f * N * N + op->P[a] + (long)op->P[a] * N];
+        similarity_immediate<T>(Gc + f * sG, N, ldg, Xs + (long)f * KD * ldx, Ys + (long)f * KD * ldx, ldx, nd, dl + f * N, dr + f * N, op->P, k, AL, AR);
+        for (int a = tid; a < k; a += nthr) gdiag[f * N + op->P[a]] = Gc[f * sG + op->P[a] + (long)op->P[a] * ldg];
       }
       __syncthreads();
     }
@@ -381,7 +386,8 @@ __global__ void __launch_bounds__(512, 1) k_wrapgr(T* __restrict__ G, int N, int
   // ---------- end of slice: materialise G
   __syncthreads();
   for (int f = 0; f < F; ++f)
-    flush_flavor<T>(Gc + (long)f * N * N, N, Xs + (long)f * KD * ldx, Ys + (long)f * KD * ldx, ldx, nd, dl + f * N, dr + f * N);
+    flush_flavor<T>(Gc + f * sG, N, ldg, Xs + (long)f * KD * ldx, Ys + (long)f * KD * ldx, ldx, nd, dl + f * N, dr + f * N);
+  if (stage_g) { __syncthreads(); for (long e = tid; e < (long)F * N * N; e += nthr) { const long fq = e / ((long)N * N), q = e - fq * N * N; Gglob[e] = Gc[fq * sG + (q % N) + (q / N) * ldg]; } }
   if (tid == 0) {
     rng[chain * 4 + 0] = r.s0; rng[chain * 4 + 1] = r.s1; rng[chain * 4 + 2] = r.s2; rng[chain * 4 + 3] = r.s3;
     phase[chain] = ph;

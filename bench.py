@@ -33,6 +33,7 @@ WORKLOADS = {
     "hubbard_8x8_beta10": (8, 8, 10.0, 0.1, 4.0, 10, 296),          # configs[1]
     "hubbard_4x4_beta5": (4, 4, 5.0, 0.1, 4.0, 10, 296),            # configs[0]
     "kondo_12x12_beta20": (12, 12, 20.0, 0.1, None, 5, 148),        # configs[3]: SU(2) Kondo lattice, N_dim = 288, complex, Nwrap = 5
+    "z2_matter_12x12": (12, 12, 10.0, 0.1, None, 10, 148),          # configs[4]: Z2 gauge + matter, projective (theta = 10, Ltrot = 300), N_Global_tau = 36; use --ltau 0 --steps 1 --warmup 1
 }
 
 
@@ -41,6 +42,9 @@ def make_model(name):
     L1, L2, beta, dtau, U, nwrap, chains = WORKLOADS[name]
     if name.startswith("kondo"):
         return kondo_square(L1, L2, beta=beta, dtau=dtau), nwrap, chains
+    if name.startswith("z2_matter"):
+        from alf_b200.model import z2_matter_square
+        return z2_matter_square(L1, L2, beta=beta, dtau=dtau, projector=True, theta=10.0), nwrap, chains
     return hubbard_square(L1, L2, beta=beta, dtau=dtau, U=U), nwrap, chains
 
 
