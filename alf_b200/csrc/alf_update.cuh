@@ -149,6 +149,27 @@ __device__ __forceinline__ double s0_eval(const S0TabDev& t, const int8_t* __res
   return S;
 }
 
+// the same product evaluated by one warp: lane l takes entry l (mod 32) of the field's flattened entry list, the parity of every term comes
+// from a ballot; all lanes return the value.  Terms of one field hold at most a few dozen entries.
+__device__ __forceinline__ double s0_eval_warp(const S0TabDev& t, const int8_t* __restrict__ fchain, int n, int nt, int Ltrot, int n_opv) {
+  if (!t.on) return 1.0;
+  const int lane = threadIdx.x & 31;
+  const int q0 = t.op_start[n], q1 = t.op_start[n + 1];
+  double S = 1.0;
+  for (int q = q0; q < q1; ++q) {
+    const int e0 = t.term_start[q], e1 = t.term_start[q + 1];
+    int neg = 0, out = 0;
+    for (int e = e0 + lane; e < e1; e += 32) {
+      int nt1 = nt + t.e_dt[e];
+      if (nt1 > Ltrot || nt1 < 1) { if (t.open_bc) { out = 1; continue; } nt1 = (nt1 > Ltrot) ? nt1 - Ltrot : nt1 + Ltrot; }
+      neg ^= (fchain[(long)(nt1 - 1) * n_opv + t.e_op[e]] < 0) ? 1 : 0;
+    }
+    const unsigned mneg = __ballot_sync(0xffffffffu, neg), mout = __ballot_sync(0xffffffffu, out);
+    if (!mout) S *= t.w[2 * q + ((__popc(mneg) & 1) ? 0 : 1)];
+  }
+  return S;
+}
+
 // dynamic smem: X[F][KD][ldx], Y[F][KD][ldx], dl[F][N], dr[F][N], gdiag[F][N] (all T)
 template <typename T, int UP>
 __global__ void __launch_bounds__(512, 1) k_wrapgr(T* __restrict__ G, int N, int F, int n_sun, int n0, int cnt, int n_opv, int log_off,
@@ -161,6 +182,7 @@ __global__ void __launch_bounds__(512, 1) k_wrapgr(T* __restrict__ G, int N, int
   __shared__ T gpp_s[ALF_FMAX][ALF_KMAX][ALF_KMAX];
   __shared__ T xfac_s[ALF_FMAX];
   __shared__ T bc_s[2];
+  __shared__ double s0_s;
   const int chain = blockIdx.x, tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5;
   const int ldx = N + 2;
   T* Xs = reinterpret_cast<T*>(smem_raw);
@@ -187,6 +209,11 @@ __global__ void __launch_bounds__(512, 1) k_wrapgr(T* __restrict__ G, int N, int
     const int k = op0->k, isdiag = op0->diag, type = op0->type;
     const int s_old = (int)fld[n];
     UpdCtl* cb = &ctl[step & 1];
+    // ham%S0 of this visit (fields only; they were last changed before the previous visit's closing barrier): warp 1 evaluates it while the
+    // others run the similarity transformation; lane 0 of warp 0 reads it after the barrier in front of the decision
+    // (diagonal vertices have no block barrier before the decision: warp 0 evaluates it itself)
+    double s0_local = 1.0; const int s0_warp = (isdiag || nthr <= 32) ? 0 : 1;
+    if (s0t.on && warp == s0_warp) { s0_local = s0_eval_warp(s0t, fields + (long)chain * Ltrot * n_opv, n, nt, Ltrot, n_opv); if (s0_warp == 1 && lane == 0) s0_s = s0_local; }
 
     // ---------- similarity before the update: UP = Op_Wrapup N_type 1 (old field); DOWN = Op_Wrapdo N_type 2
     if (isdiag) {
@@ -241,7 +268,7 @@ __global__ void __launch_bounds__(512, 1) k_wrapgr(T* __restrict__ G, int N, int
         // --- proposal: nsigma%flip (Fields_mod.F90:173-217), types 1 and 2
         int s_new;
         if (type == 1) s_new = -s_old; else s_new = ft.flip[s_old + 2][r.nranf(3)];
-        double S0_ratio = s0_eval(s0t, fields + (long)chain * Ltrot * n_opv, n, nt, Ltrot, n_opv), T0_proposal = 1.5, T0_Proposal_ratio = 1.0;   // Propose_S0 only for type 1 (Wrapgr_mod.F90:127-132)
+        double S0_ratio = s0t.on ? (s0_warp == 0 ? s0_local : s0_s) : 1.0, T0_proposal = 1.5, T0_Proposal_ratio = 1.0;   // Propose_S0 only for type 1 (Wrapgr_mod.F90:127-132)
         if (propose_s0 && type == 1) { T0_proposal = 1.0 - 1.0 / (1.0 + S0_ratio); T0_Proposal_ratio = 1.0 / S0_ratio; }
         int acc = 0;
         if (T0_proposal > r.ranf()) {
