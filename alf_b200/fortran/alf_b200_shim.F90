@@ -179,6 +179,28 @@ module alf_b200_shim
        type(c_ptr), value :: h
        complex(c_double_complex), intent(out) :: ph(*)
      end function
+     integer(c_int) function alf_b200_set_s0_ising(h, n_terms, op_start, term_start, entry_op, entry_dt, w, open_boundaries, propose_s0) &
+          bind(c, name="alf_b200_set_s0_ising")
+       import :: c_ptr, c_int, c_double
+       type(c_ptr), value :: h
+       integer(c_int), value :: n_terms, open_boundaries, propose_s0
+       integer(c_int), intent(in) :: op_start(*), term_start(*), entry_op(*), entry_dt(*)
+       real(c_double), intent(in) :: w(*)
+     end function
+     integer(c_int) function alf_b200_set_global_tau_sampling(h, nt_sequential_start, nt_sequential_end, n_global_tau) &
+          bind(c, name="alf_b200_set_global_tau_sampling")
+       import :: c_ptr, c_int
+       type(c_ptr), value :: h
+       integer(c_int), value :: nt_sequential_start, nt_sequential_end, n_global_tau
+     end function
+     integer(c_int) function alf_b200_set_global_move_tau_ising(h, n_sites, move_start, move_fields, n_terms, site_term_start, term_start, &
+          entry_op, entry_dt, w, open_boundaries) bind(c, name="alf_b200_set_global_move_tau_ising")
+       import :: c_ptr, c_int, c_double
+       type(c_ptr), value :: h
+       integer(c_int), value :: n_sites, n_terms, open_boundaries
+       integer(c_int), intent(in) :: move_start(*), move_fields(*), site_term_start(*), term_start(*), entry_op(*), entry_dt(*)
+       real(c_double), intent(in) :: w(*)
+     end function
      integer(c_int) function alf_b200_udv_wrap_pivot(device, is_complex, n1, n2, batch, A, U, D, V) bind(c, name="alf_b200_udv_wrap_pivot")
        import :: c_int, c_double_complex
        integer(c_int), value :: device, is_complex, n1, n2, batch
