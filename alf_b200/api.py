@@ -76,6 +76,8 @@ class AlfB200:
             self._ck(L.alf_b200_set_s0_ising(self.h, int(t["n_terms"]), arr["op_start"].ctypes.data_as(_ip), arr["term_start"].ctypes.data_as(_ip),
                                              arr["e_op"].ctypes.data_as(_ip), arr["e_dt"].ctypes.data_as(_ip), _d(w), int(t["open_bc"]),
                                              int(bool(getattr(model, "propose_s0", False)))))
+        if getattr(model, "s0_gaussian", False):
+            self._ck(L.alf_b200_set_s0_gaussian(self.h, 1))
         gt = getattr(model, "global_tau", None)
         if gt is not None and (gt["n_global_tau"] > 0 or gt["nt_seq_end"] != model.n_opv):
             self._ck(L.alf_b200_set_global_tau_sampling(self.h, int(gt["nt_seq_start"]), int(gt["nt_seq_end"]), int(gt["n_global_tau"])))

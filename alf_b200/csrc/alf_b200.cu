@@ -58,6 +58,7 @@ int alf_b200_destroy(alf_b200_handle* h) {
   cudaSetDevice(h->device);
   if (t_prof == &h->prof) t_prof = nullptr;          // the launch-accounting pointer must not outlive its handle
   h->eng.reset();
+  if (h->d_fields_c) cudaFree(h->d_fields_c);
   if (h->d_fields) cudaFree(h->d_fields); if (h->d_rng) cudaFree(h->d_rng); if (h->d_phase) cudaFree(h->d_phase);
   if (h->d_obse_acc) cudaFree(h->d_obse_acc); if (h->d_obse_bg) cudaFree(h->d_obse_bg); if (h->d_obse_cnt) cudaFree(h->d_obse_cnt);
   if (h->d_obst_acc) cudaFree(h->d_obst_acc); if (h->d_obst_bg) cudaFree(h->d_obst_bg); if (h->d_obst_cnt) cudaFree(h->d_obst_cnt);
@@ -137,6 +138,8 @@ int alf_b200_set_global_move_tau_ising(alf_b200_handle* h, int n_sites, const in
   h->gmt_e_dt.assign(entry_dt, entry_dt + ne); h->gmt_w.assign(w, w + 2 * (size_t)n_terms);
   return ALF_OK;
 }
+int alf_b200_set_s0_gaussian(alf_b200_handle* h, int on) { if (!h) return ALF_ERROR_GENERIC; h->s0_gaussian = on != 0; return ALF_OK; }
+int alf_b200_set_amplitude(alf_b200_handle* h, double amplitude) { if (!h) return ALF_ERROR_GENERIC; h->amplitude = amplitude; return ALF_OK; }
 int alf_b200_set_projector(alf_b200_handle* h, int thtrot, int n_part) {
   if (!h || h->finalized || thtrot < 0 || n_part < 1 || n_part > h->ndim) return ALF_ERROR_HAMILTONIAN;
   h->projector = true; h->thtrot = thtrot; h->n_part = n_part;
@@ -155,7 +158,12 @@ int alf_b200_finalize_model(alf_b200_handle* h) {
   API_BEGIN(h)
   for (auto& o : h->opv) if (!o.set) { h->err = "finalize_model: an Op_V entry was never set"; return ALF_ERROR_HAMILTONIAN; }
   for (auto& o : h->opt) if (!o.set) { h->err = "finalize_model: an Op_T entry was never set"; return ALF_ERROR_HAMILTONIAN; }
-  for (auto& o : h->opv) if (o.type != 1 && o.type != 2) { h->err = "only discrete fields (type 1, 2) are supported in this build"; return ALF_ERROR_UNSUPPORTED; }
+  bool has_cont = false;
+  for (auto& o : h->opv) {
+    if (o.type == 3) { has_cont = true; if (o.N != 1) { h->err = "continuous fields (type 3) are supported for single-site vertices only in this build"; return ALF_ERROR_UNSUPPORTED; } }
+    else if (o.type != 1 && o.type != 2) { h->err = "field types 1, 2 (discrete) and 3 (continuous, real) are supported in this build; type 4 is not"; return ALF_ERROR_UNSUPPORTED; }
+  }
+  if (has_cont && (h->n_global_tau > 0 || h->s0_on)) { h->err = "continuous fields together with Ising action tables / global moves are not supported in this build"; return ALF_ERROR_UNSUPPORTED; }
   // real instantiation iff every table the sweep touches is real
   bool cplx_needed = false;
   for (auto& o : h->opt) { if (o.g.imag() != 0.0) cplx_needed = true; for (auto& u : o.U) if (u.imag() != 0.0) cplx_needed = true; }
@@ -171,6 +179,7 @@ int alf_b200_finalize_model(alf_b200_handle* h) {
   h->is_complex = cplx_needed;
   const long C = h->n_chains;
   CK(cudaMalloc(&h->d_fields, (size_t)C * h->ltrot * std::max(1, h->n_opv))); CK(cudaMemset(h->d_fields, 1, (size_t)C * h->ltrot * std::max(1, h->n_opv)));
+  if (has_cont) { const size_t nf = (size_t)C * h->ltrot * h->n_opv; std::vector<double> one(nf, 1.0); CK(cudaMalloc(&h->d_fields_c, sizeof(double) * nf)); CK(cudaMemcpy(h->d_fields_c, one.data(), sizeof(double) * nf, cudaMemcpyHostToDevice)); }
   CK(cudaMalloc(&h->d_rng, sizeof(uint64_t) * 4 * C)); CK(cudaMalloc(&h->d_phase, sizeof(cplx) * C));
   CK(cudaMalloc(&h->d_counters, sizeof(unsigned long long) * 4 * C)); CK(cudaMemset(h->d_counters, 0, sizeof(unsigned long long) * 4 * C));
   CK(cudaMalloc(&h->d_ctl, sizeof(double) * 8 * C)); CK(cudaMemset(h->d_ctl, 0, sizeof(double) * 8 * C));
@@ -198,14 +207,19 @@ int alf_b200_set_rng_state(alf_b200_handle* h, const uint64_t* s) { API_BEGIN(h)
 int alf_b200_fields_set(alf_b200_handle* h) {
   API_BEGIN(h) NEED_FINAL(h)
   KL(KC_EW, h->stream, k_fields_set<<<(h->n_chains + 63) / 64, 64, 0, h->stream>>>(h->d_fields, h->d_rng, h->n_chains, (long)h->ltrot * h->n_opv));
+  if (h->d_fields_c) { const long nf = (long)h->n_chains * h->ltrot * h->n_opv; KL(KC_EW, h->stream, k_i8_to_f64<<<ew_blocks(nf), 256, 0, h->stream>>>(h->d_fields, h->d_fields_c, nf)); }   // type 3 starts from +-1 too (Fields_mod.F90:600-602)
   API_END(h)
 }
 int alf_b200_set_fields(alf_b200_handle* h, const double* f) {
   API_BEGIN(h) NEED_FINAL(h)
   const size_t n = (size_t)h->n_chains * h->ltrot * h->n_opv; std::vector<int8_t> b(n);
-  for (size_t i = 0; i < n; ++i) { long s = std::lround(f[2 * i]); int t = h->types[i % h->n_opv];
-    if (s == 0 || std::labs(s) > t) { h->err = "set_fields: field value outside the discrete range of its operator type"; return ALF_ERROR_FIELDS; } b[i] = (int8_t)s; }
+  std::vector<double> bc(h->d_fields_c ? n : 0);
+  for (size_t i = 0; i < n; ++i) { int t = h->types[i % h->n_opv];
+    if (t == 3) { b[i] = 1; bc[i] = f[2 * i]; continue; }
+    long s = std::lround(f[2 * i]);
+    if (s == 0 || std::labs(s) > t) { h->err = "set_fields: field value outside the discrete range of its operator type"; return ALF_ERROR_FIELDS; } b[i] = (int8_t)s; if (h->d_fields_c) bc[i] = (double)s; }
   CK(cudaStreamSynchronize(h->stream)); CK(cudaMemcpy(h->d_fields, b.data(), n, cudaMemcpyHostToDevice));
+  if (h->d_fields_c) CK(cudaMemcpy(h->d_fields_c, bc.data(), sizeof(double) * n, cudaMemcpyHostToDevice));
   API_END(h)
 }
 int alf_b200_get_fields(alf_b200_handle* h, double* f) {
@@ -213,6 +227,7 @@ int alf_b200_get_fields(alf_b200_handle* h, double* f) {
   const size_t n = (size_t)h->n_chains * h->ltrot * h->n_opv; std::vector<int8_t> b(n);
   CK(cudaStreamSynchronize(h->stream)); CK(cudaMemcpy(b.data(), h->d_fields, n, cudaMemcpyDeviceToHost));
   for (size_t i = 0; i < n; ++i) { f[2 * i] = (double)b[i]; f[2 * i + 1] = 0.0; }
+  if (h->d_fields_c) { std::vector<double> bc(n); CK(cudaMemcpy(bc.data(), h->d_fields_c, sizeof(double) * n, cudaMemcpyDeviceToHost)); for (size_t i = 0; i < n; ++i) if (h->types[i % h->n_opv] == 3) f[2 * i] = bc[i]; }
   API_END(h)
 }
 
@@ -232,14 +247,19 @@ int alf_b200_sweep_host(alf_b200_handle* h, int n_sweeps, int ltau, const double
   const size_t n = (size_t)h->n_chains * h->ltrot * h->n_opv;
   if (!h->pin_fields) CK(cudaHostAlloc((void**)&h->pin_fields, n ? n : 1, cudaHostAllocDefault));
   if (fields_in) {
-    for (size_t i = 0; i < n; ++i) { long s = std::lround(fields_in[2 * i]); int t = h->types[i % h->n_opv];
-      if (s == 0 || std::labs(s) > t) { h->err = "sweep_host: field value outside the discrete range of its operator type"; return ALF_ERROR_FIELDS; } h->pin_fields[i] = (int8_t)s; }
+    std::vector<double> bc(h->d_fields_c ? n : 0);
+    for (size_t i = 0; i < n; ++i) { int t = h->types[i % h->n_opv];
+      if (t == 3) { h->pin_fields[i] = 1; bc[i] = fields_in[2 * i]; continue; }
+      long s = std::lround(fields_in[2 * i]);
+      if (s == 0 || std::labs(s) > t) { h->err = "sweep_host: field value outside the discrete range of its operator type"; return ALF_ERROR_FIELDS; } h->pin_fields[i] = (int8_t)s; if (h->d_fields_c) bc[i] = (double)s; }
     CK(cudaMemcpyAsync(h->d_fields, h->pin_fields, n, cudaMemcpyHostToDevice, h->stream));
+    if (h->d_fields_c) { CK(cudaStreamSynchronize(h->stream)); CK(cudaMemcpy(h->d_fields_c, bc.data(), sizeof(double) * n, cudaMemcpyHostToDevice)); }     // continuous fields: 8 bytes each
   }
   for (int s = 0; s < n_sweeps; ++s) h->eng->sweep(ltau);
   if (fields_out) {
     CK(cudaMemcpyAsync(h->pin_fields, h->d_fields, n, cudaMemcpyDeviceToHost, h->stream)); CK(cudaStreamSynchronize(h->stream));
     for (size_t i = 0; i < n; ++i) { fields_out[2 * i] = (double)h->pin_fields[i]; fields_out[2 * i + 1] = 0.0; }
+    if (h->d_fields_c) { std::vector<double> bc(n); CK(cudaMemcpy(bc.data(), h->d_fields_c, sizeof(double) * n, cudaMemcpyDeviceToHost)); for (size_t i = 0; i < n; ++i) if (h->types[i % h->n_opv] == 3) fields_out[2 * i] = bc[i]; }
   } else h->eng->sync();
   API_END_NORET(h)
   }

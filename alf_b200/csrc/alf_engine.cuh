@@ -84,8 +84,9 @@ template <> inline cd from_T<cplx>(cplx v) { return cd(v.x, v.y); }
 // one operator list under construction
 struct ListBuild {
   int nvar = 1; std::vector<int> k, P, fidx; std::vector<cd> mat;   // mat: per op nvar*KMAX*KMAX
-  void add(int kk, const int* p, int fi, const std::vector<std::vector<cd>>& mats /* nvar matrices kk x kk col-major */) {
-    k.push_back(kk); fidx.push_back(fi);
+  std::vector<unsigned char> cont;      // 1: continuous field, slot 0 of mat holds the coefficient c of exp(c phi)
+  void add(int kk, const int* p, int fi, const std::vector<std::vector<cd>>& mats /* nvar matrices kk x kk col-major */, bool is_cont = false) {
+    k.push_back(kk); fidx.push_back(fi); cont.push_back(is_cont ? 1 : 0);
     for (int a = 0; a < ALF_KMAX; ++a) P.push_back(a < kk ? p[a] : 0);
     for (int v = 0; v < nvar; ++v) for (int b = 0; b < ALF_KMAX; ++b) for (int a = 0; a < ALF_KMAX; ++a)
       mat.push_back((a < kk && b < kk) ? mats[v][a + (size_t)b * kk] : cd(0, 0));
@@ -143,6 +144,8 @@ struct alf_b200_handle {
   Prof prof;
   int8_t* pin_fields = nullptr;      // pinned staging buffer of sweep_host
   // untyped device state shared with the engine
+  double* d_fields_c = nullptr;      // continuous fields (type 3 vertices), same [chain][nt][n] layout; nullptr without such vertices
+  bool s0_gaussian = false; double amplitude = 1.0;   // ham%S0 = exp(-(phi'^2 - phi^2)/2) of the continuous HS transformation; Fields_mod Amplitude
   int8_t* d_fields = nullptr; uint64_t* d_rng = nullptr; cplx* d_phase = nullptr; unsigned long long* d_counters = nullptr;
   double* d_ctl = nullptr;            // per chain: 0 XMEANG 1 XMAXG 2 NCG 3 XMAXP 4 XMEAN_tau 5 XMAX_tau 6 NCG_tau 7 flags(nan=1, unstable=2)
   uint8_t* d_acclog = nullptr; long acclog_per_chain = 0; long acclog_pos = 0; bool acclog_on = false;
@@ -187,12 +190,15 @@ static __global__ void k_fields_set(int8_t* fields, uint64_t* rng, int n_chains,
 }
 
 // sum over (n, nt) of Im(g alpha phi(s)) per (chain, flavor)  -- Op_phase, Prog/Operator_mod.F90:160-181
-static __global__ void k_op_phase(const int8_t* __restrict__ fields, const double* __restrict__ angle_tab, int F, int n_opv, int Ltrot, double* __restrict__ out) {
+static __global__ void k_op_phase(const int8_t* __restrict__ fields, const double* __restrict__ angle_tab, int F, int n_opv, int Ltrot, double* __restrict__ out,
+                                  const double* __restrict__ fields_c, const unsigned char* __restrict__ is_cont) {
   __shared__ double red[8];
   const int b = blockIdx.x, chain = b / F, f = b % F;
   const int8_t* fl = fields + (long)chain * Ltrot * n_opv;
   double s = 0.0;
-  for (long e = threadIdx.x; e < (long)Ltrot * n_opv; e += blockDim.x) { int n = (int)(e % n_opv); s += angle_tab[((long)n * F + f) * ALF_NVAR + fl[e] + 2]; }
+  const double* fc = fields_c ? fields_c + (long)chain * Ltrot * n_opv : nullptr;
+  for (long e = threadIdx.x; e < (long)Ltrot * n_opv; e += blockDim.x) { int n = (int)(e % n_opv);
+    if (fc && is_cont[n]) s += angle_tab[((long)n * F + f) * ALF_NVAR] * fc[e]; else s += angle_tab[((long)n * F + f) * ALF_NVAR + fl[e] + 2]; }
   s = warp_sum(s);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
   __syncthreads();
@@ -244,6 +250,7 @@ __global__ void __launch_bounds__(128) k_obs_scalar(const T* __restrict__ G, lon
   }
 }
 
+static __global__ void k_i8_to_f64(const int8_t* __restrict__ a, double* __restrict__ b, long n) { for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) b[i] = (double)a[i]; }
 static __global__ void k_fill_int(int* __restrict__ p, int n, int v) { const int i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) p[i] = v; }
 // G0T = -(1 - G)  (tau_m_mod.F90:96-104)
 template <typename T>
@@ -280,7 +287,7 @@ struct Engine : EngineBase {
   UdvDev<T> udvl, udvr; std::vector<UdvDev<T>> udvst;
   LaWork<T> w;
   cplx* d_z = nullptr; double* d_angle = nullptr; double* d_angle_tab = nullptr; double* d_cmp = nullptr;
-  VopDev<T>* d_vops = nullptr; T* d_place_tab = nullptr; int* d_place_pk = nullptr; ModelDev md; FieldTabDev ft;
+  VopDev<T>* d_vops = nullptr; T* d_place_tab = nullptr; int* d_place_pk = nullptr; unsigned char* d_is_cont = nullptr; ModelDev md; FieldTabDev ft;
   std::vector<void*> owned;     // device allocations of the op lists
   bool dense_t = false; T* d_dense[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // fwd, inv, c, half, halfinv (N*N*F each)
   int KD = 16; size_t upd_smem = 0; int ops_lk = 0; size_t ops_smem = 0;   // ops_lk = log2 of the largest small-operator dimension
@@ -320,7 +327,7 @@ struct Engine : EngineBase {
       }
       uni[c] = u ? 1 : 0;
     }
-    d.uniform = dupload(uni);
+    d.uniform = dupload(uni); d.cont = dupload(lb.cont);
     return d;
   }
 
@@ -511,6 +518,8 @@ struct Engine : EngineBase {
         VopDev<T>& v = vops[(size_t)n * F + f];
         std::memset(&v, 0, sizeof(v));
         v.k = k; v.nnz = op.nnz; v.diag = op.diag; v.type = op.type;
+        for (int a = 0; a < ALF_KMAX; ++a) v.gE[a] = to_T<T>(a < op.nnz ? op.g * op.E[a] : cd(0, 0));
+        v.galpha = to_T<T>(op.g * op.alpha);
         for (int a = 0; a < k; ++a) v.P[a] = op.P[a];
         for (int a = 0; a < k; ++a) for (int b = 0; b < k; ++b) v.U[a + b * ALF_KMAX] = to_T<T>(op.U[a + (size_t)b * k]);
         mexp[n].resize(ALF_NVAR);
@@ -519,7 +528,7 @@ struct Engine : EngineBase {
           const double ph = valid ? phi_st(op.type, s) : 0.0;
           for (int a = 0; a < ALF_KMAX; ++a) v.E_exp[a][var] = to_T<T>((a < op.nnz && valid) ? std::exp(op.g * op.E[a] * ph) : cd(1, 0));
           host_op_exp(op.g * ph, op, mexp[n][var]);
-          angle_tab[((size_t)n * F + f) * ALF_NVAR + var] = valid ? (op.g * op.alpha * ph).imag() : 0.0;
+          angle_tab[((size_t)n * F + f) * ALF_NVAR + var] = (op.type == 3) ? (op.g * op.alpha).imag() : (valid ? (op.g * op.alpha * ph).imag() : 0.0);   // type 3: coefficient of phi
           for (int var2 = 0; var2 < ALF_NVAR; ++var2) {
             const int s2 = var2 - 2; const bool valid2 = (s2 != 0) && (std::abs(s2) <= op.type);
             const double dphi = (valid && valid2) ? (phi_st(op.type, s2) - ph) : 0.0;
@@ -530,15 +539,20 @@ struct Engine : EngineBase {
       }
       auto ct = [](const std::vector<cd>& A, int k) { std::vector<cd> B(A.size()); for (int i = 0; i < k; ++i) for (int j = 0; j < k; ++j) B[i + (size_t)j * k] = std::conj(A[j + (size_t)i * k]); return B; };
       for (int n = 0; n < M; ++n) { const HostOp& op = h->opv[n + (size_t)M * f]; if (std::abs(op.g) < kEpsMachine) continue;   // quick return, Operator_mod.F90:576,668
+        if (op.type == 3) {      // continuous field, k = 1: the kernels evaluate exp(c phi) with c = +g E (B), -g E (B^-1)
+          std::vector<std::vector<cd>> c1(ALF_NVAR, std::vector<cd>(1, op.g * op.E[0])), c2(ALF_NVAR, std::vector<cd>(1, -op.g * op.E[0]));
+          vn.add(1, op.P.data(), n, c1, true); vri.add(1, op.P.data(), n, c2, true); continue; }
         vn.add(op.N, op.P.data(), n, mexp[n]);
         std::vector<std::vector<cd>> mi(ALF_NVAR); for (int var = 0; var < ALF_NVAR; ++var) mi[var] = tr(mexp[n][ALF_NVAR - 1 - var], op.N);   // exp(-phi g O)^T
         vri.add(op.N, op.P.data(), n, mi); }
       for (int n = M - 1; n >= 0; --n) { const HostOp& op = h->opv[n + (size_t)M * f]; if (std::abs(op.g) < kEpsMachine) continue;
+        if (op.type == 3) { std::vector<std::vector<cd>> c3(ALF_NVAR, std::vector<cd>(1, std::conj(op.g * op.E[0]))); vc.add(1, op.P.data(), n, c3, true); continue; }   // (B)^dagger
         std::vector<std::vector<cd>> mc(ALF_NVAR); for (int var = 0; var < ALF_NVAR; ++var) mc[var] = ct(mexp[n][var], op.N);
         vc.add(op.N, op.P.data(), n, mc); }
       md.lists[L_VL_N][f] = upload_list(vn); md.lists[L_VL_C][f] = upload_list(vc); md.lists[L_VR_INV][f] = upload_list(vri);
     }
-    d_vops = dupload(vops); d_angle_tab = dupload(angle_tab);
+    d_vops = dupload(vops); d_angle_tab = dupload(angle_tab); md.fields_c = h->d_fields_c;
+    { std::vector<unsigned char> tc(M); for (int n = 0; n < M; ++n) tc[n] = h->opv[n].type == 3 ? 1 : 0; d_is_cont = dupload(tc); }
     {   // e^{+V_n(s)} and e^{-V_n(s)} per vertex and field value for Wrapgr_PlaceGR (gm_place_step)
       std::vector<T> pt((size_t)M * F * ALF_NVAR * 2 * ALF_KMAX * ALF_KMAX, zero_<T>());
       for (int f = 0; f < F; ++f) for (int n = 0; n < M; ++n) {
@@ -639,7 +653,7 @@ struct Engine : EngineBase {
     std::swap(G, G2);
     l2_window(G, sizeof(T) * n2 * NM);
     double* ang = nullptr;
-    if (h->is_complex) { KL(KC_EW, st, k_op_phase<<<NM, 256, 0, st>>>(h->d_fields, d_angle_tab, F, M, L, d_angle)); ang = d_angle; }
+    if (h->is_complex) { KL(KC_EW, st, k_op_phase<<<NM, 256, 0, st>>>(h->d_fields, d_angle_tab, F, M, L, d_angle, h->d_fields_c, d_is_cont)); ang = d_angle; }
     KL(KC_EW, st, k_phase_update<<<(C + 127) / 128, 128, 0, st>>>(d_z, ang, F, h->n_sun, h->d_phase, h->d_ctl, compare ? 1 : 0, C));
   }
   void cgr_call(int nvar) override { cgr_and_phase(nvar, false); }
@@ -676,8 +690,8 @@ struct Engine : EngineBase {
       const VGroup& g = groups[up ? gi : (int)groups.size() - 1 - gi];
       if (g.n0 < seq_lo || g.n0 >= seq_hi) continue;                  // not visited sequentially (Nt_sequential_start .. Nt_sequential_end)
       if (g.kind == 0) {
-        if (up) KL(KC_UPDATE, st, k_wrapgr<T, 1><<<C, 512, upd_smem, st>>>(G, N, F, h->n_sun, g.n0, g.cnt, M, off, d_vops, ft, h->d_fields, L, nt, h->d_rng, h->d_phase, h->d_counters, KD, lg, h->propose_s0, s0dev, stage_g));
-        else KL(KC_UPDATE, st, k_wrapgr<T, 0><<<C, 512, upd_smem, st>>>(G, N, F, h->n_sun, g.n0, g.cnt, M, off, d_vops, ft, h->d_fields, L, nt, h->d_rng, h->d_phase, h->d_counters, KD, lg, h->propose_s0, s0dev, stage_g));
+        if (up) KL(KC_UPDATE, st, k_wrapgr<T, 1><<<C, 512, upd_smem, st>>>(G, N, F, h->n_sun, g.n0, g.cnt, M, off, d_vops, ft, h->d_fields, L, nt, h->d_rng, h->d_phase, h->d_counters, KD, lg, h->propose_s0, s0dev, stage_g, h->d_fields_c, h->s0_gaussian ? 1 : 0, h->amplitude));
+        else KL(KC_UPDATE, st, k_wrapgr<T, 0><<<C, 512, upd_smem, st>>>(G, N, F, h->n_sun, g.n0, g.cnt, M, off, d_vops, ft, h->d_fields, L, nt, h->d_rng, h->d_phase, h->d_counters, KD, lg, h->propose_s0, s0dev, stage_g, h->d_fields_c, h->s0_gaussian ? 1 : 0, h->amplitude));
       } else {
         if (g.kind == 2) rotate_group(g, true);
 #define FAST_LAUNCH(UPV, IPT, PR) KL(KC_UPDATE, st, k_wrapgr_fast<T, UPV, IPT, PR><<<C, 512, fast_smem, st>>>(G, N, F, h->n_sun, g.n0, g.cnt, M, off, d_vops, ft, h->d_fields, L, nt, h->d_rng, h->d_phase, h->d_counters, KDf, ldxf, lg))

@@ -26,6 +26,7 @@ struct OpListDev {
   const int* fidx;                  // n_ops : field index n (0-based) or -1
   const void* mat;                  // n_ops * nvar * KMAX*KMAX entries of T, column-major a + b*KMAX
   const unsigned char* uniform;     // n_levels: 1 if every operator of the chunk is a k = 2 operator with one and the same matrix
+  const unsigned char* cont;        // n_ops (vertex lists only): 1 = continuous field (type 3, k = 1): mat slot 0 holds the coefficient c, the factor is exp(c phi)
 };
 
 enum {  // which operator lists a launch applies (per slice nt in [nt_a, nt_b])
@@ -45,6 +46,7 @@ enum { L_TL_FWD = 0, L_TL_INV, L_TL_C, L_TL_HALF, L_TR_FWD, L_TR_INV, L_TR_HALFI
 
 struct ModelDev {
   OpListDev lists[L_COUNT][ALF_FMAX];
+  const double* fields_c;           // continuous fields [chain][nt][n] (type 3 vertices), or nullptr
 };
 
 // Every launch executes a "program": for each requested time slice, up to two operator lists in a fixed order.  The lists are
@@ -164,7 +166,7 @@ __global__ void __launch_bounds__(256) k_apply_ops(T* M, long sM, int N, int nve
   struct Pref { int4 rP; T rM[MPT]; int rcnt; bool runi; };
   Pref pf0, pf1; pf0.rcnt = pf1.rcnt = 0; pf0.runi = pf1.runi = false;
   int f_sl = 0, f_r = 0, f_n = 0;                     // cursor of the next meta load
-  bool m_second = false; int m_a0 = 0, m_cnt = 0; bool m_uni = false; const int8_t* m_fld = nullptr;
+  bool m_second = false; int m_a0 = 0, m_cnt = 0; bool m_uni = false; const int8_t* m_fld = nullptr; const double* m_fc = nullptr;
   auto meta_load = [&]() {
     if (f_n >= total) { m_cnt = 0; return; }
     m_second = f_r >= nch0;
@@ -173,6 +175,7 @@ __global__ void __launch_bounds__(256) k_apply_ops(T* M, long sM, int N, int nve
     m_a0 = L.level_start[c]; m_cnt = L.level_start[c + 1] - m_a0; m_uni = L.uniform[c] != 0;
     const int nt = (dir > 0) ? nt_a + f_sl : nt_b - f_sl;
     m_fld = ((m_second ? uf1 : uf0) && fbase) ? fbase + (nt - 1) * n_opv : nullptr;
+    m_fc = (m_fld && md.fields_c) ? md.fields_c + ((long)chain * Ltrot + (nt - 1)) * n_opv : nullptr;
     ++f_n; if (++f_r == per) { f_r = 0; ++f_sl; }
   };
   auto data_issue = [&](Pref& pf) {                   // uses the meta registers loaded one step earlier
@@ -189,7 +192,13 @@ __global__ void __launch_bounds__(256) k_apply_ops(T* M, long sM, int N, int nve
       if (e < m_cnt * ms) {
         const int o = e >> (2 * LK), rr = e & (ms - 1), a = rr & (kk - 1), bb = rr >> LK, og = m_a0 + o;
         int var = 0;
-        if (L.nvar > 1) var = (int)m_fld[L.fidx[og]] + 2;
+        if (L.nvar > 1) {
+          if (m_fc && L.cont[og]) {        // continuous field: exp(c phi) on the fly (Op_exp for types 3, 4: Operator_mod.F90:585-600)
+            pf.rM[u] = (rr == 0) ? exp_(mats[(og * L.nvar) * (ALF_KMAX * ALF_KMAX)] * m_fc[L.fidx[og]]) : zero_<T>();
+            continue;
+          }
+          var = (int)m_fld[L.fidx[og]] + 2;
+        }
         pf.rM[u] = mats[(og * L.nvar + var) * (ALF_KMAX * ALF_KMAX) + a + bb * ALF_KMAX];
       }
     }

@@ -58,6 +58,8 @@ ALF_HD void fmac_(cplx& c, cplx a, cplx b) {  // c += conj(a)*b
 template <typename T> ALF_HD T make_(double re, double im);
 template <> ALF_HD double make_<double>(double re, double) { return re; }
 template <> ALF_HD cplx make_<cplx>(double re, double im) { return cplx(re, im); }
+ALF_HD double exp_(double a) { return exp(a); }
+ALF_HD cplx exp_(cplx a) { const double e = exp(a.x); double sn, cs; sincos(a.y, &sn, &cs); return cplx(e * cs, e * sn); }
 template <typename T> ALF_HD T zero_() { return make_<T>(0.0, 0.0); }
 template <typename T> ALF_HD T one_() { return make_<T>(1.0, 0.0); }
 ALF_HD bool isnan_(double a) { return a != a; }

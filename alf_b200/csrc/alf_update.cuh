@@ -28,6 +28,8 @@ struct VopDev {                       // one interaction vertex Op_V(n, nf) as t
   T delta[ALF_KMAX][ALF_NVAR][ALF_NVAR];   // exp(g (phi(s')-phi(s)) E_a) - 1, [a][s+2][s'+2]   (upgrade_mod.F90:168-175)
   T expalpha[ALF_NVAR][ALF_NVAR];     // exp(g (phi(s')-phi(s)) alpha)    (upgrade_mod.F90:193)
   T U[ALF_KMAX * ALF_KMAX];           // eigenvectors (non-diagonal vertices), column-major
+  T gE[ALF_KMAX];                     // g E_a: continuous fields (type 3) evaluate exp(g phi E_a) on the fly (Operator_mod.F90:585-600)
+  T galpha;                           // g alpha
 };
 
 struct FieldTabDev {                  // Prog/Fields_mod.F90:258-303
@@ -51,7 +53,7 @@ struct Xoshiro {
 };
 
 struct UpdCtl {                       // per-op broadcast block (double buffered by op parity)
-  int accept; int s_new; int pad0, pad1;
+  int accept; int s_new; double phi_new;
 };
 
 // ---- G0 <- DL G0 DR - X Y^T for one flavor, then DL = DR = 1.  128 x 128 output tiles, 8 x 4 register micro-tiles.
@@ -176,7 +178,8 @@ __global__ void __launch_bounds__(512, 1) k_wrapgr(T* __restrict__ G, int N, int
                                                    const VopDev<T>* __restrict__ vops,
                                                    FieldTabDev ft, int8_t* __restrict__ fields, int Ltrot, int nt, uint64_t* __restrict__ rng,
                                                    cplx* __restrict__ phase, unsigned long long* __restrict__ counters, int KD,
-                                                   uint8_t* __restrict__ acclog, int propose_s0, S0TabDev s0t, int stage_g) {   // visits the vertices n0 .. n0 + cnt - 1 of the slice
+                                                   uint8_t* __restrict__ acclog, int propose_s0, S0TabDev s0t, int stage_g,
+                                                   double* __restrict__ fields_c, int s0_gaussian, double amplitude) {   // visits the vertices n0 .. n0 + cnt - 1 of the slice
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ UpdCtl ctl[2];
   __shared__ T gpp_s[ALF_FMAX][ALF_KMAX][ALF_KMAX];
@@ -197,6 +200,7 @@ __global__ void __launch_bounds__(512, 1) k_wrapgr(T* __restrict__ G, int N, int
   T* Gc = stage_g ? (gdiag + (long)F * N) : Gglob;
   if (stage_g) { for (long e = threadIdx.x; e < (long)F * N * N; e += blockDim.x) { const long fq = e / ((long)N * N), q = e - fq * N * N; Gc[fq * sG + (q % N) + (q / N) * ldg] = Gglob[e]; } __syncthreads(); }
   int8_t* fld = fields + ((long)chain * Ltrot + (nt - 1)) * n_opv;
+  double* fc = fields_c ? fields_c + ((long)chain * Ltrot + (nt - 1)) * n_opv : nullptr;      // continuous fields (type 3) of this slice
   for (int e = tid; e < F * N; e += nthr) { dl[e] = one_<T>(); dr[e] = one_<T>(); int f = e / N, i = e % N; gdiag[e] = Gc[f * sG + i + (long)i * ldg]; }
   Xoshiro r; cplx ph; unsigned long long n_acc = 0, n_prop = 0;
   if (tid == 0) { r.s0 = rng[chain * 4 + 0]; r.s1 = rng[chain * 4 + 1]; r.s2 = rng[chain * 4 + 2]; r.s3 = rng[chain * 4 + 3]; ph = phase[chain]; }
@@ -208,6 +212,7 @@ __global__ void __launch_bounds__(512, 1) k_wrapgr(T* __restrict__ G, int N, int
     const VopDev<T>* op0 = vops + (long)n * F;
     const int k = op0->k, isdiag = op0->diag, type = op0->type;
     const int s_old = (int)fld[n];
+    const bool cont = (type == 3) && fc; const double phi_old = cont ? fc[n] : 0.0;
     UpdCtl* cb = &ctl[step & 1];
     // ham%S0 of this visit (fields only; they were last changed before the previous visit's closing barrier): warp 1 evaluates it while the
     // others run the similarity transformation; lane 0 of warp 0 reads it after the barrier in front of the decision
@@ -221,7 +226,7 @@ __global__ void __launch_bounds__(512, 1) k_wrapgr(T* __restrict__ G, int N, int
         for (int f = 0; f < F; ++f) {
           const VopDev<T>* op = op0 + f;
           for (int a = 0; a < k; ++a) {
-            const T e = op->E_exp[a][s_old + 2]; const T ei = one_<T>() / e; const int p = op->P[a];
+            const T e = cont ? exp_(op->gE[a] * phi_old) : op->E_exp[a][s_old + 2]; const T ei = one_<T>() / e; const int p = op->P[a];
             for (int kk = lane; kk < nd; kk += 32) { Xs[((long)f * KD + kk) * ldx + p] = Xs[((long)f * KD + kk) * ldx + p] * e; Ys[((long)f * KD + kk) * ldx + p] = Ys[((long)f * KD + kk) * ldx + p] * ei; }
             if (lane == 0) { dl[f * N + p] = dl[f * N + p] * e; dr[f * N + p] = dr[f * N + p] * ei; }
           }
@@ -266,18 +271,21 @@ __global__ void __launch_bounds__(512, 1) k_wrapgr(T* __restrict__ G, int N, int
       __syncwarp();
       if (lane == 0) {
         // --- proposal: nsigma%flip (Fields_mod.F90:173-217), types 1 and 2
-        int s_new;
-        if (type == 1) s_new = -s_old; else s_new = ft.flip[s_old + 2][r.nranf(3)];
+        int s_new; double phi_new = 0.0;
+        if (cont) { s_new = s_old; phi_new = phi_old + amplitude * (r.ranf() - 0.5); }      // Fields_mod.F90:185-186
+        else if (type == 1) s_new = -s_old; else s_new = ft.flip[s_old + 2][r.nranf(3)];
         double S0_ratio = s0t.on ? (s0_warp == 0 ? s0_local : s0_s) : 1.0, T0_proposal = 1.5, T0_Proposal_ratio = 1.0;   // Propose_S0 only for type 1 (Wrapgr_mod.F90:127-132)
+        if (cont && s0_gaussian) S0_ratio = exp((-phi_new * phi_new + phi_old * phi_old) / 2.0);      // Hamiltonian_Hubbard_smod.F90:880-882
         if (propose_s0 && type == 1) { T0_proposal = 1.0 - 1.0 / (1.0 + S0_ratio); T0_Proposal_ratio = 1.0 / S0_ratio; }
         int acc = 0;
         if (T0_proposal > r.ranf()) {
           cplx ratiotot = cplx(1.0, 0.0);
           for (int f = 0; f < F; ++f) {
             const VopDev<T>* op = op0 + f; const int nz = op->nnz;
-            T Mat[ALF_KMAX][ALF_KMAX];
+            T Mat[ALF_KMAX][ALF_KMAX]; T d0 = zero_<T>();
             for (int m = 0; m < nz; ++m) {
-              const T d = op->delta[m][s_old + 2][s_new + 2];
+              const T d = cont ? exp_(op->gE[m] * (phi_new - phi_old)) - one_<T>() : op->delta[m][s_old + 2][s_new + 2];
+              if (m == 0) d0 = d;
               for (int q = 0; q < nz; ++q) Mat[q][m] = -(d * gpp_s[f][q][m]);
               Mat[m][m] = Mat[m][m] + (d + one_<T>());
             }
@@ -297,13 +305,13 @@ __global__ void __launch_bounds__(512, 1) k_wrapgr(T* __restrict__ G, int N, int
                 for (int q = c + 1; q < nz; ++q) { T l = Mat[q][c] / Mat[c][c]; for (int w = c; w < nz; ++w) Mat[q][w] = Mat[q][w] - l * Mat[c][w]; }
               }
             }
-            const T rf = D * op->expalpha[s_old + 2][s_new + 2];
+            const T rf = D * (cont ? exp_(op->galpha * (phi_new - phi_old)) : op->expalpha[s_old + 2][s_new + 2]);
             ratiotot = ratiotot * cplx(real_(rf), imag_(rf));
-            if (nz >= 1) xfac_s[f] = op->delta[0][s_old + 2][s_new + 2] / Mat[0][0];   // only used for nnz == 1
+            if (nz >= 1) xfac_s[f] = d0 / Mat[0][0];   // only used for nnz == 1
           }
           cplx rt = ratiotot;
           for (int q = 1; q < n_sun; ++q) rt = rt * ratiotot;
-          const double gr = ft.gama[type][s_new + 2] / ft.gama[type][s_old + 2];
+          const double gr = cont ? 1.0 : ft.gama[type][s_new + 2] / ft.gama[type][s_old + 2];
           rt = rt * gr;
           const cplx pr = ph * rt;
           const double weight = S0_ratio * T0_Proposal_ratio * fabs(pr.x / ph.x);
@@ -315,13 +323,14 @@ __global__ void __launch_bounds__(512, 1) k_wrapgr(T* __restrict__ G, int N, int
           }
           if (acclog) acclog[(long)chain * n_opv + log_off + step] = (uint8_t)acc;
         } else if (acclog) acclog[(long)chain * n_opv + log_off + step] = 2;
-        cb->accept = acc; cb->s_new = s_new;
-        if (acc) fld[n] = (int8_t)s_new;
+        cb->accept = acc; cb->s_new = s_new; cb->phi_new = phi_new;
+        if (acc) { if (cont) fc[n] = phi_new; else fld[n] = (int8_t)s_new; }
       }
     }
     __syncthreads();
     const int accepted = cb->accept;
     const int s_cur = accepted ? cb->s_new : s_old;
+    const double phi_cur = (cont && accepted) ? cb->phi_new : phi_old;
 
     // ---------- accepted: append the rank-1 factors (sequentially over the non-zero eigen-directions)
     if (accepted) {
@@ -383,7 +392,7 @@ __global__ void __launch_bounds__(512, 1) k_wrapgr(T* __restrict__ G, int N, int
         for (int f = 0; f < F; ++f) {
           const VopDev<T>* op = op0 + f;
           for (int a = 0; a < k; ++a) {
-            const T e = op->E_exp[a][s_cur + 2]; const T ei = one_<T>() / e; const int p = op->P[a];
+            const T e = cont ? exp_(op->gE[a] * phi_cur) : op->E_exp[a][s_cur + 2]; const T ei = one_<T>() / e; const int p = op->P[a];
             for (int kk = lane; kk < nd; kk += 32) { Xs[((long)f * KD + kk) * ldx + p] = Xs[((long)f * KD + kk) * ldx + p] * ei; Ys[((long)f * KD + kk) * ldx + p] = Ys[((long)f * KD + kk) * ldx + p] * e; }
             if (lane == 0) { dl[f * N + p] = dl[f * N + p] * ei; dr[f * N + p] = dr[f * N + p] * e; }
           }

@@ -187,6 +187,11 @@ module alf_b200_shim
        integer(c_int), intent(in) :: op_start(*), term_start(*), entry_op(*), entry_dt(*)
        real(c_double), intent(in) :: w(*)
      end function
+     integer(c_int) function alf_b200_set_s0_gaussian(h, on) bind(c, name="alf_b200_set_s0_gaussian")
+       import :: c_ptr, c_int
+       type(c_ptr), value :: h
+       integer(c_int), value :: on
+     end function
      integer(c_int) function alf_b200_set_global_tau_sampling(h, nt_sequential_start, nt_sequential_end, n_global_tau) &
           bind(c, name="alf_b200_set_global_tau_sampling")
        import :: c_ptr, c_int

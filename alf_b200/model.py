@@ -172,6 +172,7 @@ class Model:
     propose_s0: bool = False
     # Nt_sequential_start / _end, N_Global_tau (Hamiltonian_main_mod.F90 Overide_global_tau_sampling_parameters) and ham%Global_move_tau as tables
     global_tau: Optional[dict] = None
+    s0_gaussian: bool = False           # ham%S0 = exp(-(f'^2 - f^2)/2) of the continuous HS transformation (Hubbard_smod.F90:880-882)
     global_move_tau_ising: Optional[dict] = None
 
     # List(I1, 1:2) of the Hamiltonians (unit cell, orbital) per site, 1-based, and the number of orbitals per unit cell
@@ -255,7 +256,7 @@ def trial_wave_function_square(latt: Lattice, n_part: int, N_FL: int, kind: str 
 
 def hubbard_square(L1: int, L2: int, beta: float, dtau: float = 0.1, U: float = 4.0, t: float = 1.0, mu: float = 0.0,
                    Mz: bool = True, checkerboard: bool = True, symm: bool = True, N_SUN: int = 2,
-                   projector: bool = False, theta: float = 10.0, trial: str = "flux") -> Model:
+                   projector: bool = False, theta: float = 10.0, trial: str = "flux", continuous: bool = False) -> Model:
     """Hubbard model on the square lattice as set up by Hamiltonian_Hubbard_smod.F90 (Ham_Set :207-330,
     Ham_Hop, Ham_V :477-542) with the shipped defaults (Scripts_and_Parameters_files/Start/parameters).
     projector=True: the projective algorithm (:236-239 Thtrot = nint(theta/dtau), Ltrot += 2 Thtrot; Ham_Trial :455-470,
@@ -310,7 +311,20 @@ def hubbard_square(L1: int, L2: int, beta: float, dtau: float = 0.1, U: float = 
     Op_V: List[List[Operator]] = []
     if abs(U) > EPS_SMALL:
         for I in range(1, latt.N + 1):
-            if Mz:
+            if Mz and continuous:
+                # Predefined_Int_U_MZ_continuous_HS (Predefined_Int_mod.F90:160-181), called with Ham_U_vec/N_SUN (Hubbard_smod.F90:510-512)
+                ops = []
+                for sgn in (+1.0, -1.0):
+                    op = Op_make(1); op.P[0] = I; op.O[0, 0] = 1.0; op.alpha = 0.0
+                    op.g = sgn * np.sqrt(complex(dtau * U / float(n_sun), 0.0)); op.type = 3
+                    Op_set(op); ops.append(op)
+                Op_V.append(ops)
+            elif continuous:
+                # Predefined_Int_U_SUN_continuous_HS (Predefined_Int_mod.F90:90-105)
+                op = Op_make(1); op.P[0] = I; op.O[0, 0] = 1.0; op.alpha = -0.5
+                op.g = np.sqrt(complex(-dtau * U * 2.0 / float(N_FL * n_sun), 0.0)); op.type = 3
+                Op_set(op); Op_V.append([op])
+            elif Mz:
                 # Predefined_Int_U_MZ (Predefined_Int_mod.F90:107-133); Ham_U_vec/N_SUN with N_SUN already halved
                 Ueff = U / float(n_sun)
                 ops = []
@@ -338,6 +352,7 @@ def hubbard_square(L1: int, L2: int, beta: float, dtau: float = 0.1, U: float = 
               Op_V=Op_V, Op_T=Op_T, latt=latt,
               params=dict(L1=L1, L2=L2, beta=beta, dtau=dtau, U=U, t=t, mu=mu, Mz=Mz, checkerboard=checkerboard, symm=symm,
                           projector=projector, theta=theta, trial=trial))
+    m.s0_gaussian = bool(continuous)
     if projector:
         m.Projector, m.Thtrot = True, Thtrot
         m.WF_L, m.WF_R, m.params["wf_degen"] = trial_wave_function_square(latt, Ndim // 2, N_FL, trial, t)

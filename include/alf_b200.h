@@ -80,6 +80,13 @@ int alf_b200_set_global_tau_sampling(alf_b200_handle* h, int nt_sequential_start
 int alf_b200_set_global_move_tau_ising(alf_b200_handle* h, int n_sites, const int* move_start /* n_sites+1 */, const int* move_fields, int n_terms,
                                        const int* site_term_start /* n_sites+1 */, const int* term_start /* n_terms+1 */, const int* entry_op,
                                        const int* entry_dt, const double* w /* 2*n_terms */, int open_boundaries);
+/* Continuous Hubbard-Stratonovich fields (Op_V%type = 3, e.g. Predefined_Int_U_MZ_continuous_HS / _U_SUN_continuous_HS, Prog/Predefined_Int_mod.F90:
+ * 90-105,160-181; single-site vertices): nsigma%f is real, phi = f, gamma = 1 (Prog/Fields_mod.F90:112-170), the proposal is
+ * f + Amplitude (ranf - 1/2) (:185-186), exp(g phi O) is evaluated on the fly (Op_exp, Prog/Operator_mod.F90:585-600).  The Gaussian weight of
+ * the transformation is the plugin's ham%S0 = exp(-(f'^2 - f^2)/2) (Prog/Hamiltonians/Hamiltonian_Hubbard_smod.F90:880-882): switch it on here.
+ * Amplitude is Fields_mod's module variable (default 1). */
+int alf_b200_set_s0_gaussian(alf_b200_handle* h, int on);
+int alf_b200_set_amplitude(alf_b200_handle* h, double amplitude);
 int alf_b200_finalize_model(alf_b200_handle* h);
 int alf_b200_is_complex(const alf_b200_handle* h);   /* 1 if the complex instantiation was selected */
 

@@ -773,7 +773,11 @@ struct Oracle {
     }
     return S;
   }
-  double S0(int n, int nt, cd) { return s0tab.on ? ising_terms(s0tab, n, nt) : 1.0; }
+  bool s0_gaussian = false;     // Hamiltonian_Hubbard_smod.F90:880-882 (Continuous): S0 = exp((-Hs_new^2 + nsigma%f(n,nt)^2)/2)
+  double S0(int n, int nt, cd Hs_new) {
+    if (s0_gaussian && OpV(n, 0).type == 3) { const double a = Hs_new.real(), b = fld(n, nt).real(); return std::exp((-a * a + b * b) / 2.0); }
+    return s0tab.on ? ising_terms(s0tab, n, nt) : 1.0;
+  }
 
   // ham%Global_move_tau for Ising star moves as tables (Hamiltonian_Z2_Matter_smod.F90:535-643): a site I = nranf(n_sites) is drawn, the
   // fields move_fields[move_start[I] ..) are flipped (Flip_value = nsigma%flip), S0_Matter is the product of the site's coupling terms
@@ -1155,6 +1159,7 @@ void orc_set_global_move_tau_ising(void* h, int n_sites, const int* move_start, 
 long orc_get_gm_log(void* h, uint8_t* out, long cap) { Oracle* o = (Oracle*)h; long n = (long)o->gm_log.size(); for (long i = 0; i < n && i < cap; ++i) out[i] = o->gm_log[i]; return n; }
 double orc_global_move_s0(void* h, int site, int nt) { Oracle* o = (Oracle*)h; return o->ising_terms(o->gmt.terms, site - 1, nt); }
 double orc_s0(void* h, int n, int nt) { return ((Oracle*)h)->S0(n - 1, nt, cd(0, 0)); }   // ham%S0(n, nt, .) on the current configuration
+void orc_set_s0_gaussian(void* h, int on) { ((Oracle*)h)->s0_gaussian = on != 0; }
 void orc_set_propose_s0(void* h, int on) { ((Oracle*)h)->propose_s0 = on != 0; }
 // table-driven Ising action: op_start[n_opv + 1] -> terms of field n; term_start[n_terms + 1] -> entries; entry = (field, 1-based; dt); w = [n_terms][2]
 void orc_set_s0_ising(void* h, int n_terms, const int* op_start, const int* term_start, const int* e_op, const int* e_dt, const double* w, int open_bc, int propose_s0) {

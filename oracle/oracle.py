@@ -88,6 +88,8 @@ class Oracle:
             elif getattr(model, "propose_s0", False):
                 L.orc_set_propose_s0(self.h, 1)
 
+        if getattr(model, "s0_gaussian", False):
+            L.orc_set_s0_gaussian(self.h, 1)
         gt = getattr(model, "global_tau", None)
         if gt is not None and (gt["n_global_tau"] > 0 or gt["nt_seq_end"] != model.n_opv):
             L.orc_set_global_tau_sampling(self.h, int(gt["nt_seq_start"]), int(gt["nt_seq_end"]), int(gt["n_global_tau"]))

@@ -871,3 +871,28 @@ def test_z2_matter_batched_sweep_parity(variant):
         assert relF(g.green(c, 1), o.green(1)) < TOL_G
         assert abs(ph[c] - o.phase()) < 1e-9
     g.close()
+
+
+@pytest.mark.parametrize("mz", [True, False])
+def test_continuous_hs_fields_sweep_parity(mz):
+    """Continuous Hubbard-Stratonovich fields (Op_V%type = 3; Hamiltonian_Hubbard with Continuous = .true.: Predefined_Int_U_MZ_continuous_HS /
+    _U_SUN_continuous_HS, Gaussian ham%S0, proposal f + Amplitude (ranf - 1/2), exponentials evaluated on the fly): the batched sweep gives the
+    oracle's accept / reject sequence, bit-identical real-valued fields, G and phase.  Mz: real arithmetic; SU(2): imaginary coupling, complex."""
+    m = hubbard_square(4, 4, 1.0, Mz=mz, continuous=True)
+    assert all(op[0].type == 3 for op in m.Op_V) and m.s0_gaussian
+    seeds = SEEDS[:3]
+    g = AlfB200(m, n_chains=len(seeds), nwrap=5); g.set_seeds(seeds); g.fields_set(); g.init_sweep(); g.accept_log(2); g.sweep(2, 1)
+    assert g.is_complex == (not mz)
+    log = g.get_accept_log(); f = g.get_fields(); ph = g.phase()
+    for c, s in enumerate(seeds):
+        o = Oracle(m, nwrap=5); o.ranset(s); o.fields_set(); o.init(); o.log(True); o.sweep(1); o.sweep(1)
+        acc, _ = o.get_log()
+        assert np.array_equal(acc, log[c])
+        fo = o.get_fields()
+        assert np.array_equal(f[c], fo) and np.abs(fo.real - np.rint(fo.real)).max() > 1e-3      # genuinely continuous values
+        for nf in range(1, m.N_FL + 1):
+            assert relF(g.green(c, nf), o.green(nf)) < TOL_G
+        assert abs(ph[c] - o.phase()) < 1e-9
+    # host round trip of real-valued fields
+    g.set_fields(f); assert np.array_equal(g.get_fields(), f)
+    g.close()
