@@ -910,7 +910,7 @@ struct Engine : EngineBase {
   // shared memory of k_random_update; G is staged there when it fits (gm_stage)
   int gm_stage = 0, gm_stage_f = 0;
   size_t gm_smem() {
-    const size_t base = sizeof(T) * ((size_t)3 * N + 2 * ALF_KMAX * ALF_KMAX) + 64, staged = base + sizeof(T) * (size_t)F * (N | 1) * N;
+    const size_t base = sizeof(T) * ((size_t)4 * N + 2 * ALF_KMAX * ALF_KMAX) + 64, staged = base + sizeof(T) * (size_t)F * (N | 1) * N;
     gm_stage = (staged <= 220 * 1024 && !getenv("ALF_B200_NO_STAGE_G")) ? 1 : 0;
     size_t sz = gm_stage ? staged : base;
     gm_stage_f = (sz + (size_t)M + 16 <= 224 * 1024) ? 1 : 0;

@@ -13,7 +13,7 @@
 #include "alf_update.cuh"
 
 template <typename T>
-__device__ __forceinline__ void gm_similarity(T* __restrict__ Gf, int N, int ldg, const VopDev<T>* op, int s, int mode, T* ones, T* AL_s, T* AR_s) {
+__device__ __forceinline__ void gm_similarity(T* __restrict__ Gf, int N, int ldg, const VopDev<T>* op, int s, int mode, T* ones, T* ones_r, T* AL_s, T* AR_s) {
   // mode 0: Op_Wrapup N_type 1 (AL = diag(e) U^H, AR = U diag(1/e)); 1: Op_Wrapup N_type 2 (AL = U, AR = U^H)
   // mode 2: Op_Wrapdo N_type 2 (AL = U^H, AR = U);                    3: Op_Wrapdo N_type 1 (AL = U diag(1/e), AR = diag(e) U^H)
   // mode 4 / 5: both steps of a whole vertex at once, AL = U diag(e^{+-1}) U^H, AR = U diag(e^{-+1}) U^H
@@ -42,7 +42,7 @@ __device__ __forceinline__ void gm_similarity(T* __restrict__ Gf, int N, int ldg
   T AL[ALF_KMAX * ALF_KMAX], AR[ALF_KMAX * ALF_KMAX];
 #pragma unroll
   for (int e = 0; e < ALF_KMAX * ALF_KMAX; ++e) { AL[e] = AL_s[e]; AR[e] = AR_s[e]; }
-  similarity_immediate<T>(Gf, N, ldg, nullptr, nullptr, 0, 0, ones, ones, op->P, k, AL, AR);
+  similarity_immediate<T>(Gf, N, ldg, nullptr, nullptr, 0, 0, ones, ones_r, op->P, k, AL, AR);      // dl, dr: two arrays of ones (no pending diagonal factors here)
 }
 
 // ham%Global_move_tau for Ising star moves as tables (Hamiltonian_Z2_Matter_smod.F90:535-643), evaluated on the device: a site
@@ -155,7 +155,8 @@ __global__ void __launch_bounds__(512, 1) k_random_update(T* __restrict__ G, T* 
                                                           const int* __restrict__ place_pk /* [n][f][8]: P[0..3], k */, int stage_f) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   T* ones = reinterpret_cast<T*>(smem_raw);        // N
-  T* col = ones + N;                               // N
+  T* ones_r = ones + N;                            // N
+  T* col = ones_r + N;                             // N
   T* row = col + N;                                // N
   T* AL_s = row + N; T* AR_s = AL_s + ALF_KMAX * ALF_KMAX;
   __shared__ int s_acc; __shared__ T s_xf; __shared__ double s_prev[2];
@@ -169,7 +170,7 @@ __global__ void __launch_bounds__(512, 1) k_random_update(T* __restrict__ G, T* 
   // stage_f: the slice's fields in shared memory too (read at every PlaceGR step); writes go to both copies
   int8_t* fld = stage_f ? reinterpret_cast<int8_t*>(Gc_end(AR_s, stage_g, F, N)) : fld_g;
   if (stage_f) for (int i = tid; i < M; i += nthr) fld[i] = fld_g[i];
-  for (int i = tid; i < N; i += nthr) ones[i] = one_<T>();
+  for (int i = tid; i < N; i += nthr) { ones[i] = one_<T>(); ones_r[i] = one_<T>(); }
   __syncthreads();
   int m = mpos[chain];
   Xoshiro r; cplx ph = phase[chain];
@@ -216,7 +217,7 @@ __global__ void __launch_bounds__(512, 1) k_random_update(T* __restrict__ G, T* 
       if (c == 0 && len > 1) { for (long e = tid; e < (long)F * N * N; e += nthr) { const long fq = e / ((long)N * N), q = e - fq * N * N; Gs[e] = Gc[fq * sG + (q % N) + (q / N) * ldg]; } }
       const int s_old = fld[n], s_new = fv[c];
       const VopDev<T>* op0 = vops + (long)n * F;
-      for (int f = 0; f < F; ++f) gm_similarity<T>(Gc + f * sG, N, ldg, op0 + f, s_old, 0, ones, AL_s, AR_s);
+      for (int f = 0; f < F; ++f) gm_similarity<T>(Gc + f * sG, N, ldg, op0 + f, s_old, 0, ones, ones_r, AL_s, AR_s);
       // ---- Upgrade2: ratio (every thread computes it redundantly from global G; k <= 4)
       cplx ratiotot = cplx(1.0, 0.0);
       for (int f = 0; f < F; ++f) {
@@ -280,7 +281,7 @@ __global__ void __launch_bounds__(512, 1) k_random_update(T* __restrict__ G, T* 
         if (tid == 0) { fld[n] = (int8_t)s_new; fld_g[n] = (int8_t)s_new; }
         __syncthreads();
       }
-      for (int f = 0; f < F; ++f) gm_similarity<T>(Gc + f * sG, N, ldg, op0 + f, s_old, 1, ones, AL_s, AR_s);
+      for (int f = 0; f < F; ++f) gm_similarity<T>(Gc + f * sG, N, ldg, op0 + f, s_old, 1, ones, ones_r, AL_s, AR_s);
       m = n + 1;                                   // reference: m = n (1-based)
     }
     if (!acc && len > 1) {                         // rollback (:421-427)
