@@ -15,7 +15,8 @@ import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from alf_b200.api import AlfB200  # noqa: E402
 from alf_b200.bins import print_bin_latt, print_bin_vec  # noqa: E402
-from alf_b200.model import hubbard_square  # noqa: E402
+from alf_b200.model import hubbard_square, z2_matter_square  # noqa: E402
+from alf_b200 import conf  # noqa: E402
 
 
 def main(argv=None):
@@ -25,11 +26,20 @@ def main(argv=None):
     ap.add_argument("--chains", type=int, default=32); ap.add_argument("--nwrap", type=int, default=10)
     ap.add_argument("--bins", type=int, default=2); ap.add_argument("--sweeps", type=int, default=5); ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--ltau", type=int, default=1); ap.add_argument("--out", default="."); ap.add_argument("--seed0", type=int, default=4711)
+    ap.add_argument("--model", default="hubbard", choices=["hubbard", "hubbard_continuous", "z2_matter"],
+                    help="hubbard_continuous: Continuous = .true. (type-3 fields); z2_matter: Hamiltonian_Z2_Matter with S0 / Global_move_tau tables on the device")
+    ap.add_argument("--restart", action="store_true", help="start from confin_<chain> in --out instead of a random configuration (Fields_in)")
     a = ap.parse_args(argv)
     os.makedirs(a.out, exist_ok=True)
-    model = hubbard_square(a.L1, a.L2, beta=a.beta, dtau=a.dtau, U=a.U)
+    if a.model == "z2_matter":
+        model = z2_matter_square(a.L1, a.L2, beta=a.beta, dtau=a.dtau)
+    else:
+        model = hubbard_square(a.L1, a.L2, beta=a.beta, dtau=a.dtau, U=a.U, continuous=(a.model == "hubbard_continuous"))
     g = AlfB200(model, n_chains=a.chains, nwrap=a.nwrap)
-    g.set_seeds([a.seed0 + 7919 * c for c in range(a.chains)]); g.fields_set(); g.init_sweep()
+    g.set_seeds([a.seed0 + 7919 * c for c in range(a.chains)]); g.fields_set()
+    if a.restart:
+        conf.read_confs(g, a.out)                                  # confin_<chain>: random-number state and nsigma%f of every chain
+    g.init_sweep()
     g.sweep(a.warmup, 0)
     g.obs_eq_enable(True)
     if a.ltau:
@@ -55,6 +65,8 @@ def main(argv=None):
                                s, n / a.chains, a.chains, model.latt, dtau=a.dtau, channel="P")
         c = g.control()
         print(f"bin {nb}: acceptance {c['ACC_up'] / max(c['NC_up'], 1):.3f}, precision Green max {c['XMAXG']:.2e}, <sign> {ob[1] / ob[0]:.3f}, <N> {ob[2] / ob[0]:.4f}")
+    for f in conf.write_confs(g, a.out):                           # confout_<chain>, then renamed as ALF's out_to_in.sh does
+        os.replace(f, os.path.join(os.path.dirname(f), os.path.basename(f).replace("confout", "confin")))
     g.close()
     return 0
 

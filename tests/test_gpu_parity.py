@@ -717,6 +717,23 @@ def test_example_writes_alf_bin_files(tmp_path):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("model", ["hubbard_continuous", "z2_matter"])
+def test_example_other_models_and_restart(tmp_path, model):
+    """The same end-to-end example with continuous fields and with Hamiltonian_Z2_Matter (S0 / Global_move_tau tables), including the restart
+    from the confin_<chain> files the first run leaves behind: bins are appended, particle number stays at half filling."""
+    import importlib.util
+    from alf_b200.bins import read_scal
+    spec = importlib.util.spec_from_file_location("hubbard_bins", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "examples", "hubbard_bins.py"))
+    mod = importlib.util.module_from_spec(spec); spec.loader.exec_module(mod)
+    out = str(tmp_path / "run")
+    args = ["--model", model, "--L1", "4", "--L2", "4", "--beta", "0.6", "--chains", "4", "--bins", "1", "--sweeps", "2", "--warmup", "1", "--nwrap", "3", "--ltau", "0", "--out", out]
+    assert mod.main(args) == 0 and os.path.exists(os.path.join(out, "confin_3"))
+    assert mod.main(args + ["--restart"]) == 0
+    obs, sign = read_scal(os.path.join(out, "Part_scal"))
+    assert obs.shape == (2, 1) and np.all(np.abs(obs[:, 0].real - 16.0) < 1.5)
+
+
+@pytest.mark.gpu
 def test_ed_correlations_plaquette_device_observables():
     """Full chain of the device-side measurements against exact diagonalisation (testsuite/test_vs_ed in spirit): 2x2 Hubbard plaquette,
     U = 4, beta = 2: equal-time spin and density correlation functions accumulated ON THE DEVICE over 64 chains vs the 256-state Fock space."""
