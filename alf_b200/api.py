@@ -215,6 +215,12 @@ class AlfB200:
         self._ck(lib().alf_b200_wrapgr_get_position(self.h, m.ctypes.data_as(_ip)))
         return m
 
+    def compute_fermion_det(self):
+        """Compute_Fermion_Det (Prog/Global_mod.F90:792) with storage = "Empty": (log|det| [chain, nf], phase [chain, nf]) of the current fields."""
+        ld = np.zeros((self.C, self.m.N_FL)); ph = np.zeros((self.C, self.m.N_FL), dtype=np.complex128)
+        self._ck(lib().alf_b200_compute_fermion_det(self.h, _d(ld), _d(ph)))
+        return ld, ph
+
     def wrapgr_placegr(self, m1, ntau):
         self._ck(lib().alf_b200_wrapgr_placegr(self.h, int(m1), int(ntau)))
 

@@ -275,6 +275,14 @@ int alf_b200_wrapur(alf_b200_handle* h, int ntau, int ntau1) { API_BEGIN(h) NEED
 int alf_b200_wrapul(alf_b200_handle* h, int ntau1, int ntau) { API_BEGIN(h) NEED_FINAL(h) h->eng->wrapul(ntau1, ntau); h->eng->sync(); API_END(h) }
 int alf_b200_udv_reset(alf_b200_handle* h, int which, char side) { API_BEGIN(h) NEED_FINAL(h) h->eng->udv_reset(which, side); h->eng->sync(); API_END(h) }
 int alf_b200_cgr(alf_b200_handle* h, int nvar) { API_BEGIN(h) NEED_FINAL(h) h->eng->cgr_call(nvar); h->eng->sync(); API_END(h) }
+int alf_b200_compute_fermion_det(alf_b200_handle* h, double* log_abs_det, double* phase_det) {
+  API_BEGIN(h) NEED_FINAL(h)
+  if (!log_abs_det || !phase_det) return ALF_ERROR_GENERIC;
+  std::vector<cd> ph((size_t)h->n_chains * h->n_fl);
+  h->eng->fermion_det(log_abs_det, ph.data());
+  for (size_t i = 0; i < ph.size(); ++i) { phase_det[2 * i] = ph[i].real(); phase_det[2 * i + 1] = ph[i].imag(); }
+  API_END(h)
+}
 int alf_b200_tau_m(alf_b200_handle* h) { API_BEGIN(h) NEED_FINAL(h) h->eng->tau_m(); h->eng->sync(); API_END(h) }
 int alf_b200_tau_p(alf_b200_handle* h, int nst_in) { API_BEGIN(h) NEED_FINAL(h) if (nst_in < 0) return ALF_ERROR_GENERIC; h->eng->tau_p(nst_in); h->eng->sync(); API_END(h) }
 

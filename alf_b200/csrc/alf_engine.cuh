@@ -131,6 +131,7 @@ struct EngineBase {
   virtual void set_green(int chain, int nf, const cd* in) = 0;
   virtual void get_udv(int which, int nst, int chain, int nf, cd* U, cd* D, cd* V) = 0;
   virtual void hop_apply(int which, int nf, cd* A) = 0;
+  virtual void fermion_det(double* logdet, cd* phase) = 0;
   virtual void sync() = 0;
 };
 
@@ -252,6 +253,33 @@ __global__ void __launch_bounds__(128) k_obs_scalar(const T* __restrict__ G, lon
 
 static __global__ void k_i8_to_f64(const int8_t* __restrict__ a, double* __restrict__ b, long n) { for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) b[i] = (double)a[i]; }
 static __global__ void k_fill_int(int* __restrict__ p, int n, int v) { const int i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) p[i] = v; }
+// Compute_Fermion_Det (Prog/Global_mod.F90:792-1000), finite temperature: TP = U + V diag(D) with the scale separation of the STAB3 branch
+// (columns with D > 1 are divided by D and log D is put aside, :912-918); extra[b] = sum_{D_J > 1} log D_J
+template <typename T>
+__global__ void k_fdet_build(T* __restrict__ TP, const T* __restrict__ U, const T* __restrict__ V, const double* __restrict__ D, long sM, int n, double* __restrict__ extra) {
+  const int b = blockIdx.y; TP += (long)b * sM; U += (long)b * sM; V += (long)b * sM; D += (long)b * n;
+  for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < (long)n * n; e += (long)gridDim.x * blockDim.x) {
+    const int j = (int)(e / n); const double d = D[j];
+    TP[e] = (d <= 1.0) ? U[e] + V[e] * d : U[e] * (1.0 / d) + V[e];
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) { double s = 0.0; for (int j = 0; j < n; ++j) if (D[j] > 1.0) s += log(D[j]); extra[b] = s; }
+}
+// log|det| = sum log Dq + extra (+ sum of the log D of the given states, projector);  phase = detq * diag_phase * perm_sign [* conj(det U)]
+static __global__ void k_fdet_finish(const double* __restrict__ Dq, int n, const QrOut* __restrict__ q, const double* __restrict__ extra, const cplx* __restrict__ detU,
+                                     double* __restrict__ logdet, cplx* __restrict__ phase, int nm) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x; if (b >= nm) return;
+  double s = extra ? extra[b] : 0.0;
+  for (int i = 0; i < n; ++i) s += log(Dq[(long)b * n + i]);
+  cplx p = (q[b].detq * q[b].diag_phase) * q[b].perm_sign;
+  if (detU) p = p * conj_(detU[b]);
+  const double a = abs_(p);
+  logdet[b] = s; phase[b] = cplx(p.x / a, p.y / a);
+}
+static __global__ void k_fdet_addlog(const double* __restrict__ D, int ldD, int np, double* __restrict__ acc, int nm) {      // acc[b] += sum_{n < np} log D(n)
+  const int b = blockIdx.x * blockDim.x + threadIdx.x; if (b >= nm) return;
+  double s = 0.0; for (int i = 0; i < np; ++i) s += log(D[(long)b * ldD + i]);
+  acc[b] += s;
+}
 // G0T = -(1 - G)  (tau_m_mod.F90:96-104)
 template <typename T>
 __global__ void k_g0t_init(T* __restrict__ G0T, const T* __restrict__ G, long sM, int n) {
@@ -716,6 +744,37 @@ struct Engine : EngineBase {
     wrapul_on(udvl, stab_nt[1], 0);
     cgr_and_phase(1, false);
   }
+
+  // Compute_Fermion_Det with storage = "Empty" (Prog/Global_mod.F90:792-1000): the left propagation is rebuilt from the current fields
+  // (udvl, udvst as after main.F90:589-627), then per chain and flavor log|det| and phase of the fermion determinant.  Finite temperature:
+  // det(1 + B(beta,0)) through TP = U_L + V_L D_L; the reference factorises TP by QR + SVD (UDV_WRAP) and keeps the individual log singular values,
+  // of which only the sum enters Compute_Ratio_Global (:700-760) -- here the sum comes from the pivoted QR.  Projector: sum of the log D of all
+  // stored decompositions + log|det(U_L^H P_R)| (:846-884).
+  void fermion_det(double* logdet_host, cd* phase_host) override {
+    reset_udv(udvl, 'l'); reset_udv(udvst[S - 1], 'l');
+    double* d_extra = dalloc_tmp<double>(NM); double* d_ld = dalloc_tmp<double>(NM); cplx* d_ph = dalloc_tmp<cplx>(NM);
+    CK(cudaMemsetAsync(d_extra, 0, sizeof(double) * NM, st));
+    for (int NST = S - 1; NST >= 1; --NST) { wrapul_on(udvl, stab_nt[NST + 1], stab_nt[NST]); copy_udv(udvst[NST - 1], udvl);
+      if (proj) KL(KC_EW, st, k_fdet_addlog<<<(NM + 127) / 128, 128, 0, st>>>(udvl.D, N, NP, d_extra, NM)); }
+    wrapul_on(udvl, stab_nt[1], 0);
+    if (proj) {
+      KL(KC_EW, st, k_fdet_addlog<<<(NM + 127) / 128, 128, 0, st>>>(udvl.D, N, NP, d_extra, NM));
+      // S = U_L^H P_R (N_part x N_part), P_R per flavor
+      reset_udv(udvr, 'r');
+      gemm<T, 1, 0, 0>(st, NP, NP, N, udvl.U, N, n2, udvr.U, N, n2, wp.W[2], NP, wp.n2(), NM);
+      la_qrp<T>(wp, wp.W[2], NP, NP, wp.Dq);
+      KL(KC_EW, st, k_fdet_finish<<<(NM + 127) / 128, 128, 0, st>>>(wp.Dq, NP, wp.qrout, d_extra, nullptr, d_ld, d_ph, NM));
+    } else {
+      KL(KC_EW, st, k_fdet_build<T><<<dim3(ew_blocks(n2), NM), 256, 0, st>>>(w.W[0], udvl.U, udvl.V, udvl.D, n2, N, d_extra));
+      la_qrp<T>(w, w.W[0], N, N, w.Dq);
+      KL(KC_EW, st, k_fdet_finish<<<(NM + 127) / 128, 128, 0, st>>>(w.Dq, N, w.qrout, d_extra, udvl.det, d_ld, d_ph, NM));
+    }
+    std::vector<cplx> ph(NM);
+    CK(cudaMemcpyAsync(logdet_host, d_ld, sizeof(double) * NM, cudaMemcpyDeviceToHost, st)); CK(cudaMemcpyAsync(ph.data(), d_ph, sizeof(cplx) * NM, cudaMemcpyDeviceToHost, st)); sync();
+    for (int b = 0; b < NM; ++b) phase_host[b] = cd(ph[b].x, ph[b].y);
+    cudaFree(d_extra); cudaFree(d_ld); cudaFree(d_ph);
+  }
+  template <typename X> X* dalloc_tmp(size_t n) { X* p = nullptr; CK(cudaMalloc(&p, sizeof(X) * (n ? n : 1))); return p; }
 
   // where main.F90:757-773 / 789-802 call ham%Obser: NTAU1 in [LOBS_ST, LOBS_EN] (defaults of QMC_runtime_var_mod.F90:156-189)
   void measure_hook(int ntau1) {

@@ -134,6 +134,12 @@ int alf_b200_get_obs_eq(alf_b200_handle* h, double* acc, double* bg, double* cnt
 int alf_b200_obs_tau_dims(const alf_b200_handle* h, int* n_channels, int* ntau, int* norb, int* n_unit);
 int alf_b200_get_obs_tau(alf_b200_handle* h, double* acc, double* bg, double* cnt);
 
+/* Compute_Fermion_Det(Phase_det, Det_Vec, udvl, udvst, Stab_nt, storage = "Empty"), Prog/Global_mod.F90:792-1000 (what Global_Updates :450 and
+ * the tempering exchange :108 weigh configurations with): rebuilds the left propagation from the CURRENT fields (udvl and the storage udvst
+ * are overwritten as after main.F90:589-627; GR is not touched) and returns, per chain and flavor ([chain][nf]), log|det| = sum_I Det_Vec(I, nf)
+ * and Phase_det(nf) (complex).  Finite temperature: det(1 + B(beta, 0)); projector: det(P_L^H B(2 theta + beta, 0) P_R). */
+int alf_b200_compute_fermion_det(alf_b200_handle* h, double* log_abs_det /* n_chains*n_fl */, double* phase_det /* complex n_chains*n_fl */);
+
 /* Global-in-slice moves (N_Global_tau > 0), Prog/Wrapgr_mod.F90:247-433.  ham%Global_move_tau stays a host plugin callback:
  * its outputs (Flip_length, Flip_list (1-based), Flip_value, T0_Proposal_ratio, S0_ratio) are passed for every chain and every
  * one of the n_moves proposals ([chain][move], lists [chain][move][maxlen], maxlen <= 16); the device sorts the lists

@@ -35,6 +35,7 @@ extern "C" {
 void scipy_zgeqp3_(int*, int*, cd*, int*, int*, cd*, cd*, int*, double*, int*);
 void scipy_zungqr_(int*, int*, int*, cd*, int*, cd*, cd*, int*, int*);
 void scipy_zgeqrf_(int*, int*, cd*, int*, cd*, cd*, int*, int*);
+void scipy_zgesvd_(const char*, const char*, int*, int*, cd*, int*, double*, cd*, int*, cd*, int*, cd*, int*, double*, int*);
 void scipy_zunmqr_(const char*, const char*, int*, int*, int*, cd*, int*, cd*, cd*, int*, cd*, int*, int*);
 void scipy_ztrsm_(const char*, const char*, const char*, const char*, int*, int*, cd*, cd*, int*, cd*, int*);
 void scipy_ztrmm_(const char*, const char*, const char*, const char*, int*, int*, cd*, cd*, int*, cd*, int*);
@@ -808,6 +809,49 @@ struct Oracle {
     }
   }
 
+  // ---- Compute_Fermion_Det(Phase_det, Det_Vec, udvl, udvst, Stab_nt, storage = "Empty"), Prog/Global_mod.F90:792-1000 (default build: no STAB3 / STABLOG).
+  // Det_Vec: ndim entries per flavor.  UDV_WRAP = QR followed by an SVD of the triangular factor (Prog/UDV_WRAP_mod.F90:212-258).
+  void compute_fermion_det(std::vector<cd>& Phase_det, std::vector<double>& Det_Vec) {
+    Phase_det.assign(n_fl, cd(1, 0)); Det_Vec.assign((size_t)ndim * n_fl, 0.0);
+    for (int nf = 0; nf < n_fl; ++nf) reset_udv(udvl[nf], 'l', nf);
+    for (int NST = nstm - 1; NST >= 1; --NST) { wrapul(stab_nt[NST + 1], stab_nt[NST], udvl); for (int nf = 0; nf < n_fl; ++nf) st(NST, nf) = udvl[nf]; }
+    wrapul(stab_nt[1], 0, udvl);
+    if (projector) {
+      for (int nf = 0; nf < n_fl; ++nf) {
+        const int np = n_part;
+        for (int i = 1; i <= nstm - 1; ++i) for (int n = 0; n < np; ++n) Det_Vec[n + (size_t)ndim * nf] += std::log(st(i, nf).D[n].real());
+        for (int n = 0; n < np; ++n) Det_Vec[n + (size_t)ndim * nf] += std::log(udvl[nf].D[n].real());
+        std::vector<cd> TP((size_t)np * np);
+        zgemm('C', 'N', np, np, ndim, cd(1, 0), udvl[nf].U.data(), ndim, WF_R[nf].data(), ndim, cd(0, 0), TP.data(), np);
+        std::vector<int> ipiv(np); int info, n1 = np; scipy_zgetrf_(&n1, &n1, TP.data(), &n1, ipiv.data(), &info);
+        cd Z(1, 0); for (int J = 0; J < np; ++J) { if (ipiv[J] != J + 1) Z = -Z; Z *= TP[J + (size_t)J * np]; }
+        Phase_det[nf] = Z / std::abs(Z); Det_Vec[(size_t)ndim * nf] += std::log(std::abs(Z));
+      }
+      return;
+    }
+    const int N = ndim;
+    for (int nf = 0; nf < n_fl; ++nf) {
+      std::vector<cd> TP = udvl[nf].U;
+      for (int J = 0; J < N; ++J) for (int i = 0; i < N; ++i) TP[i + (size_t)J * N] += udvl[nf].V[i + (size_t)J * N] * udvl[nf].D[J];
+      // UDV_WRAP: QR, then SVD of R, U <- Q U1
+      std::vector<cd> TAU(N), WORK(1); int info = 0, m1 = -1, n1 = N;
+      scipy_zgeqrf_(&n1, &n1, TP.data(), &n1, TAU.data(), WORK.data(), &m1, &info); int LW = (int)WORK[0].real(); WORK.resize(std::max(LW, 1));
+      scipy_zgeqrf_(&n1, &n1, TP.data(), &n1, TAU.data(), WORK.data(), &LW, &info);
+      std::vector<cd> Rm((size_t)N * N, cd(0, 0)); for (int j = 0; j < N; ++j) for (int i = 0; i <= j; ++i) Rm[i + (size_t)j * N] = TP[i + (size_t)j * N];
+      scipy_zungqr_(&n1, &n1, &n1, TP.data(), &n1, TAU.data(), WORK.data(), &LW, &info);       // TP = Q
+      std::vector<cd> U1((size_t)N * N), VT((size_t)N * N), W2(1); std::vector<double> Sv(N), RW(5 * (size_t)N);
+      scipy_zgesvd_("A", "A", &n1, &n1, Rm.data(), &n1, Sv.data(), U1.data(), &n1, VT.data(), &n1, W2.data(), &m1, RW.data(), &info); int LW2 = (int)W2[0].real(); W2.resize(std::max(LW2, 1));
+      scipy_zgesvd_("A", "A", &n1, &n1, Rm.data(), &n1, Sv.data(), U1.data(), &n1, VT.data(), &n1, W2.data(), &LW2, RW.data(), &info);
+      std::vector<cd> Ul((size_t)N * N); zgemm('N', 'N', N, N, N, cd(1, 0), TP.data(), N, U1.data(), N, cd(0, 0), Ul.data(), N);
+      cd Z = det_c(VT, N);
+      std::vector<cd> T2((size_t)N * N); zgemm('C', 'N', N, N, N, cd(1, 0), udvl[nf].U.data(), N, Ul.data(), N, cd(0, 0), T2.data(), N);
+      cd Z1 = det_c(T2, N);
+      Phase_det[nf] = Z * Z1 / std::abs(Z * Z1);
+      for (int i = 0; i < N; ++i) Det_Vec[i + (size_t)N * nf] = std::log(Sv[i]);
+      Det_Vec[(size_t)N * nf] = std::log(Sv[0]) + std::log(std::abs(Z * Z1));
+    }
+  }
+
   // ---- Prog/Wrapgr_mod.F90:81-157
   void wrapgrup(int NTAU) {
     int NTAU1 = NTAU + 1;
@@ -1158,6 +1202,11 @@ void orc_set_global_move_tau_ising(void* h, int n_sites, const int* move_start, 
 }
 long orc_get_gm_log(void* h, uint8_t* out, long cap) { Oracle* o = (Oracle*)h; long n = (long)o->gm_log.size(); for (long i = 0; i < n && i < cap; ++i) out[i] = o->gm_log[i]; return n; }
 double orc_global_move_s0(void* h, int site, int nt) { Oracle* o = (Oracle*)h; return o->ising_terms(o->gmt.terms, site - 1, nt); }
+void orc_compute_fermion_det(void* h, double* phase_det /* complex n_fl */, double* det_vec /* ndim*n_fl */) {
+  Oracle* o = (Oracle*)h; std::vector<cd> ph; std::vector<double> dv; o->compute_fermion_det(ph, dv);
+  for (int nf = 0; nf < o->n_fl; ++nf) { phase_det[2 * nf] = ph[nf].real(); phase_det[2 * nf + 1] = ph[nf].imag(); }
+  std::copy(dv.begin(), dv.end(), det_vec);
+}
 double orc_s0(void* h, int n, int nt) { return ((Oracle*)h)->S0(n - 1, nt, cd(0, 0)); }   // ham%S0(n, nt, .) on the current configuration
 void orc_set_s0_gaussian(void* h, int on) { ((Oracle*)h)->s0_gaussian = on != 0; }
 void orc_set_propose_s0(void* h, int on) { ((Oracle*)h)->propose_s0 = on != 0; }

@@ -117,6 +117,12 @@ class Oracle:
         lib().orc_get_gm_log(self.h, out.ctypes.data_as(C.POINTER(C.c_uint8)), n)
         return out[:n]
 
+    def compute_fermion_det(self):
+        """Compute_Fermion_Det (Prog/Global_mod.F90:792), storage = "Empty": (Phase_det [nf], Det_Vec [nf, ndim])."""
+        ph = np.zeros(self.m.N_FL, dtype=np.complex128); dv = np.zeros((self.m.N_FL, self.N))
+        lib().orc_compute_fermion_det(self.h, _d(ph), _d(dv))
+        return ph, dv
+
     def s0(self, n: int, nt: int) -> float:
         """ham%S0(n, nt, flipped value) on the current configuration (1-based n, nt)."""
         return lib().orc_s0(self.h, int(n), int(nt))

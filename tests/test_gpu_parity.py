@@ -913,3 +913,26 @@ def test_continuous_hs_fields_sweep_parity(mz):
     # host round trip of real-valued fields
     g.set_fields(f); assert np.array_equal(g.get_fields(), f)
     g.close()
+
+
+@pytest.mark.parametrize("variant", ["mz", "su2_continuous", "kondo", "projector", "z2_matter"])
+def test_compute_fermion_det(variant):
+    """alf_b200_compute_fermion_det = Compute_Fermion_Det with storage = "Empty" (Prog/Global_mod.F90:792-1000) for every chain: log|det| (the sum
+    of Det_Vec, all that Compute_Ratio_Global uses) and Phase_det against the oracle's restatement (QR + SVD as UDV_WRAP), after a sweep has
+    changed the fields; the rebuilt storage then continues the Markov chain exactly as the oracle's does."""
+    m = {"mz": lambda: hubbard_square(4, 4, 1.0), "su2_continuous": lambda: hubbard_square(4, 4, 1.0, Mz=False, continuous=True),
+         "kondo": lambda: kondo_square(2, 2, 0.6), "projector": lambda: hubbard_square(4, 4, 0.4, projector=True, theta=0.3, trial="dimer"),
+         "z2_matter": lambda: z2_matter_square(4, 4, 0.5)}[variant]()
+    seeds = SEEDS[:3]
+    g = AlfB200(m, n_chains=len(seeds), nwrap=5); g.set_seeds(seeds); g.fields_set(); g.init_sweep(); g.sweep(1, 0)
+    ld, ph = g.compute_fermion_det()
+    g.sweep(1, 0); f = g.get_fields()
+    for c, s in enumerate(seeds):
+        o = Oracle(m, nwrap=5); o.ranset(s); o.fields_set(); o.init(); o.sweep(0)
+        pho, dv = o.compute_fermion_det()
+        for nf in range(m.N_FL):
+            assert abs(ld[c, nf] - dv[nf].sum()) < 1e-8 * max(1.0, abs(dv[nf].sum())), (variant, ld[c, nf], dv[nf].sum())
+            assert abs(ph[c, nf] - pho[nf]) < 1e-8, (variant, ph[c, nf], pho[nf])
+        o.sweep(0)
+        assert np.array_equal(f[c], o.get_fields())
+    g.close()
