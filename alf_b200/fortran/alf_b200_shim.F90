@@ -206,6 +206,12 @@ module alf_b200_shim
        integer(c_int), intent(in) :: move_start(*), move_fields(*), site_term_start(*), term_start(*), entry_op(*), entry_dt(*)
        real(c_double), intent(in) :: w(*)
      end function
+     integer(c_int) function alf_b200_compute_fermion_det(h, log_abs_det, phase_det) bind(c, name="alf_b200_compute_fermion_det")
+       import :: c_ptr, c_int, c_double, c_double_complex
+       type(c_ptr), value :: h
+       real(c_double), intent(out) :: log_abs_det(*)
+       complex(c_double_complex), intent(out) :: phase_det(*)
+     end function
      integer(c_int) function alf_b200_udv_wrap_pivot(device, is_complex, n1, n2, batch, A, U, D, V) bind(c, name="alf_b200_udv_wrap_pivot")
        import :: c_int, c_double_complex
        integer(c_int), value :: device, is_complex, n1, n2, batch
