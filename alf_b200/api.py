@@ -215,6 +215,18 @@ class AlfB200:
         self._ck(lib().alf_b200_wrapgr_get_position(self.h, m.ctypes.data_as(_ip)))
         return m
 
+    def langevin_forces(self):
+        """Langevin_HMC_Forces (Prog/Langevin_HMC_mod.F90:107): fermionic forces [chain, nt, n] (complex)."""
+        F = np.zeros((self.C, self.m.Ltrot, self.m.n_opv), dtype=np.complex128)
+        self._ck(lib().alf_b200_langevin_forces(self.h, _d(F)))
+        return F
+
+    def langevin_update(self, delta_t, max_force):
+        """One update of scheme "Langevin" (Prog/Langevin_HMC_mod.F90:355-392) for every chain; returns Delta_t_running [chain]."""
+        dt = np.zeros(self.C)
+        self._ck(lib().alf_b200_langevin_update(self.h, C.c_double(delta_t), C.c_double(max_force), _d(dt)))
+        return dt
+
     def compute_fermion_det(self):
         """Compute_Fermion_Det (Prog/Global_mod.F90:792) with storage = "Empty": (log|det| [chain, nf], phase [chain, nf]) of the current fields."""
         ld = np.zeros((self.C, self.m.N_FL)); ph = np.zeros((self.C, self.m.N_FL), dtype=np.complex128)

@@ -275,6 +275,20 @@ int alf_b200_wrapur(alf_b200_handle* h, int ntau, int ntau1) { API_BEGIN(h) NEED
 int alf_b200_wrapul(alf_b200_handle* h, int ntau1, int ntau) { API_BEGIN(h) NEED_FINAL(h) h->eng->wrapul(ntau1, ntau); h->eng->sync(); API_END(h) }
 int alf_b200_udv_reset(alf_b200_handle* h, int which, char side) { API_BEGIN(h) NEED_FINAL(h) h->eng->udv_reset(which, side); h->eng->sync(); API_END(h) }
 int alf_b200_cgr(alf_b200_handle* h, int nvar) { API_BEGIN(h) NEED_FINAL(h) h->eng->cgr_call(nvar); h->eng->sync(); API_END(h) }
+int alf_b200_langevin_forces(alf_b200_handle* h, double* forces) {
+  API_BEGIN(h) NEED_FINAL(h)
+  if (!forces) return ALF_ERROR_GENERIC;
+  std::vector<cd> f((size_t)h->n_chains * h->ltrot * h->n_opv);
+  h->eng->langevin_get_forces(f.data());
+  for (size_t i = 0; i < f.size(); ++i) { forces[2 * i] = f[i].real(); forces[2 * i + 1] = f[i].imag(); }
+  API_END(h)
+}
+int alf_b200_langevin_update(alf_b200_handle* h, double delta_t, double max_force, double* delta_t_running) {
+  API_BEGIN(h) NEED_FINAL(h)
+  if (!(delta_t > 0.0) || !(max_force > 0.0)) return ALF_ERROR_GENERIC;
+  h->eng->langevin_update(delta_t, max_force, delta_t_running);
+  API_END(h)
+}
 int alf_b200_compute_fermion_det(alf_b200_handle* h, double* log_abs_det, double* phase_det) {
   API_BEGIN(h) NEED_FINAL(h)
   if (!log_abs_det || !phase_det) return ALF_ERROR_GENERIC;

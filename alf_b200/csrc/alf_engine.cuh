@@ -132,6 +132,8 @@ struct EngineBase {
   virtual void get_udv(int which, int nst, int chain, int nf, cd* U, cd* D, cd* V) = 0;
   virtual void hop_apply(int which, int nf, cd* A) = 0;
   virtual void fermion_det(double* logdet, cd* phase) = 0;
+  virtual void langevin_get_forces(cd* out) = 0;
+  virtual void langevin_update(double delta_t, double max_force, double* dt_running) = 0;
   virtual void sync() = 0;
 };
 
@@ -253,6 +255,50 @@ __global__ void __launch_bounds__(128) k_obs_scalar(const T* __restrict__ G, lon
 
 static __global__ void k_i8_to_f64(const int8_t* __restrict__ a, double* __restrict__ b, long n) { for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) b[i] = (double)a[i]; }
 static __global__ void k_fill_int(int* __restrict__ p, int n, int v) { const int i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) p[i] = v; }
+// Wrapgrup_Forces (Prog/Langevin_HMC_mod.F90:194-226) for single-site continuous vertices: with G already propagated through the slice,
+// Forces(n, nt) = - sum_nf g_nf N_SUN ( O(1,1) (1 - G_nf(P, P)) + alpha_nf ).  (The conjugation with a diagonal vertex leaves the diagonal of G
+// unchanged, so every force of the slice is read off one G.)  coef: per (n, f) [g O(1,1), g alpha] as T.
+template <typename T>
+__global__ void k_langevin_forces(const T* __restrict__ G, long sM, int N, int F, int n_sun, int M, const int* __restrict__ site /* [n][f] */, const T* __restrict__ coef /* [n][f][2] */,
+                                  const unsigned char* __restrict__ is_cont, cplx* __restrict__ forces /* [chain][nt][n] */, int Ltrot, int nt) {
+  const int chain = blockIdx.y;
+  for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < M; n += gridDim.x * blockDim.x) {
+    cplx acc = cplx(0.0, 0.0);
+    if (is_cont[n]) for (int f = 0; f < F; ++f) {
+      const int p = site[n * F + f]; const T g = G[((long)chain * F + f) * sM + p + (long)p * N];
+      const T z = coef[(n * F + f) * 2] * (one_<T>() - g) + coef[(n * F + f) * 2 + 1];
+      acc = acc - cplx(real_(z), imag_(z)) * (double)n_sun;
+    }
+    forces[((long)chain * Ltrot + (nt - 1)) * M + n] = acc;
+  }
+}
+// Scheme "Langevin" (Prog/Langevin_HMC_mod.F90:362-390): per chain the adaptive step Delta_t_running from the largest |Re force| (fermionic and
+// Forces_0 = phi of the Gaussian action), then for n (outer), nt (inner):  phi -= (phi + Re(Phase F)/Re(Phase)) dt - sqrt(2 dt) rang()
+static __global__ void k_langevin_update(double* __restrict__ fc, const cplx* __restrict__ forces, const unsigned char* __restrict__ is_cont, int M, int Ltrot,
+                                         uint64_t* __restrict__ rng, const cplx* __restrict__ phase, double delta_t, double max_force, double* __restrict__ dt_out, int n_chains) {
+  __shared__ double red[32];
+  const int chain = blockIdx.x; if (chain >= n_chains) return;
+  double* f = fc + (long)chain * Ltrot * M; const cplx* F = forces + (long)chain * Ltrot * M;
+  double xm = 0.0;
+  for (long e = threadIdx.x; e < (long)Ltrot * M; e += blockDim.x) { const int n = (int)(e % M); xm = fmax(xm, fabs(F[e].x)); if (is_cont[n]) xm = fmax(xm, fabs(f[e])); }
+  for (int o = 16; o > 0; o >>= 1) xm = fmax(xm, __shfl_xor_sync(0xffffffffu, xm, o));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = xm;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) xm = fmax(xm, red[w]);
+    double dt = delta_t; if (xm > max_force) dt = max_force * delta_t / xm;
+    dt_out[chain] = dt;
+    Xoshiro r; r.s0 = rng[chain * 4]; r.s1 = rng[chain * 4 + 1]; r.s2 = rng[chain * 4 + 2]; r.s3 = rng[chain * 4 + 3];
+    const cplx ph = phase[chain]; const double sq = sqrt(2.0 * dt);
+    for (int n = 0; n < M; ++n) if (is_cont[n]) for (int nt = 0; nt < Ltrot; ++nt) {
+      const long e = (long)nt * M + n;
+      const double f0 = f[e]; const cplx pf = ph * F[e]; const double fr = pf.x / ph.x;
+      const double ranmod = sqrt(-2.0 * log(r.ranf())); const double theta = 6.283185307179586476925286766559 * r.ranf();      // rang_wrap, random_wrap_mod.F90:144-157
+      f[e] = f0 - (f0 + fr) * dt + sq * (ranmod * cos(theta));
+    }
+    rng[chain * 4] = r.s0; rng[chain * 4 + 1] = r.s1; rng[chain * 4 + 2] = r.s2; rng[chain * 4 + 3] = r.s3;
+  }
+}
 // Compute_Fermion_Det (Prog/Global_mod.F90:792-1000), finite temperature: TP = U + V diag(D) with the scale separation of the STAB3 branch
 // (columns with D > 1 are divided by D and log D is put aside, :912-918); extra[b] = sum_{D_J > 1} log D_J
 template <typename T>
@@ -743,6 +789,48 @@ struct Engine : EngineBase {
     for (int NST = S - 1; NST >= 1; --NST) { wrapul_on(udvl, stab_nt[NST + 1], stab_nt[NST]); copy_udv(udvst[NST - 1], udvl); }
     wrapul_on(udvl, stab_nt[1], 0);
     cgr_and_phase(1, false);
+  }
+
+  // Langevin_HMC_Forces (Prog/Langevin_HMC_mod.F90:107-191, without its measurements): an upward pass without updates,
+  // G <- B(nt) G B(nt)^-1 slice by slice with the forces read off G, and the stabilisation of main.F90:731-755 against the stored udvst
+  // (which stays untouched here).  Needs the state init_sweep / a finished sweep leaves behind.  Forces on the device: [chain][nt][n] complex.
+  cplx* d_forces = nullptr; int* d_lf_site = nullptr; T* d_lf_coef = nullptr; double* d_lf_dt = nullptr;
+  void langevin_alloc() {
+    if (d_forces) return;
+    if (!h->d_fields_c) throw CudaError("Langevin updates need continuous fields (Op_V type 3)");
+    d_forces = dalloc<cplx>((size_t)C * L * M); d_lf_dt = dalloc<double>(C);
+    std::vector<int> site((size_t)M * F, 0); std::vector<T> coef((size_t)M * F * 2, zero_<T>());
+    for (int n = 0; n < M; ++n) for (int f = 0; f < F; ++f) { const HostOp& op = h->opv[n + (size_t)M * f];
+      site[(size_t)n * F + f] = op.P[0];
+      if (op.type == 3) { coef[((size_t)n * F + f) * 2] = to_T<T>(op.g * op.E[0]); coef[((size_t)n * F + f) * 2 + 1] = to_T<T>(op.g * op.alpha); } }      // O(1,1) = E(1) for N = 1
+    d_lf_site = dupload(site); d_lf_coef = dupload(coef);
+  }
+  void langevin_forces() {
+    langevin_alloc();
+    reset_udv(udvr, 'r');
+    int NST = 1;
+    for (int NTAU1 = 1; NTAU1 <= L; ++NTAU1) {
+      propr(G, NTAU1); proprm1(G, NTAU1);
+      KL(KC_OBS, st, k_langevin_forces<T><<<dim3((M + 127) / 128, C), 128, 0, st>>>(G, n2, N, F, h->n_sun, M, d_lf_site, d_lf_coef, d_is_cont, d_forces, L, NTAU1));
+      if (NTAU1 == stab_nt[NST]) {
+        wrapur_on(udvr, stab_nt[NST - 1], NTAU1);
+        copy_udv(udvl, udvst[NST - 1]);             // udvl = udvst(NST); the storage is intent(in) here
+        cgr_and_phase(NTAU1 > L / 2 ? 2 : 1, true);
+        NST++;
+      }
+    }
+  }
+  void langevin_get_forces(cd* out) override {
+    langevin_forces(); std::vector<cplx> b((size_t)C * L * M);
+    CK(cudaMemcpyAsync(b.data(), d_forces, sizeof(cplx) * b.size(), cudaMemcpyDeviceToHost, st)); sync();
+    for (size_t i = 0; i < b.size(); ++i) out[i] = cd(b[i].x, b[i].y);
+  }
+  void langevin_update(double delta_t, double max_force, double* dt_running_host) override {
+    langevin_forces();
+    KL(KC_UPDATE, st, k_langevin_update<<<C, 256, 0, st>>>(h->d_fields_c, d_forces, d_is_cont, M, L, h->d_rng, h->d_phase, delta_t, max_force, d_lf_dt, C));
+    init_sweep();                                   // Langevin_HMC_Reset_storage (:228-285)
+    if (dt_running_host) { CK(cudaMemcpyAsync(dt_running_host, d_lf_dt, sizeof(double) * C, cudaMemcpyDeviceToHost, st)); }
+    sync();
   }
 
   // Compute_Fermion_Det with storage = "Empty" (Prog/Global_mod.F90:792-1000): the left propagation is rebuilt from the current fields

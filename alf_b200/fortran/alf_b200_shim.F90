@@ -206,6 +206,17 @@ module alf_b200_shim
        integer(c_int), intent(in) :: move_start(*), move_fields(*), site_term_start(*), term_start(*), entry_op(*), entry_dt(*)
        real(c_double), intent(in) :: w(*)
      end function
+     integer(c_int) function alf_b200_langevin_update(h, delta_t, max_force, delta_t_running) bind(c, name="alf_b200_langevin_update")
+       import :: c_ptr, c_int, c_double
+       type(c_ptr), value :: h
+       real(c_double), value :: delta_t, max_force
+       real(c_double), intent(out) :: delta_t_running(*)
+     end function
+     integer(c_int) function alf_b200_langevin_forces(h, forces) bind(c, name="alf_b200_langevin_forces")
+       import :: c_ptr, c_int, c_double_complex
+       type(c_ptr), value :: h
+       complex(c_double_complex), intent(out) :: forces(*)
+     end function
      integer(c_int) function alf_b200_compute_fermion_det(h, log_abs_det, phase_det) bind(c, name="alf_b200_compute_fermion_det")
        import :: c_ptr, c_int, c_double, c_double_complex
        type(c_ptr), value :: h

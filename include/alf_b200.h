@@ -134,6 +134,17 @@ int alf_b200_get_obs_eq(alf_b200_handle* h, double* acc, double* bg, double* cnt
 int alf_b200_obs_tau_dims(const alf_b200_handle* h, int* n_channels, int* ntau, int* norb, int* n_unit);
 int alf_b200_get_obs_tau(alf_b200_handle* h, double* acc, double* bg, double* cnt);
 
+/* Langevin updates of continuous fields, Prog/Langevin_HMC_mod.F90 (scheme "Langevin"; single-site type-3 vertices, e.g. Hamiltonian_Hubbard with
+ * Continuous = .true.; the state must be the one alf_b200_init_sweep or a finished sweep leaves):
+ *  - alf_b200_langevin_forces: Langevin_HMC_Forces (:107-191, without its measurements) -> the fermionic forces dS_F/dphi of every chain,
+ *    complex [chain][nt][n]; GR, udvr, udvl and Phase advance as in the reference (upward pass with stabilisation, storage udvst untouched).
+ *  - alf_b200_langevin_update: Langevin_HMC_update (:355-392): forces, Forces_0 = dS_0/dphi = phi (Ham_Langevin_HMC_S0 of the Gaussian action,
+ *    Hamiltonian_Hubbard_smod.F90:896-915), Delta_t_running = delta_t, reduced to max_force * delta_t / max|force| when a force exceeds
+ *    max_force, phi -= (Forces_0 + Re(Phase F)/Re(Phase)) Delta_t_running - sqrt(2 Delta_t_running) rang() with rang_wrap's Box-Muller draws from
+ *    the chain's stream (n outer, nt inner), then Langevin_HMC_Reset_storage (:228-285).  delta_t_running [chain] may be NULL. */
+int alf_b200_langevin_forces(alf_b200_handle* h, double* forces /* complex n_chains*ltrot*n_opv */);
+int alf_b200_langevin_update(alf_b200_handle* h, double delta_t, double max_force, double* delta_t_running);
+
 /* Compute_Fermion_Det(Phase_det, Det_Vec, udvl, udvst, Stab_nt, storage = "Empty"), Prog/Global_mod.F90:792-1000 (what Global_Updates :450 and
  * the tempering exchange :108 weigh configurations with): rebuilds the left propagation from the CURRENT fields (udvl and the storage udvst
  * are overwritten as after main.F90:589-627; GR is not touched) and returns, per chain and flavor ([chain][nf]), log|det| = sum_I Det_Vec(I, nf)

@@ -911,6 +911,75 @@ struct Oracle {
     Phase = std::pow(ph, n_sun);
   }
 
+  // ---- Langevin updates of continuous fields: Prog/Langevin_HMC_mod.F90:107-226 (forces), :330-392 (scheme "Langevin"), :228-285 (reset storage)
+  double rang() { const double ranmod = std::sqrt(-2.0 * std::log(rng.ranf())); const double theta = 6.283185307179586476925286766559 * rng.ranf(); return ranmod * std::cos(theta); }   // random_wrap_mod.F90:144-157
+  void reset_storage() {      // Langevin_HMC_Reset_storage = main.F90:589-631 on allocated states
+    for (int nf = 0; nf < n_fl; ++nf) { reset_udv(udvl[nf], 'l', nf); reset_udv(st(nstm, nf), 'l', nf); }
+    for (int NST = nstm - 1; NST >= 1; --NST) { wrapul(stab_nt[NST + 1], stab_nt[NST], udvl); for (int nf = 0; nf < n_fl; ++nf) st(NST, nf) = udvl[nf]; }
+    wrapul(stab_nt[1], 0, udvl);
+    for (int nf = 0; nf < n_fl; ++nf) reset_udv(udvr[nf], 'r', nf);
+    cd ph = 1;
+    for (int nf = 0; nf < n_fl; ++nf) { cd Z; cgr(Z, 1, GR[nf].data(), udvr[nf], udvl[nf], stab3); op_phase(Z, nf); ph *= Z; }
+    Phase = std::pow(ph, n_sun);
+  }
+  void wrapgrup_forces(std::vector<cd>& Forces, int nt1) {      // :194-226
+    for (int nf = 0; nf < n_fl; ++nf) { mmthr(GR[nf].data(), ndim, ndim, nf); mmthl_m1(GR[nf].data(), ndim, ndim, nf); }
+    for (int n = 0; n < n_opv; ++n) {
+      Forces[n + (size_t)n_opv * (nt1 - 1)] = cd(0, 0);
+      for (int nf = 0; nf < n_fl; ++nf) { cd spin = fld(n, nt1); op_wrapup(GR[nf].data(), OpV(n, nf), spin, 1); op_wrapup(GR[nf].data(), OpV(n, nf), spin, 2); }
+      if (OpV(n, 0).type == 3) {
+        for (int nf = 0; nf < n_fl; ++nf) {
+          const Op& op = OpV(n, nf); const int k = op.N; cd Z(0, 0);
+          for (int I = 0; I < k; ++I) for (int J = 0; J < k; ++J) {
+            cd O(0, 0); for (int c = 0; c < k; ++c) O += op.U[I + (size_t)c * k] * op.E[c] * std::conj(op.U[J + (size_t)c * k]);      // O = U E U^dagger
+            const cd Z1 = (I == J) ? cd(1, 0) : cd(0, 0);
+            Z += O * (Z1 - GR[nf][op.P[J] + (size_t)op.P[I] * ndim]);
+          }
+          Z += op.alpha;
+          Forces[n + (size_t)n_opv * (nt1 - 1)] -= op.g * Z * (double)n_sun;
+        }
+      }
+    }
+  }
+  void langevin_forces(std::vector<cd>& Forces) {               // :107-191 without the measurements
+    Forces.assign((size_t)n_opv * ltrot, cd(0, 0));
+    for (int nf = 0; nf < n_fl; ++nf) reset_udv(udvr[nf], 'r', nf);
+    int NST = 1;
+    for (int NTAU = 0; NTAU <= ltrot - 1; ++NTAU) {
+      const int NTAU1 = NTAU + 1;
+      wrapgrup_forces(Forces, NTAU1);
+      if (NTAU1 == stab_nt[NST]) {
+        wrapur(stab_nt[NST - 1], NTAU1, udvr);
+        cd ph = 1; std::vector<cd> Test((size_t)ndim * ndim);
+        for (int nf = 0; nf < n_fl; ++nf) {
+          udvl[nf] = st(NST, nf);
+          int NVAR = 1; if (NTAU1 > ltrot / 2) NVAR = 2;
+          Test = GR[nf]; cd Z1; cgr(Z1, NVAR, GR[nf].data(), udvr[nf], udvl[nf], stab3);
+          control_precisionG(GR[nf].data(), Test.data()); op_phase(Z1, nf); ph *= Z1;
+        }
+        cd Z = std::pow(ph, n_sun); double X = std::abs(Z - Phase); if (X > ctl.XMAXP) ctl.XMAXP = X; Phase = Z;
+        NST++;
+      }
+    }
+  }
+  double langevin_update(double Delta_t, double Max_Force) {    // returns Delta_t_running
+    std::vector<cd> Forces; langevin_forces(Forces);
+    double Xmax = 0.0;
+    for (int n = 0; n < n_opv; ++n) for (int nt = 1; nt <= ltrot; ++nt) {
+      Xmax = std::max(Xmax, std::abs(Forces[n + (size_t)n_opv * (nt - 1)].real()));
+      const double f0 = (OpV(n, 0).type == 3) ? fld(n, nt).real() : 0.0;      // Ham_Langevin_HMC_S0, Hamiltonian_Hubbard_smod.F90:896-915
+      Xmax = std::max(Xmax, std::abs(f0));
+    }
+    double dt = Delta_t; if (Xmax > Max_Force) dt = Max_Force * Delta_t / Xmax;
+    for (int n = 0; n < n_opv; ++n) if (OpV(n, 0).type == 3) for (int nt = 1; nt <= ltrot; ++nt) {
+      const double f0 = fld(n, nt).real();
+      const double fr = (Phase * Forces[n + (size_t)n_opv * (nt - 1)]).real() / Phase.real();
+      fld(n, nt) = fld(n, nt) - cd((f0 + fr) * dt, 0.0) + cd(std::sqrt(2.0 * dt) * rang(), 0.0);
+    }
+    reset_storage();
+    return dt;
+  }
+
   std::vector<cd> eq_capture; int eq_capture_on = 0;   // G handed to ham%Obser: [visit][nf][N*N]
   bool obse_on = false; std::vector<cd> obse_acc, obse_bg; double obse_cnt[2] = {0, 0};      // equal-time lattice observables (lattice tables: obst_* below)
   double obs_scal[4] = {0, 0, 0, 0};   // [0] N_meas, [1] sum ZS, [2..3] sum Part ZP ZS  (same model-independent scalars as the device)
@@ -1202,6 +1271,11 @@ void orc_set_global_move_tau_ising(void* h, int n_sites, const int* move_start, 
 }
 long orc_get_gm_log(void* h, uint8_t* out, long cap) { Oracle* o = (Oracle*)h; long n = (long)o->gm_log.size(); for (long i = 0; i < n && i < cap; ++i) out[i] = o->gm_log[i]; return n; }
 double orc_global_move_s0(void* h, int site, int nt) { Oracle* o = (Oracle*)h; return o->ising_terms(o->gmt.terms, site - 1, nt); }
+void orc_langevin_forces(void* h, double* forces /* complex [nt][n] */) {
+  Oracle* o = (Oracle*)h; std::vector<cd> F; o->langevin_forces(F);
+  for (size_t i = 0; i < F.size(); ++i) { forces[2 * i] = F[i].real(); forces[2 * i + 1] = F[i].imag(); }
+}
+double orc_langevin_update(void* h, double delta_t, double max_force) { return ((Oracle*)h)->langevin_update(delta_t, max_force); }
 void orc_compute_fermion_det(void* h, double* phase_det /* complex n_fl */, double* det_vec /* ndim*n_fl */) {
   Oracle* o = (Oracle*)h; std::vector<cd> ph; std::vector<double> dv; o->compute_fermion_det(ph, dv);
   for (int nf = 0; nf < o->n_fl; ++nf) { phase_det[2 * nf] = ph[nf].real(); phase_det[2 * nf + 1] = ph[nf].imag(); }

@@ -33,6 +33,7 @@ def lib():
         _lib.orc_create.restype = C.c_void_p
         _lib.orc_ranf.restype = C.c_double
         _lib.orc_s0.restype = C.c_double
+        _lib.orc_langevin_update.restype = C.c_double
         _lib.orc_global_move_s0.restype = C.c_double
         _lib.orc_get_gm_log.restype = C.c_long
         _lib.orc_get_log.restype = C.c_long
@@ -116,6 +117,16 @@ class Oracle:
         out = np.zeros(max(n, 1), dtype=np.uint8)
         lib().orc_get_gm_log(self.h, out.ctypes.data_as(C.POINTER(C.c_uint8)), n)
         return out[:n]
+
+    def langevin_forces(self):
+        """Langevin_HMC_Forces (Prog/Langevin_HMC_mod.F90:107): fermionic forces [nt, n] (complex) of the current configuration."""
+        F = np.zeros((self.m.Ltrot, self.m.n_opv), dtype=np.complex128)
+        lib().orc_langevin_forces(self.h, _d(F))
+        return F
+
+    def langevin_update(self, delta_t, max_force):
+        """One update of scheme "Langevin" (Prog/Langevin_HMC_mod.F90:355-392); returns Delta_t_running."""
+        return lib().orc_langevin_update(self.h, C.c_double(delta_t), C.c_double(max_force))
 
     def compute_fermion_det(self):
         """Compute_Fermion_Det (Prog/Global_mod.F90:792), storage = "Empty": (Phase_det [nf], Det_Vec [nf, ndim])."""

@@ -936,3 +936,33 @@ def test_compute_fermion_det(variant):
         o.sweep(0)
         assert np.array_equal(f[c], o.get_fields())
     g.close()
+
+
+@pytest.mark.parametrize("mz", [True, False])
+def test_langevin_forces_and_update(mz):
+    """Langevin scheme for continuous fields (Prog/Langevin_HMC_mod.F90): the fermionic forces of every chain equal the oracle's (which are checked
+    against a finite difference of log det in the CPU suite), and three Langevin updates -- adaptive step, Box-Muller noise from the chain's
+    stream, storage reset -- leave the same fields (to rounding), the same random-number state, G and phase."""
+    m = hubbard_square(4, 4, 1.0, Mz=mz, continuous=True)
+    seeds = SEEDS[:3]
+    g = AlfB200(m, n_chains=len(seeds), nwrap=5); g.set_seeds(seeds); g.fields_set(); g.init_sweep(); g.sweep(1, 0)
+    F = g.langevin_forces()
+    orcs = []
+    for c, s in enumerate(seeds):
+        o = Oracle(m, nwrap=5); o.ranset(s); o.fields_set(); o.init(); o.sweep(0); orcs.append(o)
+        Fo = o.langevin_forces()
+        assert np.abs(F[c] - Fo).max() < 1e-9 * max(1.0, np.abs(Fo).max()) and np.abs(Fo).max() > 1e-2
+    for it in range(3):
+        dt = g.langevin_update(0.02, 0.4)             # max_force small enough to make the step adaptive
+        for c, o in enumerate(orcs):
+            dto = o.langevin_update(0.02, 0.4)
+            assert abs(dt[c] - dto) < 1e-9 * dto
+    assert (dt < 0.02).any()
+    f = g.get_fields(); rs = g.rng_state(); ph = g.phase()
+    for c, o in enumerate(orcs):
+        assert np.abs(f[c] - o.get_fields()).max() < 1e-8
+        assert np.array_equal(rs[c], o.rng_state())
+        for nf in range(1, m.N_FL + 1):
+            assert relF(g.green(c, nf), o.green(nf)) < 1e-7      # G of slightly different fields (forces agree to 1e-9)
+        assert abs(ph[c] - o.phase()) < 1e-6
+    g.close()
