@@ -227,6 +227,12 @@ class AlfB200:
         self._ck(lib().alf_b200_langevin_update(self.h, C.c_double(delta_t), C.c_double(max_force), _d(dt)))
         return dt
 
+    def hmc_update(self, delta_t, leapfrog_steps):
+        """One update of scheme "HMC" (Prog/Langevin_HMC_mod.F90:393-571) for every chain; returns (accepted [chain] bool, Weight [chain])."""
+        w = np.zeros(self.C); acc = np.zeros(self.C, dtype=np.uint8)
+        self._ck(lib().alf_b200_hmc_update(self.h, C.c_double(delta_t), int(leapfrog_steps), _d(w), acc.ctypes.data_as(C.POINTER(C.c_uint8))))
+        return acc.astype(bool), w
+
     def compute_fermion_det(self):
         """Compute_Fermion_Det (Prog/Global_mod.F90:792) with storage = "Empty": (log|det| [chain, nf], phase [chain, nf]) of the current fields."""
         ld = np.zeros((self.C, self.m.N_FL)); ph = np.zeros((self.C, self.m.N_FL), dtype=np.complex128)

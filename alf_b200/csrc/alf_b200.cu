@@ -289,6 +289,12 @@ int alf_b200_langevin_update(alf_b200_handle* h, double delta_t, double max_forc
   h->eng->langevin_update(delta_t, max_force, delta_t_running);
   API_END(h)
 }
+int alf_b200_hmc_update(alf_b200_handle* h, double delta_t, int leapfrog_steps, double* weight, uint8_t* accepted) {
+  API_BEGIN(h) NEED_FINAL(h)
+  if (!(delta_t > 0.0) || leapfrog_steps < 1) return ALF_ERROR_GENERIC;
+  h->eng->hmc_update(delta_t, leapfrog_steps, weight, accepted);
+  API_END(h)
+}
 int alf_b200_compute_fermion_det(alf_b200_handle* h, double* log_abs_det, double* phase_det) {
   API_BEGIN(h) NEED_FINAL(h)
   if (!log_abs_det || !phase_det) return ALF_ERROR_GENERIC;

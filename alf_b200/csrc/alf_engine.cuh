@@ -134,6 +134,7 @@ struct EngineBase {
   virtual void fermion_det(double* logdet, cd* phase) = 0;
   virtual void langevin_get_forces(cd* out) = 0;
   virtual void langevin_update(double delta_t, double max_force, double* dt_running) = 0;
+  virtual void hmc_update(double delta_t, int leapfrog_steps, double* weight, unsigned char* acc) = 0;
   virtual void sync() = 0;
 };
 
@@ -298,6 +299,66 @@ static __global__ void k_langevin_update(double* __restrict__ fc, const cplx* __
     }
     rng[chain * 4] = r.s0; rng[chain * 4 + 1] = r.s1; rng[chain * 4 + 2] = r.s2; rng[chain * 4 + 3] = r.s3;
   }
+}
+// Scheme "HMC" (Prog/Langevin_HMC_mod.F90:393-571): momenta p(n, nt) = rang_wrap() drawn nt outer / n inner (:429-434), kinetic energy
+static __global__ void k_hmc_momenta(double* __restrict__ p, uint64_t* __restrict__ rng, int M, int Ltrot, double* __restrict__ ekin, int n_chains) {
+  const int chain = blockIdx.x * blockDim.x + threadIdx.x; if (chain >= n_chains) return;
+  Xoshiro r; r.s0 = rng[chain * 4]; r.s1 = rng[chain * 4 + 1]; r.s2 = rng[chain * 4 + 2]; r.s3 = rng[chain * 4 + 3];
+  double* pc = p + (long)chain * Ltrot * M; double e = 0.0;
+  for (long q = 0; q < (long)Ltrot * M; ++q) { const double ranmod = sqrt(-2.0 * log(r.ranf())); const double theta = 6.283185307179586476925286766559 * r.ranf();
+    const double x = ranmod * cos(theta); pc[q] = x; e += 0.5 * x * x; }
+  ekin[chain] = e;
+  rng[chain * 4] = r.s0; rng[chain * 4 + 1] = r.s1; rng[chain * 4 + 2] = r.s2; rng[chain * 4 + 3] = r.s3;
+}
+// p -= x dt (Forces_0 + Re(Phase F)/Re(Phase)), Forces_0 = phi (Gaussian action)      (:436-440, :476-484)
+static __global__ void k_hmc_kick(double* __restrict__ p, const double* __restrict__ fc, const cplx* __restrict__ forces, const cplx* __restrict__ phase, double xdt, long per_chain, int n_chains) {
+  const int chain = blockIdx.y; const cplx ph = phase[chain];
+  for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < per_chain; e += (long)gridDim.x * blockDim.x) {
+    const long q = (long)chain * per_chain + e; const cplx pf = ph * forces[q];
+    p[q] -= xdt * (fc[q] + pf.x / ph.x);
+  }
+}
+static __global__ void k_hmc_drift(double* __restrict__ fc, const double* __restrict__ p, double dt, long n) {      // nsigma%f += dt p (:447-449)
+  for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long)gridDim.x * blockDim.x) fc[e] += dt * p[e];
+}
+// Compute_Ratio_Global (Prog/Global_mod.F90:651-760) with the Gaussian Get_Delta_S0_global, Weight, Metropolis test, restore on rejection (:516-563).
+// ga[n][f] = N_SUN g alpha (complex).  One CTA per chain.
+static __global__ void k_hmc_decide(double* __restrict__ fc, const double* __restrict__ fc_old, const double* __restrict__ p, const double* __restrict__ ekin_old,
+                                    const double* __restrict__ ld_old, const cplx* __restrict__ pd_old, const double* __restrict__ ld_new, const cplx* __restrict__ pd_new,
+                                    const cplx* __restrict__ ga, const cplx* __restrict__ phase_old, int F, int n_sun, int M, int Ltrot, uint64_t* __restrict__ rng,
+                                    double* __restrict__ weight_out, unsigned char* __restrict__ acc_out) {
+  __shared__ double red[4][8]; __shared__ int s_acc;
+  const int chain = blockIdx.x, tid = threadIdx.x; const long per = (long)Ltrot * M;
+  double* f = fc + chain * per; const double* fo = fc_old + chain * per; const double* pc = p + chain * per;
+  double ek = 0.0, ds = 0.0, zr = 0.0, zi = 0.0;      // E_kin_new, sum(new^2 - old^2), sum_{n,nt,f} dphi N_SUN g alpha
+  for (long e = tid; e < per; e += blockDim.x) {
+    const int n = (int)(e % M); const double a = f[e], b = fo[e], d = a - b;
+    ek += 0.5 * pc[e] * pc[e]; ds += a * a - b * b;
+    for (int ff = 0; ff < F; ++ff) { const cplx g = ga[n * F + ff]; zr += d * g.x; zi += d * g.y; }
+  }
+  ek = warp_sum(ek); ds = warp_sum(ds); zr = warp_sum(zr); zi = warp_sum(zi);
+  if ((tid & 31) == 0) { red[0][tid >> 5] = ek; red[1][tid >> 5] = ds; red[2][tid >> 5] = zr; red[3][tid >> 5] = zi; }
+  __syncthreads();
+  if (tid == 0) {
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) { ek += red[0][w]; ds += red[1][w]; zr += red[2][w]; zi += red[3][w]; }
+    double r2 = 0.0; cplx r1 = cplx(1.0, 0.0);
+    for (int ff = 0; ff < F; ++ff) {
+      r2 += (double)n_sun * (ld_new[chain * F + ff] - ld_old[chain * F + ff]);
+      const cplx q = pd_new[chain * F + ff] * conj_(pd_old[chain * F + ff]);      // unit-modulus phases: ratio = new * conj(old)
+      cplx qn = q; for (int k = 1; k < n_sun; ++k) qn = qn * q;
+      r1 = r1 * qn;
+    }
+    const double em = exp(zr); r1 = r1 * cplx(em * cos(zi), em * sin(zi));
+    r2 += -0.5 * ds + (-ek + ekin_old[chain]);
+    const cplx rt = r1 * exp(r2); const cplx ph = phase_old[chain]; const cplx pr = ph * rt;
+    const double weight = fabs(pr.x / ph.x);
+    Xoshiro r; r.s0 = rng[chain * 4]; r.s1 = rng[chain * 4 + 1]; r.s2 = rng[chain * 4 + 2]; r.s3 = rng[chain * 4 + 3];
+    const int acc = (weight > r.ranf()) ? 1 : 0;
+    rng[chain * 4] = r.s0; rng[chain * 4 + 1] = r.s1; rng[chain * 4 + 2] = r.s2; rng[chain * 4 + 3] = r.s3;
+    s_acc = acc; if (weight_out) weight_out[chain] = weight; if (acc_out) acc_out[chain] = (unsigned char)acc;
+  }
+  __syncthreads();
+  if (!s_acc) for (long e = tid; e < per; e += blockDim.x) f[e] = fo[e];
 }
 // Compute_Fermion_Det (Prog/Global_mod.F90:792-1000), finite temperature: TP = U + V diag(D) with the scale separation of the STAB3 branch
 // (columns with D > 1 are divided by D and log D is put aside, :912-918); extra[b] = sum_{D_J > 1} log D_J
@@ -820,6 +881,41 @@ struct Engine : EngineBase {
       }
     }
   }
+  // Scheme "HMC" (Prog/Langevin_HMC_mod.F90:393-571), L_Forces = .false., Apply_B_HMC = identity: leapfrog trajectory of all chains, then per chain the
+  // Metropolis test on Compute_Ratio_Global and the restore of rejected configurations; ends with Langevin_HMC_Reset_storage.
+  double *d_hmc_p = nullptr, *d_hmc_fold = nullptr, *d_hmc_ek = nullptr, *d_hmc_ld[2] = {nullptr, nullptr}, *d_hmc_w = nullptr; cplx *d_hmc_pd[2] = {nullptr, nullptr}, *d_hmc_ga = nullptr, *d_hmc_ph = nullptr;
+  unsigned char* d_hmc_acc = nullptr;
+  void hmc_update(double delta_t, int leapfrog_steps, double* weight_host, unsigned char* acc_host) override {
+    langevin_alloc();
+    for (int n = 0; n < M; ++n) if (h->opv[n].type != 3) throw CudaError("HMC moves every field: all vertices must carry continuous (type 3) fields");
+    const long per = (long)L * M, tot = per * C;
+    if (!d_hmc_p) {
+      d_hmc_p = dalloc<double>(tot); d_hmc_fold = dalloc<double>(tot); d_hmc_ek = dalloc<double>(C); d_hmc_w = dalloc<double>(C); d_hmc_acc = dalloc<unsigned char>(C); d_hmc_ph = dalloc<cplx>(C);
+      for (int q = 0; q < 2; ++q) { d_hmc_ld[q] = dalloc<double>(NM); d_hmc_pd[q] = dalloc<cplx>(NM); }
+      std::vector<cplx> ga((size_t)M * F); for (int n = 0; n < M; ++n) for (int f = 0; f < F; ++f) { const HostOp& op = h->opv[n + (size_t)M * f]; const cd z = (double)h->n_sun * op.g * op.alpha; ga[(size_t)n * F + f] = cplx(z.real(), z.imag()); }
+      d_hmc_ga = dupload(ga);
+    }
+    fermion_det_dev(d_hmc_ld[0], d_hmc_pd[0]);
+    CK(cudaMemcpyAsync(d_hmc_fold, h->d_fields_c, sizeof(double) * tot, cudaMemcpyDeviceToDevice, st)); CK(cudaMemcpyAsync(d_hmc_ph, h->d_phase, sizeof(cplx) * C, cudaMemcpyDeviceToDevice, st));
+    langevin_forces();
+    KL(KC_UPDATE, st, k_hmc_momenta<<<(C + 31) / 32, 32, 0, st>>>(d_hmc_p, h->d_rng, M, L, d_hmc_ek, C));
+    dim3 eg(ew_blocks(per), C);
+    KL(KC_EW, st, k_hmc_kick<<<eg, 256, 0, st>>>(d_hmc_p, h->d_fields_c, d_forces, h->d_phase, 0.5 * delta_t, per, C));
+    for (int t = 1; t <= leapfrog_steps; ++t) {
+      KL(KC_EW, st, k_hmc_drift<<<ew_blocks(tot), 256, 0, st>>>(h->d_fields_c, d_hmc_p, delta_t, tot));
+      init_sweep();
+      const bool last = t == leapfrog_steps;
+      if (last) fermion_det_dev(d_hmc_ld[1], d_hmc_pd[1]);
+      langevin_forces();
+      KL(KC_EW, st, k_hmc_kick<<<eg, 256, 0, st>>>(d_hmc_p, h->d_fields_c, d_forces, h->d_phase, (last ? 0.5 : 1.0) * delta_t, per, C));
+    }
+    KL(KC_UPDATE, st, k_hmc_decide<<<C, 256, 0, st>>>(h->d_fields_c, d_hmc_fold, d_hmc_p, d_hmc_ek, d_hmc_ld[0], d_hmc_pd[0], d_hmc_ld[1], d_hmc_pd[1], d_hmc_ga, d_hmc_ph,
+                                                      F, h->n_sun, M, L, h->d_rng, d_hmc_w, d_hmc_acc));
+    init_sweep();
+    if (weight_host) CK(cudaMemcpyAsync(weight_host, d_hmc_w, sizeof(double) * C, cudaMemcpyDeviceToHost, st));
+    if (acc_host) CK(cudaMemcpyAsync(acc_host, d_hmc_acc, C, cudaMemcpyDeviceToHost, st));
+    sync();
+  }
   void langevin_get_forces(cd* out) override {
     langevin_forces(); std::vector<cplx> b((size_t)C * L * M);
     CK(cudaMemcpyAsync(b.data(), d_forces, sizeof(cplx) * b.size(), cudaMemcpyDeviceToHost, st)); sync();
@@ -839,8 +935,16 @@ struct Engine : EngineBase {
   // of which only the sum enters Compute_Ratio_Global (:700-760) -- here the sum comes from the pivoted QR.  Projector: sum of the log D of all
   // stored decompositions + log|det(U_L^H P_R)| (:846-884).
   void fermion_det(double* logdet_host, cd* phase_host) override {
+    double* d_ld = dalloc_tmp<double>(NM); cplx* d_ph = dalloc_tmp<cplx>(NM);
+    fermion_det_dev(d_ld, d_ph);
+    std::vector<cplx> ph(NM);
+    CK(cudaMemcpyAsync(logdet_host, d_ld, sizeof(double) * NM, cudaMemcpyDeviceToHost, st)); CK(cudaMemcpyAsync(ph.data(), d_ph, sizeof(cplx) * NM, cudaMemcpyDeviceToHost, st)); sync();
+    for (int b = 0; b < NM; ++b) phase_host[b] = cd(ph[b].x, ph[b].y);
+    cudaFree(d_ld); cudaFree(d_ph);
+  }
+  void fermion_det_dev(double* d_ld, cplx* d_ph) {
     reset_udv(udvl, 'l'); reset_udv(udvst[S - 1], 'l');
-    double* d_extra = dalloc_tmp<double>(NM); double* d_ld = dalloc_tmp<double>(NM); cplx* d_ph = dalloc_tmp<cplx>(NM);
+    double* d_extra = dalloc_tmp<double>(NM);
     CK(cudaMemsetAsync(d_extra, 0, sizeof(double) * NM, st));
     for (int NST = S - 1; NST >= 1; --NST) { wrapul_on(udvl, stab_nt[NST + 1], stab_nt[NST]); copy_udv(udvst[NST - 1], udvl);
       if (proj) KL(KC_EW, st, k_fdet_addlog<<<(NM + 127) / 128, 128, 0, st>>>(udvl.D, N, NP, d_extra, NM)); }
@@ -857,10 +961,7 @@ struct Engine : EngineBase {
       la_qrp<T>(w, w.W[0], N, N, w.Dq);
       KL(KC_EW, st, k_fdet_finish<<<(NM + 127) / 128, 128, 0, st>>>(w.Dq, N, w.qrout, d_extra, udvl.det, d_ld, d_ph, NM));
     }
-    std::vector<cplx> ph(NM);
-    CK(cudaMemcpyAsync(logdet_host, d_ld, sizeof(double) * NM, cudaMemcpyDeviceToHost, st)); CK(cudaMemcpyAsync(ph.data(), d_ph, sizeof(cplx) * NM, cudaMemcpyDeviceToHost, st)); sync();
-    for (int b = 0; b < NM; ++b) phase_host[b] = cd(ph[b].x, ph[b].y);
-    cudaFree(d_extra); cudaFree(d_ld); cudaFree(d_ph);
+    sync(); cudaFree(d_extra);
   }
   template <typename X> X* dalloc_tmp(size_t n) { X* p = nullptr; CK(cudaMalloc(&p, sizeof(X) * (n ? n : 1))); return p; }
 

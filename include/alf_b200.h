@@ -142,6 +142,11 @@ int alf_b200_get_obs_tau(alf_b200_handle* h, double* acc, double* bg, double* cn
  *    Hamiltonian_Hubbard_smod.F90:896-915), Delta_t_running = delta_t, reduced to max_force * delta_t / max|force| when a force exceeds
  *    max_force, phi -= (Forces_0 + Re(Phase F)/Re(Phase)) Delta_t_running - sqrt(2 Delta_t_running) rang() with rang_wrap's Box-Muller draws from
  *    the chain's stream (n outer, nt inner), then Langevin_HMC_Reset_storage (:228-285).  delta_t_running [chain] may be NULL. */
+/*  - alf_b200_hmc_update: scheme "HMC" (:393-571) with L_Forces = .false. and the base Apply_B_HMC (identity): momenta from rang_wrap (nt outer, n inner),
+ *    Leapfrog_Steps leapfrog steps (storage reset + force pass each), Compute_Fermion_Det before and after, Compute_Ratio_Global
+ *    (Prog/Global_mod.F90:651-760) with the Gaussian Get_Delta_S0_global, Weight > ranf per chain, rejected chains restored, storage reset.
+ *    All vertices must carry type-3 fields.  weight [chain], accepted [chain] may be NULL. */
+int alf_b200_hmc_update(alf_b200_handle* h, double delta_t, int leapfrog_steps, double* weight, uint8_t* accepted);
 int alf_b200_langevin_forces(alf_b200_handle* h, double* forces /* complex n_chains*ltrot*n_opv */);
 int alf_b200_langevin_update(alf_b200_handle* h, double delta_t, double max_force, double* delta_t_running);
 

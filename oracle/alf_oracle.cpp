@@ -980,6 +980,54 @@ struct Oracle {
     return dt;
   }
 
+  // Scheme "HMC" (Prog/Langevin_HMC_mod.F90:393-571) with L_Forces = .false. (sequential runs, main.F90:683), Apply_B_HMC = identity (base),
+  // Compute_Ratio_Global (Prog/Global_mod.F90:651-760) with the Gaussian Get_Delta_S0_global (Hamiltonian_Hubbard_smod.F90:932-958).
+  // All fields must be continuous (the momenta move every field).  Returns the acceptance.
+  bool hmc_update(double Delta_t, int Leapfrog_Steps, double* weight_out) {
+    std::vector<cd> Phase_det_old, Phase_det_new; std::vector<double> Det_old, Det_new;
+    compute_fermion_det(Phase_det_old, Det_old);                   // storage "Full" in the reference: the same numbers from the existing storage
+    const std::vector<cd> f_old = f; const cd Phase_old = Phase;
+    std::vector<cd> Forces; langevin_forces(Forces);
+    const size_t nf_tot = (size_t)n_opv * ltrot; std::vector<double> p(nf_tot), F0(nf_tot);
+    double E_kin_old = 0.0;
+    for (int j = 0; j < ltrot; ++j) for (int i = 0; i < n_opv; ++i) { const double x = rang(); p[i + (size_t)n_opv * j] = x; E_kin_old += 0.5 * x * x; }
+    auto total_force = [&]() { for (int j = 0; j < ltrot; ++j) for (int i = 0; i < n_opv; ++i) { const size_t e = i + (size_t)n_opv * j;
+      F0[e] = ((OpV(i, 0).type == 3) ? f[e].real() : 0.0) + (Phase * Forces[e]).real() / Phase.real(); } };
+    total_force();
+    for (size_t e = 0; e < nf_tot; ++e) p[e] -= 0.5 * Delta_t * F0[e];
+    for (int t_leap = 1; t_leap <= Leapfrog_Steps; ++t_leap) {
+      for (size_t e = 0; e < nf_tot; ++e) f[e] += cd(Delta_t * p[e], 0.0);
+      reset_storage();
+      double X = 1.0;
+      if (t_leap == Leapfrog_Steps) { compute_fermion_det(Phase_det_new, Det_new); X = 0.5; }
+      langevin_forces(Forces); total_force();
+      for (size_t e = 0; e < nf_tot; ++e) p[e] -= X * Delta_t * F0[e];
+    }
+    double E_kin_new = 0.0; for (size_t e = 0; e < nf_tot; ++e) E_kin_new += 0.5 * p[e] * p[e];
+    const double log_T0 = -E_kin_new + E_kin_old;
+    // Compute_Ratio_Global
+    cd Ratio1(1, 0); double Ratio2 = 0.0;
+    for (int nf = 0; nf < n_fl; ++nf) {
+      double r2 = 0.0; for (int I = 0; I < ndim; ++I) r2 += Det_new[I + (size_t)ndim * nf] - Det_old[I + (size_t)ndim * nf];
+      Ratio2 += (double)n_sun * r2;
+      cd r1 = std::pow(Phase_det_new[nf] / Phase_det_old[nf], (double)n_sun);
+      for (int i = 0; i < n_opv; ++i) for (int nt = 1; nt <= ltrot; ++nt) {
+        const cd Z = ft.phi(OpV(i, nf).type, fld(i, nt)) - ft.phi(OpV(i, nf).type, f_old[i + (size_t)n_opv * (nt - 1)]);
+        r1 *= std::exp(Z * (double)n_sun * OpV(i, nf).g * OpV(i, nf).alpha);
+      }
+      Ratio1 *= r1;
+    }
+    double S0_old = 0.0, S0_new = 0.0; for (size_t e = 0; e < nf_tot; ++e) { S0_old += f_old[e].real() * f_old[e].real(); S0_new += f[e].real() * f[e].real(); }
+    Ratio2 += (-0.5 * S0_new + 0.5 * S0_old) + log_T0;
+    const cd Ratiotot = Ratio1 * std::exp(Ratio2);
+    const double Weight = std::abs((Phase_old * Ratiotot).real() / Phase_old.real());
+    if (weight_out) *weight_out = Weight;
+    const bool toggle = Weight > rng.ranf();
+    if (!toggle) f = f_old;
+    reset_storage();
+    return toggle;
+  }
+
   std::vector<cd> eq_capture; int eq_capture_on = 0;   // G handed to ham%Obser: [visit][nf][N*N]
   bool obse_on = false; std::vector<cd> obse_acc, obse_bg; double obse_cnt[2] = {0, 0};      // equal-time lattice observables (lattice tables: obst_* below)
   double obs_scal[4] = {0, 0, 0, 0};   // [0] N_meas, [1] sum ZS, [2..3] sum Part ZP ZS  (same model-independent scalars as the device)
@@ -1276,6 +1324,7 @@ void orc_langevin_forces(void* h, double* forces /* complex [nt][n] */) {
   for (size_t i = 0; i < F.size(); ++i) { forces[2 * i] = F[i].real(); forces[2 * i + 1] = F[i].imag(); }
 }
 double orc_langevin_update(void* h, double delta_t, double max_force) { return ((Oracle*)h)->langevin_update(delta_t, max_force); }
+int orc_hmc_update(void* h, double delta_t, int leapfrog_steps, double* weight) { return ((Oracle*)h)->hmc_update(delta_t, leapfrog_steps, weight) ? 1 : 0; }
 void orc_compute_fermion_det(void* h, double* phase_det /* complex n_fl */, double* det_vec /* ndim*n_fl */) {
   Oracle* o = (Oracle*)h; std::vector<cd> ph; std::vector<double> dv; o->compute_fermion_det(ph, dv);
   for (int nf = 0; nf < o->n_fl; ++nf) { phase_det[2 * nf] = ph[nf].real(); phase_det[2 * nf + 1] = ph[nf].imag(); }

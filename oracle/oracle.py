@@ -128,6 +128,12 @@ class Oracle:
         """One update of scheme "Langevin" (Prog/Langevin_HMC_mod.F90:355-392); returns Delta_t_running."""
         return lib().orc_langevin_update(self.h, C.c_double(delta_t), C.c_double(max_force))
 
+    def hmc_update(self, delta_t, leapfrog_steps):
+        """One update of scheme "HMC" (Prog/Langevin_HMC_mod.F90:393-571); returns (accepted, Weight)."""
+        w = C.c_double(0.0)
+        acc = lib().orc_hmc_update(self.h, C.c_double(delta_t), int(leapfrog_steps), C.byref(w))
+        return bool(acc), w.value
+
     def compute_fermion_det(self):
         """Compute_Fermion_Det (Prog/Global_mod.F90:792), storage = "Empty": (Phase_det [nf], Det_Vec [nf, ndim])."""
         ph = np.zeros(self.m.N_FL, dtype=np.complex128); dv = np.zeros((self.m.N_FL, self.N))

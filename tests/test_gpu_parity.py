@@ -966,3 +966,34 @@ def test_langevin_forces_and_update(mz):
             assert relF(g.green(c, nf), o.green(nf)) < 1e-7      # G of slightly different fields (forces agree to 1e-9)
         assert abs(ph[c] - o.phase()) < 1e-6
     g.close()
+
+
+@pytest.mark.parametrize("mz", [True, False])
+def test_hmc_update(mz):
+    """Scheme "HMC" (Prog/Langevin_HMC_mod.F90:393-571): leapfrog trajectories of all chains on the device, Compute_Fermion_Det before and after,
+    Compute_Ratio_Global, Metropolis test per chain.  Weight, acceptance, fields (to rounding), random-number state, G and phase follow the oracle;
+    a small step conserves the Hamiltonian (Weight ~ 1), a large one does not."""
+    m = hubbard_square(4, 4, 1.0, Mz=mz, continuous=True)
+    seeds = SEEDS[:3]
+    g = AlfB200(m, n_chains=len(seeds), nwrap=5); g.set_seeds(seeds); g.fields_set(); g.init_sweep(); g.sweep(1, 0)
+    orcs = []
+    for s in seeds:
+        o = Oracle(m, nwrap=5); o.ranset(s); o.fields_set(); o.init(); o.sweep(0); orcs.append(o)
+    for (dt, nl) in ((0.02, 5), (0.6, 2), (0.1, 3)):
+        acc, w = g.hmc_update(dt, nl)
+        for c, o in enumerate(orcs):
+            acco, wo = o.hmc_update(dt, nl)
+            assert abs(w[c] - wo) < 1e-6 * max(1.0, wo), (dt, nl, w[c], wo)
+            assert bool(acc[c]) == acco
+        if dt == 0.02:
+            assert np.all(np.abs(w - 1.0) < 5e-3)
+        if dt == 0.6:
+            assert np.any(np.abs(w - 1.0) > 5e-2)
+    f = g.get_fields(); rs = g.rng_state(); ph = g.phase()
+    for c, o in enumerate(orcs):
+        assert np.abs(f[c] - o.get_fields()).max() < 1e-7
+        assert np.array_equal(rs[c], o.rng_state())
+        for nf in range(1, m.N_FL + 1):
+            assert relF(g.green(c, nf), o.green(nf)) < 1e-6
+        assert abs(ph[c] - o.phase()) < 1e-6
+    g.close()

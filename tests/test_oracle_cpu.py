@@ -432,3 +432,17 @@ def test_langevin_forces_are_the_gradient_of_the_fermion_action():
         fp, fm = f.copy(), f.copy(); fp[nt, n] += eps; fm[nt, n] -= eps
         fd = -(logdet(fp) - logdet(fm)) / (2 * eps)
         assert abs(fd - F[nt, n].real) < 1e-6 * max(1.0, abs(fd)), (nt, n, fd, F[nt, n])
+
+
+def test_hmc_conserves_the_hamiltonian_to_second_order():
+    """Scheme "HMC" (Prog/Langevin_HMC_mod.F90:393-571) in the oracle: the Metropolis weight exp(-Delta H) of a leapfrog trajectory of fixed length tends to 1
+    like dt^2 -- forces (Langevin_HMC_Forces), determinants (Compute_Fermion_Det), Gaussian action and phase factors (Compute_Ratio_Global) are
+    mutually consistent.  Same random momenta for every step size."""
+    from alf_b200.model import hubbard_square
+    m = hubbard_square(4, 2, 0.6, Mz=False, continuous=True)
+    errs = []
+    for dt, nl in ((0.1, 2), (0.05, 4), (0.025, 8)):
+        o = Oracle(m, nwrap=3); o.ranset(99); o.fields_set(); o.init(); o.sweep(0)
+        acc, w = o.hmc_update(dt, nl)
+        errs.append(abs(np.log(w)))
+    assert errs[0] < 0.2 and errs[1] < 0.4 * errs[0] and errs[2] < 0.4 * errs[1], errs
