@@ -718,7 +718,7 @@ struct Engine : EngineBase {
     if (!Mout) Mout = Mx;                          // in place unless a result buffer is given (full matrices only)
     const ModelDev& md = mdo ? *mdo : this->md;
     dim3 grid((nvec + OPS_PW - 1) / OPS_PW, NM);
-#define OPS_LAUNCH(SD, LKV) KL(KC_OPS, st, k_apply_ops<T, SD, LKV><<<grid, 256, ops_smem, st>>>(Mx, n2, N, nvec, md, F, mode, nt_a, nt_b, h->d_fields, L, M, Mout))
+#define OPS_LAUNCH(SD, LKV) KL(KC_OPS, st, k_apply_ops<T, SD, LKV><<<grid, OPS_NT, ops_smem, st>>>(Mx, n2, N, nvec, md, F, mode, nt_a, nt_b, h->d_fields, L, M, Mout))
     if (side == 0) { if (ops_lk == 0) OPS_LAUNCH(0, 0); else if (ops_lk == 1) OPS_LAUNCH(0, 1); else OPS_LAUNCH(0, 2); }
     else { if (ops_lk == 0) OPS_LAUNCH(1, 0); else if (ops_lk == 1) OPS_LAUNCH(1, 1); else OPS_LAUNCH(1, 2); }
 #undef OPS_LAUNCH

@@ -59,6 +59,7 @@ struct ModelDev {
 //    one block-wide barrier per chunk.
 #define OPS_CH 64            // operators per chunk
 #define OPS_PW 32            // panel width = warp size
+#define OPS_NT 256           // threads per CTA (8 warps, three CTAs per SM at N = 256; measured: 512 threads and 128-operator chunks are both slower)
 
 // Shared-memory descriptor of one operator: x = (k << 28) | element offset of row P[0] in the panel, y, z, w = offsets of P[1..3];
 // its k x k matrix sits in dM[o << 2 LK] with leading dimension 1 << LK.
@@ -127,11 +128,11 @@ __device__ __forceinline__ void ops_process_chunk(T* __restrict__ S, bool lane_o
 // SIDE 1: panel of OPS_PW rows    [v0, v0+pw) of M;  S[i][j] = M(v0+j, i)   (right multiplication = left on the transpose)
 // grid = (ceil(nvec/OPS_PW), n_matrices); matrix b belongs to chain b / F, flavor b % F.  LK = log2 of the largest operator size.
 template <typename T, int SIDE, int LK>
-__global__ void __launch_bounds__(256) k_apply_ops(T* M, long sM, int N, int nvec, ModelDev md, int F, int mode,
+__global__ void __launch_bounds__(OPS_NT) k_apply_ops(T* M, long sM, int N, int nvec, ModelDev md, int F, int mode,
                                                    int nt_a, int nt_b, const int8_t* __restrict__ fields, int Ltrot, int n_opv, T* Mout) {   // Mout: result buffer (may be M)
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int ldp = OPS_PW + 1, ms = 1 << (2 * LK), kk = 1 << LK;
-  constexpr int MPT = (OPS_CH * ms + 255) / 256;       // descriptor-matrix entries prefetched per thread
+  constexpr int MPT = (OPS_CH * ms + OPS_NT - 1) / OPS_NT;       // descriptor-matrix entries prefetched per thread
   T* S = reinterpret_cast<T*>(smem_raw);
   T* dMb = S + ((N * ldp + 1) & ~1);                  // keeps the int4 descriptor arrays 16-byte aligned
   int4* dPb = reinterpret_cast<int4*>(dMb + 2 * OPS_CH * ms);
@@ -188,7 +189,7 @@ __global__ void __launch_bounds__(256) k_apply_ops(T* M, long sM, int N, int nve
     const T* mats = reinterpret_cast<const T*>(L.mat);
 #pragma unroll
     for (int u = 0; u < MPT; ++u) {
-      const int e = tid + u * 256;
+      const int e = tid + u * OPS_NT;
       if (e < m_cnt * ms) {
         const int o = e >> (2 * LK), rr = e & (ms - 1), a = rr & (kk - 1), bb = rr >> LK, og = m_a0 + o;
         int var = 0;
@@ -206,7 +207,7 @@ __global__ void __launch_bounds__(256) k_apply_ops(T* M, long sM, int N, int nve
   auto commit = [&](const Pref& pf, int buf) {
     if (tid < pf.rcnt) dPb[buf * OPS_CH + tid] = pf.rP;
 #pragma unroll
-    for (int u = 0; u < MPT; ++u) { const int e = tid + u * 256; if (e < pf.rcnt * ms) dMb[buf * OPS_CH * ms + e] = pf.rM[u]; }
+    for (int u = 0; u < MPT; ++u) { const int e = tid + u * OPS_NT; if (e < pf.rcnt * ms) dMb[buf * OPS_CH * ms + e] = pf.rM[u]; }
   };
   meta_load();
   if (total > 0) { data_issue(pf0); meta_load(); }
