@@ -350,6 +350,107 @@ __global__ void __launch_bounds__(512) k_qrp(T* __restrict__ A, int m, int n, in
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------------------
+// Small matrices (m, n <= 64; BASELINE config 2: N_dim = 64): the warp-per-column kernels above spend their time in shuffle reductions
+// over two rows per lane.  Here ONE THREAD OWNS ONE COLUMN (staged in shared memory with an odd leading dimension, so the lanes of a
+// warp hit different banks and the reflector is a broadcast): dot products and norms are serial per thread, no shuffles, 64 threads
+// per matrix, several matrices per SM.  Same outputs as k_qrp.  Columns never move: the pivoting is a permutation table.  (The same layout was
+// tried for the explicit Q and measured slower than k_formq, whose reflector applications have no pivot search in between.)
+// ------------------------------------------------------------------------------------------------------------------------
+template <typename T, int PIVOT>
+__global__ void __launch_bounds__(64) k_qrp_small(T* __restrict__ A, int m, int n, int ld, long sA, T* __restrict__ tau, long sTau,
+                                                  int* __restrict__ jpvt, long sP, double* __restrict__ D, long sD, QrOut* __restrict__ out) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int b = blockIdx.x, c = threadIdx.x, lane = c & 31;
+  A += (long)b * sA; tau += (long)b * sTau; jpvt += (long)b * sP; D += (long)b * sD;
+  const int lds = m | 1;
+  T* As = reinterpret_cast<T*>(smem_raw);          // column c at As + c * lds
+  T* v_s = As + (long)lds * 64;                    // reflector
+  double* key_s = reinterpret_cast<double*>(v_s + 64);     // [2] per-warp best norm
+  int* pos_s = reinterpret_cast<int*>(key_s + 2);  // [2] per-warp best position; then sto_at[64] (storage column at position), then scalars
+  int* sto_at = pos_s + 2;
+  __shared__ T s_tau; __shared__ int s_piv_sto;
+  for (int e = c; e < m * n; e += 64) { const int i = e % m, cc = e / m; As[i + (long)cc * lds] = A[i + (long)cc * ld]; }
+  if (c < n) sto_at[c] = c;
+  __syncthreads();
+  T* col = As + (long)c * lds;
+  int mypos = c;                                   // position of my column in the permuted matrix
+  bool done = c >= n;                              // columns already turned into reflectors
+  double vn = 0.0;
+  if (c < n) { for (int i = 0; i < m; ++i) vn += abs2_(col[i]); vn = sqrt(vn); }
+  cplx detq = cplx(1.0, 0.0);
+  const int kmax = (m < n) ? m : n;
+  for (int j = 0; j < kmax; ++j) {
+    // ---- pivot: largest partial norm among the remaining columns, lowest position on ties (ZGEQP3's IDAMAX over positions j..n-1)
+    if (PIVOT) {
+      double best = done ? -1.0 : vn; int bp = done ? (1 << 30) : mypos;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const double ob = __shfl_xor_sync(0xffffffffu, best, o); const int op = __shfl_xor_sync(0xffffffffu, bp, o);
+        if (ob > best || (ob == best && op < bp)) { best = ob; bp = op; }
+      }
+      if (lane == 0) { key_s[c >> 5] = best; pos_s[c >> 5] = bp; }
+      __syncthreads();
+      const double b0 = key_s[0], b1 = key_s[1]; const int p0 = pos_s[0], p1 = pos_s[1];
+      const int pp = (b1 > b0 || (b1 == b0 && p1 < p0)) ? p1 : p0;       // position of the pivot column
+      // swap positions j and pp
+      const int sj = sto_at[j], sp = sto_at[pp];
+      __syncthreads();
+      if (c == sp) mypos = j; else if (c == sj) mypos = pp;
+      if (c == 0) { sto_at[j] = sp; sto_at[pp] = sj; }
+      if (c == sp) s_piv_sto = sp;
+    } else if (c == 0) s_piv_sto = j;
+    __syncthreads();
+    const int ps = s_piv_sto;
+    // ---- reflector from the pivot column (ZLARFG, no safmin rescaling loop): its owner works alone
+    if (c == ps) {
+      double xn2 = 0.0; for (int i = j + 1; i < m; ++i) xn2 += abs2_(col[i]);
+      const T alpha = col[j]; T tj, scal; double beta;
+      if (xn2 == 0.0 && imag_(alpha) == 0.0) { tj = zero_<T>(); scal = zero_<T>(); beta = real_(alpha); }
+      else { beta = -copysign(sqrt(abs2_(alpha) + xn2), real_(alpha)); tj = make_<T>((beta - real_(alpha)) / beta, -imag_(alpha) / beta); scal = one_<T>() / (alpha - make_<T>(beta, 0.0)); }
+      v_s[j] = one_<T>();
+      for (int i = j + 1; i < m; ++i) { const T y = col[i] * scal; col[i] = y; v_s[i] = y; }
+      col[j] = make_<T>(beta, 0.0); s_tau = tj; tau[j] = tj;
+      done = true;
+    }
+    __syncthreads();
+    const T tj = s_tau;
+    if (abs2_(tj) != 0.0) {      // det(H_j) = 1 - 2 (tau/|tau|) (Re tau/|tau|)   (Prog/cgr1_mod.F90:338-347); every thread keeps the same product
+      const double X = abs_(tj); const cplx z = cplx(real_(tj) / X, imag_(tj) / X);
+      const cplx d = cplx(1.0, 0.0) - 2.0 * (real_(tj) / X) * z; const double ad = abs_(d); detq = detq * cplx(d.x / ad, d.y / ad);
+    }
+    // ---- apply H_j^H to my column and refresh its partial norm
+    if (!done) {
+      if (abs2_(tj) != 0.0) {
+        const T tauc = conj_(tj);
+        T w = zero_<T>(); for (int i = j; i < m; ++i) fmac_(w, v_s[i], col[i]);
+        const T sc = tauc * w; double nrm = 0.0;
+        for (int i = j; i < m; ++i) { const T y = col[i] - v_s[i] * sc; col[i] = y; if (i > j) nrm += abs2_(y); }
+        vn = sqrt(nrm);
+      } else if (PIVOT) { double nrm = 0.0; for (int i = j + 1; i < m; ++i) nrm += abs2_(col[i]); vn = sqrt(nrm); }
+    }
+    __syncthreads();
+  }
+  // ---- outputs: columns in position order, D(i) = |R(i,i)|, R(i, i:) /= D(i), jpvt, phases
+  if (c < kmax) { const double x = abs_(As[c + (long)sto_at[c] * lds]); D[c] = x; key_s[0] = 0.0; reinterpret_cast<double*>(v_s)[c] = x; }
+  __syncthreads();
+  const double* dd = reinterpret_cast<const double*>(v_s);
+  if (c < n) {
+    T* dst = A + (long)mypos * ld;
+    for (int i = 0; i < m; ++i) { T y = col[i]; if (i <= mypos && i < kmax) y = y * (1.0 / dd[i]); dst[i] = y; }
+    jpvt[mypos] = c;
+  }
+  __syncthreads();
+  if (c == 0) {
+    cplx ph = cplx(1.0, 0.0);
+    for (int i = 0; i < kmax; ++i) { const T r = As[i + (long)sto_at[i] * lds] * (1.0 / dd[i]); ph = ph * cplx(real_(r), imag_(r)); }
+    double sg = 1.0; unsigned long long seen = 0ull;        // permutation parity: cycles of even length flip the sign (n <= 64)
+    for (int i = 0; i < n; ++i) if (!((seen >> i) & 1ull)) { int next = i, L = 0; while (!((seen >> next) & 1ull)) { ++L; seen |= 1ull << next; next = sto_at[next]; } if ((L & 1) == 0) sg = -sg; }
+    out[b].perm_sign = sg; out[b].diag_phase = ph; out[b].detq = detq;
+  }
+}
+static size_t qrp_small_smem(size_t elem, int m) { return elem * ((size_t)(m | 1) * 64 + 64) + 2 * sizeof(double) + (2 + 64) * sizeof(int) + 64; }
+
 // Explicit Q (m x n, n reflectors) in place of the reflectors, backward accumulation (ZUNG2R order).
 // Optionally scales column 0 by `colscale[b]` afterwards (udv_state_mod.F90:578).
 template <typename T, int MAXR, int STAGE>

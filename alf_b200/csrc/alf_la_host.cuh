@@ -117,6 +117,12 @@ static void launch_qrp(cudaStream_t st, T* A, int m, int n, int ld, long sA, T* 
     k_qrp<T, MAXR, PIVOT, STG><<<batch, 512, smem, st>>>(A, m, n, ld, sA, tau, sTau, jpvt, sP, D, sD, out); } while (0)
 #define QRP_DISPATCH(MAXR) do { if (do_stage) QRP_LAUNCH(MAXR, 1); else QRP_LAUNCH(MAXR, 0); } while (0)
   count_flops(KC_QRP, flop_scale<T>() * (2.0 * m * n * n - 2.0 * n * n * n / 3.0) * batch);
+  if (m <= 64 && n <= 64 && n <= m && !getenv("ALF_B200_NO_SMALL_QR")) {      // thread-per-column kernel, several matrices per SM
+    const size_t sm = qrp_small_smem(sizeof(T), m);
+    CK(alf_raise_smem(k_qrp_small<T, PIVOT>));
+    KL(KC_QRP, st, k_qrp_small<T, PIVOT><<<batch, 64, sm, st>>>(A, m, n, ld, sA, tau, sTau, jpvt, sP, D, sD, out));
+    return;
+  }
   { KScope ks_(KC_QRP, st);
   if (m <= 64) QRP_DISPATCH(2); else if (m <= 128) QRP_DISPATCH(4); else if (m <= 288) QRP_DISPATCH(9); else if (m <= 576) QRP_DISPATCH(18);
   else throw CudaError("k_qrp: matrices with more than 576 rows are not supported in this build");
