@@ -19,3 +19,8 @@ os.environ["ALF_B200_NO_STAGE_G"] = "1"
 model = z2_matter_square(4, 4, 0.3); g = AlfB200(model, n_chains=2, nwrap=2); g.set_seeds([5, 6]); g.fields_set(); g.init_sweep(); g.sweep(1, 0); print("z2 unstaged", g.control()["XMAXG"]); g.close()
 del os.environ["ALF_B200_NO_STAGE_G"]
 A = rng.normal(size=(2, 24, 9)) + 1j * rng.normal(size=(2, 24, 9)); api.udv_wrap_pivot(A, True); api.udv_wrap_pivot(rng.normal(size=(1, 256, 256)), False); print("udv_wrap_pivot ok")
+# Compute_Fermion_Det, Langevin forces / update, HMC on continuous fields (Mz real and SU(2) complex)
+for mz in (True, False):
+    model = hubbard_square(4, 4, 0.4, Mz=mz, continuous=True)
+    g = AlfB200(model, n_chains=2, nwrap=2); g.set_seeds([5, 6]); g.fields_set(); g.init_sweep()
+    ld, ph = g.compute_fermion_det(); g.langevin_update(0.02, 1.5); acc, w = g.hmc_update(0.05, 2); print("det / langevin / hmc", ld[0], w); g.close()
