@@ -276,7 +276,7 @@ class AlfB200:
     def control(self):
         out = np.zeros(16)
         self._ck(lib().alf_b200_get_control(self.h, _d(out)))
-        keys = ["XMEANG", "XMAXG", "NCG", "XMAXP", "XMEAN_tau", "XMAX_tau", "NCG_tau", "NC_up", "ACC_up", "NC_eff_up", "ACC_eff_up", "nan", "unstable"]
+        keys = ["XMEANG", "XMAXG", "NCG", "XMAXP", "XMEAN_tau", "XMAX_tau", "NCG_tau", "NC_up", "ACC_up", "NC_eff_up", "ACC_eff_up", "nan", "unstable", "flushes"]
         return dict(zip(keys, out))
 
     def accept_log(self, n_sweeps=1):

@@ -79,10 +79,12 @@ def fourier_r_to_k(x_r, latt):
     return (phase @ np.asarray(x_r, dtype=np.complex128)) / latt.N, kv
 
 
-def print_bin_latt(name, obs_sum, bg_sum, sign_sum, n_meas_per_chain, n_chains, latt, dtau=None, channel="---"):
+def print_bin_latt(name, obs_sum, bg_sum, sign_sum, n_meas_per_chain, n_chains, latt, dtau=None, channel="---", n_coord=2, orb_pos=None):
     """Print_bin_Latt (Prog/observables_mod.F90:355-515), text layout (:494-512): appends one bin to `<name>_tau` (or `<name>_eq` if
     there is a single time point).  obs_sum[nt, no, no1, r]: real-space accumulator summed over chains (Obs_Latt(imj, nt, no, no1));
-    bg_sum[no]: Obs_Latt0 summed over chains and time points; n_meas_per_chain = Obs%N."""
+    bg_sum[no]: Obs_Latt0 summed over chains and time points; n_meas_per_chain = Obs%N.  n_coord, orb_pos[no][:] = Latt_unit%N_coord and
+    Latt_unit%Orb_pos_p (Prog/Predefined_Latt_mod.F90:117-237; default: square lattice, one orbital at the origin): they go into the
+    `_info` file (:457-491) in exactly the order Analysis/ana_mod.F90:285-309 reads them back."""
     obs_sum = np.asarray(obs_sum, dtype=np.complex128); ntau, norb, _, ns = obs_sum.shape
     assert ns == latt.N
     suffix = "_eq" if ntau == 1 else "_tau"
@@ -92,14 +94,20 @@ def print_bin_latt(name, obs_sum, bg_sum, sign_sum, n_meas_per_chain, n_chains, 
     bg = np.asarray(bg_sum, dtype=np.complex128) / (norm * ns * ntau)  # Obs_Latt0 / (N Ns Ntau)
     ave_sign = float(sign_sum) / norm
     info = file_pr + "_info"
+    if orb_pos is None:
+        orb_pos = np.zeros((norb, 2))
+    orb_pos = np.asarray(orb_pos, dtype=np.float64).reshape(norb, -1)
     if not os.path.exists(info):
-        with open(info, "w") as f:
+        with open(info, "w") as f:           # formats 11-15 of observables_mod.F90:462-466
             f.write(f"{'Observable':>20s}: {os.path.basename(file_pr)}\n{'Channel':>20s}: {channel}\n{'Ntau':>20s}: {ntau:10d}\n")
             f.write(f"{'dtau':>20s}: " + _e(dtau or 0.0, 26) + "\n       ====== Bravais Lattice ======\n")
             f.write(f"{'Unit cells':>20s}: {latt.N:10d}\n{'L1':>20s}: " + _e(float(latt.L1), 26) + _e(0.0, 26) + "\n")
             f.write(f"{'L2':>20s}: " + _e(0.0, 26) + _e(float(latt.L2), 26) + "\n")
             f.write(f"{'a1':>20s}: " + _e(1.0, 26) + _e(0.0, 26) + f"\n{'a2':>20s}: " + _e(0.0, 26) + _e(1.0, 26) + "\n")
-            f.write("       ========= Unit cell =========\n" + f"{'Number of orbitals':>20s}: {norb:10d}\n")
+            f.write("       ========= Unit cell =========\n")
+            f.write(f"{'Coordination number':>20s}: {int(n_coord):10d}\n{'Number of orbitals':>20s}: {norb:10d}\n{'Ndim':>20s}: {orb_pos.shape[1]:10d}\n")
+            for no in range(norb):
+                f.write(f"{'Orbital %d' % (no + 1):>20s}: " + "".join(_e(x, 26) for x in orb_pos[no]) + "\n")
     lines = []
     if ntau == 1:
         lines.append(_e(ave_sign, 25) + f"{norb:11d}{latt.N:11d}")
@@ -146,3 +154,31 @@ def read_latt(file_pr):
                         obs[i, nt, no, no1] = cplx(toks[pos]); pos += 1
         bins.append((sign, np.array(bg), ks, obs))
     return bins
+
+
+def read_latt_info(file_pr):
+    """The read sequence of Analysis/ana_mod.F90:285-309 on `<file>_info`, line by line with its formats 11-13 (A22 label, then the value):
+    returns (channel, ntau, dtau, n_unit, L1_p, L2_p, a1_p, a2_p, n_coord, norb, orb_pos[norb, ndim_unit])."""
+    with open(file_pr + "_info") as f:
+        ln = f.read().split("\n")
+    it = iter(ln)
+
+    def a22(line):
+        return line[22:]
+
+    def reals(line):
+        body = a22(line); return [float(body[i:i + 26]) for i in range(0, len(body.rstrip()), 26)]
+    next(it)                                             # read(10, *)
+    channel = a22(next(it)).strip()
+    ntau = int(a22(next(it))[:10])
+    dtau = reals(next(it))[0]
+    next(it)
+    n_unit = int(a22(next(it))[:10])
+    L1_p = reals(next(it)); L2_p = reals(next(it)); a1_p = reals(next(it)); a2_p = reals(next(it))
+    next(it)
+    n_coord = int(a22(next(it))[:10]); norb = int(a22(next(it))[:10]); ndim_unit = int(a22(next(it))[:10])
+    orb = np.zeros((norb, ndim_unit))
+    for no in range(norb):
+        v = reals(next(it)); assert len(v) == ndim_unit
+        orb[no] = v
+    return channel, ntau, dtau, n_unit, L1_p, L2_p, a1_p, a2_p, n_coord, norb, orb

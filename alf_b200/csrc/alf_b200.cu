@@ -181,7 +181,7 @@ int alf_b200_finalize_model(alf_b200_handle* h) {
   CK(cudaMalloc(&h->d_fields, (size_t)C * h->ltrot * std::max(1, h->n_opv))); CK(cudaMemset(h->d_fields, 1, (size_t)C * h->ltrot * std::max(1, h->n_opv)));
   if (has_cont) { const size_t nf = (size_t)C * h->ltrot * h->n_opv; std::vector<double> one(nf, 1.0); CK(cudaMalloc(&h->d_fields_c, sizeof(double) * nf)); CK(cudaMemcpy(h->d_fields_c, one.data(), sizeof(double) * nf, cudaMemcpyHostToDevice)); }
   CK(cudaMalloc(&h->d_rng, sizeof(uint64_t) * 4 * C)); CK(cudaMalloc(&h->d_phase, sizeof(cplx) * C));
-  CK(cudaMalloc(&h->d_counters, sizeof(unsigned long long) * 4 * C)); CK(cudaMemset(h->d_counters, 0, sizeof(unsigned long long) * 4 * C));
+  CK(cudaMalloc(&h->d_counters, sizeof(unsigned long long) * 5 * C)); CK(cudaMemset(h->d_counters, 0, sizeof(unsigned long long) * 5 * C));   // [chain][4] control counters, then [chain] flushes
   CK(cudaMalloc(&h->d_ctl, sizeof(double) * 8 * C)); CK(cudaMemset(h->d_ctl, 0, sizeof(double) * 8 * C));
   h->obs_size = 16; CK(cudaMalloc(&h->d_obs, sizeof(double) * h->obs_size)); CK(cudaMemset(h->d_obs, 0, sizeof(double) * h->obs_size));
   { std::vector<int32_t> z(C, 0); int32_t* d; CK(cudaMalloc(&d, sizeof(int32_t) * C)); CK(cudaMemcpy(d, z.data(), sizeof(int32_t) * C, cudaMemcpyHostToDevice));
@@ -323,6 +323,7 @@ int alf_b200_obs_tau_enable(alf_b200_handle* h, int on) {
   API_BEGIN(h) NEED_FINAL(h)
   if (on && !h->d_obst_acc) {
     if (h->n_unit <= 0) { h->err = "obs_tau_enable: call alf_b200_set_lattice first"; return ALF_ERROR_GENERIC; }
+    if (h->n_fl > 2) { h->err = "obs_tau_enable: the device-side lattice observables support N_FL <= 2 (keep ham%ObserT on the host for more flavors)"; return ALF_ERROR_UNSUPPORTED; }
     h->obst_ntau = h->projector ? h->ltrot - 2 * h->thtrot + 1 : h->ltrot + 1;          // Ltau + 1 time points (Hubbard_smod.F90:628,666)
     CK(cudaMalloc(&h->d_obst_acc, sizeof(double) * obst_acc_len(h))); CK(cudaMalloc(&h->d_obst_bg, sizeof(double) * obst_bg_len(h))); CK(cudaMalloc(&h->d_obst_cnt, sizeof(double) * 2));
     CK(cudaMemsetAsync(h->d_obst_acc, 0, sizeof(double) * obst_acc_len(h), h->stream)); CK(cudaMemsetAsync(h->d_obst_bg, 0, sizeof(double) * obst_bg_len(h), h->stream));
@@ -337,6 +338,7 @@ int alf_b200_obs_eq_enable(alf_b200_handle* h, int on) {
   API_BEGIN(h) NEED_FINAL(h)
   if (on && !h->d_obse_acc) {
     if (h->n_unit <= 0) { h->err = "obs_eq_enable: call alf_b200_set_lattice first"; return ALF_ERROR_GENERIC; }
+    if (h->n_fl > 2) { h->err = "obs_eq_enable: the device-side lattice observables support N_FL <= 2 (keep ham%Obser on the host for more flavors)"; return ALF_ERROR_UNSUPPORTED; }
     const size_t na = (size_t)2 * OBST_NCH * h->norb * h->norb * h->n_unit, nb = (size_t)2 * 2 * h->norb;
     CK(cudaMalloc(&h->d_obse_acc, sizeof(double) * na)); CK(cudaMalloc(&h->d_obse_bg, sizeof(double) * nb)); CK(cudaMalloc(&h->d_obse_cnt, sizeof(double) * 2));
     CK(cudaMemsetAsync(h->d_obse_acc, 0, sizeof(double) * na, h->stream)); CK(cudaMemsetAsync(h->d_obse_bg, 0, sizeof(double) * nb, h->stream));
@@ -419,15 +421,16 @@ int alf_b200_get_udv(alf_b200_handle* h, int which, int nst, int chain, int nf, 
 }
 int alf_b200_get_control(alf_b200_handle* h, double* out) {
   API_BEGIN(h) NEED_FINAL(h)
-  const int C = h->n_chains; std::vector<double> c((size_t)C * 8); std::vector<unsigned long long> k((size_t)C * 4);
+  const int C = h->n_chains; std::vector<double> c((size_t)C * 8); std::vector<unsigned long long> k((size_t)C * 5);
   CK(cudaStreamSynchronize(h->stream));
-  CK(cudaMemcpy(c.data(), h->d_ctl, sizeof(double) * 8 * C, cudaMemcpyDeviceToHost)); CK(cudaMemcpy(k.data(), h->d_counters, sizeof(unsigned long long) * 4 * C, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(c.data(), h->d_ctl, sizeof(double) * 8 * C, cudaMemcpyDeviceToHost)); CK(cudaMemcpy(k.data(), h->d_counters, sizeof(unsigned long long) * 5 * C, cudaMemcpyDeviceToHost));
   for (int i = 0; i < 16; ++i) out[i] = 0.0;
   for (int ch = 0; ch < C; ++ch) {   // the reductions of Control_Print (control_mod.F90:397-452): SUM for counters/means, MAX for maxima
     out[0] += c[ch * 8 + 0]; out[1] = std::max(out[1], c[ch * 8 + 1]); out[2] += c[ch * 8 + 2]; out[3] = std::max(out[3], c[ch * 8 + 3]);
     out[4] += c[ch * 8 + 4]; out[5] = std::max(out[5], c[ch * 8 + 5]); out[6] += c[ch * 8 + 6];
     out[7] += (double)k[ch * 4 + 0]; out[8] += (double)k[ch * 4 + 1]; out[9] += (double)k[ch * 4 + 2]; out[10] += (double)k[ch * 4 + 3];
     int fl = (int)c[ch * 8 + 7]; if (fl & 1) out[11] = 1.0; if (fl & 2) out[12] = 1.0;
+    out[13] += (double)k[(size_t)4 * C + ch];
   }
   API_END(h)
 }

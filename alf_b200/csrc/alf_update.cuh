@@ -202,7 +202,7 @@ __global__ void __launch_bounds__(512, 1) k_wrapgr(T* __restrict__ G, int N, int
   int8_t* fld = fields + ((long)chain * Ltrot + (nt - 1)) * n_opv;
   double* fc = fields_c ? fields_c + ((long)chain * Ltrot + (nt - 1)) * n_opv : nullptr;      // continuous fields (type 3) of this slice
   for (int e = tid; e < F * N; e += nthr) { dl[e] = one_<T>(); dr[e] = one_<T>(); int f = e / N, i = e % N; gdiag[e] = Gc[f * sG + i + (long)i * ldg]; }
-  Xoshiro r; cplx ph; unsigned long long n_acc = 0, n_prop = 0;
+  Xoshiro r; cplx ph; unsigned long long n_acc = 0, n_prop = 0, n_flush = 1;
   if (tid == 0) { r.s0 = rng[chain * 4 + 0]; r.s1 = rng[chain * 4 + 1]; r.s2 = rng[chain * 4 + 2]; r.s3 = rng[chain * 4 + 3]; ph = phase[chain]; }
   int nd = 0;
   __syncthreads();
@@ -378,7 +378,7 @@ __global__ void __launch_bounds__(512, 1) k_wrapgr(T* __restrict__ G, int N, int
         if (nd == KD) {
           for (int f = 0; f < F; ++f)
             flush_flavor<T>(Gc + f * sG, N, ldg, Xs + (long)f * KD * ldx, Ys + (long)f * KD * ldx, ldx, nd, dl + f * N, dr + f * N);
-          nd = 0;
+          nd = 0; n_flush++;
           __syncthreads();
           for (int e = tid; e < F * N; e += nthr) { int f = e / N, i = e % N; gdiag[e] = Gc[f * sG + i + (long)i * ldg]; }
           __syncthreads();
@@ -431,5 +431,6 @@ __global__ void __launch_bounds__(512, 1) k_wrapgr(T* __restrict__ G, int N, int
     counters[chain * 4 + 1] += n_acc;    // ACC_up
     counters[chain * 4 + 2] += (unsigned long long)cnt;     // NC_eff_up
     counters[chain * 4 + 3] += n_acc;    // ACC_eff_up
+    if (!stage_g) counters[4 * (long)gridDim.x + chain] += n_flush;   // rewrites of G0 in global memory (measurement support)
   }
 }

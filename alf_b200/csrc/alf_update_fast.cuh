@@ -256,7 +256,7 @@ __global__ void __launch_bounds__(512, 1) k_wrapgr_fast(T* __restrict__ G, int N
   __syncthreads();
 
   cplx ph = phase[chain];
-  unsigned long long n_acc = 0;
+  unsigned long long n_acc = 0, n_flush = 0;
   int nd = 0;
   int flush_rev = (nt + (UP ? 0 : 1)) & 1;      // alternate the tile order between consecutive flushes (also across slices)
 
@@ -272,7 +272,7 @@ __global__ void __launch_bounds__(512, 1) k_wrapgr_fast(T* __restrict__ G, int N
       flush_g0(Gc + (long)f * N * N, N, Xs + (long)f * KD * ldx, Ys + (long)f * KD * ldx, ldx, nd4, dl + f * N, dr + f * N, flush_rev);
     }
     flush_rev ^= 1;
-    nd = 0;
+    nd = 0; n_flush++;
     __syncthreads();
   };
 
@@ -473,5 +473,6 @@ __global__ void __launch_bounds__(512, 1) k_wrapgr_fast(T* __restrict__ G, int N
     counters[chain * 4 + 1] += n_acc;                   // ACC_up
     counters[chain * 4 + 2] += (unsigned long long)cnt; // NC_eff_up
     counters[chain * 4 + 3] += n_acc;                   // ACC_eff_up
+    counters[4 * (long)gridDim.x + chain] += n_flush;   // rank-KD rewrites of G0 (measurement support: algorithmic HBM bytes of this kernel)
   }
 }

@@ -180,6 +180,9 @@ class Model:
     site_cell: Optional[np.ndarray] = None
     site_orb: Optional[np.ndarray] = None
     n_orb: int = 1
+    # Latt_unit%N_coord and Latt_unit%Orb_pos_p (Prog/Predefined_Latt_mod.F90:117-237); they only enter the `_info` files of the lattice bins
+    n_coord: int = 2
+    orb_pos: Optional[np.ndarray] = None
 
     def lattice_tables(self):
         """(n_unit, n_orb, site_cell, site_orb, imj) as the C-ABI's alf_b200_set_lattice wants them (all 1-based)."""
@@ -437,6 +440,7 @@ def kondo_square(L1: int, L2: int, beta: float, dtau: float = 0.1, t: float = 1.
     m = Model(name="Kondo", Ndim=Ndim, N_FL=1, N_SUN=N_SUN, Ltrot=Ltrot, Dtau=dtau, Symm=symm, Op_V=Op_V, Op_T=Op_T, latt=latt,
               params=dict(L1=L1, L2=L2, beta=beta, dtau=dtau, t=t, J=J, Uf=Uf, symm=symm))
     m.n_orb = 2
+    m.n_coord = 2; m.orb_pos = np.array([[0.0, 0.0, 0.0], [0.0, 0.0, -1.0]])      # Bilayer_square: Orb_pos_p(no, 3) = 1 - no
     m.site_cell = np.repeat(np.arange(1, Nc + 1, dtype=np.int32), 2)
     m.site_orb = np.tile(np.array([1, 2], dtype=np.int32), Nc)
     return m

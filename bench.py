@@ -104,8 +104,10 @@ class ClockSampler:
 # ----------------------------------------------------------------------------------------------- CPU arm
 def cpu_sample(workload, ltau, cores, seconds_target, steps, warmup):
     """Times the oracle (one independent chain per host thread, OPENBLAS_NUM_THREADS=1 as Documentation/running.tex:352
-    advises) on a bounded sample: `seg` consecutive stabilisation intervals of the sweep per step (a sweep has 2*NSTM
-    (+NSTM with TAU_M) of them, equal in cost).  Returns per-step seconds and the sample description."""
+    advises).  A step is ONE WHOLE SWEEP of every chain when (steps + warmup) sweeps fit the time target (config 3: about 15-25 s per
+    sweep); otherwise a step is a bounded sample: the first `seg` of the sweep's `nseg` stabilisation intervals (they must run in order),
+    and the rate is extrapolated by seg / nseg (the intervals of the up pass, the down pass and TAU_M differ in cost, so the
+    extrapolation is only approximate -- the line says so).  Returns per-step seconds, seg, nseg and the oracle's precision monitors."""
     os.environ.setdefault("OPENBLAS_NUM_THREADS", "1")
     from oracle.oracle import Oracle
     model, nwrap, _ = make_model(workload)
@@ -126,14 +128,43 @@ def cpu_sample(workload, ltau, cores, seconds_target, steps, warmup):
             for i in range(lo, lo + k):
                 o.sweep_segment(i % nseg, ltau)
         par(work); pos[0] = lo + k
-    t0 = time.perf_counter(); run_segments(1); t_seg = time.perf_counter() - t0        # calibration (also a warm-up)
-    seg = max(1, min(nseg, int(seconds_target / max(t_seg, 1e-6) / max(1, steps + warmup))))
+    t0 = time.perf_counter(); run_segments(1); t_seg = time.perf_counter() - t0        # calibration on the first interval of the up pass (also a warm-up)
+    # TAU_M intervals cost about 3x an up/down interval (CGR2_2 on the 2N x 2N system): estimate of a whole sweep from the calibration
+    est_sweep = t_seg * (nseg if not ltau else 2 * nseg / 3 + 3 * nseg / 3)
+    if est_sweep * (steps + warmup + 1) <= seconds_target:
+        run_segments(nseg - 1)                                                        # finish the calibration sweep
+        seg = nseg
+    else:
+        seg = max(1, min(nseg, int(seconds_target / max(t_seg, 1e-6) / max(1, steps + warmup))))
+        if seg < nseg:
+            pos[0] = 0                                                                # samples restart at the first interval (intervals run in order)
+            for o in orcs:
+                o.init()
     for _ in range(warmup):
         run_segments(seg)
+        if seg < nseg:
+            pos[0] = 0
     times = []
     for _ in range(steps):
+        if seg < nseg:
+            pos[0] = 0
         t0 = time.perf_counter(); run_segments(seg); times.append(time.perf_counter() - t0)
-    return times, seg, nseg
+    prec = None
+    try:
+        cs = [o.control() for o in orcs]
+        prec = {"green_max": max(c["XMAXG"] for c in cs), "green_mean": sum(c["XMEANG"] for c in cs) / max(1.0, sum(c["NCG"] for c in cs)),
+                "tau_max": max(c["XMAX_tau"] for c in cs), "tau_mean": sum(c["XMEAN_tau"] for c in cs) / max(1.0, sum(c["NCG_tau"] for c in cs))}
+    except Exception:
+        pass
+    return times, seg, nseg, prec
+
+
+def _cpu_sample_text(seg, nseg, cores):
+    what = "whole sweeps (all %d stabilisation intervals)" % nseg if seg == nseg else \
+        "the first %d of %d stabilisation intervals of one sweep per step, rate extrapolated by %d/%d (intervals differ in cost: approximate)" % (seg, nseg, seg, nseg)
+    return (f"{what}; {cores} independent chains, 1 per host thread, OPENBLAS_NUM_THREADS=1; oracle-CPU = C++ restatement of ALF (not ALF.out) built "
+            "-O3 -ffast-math like ALF's GNU build, same LAPACK/BLAS calls (scipy OpenBLAS); it computes in complex f64 as ALF does; for real-valued models (Hubbard Mz) the GPU arm "
+            "uses real f64 (SURVEY F6), which is worth 2-4x of the ratio")
 
 
 def run_reference(args):
@@ -141,16 +172,16 @@ def run_reference(args):
     if rank != 0:
         return 0
     cores = args.cpu_cores or (os.cpu_count() or 1)
-    times, seg, nseg = cpu_sample(args.workload, args.ltau, cores, 150.0, args.steps, args.warmup)
+    times, seg, nseg, prec = cpu_sample(args.workload, args.ltau, cores, 240.0, args.steps, args.warmup)
     tot = sum(times)
     value = cores * len(times) * (seg / nseg) / tot
-    sample = f"{seg} of {nseg} stabilisation intervals of one sweep per step, {cores} independent chains (1 per host thread)"
+    sample = _cpu_sample_text(seg, nseg, cores)
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * tot / len(times), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "c128 (complex f64, as ALF)",
             "data": "synthetic", "config": {"workload": args.workload, "ltau": args.ltau, "chains": cores},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
                              "note": "oracle-CPU: C++ restatement of ALF calling the same LAPACK/BLAS routines (scipy OpenBLAS); gfortran is absent so ALF.out cannot be built"},
-            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0, "precision": prec}
     print(json.dumps(line), flush=True)
     return 0
 
@@ -228,6 +259,10 @@ def run_b200(args):
         barrier()
         return max_over_ranks(max(ev0[a].elapsed_time(ev1[b]) for a in range(H) for b in range(H)))
 
+    obsert_on = bool(args.ltau and args.obs_tau and model.latt is not None and not getattr(model, "Projector", False))
+    if obsert_on:      # BASELINE configs[2] is "with time-displaced Green/spin observables": the device-side ObserT is part of every timed sweep
+        for gk in gs:
+            gk.obs_tau_enable(True)
     on_all(lambda k: gs[k].sweep(args.warmup, args.ltau) if args.warmup > 0 else None)
     # ---- timed region 1: device-resident sweeps
     for gk in gs:
@@ -265,16 +300,14 @@ def run_b200(args):
     g.sweep(1, args.ltau)
     cat_stats = g.kernel_stats(); cat_flops = g.kernel_flops()
     g.kernel_timing(0)
-    with_obsert = None
-    if args.ltau and args.obs_tau:           # the same sweep with the device-side ObserT (time-displaced Green / spin / density correlations) switched on
-        for gk in gs:
-            gk.obs_tau_enable(True)
-        on_all(lambda k: gs[k].sweep(1, args.ltau))
-        ot_ms = timed(lambda k: gs[k].sweep(1, args.ltau))
+    without_obsert = None
+    if obsert_on:           # the same sweep with the device-side ObserT switched off (TAU_M propagates and stabilises, nothing is measured)
         for gk in gs:
             gk.obs_tau_enable(False)
-        with_obsert = {"value": world * H * C / (ot_ms * 1e-3), "unit": UNIT, "ms_per_step": ot_ms, "steps": 1,
-                       "note": "sweep + TAU_M + device-side ObserT: Hop_mod_Symm of GT0, G0T, G00, GTT and Predefined_Obs_tau_Green/SpinMz/Den at every time point"}
+        on_all(lambda k: gs[k].sweep(1, args.ltau))
+        ot_ms = timed(lambda k: gs[k].sweep(1, args.ltau))
+        without_obsert = {"value": world * H * C / (ot_ms * 1e-3), "unit": UNIT, "ms_per_step": ot_ms, "steps": 1,
+                          "note": "sweep + TAU_M without ObserT (no Hop_mod_Symm of GT0, G0T, G00, GTT, no Predefined_Obs_tau_* at the time points)"}
     eq_only = None
     if args.ltau:
         eq_ms = timed(lambda k: gs[k].sweep(1, 0))
@@ -307,21 +340,42 @@ def run_b200(args):
             if cn and cms > 0:
                 tf = cat_flops[cat] / (cms * 1e-3) / 1e12
                 fp64_kernels[cat] = {"launches": cn, "ms": cms, "tflops": tf, "frac_of_dmma_peak": tf / dmma if dmma else None}
-        alg_bytes_per_launch = (acc * F * 2.0 * w * N * N) / max(upd_n, 1)        # 2*w*N^2 per accepted rank-1 update and flavor
+        # Dominant kernel = the slice kernel (k_wrapgr_fast / k_wrapgr).  Its algorithm keeps accepted flips as delayed rank-1 factors in shared
+        # memory and rewrites G in HBM once per KD accepts ("flush"): algorithmic bytes per flush and chain = F * 2 * w * N^2 (G read + written).
+        # The flush count is measured on the device (control["flushes"]).  DESIGN.md section 3 states both figures.
+        flushes = sum(b["flushes"] - a["flushes"] for a, b in zip(c0, c1))
+        alg_bytes_per_launch = (flushes * F * 2.0 * w * N * N) / max(upd_n, 1)
+        ref_alg_bytes_per_launch = (acc * F * 2.0 * w * N * N) / max(upd_n, 1)    # the REFERENCE algorithm (one ZGERU pass over G per accepted flip and flavor)
         alg_flops_per_launch = (acc * F * 2.0 * (4 if g.is_complex else 1) * N * N) / max(upd_n, 1)
         avg_s = upd_ms * 1e-3 / max(upd_n, 1)
         achieved = alg_bytes_per_launch / avg_s / 1e9 if avg_s > 0 else 0.0
-        roof = {"kernel": "k_wrapgr (delayed-update slice kernel)", "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r2_ncu_update_kernel.json")))
+            if tj.get("workload") == args.workload and tj.get("chains") == C:
+                traffic = float(tj["dram_bytes_per_launch"]); traffic_src = tj.get("source")
+        except Exception:
+            pass
+        roof = {"kernel": "k_wrapgr_fast (delayed-update slice kernel)", "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                 "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "launches": upd_n, "avg_launch_ms": 1e3 * avg_s, "share_of_step": upd_ms / (H * ms) if ms > 0 else None,
-                "algorithmic_bytes_per_launch": alg_bytes_per_launch,
-                "note": "algorithmic bytes = SURVEY 8d's figure for the reference algorithm (2*w*N^2 per accepted rank-1 ZGERU update and flavor); this kernel keeps accepted updates as delayed factors in shared memory and rewrites G once per KD accepts, so its DRAM traffic (see traffic) is ~20x below the algorithmic bytes and frac exceeds 1 by design",
+                "algorithmic_bytes_per_launch": alg_bytes_per_launch, "flushes_per_launch_and_chain": flushes / max(upd_n, 1) / C,
+                "reference_algorithm_bytes_per_launch": ref_alg_bytes_per_launch,
+                "note": "algorithmic bytes = (rank-KD rewrites of G counted on the device) x F x 2 w N^2; the reference algorithm (one rank-1 pass over G per accepted flip, SURVEY 8d) would move reference_algorithm_bytes_per_launch; the kernel is bound by the latency of the sequential Metropolis decisions, not by HBM",
                 "fp64": {"achieved_tflops": alg_flops_per_launch / avg_s / 1e12 if avg_s > 0 else 0.0, "peak_tflops_dfma_measured": dfma, "peak_tflops_dmma_measured": dmma}}
-        cpu = None
+        # one roofline entry per dense FP64 kernel category (north_star: FP64 pipe utilisation of the wrap / QR kernels): algorithmic flops counted by the
+        # library per launch (alf_b200_get_kernel_flops), CUDA-event time of the launches (one handle alone), DMMA peak measured in this run
+        rooflines = [roof]
+        names = {"gemm": "k_gemm (ZGEMM/ZTRMM)", "qrp": "k_qrp_* (ZGEQP3)", "formq": "k_apply_q* (ZUNGQR/ZUNMQR)", "trsm": "k_trsm_blk (ZTRSM)"}
+        dense_fl = dense_ms = 0.0
+        for cat, kv in fp64_kernels.items():
+            rooflines.append({"kernel": names[cat], "bound": "fp64-tensor (DMMA m8n8k4)", "achieved": kv["tflops"], "peak": dmma, "unit": "TFLOP/s", "frac": kv["frac_of_dmma_peak"],
+                              "launches": kv["launches"], "ms_per_sweep": kv["ms"], "traffic": None})
+            dense_fl += cat_flops[cat]; dense_ms += kv["ms"]
+        dense_weighted = {"tflops": dense_fl / (dense_ms * 1e-3) / 1e12 if dense_ms > 0 else None, "frac_of_dmma_peak": (dense_fl / (dense_ms * 1e-3) / 1e12 / dmma) if dense_ms > 0 and dmma else None}
+        cpu = None; cpu_prec = None
         if world == 1 and not args.no_cpu_baseline:
             cores = args.cpu_cores or (os.cpu_count() or 1)
-            times, seg, nseg = cpu_sample(args.workload, args.ltau, cores, 20.0, 1, 0)
-            cpu = {"value": cores * (seg / nseg) / times[0], "unit": UNIT, "cores": cores, "kind": "port",
-                   "sample": f"{seg} of {nseg} stabilisation intervals of one sweep, {cores} independent chains (1 per host thread), oracle-CPU (restatement of ALF, not ALF.out)"}
+            times, seg, nseg, cpu_prec = cpu_sample(args.workload, args.ltau, cores, 30.0, 1, 0)
+            cpu = {"value": cores * (seg / nseg) / times[0], "unit": UNIT, "cores": cores, "kind": "port", "sample": _cpu_sample_text(seg, nseg, cores)}
         nl = sum(v[1] for v in stats.values())
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "c128" if g.is_complex else "f64", "data": "synthetic",
@@ -332,9 +386,13 @@ def run_b200(args):
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
                 "gpu_launches": nl, "kernel_launches": {k: v[1] for k, v in stats.items()},
                 "acceptance": acc / max(nprop, 1), "precision_green_max": max(c["XMAXG"] for c in c1),
-                "clocks": clk, "roofline": roof, "cpu_baseline": cpu,
+                "precision": {"green_max": max(c["XMAXG"] for c in c1), "green_mean": sum(c["XMEANG"] for c in c1) / max(1.0, sum(c["NCG"] for c in c1)),
+                              "tau_max": max(c["XMAX_tau"] for c in c1), "tau_mean": sum(c["XMEAN_tau"] for c in c1) / max(1.0, sum(c["NCG_tau"] for c in c1)),
+                              "phase_max": max(c["XMAXP"] for c in c1), "oracle_cpu_sample": cpu_prec,
+                              "note": "Control_PrecisionG / _tau / P accumulated over all sweeps since init (mean = sum / count, ALF's 'Precision Green Mean'); stabilization.tex:225 recommends mean <= 1e-8"},
+                "clocks": clk, "roofline": roof, "rooflines": rooflines, "fp64_dense_flop_weighted": dense_weighted, "cpu_baseline": cpu,
                 "fp64_kernels": fp64_kernels, "fp64_peak_measured": {"dfma_tflops": dfma, "dmma_tflops": dmma},
-                "breakdown_ms_per_sweep": {k: round(v[0], 3) for k, v in cat_stats.items()}, "equal_time_only": eq_only, "with_device_obsert": with_obsert}
+                "breakdown_ms_per_sweep": {k: round(v[0], 3) for k, v in cat_stats.items()}, "equal_time_only": eq_only, "device_obsert_in_value": obsert_on, "without_device_obsert": without_obsert}
     for gk in gs:
         gk.close()
     if world > 1:

@@ -45,6 +45,10 @@ def main(argv=None):
     if a.ltau:
         g.obs_tau_enable(True)
     names = ["Green", "SpinZ", "SpinXY", "Den"]
+
+    def background(nm, bg):      # Obs_Latt0 is accumulated for SpinZ (ObsZ) and Den only (Prog/Predefined_Obs_mod.F90:190-191,514-515); Green and SpinXY: 0
+        return bg[0].sum(0) if nm == "SpinZ" else bg[1].sum(0) if nm == "Den" else np.zeros(model.n_orb)
+    unit = dict(n_coord=model.n_coord, orb_pos=model.orb_pos)
     for nb in range(a.bins):
         g.obs_reset()
         if a.ltau:
@@ -56,13 +60,13 @@ def main(argv=None):
         acc, bg, n, s = g.obs_eq()
         acc, bg, n, s = acc - acc0, bg - bg0, n - n0, s - s0
         for ch, nm in enumerate(names):
-            print_bin_latt(os.path.join(a.out, nm), acc[ch].transpose(0, 2, 1, 3), bg[0 if nm.startswith("Spin") else 1].sum(0) if nm != "Green" else np.zeros(model.n_orb),
-                           s, n / a.chains, a.chains, model.latt, channel="---")
+            print_bin_latt(os.path.join(a.out, nm), acc[ch].transpose(0, 2, 1, 3), background(nm, bg),
+                           s, n / a.chains, a.chains, model.latt, channel="---", **unit)
         if a.ltau:
             acc, bg, n, s = g.obs_tau()
             for ch, nm in enumerate(names):
-                print_bin_latt(os.path.join(a.out, nm), acc[ch].transpose(0, 2, 1, 3), bg[0 if nm.startswith("Spin") else 1].sum(0) if nm != "Green" else np.zeros(model.n_orb),
-                               s, n / a.chains, a.chains, model.latt, dtau=a.dtau, channel="P")
+                print_bin_latt(os.path.join(a.out, nm), acc[ch].transpose(0, 2, 1, 3), background(nm, bg),
+                               s, n / a.chains, a.chains, model.latt, dtau=a.dtau, channel="P", **unit)
         c = g.control()
         print(f"bin {nb}: acceptance {c['ACC_up'] / max(c['NC_up'], 1):.3f}, precision Green max {c['XMAXG']:.2e}, <sign> {ob[1] / ob[0]:.3f}, <N> {ob[2] / ob[0]:.4f}")
     for f in conf.write_confs(g, a.out):                           # confout_<chain>, then renamed as ALF's out_to_in.sh does

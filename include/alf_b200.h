@@ -179,7 +179,8 @@ int alf_b200_get_udv(alf_b200_handle* h, int which /*0 udvl,1 udvr,2 udvst*/, in
                      double* U, double* D, double* V /* complex */);
 /* control accumulators (Prog/control_mod.F90:53-71), reduced over chains:
  * [0] XMEANG sum [1] XMAXG [2] NCG [3] XMAXP [4] XMEAN_tau sum [5] XMAX_tau [6] NCG_tau [7] NC_up [8] ACC_up
- * [9] NC_eff_up [10] ACC_eff_up [11] NaN flag [12] unstable flag (XMAX > 10) */
+ * [9] NC_eff_up [10] ACC_eff_up [11] NaN flag [12] unstable flag (XMAX > 10)
+ * [13] (measurement support, no reference counterpart) number of rank-KD rewrites of G in global memory by the slice kernels */
 int alf_b200_get_control(alf_b200_handle* h, double* out /* 16 */);
 int alf_b200_accept_log(alf_b200_handle* h, int n_sweeps);   /* record accept/reject per field visit for the next n_sweeps sweeps (check 2); 0 = off */
 int alf_b200_get_accept_log(alf_b200_handle* h, uint8_t* out, long cap, long* n_per_chain);

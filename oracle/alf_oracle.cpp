@@ -43,6 +43,8 @@ void scipy_zgetrf_(int*, int*, cd*, int*, int*, int*);
 void scipy_zgetri_(int*, cd*, int*, int*, cd*, int*, int*);
 void scipy_zgetrs_(const char*, int*, int*, cd*, int*, int*, cd*, int*, int*);
 void scipy_zgemm_(const char*, const char*, int*, int*, int*, cd*, cd*, int*, cd*, int*, cd*, cd*, int*);
+void scipy_zgeru_(int*, int*, cd*, cd*, int*, cd*, int*, cd*, int*);
+void scipy_zgemv_(const char*, int*, int*, cd*, cd*, int*, cd*, int*, cd*, cd*, int*);
 void scipy_zlapmr_(int*, int*, int*, cd*, int*, int*);
 void scipy_zlapmt_(int*, int*, int*, cd*, int*, int*);
 void scipy_openblas_set_num_threads(int);
@@ -691,22 +693,26 @@ struct Oracle {
           for (int i = 0; i < Nd; ++i) { x_v[i + (size_t)n * Nd] = u[i + (size_t)n * Nd]; y_v[i + (size_t)n * Nd] = v[i + (size_t)n * Nd]; }
           cd Z = 1.0 + u[op.P[n] + (size_t)n * Nd] * v[op.P[n] + (size_t)n * Nd];
           std::vector<cd> syu(n), sxv(n);
-          for (int m = 0; m < n; ++m) { cd a = 0, b = 0;
-            for (int i = 0; i < Nd; ++i) { a += y_v[i + (size_t)m * Nd] * u[i + (size_t)n * Nd]; b += x_v[i + (size_t)m * Nd] * v[i + (size_t)n * Nd]; }
-            syu[m] = -a; sxv[m] = -b; }
-          for (int m = 0; m < n; ++m) for (int i = 0; i < Nd; ++i) { x_v[i + (size_t)n * Nd] += x_v[i + (size_t)m * Nd] * syu[m]; y_v[i + (size_t)n * Nd] += y_v[i + (size_t)m * Nd] * sxv[m]; }
+          { cd am(-1, 0), a1(1, 0), b0(0, 0); int one = 1, nn = n;      // the four ZGEMV calls of upgrade_mod.F90:255-258
+            scipy_zgemv_("T", &Nd, &nn, &am, y_v.data(), &Nd, u.data() + (size_t)n * Nd, &one, &b0, syu.data(), &one);
+            scipy_zgemv_("T", &Nd, &nn, &am, x_v.data(), &Nd, v.data() + (size_t)n * Nd, &one, &b0, sxv.data(), &one);
+            scipy_zgemv_("N", &Nd, &nn, &a1, x_v.data(), &Nd, syu.data(), &one, &a1, x_v.data() + (size_t)n * Nd, &one);
+            scipy_zgemv_("N", &Nd, &nn, &a1, y_v.data(), &Nd, sxv.data(), &one, &a1, y_v.data() + (size_t)n * Nd, &one); }
           for (int m = 0; m < n; ++m) Z -= syu[m] * sxv[m];
           Z = 1.0 / Z;
           for (int i = 0; i < Nd; ++i) x_v[i + (size_t)n * Nd] *= Z;
         }
         if (op.N == 1) {
           for (int i = 0; i < Nd; ++i) xp_v[i] = G[i + (size_t)op.P[0] * Nd];
-          cd Z = -x_v[op.P[0]];
-          for (int j = 0; j < Nd; ++j) for (int i = 0; i < Nd; ++i) G[i + (size_t)j * Nd] += Z * xp_v[i] * y_v[j];
+          cd Z = -x_v[op.P[0]]; int one = 1;
+          scipy_zgeru_(&Nd, &Nd, &Z, xp_v.data(), &one, y_v.data(), &one, G, &Nd);                  // ZGERU, upgrade_mod.F90:269
         } else {
-          // xp_v = G(:,P) * x_v(P,:) ; G -= xp_v * y_v^T
-          for (int n = 0; n < od; ++n) for (int i = 0; i < Nd; ++i) { cd s = 0; for (int m = 0; m < od; ++m) s += G[i + (size_t)op.P[m] * Nd] * x_v[op.P[m] + (size_t)n * Nd]; xp_v[i + (size_t)n * Nd] = s; }
-          for (int j = 0; j < Nd; ++j) for (int i = 0; i < Nd; ++i) { cd s = 0; for (int n = 0; n < od; ++n) s += xp_v[i + (size_t)n * Nd] * y_v[j + (size_t)n * Nd]; G[i + (size_t)j * Nd] -= s; }
+          // xp_v = G(:,P) * x_v(P,:) ; G -= xp_v * y_v^T   (the two ZGEMM calls of upgrade_mod.F90:271-280)
+          std::vector<cd> zarr((size_t)od * od), grarr((size_t)Nd * od);
+          for (int n = 0; n < od; ++n) for (int m = 0; m < od; ++m) zarr[m + (size_t)n * od] = x_v[op.P[m] + (size_t)n * Nd];
+          for (int m = 0; m < od; ++m) for (int i = 0; i < Nd; ++i) grarr[i + (size_t)m * Nd] = G[i + (size_t)op.P[m] * Nd];
+          zgemm('N', 'N', Nd, od, od, cd(1, 0), grarr.data(), Nd, zarr.data(), od, cd(0, 0), xp_v.data(), Nd);
+          zgemm('N', 'T', Nd, Nd, od, cd(-1, 0), xp_v.data(), Nd, y_v.data(), Nd, cd(1, 0), G, Nd);
         }
       }
       fld(n_op, nt) = Hs_new;

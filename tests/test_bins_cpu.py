@@ -54,6 +54,19 @@ def test_latt_bin_layout_fourier_and_roundtrip(tmp_path):
     assert sign == 1.0 and np.allclose(bg, [2.0]) and o.shape == (8, 3, 1, 1)
     assert np.allclose(o[:, :, 0, 0], np.array([1.0, 2.0, 3.0])[None, :])
     assert "Unit cells" in open(p + "_info").read()
+    # the `_info` file parses with the exact read sequence and formats of Analysis/ana_mod.F90:285-309
+    from alf_b200.bins import read_latt_info
+    ch, nt_, dt_, nu, L1p, L2p, a1p, a2p, ncoord, norb_, orb = read_latt_info(p)
+    assert (ch, nt_, nu, ncoord, norb_) == ("---", 3, 8, 2, 1) and dt_ == 0.1
+    assert L1p == [4.0, 0.0] and L2p == [0.0, 2.0] and a1p == [1.0, 0.0] and a2p == [0.0, 1.0] and orb.shape == (1, 2) and not orb.any()
+    # two orbitals with three-component positions (Bilayer_square, Predefined_Latt_mod.F90:155-160)
+    obs2 = np.zeros((1, 2, 2, latt.N), dtype=complex)
+    p2 = print_bin_latt(str(tmp_path / "Den"), obs2, [0.0, 0.0], 1.0, 1, 1, latt, n_coord=2, orb_pos=[[0, 0, 0], [0, 0, -1.0]])
+    r = read_latt_info(p2)
+    assert r[8:10] == (2, 2) and r[10].shape == (2, 3) and r[10][1, 2] == -1.0 and r[1] == 1
+    lines = open(p2 + "_info").read().split("\n")
+    assert lines[11].startswith(" Coordination number: ") and lines[12].startswith("  Number of orbitals: ") and lines[13].startswith("                Ndim: ")
+    assert lines[14].startswith("           Orbital 1: ") and len(lines[15]) == 22 + 3 * 26
 
 
 def test_conf_roundtrip_all_field_types(tmp_path):
