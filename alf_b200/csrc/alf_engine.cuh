@@ -423,6 +423,7 @@ struct Engine : EngineBase {
   LaWork<T> w;
   cplx* d_z = nullptr; double* d_angle = nullptr; double* d_angle_tab = nullptr; double* d_cmp = nullptr;
   VopDev<T>* d_vops = nullptr; T* d_place_tab = nullptr; int* d_place_pk = nullptr; unsigned char* d_is_cont = nullptr; ModelDev md; FieldTabDev ft;
+  ModelFixDev mf; bool fix_any = false; int fix_max_ops = 0;      // resident-descriptor form of the bond-operator lists (k_apply_ops_fixed)
   std::vector<void*> owned;     // device allocations of the op lists
   bool dense_t = false; T* d_dense[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // fwd, inv, c, half, halfinv (N*N*F each)
   int KD = 16; size_t upd_smem = 0; int ops_lk = 0; size_t ops_smem = 0;   // ops_lk = log2 of the largest small-operator dimension
@@ -466,11 +467,59 @@ struct Engine : EngineBase {
     return d;
   }
 
+  // Resident-descriptor form of a fixed list of k = 2 bond operators (k_apply_ops_fixed): families = maximal runs of consecutive operators with
+  // pairwise disjoint supports, one 32-bit word per operator.
+  FixListDev upload_fixed(const ListBuild& lb) {
+    FixListDev d = {0, 0, nullptr, nullptr, nullptr, nullptr};
+    if (lb.nvar != 1 || lb.k.empty() || N * OPS_PW > 65535 + OPS_PW || getenv("ALF_B200_NO_FIXED_OPS")) return d;
+    for (int kk : lb.k) if (kk != 2) return d;
+    const int n = (int)lb.k.size();
+    std::vector<int> fs = lb.levels(N, 1 << 30);
+    std::vector<unsigned> offs(n); std::vector<T> m((size_t)n * 4); std::vector<unsigned char> uni(fs.size() - 1, 1);
+    for (int o = 0; o < n; ++o) {
+      offs[o] = (unsigned)(lb.P[(size_t)o * ALF_KMAX] * OPS_PW) | ((unsigned)(lb.P[(size_t)o * ALF_KMAX + 1] * OPS_PW) << 16);
+      const cd* a = &lb.mat[(size_t)o * ALF_KMAX * ALF_KMAX];
+      m[4 * o] = to_T<T>(a[0]); m[4 * o + 1] = to_T<T>(a[1]); m[4 * o + 2] = to_T<T>(a[ALF_KMAX]); m[4 * o + 3] = to_T<T>(a[ALF_KMAX + 1]);
+    }
+    for (size_t c = 0; c + 1 < fs.size(); ++c) for (int o = fs[c]; o < fs[c + 1]; ++o) for (int e = 0; e < 4; ++e) {
+      const cd x = lb.mat[(size_t)o * ALF_KMAX * ALF_KMAX + (e & 1) + (size_t)(e >> 1) * ALF_KMAX], y = lb.mat[(size_t)fs[c] * ALF_KMAX * ALF_KMAX + (e & 1) + (size_t)(e >> 1) * ALF_KMAX];
+      if (x != y) uni[c] = 0; }
+    d.n_fam = (int)fs.size() - 1; d.n_ops = n; d.fam_start = dupload(fs); d.offs = dupload(offs); d.mat = dupload(m); d.uniform = dupload(uni);
+    fix_any = true; fix_max_ops = std::max(fix_max_ops, n);
+    return d;
+  }
+  // vertex list usable as a row scaling: only k = 1 (diagonal) factors, every site at most once
+  unsigned char diag_list_ok(const ListBuild& lb) const {
+    std::vector<char> seen(N, 0);
+    for (size_t o = 0; o < lb.k.size(); ++o) { if (lb.k[o] != 1) return 0; const int p = lb.P[o * ALF_KMAX]; if (seen[p]) return 0; seen[p] = 1; }
+    return 1;
+  }
+  bool fixed_mode_ok(int mode) const {
+    if (!fix_any) return false;
+    int t = -1, v = -1;
+    switch (mode) {
+      case MODE_WRAPUR: t = L_TL_FWD; v = L_VL_N; break;
+      case MODE_WRAPUL: t = L_TL_C; v = L_VL_C; break;
+      case MODE_TL_FWD: t = L_TL_FWD; break;
+      case MODE_TL_INV: t = L_TL_INV; break;
+      case MODE_TL_C: t = L_TL_C; break;
+      case MODE_TL_HALF: t = L_TL_HALF; break;
+      case MODE_TR_FWD: t = L_TR_FWD; break;
+      case MODE_TR_INV: t = L_TR_INV; break;
+      case MODE_TR_HALFINV: t = L_TR_HALFINV; break;
+      case MODE_PROPRM1: t = L_TR_INV; v = L_VR_INV; break;
+      default: return false;
+    }
+    for (int f = 0; f < F; ++f) { if (mf.fix[t][f].n_fam <= 0) return false; if (v >= 0 && !mf.diag_ok[v][f]) return false; }
+    return true;
+  }
+
   Engine(alf_b200_handle* hh) : h(hh) {
     C = h->n_chains; F = h->n_fl; N = h->ndim; L = h->ltrot; M = h->n_opv; NM = C * F; n2 = (long)N * N; st = h->stream;
     if (F > ALF_FMAX) throw CudaError("more than ALF_FMAX flavors");
     if (N > 576) throw CudaError("Ndim > 576 is not supported in this build (QR / TRSM kernels hold <= 18 rows per lane; TAU_M needs 2 Ndim <= 576)");
     S = (L % h->nwrap == 0) ? L / h->nwrap : L / h->nwrap + 1;                 // main.F90:446-457
+    std::memset(&mf, 0, sizeof(mf));
     stab_nt.assign(S + 1, 0); for (int n = 1; n < S; ++n) stab_nt[n] = h->nwrap * n; stab_nt[S] = L;
     build_model();
     G = dalloc<T>(n2 * NM); G2 = dalloc<T>(n2 * NM);
@@ -572,12 +621,14 @@ struct Engine : EngineBase {
       }
     }
     // op-list kernel: panel of 32 columns (rows) + double-buffered operator descriptors
-    ops_smem = (((size_t)N * (OPS_PW + 1) + 1) & ~(size_t)1) * sizeof(T) + 2 * OPS_CH * ((sizeof(T) << (2 * ops_lk)) + 4 * sizeof(int));
+    ops_smem = (((size_t)N * OPS_PW + 1) & ~(size_t)1) * sizeof(T) + 2 * OPS_CH * ((sizeof(T) << (2 * ops_lk)) + 4 * sizeof(int));
     if (ops_smem > 227 * 1024) throw CudaError("Ndim too large for the op-list kernel's shared-memory panel");
 #define OPS_ATTR(LKV) do { CK(alf_raise_smem(k_apply_ops<T, 0, LKV>)); \
                             CK(alf_raise_smem(k_apply_ops<T, 1, LKV>)); } while (0)
     if (ops_lk == 0) OPS_ATTR(0); else if (ops_lk == 1) OPS_ATTR(1); else OPS_ATTR(2);
 #undef OPS_ATTR
+    if (fix_any && ops_fixed_smem(sizeof(T), N, fix_max_ops) > 227 * 1024) fix_any = false;
+    if (fix_any) { CK(alf_raise_smem(k_apply_ops_fixed<T, 0>)); CK(alf_raise_smem(k_apply_ops_fixed<T, 1>)); }
   }
   ~Engine() { for (void* p : owned) cudaFree(p); w.release(); if (proj) wp.release(); if (w2_ready) w2.release(); }
   // Optional (ALF_B200_L2_PERSIST=1): persisting-L2 access window over the batch of Green functions.  Measured on B200 with
@@ -624,6 +675,10 @@ struct Engine : EngineBase {
       md.lists[L_TL_FWD][f] = upload_list(fwd); md.lists[L_TL_INV][f] = upload_list(inv); md.lists[L_TL_C][f] = upload_list(cc);
       md.lists[L_TL_HALF][f] = upload_list(half); md.lists[L_TR_FWD][f] = upload_list(rfwd); md.lists[L_TR_INV][f] = upload_list(rinv);
       md.lists[L_TR_HALFINV][f] = upload_list(rhalfinv);
+      if (!dense_t) {
+        mf.fix[L_TL_FWD][f] = upload_fixed(fwd); mf.fix[L_TL_INV][f] = upload_fixed(inv); mf.fix[L_TL_C][f] = upload_fixed(cc); mf.fix[L_TL_HALF][f] = upload_fixed(half);
+        mf.fix[L_TR_FWD][f] = upload_fixed(rfwd); mf.fix[L_TR_INV][f] = upload_fixed(rinv); mf.fix[L_TR_HALFINV][f] = upload_fixed(rhalfinv);
+      }
     }
     if (dense_t) {
       // products of the (few) dense factors in the orders of Hop_mod.F90:143-250
@@ -685,6 +740,7 @@ struct Engine : EngineBase {
         std::vector<std::vector<cd>> mc(ALF_NVAR); for (int var = 0; var < ALF_NVAR; ++var) mc[var] = ct(mexp[n][var], op.N);
         vc.add(op.N, op.P.data(), n, mc); }
       md.lists[L_VL_N][f] = upload_list(vn); md.lists[L_VL_C][f] = upload_list(vc); md.lists[L_VR_INV][f] = upload_list(vri);
+      mf.diag_ok[L_VL_N][f] = diag_list_ok(vn); mf.diag_ok[L_VL_C][f] = diag_list_ok(vc); mf.diag_ok[L_VR_INV][f] = diag_list_ok(vri);
     }
     d_vops = dupload(vops); d_angle_tab = dupload(angle_tab); md.fields_c = h->d_fields_c;
     { std::vector<unsigned char> tc(M); for (int n = 0; n < M; ++n) tc[n] = h->opv[n].type == 3 ? 1 : 0; d_is_cont = dupload(tc); }
@@ -718,6 +774,12 @@ struct Engine : EngineBase {
     if (!Mout) Mout = Mx;                          // in place unless a result buffer is given (full matrices only)
     const ModelDev& md = mdo ? *mdo : this->md;
     dim3 grid((nvec + OPS_PW - 1) / OPS_PW, NM);
+    if (!mdo && fixed_mode_ok(mode)) {             // bond-operator hopping list (+ diagonal vertices): resident-descriptor kernel
+      const size_t sm = ops_fixed_smem(sizeof(T), N, fix_max_ops);
+      if (side == 0) KL(KC_OPS, st, k_apply_ops_fixed<T, 0><<<grid, OPS_NT, sm, st>>>(Mx, n2, N, nvec, md, mf, F, mode, nt_a, nt_b, h->d_fields, L, M, Mout));
+      else KL(KC_OPS, st, k_apply_ops_fixed<T, 1><<<grid, OPS_NT, sm, st>>>(Mx, n2, N, nvec, md, mf, F, mode, nt_a, nt_b, h->d_fields, L, M, Mout));
+      CKL(); return;
+    }
 #define OPS_LAUNCH(SD, LKV) KL(KC_OPS, st, k_apply_ops<T, SD, LKV><<<grid, OPS_NT, ops_smem, st>>>(Mx, n2, N, nvec, md, F, mode, nt_a, nt_b, h->d_fields, L, M, Mout))
     if (side == 0) { if (ops_lk == 0) OPS_LAUNCH(0, 0); else if (ops_lk == 1) OPS_LAUNCH(0, 1); else OPS_LAUNCH(0, 2); }
     else { if (ops_lk == 0) OPS_LAUNCH(1, 0); else if (ops_lk == 1) OPS_LAUNCH(1, 1); else OPS_LAUNCH(1, 2); }

@@ -249,6 +249,17 @@ static void launch_apply_q(cudaStream_t st, const T* QR, int m, int n, int ld, l
   count_flops(KC_FORMQ, flop_scale<T>() * (4.0 * m * n * ncols - 2.0 * n * n * ncols) * (ident ? 0.5 : 1.0) * batch);
   if constexpr (std::is_same<T, double>::value) {
     if (use_qr2<T>(m, n)) {
+      if (applyq2p_smem(m, 16) <= 226 * 1024 && !getenv("ALF_B200_NO_Q_PREFETCH")) {      // double-buffered reflector panels (cp.async prefetch)
+        const size_t smemp = applyq2p_smem(m, 16); const int cpcp = 128; dim3 gridp((ncols + cpcp - 1) / cpcp, batch);
+        const long sTp = (long)(n + 32) * 32;
+        KScope ks_(KC_FORMQ, st);
+#define AQ2P_LAUNCH(MD, ID) do { CK(alf_raise_smem(k_apply_q2p<MD, ID>)); \
+          k_apply_q2p<MD, ID><<<gridp, 512, smemp, st>>>(QR, m, n, ld, sQ, Tbuf, sTp, X, ldx, sX, ncols, cpcp); } while (0)
+        if (mode == 0) AQ2P_LAUNCH(0, 0); else if (ident) AQ2P_LAUNCH(1, 1); else AQ2P_LAUNCH(1, 0);
+#undef AQ2P_LAUNCH
+        CKL();
+        return;
+      }
       const bool small = applyq2_smem(m, 8) + 1024 <= 113 * 1024;        // two 8-warp CTAs per SM, else one 16-warp CTA
       const size_t smem = applyq2_smem(m, small ? 8 : 16); const int cpc2 = small ? 64 : 128; dim3 grid2((ncols + cpc2 - 1) / cpc2, batch);
       const long sT2 = (long)(n + 32) * 32;

@@ -61,13 +61,19 @@ struct ModelDev {
 #define OPS_PW 32            // panel width = warp size
 #define OPS_NT 256           // threads per CTA (8 warps, three CTAs per SM at N = 256; measured: 512 threads and 128-operator chunks are both slower)
 
+// Panel layout: element (row i, lane j) at S[i * 32 + (j ^ (i & 31))].  Rows are aligned 256-byte (512-byte) lines, so a warp's access to one
+// row costs the minimum number of shared-memory wavefronts (with the former odd row stride of 33 every row straddled three 128-byte bank rows
+// instead of two), and the XOR keeps the transposing accesses of the staging (32 consecutive rows, one lane) conflict free as well.
+__device__ __forceinline__ int ops_sw(int off, int lane) { return off + (lane ^ ((off >> 5) & 31)); }
+
 // Shared-memory descriptor of one operator: x = (k << 28) | element offset of row P[0] in the panel, y, z, w = offsets of P[1..3];
 // its k x k matrix sits in dM[o << 2 LK] with leading dimension 1 << LK.
 template <typename T, int LK>
 __device__ __forceinline__ void ops_process_chunk(T* __restrict__ S, bool lane_ok, int cnt, const int4* __restrict__ dP, const T* __restrict__ dM, bool uniform) {
   constexpr int kk = 1 << LK, ms = 1 << (2 * LK);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  T* Sl = S + lane;
+  // element (row offset off = P * 32, lane): rows are aligned 32-element lines, the lane index is XOR-swizzled with the row (ops_sw)
+  #define Sl(off) S[ops_sw(off, lane)]
   if (LK >= 1 && uniform) {                   // translation-invariant checkerboard family: one matrix for the whole chunk
     const T a00 = dM[0], a10 = dM[1], a01 = dM[kk], a11 = dM[kk + 1];
     for (int o = warp; o < cnt; o += 2 * nw) {
@@ -75,9 +81,9 @@ __device__ __forceinline__ void ops_process_chunk(T* __restrict__ S, bool lane_o
       const int4 P = dP[o], Q = dP[o2];
       const int px = P.x & 0x0fffffff, qx = Q.x & 0x0fffffff;
       if (lane_ok) {
-        const T v0 = Sl[px], v1 = Sl[P.y], w0 = Sl[qx], w1 = Sl[Q.y];
-        Sl[px] = a00 * v0 + a01 * v1; Sl[P.y] = a10 * v0 + a11 * v1;
-        if (o2 != o) { Sl[qx] = a00 * w0 + a01 * w1; Sl[Q.y] = a10 * w0 + a11 * w1; }
+        const T v0 = Sl(px), v1 = Sl(P.y), w0 = Sl(qx), w1 = Sl(Q.y);
+        Sl(px) = a00 * v0 + a01 * v1; Sl(P.y) = a10 * v0 + a11 * v1;
+        if (o2 != o) { Sl(qx) = a00 * w0 + a01 * w1; Sl(Q.y) = a10 * w0 + a11 * w1; }
       }
     }
     return;
@@ -93,15 +99,15 @@ __device__ __forceinline__ void ops_process_chunk(T* __restrict__ S, bool lane_o
       const T a00 = A[0], a10 = A[1], a01 = A[kk], a11 = A[kk + 1];
       const T b00 = Bm[0], b10 = Bm[1], b01 = Bm[kk], b11 = Bm[kk + 1];
       if (lane_ok) {
-        const T v0 = Sl[px], v1 = Sl[P.y], w0 = Sl[qx], w1 = Sl[Q.y];
-        Sl[px] = a00 * v0 + a01 * v1; Sl[P.y] = a10 * v0 + a11 * v1;
-        if (two) { Sl[qx] = b00 * w0 + b01 * w1; Sl[Q.y] = b10 * w0 + b11 * w1; }
+        const T v0 = Sl(px), v1 = Sl(P.y), w0 = Sl(qx), w1 = Sl(Q.y);
+        Sl(px) = a00 * v0 + a01 * v1; Sl(P.y) = a10 * v0 + a11 * v1;
+        if (two) { Sl(qx) = b00 * w0 + b01 * w1; Sl(Q.y) = b10 * w0 + b11 * w1; }
       }
       continue;
     }
     if (k == 1 && k2 == 1) {                  // diagonal single-site vertices
       const T a = A[0], bq = Bm[0];
-      if (lane_ok) { const T v0 = Sl[px], w0 = Sl[qx]; Sl[px] = a * v0; if (two) Sl[qx] = bq * w0; }
+      if (lane_ok) { const T v0 = Sl(px), w0 = Sl(qx); Sl(px) = a * v0; if (two) Sl(qx) = bq * w0; }
       continue;
     }
     for (int h = 0; h < (two ? 2 : 1); ++h) {
@@ -110,7 +116,7 @@ __device__ __forceinline__ void ops_process_chunk(T* __restrict__ S, bool lane_o
       const int Pa[ALF_KMAX] = {PP.x & 0x0fffffff, PP.y, PP.z, PP.w};
       T v[kk], r[kk];
 #pragma unroll
-      for (int a = 0; a < kk; ++a) v[a] = (a < kc) ? Sl[Pa[a]] : zero_<T>();
+      for (int a = 0; a < kk; ++a) v[a] = (a < kc) ? Sl(Pa[a]) : zero_<T>();
 #pragma unroll
       for (int a = 0; a < kk; ++a) {
         T sacc = zero_<T>();
@@ -119,7 +125,7 @@ __device__ __forceinline__ void ops_process_chunk(T* __restrict__ S, bool lane_o
         r[a] = sacc;
       }
 #pragma unroll
-      for (int a = 0; a < kk; ++a) if (a < kc) Sl[Pa[a]] = r[a];
+      for (int a = 0; a < kk; ++a) if (a < kc) Sl(Pa[a]) = r[a];
     }
   }
 }
@@ -131,7 +137,7 @@ template <typename T, int SIDE, int LK>
 __global__ void __launch_bounds__(OPS_NT) k_apply_ops(T* M, long sM, int N, int nvec, ModelDev md, int F, int mode,
                                                    int nt_a, int nt_b, const int8_t* __restrict__ fields, int Ltrot, int n_opv, T* Mout) {   // Mout: result buffer (may be M)
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  constexpr int ldp = OPS_PW + 1, ms = 1 << (2 * LK), kk = 1 << LK;
+  constexpr int ldp = OPS_PW, ms = 1 << (2 * LK), kk = 1 << LK;
   constexpr int MPT = (OPS_CH * ms + OPS_NT - 1) / OPS_NT;       // descriptor-matrix entries prefetched per thread
   T* S = reinterpret_cast<T*>(smem_raw);
   T* dMb = S + ((N * ldp + 1) & ~1);                  // keeps the int4 descriptor arrays 16-byte aligned
@@ -214,9 +220,9 @@ __global__ void __launch_bounds__(OPS_NT) k_apply_ops(T* M, long sM, int N, int 
   if (total > 1) { data_issue(pf1); meta_load(); }
   // ---- stage the panel
   if (SIDE == 0) {
-    for (int j = warp; j < pw; j += nw) { const T* col = M + (long)(v0 + j) * N; for (int i = lane; i < N; i += 32) S[i * ldp + j] = col[i]; }
+    for (int j = warp; j < pw; j += nw) { const T* col = M + (long)(v0 + j) * N; for (int i = lane; i < N; i += 32) S[ops_sw(i * ldp, j)] = col[i]; }
   } else {
-    if (lane < pw) { const T* src = M + v0 + lane; for (int i = warp; i < N; i += nw) S[i * ldp + lane] = src[(long)i * N]; }
+    if (lane < pw) { const T* src = M + v0 + lane; for (int i = warp; i < N; i += nw) S[ops_sw(i * ldp, lane)] = src[(long)i * N]; }
   }
   int cnt_cur = pf0.rcnt; bool uni_cur = pf0.runi;
   if (total > 0) commit(pf0, 0);
@@ -236,8 +242,127 @@ __global__ void __launch_bounds__(OPS_NT) k_apply_ops(T* M, long sM, int N, int 
   }
   // ---- write back
   if (SIDE == 0) {
-    for (int j = warp; j < pw; j += nw) { T* col = Mout + (long)(v0 + j) * N; for (int i = lane; i < N; i += 32) col[i] = S[i * ldp + j]; }
+    for (int j = warp; j < pw; j += nw) { T* col = Mout + (long)(v0 + j) * N; for (int i = lane; i < N; i += 32) col[i] = S[ops_sw(i * ldp, j)]; }
   } else {
-    if (lane < pw) { T* dst = Mout + v0 + lane; for (int i = warp; i < N; i += nw) dst[(long)i * N] = S[i * ldp + lane]; }
+    if (lane < pw) { T* dst = Mout + v0 + lane; for (int i = warp; i < N; i += nw) dst[(long)i * N] = S[ops_sw(i * ldp, lane)]; }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------------
+// k_apply_ops_fixed: the same programs for the common case that the program's hopping list consists of k = 2 bond operators only
+// (checkerboard decomposition) and its vertex list, if any, of diagonal single-site factors (every Hubbard variant).
+// k_apply_ops is instruction bound (ncu: 55 % issue-slot utilisation; about 45 % of its instructions are the per-chunk descriptor
+// pipeline that resolves field-dependent matrices).  Here the descriptors of the WHOLE hopping list are resident in shared memory
+// in their final form (one 32-bit word per operator: the two panel-row offsets), a family (= level of pairwise disjoint operators)
+// is processed between two barriers without any chunking, the 2 x 2 matrix of a translation-invariant family sits in registers,
+// and e^{V(s)} of a slice is a row scaling built once per slice from the field values.
+// ------------------------------------------------------------------------------------------------------------------------
+struct FixListDev {
+  int n_fam, n_ops;                 // n_fam = 0: the list has no fixed form
+  const int* fam_start;             // n_fam + 1
+  const unsigned* offs;             // n_ops: (P0 * 32) | (P1 * 32) << 16   (panel-row offsets, 16 bits each)
+  const void* mat;                  // n_ops * 4 entries of T: a00, a10, a01, a11
+  const unsigned char* uniform;     // n_fam: all operators of the family carry the same matrix
+};
+struct ModelFixDev {
+  FixListDev fix[L_COUNT][ALF_FMAX];
+  unsigned char diag_ok[L_COUNT][ALF_FMAX];   // vertex lists: only k = 1 factors, every site at most once
+};
+static inline size_t ops_fixed_smem(size_t sizeof_T, int N, int max_ops) { return sizeof_T * ((size_t)N * OPS_PW + N) + sizeof(unsigned) * (size_t)(max_ops + 4) + 16; }
+
+template <typename T, int SIDE>
+__global__ void __launch_bounds__(OPS_NT) k_apply_ops_fixed(T* M, long sM, int N, int nvec, ModelDev md, ModelFixDev mf, int F, int mode, int nt_a, int nt_b,
+                                                            const int8_t* __restrict__ fields, int Ltrot, int n_opv, T* Mout) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr int ldp = OPS_PW;
+  T* S = reinterpret_cast<T*>(smem_raw);
+  T* dsc = S + (long)N * ldp;
+  unsigned* offs = reinterpret_cast<unsigned*>(dsc + N);
+  const int b = blockIdx.y, chain = b / F, f = b % F;
+  M += (long)b * sM; Mout += (long)b * sM;
+  const int v0 = blockIdx.x * OPS_PW, pw = min(OPS_PW, nvec - v0);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+  int li0 = 0, li1 = -1, uf0 = 0, uf1 = 0, dir = 1;
+  switch (mode) {
+    case MODE_WRAPUR: li0 = L_TL_FWD; li1 = L_VL_N; uf1 = 1; break;
+    case MODE_WRAPUL: li0 = L_VL_C; uf0 = 1; li1 = L_TL_C; dir = -1; break;
+    case MODE_TL_FWD: li0 = L_TL_FWD; break;
+    case MODE_TL_INV: li0 = L_TL_INV; break;
+    case MODE_TL_C: li0 = L_TL_C; break;
+    case MODE_TL_HALF: li0 = L_TL_HALF; break;
+    case MODE_TR_FWD: li0 = L_TR_FWD; break;
+    case MODE_TR_INV: li0 = L_TR_INV; break;
+    case MODE_TR_HALFINV: li0 = L_TR_HALFINV; break;
+    case MODE_PROPRM1: li0 = L_TR_INV; li1 = L_VR_INV; uf1 = 1; break;
+  }
+  const FixListDev FL = mf.fix[uf0 ? li1 : li0][f];          // the program's hopping list (exactly one per mode)
+  for (int e = tid; e < FL.n_ops; e += blockDim.x) offs[e] = FL.offs[e];
+  // ---- stage the panel (coalesced global reads; the XOR-swizzled rows keep the transposing writes conflict free)
+  if (SIDE == 0) {
+    for (int j = warp; j < pw; j += nw) { const T* col = M + (long)(v0 + j) * N; for (int i = lane; i < N; i += 32) S[ops_sw(i * ldp, j)] = col[i]; }
+  } else {
+    if (lane < pw) { const T* src = M + v0 + lane; for (int i = warp; i < N; i += nw) S[ops_sw(i * ldp, lane)] = src[(long)i * N]; }
+  }
+  __syncthreads();
+  const bool lane_ok = lane < pw;
+  const T* mats = reinterpret_cast<const T*>(FL.mat);
+  const int ns = (uf0 || uf1) ? (nt_b - nt_a + 1) : 1;
+  for (int sl = 0; sl < ns; ++sl) {
+    const int nt = (dir > 0) ? nt_a + sl : nt_b - sl;
+    for (int part = 0; part < 2; ++part) {
+      const int li = part ? li1 : li0; if (li < 0) continue;
+      if (!(part ? uf1 : uf0)) {
+        for (int fa = 0; fa < FL.n_fam; ++fa) {
+          const int o0 = FL.fam_start[fa], o1 = FL.fam_start[fa + 1];
+          if (FL.uniform[fa]) {
+            const T a00 = mats[4 * o0], a10 = mats[4 * o0 + 1], a01 = mats[4 * o0 + 2], a11 = mats[4 * o0 + 3];
+            for (int o = o0 + warp; o < o1; o += 2 * nw) {
+              const bool two = o + nw < o1;
+              const unsigned d0 = offs[o], d1 = offs[two ? o + nw : o];
+              if (lane_ok) {
+                const int p0 = ops_sw(d0 & 0xffff, lane), p1 = ops_sw(d0 >> 16, lane), q0 = ops_sw(d1 & 0xffff, lane), q1 = ops_sw(d1 >> 16, lane);
+                const T x0 = S[p0], x1 = S[p1], y0 = S[q0], y1 = S[q1];
+                S[p0] = a00 * x0 + a01 * x1; S[p1] = a10 * x0 + a11 * x1;
+                if (two) { S[q0] = a00 * y0 + a01 * y1; S[q1] = a10 * y0 + a11 * y1; }
+              }
+            }
+          } else {
+            for (int o = o0 + warp; o < o1; o += nw) {
+              const unsigned d0 = offs[o];
+              const T a00 = mats[4 * o], a10 = mats[4 * o + 1], a01 = mats[4 * o + 2], a11 = mats[4 * o + 3];
+              if (lane_ok) {
+                const int p0 = ops_sw(d0 & 0xffff, lane), p1 = ops_sw(d0 >> 16, lane);
+                const T x0 = S[p0], x1 = S[p1];
+                S[p0] = a00 * x0 + a01 * x1; S[p1] = a10 * x0 + a11 * x1;
+              }
+            }
+          }
+          __syncthreads();
+        }
+      } else {
+        // diagonal vertices of slice nt: row scaling d(P_n) = exp(+-g phi(s_n) E_n) (tabulated per field value; continuous fields on the fly)
+        const OpListDev& L = md.lists[li][f];
+        const T* vm = reinterpret_cast<const T*>(L.mat);
+        const int8_t* fl = fields + ((long)chain * Ltrot + (nt - 1)) * n_opv;
+        const double* fc = md.fields_c ? md.fields_c + ((long)chain * Ltrot + (nt - 1)) * n_opv : nullptr;
+        for (int i = tid; i < N; i += blockDim.x) dsc[i] = one_<T>();
+        __syncthreads();
+        for (int o = tid; o < L.n_ops; o += blockDim.x) {
+          const int n = L.fidx[o]; T v;
+          if (fc && L.cont[o]) v = exp_(vm[((long)o * L.nvar) * (ALF_KMAX * ALF_KMAX)] * fc[n]);
+          else v = vm[((long)o * L.nvar + (int)fl[n] + 2) * (ALF_KMAX * ALF_KMAX)];
+          dsc[L.P[(long)o * ALF_KMAX]] = v;
+        }
+        __syncthreads();
+        if (lane_ok) for (int i = warp; i < N; i += nw) { const int e = ops_sw(i * ldp, lane); S[e] = dsc[i] * S[e]; }
+        __syncthreads();
+      }
+    }
+  }
+  // ---- write back
+  if (SIDE == 0) {
+    for (int j = warp; j < pw; j += nw) { T* col = Mout + (long)(v0 + j) * N; for (int i = lane; i < N; i += 32) col[i] = S[ops_sw(i * ldp, j)]; }
+  } else {
+    if (lane < pw) { T* dst = Mout + v0 + lane; for (int i = warp; i < N; i += nw) dst[(long)i * N] = S[ops_sw(i * ldp, lane)]; }
   }
 }

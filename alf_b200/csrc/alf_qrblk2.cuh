@@ -32,6 +32,11 @@ static size_t applyq2_smem(int m, int nw) {
 // X(r0:m, strip) <- (I - V op(T) V^T) X(r0:m, strip) for the 8-column strips c_begin + 8 (warp + k nw) < c_end of this CTA.
 // Vs: (m - r0) x 32 explicit unit-lower trapezoid, zero padded to mvp rows and 32 columns; Ts: 32 x 32 upper triangular (ld 36).
 // CONJT = 1: op(T) = T^T (Q^T from the left), 0: op(T) = T.  vn != nullptr: 2-norm of X(r0 + nbk : m, c) -> vn[c].
+// Both GEMM phases are software-pipelined: the C fragments of the next group of k-steps (phase 1) / row blocks (phase 3) are
+// already in flight while the tensor cores work on the current group, so a warp never waits a full L2 round trip per group
+// (round 1's ncu source view: 49 % long-scoreboard stall on the DMMA line of phase 3, which had a one-block prefetch only).
+#define QR2_KU 8      // k-steps (of 4 rows) per load group in phase 1
+#define QR2_RB 4      // row blocks (of 8 rows) per load group in phase 3: four independent accumulator chains
 template <int CONJT>
 __device__ __forceinline__ void apply_panel_strips(double* __restrict__ X, int ldx, int r0, int m, int c_begin, int c_end, const double* __restrict__ Vs,
                                                    int ldv, const double* __restrict__ Ts, int nbk, double* __restrict__ Wsc, double* __restrict__ vn) {
@@ -46,13 +51,26 @@ __device__ __forceinline__ void apply_panel_strips(double* __restrict__ X, int l
     for (int ib = 0; ib < 4; ++ib) { w[ib][0] = 0.0; w[ib][1] = 0.0; }
     const bool colb = (c0 + g) < c_end;
     const double* xb = X + (long)(c0 + g) * ldx + r0 + q;
-#pragma unroll 4
-    for (int ks = 0; ks < mvp / 4; ++ks) {
-      const int r = 4 * ks + q;
-      const double bv = (colb && r < mv) ? xb[4 * ks] : 0.0;
-      const double* vp = Vs + r + (long)g * ldv;
+    const int nks = mvp / 4;
+    double bc[QR2_KU], bn[QR2_KU];
 #pragma unroll
-      for (int ib = 0; ib < 4; ++ib) dmma884(w[ib][0], w[ib][1], vp[(long)(8 * ib) * ldv], bv);
+    for (int u = 0; u < QR2_KU; ++u) bc[u] = (colb && 4 * u + q < mv) ? xb[4 * u] : 0.0;
+    for (int ks0 = 0; ks0 < nks; ks0 += QR2_KU) {
+      if (ks0 + QR2_KU < nks) {
+#pragma unroll
+        for (int u = 0; u < QR2_KU; ++u) { const int ks = ks0 + QR2_KU + u; bn[u] = (colb && 4 * ks + q < mv) ? xb[4 * ks] : 0.0; }
+      }
+#pragma unroll
+      for (int u = 0; u < QR2_KU; ++u) {
+        const int ks = ks0 + u;
+        if (ks < nks) {                                       // warp-uniform; rows beyond mvp of Vs are not initialised
+          const double* vp = Vs + (4 * ks + q) + (long)g * ldv;
+#pragma unroll
+          for (int ib = 0; ib < 4; ++ib) dmma884(w[ib][0], w[ib][1], vp[(long)(8 * ib) * ldv], bc[u]);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < QR2_KU; ++u) bc[u] = bn[u];
     }
 #pragma unroll
     for (int ib = 0; ib < 4; ++ib) { Wm[(8 * ib + g) + (2 * q) * QR2_LDW] = w[ib][0]; Wm[(8 * ib + g) + (2 * q + 1) * QR2_LDW] = w[ib][1]; }
@@ -77,22 +95,40 @@ __device__ __forceinline__ void apply_panel_strips(double* __restrict__ X, int l
 #pragma unroll
     for (int ks = 0; ks < 8; ++ks) bw[ks] = Wm[(4 * ks + q) + g * QR2_LDW];       // -W2 as B fragments
     __syncwarp();
-    // ---- C -= V W2, 8 rows at a time; exact norms of the rows below the panel
+    // ---- C -= V W2, QR2_RB blocks of 8 rows at a time; exact norms of the rows below the panel
     const bool ca = (c0 + 2 * q) < c_end, cb2 = (c0 + 2 * q + 1) < c_end;
     double* xc = X + (long)(c0 + 2 * q) * ldx + r0 + g;
     double n0 = 0.0, n1 = 0.0;
     const int nrb = mvp / 8;
-    double p0 = (g < mv && ca) ? xc[0] : 0.0, p1 = (g < mv && cb2) ? xc[ldx] : 0.0;       // row block 0, prefetched
-    for (int rb = 0; rb < nrb; ++rb) {
-      const int r = 8 * rb + g; const bool rok = r < mv;
-      double a0 = p0, a1 = p1;
-      if (rb + 1 < nrb) { const bool nok = r + 8 < mv; p0 = (nok && ca) ? xc[8 * rb + 8] : 0.0; p1 = (nok && cb2) ? xc[8 * rb + 8 + ldx] : 0.0; }
-      const double* vp = Vs + r + (long)q * ldv;
+    double pa[QR2_RB][2], pb[QR2_RB][2];
 #pragma unroll
-      for (int ks = 0; ks < 8; ++ks) dmma884(a0, a1, vp[(long)(4 * ks) * ldv], bw[ks]);
-      if (rok && ca) xc[8 * rb] = a0;
-      if (rok && cb2) xc[8 * rb + ldx] = a1;
-      if (r >= nbk) { n0 = fma(a0, a0, n0); n1 = fma(a1, a1, n1); }
+    for (int t = 0; t < QR2_RB; ++t) { const bool ok = 8 * t + g < mv; pa[t][0] = (ok && ca) ? xc[8 * t] : 0.0; pa[t][1] = (ok && cb2) ? xc[8 * t + ldx] : 0.0; }
+    for (int rb = 0; rb < nrb; rb += QR2_RB) {
+      if (rb + QR2_RB < nrb) {
+#pragma unroll
+        for (int t = 0; t < QR2_RB; ++t) { const int rr = 8 * (rb + QR2_RB + t); const bool ok = rr + g < mv; pb[t][0] = (ok && ca) ? xc[rr] : 0.0; pb[t][1] = (ok && cb2) ? xc[rr + ldx] : 0.0; }
+      }
+      const double* vp = Vs + (8 * rb + g) + (long)q * ldv;
+      if (rb + QR2_RB <= nrb) {                               // full group: four interleaved accumulator chains
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks)
+#pragma unroll
+          for (int t = 0; t < QR2_RB; ++t) dmma884(pa[t][0], pa[t][1], vp[8 * t + (long)(4 * ks) * ldv], bw[ks]);
+      } else {
+#pragma unroll
+        for (int t = 0; t < QR2_RB; ++t) if (rb + t < nrb) {
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks) dmma884(pa[t][0], pa[t][1], vp[8 * t + (long)(4 * ks) * ldv], bw[ks]);
+        }
+      }
+#pragma unroll
+      for (int t = 0; t < QR2_RB; ++t) {
+        const int r = 8 * (rb + t) + g; const bool rok = r < mv;
+        if (rok && ca) xc[8 * (rb + t)] = pa[t][0];
+        if (rok && cb2) xc[8 * (rb + t) + ldx] = pa[t][1];
+        if (rok && r >= nbk) { n0 = fma(pa[t][0], pa[t][0], n0); n1 = fma(pa[t][1], pa[t][1], n1); }
+        pa[t][0] = pb[t][0]; pa[t][1] = pb[t][1];
+      }
     }
     if (vn) {
       n0 += __shfl_xor_sync(0xffffffffu, n0, 4); n1 += __shfl_xor_sync(0xffffffffu, n1, 4);
@@ -227,6 +263,7 @@ __global__ void __launch_bounds__(32 * (QR2_NB / CPW), CPW == 4 ? 2 : 1) k_qrp_r
         else { beta = -copysign(cn, alpha); tj = (beta - alpha) / beta; scal = 1.0 / (alpha - beta); }
 #pragma unroll
         for (int r = 0; r < MAXR; ++r) {
+          if (32 * r + 31 < prow) continue;
           const int i = lane + 32 * r;
           if (i < m && i >= prow) {
             double x = cr[0][r];
@@ -249,19 +286,24 @@ __global__ void __launch_bounds__(32 * (QR2_NB / CPW), CPW == 4 ? 2 : 1) k_qrp_r
 #pragma unroll
         for (int h = 0; h < CPW; ++h) { doh[h] = (sb + h < nbk) && !((used >> (sb + h)) & 1u); any = any || doh[h]; }
         if (any) {
-          double w[CPW], qn[CPW];
+          // rows above the pivot row are finished: row blocks r with 32 r + 31 < prow are skipped by the whole warp (on average half of
+          // them); the dot products and norms run as two interleaved chains (even / odd row blocks)
+          double w[CPW], wb[CPW], qn[CPW], qb[CPW];
 #pragma unroll
-          for (int h = 0; h < CPW; ++h) { w[h] = 0.0; qn[h] = 0.0; }
+          for (int h = 0; h < CPW; ++h) { w[h] = 0.0; wb[h] = 0.0; qn[h] = 0.0; qb[h] = 0.0; }
           if (tj != 0.0) {
 #pragma unroll
             for (int r = 0; r < MAXR; ++r) {
+              if (32 * r + 31 < prow) continue;
               const int i = lane + 32 * r;
               if (i >= prow && i < m) {
                 const double v = v_s[i];
 #pragma unroll
-                for (int h = 0; h < CPW; ++h) w[h] = fma(v, cr[h][r], w[h]);
+                for (int h = 0; h < CPW; ++h) { if (r & 1) wb[h] = fma(v, cr[h][r], wb[h]); else w[h] = fma(v, cr[h][r], w[h]); }
               }
             }
+#pragma unroll
+            for (int h = 0; h < CPW; ++h) w[h] += wb[h];
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1)
 #pragma unroll
@@ -271,16 +313,19 @@ __global__ void __launch_bounds__(32 * (QR2_NB / CPW), CPW == 4 ? 2 : 1) k_qrp_r
           }
 #pragma unroll
           for (int r = 0; r < MAXR; ++r) {
+            if (32 * r + 31 < prow) continue;
             const int i = lane + 32 * r;
             if (i >= prow && i < m) {
               const double v = (tj != 0.0) ? v_s[i] : 0.0;
 #pragma unroll
               for (int h = 0; h < CPW; ++h) {
                 if (doh[h]) cr[h][r] = fma(-v, w[h], cr[h][r]);
-                if (i > prow) qn[h] = fma(cr[h][r], cr[h][r], qn[h]);
+                if (i > prow) { if (r & 1) qb[h] = fma(cr[h][r], cr[h][r], qb[h]); else qn[h] = fma(cr[h][r], cr[h][r], qn[h]); }
               }
             }
           }
+#pragma unroll
+          for (int h = 0; h < CPW; ++h) qn[h] += qb[h];
 #pragma unroll
           for (int o = 16; o > 0; o >>= 1)
 #pragma unroll
@@ -399,6 +444,67 @@ __global__ void __launch_bounds__(NTHR, NTHR == 256 ? 2 : 1) k_apply_q2(const do
     for (int e = tid; e < LDW * NB; e += nthr) { const int r = e % LDW, c = e / LDW; Ts[e] = (r < NB) ? Tbuf[(long)pi * NB * NB + r + (long)c * NB] : 0.0; }
     __syncthreads();
     apply_panel_strips<MODE ? 0 : 1>(X, ldx, k0, m, c_lo, ce, Vs, ldv, Ts, nbk, Wsc, nullptr);
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------------
+// k_apply_q2p: k_apply_q2 with the reflector panel DOUBLE-BUFFERED in shared memory: the V and T factors of panel p + 1 are
+// requested with cp.async (LDGSTS, no register staging) before the strips of panel p are worked on, so their L2 / HBM latency
+// hides behind the tensor-core work (round 2's ncu source view of k_apply_q2: 31 % of the warp-stall samples were long-scoreboard
+// waits on the panel load).  One CTA of 16 warps per SM, 128 columns of X per CTA.  Used when two panels fit (m <= ~330).
+// ------------------------------------------------------------------------------------------------------------------------
+static size_t applyq2p_smem(int m, int nw) {
+  const int mp = (m + 7) & ~7, ldv = ld_pad(mp);
+  return sizeof(double) * (2 * ((size_t)ldv * QR2_NB + QR2_LDW * QR2_NB) + (size_t)nw * QR2_WSC) + 64;
+}
+__device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"(sa), "l"(gsrc) : "memory");
+}
+template <int MODE, int IDENT>
+__global__ void __launch_bounds__(512, 1) k_apply_q2p(const double* __restrict__ QR, int m, int n, int ld, long sQ, const double* __restrict__ Tbuf, long sT,
+                                                    double* __restrict__ X, int ldx, long sX, int ncols, int cols_per_cta) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr int NB = QR2_NB, LDW = QR2_LDW;
+  const int b = blockIdx.y, tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = nthr >> 5;
+  QR += (long)b * sQ; Tbuf += (long)b * sT; X += (long)b * sX;
+  const int mp = (m + 7) & ~7, ldv = ld_pad(mp);
+  double* Vb[2]; double* Tb[2];
+  Vb[0] = reinterpret_cast<double*>(smem_raw); Vb[1] = Vb[0] + (long)ldv * NB;
+  Tb[0] = Vb[1] + (long)ldv * NB; Tb[1] = Tb[0] + LDW * NB;
+  double* Wsc = Tb[1] + LDW * NB;
+  const int cb = blockIdx.x * cols_per_cta, ce = min(ncols, cb + cols_per_cta);
+  const int kmax = (m < n) ? m : n, npan = (kmax + NB - 1) / NB;
+  auto panel_of = [&](int pp, int& pi, int& k0, int& nbk, int& c_lo) {
+    pi = MODE ? (npan - 1 - pp) : pp; k0 = pi * NB; nbk = min(NB, kmax - k0);
+    c_lo = cb; if (IDENT) c_lo = max(cb, k0 & ~7);
+  };
+  auto issue = [&](int pp, int buf) {          // raw copy: rows k0 .. m-1 of the panel's columns (R entries on and above the diagonal are fixed up on arrival)
+    int pi, k0, nbk, c_lo; panel_of(pp, pi, k0, nbk, c_lo);
+    const int mv = m - k0;
+    for (int c = warp; c < nbk; c += nw) { const double* src = QR + k0 + (long)(k0 + c) * ld; double* dst = Vb[buf] + (long)c * ldv; for (int r = lane; r < mv; r += 32) cp_async8(dst + r, src + r); }
+    for (int e = tid; e < NB * NB; e += nthr) cp_async8(Tb[buf] + (e & 31) + (e >> 5) * LDW, Tbuf + (long)pi * NB * NB + e);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  for (int e = tid; e < 2 * LDW * NB; e += nthr) { const int r = (e % (LDW * NB)) % LDW; if (r >= NB) Tb[0][e] = 0.0; }      // pad rows 32 .. 35 of both T buffers (Tb[1] follows Tb[0])
+  int first = 0;
+  for (; first < npan; ++first) { int pi, k0, nbk, c_lo; panel_of(first, pi, k0, nbk, c_lo); if (c_lo < ce) break; }
+  if (first >= npan) return;
+  issue(first, 0);
+  for (int pp = first; pp < npan; ++pp) {
+    const int buf = (pp - first) & 1;
+    int pi, k0, nbk, c_lo; panel_of(pp, pi, k0, nbk, c_lo);
+    const int mv = m - k0, mvp = (mv + 7) & ~7;
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+    double* Vs = Vb[buf];
+    for (int e = tid; e < NB * NB; e += nthr) { const int r = e & 31, c = e >> 5; if (c < nbk && r <= c && r < mvp) Vs[r + (long)c * ldv] = (r == c) ? 1.0 : 0.0; }
+    for (int e = tid; e < (mvp - mv) * NB; e += nthr) { const int r = mv + e % (mvp - mv), c = e / (mvp - mv); Vs[r + (long)c * ldv] = 0.0; }
+    if (nbk < NB) for (int e = tid; e < mvp * (NB - nbk); e += nthr) { const int r = e % mvp, c = nbk + e / mvp; Vs[r + (long)c * ldv] = 0.0; }
+    __syncthreads();
+    if (pp + 1 < npan) issue(pp + 1, buf ^ 1);
+    if (c_lo < ce) apply_panel_strips<MODE ? 0 : 1>(X, ldx, k0, m, c_lo, ce, Vs, ldv, Tb[buf], nbk, Wsc, nullptr);
     __syncthreads();
   }
 }
