@@ -322,6 +322,14 @@ class AlfB200:
     def obs_reset(self):
         self._ck(lib().alf_b200_obs_reset(self.h))
 
+    def set_obs_scal_tables(self, tab):
+        """Kin / Pot / Ener of ham%Obser on the device from tables (alf_b200_set_obs_scal_tables); `tab` = alf_b200.model.obs_scal_tables(model)."""
+        a = {k: np.ascontiguousarray(tab[k], dtype=np.int32) for k in ("kin_i", "kin_j", "kin_nf", "pot_i1", "pot_nf1", "pot_i2", "pot_nf2")}
+        kc = np.ascontiguousarray(tab["kin_coef"], dtype=np.complex128); pc = np.ascontiguousarray(tab["pot_coef"], dtype=np.complex128)
+        p = lambda x: x.ctypes.data_as(_ip)
+        self._ck(lib().alf_b200_set_obs_scal_tables(self.h, int(kc.size), p(a["kin_i"]), p(a["kin_j"]), p(a["kin_nf"]), _d(kc),
+                                                    int(pc.size), p(a["pot_i1"]), p(a["pot_nf1"]), p(a["pot_i2"]), p(a["pot_nf2"]), _d(pc)))
+
     def obs_device_ptr(self):
         p = _dp(); n = C.c_long(0)
         self._ck(lib().alf_b200_obs_device_ptr(self.h, C.byref(p), C.byref(n)))

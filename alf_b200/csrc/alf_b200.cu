@@ -63,6 +63,7 @@ int alf_b200_destroy(alf_b200_handle* h) {
   if (h->d_obse_acc) cudaFree(h->d_obse_acc); if (h->d_obse_bg) cudaFree(h->d_obse_bg); if (h->d_obse_cnt) cudaFree(h->d_obse_cnt);
   if (h->d_obst_acc) cudaFree(h->d_obst_acc); if (h->d_obst_bg) cudaFree(h->d_obst_bg); if (h->d_obst_cnt) cudaFree(h->d_obst_cnt);
   if (h->d_counters) cudaFree(h->d_counters); if (h->d_ctl) cudaFree(h->d_ctl); if (h->d_acclog) cudaFree(h->d_acclog); if (h->d_obs) cudaFree(h->d_obs);
+  if (h->d_kin_idx) cudaFree(h->d_kin_idx); if (h->d_pot_idx) cudaFree(h->d_pot_idx); if (h->d_kin_coef) cudaFree(h->d_kin_coef); if (h->d_pot_coef) cudaFree(h->d_pot_coef);
   if (h->pin_fields) cudaFreeHost(h->pin_fields);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
@@ -316,6 +317,26 @@ int alf_b200_set_lattice(alf_b200_handle* h, int n_unit, int norb, const int* si
   }
   for (size_t i = 0; i < h->imj.size(); ++i) { if (imj[i] < 1 || imj[i] > n_unit) { h->err = "set_lattice: imj entry out of range"; return ALF_ERROR_GENERIC; } h->imj[i] = imj[i] - 1; }
   return ALF_OK;
+}
+int alf_b200_set_obs_scal_tables(alf_b200_handle* h, int n_kin, const int* kin_i, const int* kin_j, const int* kin_nf, const double* kin_coef,
+                                 int n_pot, const int* pot_i1, const int* pot_nf1, const int* pot_i2, const int* pot_nf2, const double* pot_coef) {
+  API_BEGIN(h) NEED_FINAL(h)
+  if (n_kin < 0 || n_pot < 0) return ALF_ERROR_GENERIC;
+  CK(cudaStreamSynchronize(h->stream));
+  for (void* p : {(void*)h->d_kin_idx, (void*)h->d_pot_idx, (void*)h->d_kin_coef, (void*)h->d_pot_coef}) if (p) cudaFree(p);
+  h->d_kin_idx = h->d_pot_idx = nullptr; h->d_kin_coef = h->d_pot_coef = nullptr; h->n_kin = h->n_pot = 0;
+  auto bad = [&](int i) { return i < 1 || i > h->ndim; }; auto badf = [&](int f) { return f < 1 || f > h->n_fl; };
+  std::vector<int> ki((size_t)3 * n_kin), pi((size_t)4 * n_pot); std::vector<cplx> kc(n_kin), pc(n_pot);
+  for (int t = 0; t < n_kin; ++t) { if (bad(kin_i[t]) || bad(kin_j[t]) || badf(kin_nf[t])) { h->err = "set_obs_scal_tables: Kin index out of range"; return ALF_ERROR_GENERIC; }
+    ki[3 * t] = kin_i[t] - 1; ki[3 * t + 1] = kin_j[t] - 1; ki[3 * t + 2] = kin_nf[t] - 1; kc[t] = cplx(kin_coef[2 * t], kin_coef[2 * t + 1]); }
+  for (int t = 0; t < n_pot; ++t) { if (bad(pot_i1[t]) || bad(pot_i2[t]) || badf(pot_nf1[t]) || badf(pot_nf2[t])) { h->err = "set_obs_scal_tables: Pot index out of range"; return ALF_ERROR_GENERIC; }
+    pi[4 * t] = pot_i1[t] - 1; pi[4 * t + 1] = pot_nf1[t] - 1; pi[4 * t + 2] = pot_i2[t] - 1; pi[4 * t + 3] = pot_nf2[t] - 1; pc[t] = cplx(pot_coef[2 * t], pot_coef[2 * t + 1]); }
+  if (n_kin) { CK(cudaMalloc(&h->d_kin_idx, sizeof(int) * ki.size())); CK(cudaMalloc(&h->d_kin_coef, sizeof(cplx) * n_kin));
+    CK(cudaMemcpy(h->d_kin_idx, ki.data(), sizeof(int) * ki.size(), cudaMemcpyHostToDevice)); CK(cudaMemcpy(h->d_kin_coef, kc.data(), sizeof(cplx) * n_kin, cudaMemcpyHostToDevice)); }
+  if (n_pot) { CK(cudaMalloc(&h->d_pot_idx, sizeof(int) * pi.size())); CK(cudaMalloc(&h->d_pot_coef, sizeof(cplx) * n_pot));
+    CK(cudaMemcpy(h->d_pot_idx, pi.data(), sizeof(int) * pi.size(), cudaMemcpyHostToDevice)); CK(cudaMemcpy(h->d_pot_coef, pc.data(), sizeof(cplx) * n_pot, cudaMemcpyHostToDevice)); }
+  h->n_kin = n_kin; h->n_pot = n_pot;
+  API_END(h)
 }
 static size_t obst_acc_len(const alf_b200_handle* h) { return (size_t)2 * OBST_NCH * h->obst_ntau * h->norb * h->norb * h->n_unit; }
 static size_t obst_bg_len(const alf_b200_handle* h) { return (size_t)2 * 2 * h->obst_ntau * h->norb; }

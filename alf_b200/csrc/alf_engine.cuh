@@ -154,6 +154,8 @@ struct alf_b200_handle {
   double* d_ctl = nullptr;            // per chain: 0 XMEANG 1 XMAXG 2 NCG 3 XMAXP 4 XMEAN_tau 5 XMAX_tau 6 NCG_tau 7 flags(nan=1, unstable=2)
   uint8_t* d_acclog = nullptr; long acclog_per_chain = 0; long acclog_pos = 0; bool acclog_on = false;
   double* d_obs = nullptr; int obs_size = 0;
+  // model-specific scalar observables as tables (alf_b200_set_obs_scal_tables): Kin terms (i, j, nf, coef), Pot terms (i1, nf1, i2, nf2, coef); 0-based
+  int n_kin = 0, n_pot = 0; int *d_kin_idx = nullptr, *d_pot_idx = nullptr; cplx *d_kin_coef = nullptr, *d_pot_coef = nullptr;
   int taum_every = 0; std::vector<std::vector<cd>> taum_host, taum_fresh_host;   // per chain captured matrices
   std::vector<int> types;            // operator type per n
   // lattice tables for the device-side lattice observables (0-based; site -> unit cell / orbital, imj(I,J) column-major)
@@ -251,6 +253,30 @@ __global__ void __launch_bounds__(128) k_obs_scalar(const T* __restrict__ G, lon
     const cplx ph = phase[c]; const double zs = (ph.x >= 0.0) ? 1.0 : -1.0; const cplx zp = cplx(1.0, ph.y / ph.x);
     const cplx v = (cplx(a * n_sun, b * n_sun) * zp) * zs;
     atomicAdd(obs + 0, 1.0); atomicAdd(obs + 1, zs); atomicAdd(obs + 2, v.x); atomicAdd(obs + 3, v.y);
+  }
+}
+
+// Kin, Pot, Ener of ham%Obser from tables (see alf_b200_set_obs_scal_tables) on the Green function handed to ham%Obser; one CTA per chain.
+// obs: [4..5] Kin, [6..7] Pot, [8..9] Ener, each sum over chains of value ZP ZS.
+template <typename T>
+__global__ void __launch_bounds__(256) k_obs_scal_tables(const T* __restrict__ G, long sM, int N, int F, int n_sun, const cplx* __restrict__ phase, int n_kin, const int* __restrict__ kin_idx,
+                                                         const cplx* __restrict__ kin_coef, int n_pot, const int* __restrict__ pot_idx, const cplx* __restrict__ pot_coef, double* __restrict__ obs) {
+  __shared__ double red[4][8];
+  const int c = blockIdx.x, tid = threadIdx.x;
+  const T* Gc = G + (long)c * F * sM;
+  auto grc = [&](int i, int j, int f) { const T g = Gc[(long)f * sM + j + (long)i * N]; return cplx(((i == j) ? 1.0 : 0.0) - real_(g), -imag_(g)); };      // delta_ij - GR(j,i)
+  cplx kin = cplx(0.0, 0.0), pot = cplx(0.0, 0.0);
+  for (int t = tid; t < n_kin; t += blockDim.x) kin = kin + kin_coef[t] * grc(kin_idx[3 * t], kin_idx[3 * t + 1], kin_idx[3 * t + 2]);
+  for (int t = tid; t < n_pot; t += blockDim.x) { const int i1 = pot_idx[4 * t], f1 = pot_idx[4 * t + 1], i2 = pot_idx[4 * t + 2], f2 = pot_idx[4 * t + 3]; pot = pot + pot_coef[t] * (grc(i1, i1, f1) * grc(i2, i2, f2)); }
+  double v[4] = {kin.x * n_sun, kin.y * n_sun, pot.x, pot.y};
+#pragma unroll
+  for (int q = 0; q < 4; ++q) { v[q] = warp_sum(v[q]); if ((tid & 31) == 0) red[q][tid >> 5] = v[q]; }
+  __syncthreads();
+  if (tid == 0) {
+    for (int q = 0; q < 4; ++q) { v[q] = 0.0; for (int w = 0; w < (int)(blockDim.x >> 5); ++w) v[q] += red[q][w]; }
+    const cplx ph = phase[c]; const double zs = (ph.x >= 0.0) ? 1.0 : -1.0; const cplx zpzs = cplx(zs, zs * ph.y / ph.x);
+    const cplx k = cplx(v[0], v[1]) * zpzs, p = cplx(v[2], v[3]) * zpzs;
+    atomicAdd(obs + 4, k.x); atomicAdd(obs + 5, k.y); atomicAdd(obs + 6, p.x); atomicAdd(obs + 7, p.y); atomicAdd(obs + 8, k.x + p.x); atomicAdd(obs + 9, k.y + p.y);
   }
 }
 
@@ -517,6 +543,7 @@ struct Engine : EngineBase {
   Engine(alf_b200_handle* hh) : h(hh) {
     C = h->n_chains; F = h->n_fl; N = h->ndim; L = h->ltrot; M = h->n_opv; NM = C * F; n2 = (long)N * N; st = h->stream;
     if (F > ALF_FMAX) throw CudaError("more than ALF_FMAX flavors");
+    if ((long)C * F > 65535) throw CudaError("n_chains * N_FL > 65535: the batched kernels index the matrices of a handle with gridDim.y; use several handles");
     if (N > 576) throw CudaError("Ndim > 576 is not supported in this build (QR / TRSM kernels hold <= 18 rows per lane; TAU_M needs 2 Ndim <= 576)");
     S = (L % h->nwrap == 0) ? L / h->nwrap : L / h->nwrap + 1;                 // main.F90:446-457
     std::memset(&mf, 0, sizeof(mf));
@@ -1032,16 +1059,20 @@ struct Engine : EngineBase {
     const int lobs_st = proj ? thtrot + 1 : 1, lobs_en = proj ? L - thtrot : L;
     if (ntau1 < lobs_st || ntau1 > lobs_en) return;
     KL(KC_OBS, st, k_obs_scalar<T><<<C, 128, 0, st>>>(G, n2, N, F, h->n_sun, h->d_phase, h->d_obs));
-    if (h->obs_eq_on) {      // equal-time lattice observables on the symmetrised G (main.F90:761-764 hands GR_Tilde to ham%Obser)
-      obs_tau_setup();
+    const bool scal_tab = h->n_kin > 0 || h->n_pot > 0;
+    if (h->obs_eq_on || scal_tab) {      // observables on the symmetrised G (main.F90:761-764 hands GR_Tilde to ham%Obser)
+      if (h->obs_eq_on) obs_tau_setup(); else if (!obsS[0]) { for (int q = 0; q < 2; ++q) obsS[q] = dalloc<T>(n2 * NM); }
       const T* gs = G;
       if (h->symm) {
         if (dense_t) { CK(cudaMemcpyAsync(obsS[0], G, sizeof(T) * n2 * NM, cudaMemcpyDeviceToDevice, st)); hop_symm(obsS[0]); }
         else { apply_ops(G, 0, MODE_TL_HALF, 0, 0, -1, nullptr, obsS[0]); apply_ops(obsS[0], 1, MODE_TR_HALFINV, 0, 0); }
         gs = obsS[0];
       }
-      KL(KC_EW, st, k_g0t_init<T><<<dim3(ew_blocks(n2), NM), 256, 0, st>>>(obsS[1], gs, n2, N));      // G - 1
-      KL(KC_OBS, st, k_obs_tau<T, 1><<<C, 256, obst_smem, st>>>(gs, obsS[1], gs, gs, n2, N, F, h->n_sun, h->d_phase, lt, 0, 1, h->d_obse_acc, h->d_obse_bg, h->d_obse_cnt));
+      if (scal_tab) KL(KC_OBS, st, k_obs_scal_tables<T><<<C, 256, 0, st>>>(gs, n2, N, F, h->n_sun, h->d_phase, h->n_kin, h->d_kin_idx, h->d_kin_coef, h->n_pot, h->d_pot_idx, h->d_pot_coef, h->d_obs));
+      if (h->obs_eq_on) {
+        KL(KC_EW, st, k_g0t_init<T><<<dim3(ew_blocks(n2), NM), 256, 0, st>>>(obsS[1], gs, n2, N));      // G - 1
+        KL(KC_OBS, st, k_obs_tau<T, 1><<<C, 256, obst_smem, st>>>(gs, obsS[1], gs, gs, n2, N, F, h->n_sun, h->d_phase, lt, 0, 1, h->d_obse_acc, h->d_obse_bg, h->d_obse_cnt));
+      }
     }
   }
 
@@ -1121,7 +1152,7 @@ struct Engine : EngineBase {
     if (F > 2) throw CudaError("obs_tau: more than two flavors are not supported");
     lt.n_unit = h->n_unit; lt.norb = h->norb;
     lt.cell = dupload(h->site_cell); lt.orb = dupload(h->site_orb); lt.imj = dupload(h->imj);
-    for (int q = 0; q < 4; ++q) obsS[q] = dalloc<T>(n2 * NM);
+    for (int q = 0; q < 4; ++q) if (!obsS[q]) obsS[q] = dalloc<T>(n2 * NM);
     obst_smem = obs_tau_smem<T>(N, lt.n_unit, lt.norb);
     if (obst_smem > 227 * 1024) throw CudaError("obs_tau: lattice too large for the shared-memory bins");
     CK(alf_raise_smem(k_obs_tau<T, 0>));

@@ -362,11 +362,35 @@ def hubbard_square(L1: int, L2: int, beta: float, dtau: float = 0.1, U: float = 
     return m
 
 
-def hubbard_chain(L: int, beta: float, dtau: float, U: float = 4.0, t: float = 1.0, Mz: bool = True, symm: bool = True) -> Model:
-    """N_leg_ladder with L2=1 and Checkerboard=.false. as in testsuite/test_vs_ed/test_specs.yaml:24-56
-    (dense hopping matrix, periodic chain; with Symm the half-step similarity is applied before measuring)."""
+def trial_wave_function_chain(L: int, n_part: int, N_FL: int, t: float = 1.0):
+    """Predefined_TrialWaveFunction for Lattice_type = N_leg_ladder with one leg (Prog/Predefined_Trial_mod.F90:319-325, 352-364): the N_part lowest
+    eigenvectors of the non-interacting ring with Ham_T = 1 and a twist Phi_X = 0.01 applied as a BOUNDARY condition (Bulk = .false.: only the bond
+    that crosses the boundary carries exp(2 pi i Phi_X N1), Generic_hopping, Prog/Predefined_Hop_mod.F90:2105-2115), which lifts the degeneracy at
+    half filling.  Returns (WF_L, WF_R, E(N_part+1) - E(N_part))."""
+    H = np.zeros((L, L), dtype=np.complex128)
+    for I in range(L):
+        J = (I + 1) % L
+        if L == 2 and I == 1:
+            continue
+        z = -t * (np.exp(2j * np.pi * 0.01) if J < I else 1.0)
+        H[I, J] += z
+        H[J, I] += np.conj(z)
+    E, Uv = np.linalg.eigh(H)
+    P = np.asfortranarray(Uv[:, :n_part])
+    return [P.copy(order="F") for _ in range(N_FL)], [P.copy(order="F") for _ in range(N_FL)], float(E[n_part] - E[n_part - 1])
+
+
+def hubbard_chain(L: int, beta: float, dtau: float, U: float = 4.0, t: float = 1.0, Mz: bool = True, symm: bool = True,
+                  projector: bool = False, theta: float = 5.0) -> Model:
+    """N_leg_ladder with L2=1 and Checkerboard=.false. as in testsuite/test_vs_ed/test_specs.yaml:24-94
+    (dense hopping matrix, periodic chain; with Symm the half-step similarity is applied before measuring).
+    projector=True: Hamiltonian_Hubbard_smod.F90:236-239 (Thtrot = nint(theta/dtau), Ltrot += 2 Thtrot) with the trial wave function of Ham_Trial
+    (N_part = Ndim/2)."""
     Ndim = L
     Ltrot = int(round(beta / dtau))
+    Thtrot = 0
+    if projector:
+        Thtrot = int(round(theta / dtau)); Ltrot += 2 * Thtrot
     N_FL = 2 if Mz else 1
     row = []
     for nf in range(N_FL):
@@ -394,8 +418,12 @@ def hubbard_chain(L: int, beta: float, dtau: float, U: float = 4.0, t: float = 1
             op = Op_make(1); op.P[0] = I; op.O[0, 0] = 1.0; op.alpha = -0.5
             op.g = np.sqrt(complex(-dtau * U / 2.0, 0.0)); op.type = 2
             Op_set(op); Op_V.append([op])
-    return Model(name="Hubbard_chain", Ndim=Ndim, N_FL=N_FL, N_SUN=1 if Mz else 2, Ltrot=Ltrot, Dtau=dtau, Symm=symm,
-                 Op_V=Op_V, Op_T=[row], params=dict(L=L, beta=beta, dtau=dtau, U=U, t=t, Mz=Mz, symm=symm))
+    m = Model(name="Hubbard_chain", Ndim=Ndim, N_FL=N_FL, N_SUN=1 if Mz else 2, Ltrot=Ltrot, Dtau=dtau, Symm=symm,
+              Op_V=Op_V, Op_T=[row], params=dict(L=L, beta=beta, dtau=dtau, U=U, t=t, Mz=Mz, symm=symm, projector=projector, theta=theta))
+    if projector:
+        m.Projector, m.Thtrot = True, Thtrot
+        m.WF_L, m.WF_R, m.params["wf_degen"] = trial_wave_function_chain(L, Ndim // 2, N_FL, t)
+    return m
 
 
 def kondo_square(L1: int, L2: int, beta: float, dtau: float = 0.1, t: float = 1.0, J: float = 2.0, Uf: float = 1.0,
@@ -609,6 +637,31 @@ def z2_gauge_square(L1: int, L2: int, beta: float, dtau: float = 0.1, t_z2: floa
     """The Z2-gauge sector of Hamiltonian_Z2_Matter (Ham_T = 0, hence Ham_J = Ham_h = 0, :163-166): only the Ising bond fields the fermions
     hop through (+ optional Hubbard vertices); all fields are visited sequentially, N_Global_tau = 0."""
     return z2_matter_square(L1, L2, beta, dtau, t=0.0, t_z2=t_z2, chem=chem, U=U, J=0.0, K=K, h=0.0, g=g, N_SUN=N_SUN, propose_s0=propose_s0)
+
+
+def obs_scal_tables(model: Model) -> dict:
+    """Tables for alf_b200_set_obs_scal_tables: what ham%Obser of the Hubbard Hamiltonian accumulates as Kin, Pot, Ener
+    (Prog/Hamiltonians/Hamiltonian_Hubbard_smod.F90:738-772).  Kin = N_SUN sum_{nf,i,j} T(i,j,nf) GRC(i,j,nf) with the hopping matrix
+    T = sum_nc Op_T(nc)%O g_nc / (-dtau) (Predefined_Hoppings_Compute_Kin, Predefined_Hop_mod.F90:1850-1959: per bond Z GRC(I1,J1) + conj(Z) GRC(J1,I1),
+    per site T_Loc GRC(I1,I1); the checkerboard / symmetric decomposition only splits the same matrix over several Op_T);
+    Pot = ham_U sum_i GRC(i,i,1) GRC(i,i,dec), dec = 2 for Mz (N_FL = 2) else 1.  Indices 1-based."""
+    N, F = model.Ndim, model.N_FL
+    ki, kj, kf, kc = [], [], [], []
+    for nf in range(F):
+        Tm = np.zeros((N, N), dtype=np.complex128)
+        for row in model.Op_T:
+            op = row[nf]
+            P = np.asarray(op.P) - 1
+            Tm[np.ix_(P, P)] += op.O * (op.g / (-model.Dtau))
+        for i, j in zip(*np.nonzero(np.abs(Tm) > 1e-14)):
+            ki.append(i + 1); kj.append(j + 1); kf.append(nf + 1); kc.append(Tm[i, j])
+    p1, f1, p2, f2, pc = [], [], [], [], []
+    U = model.params.get("U", 0.0) if model.name.startswith("Hubbard") else 0.0
+    if abs(U) > EPS_SMALL:
+        dec = 2 if F == 2 else 1
+        for i in range(1, N + 1):
+            p1.append(i); f1.append(1); p2.append(i); f2.append(dec); pc.append(complex(U))
+    return dict(kin_i=ki, kin_j=kj, kin_nf=kf, kin_coef=kc, pot_i1=p1, pot_nf1=f1, pot_i2=p2, pot_nf2=f2, pot_coef=pc)
 
 
 def flatten_ops(model: Model):

@@ -189,8 +189,18 @@ int alf_b200_get_taum(alf_b200_handle* h, int chain, double* out, long cap_compl
 /* the four matrices right after every CGR2_2 of TAU_M (freshly recomputed; not symmetrised), same layout */
 int alf_b200_get_taum_fresh(alf_b200_handle* h, int chain, double* out, long cap_complex, long* n_complex);
 
-/* ---- device-side scalar observables accumulated where main.F90 calls ham%Obser (:757-773,:789-802).
- * Layout: [0] N_meas, [1..2] sum phase/|Re phase| sign, then per chain-summed: Kin, Pot, Part, Ener (re,im each). */
+/* ---- device-side scalar observables accumulated where main.F90 calls ham%Obser (:757-773,:789-802), summed over the chains of the handle.
+ * Layout (alf_b200_obs_size() = 16 doubles): [0] N_meas (chain-measurements), [1] sum ZS, [2..3] Part, [4..5] Kin, [6..7] Pot, [8..9] Ener
+ * (re, im each; every entry is sum Obs ZP ZS with ZP = Phase / Re Phase, ZS = sign Re Phase: Hamiltonian_Hubbard_smod.F90:711-772).
+ * Part = N_SUN sum_nf sum_i GRC(i,i,nf) needs no model input.  Kin, Pot and Ener = Kin + Pot are model specific and are handed over as
+ * tables, evaluated on the Green function ham%Obser receives (Hop_mod_Symm(GR) when Symm, main.F90:761-764), with
+ * GRC(i,j,nf) = delta_ij - GR(j,i,nf):
+ *   Kin = N_SUN sum_t kin_coef[t] GRC(kin_i[t], kin_j[t], kin_nf[t])        Predefined_Hoppings_Compute_Kin, Prog/Predefined_Hop_mod.F90:1850-1959:
+ *                                                                            per bond Z GRC(I1,J1,nf) + conj(Z) GRC(J1,I1,nf), per site T_Loc GRC(I1,I1,nf)
+ *   Pot = sum_t pot_coef[t] GRC(i1,i1,nf1) GRC(i2,i2,nf2)                   Hamiltonian_Hubbard_smod.F90:744-760 (ham_U n_up n_down), Kondo / tV likewise
+ * Indices and flavors 1-based, coefficients complex.  n_kin = n_pot = 0 switches the tables off. */
+int alf_b200_set_obs_scal_tables(alf_b200_handle* h, int n_kin, const int* kin_i, const int* kin_j, const int* kin_nf, const double* kin_coef,
+                                 int n_pot, const int* pot_i1, const int* pot_nf1, const int* pot_i2, const int* pot_nf2, const double* pot_coef);
 int alf_b200_obs_size(const alf_b200_handle* h);
 int alf_b200_obs_reset(alf_b200_handle* h);
 int alf_b200_obs_device_ptr(alf_b200_handle* h, double** dptr, long* n_doubles);  /* for the NCCL bin reduction */

@@ -1036,7 +1036,9 @@ struct Oracle {
 
   std::vector<cd> eq_capture; int eq_capture_on = 0;   // G handed to ham%Obser: [visit][nf][N*N]
   bool obse_on = false; std::vector<cd> obse_acc, obse_bg; double obse_cnt[2] = {0, 0};      // equal-time lattice observables (lattice tables: obst_* below)
-  double obs_scal[4] = {0, 0, 0, 0};   // [0] N_meas, [1] sum ZS, [2..3] sum Part ZP ZS  (same model-independent scalars as the device)
+  double obs_scal[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};   // [0] N_meas, [1] sum ZS, [2..3] Part, [4..5] Kin, [6..7] Pot, [8..9] Ener (each sum Obs ZP ZS)
+  // Kin / Pot of ham%Obser as tables (0-based): Predefined_Hoppings_Compute_Kin (Prog/Predefined_Hop_mod.F90:1850-1959), Hamiltonian_Hubbard_smod.F90:738-772
+  std::vector<int> kin_idx, pot_idx; std::vector<cd> kin_coef, pot_coef;
   void obser_hook(int ntau1) {
     const int lobs_st = projector ? thtrot + 1 : 1, lobs_en = projector ? ltrot - thtrot : ltrot;   // QMC_runtime_var_mod.F90:156-189
     if (ntau1 < lobs_st || ntau1 > lobs_en) return;
@@ -1044,6 +1046,18 @@ struct Oracle {
       cd tr = 0; for (int nf = 0; nf < n_fl; ++nf) for (int i = 0; i < ndim; ++i) tr += cd(1, 0) - GR[nf][i + (size_t)i * ndim];
       cd ZP = Phase / Phase.real(); double ZS = Phase.real() >= 0 ? 1.0 : -1.0; cd v = tr * (double)n_sun * ZP * ZS;
       obs_scal[0] += 1; obs_scal[1] += ZS; obs_scal[2] += v.real(); obs_scal[3] += v.imag();
+    }
+    if (!kin_coef.empty() || !pot_coef.empty()) {   // Zkin, ZPot, Ener on GR_Tilde (main.F90:761-764), GRC(I,J) = delta_IJ - GR(J,I)
+      const int N = ndim; std::vector<std::vector<cd>> GRt(n_fl, std::vector<cd>((size_t)N * N));
+      for (int nf = 0; nf < n_fl; ++nf) { if (symm) hop_symm(GRt[nf].data(), GR[nf].data(), nf); else GRt[nf] = GR[nf]; }
+      auto grc = [&](int i, int j, int nf) { return ((i == j) ? cd(1, 0) : cd(0, 0)) - GRt[nf][j + (size_t)i * N]; };
+      cd Zkin = 0, ZPot = 0;
+      for (size_t t = 0; t < kin_coef.size(); ++t) Zkin += kin_coef[t] * grc(kin_idx[3 * t], kin_idx[3 * t + 1], kin_idx[3 * t + 2]);
+      Zkin *= (double)n_sun;
+      for (size_t t = 0; t < pot_coef.size(); ++t) ZPot += pot_coef[t] * grc(pot_idx[4 * t], pot_idx[4 * t], pot_idx[4 * t + 1]) * grc(pot_idx[4 * t + 2], pot_idx[4 * t + 2], pot_idx[4 * t + 3]);
+      cd ZP = Phase / Phase.real(); double ZS = Phase.real() >= 0 ? 1.0 : -1.0;
+      const cd k = Zkin * ZP * ZS, p = ZPot * ZP * ZS;
+      obs_scal[4] += k.real(); obs_scal[5] += k.imag(); obs_scal[6] += p.real(); obs_scal[7] += p.imag(); obs_scal[8] += (k + p).real(); obs_scal[9] += (k + p).imag();
     }
     if (obse_on) {   // Predefined_Obs_eq_Green / SpinMz / SpinSUN / Den_measure (Prog/Predefined_Obs_mod.F90:77-325) on GR_Tilde (main.F90:761-764)
       const int N = ndim, nu = lat_n_unit, nb = lat_norb, nb2 = nb * nb;
@@ -1460,6 +1474,12 @@ void orc_get_obs_tau(void* h, double* acc, double* bg, double* cnt) {
   cnt[0] = o->obst_cnt[0]; cnt[1] = o->obst_cnt[1];
 }
 void orc_get_obs(void* h, double* out) { Oracle* o = (Oracle*)h; for (int i = 0; i < 4; ++i) out[i] = o->obs_scal[i]; }
+void orc_get_obs_full(void* h, double* out) { Oracle* o = (Oracle*)h; for (int i = 0; i < 10; ++i) out[i] = o->obs_scal[i]; }
+void orc_set_obs_scal_tables(void* h, int n_kin, const int* ki, const int* kj, const int* knf, const double* kc, int n_pot, const int* p1, const int* f1, const int* p2, const int* f2, const double* pc) {
+  Oracle* o = (Oracle*)h; o->kin_idx.clear(); o->kin_coef.clear(); o->pot_idx.clear(); o->pot_coef.clear();
+  for (int t = 0; t < n_kin; ++t) { o->kin_idx.push_back(ki[t] - 1); o->kin_idx.push_back(kj[t] - 1); o->kin_idx.push_back(knf[t] - 1); o->kin_coef.push_back(cd(kc[2 * t], kc[2 * t + 1])); }
+  for (int t = 0; t < n_pot; ++t) { o->pot_idx.push_back(p1[t] - 1); o->pot_idx.push_back(f1[t] - 1); o->pot_idx.push_back(p2[t] - 1); o->pot_idx.push_back(f2[t] - 1); o->pot_coef.push_back(cd(pc[2 * t], pc[2 * t + 1])); }
+}
 void orc_eq_capture(void* h, int on) { Oracle* o = (Oracle*)h; o->eq_capture_on = on; o->eq_capture.clear(); }
 long orc_eq_get(void* h, double* out, long cap_complex) {
   Oracle* o = (Oracle*)h; long n = (long)o->eq_capture.size();

@@ -247,6 +247,19 @@ class Oracle:
         lib().orc_get_obs(self.h, _d(out))
         return out
 
+    def set_obs_scal_tables(self, tab):
+        """Kin / Pot tables of ham%Obser (see alf_b200_set_obs_scal_tables; `tab` = alf_b200.model.obs_scal_tables(model))."""
+        a = {k: np.ascontiguousarray(tab[k], dtype=np.int32) for k in ("kin_i", "kin_j", "kin_nf", "pot_i1", "pot_nf1", "pot_i2", "pot_nf2")}
+        kc = np.ascontiguousarray(tab["kin_coef"], dtype=np.complex128); pc = np.ascontiguousarray(tab["pot_coef"], dtype=np.complex128)
+        p = lambda x: x.ctypes.data_as(_ip)
+        lib().orc_set_obs_scal_tables(self.h, int(kc.size), p(a["kin_i"]), p(a["kin_j"]), p(a["kin_nf"]), _d(kc), int(pc.size), p(a["pot_i1"]), p(a["pot_nf1"]), p(a["pot_i2"]), p(a["pot_nf2"]), _d(pc))
+
+    def obs_full(self):
+        """[N_meas, sum sign, Part(re, im), Kin(re, im), Pot(re, im), Ener(re, im)]."""
+        out = np.zeros(10)
+        lib().orc_get_obs_full(self.h, _d(out))
+        return out
+
     def obs_tau_enable(self):
         n_unit, norb, cell, orb, imj = self.m.lattice_tables()
         imj_f = np.ascontiguousarray(imj.T)
