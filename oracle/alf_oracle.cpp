@@ -1473,6 +1473,8 @@ void orc_get_obs_tau(void* h, double* acc, double* bg, double* cnt) {
   Oracle* o = (Oracle*)h; std::memcpy(acc, o->obst_acc.data(), sizeof(cd) * o->obst_acc.size()); std::memcpy(bg, o->obst_bg.data(), sizeof(cd) * o->obst_bg.size());
   cnt[0] = o->obst_cnt[0]; cnt[1] = o->obst_cnt[1];
 }
+// (prod_nf Op_phase)^N_SUN on the current fields, Phase = 1 on entry (testsuite/Prog.tests/9-Op-Phase.F90)
+void orc_op_phase_total(void* h, double* out) { Oracle* o = (Oracle*)h; cd ph = 1; for (int nf = 0; nf < o->n_fl; ++nf) o->op_phase(ph, nf); ph = std::pow(ph, o->n_sun); out[0] = ph.real(); out[1] = ph.imag(); }
 void orc_get_obs(void* h, double* out) { Oracle* o = (Oracle*)h; for (int i = 0; i < 4; ++i) out[i] = o->obs_scal[i]; }
 void orc_get_obs_full(void* h, double* out) { Oracle* o = (Oracle*)h; for (int i = 0; i < 10; ++i) out[i] = o->obs_scal[i]; }
 void orc_set_obs_scal_tables(void* h, int n_kin, const int* ki, const int* kj, const int* knf, const double* kc, int n_pot, const int* p1, const int* f1, const int* p2, const int* f2, const double* pc) {
@@ -1527,6 +1529,14 @@ void orc_qdrp(int ndim, int npart, double* Mat, double* D, int* ipvt, double* ta
   for (int i = 0; i < npart; ++i) ipvt[i] = 0;
   qdrp_decompose(ndim, npart, (cd*)Mat, Dc.data(), ipvt, (cd*)tau, W, lw);
   for (int i = 0; i < npart; ++i) { D[2 * i] = Dc[i].real(); D[2 * i + 1] = Dc[i].imag(); }
+}
+// testsuite/Prog.tests/16-get-blocks.F90, 17-solve-extended-system.F90: the two helpers of CGR2_2 on their own
+void orc_get_blocks(int lq, const double* inp, double* a, double* b, double* c, double* d) { get_blocks((cd*)a, (cd*)b, (cd*)c, (cd*)d, (const cd*)inp, lq); }
+void orc_solve_extended_system(int lq, double* hlp, const double* uct, const double* vinv, double* input /* 2lq x 2lq, QDRP-decomposed in place */, double* Dout) {
+  const int lq2 = 2 * lq; std::vector<cd> W, D(lq2), tau(lq2); std::vector<int> ipvt(lq2, 0); int lw;
+  qdrp_decompose(lq2, lq2, (cd*)input, D.data(), ipvt.data(), tau.data(), W, lw);
+  solve_extended_system((cd*)hlp, (const cd*)uct, (const cd*)vinv, (cd*)input, D.data(), tau.data(), ipvt.data(), lq, W, lw);
+  for (int i = 0; i < lq2; ++i) { Dout[2 * i] = D[i].real(); Dout[2 * i + 1] = D[i].imag(); }
 }
 static void load_udv(UDV& s, int n, char side, const double* U, const double* D, const double* V) {
   s.alloc(n); s.side = side; std::memcpy(s.U.data(), U, sizeof(cd) * (size_t)n * n); std::memcpy(s.V.data(), V, sizeof(cd) * (size_t)n * n);

@@ -293,6 +293,10 @@ class Oracle:
         nv = n // (self.m.N_FL * nn)
         return buf.reshape(nv, self.m.N_FL, self.N, self.N).transpose(0, 1, 3, 2)
 
+    def op_phase_total(self) -> complex:
+        """(prod_nf Op_phase(nf))^N_SUN on the current field configuration, starting from Phase = 1 (Prog/Operator_mod.F90:160-181)."""
+        p = np.zeros(2); lib().orc_op_phase_total(self.h, _d(p)); return complex(p[0], p[1])
+
     # --- building blocks
     def hop_apply(self, which: int, nf: int, A):
         A = _cplx(A).copy(order="F")
@@ -386,6 +390,22 @@ def cgr2_2(U2, D2, V2, U1, D1, V1, stab3=False):
     d2 = np.ascontiguousarray(D2, dtype=np.complex128); d1 = np.ascontiguousarray(D1, dtype=np.complex128)
     lib().orc_cgr2_2(n, int(stab3), _d(a[0]), _d(d2), _d(a[1]), _d(a[2]), _d(d1), _d(a[3]), *[_d(o) for o in outs])
     return dict(GRT0=outs[0], GR00=outs[1], GRTT=outs[2], GR0T=outs[3])
+
+
+def get_blocks(V):
+    """get_blocks (Prog/cgr2_2_mod.F90:55-72): (GR00, GR0T, GRT0, GRTT) = the four LQ x LQ blocks of the 2LQ x 2LQ matrix V."""
+    V = _cplx(V); lq = V.shape[0] // 2
+    out = [np.zeros((lq, lq), dtype=np.complex128, order="F") for _ in range(4)]
+    lib().orc_get_blocks(int(lq), _d(V), *[_d(o) for o in out])
+    return out
+
+
+def solve_extended_system(UCT, VINV, inp):
+    """QDRP_decompose(inp) followed by solve_extended_System (Prog/cgr2_2_mod.F90:155-191) as in testsuite/Prog.tests/17-solve-extended-system.F90."""
+    lq = UCT.shape[0]; inp = _cplx(inp).copy(order="F")
+    hlp = np.zeros((2 * lq, 2 * lq), dtype=np.complex128, order="F"); D = np.zeros(2 * lq, dtype=np.complex128)
+    lib().orc_solve_extended_system(int(lq), _d(hlp), _d(_cplx(UCT)), _d(_cplx(VINV)), _d(inp), _d(D))
+    return hlp
 
 
 def cgrp(UR, UL):
