@@ -181,12 +181,14 @@ class AlfB200:
         imj_f = np.ascontiguousarray(imj.T)                       # Fortran order: imj(I, J) at I-1 + (J-1) n_unit
         self._ck(lib().alf_b200_set_lattice(self.h, int(n_unit), int(norb), cell.ctypes.data_as(_ip), orb.ctypes.data_as(_ip), imj_f.ctypes.data_as(_ip)))
         self._ck(lib().alf_b200_obs_tau_enable(self.h, int(on)))
+        self._obs_tau_on = bool(on) or getattr(self, "_obs_tau_on", False)
 
     def obs_eq_enable(self, on=True):
         n_unit, norb, cell, orb, imj = self.m.lattice_tables()
         imj_f = np.ascontiguousarray(imj.T)
         self._ck(lib().alf_b200_set_lattice(self.h, int(n_unit), int(norb), cell.ctypes.data_as(_ip), orb.ctypes.data_as(_ip), imj_f.ctypes.data_as(_ip)))
         self._ck(lib().alf_b200_obs_eq_enable(self.h, int(on)))
+        self._obs_eq_on = bool(on) or getattr(self, "_obs_eq_on", False)
 
     def obs_eq(self):
         n_unit, norb = self.m.latt.N, self.m.n_orb
@@ -272,6 +274,33 @@ class AlfB200:
         U = np.zeros((self.N, self.N), dtype=np.complex128, order="F"); V = U.copy(order="F"); D = np.zeros(self.N, dtype=np.complex128)
         self._ck(lib().alf_b200_get_udv(self.h, int(which), int(nst), int(chain), int(nf), _d(U), _d(D), _d(V)))
         return U, D, V
+
+    def set_udv(self, which, nst, chain, nf, U, D, V=None):
+        """Host UDV_State -> the handle's udvl (0) / udvr (1) / udvst(nst) (2) of one chain and flavor (compat mode)."""
+        U = np.asfortranarray(U, dtype=np.complex128); D = np.ascontiguousarray(D, dtype=np.complex128)
+        Vp = _d(np.asfortranarray(V, dtype=np.complex128)) if V is not None else None
+        self._ck(lib().alf_b200_set_udv(self.h, int(which), int(nst), int(chain), int(nf), _d(U), _d(D), Vp))
+
+    # ---- multi-GPU bin reduction behind the C-ABI (NCCL)
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        buf = C.create_string_buffer(128)
+        rc = lib().alf_b200_comm_unique_id(buf)
+        if rc != 0:
+            raise AlfError(rc, "alf_b200_comm_unique_id (is libnccl.so.2 available?)")
+        return buf.raw
+
+    def comm_init(self, nranks, rank, uid: bytes):
+        self._ck(lib().alf_b200_comm_init(self.h, int(nranks), int(rank), C.create_string_buffer(uid, 128)))
+
+    def reduce_bins(self, root=0):
+        self._ck(lib().alf_b200_reduce_bins(self.h, int(root)))
+
+    def reduce_control(self, root=0):
+        out = np.zeros(16)
+        self._ck(lib().alf_b200_reduce_control(self.h, int(root), _d(out)))
+        keys = ["XMEANG", "XMAXG", "NCG", "XMAXP", "XMEAN_tau", "XMAX_tau", "NCG_tau", "NC_up", "ACC_up", "NC_eff_up", "ACC_eff_up", "nan", "unstable", "flushes"]
+        return dict(zip(keys, out))
 
     def control(self):
         out = np.zeros(16)

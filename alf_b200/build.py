@@ -41,7 +41,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         return o
     with ThreadPoolExecutor(max_workers=len(UNITS)) as ex:
         objs = list(ex.map(cc, UNITS))
-    subprocess.check_call([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB] + objs)
+    subprocess.check_call([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB] + objs + ["-ldl"])
     return LIB
 
 

@@ -1,5 +1,7 @@
 // alf_b200.cu -- the C-ABI (include/alf_b200.h).  The engine templates are instantiated in alf_inst_real.cu / alf_inst_cplx.cu.
 // There is no CPU fallback: without a CUDA device every entry point fails with ALF_ERROR_CUDA.
+#include <dlfcn.h>
+#include <nccl.h>        // types only: the symbols are resolved with dlopen (see NcclApi)
 #include "alf_engine.cuh"
 #include "alf_inst.h"
 
@@ -57,6 +59,7 @@ int alf_b200_destroy(alf_b200_handle* h) {
   if (!h) return ALF_OK;
   cudaSetDevice(h->device);
   if (t_prof == &h->prof) t_prof = nullptr;          // the launch-accounting pointer must not outlive its handle
+  alf_b200_comm_destroy(h); if (h->d_ctlred) cudaFree(h->d_ctlred);
   h->eng.reset();
   if (h->d_fields_c) cudaFree(h->d_fields_c);
   if (h->d_fields) cudaFree(h->d_fields); if (h->d_rng) cudaFree(h->d_rng); if (h->d_phase) cudaFree(h->d_phase);
@@ -440,6 +443,11 @@ int alf_b200_get_phase(alf_b200_handle* h, double* out) { API_BEGIN(h) NEED_FINA
 int alf_b200_get_udv(alf_b200_handle* h, int which, int nst, int chain, int nf, double* U, double* D, double* V) {
   API_BEGIN(h) NEED_FINAL(h) h->eng->get_udv(which, nst, chain, nf, reinterpret_cast<cd*>(U), reinterpret_cast<cd*>(D), reinterpret_cast<cd*>(V)); API_END(h)
 }
+int alf_b200_set_udv(alf_b200_handle* h, int which, int nst, int chain, int nf, const double* U, const double* D, const double* V) {
+  API_BEGIN(h) NEED_FINAL(h)
+  if (chain < 0 || chain >= h->n_chains || nf < 1 || nf > h->n_fl || which < 0 || which > 2 || !U || !D) return ALF_ERROR_GENERIC;
+  h->eng->set_udv(which, nst, chain, nf, reinterpret_cast<const cd*>(U), reinterpret_cast<const cd*>(D), reinterpret_cast<const cd*>(V)); API_END(h)
+}
 int alf_b200_get_control(alf_b200_handle* h, double* out) {
   API_BEGIN(h) NEED_FINAL(h)
   const int C = h->n_chains; std::vector<double> c((size_t)C * 8); std::vector<unsigned long long> k((size_t)C * 5);
@@ -453,6 +461,82 @@ int alf_b200_get_control(alf_b200_handle* h, double* out) {
     int fl = (int)c[ch * 8 + 7]; if (fl & 1) out[11] = 1.0; if (fl & 2) out[12] = 1.0;
     out[13] += (double)k[(size_t)4 * C + ch];
   }
+  API_END(h)
+}
+// ---- NCCL bin / control reduction (symbols resolved at run time: the library loads without NCCL on a single-GPU host)
+namespace {
+struct NcclApi {
+  void* lib = nullptr; bool tried = false;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*Reduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr; ncclResult_t (*GroupEnd)() = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+  bool load() {
+    if (tried) return lib != nullptr;
+    tried = true;
+    for (const char* nm : {"libnccl.so.2", "libnccl.so"}) { lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL); if (lib) break; }
+    if (!lib) return false;
+#define NCCL_SYM(F) *(void**)(&F) = dlsym(lib, "nccl" #F); if (!F) { lib = nullptr; return false; }
+    NCCL_SYM(GetUniqueId) NCCL_SYM(CommInitRank) NCCL_SYM(CommDestroy) NCCL_SYM(Reduce) NCCL_SYM(GroupStart) NCCL_SYM(GroupEnd) NCCL_SYM(GetErrorString)
+#undef NCCL_SYM
+    return true;
+  }
+};
+NcclApi g_nccl;
+#define NCK(h, x) do { ncclResult_t r_ = (x); if (r_ != ncclSuccess) { (h)->err = std::string("NCCL: ") + g_nccl.GetErrorString(r_); return ALF_ERROR_CUDA; } } while (0)
+}
+int alf_b200_comm_unique_id(char* id) {
+  if (!id || !g_nccl.load()) return ALF_ERROR_CUDA;
+  ncclUniqueId u; if (g_nccl.GetUniqueId(&u) != ncclSuccess) return ALF_ERROR_CUDA;
+  static_assert(sizeof(ncclUniqueId) == 128, "NCCL unique id size"); std::memcpy(id, &u, 128); return ALF_OK;
+}
+int alf_b200_comm_init(alf_b200_handle* h, int nranks, int rank, const char* id) {
+  API_BEGIN(h) NEED_FINAL(h)
+  if (nranks < 1 || rank < 0 || rank >= nranks || !id) return ALF_ERROR_GENERIC;
+  if (!g_nccl.load()) { h->err = "comm_init: libnccl.so.2 not found"; return ALF_ERROR_CUDA; }
+  if (h->comm) { g_nccl.CommDestroy((ncclComm_t)h->comm); h->comm = nullptr; }
+  ncclUniqueId u; std::memcpy(&u, id, 128); ncclComm_t c = nullptr;
+  NCK(h, g_nccl.CommInitRank(&c, nranks, u, rank));
+  h->comm = c; h->comm_nranks = nranks; h->comm_rank = rank;
+  if (!h->d_ctlred) CK(cudaMalloc(&h->d_ctlred, sizeof(double) * 32));
+  API_END(h)
+}
+int alf_b200_comm_destroy(alf_b200_handle* h) {
+  if (!h) return ALF_OK;
+  if (h->comm && g_nccl.lib) { cudaSetDevice(h->device); cudaStreamSynchronize(h->stream); g_nccl.CommDestroy((ncclComm_t)h->comm); }
+  h->comm = nullptr; h->comm_nranks = 1; h->comm_rank = 0; return ALF_OK;
+}
+int alf_b200_reduce_bins(alf_b200_handle* h, int root) {
+  API_BEGIN(h) NEED_FINAL(h)
+  if (!h->comm || h->comm_nranks <= 1) return ALF_OK;
+  if (root < 0 || root >= h->comm_nranks) return ALF_ERROR_GENERIC;
+  ncclComm_t c = (ncclComm_t)h->comm;
+  struct Buf { double* p; size_t n; };
+  std::vector<Buf> bufs; bufs.push_back({h->d_obs, (size_t)h->obs_size});
+  if (h->d_obst_acc) { bufs.push_back({h->d_obst_acc, obst_acc_len(h)}); bufs.push_back({h->d_obst_bg, obst_bg_len(h)}); bufs.push_back({h->d_obst_cnt, 2}); }
+  if (h->d_obse_acc) { bufs.push_back({h->d_obse_acc, (size_t)2 * OBST_NCH * h->norb * h->norb * h->n_unit}); bufs.push_back({h->d_obse_bg, (size_t)2 * 2 * h->norb}); bufs.push_back({h->d_obse_cnt, 2}); }
+  NCK(h, g_nccl.GroupStart());
+  for (const Buf& b : bufs) NCK(h, g_nccl.Reduce(b.p, b.p, b.n, ncclDouble, ncclSum, root, c, h->stream));
+  NCK(h, g_nccl.GroupEnd());
+  CK(cudaStreamSynchronize(h->stream));
+  h->n_reduce_calls++;
+  API_END(h)
+}
+int alf_b200_reduce_control(alf_b200_handle* h, int root, double* out) {
+  if (!h || !out) return ALF_ERROR_GENERIC;
+  int rc = alf_b200_get_control(h, out); if (rc != ALF_OK) return rc;
+  API_BEGIN(h)
+  if (!h->comm || h->comm_nranks <= 1) return ALF_OK;
+  ncclComm_t c = (ncclComm_t)h->comm;
+  CK(cudaMemcpyAsync(h->d_ctlred, out, sizeof(double) * 16, cudaMemcpyHostToDevice, h->stream)); CK(cudaMemcpyAsync(h->d_ctlred + 16, out, sizeof(double) * 16, cudaMemcpyHostToDevice, h->stream));
+  NCK(h, g_nccl.GroupStart());
+  NCK(h, g_nccl.Reduce(h->d_ctlred, h->d_ctlred, 16, ncclDouble, ncclSum, root, c, h->stream));
+  NCK(h, g_nccl.Reduce(h->d_ctlred + 16, h->d_ctlred + 16, 16, ncclDouble, ncclMax, root, c, h->stream));
+  NCK(h, g_nccl.GroupEnd());
+  double r[32]; CK(cudaMemcpyAsync(r, h->d_ctlred, sizeof(double) * 32, cudaMemcpyDeviceToHost, h->stream)); CK(cudaStreamSynchronize(h->stream));
+  if (h->comm_rank == root) { for (int i = 0; i < 16; ++i) out[i] = r[i]; for (int i : {1, 3, 5, 11, 12}) out[i] = r[16 + i]; }      // maxima as in Control_Print
   API_END(h)
 }
 int alf_b200_accept_log(alf_b200_handle* h, int enable) {

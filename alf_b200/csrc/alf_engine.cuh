@@ -130,6 +130,7 @@ struct EngineBase {
   virtual void get_green(int chain, int nf, int symm, cd* out) = 0;
   virtual void set_green(int chain, int nf, const cd* in) = 0;
   virtual void get_udv(int which, int nst, int chain, int nf, cd* U, cd* D, cd* V) = 0;
+  virtual void set_udv(int which, int nst, int chain, int nf, const cd* U, const cd* D, const cd* V) = 0;
   virtual void hop_apply(int which, int nf, cd* A) = 0;
   virtual void fermion_det(double* logdet, cd* phase) = 0;
   virtual void langevin_get_forces(cd* out) = 0;
@@ -154,6 +155,7 @@ struct alf_b200_handle {
   double* d_ctl = nullptr;            // per chain: 0 XMEANG 1 XMAXG 2 NCG 3 XMAXP 4 XMEAN_tau 5 XMAX_tau 6 NCG_tau 7 flags(nan=1, unstable=2)
   uint8_t* d_acclog = nullptr; long acclog_per_chain = 0; long acclog_pos = 0; bool acclog_on = false;
   double* d_obs = nullptr; int obs_size = 0;
+  void* comm = nullptr; int comm_nranks = 1, comm_rank = 0; double* d_ctlred = nullptr; long n_reduce_calls = 0;   // NCCL communicator of the bin reduction (alf_b200_comm_init)
   // model-specific scalar observables as tables (alf_b200_set_obs_scal_tables): Kin terms (i, j, nf, coef), Pot terms (i1, nf1, i2, nf2, coef); 0-based
   int n_kin = 0, n_pot = 0; int *d_kin_idx = nullptr, *d_pot_idx = nullptr; cplx *d_kin_coef = nullptr, *d_pot_coef = nullptr;
   int taum_every = 0; std::vector<std::vector<cd>> taum_host, taum_fresh_host;   // per chain captured matrices
@@ -396,6 +398,11 @@ __global__ void k_fdet_build(T* __restrict__ TP, const T* __restrict__ U, const 
     TP[e] = (d <= 1.0) ? U[e] + V[e] * d : U[e] * (1.0 / d) + V[e];
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) { double s = 0.0; for (int j = 0; j < n; ++j) if (D[j] > 1.0) s += log(D[j]); extra[b] = s; }
+}
+// det U / |det U| of a matrix from the outputs of its pivoted QR (det R > 0 after the D scaling up to the unit-modulus diagonal)
+static __global__ void k_det_phase(const QrOut* __restrict__ q, cplx* __restrict__ det, int nm) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x; if (b >= nm) return;
+  const cplx p = (q[b].detq * q[b].diag_phase) * q[b].perm_sign; const double a = abs_(p); det[b] = cplx(p.x / a, p.y / a);
 }
 // log|det| = sum log Dq + extra (+ sum of the log D of the given states, projector);  phase = detq * diag_phase * perm_sign [* conj(det U)]
 static __global__ void k_fdet_finish(const double* __restrict__ Dq, int n, const QrOut* __restrict__ q, const double* __restrict__ extra, const cplx* __restrict__ detU,
@@ -1315,6 +1322,23 @@ struct Engine : EngineBase {
     CK(cudaMemcpyAsync(t.data(), u.V + n2 * b, sizeof(T) * n2, cudaMemcpyDeviceToHost, st)); sync(); for (long i = 0; i < n2; ++i) V[i] = from_T<T>(t[i]);
     CK(cudaMemcpyAsync(d.data(), u.D + (long)N * b, sizeof(double) * N, cudaMemcpyDeviceToHost, st)); sync(); for (int i = 0; i < N; ++i) D[i] = cd(d[i], 0.0);
   }
+  // host UDV_State -> device (compat mode: WRAPUR / WRAPUL / CGR on the caller's states); det U is recomputed on the device
+  void set_udv(int which, int nst, int chain, int nf, const cd* U, const cd* D, const cd* V) override {
+    UdvDev<T>& u = which == 0 ? udvl : which == 1 ? udvr : udvst[nst - 1];
+    const long b = (long)chain * F + (nf - 1);
+    std::vector<T> t(n2); std::vector<double> d(N);
+    for (long i = 0; i < n2; ++i) t[i] = to_T<T>(U[i]);
+    CK(cudaMemcpyAsync(u.U + n2 * b, t.data(), sizeof(T) * n2, cudaMemcpyHostToDevice, st)); sync();
+    if (!proj && V) { for (long i = 0; i < n2; ++i) t[i] = to_T<T>(V[i]); CK(cudaMemcpyAsync(u.V + n2 * b, t.data(), sizeof(T) * n2, cudaMemcpyHostToDevice, st)); sync(); }
+    for (int i = 0; i < N; ++i) d[i] = D[i].real();
+    CK(cudaMemcpyAsync(u.D + (long)N * b, d.data(), sizeof(double) * N, cudaMemcpyHostToDevice, st)); sync();
+    if (!proj) {      // det U of this one matrix: pivoted QR of a copy (batch of one inside the workspace)
+      LaWork<T> w1; w1.alloc(N, 1, st);
+      CK(cudaMemcpyAsync(w1.W[0], u.U + n2 * b, sizeof(T) * n2, cudaMemcpyDeviceToDevice, st));
+      la_qrp<T>(w1, w1.W[0], N, N, w1.Dq);
+      k_det_phase<<<1, 32, 0, st>>>(w1.qrout, u.det + b, 1); sync(); w1.release();
+    }
+  }
   void hop_apply(int which, int nf, cd* A) override {
     // applies to matrix slot (chain 0, flavor nf) of scratch G2; the whole batch is processed (test entry point)
     std::vector<T> t(n2); for (long i = 0; i < n2; ++i) t[i] = to_T<T>(A[i]);
@@ -1384,8 +1408,15 @@ static void t_cgr(int n, int batch, int nvar, int stab, const double* UR, const 
   DevBuf<cplx> detR(batch), detL(batch), dz(batch);
   dUR.up(h2T<T>(UR, n2 * batch)); dVR.up(h2T<T>(VR, n2 * batch)); dUL.up(h2T<T>(UL, n2 * batch)); dVL.up(h2T<T>(VL, n2 * batch));
   { std::vector<double> a((size_t)n * batch), b((size_t)n * batch); for (size_t i = 0; i < a.size(); ++i) { a[i] = DR[2 * i]; b[i] = DL[2 * i]; } dDR.up(a); dDL.up(b); }
-  { std::vector<cplx> a(batch), b(batch); for (int i = 0; i < batch; ++i) { a[i] = cplx(detUR[2 * i], detUR[2 * i + 1]); b[i] = cplx(detUL[2 * i], detUL[2 * i + 1]); } detR.up(a); detL.up(b); }
   UdvDev<T> R, L; R.U = dUR.p; R.V = dVR.p; R.D = dDR.p; R.det = detR.p; L.U = dUL.p; L.V = dVL.p; L.D = dDL.p; L.det = detL.p;
+  if (detUR && detUL) { std::vector<cplx> a(batch), b(batch); for (int i = 0; i < batch; ++i) { a[i] = cplx(detUR[2 * i], detUR[2 * i + 1]); b[i] = cplx(detUL[2 * i], detUL[2 * i + 1]); } detR.up(a); detL.up(b); }
+  else {      // stand-alone call as the reference's CGR(PHASE, NVAR, GRUP, udvr, udvl): det U_R, det U_L (unit modulus) from a pivoted QR of a copy on the device
+    for (int q = 0; q < 2; ++q) {
+      CK(cudaMemcpyAsync(w.W[0], q ? dUL.p : dUR.p, sizeof(T) * n2 * batch, cudaMemcpyDeviceToDevice, 0));
+      la_qrp<T>(w, w.W[0], n, n, w.Dq);
+      k_det_phase<<<(batch + 127) / 128, 128>>>(w.qrout, q ? detL.p : detR.p, batch);
+    }
+  }
   la_cgr<T>(w, nvar, stab, R, L, dG.p, dz.p); CK(cudaDeviceSynchronize());
   T2h<T>(dG.down(), G); auto z = dz.down(); for (int i = 0; i < batch; ++i) { phase[2 * i] = z[i].x; phase[2 * i + 1] = z[i].y; }
   w.release();

@@ -2,8 +2,9 @@
 observable accumulators and of the control counters, which replaces ALF's MPI_REDUCE calls
 (Prog/observables_mod.F90:425-438,648-653,828-834; Prog/control_mod.F90:397-452) by NCCL over NVLink.
 
-The device buffers of the C-ABI handle are wrapped zero-copy (``__cuda_array_interface__``) so NCCL reads them in place.
-On CPU (tests, world_size-2 gloo) the same code path reduces host copies.
+On the GPU the reduction itself is done by the C-ABI (alf_b200_comm_init / alf_b200_reduce_bins / alf_b200_reduce_control: NCCL, in place on the
+handle's device buffers), so a Fortran or C++ host needs no Python; torch.distributed only carries the 128-byte communicator id.  On CPU
+(world_size-2 gloo tests) reduce_host_bins / reduce_control reduce host copies of the same accumulators.
 """
 from __future__ import annotations
 
@@ -50,18 +51,48 @@ def reduce_control(ctl_vec, dst: int = 0):
     return out
 
 
-def reduce_bins(g, obs_host, world: int, dst: int = 0):
-    """Per-bin reduction of the observable accumulators of handle `g` to rank `dst` (C1 of SURVEY 2.5).
-    With NCCL the handle's device buffer is reduced in place from HBM (no host staging); returns the host copy on `dst`."""
+def init_comm(handles, world: int, rank: int):
+    """One NCCL communicator per handle behind the C-ABI (alf_b200_comm_init).  The 128-byte unique ids are created on rank 0 and
+    handed to the other ranks through the process group that launched the job (ALF: MPI_BCAST) -- plumbing only."""
+    import torch.distributed as dist
+    if world <= 1:
+        return
+    ids = [type(handles[0]).comm_unique_id() for _ in handles] if rank == 0 else [None] * len(handles)
+    dist.broadcast_object_list(ids, src=0)
+    for g, uid in zip(handles, ids):
+        g.comm_init(world, rank, uid)
+
+
+def reduce_bins(handles, world: int, dst: int = 0, rank: int = 0):
+    """Per-bin reduction (C1 of SURVEY 2.5) of EVERY observable accumulator -- scalars, equal-time and time-displaced lattice observables with
+    backgrounds and counters -- of the handles of this rank: the device buffers are SUM-reduced in place over NCCL by the C-ABI
+    (alf_b200_reduce_bins), then the handles of the destination rank are added up on the host.  Returns on `dst` a dict
+    {"obs", "eq": (acc, bg, n, sign) or None, "tau": ... or None}; None elsewhere."""
+    for g in handles:
+        if world > 1:
+            g.reduce_bins(dst)
+    if world > 1 and rank != dst:
+        return None
+    out = {"obs": sum(np.asarray(g.obs()) for g in handles), "eq": None, "tau": None}
+    for key, getter, flag in (("eq", "obs_eq", "_obs_eq_on"), ("tau", "obs_tau", "_obs_tau_on")):
+        parts = [getattr(g, getter)() for g in handles if getattr(g, flag, False)]
+        if parts:
+            out[key] = tuple(sum(p[i] for p in parts) for i in range(4))
+    return out
+
+
+def reduce_host_bins(arrays, dst: int = 0):
+    """Host-side twin for process groups without GPUs (world-size-2 gloo tests on CPU): SUM-reduces a dict of numpy arrays (the same
+    accumulators, already on the host) to rank `dst`."""
     import torch
     import torch.distributed as dist
-    if world <= 1 or not (dist.is_available() and dist.is_initialized()):
-        return obs_host
-    if dist.get_backend() == "nccl":
-        ptr, n = g.obs_device_ptr()
-        t = torch.as_tensor(_DevArray(ptr, n), device="cuda").clone()
+    if not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
+        return arrays
+    out = {}
+    for k in sorted(arrays):
+        a = np.asarray(arrays[k]); cplx = np.iscomplexobj(a)
+        t = torch.as_tensor(np.ascontiguousarray(a.view(np.float64) if cplx else a.astype(np.float64))).clone()
         dist.reduce(t, dst=dst, op=dist.ReduceOp.SUM)
-        return t.cpu().numpy() if dist.get_rank() == dst else None
-    t = torch.as_tensor(np.asarray(obs_host, dtype=np.float64)).clone()
-    dist.reduce(t, dst=dst, op=dist.ReduceOp.SUM)
-    return t.numpy() if dist.get_rank() == dst else None
+        r = t.numpy()
+        out[k] = r.view(np.complex128).reshape(a.shape) if cplx else r.reshape(a.shape)
+    return out if dist.get_rank() == dst else None

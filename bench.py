@@ -208,7 +208,7 @@ def run_b200(args):
     if world > 1:
         dist.barrier()
     from alf_b200.api import AlfB200, fp64_peak
-    from alf_b200.parallel import reduce_bins
+    from alf_b200.parallel import reduce_bins, init_comm
 
     model, nwrap, chains_default = make_model(args.workload)
     C = args.chains or chains_default                  # chains per handle
@@ -220,6 +220,7 @@ def run_b200(args):
         gk.fields_set(); gk.init_sweep()
         gs.append(gk); streams.append(torch.cuda.ExternalStream(gk.stream_ptr(), device=torch.device("cuda", local)))
     g = gs[0]
+    init_comm(gs, world, rank)                         # NCCL communicators of the C-ABI's bin reduction (one per handle)
     N, L, M, F = model.Ndim, model.Ltrot, model.n_opv, model.N_FL
 
     def barrier():
@@ -284,14 +285,15 @@ def run_b200(args):
     t0 = time.perf_counter()
     for _ in range(args.steps):
         on_all(lambda k: gs[k].sweep_host(1, args.ltau, f_in[k], f_out[k], obs[k], ctl[k]))
-        for k in range(H):
-            red = reduce_bins(gs[k], obs[k], world)   # NCCL reduction of the bin accumulators (replaces MPI_REDUCE, observables_mod.F90:425-438)
+        red = reduce_bins(gs, world, 0, rank)          # alf_b200_reduce_bins: NCCL reduction of ALL bin accumulators on the device (replaces MPI_REDUCE, observables_mod.F90:425-438), then read on rank 0
         f_in, f_out = f_out, f_in
     barrier()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     e2e_value = world * H * C * args.steps / e2e_s
     h2d = world * H * C * L * M                    # int8 per field through the pinned staging buffers, all ranks
     d2h = world * H * (C * L * M + 8 * (len(obs[0]) + 16))
+    if red is not None and red.get("tau") is not None:      # rank 0 additionally reads the reduced time-displaced lattice bins (Green, SpinZ, SpinXY, Den + backgrounds)
+        d2h += H * sum(int(np.asarray(x).nbytes) for x in red["tau"][:2])
 
     # ---- un-timed extra passes (rank-local, after both timed regions): per-category device time + algorithmic FP64 flops of the
     # dense kernels on ONE handle running alone (CUDA events around every launch perturb the step, so they are kept out of the timed

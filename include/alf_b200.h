@@ -177,6 +177,9 @@ int alf_b200_set_green(alf_b200_handle* h, int chain, int nf, const double* in);
 int alf_b200_get_phase(alf_b200_handle* h, double* out /* complex [chain] */);
 int alf_b200_get_udv(alf_b200_handle* h, int which /*0 udvl,1 udvr,2 udvst*/, int nst, int chain, int nf,
                      double* U, double* D, double* V /* complex */);
+/* host UDV_State (type UDV_State, Prog/udv_state_mod.F90:85-110: U, D, V as complex arrays) -> the handle's udvl / udvr / udvst(nst) of one chain and flavor:
+ * compat mode, so that WRAPUR(NTAU, NTAU1, UDVR) / WRAPUL / CGR(PHASE, NVAR, GRUP, udvr, udvl) act on the caller's states (set, call, get). */
+int alf_b200_set_udv(alf_b200_handle* h, int which, int nst, int chain, int nf, const double* U, const double* D, const double* V);
 /* control accumulators (Prog/control_mod.F90:53-71), reduced over chains:
  * [0] XMEANG sum [1] XMAXG [2] NCG [3] XMAXP [4] XMEAN_tau sum [5] XMAX_tau [6] NCG_tau [7] NC_up [8] ACC_up
  * [9] NC_eff_up [10] ACC_eff_up [11] NaN flag [12] unstable flag (XMAX > 10)
@@ -206,6 +209,21 @@ int alf_b200_obs_reset(alf_b200_handle* h);
 int alf_b200_obs_device_ptr(alf_b200_handle* h, double** dptr, long* n_doubles);  /* for the NCCL bin reduction */
 int alf_b200_get_obs(alf_b200_handle* h, double* out);
 
+/* ---- multi-GPU: the per-bin reduction that replaces MPI_REDUCE in Print_bin_Vec / Print_bin_Latt / Print_bin_Latt_Local and Control_Print
+ * (Prog/observables_mod.F90:425-438, 648-653, 828-834; Prog/control_mod.F90:397-452).  One process per GPU; chains never talk during a sweep.
+ *   alf_b200_comm_unique_id : rank 0 creates the 128-byte NCCL id; the host program hands it to the other ranks (ALF: MPI_BCAST; here any channel);
+ *   alf_b200_comm_init      : every rank joins with its handle (one communicator per handle; NCCL is resolved with dlopen("libnccl.so.2"));
+ *   alf_b200_reduce_bins    : SUM-reduces IN PLACE on the device, over NVLink, every observable accumulator of the handle -- the scalars of
+ *                             alf_b200_get_obs, the equal-time and time-displaced lattice accumulators with their backgrounds and counters -- to
+ *                             rank `root`, where alf_b200_get_obs / _get_obs_eq / _get_obs_tau then return the sum over all ranks' chains;
+ *   alf_b200_reduce_control : the 16 control values of alf_b200_get_control reduced to `root` (SUM, and MAX for XMAXG, XMAXP, XMAX_tau and the flags).
+ * Without a communicator (single rank) the two reductions are no-ops / plain reads. */
+int alf_b200_comm_unique_id(char* id /* 128 bytes */);
+int alf_b200_comm_init(alf_b200_handle* h, int nranks, int rank, const char* id /* 128 bytes */);
+int alf_b200_comm_destroy(alf_b200_handle* h);
+int alf_b200_reduce_bins(alf_b200_handle* h, int root);
+int alf_b200_reduce_control(alf_b200_handle* h, int root, double* out /* 16 */);
+
 /* ---- UDV_Wrap_Pivot(A, U, D, V, NCON, N1, N2), Prog/UDV_WRAP_mod.F90:125-208 (default variant; the stabilisation of the STAB1 / STAB2
  * builds: wrapur_mod.F90:96, wrapul_mod.F90:98-102, cgr1_mod.F90:115,137): norm-sorted, norm-scaled columns, unpivoted Householder QR
  * (UDV_C, mymats_mod.F90:933), det V = 1.  A, U: complex n1*n2*batch, D: complex n2*batch, V: complex n2*n2*batch, A = U D V per matrix.
@@ -222,6 +240,8 @@ int alf_b200_test_qdrp(int device, int is_complex, int m, int n, int batch, doub
 int alf_b200_test_qdrp_blocked(int device, int is_complex, int m, int n, int batch, double* A, double* D, int* jpvt, double* tau,
                                double* phases, double* Q);
 int alf_b200_test_udv_decompose(int device, int is_complex, int n, int batch, char side, double* U, double* D, double* V);
+/* CGR(PHASE, NVAR, GRUP, udvr, udvl), Prog/cgr1_mod.F90:36, on a batch of host states.  detUR / detUL (complex per matrix: det U_R, det U_L, which the
+ * sweep carries along) may be NULL: they are then computed on the device, so the call needs nothing beyond the reference routine's own arguments. */
 int alf_b200_test_cgr(int device, int is_complex, int n, int batch, int nvar, int stab, const double* UR, const double* DR,
                       const double* VR, const double* UL, const double* DL, const double* VL, const double* detUR,
                       const double* detUL, double* G, double* phase);

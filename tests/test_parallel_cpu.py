@@ -21,7 +21,11 @@ def _worker(rank, world, port, q):
     try:
         # bins: rank r contributes (r + 1) * arange
         obs = (rank + 1) * np.arange(24, dtype=np.float64)
-        red = parallel.reduce_bins(None, obs, world)
+        lat = (rank + 1) * (np.arange(12).reshape(3, 4) + 1j * np.ones((3, 4)))      # a lattice accumulator (complex, like Obs_Latt)
+        both = parallel.reduce_host_bins({"obs": obs, "Green_eq": lat})
+        red = None if both is None else both["obs"]
+        if both is not None:
+            assert np.allclose(both["Green_eq"], 3.0 * (np.arange(12).reshape(3, 4) + 1j * np.ones((3, 4))))
         # control: sums except the maxima entries 1, 3, 5, 11, 12
         ctl = np.arange(16, dtype=np.float64) + 100.0 * rank
         rc = parallel.reduce_control(ctl)
@@ -42,8 +46,8 @@ def test_shard_and_seed_order():
 
 
 def test_reduce_is_noop_without_process_group():
-    obs = np.arange(5.0)
-    assert parallel.reduce_bins(None, obs, 1) is obs
+    obs = {"obs": np.arange(5.0)}
+    assert parallel.reduce_host_bins(obs) is obs
     out = parallel.reduce_control(np.arange(16.0))
     assert np.array_equal(out, np.arange(16.0))
 
