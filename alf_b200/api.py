@@ -446,10 +446,11 @@ def test_cgr(UR, DR, VR, UL, DL, VL, detUR, detUL, nvar=1, stab=0, is_complex=Tr
     cm = lambda X: np.ascontiguousarray(np.asarray(X, dtype=np.complex128).transpose(0, 2, 1))
     a = [cm(x) for x in (UR, VR, UL, VL)]
     dr = np.ascontiguousarray(DR, dtype=np.complex128); dl = np.ascontiguousarray(DL, dtype=np.complex128)
-    d1 = np.ascontiguousarray(detUR, dtype=np.complex128); d2 = np.ascontiguousarray(detUL, dtype=np.complex128)
+    have_det = detUR is not None and detUL is not None      # None: det U_R, det U_L are computed on the device (the reference routine's own argument list)
+    d1 = np.ascontiguousarray(detUR, dtype=np.complex128) if have_det else None; d2 = np.ascontiguousarray(detUL, dtype=np.complex128) if have_det else None
     G = np.zeros((batch, n, n), dtype=np.complex128); ph = np.zeros(batch, dtype=np.complex128)
     _chk(lib().alf_b200_test_cgr(device, int(is_complex), n, batch, int(nvar), int(stab), _d(a[0]), _d(dr), _d(a[1]), _d(a[2]), _d(dl), _d(a[3]),
-                                 _d(d1), _d(d2), _d(G), _d(ph)), "test_cgr")
+                                 _d(d1) if have_det else None, _d(d2) if have_det else None, _d(G), _d(ph)), "test_cgr")
     return G.transpose(0, 2, 1), ph
 
 

@@ -1326,11 +1326,12 @@ struct Engine : EngineBase {
   void set_udv(int which, int nst, int chain, int nf, const cd* U, const cd* D, const cd* V) override {
     UdvDev<T>& u = which == 0 ? udvl : which == 1 ? udvr : udvst[nst - 1];
     const long b = (long)chain * F + (nf - 1);
-    std::vector<T> t(n2); std::vector<double> d(N);
-    for (long i = 0; i < n2; ++i) t[i] = to_T<T>(U[i]);
+    std::vector<T> t(n2, zero_<T>()); std::vector<double> d(N, 1.0);
+    const long nu = proj ? (long)N * NP : n2; const int nd = proj ? NP : N;      // projector states carry U(Ndim, N_part), D(N_part) and no V
+    for (long i = 0; i < nu; ++i) t[i] = to_T<T>(U[i]);
     CK(cudaMemcpyAsync(u.U + n2 * b, t.data(), sizeof(T) * n2, cudaMemcpyHostToDevice, st)); sync();
     if (!proj && V) { for (long i = 0; i < n2; ++i) t[i] = to_T<T>(V[i]); CK(cudaMemcpyAsync(u.V + n2 * b, t.data(), sizeof(T) * n2, cudaMemcpyHostToDevice, st)); sync(); }
-    for (int i = 0; i < N; ++i) d[i] = D[i].real();
+    for (int i = 0; i < nd; ++i) d[i] = D[i].real();
     CK(cudaMemcpyAsync(u.D + (long)N * b, d.data(), sizeof(double) * N, cudaMemcpyHostToDevice, st)); sync();
     if (!proj) {      // det U of this one matrix: pivoted QR of a copy (batch of one inside the workspace)
       LaWork<T> w1; w1.alloc(N, 1, st);
