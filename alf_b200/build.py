@@ -34,6 +34,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     flags = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC"]
     if verbose:
         flags.append("-Xptxas=-v")
+    if os.environ.get("ALF_QR_PROF"):      # experimental: phase accounting inside k_qrp_reg (alf_qrblk2.cuh)
+        flags.append("-DALF_QR_PROF")
 
     def cc(u):
         o = os.path.join(OBJ, u.replace(".cu", ".o"))

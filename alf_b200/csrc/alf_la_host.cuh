@@ -226,14 +226,12 @@ static void launch_qrp_blk(cudaStream_t st, T* A, int m, int n, int ld, long sA,
   if constexpr (std::is_same<T, double>::value) {
     if (use_qr2<T>(m, n)) {
       const long sT = (long)(n + 32) * 32;
-      // one CTA of 16 warps per matrix.  Two CTAs of 8 warps per SM (ALF_B200_QR_TWO_CTA=1) measured slower on B200:
-      // 1.94 ms vs 1.72 ms per batch of 296 256x256 matrices.
-      const bool two = m <= 288 && qr2_smem(m, n, 8) + 1024 <= 113 * 1024 && getenv("ALF_B200_QR_TWO_CTA");
-      const size_t smem = qr2_smem(m, n, two ? 8 : 16);
+      // one CTA of 16 warps per matrix (two CTAs of 8 warps per SM, four panel columns per warp, measured slower twice: 1.94 vs 1.72 ms in round 1,
+      // 1.79 vs 1.35 ms with round 2's panel loop -- the column step is bound by the instruction stream of a warp, not by latency)
+      const size_t smem = qr2_smem(m, n, 16);
 #define QR2_LAUNCH(MAXR, CPW) do { CK(alf_raise_smem(k_qrp_reg<MAXR, CPW>)); \
         KL(KC_QRP, st, k_qrp_reg<MAXR, CPW><<<batch, 32 * (QR2_NB / CPW), smem, st>>>(A, m, n, ld, sA, tau, sTau, jpvt, sP, D, sD, out, Tbuf, sT)); } while (0)
-      if (two) { if (m <= 128) QR2_LAUNCH(4, 4); else QR2_LAUNCH(9, 4); }
-      else { if (m <= 128) QR2_LAUNCH(4, 2); else if (m <= 288) QR2_LAUNCH(9, 2); else QR2_LAUNCH(18, 2); }
+      if (m <= 128) QR2_LAUNCH(4, 2); else if (m <= 256) QR2_LAUNCH(8, 2); else if (m <= 288) QR2_LAUNCH(9, 2); else QR2_LAUNCH(18, 2);
 #undef QR2_LAUNCH
       return;
     }

@@ -15,14 +15,23 @@
 #include "alf_qrblk.cuh"
 
 #define QR2_NB 32
+#ifdef ALF_QR_PROF      // experimental build only: clock64 accounting of the phases of k_qrp_reg (summed over CTAs, thread 0)
+__device__ unsigned long long g_qr_prof[16];
+#define QRP_T0 long long qp_t = clock64();
+#define QRP_ACC(i) if (threadIdx.x == 0) { const long long t_ = clock64(); atomicAdd(&g_qr_prof[i], (unsigned long long)(t_ - qp_t)); qp_t = t_; }
+#else
+#define QRP_T0
+#define QRP_ACC(i)
+#endif
 #define QR2_LDW 36
 #define QR2_WSC (QR2_LDW * 8)      // per-warp scratch: 32 x 8 block, leading dimension 36
 
 // nw = warps per CTA.  The Gram matrix of the panel aliases the per-warp scratch (used in disjoint phases).
+static inline int qr2_vlen(int m) { return (m <= 128) ? 128 : (m <= 256) ? 256 : (m <= 288) ? 288 : 576; }      // 32 * MAXR of the instantiation used for m rows
 static size_t qr2_smem(int m, int n, int nw) {
-  const int mp = (m + 7) & ~7, ldv = ld_pad(mp);
+  const int mp = qr2_vlen(m), ldv = ld_pad((m + 7) & ~7);
   const size_t wsc = (size_t)nw * QR2_WSC > (size_t)QR2_LDW * QR2_NB ? (size_t)nw * QR2_WSC : (size_t)QR2_LDW * QR2_NB;
-  return sizeof(double) * ((size_t)ldv * QR2_NB + QR2_LDW * QR2_NB + wsc + mp + 2 * QR2_NB + n) + sizeof(int) * (4 * (size_t)n + 64) + 64;
+  return sizeof(double) * ((size_t)ldv * QR2_NB + QR2_LDW * QR2_NB + wsc + mp + 4 * QR2_NB + n) + sizeof(int) * (4 * (size_t)n + 64) + 64;
 }
 static size_t applyq2_smem(int m, int nw) {
   const int mp = (m + 7) & ~7, ldv = ld_pad(mp);
@@ -139,6 +148,113 @@ __device__ __forceinline__ void apply_panel_strips(double* __restrict__ X, int l
   }
 }
 
+// Column loop of one panel for NL LIVE row blocks: the registers hold rows k0 + 32 r + lane, r < NL, only (k0 is a multiple of 32, so the pivot rows
+// of the whole panel sit in block 0, pivot row j in lane j, and the rows above k0 -- finished R entries -- take no part).  Written after the
+// instrumented build and the SASS-level stall view of the first versions (4300 cycles per column: the warp owning the pivot ran ~770 branchy
+// instructions while 15 warps waited; per-row-block branches compiled to chains of convergence barriers; half of the FP64 work was spent on
+// finished rows):
+//  * the owner only STORES the raw pivot column x to shared memory; every warp derives the reflector itself: beta = -sign(alpha) |x|,
+//    v = scal x~ with x~ = x except x~(j) = alpha - beta = 1 / scal, so H c = c - x~ (gamma x~.c) with ONE division gamma = tau scal^2 =
+//    -1 / (beta (alpha - beta)); the finished column stays RAW in its registers, scal and beta are applied at the write-back;
+//  * straight-line code over exactly the live blocks (one instantiation per NL), row predicates in block 0 only;
+//  * the pivot search is two redux.sync on the bit patterns of the (non-negative) norms instead of five shuffle rounds.
+template <int MAXR, int CPW, int NL>
+__device__ __forceinline__ void qr2_panel_cols(double (&cr)[CPW][MAXR], const int nbk, const int sb, double* __restrict__ v_s, double* __restrict__ pn,
+                                               double* __restrict__ tau_s, double* __restrict__ sc_s, double* __restrict__ be_s, int* __restrict__ pos_slot,
+                                               double* __restrict__ s_detq) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  unsigned used = 0u;
+  QRP_T0
+  for (int j = 0; j < nbk; ++j) {
+    int p;
+    {   // arg max of pn over the unused slots, lowest slot on ties: key = bits(pn) + 1 (0 for used / empty slots), 64-bit max as two 32-bit redux
+      const bool cand0 = lane < nbk && !((used >> lane) & 1u);
+      const unsigned long long key = cand0 ? ((unsigned long long)__double_as_longlong(pn[lane]) + 1ull) : 0ull;
+      const unsigned khi = (unsigned)(key >> 32), klo = (unsigned)key;
+      const unsigned mhi = __reduce_max_sync(0xffffffffu, khi);
+      const bool c1 = khi == mhi;
+      const unsigned mlo = __reduce_max_sync(0xffffffffu, c1 ? klo : 0u);
+      p = __ffs(__ballot_sync(0xffffffffu, c1 && klo == mlo)) - 1;
+    }
+    used |= 1u << p;
+    const double cn_pre = sqrt(pn[p]);      // |x| of the pivot column: off the critical path (overlaps the owner's store and the barrier)
+    QRP_ACC(8)
+    if (warp == p / CPW) {      // owner: raw pivot column -> shared memory (local rows j .. ; everything else of v_s is zero)
+      const int hp = p % CPW;
+#pragma unroll
+      for (int r = 0; r < NL; ++r) {
+        double x = cr[0][r];
+#pragma unroll
+        for (int h = 1; h < CPW; ++h) x = (h == hp) ? cr[h][r] : x;
+        if (r > 0 || lane >= j) v_s[lane + 32 * r] = x;
+      }
+      if (lane == 0) { pos_slot[j] = p; if (j > 0) v_s[j - 1] = 0.0; }
+    }
+    __syncthreads();
+    QRP_ACC(9)
+    {
+      // the reflector from the raw column (every warp, redundantly): LAPACK's ZLARFG for real data.  cn = 2-norm of the pivot column below row
+      // j - 1, exact (from the previous step's update); cn == 0: H = I (ZLARFG's xnorm == 0, alpha == 0 case)
+      const double alpha = v_s[j], cn = cn_pre;
+      const double beta = (cn == 0.0) ? alpha : -copysign(cn, alpha);
+      const double dd = alpha - beta;                          // x~(j) = 1 / scal
+      const double gam = (cn == 0.0) ? 0.0 : -1.0 / (beta * dd);
+      if (tid == 0) {
+        tau_s[j] = (cn == 0.0) ? 0.0 : (beta - alpha) / beta; sc_s[p] = (cn == 0.0) ? 0.0 : 1.0 / dd; be_s[p] = beta;
+        if (cn != 0.0) { s_detq[0] = -s_detq[0]; s_detq[1] = -s_detq[1]; }      // det of a real reflector = -1 (Prog/cgr1_mod.F90:338-347)
+      }
+      bool doh[CPW];
+#pragma unroll
+      for (int h = 0; h < CPW; ++h) doh[h] = (sb + h < nbk) && !((used >> (sb + h)) & 1u);
+      double xv[NL];
+      double w[CPW], wb[CPW], qn[CPW], qb[CPW];
+#pragma unroll
+      for (int h = 0; h < CPW; ++h) { w[h] = 0.0; wb[h] = 0.0; qn[h] = 0.0; qb[h] = 0.0; }
+#pragma unroll
+      for (int r = 0; r < NL; ++r) {
+        xv[r] = v_s[lane + 32 * r];
+        if (r == 0) xv[0] = (lane == j) ? dd : xv[0];
+#pragma unroll
+        for (int h = 0; h < CPW; ++h) { if (r & 1) wb[h] = fma(xv[r], cr[h][r], wb[h]); else w[h] = fma(xv[r], cr[h][r], w[h]); }
+      }
+      if (NL > 1) {
+#pragma unroll
+        for (int h = 0; h < CPW; ++h) w[h] += wb[h];
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+        for (int h = 0; h < CPW; ++h) w[h] += __shfl_xor_sync(0xffffffffu, w[h], o);
+#pragma unroll
+      for (int h = 0; h < CPW; ++h) w[h] = doh[h] ? w[h] * gam : 0.0;      // finished columns keep their raw reflector entries
+#pragma unroll
+      for (int r = 0; r < NL; ++r) {
+#pragma unroll
+        for (int h = 0; h < CPW; ++h) {
+          cr[h][r] = fma(-xv[r], w[h], cr[h][r]);
+          const double t = (r > 0 || lane > j) ? cr[h][r] : 0.0;          // exact norm of the rows below the pivot row
+          if (r & 1) qb[h] = fma(t, t, qb[h]); else qn[h] = fma(t, t, qn[h]);
+        }
+      }
+      if (NL > 1) {
+#pragma unroll
+        for (int h = 0; h < CPW; ++h) qn[h] += qb[h];
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+        for (int h = 0; h < CPW; ++h) qn[h] += __shfl_xor_sync(0xffffffffu, qn[h], o);
+      if (lane == 0) {
+#pragma unroll
+        for (int h = 0; h < CPW; ++h) if (doh[h]) pn[sb + h] = qn[h];
+      }
+    }
+    QRP_ACC(10)
+    __syncthreads();
+    QRP_ACC(11)
+  }
+}
+
 // ------------------------------------------------------------------------------------------------------------------------
 // k_qrp_reg: windowed column-pivoted blocked Householder QR of an m x n real matrix (m >= n, m <= 32 MAXR), in place, then
 // D(i) = |R(i,i)|, R(i, i:) /= D(i).  One CTA per matrix.  Outputs as k_qrp_blk (Tbuf: 32 x 32 factor per panel).
@@ -157,9 +273,11 @@ __global__ void __launch_bounds__(32 * (QR2_NB / CPW), CPW == 4 ? 2 : 1) k_qrp_r
   double* Wsc = Ts + LDW * NB;
   double* Gs = Wsc;                   // Gram matrix: dead before the first strip update of the panel
   double* v_s = Wsc + ((nw * QR2_WSC > LDW * NB) ? nw * QR2_WSC : LDW * NB);
-  double* tau_s = v_s + mp;
+  double* tau_s = v_s + 32 * MAXR;
   double* pn = tau_s + NB;
-  double* vn = pn + NB;
+  double* sc_s = pn + NB;             // per panel slot: 1 / (alpha - beta) and beta of its reflector
+  double* be_s = sc_s + NB;
+  double* vn = be_s + NB;
   int* ipv = reinterpret_cast<int*>(vn + n);
   int* rank_s = ipv + n;
   int* lista = rank_s + n;
@@ -168,6 +286,7 @@ __global__ void __launch_bounds__(32 * (QR2_NB / CPW), CPW == 4 ? 2 : 1) k_qrp_r
   __shared__ int s_na;
   __shared__ double s_detq[2];
 
+  QRP_T0
   for (int c = warp; c < n; c += nw) {
     double s = 0.0;
     for (int i = lane; i < m; i += 32) { const double x = A[i + (long)c * ld]; s = fma(x, x, s); }
@@ -177,6 +296,7 @@ __global__ void __launch_bounds__(32 * (QR2_NB / CPW), CPW == 4 ? 2 : 1) k_qrp_r
   if (tid == 0) { s_detq[0] = 1.0; s_detq[1] = 0.0; }
   __syncthreads();
   const int kmax = n;                 // m >= n
+  QRP_ACC(0)
   for (int k0 = 0; k0 < kmax; k0 += NB) {
     const int nbk = min(NB, kmax - k0), mv = m - k0, mvp = (mv + 7) & ~7;
     // ---- (1) the nbk remaining columns of largest norm form the panel (rank by counting; ties -> lower index first)
@@ -203,141 +323,50 @@ __global__ void __launch_bounds__(32 * (QR2_NB / CPW), CPW == 4 ? 2 : 1) k_qrp_r
     const int na = s_na;
     for (int pi = warp; pi < na; pi += nw) {
       const int ca = lista[pi], cb = listb[pi];
-      for (int r = lane; r < m; r += 32) { const double x = A[r + (long)ca * ld], y = A[r + (long)cb * ld]; A[r + (long)ca * ld] = y; A[r + (long)cb * ld] = x; }
+      {   // all loads of the two columns are issued before the first store (the read-modify-write loop serialised on the global latency)
+        double xa[MAXR], xb[MAXR];
+#pragma unroll
+        for (int r = 0; r < MAXR; ++r) { const int i = lane + 32 * r; xa[r] = (i < m) ? A[i + (long)ca * ld] : 0.0; xb[r] = (i < m) ? A[i + (long)cb * ld] : 0.0; }
+#pragma unroll
+        for (int r = 0; r < MAXR; ++r) { const int i = lane + 32 * r; if (i < m) { A[i + (long)ca * ld] = xb[r]; A[i + (long)cb * ld] = xa[r]; } }
+      }
       if (lane == 0) { const int t = ipv[ca]; ipv[ca] = ipv[cb]; ipv[cb] = t; vn[ca] = vn[cb]; }
     }
     __syncthreads();
-    // ---- (3) panel columns -> registers: warp w owns slots CPW w .. CPW w + CPW - 1; exact norms below row k0
+    QRP_ACC(1)
+    // ---- (3) the LIVE rows (k0 .. m - 1) of the panel columns -> registers: warp w owns slots CPW w .. CPW w + CPW - 1, register block r holds rows
+    // k0 + 32 r + lane; exact norms.  (Rows above k0 stay in global memory; they only move with the in-panel permutation, step 5.)
     double cr[CPW][MAXR];
     const int sb = CPW * warp;
+    const int nl = (mv + 31) >> 5;                    // live row blocks of this panel
     {
       double a[CPW];
 #pragma unroll
       for (int h = 0; h < CPW; ++h) a[h] = 0.0;
 #pragma unroll
       for (int r = 0; r < MAXR; ++r) {
-        const int i = lane + 32 * r;
+        const int i = k0 + lane + 32 * r;
 #pragma unroll
         for (int h = 0; h < CPW; ++h) {
-          cr[h][r] = (i < m && sb + h < nbk) ? A[i + (long)(k0 + sb + h) * ld] : 0.0;
-          if (i >= k0) a[h] = fma(cr[h][r], cr[h][r], a[h]);
+          cr[h][r] = (r < nl && i < m && sb + h < nbk) ? A[i + (long)(k0 + sb + h) * ld] : 0.0;
+          a[h] = fma(cr[h][r], cr[h][r], a[h]);
         }
       }
 #pragma unroll
-      for (int h = 0; h < CPW; ++h) { a[h] = warp_sum(a[h]); if (lane == 0) pn[sb + h] = sqrt(a[h]); }
+      for (int h = 0; h < CPW; ++h) { a[h] = warp_sum(a[h]); if (lane == 0) pn[sb + h] = a[h]; }      // pn: SQUARED norms (the square root is taken for the pivot only)
     }
+    for (int e = tid; e < 32 * MAXR; e += nthr) v_s[e] = 0.0;
     __syncthreads();
-    // ---- (4) exact column-pivoted Householder QR of the panel, columns in registers
-    unsigned used = 0u;
-    for (int j = 0; j < nbk; ++j) {
-      const int prow = k0 + j;
-      int p;
-      {
-        double best = (lane < nbk && !((used >> lane) & 1u)) ? pn[lane] : -1.0; int bi = lane;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-          const double ob = __shfl_xor_sync(0xffffffffu, best, o); const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-          if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
-        }
-        p = bi;
-      }
-      used |= 1u << p;
-      if (tid == 0) pos_slot[j] = p;
-      if (warp == p / CPW) {
-        const int hp = p % CPW;
-        // The 2-norm of the pivot column below row prow - 1 is already known (pn, exact, from the previous step's update), so
-        // beta = -sign(alpha) pn needs no reduction on the critical path.  pn == 0: H = I (ZLARFG's xnorm == 0, alpha == 0 case).
-        double al = 0.0;
-#pragma unroll
-        for (int r = 0; r < MAXR; ++r) {
-          const int i = lane + 32 * r;
-          double x = cr[0][r];
-#pragma unroll
-          for (int h = 1; h < CPW; ++h) if (h == hp) x = cr[h][r];
-          if (i == prow) al = x;
-        }
-        const double alpha = __shfl_sync(0xffffffffu, al, prow & 31);
-        const double cn = pn[p];
-        double tj, scal, beta;
-        if (cn == 0.0) { tj = 0.0; scal = 0.0; beta = alpha; }
-        else { beta = -copysign(cn, alpha); tj = (beta - alpha) / beta; scal = 1.0 / (alpha - beta); }
-#pragma unroll
-        for (int r = 0; r < MAXR; ++r) {
-          if (32 * r + 31 < prow) continue;
-          const int i = lane + 32 * r;
-          if (i < m && i >= prow) {
-            double x = cr[0][r];
-#pragma unroll
-            for (int h = 1; h < CPW; ++h) if (h == hp) x = cr[h][r];
-            if (i > prow) { x *= scal; v_s[i] = x; } else { x = beta; v_s[i] = 1.0; }
-#pragma unroll
-            for (int h = 0; h < CPW; ++h) if (h == hp) cr[h][r] = x;
-          }
-        }
-        if (lane == 0) {
-          tau_s[j] = tj;
-          if (tj != 0.0) { s_detq[0] = -s_detq[0]; s_detq[1] = -s_detq[1]; }      // det of a real reflector = -1 (Prog/cgr1_mod.F90:338-347)
-        }
-      }
-      __syncthreads();
-      {
-        const double tj = tau_s[j];
-        bool doh[CPW]; bool any = false;
-#pragma unroll
-        for (int h = 0; h < CPW; ++h) { doh[h] = (sb + h < nbk) && !((used >> (sb + h)) & 1u); any = any || doh[h]; }
-        if (any) {
-          // rows above the pivot row are finished: row blocks r with 32 r + 31 < prow are skipped by the whole warp (on average half of
-          // them); the dot products and norms run as two interleaved chains (even / odd row blocks)
-          double w[CPW], wb[CPW], qn[CPW], qb[CPW];
-#pragma unroll
-          for (int h = 0; h < CPW; ++h) { w[h] = 0.0; wb[h] = 0.0; qn[h] = 0.0; qb[h] = 0.0; }
-          if (tj != 0.0) {
-#pragma unroll
-            for (int r = 0; r < MAXR; ++r) {
-              if (32 * r + 31 < prow) continue;
-              const int i = lane + 32 * r;
-              if (i >= prow && i < m) {
-                const double v = v_s[i];
-#pragma unroll
-                for (int h = 0; h < CPW; ++h) { if (r & 1) wb[h] = fma(v, cr[h][r], wb[h]); else w[h] = fma(v, cr[h][r], w[h]); }
-              }
-            }
-#pragma unroll
-            for (int h = 0; h < CPW; ++h) w[h] += wb[h];
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1)
-#pragma unroll
-              for (int h = 0; h < CPW; ++h) w[h] += __shfl_xor_sync(0xffffffffu, w[h], o);
-#pragma unroll
-            for (int h = 0; h < CPW; ++h) w[h] *= tj;
-          }
-#pragma unroll
-          for (int r = 0; r < MAXR; ++r) {
-            if (32 * r + 31 < prow) continue;
-            const int i = lane + 32 * r;
-            if (i >= prow && i < m) {
-              const double v = (tj != 0.0) ? v_s[i] : 0.0;
-#pragma unroll
-              for (int h = 0; h < CPW; ++h) {
-                if (doh[h]) cr[h][r] = fma(-v, w[h], cr[h][r]);
-                if (i > prow) { if (r & 1) qb[h] = fma(cr[h][r], cr[h][r], qb[h]); else qn[h] = fma(cr[h][r], cr[h][r], qn[h]); }
-              }
-            }
-          }
-#pragma unroll
-          for (int h = 0; h < CPW; ++h) qn[h] += qb[h];
-#pragma unroll
-          for (int o = 16; o > 0; o >>= 1)
-#pragma unroll
-            for (int h = 0; h < CPW; ++h) qn[h] += __shfl_xor_sync(0xffffffffu, qn[h], o);
-          if (lane == 0) {
-#pragma unroll
-            for (int h = 0; h < CPW; ++h) if (doh[h]) pn[sb + h] = sqrt(qn[h]);
-          }
-        }
-      }
-      __syncthreads();
+    QRP_ACC(2)
+    // ---- (4) exact column-pivoted Householder QR of the panel, columns in registers: one instantiation per number of live row blocks
+#define QR2_CASE(NLV) case NLV: if constexpr (NLV <= MAXR) qr2_panel_cols<MAXR, CPW, NLV>(cr, nbk, sb, v_s, pn, tau_s, sc_s, be_s, pos_slot, s_detq); break;
+    switch (nl) {
+      QR2_CASE(1) QR2_CASE(2) QR2_CASE(3) QR2_CASE(4) QR2_CASE(5) QR2_CASE(6) QR2_CASE(7) QR2_CASE(8) QR2_CASE(9) QR2_CASE(10) QR2_CASE(11) QR2_CASE(12)
+      QR2_CASE(13) QR2_CASE(14) QR2_CASE(15) QR2_CASE(16) QR2_CASE(17) QR2_CASE(18)
+      default: break;
     }
+#undef QR2_CASE
+    QRP_ACC(3)
     // ---- (5) write the factored panel back at the logical positions; V panel (explicit unit lower trapezoid) -> shared memory
     int pos[CPW];
     {
@@ -347,16 +376,39 @@ __global__ void __launch_bounds__(32 * (QR2_NB / CPW), CPW == 4 ? 2 : 1) k_qrp_r
     }
     for (int e = tid; e < (mvp - mv) * NB; e += nthr) { const int r = mv + e % (mvp - mv), c = e / (mvp - mv); Vs[r + (long)c * ldv] = 0.0; }
     for (int e = tid; e < mvp * (NB - nbk); e += nthr) { const int r = e % mvp, c = nbk + e / mvp; Vs[r + (long)c * ldv] = 0.0; }
+    double sch[CPW], beh[CPW];                            // the finished columns are still raw below their pivot row: v = scal x, R(pos, pos) = beta
+#pragma unroll
+    for (int h = 0; h < CPW; ++h) { sch[h] = (sb + h < nbk) ? sc_s[sb + h] : 0.0; beh[h] = (sb + h < nbk) ? be_s[sb + h] : 0.0; }
+    // live rows: from the registers to the logical positions, with the scaling of the reflector entries and beta on the diagonal
 #pragma unroll
     for (int r = 0; r < MAXR; ++r) {
-      const int i = lane + 32 * r;
-      if (i < m) {
+      const int rr = lane + 32 * r;                       // local row
+      if (r < nl && k0 + rr < m) {
 #pragma unroll
         for (int h = 0; h < CPW; ++h) if (pos[h] >= 0) {
-          A[i + (long)(k0 + pos[h]) * ld] = cr[h][r];
-          if (i >= k0) { const int rr = i - k0; Vs[rr + (long)pos[h] * ldv] = (rr > pos[h]) ? cr[h][r] : ((rr == pos[h]) ? 1.0 : 0.0); }
+          const double val = (rr > pos[h]) ? cr[h][r] * sch[h] : ((rr == pos[h]) ? beh[h] : cr[h][r]);
+          A[(k0 + rr) + (long)(k0 + pos[h]) * ld] = val;
+          Vs[rr + (long)pos[h] * ldv] = (rr > pos[h]) ? val : ((rr == pos[h]) ? 1.0 : 0.0);
         }
       }
+    }
+    // rows above k0 (entries of R computed by earlier panels) follow the in-panel permutation: four row blocks at a time through registers
+    for (int rb0 = 0; rb0 < (k0 >> 5); rb0 += 4) {
+      double up[CPW][4];
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const int i = lane + 32 * (rb0 + t);
+#pragma unroll
+        for (int h = 0; h < CPW; ++h) up[h][t] = (i < k0 && pos[h] >= 0) ? A[i + (long)(k0 + sb + h) * ld] : 0.0;
+      }
+      __syncthreads();
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const int i = lane + 32 * (rb0 + t);
+#pragma unroll
+        for (int h = 0; h < CPW; ++h) if (i < k0 && pos[h] >= 0) A[i + (long)(k0 + pos[h]) * ld] = up[h][t];
+      }
+      __syncthreads();
     }
     if (lane == 0) {
 #pragma unroll
@@ -366,56 +418,61 @@ __global__ void __launch_bounds__(32 * (QR2_NB / CPW), CPW == 4 ? 2 : 1) k_qrp_r
     if (tid >= nbk && tid < NB) tau_s[tid] = 0.0;
     __syncthreads();
     if (tid < nbk) ipv[k0 + tid] = lista[tid];
+    QRP_ACC(4)
     // ---- (6) Gram matrix of the reflectors, then the triangular factor T (ZLARFT forward / columnwise) by one warp
     blk_gemm<1, 0>(NB, NB, mvp, Vs, ldv, Vs, ldv, Gs, LDW, 1.0);
     __syncthreads();
     if (warp == 0) {
-      double trow[NB];
+      // T (ZLARFT, forward / columnwise): T(:, j) = -tau_j T(:, 0:j) G(0:j, j), lane i owns row i.  Right-looking form: as soon as column l is final its
+      // contribution T(i, l) G(l, j) goes to the accumulators of ALL later columns -- independent FMAs instead of one dependent chain per column.
+      double acc[NB];
 #pragma unroll
-      for (int l = 0; l < NB; ++l) trow[l] = 0.0;
+      for (int l = 0; l < NB; ++l) acc[l] = 0.0;
 #pragma unroll
-      for (int j = 0; j < NB; ++j) {
-        const double tj = tau_s[j];
-        double x0 = 0.0, x1 = 0.0;
+      for (int l = 0; l < NB; ++l) {
+        const double tl = tau_s[l];
+        const double t = (lane < l) ? -tl * acc[l] : ((lane == l) ? tl : 0.0);
+        Ts[lane + l * LDW] = t;
+        Tbuf[(long)(k0 / NB) * NB * NB + lane + l * NB] = t;
 #pragma unroll
-        for (int l = 0; l < j; ++l) { if (l & 1) x1 = fma(trow[l], Gs[l + j * LDW], x1); else x0 = fma(trow[l], Gs[l + j * LDW], x0); }
-        const double t = (lane < j) ? -tj * (x0 + x1) : ((lane == j) ? tj : 0.0);
-        trow[j] = t;
-        Ts[lane + j * LDW] = t;
-        Tbuf[(long)(k0 / NB) * NB * NB + lane + j * NB] = t;
+        for (int jj = l + 1; jj < NB; ++jj) acc[jj] = fma(t, Gs[l + jj * LDW], acc[jj]);
       }
     }
     __syncthreads();
+    QRP_ACC(5)
     // ---- (7) trailing update with exact recomputation of the remaining column norms
     apply_panel_strips<1>(A, ld, k0, m, k0 + nbk, n, Vs, ldv, Ts, nbk, Wsc, vn);
     __syncthreads();
+    QRP_ACC(6)
   }
   // ---- D(i) = |R(i,i)|, R(i, i:) /= D(i); phases (QDRP_decompose_mod.F90:86-100, Pivot_phase :103-126)
-  for (int i = tid; i < kmax; i += nthr) { const double x = fabs(A[i + (long)i * ld]); D[i] = x; v_s[i] = x; }
-  __syncthreads();
-  for (int c = warp; c < n; c += nw) {
-    const int top = min(c, kmax - 1);
-    for (int i = lane; i <= top; i += 32) A[i + (long)c * ld] = A[i + (long)c * ld] * (1.0 / v_s[i]);
-  }
-  for (int c = tid; c < n; c += nthr) jpvt[c] = ipv[c];
-  __syncthreads();
-  if (warp == 0) {
-    // sign of prod R_ii (after the scaling R_ii = +-1)
-    int neg = 0;
-    for (int i = lane; i < kmax; i += 32) neg ^= (A[i + (long)i * ld] < 0.0) ? 1 : 0;
+  int negd = 0;                                        // sign of prod R_ii
+  for (int i = tid; i < kmax; i += nthr) { const double r = A[i + (long)i * ld], x = fabs(r); D[i] = x; v_s[i] = 1.0 / x; negd ^= (r < 0.0) ? 1 : 0; }
+  const int neg_total = __syncthreads_count(negd) & 1;
+  // the upper trapezoid as one flat loop over all threads (independent, coalesced read-modify-writes)
+  for (int c0 = 8 * warp; c0 < n; c0 += 8 * nw) {        // eight columns per warp and pass: all loads before the first store
+    for (int i0 = 0; i0 < kmax && i0 <= c0 + 7; i0 += 32) {
+      const int i = i0 + lane; double x[8];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) neg ^= __shfl_xor_sync(0xffffffffu, neg, o);
-    if (lane == 0) {
-      double sg = 1.0;      // permutation parity: cycles of even length flip the sign
-      for (int i = 0; i < n; ++i) rank_s[i] = 0;
-      for (int i = 0; i < n; ++i) if (rank_s[i] == 0) {
-        int next = i, L = 0;
-        while (rank_s[next] == 0) { ++L; rank_s[next] = 1; next = ipv[next]; }
-        if ((L & 1) == 0) sg = -sg;
-      }
-      out[b].perm_sign = sg; out[b].diag_phase = cplx(neg ? -1.0 : 1.0, 0.0); out[b].detq = cplx(s_detq[0], s_detq[1]);
+      for (int t = 0; t < 8; ++t) x[t] = (c0 + t < n && i < kmax && i <= c0 + t) ? A[i + (long)(c0 + t) * ld] : 0.0;
+      const double sc = (i < kmax) ? v_s[i] : 0.0;
+#pragma unroll
+      for (int t = 0; t < 8; ++t) if (c0 + t < n && i < kmax && i <= c0 + t) A[i + (long)(c0 + t) * ld] = x[t] * sc;
     }
   }
+  for (int c = tid; c < n; c += nthr) jpvt[c] = ipv[c];
+  // permutation parity = (-1)^(n - number of cycles): every thread walks the cycle of its element; the smallest element of a cycle counts it
+  int leaders = 0;
+  for (int i = tid; i < n; i += nthr) { int mn = i, x = ipv[i]; while (x != i) { mn = min(mn, x); x = ipv[x]; } leaders += (mn == i) ? 1 : 0; }
+  __shared__ int s_cyc;
+  if (tid == 0) s_cyc = 0;
+  __syncthreads();
+  leaders += __shfl_xor_sync(0xffffffffu, leaders, 16); leaders += __shfl_xor_sync(0xffffffffu, leaders, 8); leaders += __shfl_xor_sync(0xffffffffu, leaders, 4);
+  leaders += __shfl_xor_sync(0xffffffffu, leaders, 2); leaders += __shfl_xor_sync(0xffffffffu, leaders, 1);
+  if (lane == 0 && leaders) atomicAdd(&s_cyc, leaders);
+  __syncthreads();
+  if (tid == 0) { out[b].perm_sign = ((n - s_cyc) & 1) ? -1.0 : 1.0; out[b].diag_phase = cplx(neg_total ? -1.0 : 1.0, 0.0); out[b].detq = cplx(s_detq[0], s_detq[1]); }
+  QRP_ACC(7)
 }
 
 // ------------------------------------------------------------------------------------------------------------------------
