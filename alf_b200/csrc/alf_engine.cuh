@@ -1078,7 +1078,8 @@ struct Engine : EngineBase {
       if (scal_tab) KL(KC_OBS, st, k_obs_scal_tables<T><<<C, 256, 0, st>>>(gs, n2, N, F, h->n_sun, h->d_phase, h->n_kin, h->d_kin_idx, h->d_kin_coef, h->n_pot, h->d_pot_idx, h->d_pot_coef, h->d_obs));
       if (h->obs_eq_on) {
         KL(KC_EW, st, k_g0t_init<T><<<dim3(ew_blocks(n2), NM), 256, 0, st>>>(obsS[1], gs, n2, N));      // G - 1
-        KL(KC_OBS, st, k_obs_tau<T, 1><<<C, 256, obst_smem, st>>>(gs, obsS[1], gs, gs, n2, N, F, h->n_sun, h->d_phase, lt, 0, 1, h->d_obse_acc, h->d_obse_bg, h->d_obse_cnt));
+        if (lt.shift32) KL(KC_OBS, st, k_obs_tau_diag<T, 1><<<dim3(N / 32, C), 256, obst_smem, st>>>(gs, obsS[1], gs, gs, n2, N, F, h->n_sun, h->d_phase, lt, 0, 1, h->d_obse_acc, h->d_obse_bg, h->d_obse_cnt));
+        else KL(KC_OBS, st, k_obs_tau<T, 1><<<C, 256, obst_smem, st>>>(gs, obsS[1], gs, gs, n2, N, F, h->n_sun, h->d_phase, lt, 0, 1, h->d_obse_acc, h->d_obse_bg, h->d_obse_cnt));
       }
     }
   }
@@ -1159,11 +1160,20 @@ struct Engine : EngineBase {
     if (F > 2) throw CudaError("obs_tau: more than two flavors are not supported");
     lt.n_unit = h->n_unit; lt.norb = h->norb;
     lt.cell = dupload(h->site_cell); lt.orb = dupload(h->site_orb); lt.imj = dupload(h->imj);
+    {   // is the site numbering invariant under a shift by 32 sites (a lattice translation that keeps orbitals and lattice displacements)?  -> k_obs_tau_diag
+      bool ok = (N % 32 == 0) && N >= 64 && !getenv("ALF_B200_NO_OBS_DIAG");
+      for (int i = 0; i < N && ok; ++i) { const int i2 = (i + 32) % N; if (h->site_cell[i] < 0 || h->site_cell[i2] < 0 || h->site_orb[i] != h->site_orb[i2]) ok = false; }
+      for (int i = 0; i < N && ok; ++i) for (int j = 0; j < N && ok; ++j)
+        if (h->imj[h->site_cell[(i + 32) % N] + (size_t)h->site_cell[(j + 32) % N] * h->n_unit] != h->imj[h->site_cell[i] + (size_t)h->site_cell[j] * h->n_unit]) ok = false;
+      lt.shift32 = ok ? 1 : 0;
+    }
     for (int q = 0; q < 4; ++q) if (!obsS[q]) obsS[q] = dalloc<T>(n2 * NM);
     obst_smem = obs_tau_smem<T>(N, lt.n_unit, lt.norb);
     if (obst_smem > 227 * 1024) throw CudaError("obs_tau: lattice too large for the shared-memory bins");
     CK(alf_raise_smem(k_obs_tau<T, 0>));
     CK(alf_raise_smem(k_obs_tau<T, 1>));
+    CK(alf_raise_smem(k_obs_tau_diag<T, 0>));
+    CK(alf_raise_smem(k_obs_tau_diag<T, 1>));
   }
   void obsert(int nt_index) {      // where TAU_M / Tau_p call ham%ObserT(nt_index, GT0, G0T, G00, GTT, Phase): tau_m_mod.F90:115-124,151-177
     if (!h->obs_tau_on || nt_index < 0 || nt_index >= h->obst_ntau) return;
@@ -1179,7 +1189,9 @@ struct Engine : EngineBase {
       }
       if (q == 2) g00_sym_of = G00;
     }
-    KL(KC_OBS, st, k_obs_tau<T, 0><<<C, 256, obst_smem, st>>>(use[0], use[1], use[2], use[3], n2, N, F, h->n_sun, h->d_phase, lt, nt_index, h->obst_ntau,
+    if (lt.shift32) KL(KC_OBS, st, k_obs_tau_diag<T, 0><<<dim3(N / 32, C), 256, obst_smem, st>>>(use[0], use[1], use[2], use[3], n2, N, F, h->n_sun, h->d_phase, lt, nt_index, h->obst_ntau,
+                                                                                 h->d_obst_acc, h->d_obst_bg, h->d_obst_cnt));
+    else KL(KC_OBS, st, k_obs_tau<T, 0><<<C, 256, obst_smem, st>>>(use[0], use[1], use[2], use[3], n2, N, F, h->n_sun, h->d_phase, lt, nt_index, h->obst_ntau,
                                                         h->d_obst_acc, h->d_obst_bg, h->d_obst_cnt));
   }
   void compare_tau(const T* A, const T* B) {   // Control_Precision_tau, control_mod.F90:300-311

@@ -15,7 +15,7 @@
 
 #define OBST_NCH 4
 
-struct LattDev { int n_unit = 0, norb = 1; const int* cell = nullptr; const int* orb = nullptr; const int* imj = nullptr; };   // 0-based tables
+struct LattDev { int n_unit = 0, norb = 1; const int* cell = nullptr; const int* orb = nullptr; const int* imj = nullptr; int shift32 = 0; };   // 0-based tables; shift32: see k_obs_tau_diag
 
 // acc: [ch][nt][no_J][no_I][imj] complex; bg: [2][nt][norb] complex; cnt: [0] N (chain-measurements at nt = 0), [1] sum ZS
 // EQ = 1: the equal-time variants Predefined_Obs_eq_Green / SpinMz / SpinSUN / Den_measure (Predefined_Obs_mod.F90:77-325) on the inputs
@@ -106,6 +106,99 @@ __global__ void __launch_bounds__(256) k_obs_tau(const T* __restrict__ GT0, cons
     atomicAdd(b0, bz.x); atomicAdd(b0 + 1, bz.y); atomicAdd(b1, bd.x); atomicAdd(b1 + 1, bd.y);
   }
   if (tid == 0 && nt == 0) { atomicAdd(cnt, 1.0); atomicAdd(cnt + 1, zs); }
+}
+
+// ------------------------------------------------------------------------------------------------------------------------
+// k_obs_tau_diag: the same accumulation for lattices whose site numbering is invariant under a shift by 32 sites (imj(i + 32, j + 32) = imj(i, j),
+// same orbitals -- e.g. the 16 x 16 square lattice, where 32 sites are two lattice rows; checked on the host, LattDev::shift32).  k_obs_tau spends
+// its time in eight shared-memory FP64 atomics per site pair (0.69 ms per time point against an HBM floor of 0.05 ms).  Here a CTA (chain, Delta)
+// walks the N/32 tiles (I, J) = (J + Delta, J) of one block diagonal: a thread's site pair keeps its lattice displacement d from tile to tile, so the
+// four channels accumulate in REGISTERS over the whole diagonal and go to the shared-memory bins once.
+// ------------------------------------------------------------------------------------------------------------------------
+template <typename T, int EQ>
+__global__ void __launch_bounds__(256) k_obs_tau_diag(const T* __restrict__ GT0, const T* __restrict__ G0T, const T* __restrict__ G00, const T* __restrict__ GTT,
+                                                      long sM, int N, int F, int n_sun, const cplx* __restrict__ phase, LattDev lt, int nt, int ntau,
+                                                      double* __restrict__ acc, double* __restrict__ bg, double* __restrict__ cnt) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int n_unit = lt.n_unit, norb = lt.norb, norb2 = norb * norb;
+  double* bins = reinterpret_cast<double*>(smem_raw);                 // [ch][no][imj] (re, im)
+  T* dTT = reinterpret_cast<T*>(bins + (size_t)2 * OBST_NCH * norb2 * n_unit);     // [f][N]
+  T* d00 = dTT + (size_t)2 * N;
+  typedef T Tile[32][33];
+  Tile* tB = reinterpret_cast<Tile*>(d00 + (size_t)2 * N);      // [f]: G0T tile as stored (rows J fastest), [i][j]
+  const int c = blockIdx.y, delta = blockIdx.x, tid = threadIdx.x, tx = tid & 31, ty = tid >> 5, ntl = N >> 5;
+  const long base = (long)c * F * sM;
+  for (int e = tid; e < 2 * OBST_NCH * norb2 * n_unit; e += blockDim.x) bins[e] = 0.0;
+  for (int e = tid; e < F * N; e += blockDim.x) { const int f = e / N, i = e % N; dTT[e] = GTT[base + f * sM + i + (long)i * N]; d00[e] = G00[base + f * sM + i + (long)i * N]; }
+  __syncthreads();
+  cplx v[4][OBST_NCH];
+#pragma unroll
+  for (int q = 0; q < 4; ++q)
+#pragma unroll
+    for (int ch = 0; ch < OBST_NCH; ++ch) v[q][ch] = cplx(0.0, 0.0);
+  for (int k = 0; k < ntl; ++k) {
+    const int J = k, I = (k + delta) % ntl, i0 = 32 * I, j0 = 32 * J;
+    for (int f = 0; f < F && f < 2; ++f)
+      for (int r = ty; r < 32; r += 8) tB[f][r][tx] = G0T[base + f * sM + (j0 + tx) + (long)(i0 + r) * N];      // G0T(jj, ii): jj fastest
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int r = ty + 8 * q, i = i0 + tx, j = j0 + r;
+      cplx gt0[2], g0t[2];
+      for (int f = 0; f < F && f < 2; ++f) { const T a = GT0[base + f * sM + i + (long)j * N], b2 = tB[f][tx][r]; gt0[f] = cplx(real_(a), imag_(a)); g0t[f] = cplx(real_(b2), imag_(b2)); }
+      cplx zi = cplx(0.0, 0.0), zj = cplx(0.0, 0.0), zz = cplx(0.0, 0.0), gsum = cplx(0.0, 0.0);
+      for (int f = 0; f < F && f < 2; ++f) {
+        const T a = dTT[f * N + i], b2 = d00[f * N + j];
+        zi = zi + (cplx(1.0, 0.0) - cplx(real_(a), imag_(a))); zj = zj + (cplx(1.0, 0.0) - cplx(real_(b2), imag_(b2)));
+        zz = zz - g0t[f] * gt0[f]; gsum = gsum + gt0[f];
+      }
+      if (EQ) { cplx gc = cplx(0.0, 0.0); for (int f = 0; f < F && f < 2; ++f) gc = gc - g0t[f]; v[q][0] = v[q][0] + gc * (double)n_sun; }
+      else v[q][0] = v[q][0] + gsum * (1.0 / (double)F);
+      if (F >= 2) {
+        const T a1 = dTT[i], a2 = dTT[N + i], b1 = d00[j], b2 = d00[N + j];
+        const cplx da = cplx(real_(a1) - real_(a2), imag_(a1) - imag_(a2)), db = cplx(real_(b1) - real_(b2), imag_(b1) - imag_(b2));
+        v[q][1] = v[q][1] + (da * db + zz);
+        v[q][2] = v[q][2] - g0t[0] * gt0[1] - g0t[1] * gt0[0];
+      } else v[q][1] = v[q][1] + zz * (double)n_sun;
+      v[q][3] = v[q][3] + ((zi * (double)n_sun) * (zj * (double)n_sun) + zz * (double)n_sun);
+    }
+    __syncthreads();
+  }
+  // a thread's four site pairs (tile-independent displacement and orbital pair): registers -> bins
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int i = 32 * delta + tx, j = ty + 8 * q;          // representative pair of the diagonal: tile (Delta, 0)
+    const int ci = lt.cell[i % N], cj = lt.cell[j];
+    if (ci >= 0 && cj >= 0) {
+      const int no = lt.orb[i % N] + norb * lt.orb[j]; const int d = lt.imj[ci + (long)cj * n_unit];
+#pragma unroll
+      for (int ch = 0; ch < OBST_NCH; ++ch) { double* bp = bins + 2 * ((size_t)(ch * norb2 + no) * n_unit + d); atomicAdd(bp, v[q][ch].x); atomicAdd(bp + 1, v[q][ch].y); }
+    }
+  }
+  __syncthreads();
+  const cplx ph = phase[c]; const double zs = (ph.x >= 0.0) ? 1.0 : -1.0; const cplx zpzs = cplx(zs, zs * ph.y / ph.x);
+  for (int e = tid; e < OBST_NCH * norb2 * n_unit; e += blockDim.x) {
+    if (bins[2 * e] == 0.0 && bins[2 * e + 1] == 0.0) continue;      // displacements this diagonal does not contain
+    const int ch = e / (norb2 * n_unit), rest = e % (norb2 * n_unit);
+    const cplx vv = cplx(bins[2 * e], bins[2 * e + 1]) * zpzs;
+    double* ap = acc + 2 * (((size_t)ch * ntau + nt) * norb2 * n_unit + rest);
+    atomicAdd(ap, vv.x); atomicAdd(ap + 1, vv.y);
+  }
+  if (delta == 0) {      // backgrounds (Obs_Latt0) and counters: once per chain
+    if (tid < norb) {
+      cplx bz = cplx(0.0, 0.0), bd = cplx(0.0, 0.0);
+      for (int i = 0; i < N; ++i) if (lt.cell[i] >= 0 && lt.orb[i] == tid) {
+        cplx zi = cplx(0.0, 0.0);
+        for (int f = 0; f < F && f < 2; ++f) { const T a = dTT[f * N + i]; zi = zi + (cplx(1.0, 0.0) - cplx(real_(a), imag_(a))); }
+        bd = bd + zi * (double)n_sun;
+        if (F >= 2) { const T a1 = dTT[i], a2 = dTT[N + i]; const cplx dd = cplx(real_(a2) - real_(a1), imag_(a2) - imag_(a1)); bz = EQ ? bz - dd : bz + dd; }
+      }
+      bz = bz * zpzs; bd = bd * zpzs;
+      double* b0 = bg + 2 * ((size_t)(0 * ntau + nt) * norb + tid); double* b1 = bg + 2 * ((size_t)(1 * ntau + nt) * norb + tid);
+      atomicAdd(b0, bz.x); atomicAdd(b0 + 1, bz.y); atomicAdd(b1, bd.x); atomicAdd(b1 + 1, bd.y);
+    }
+    if (tid == 0 && nt == 0) { atomicAdd(cnt, 1.0); atomicAdd(cnt + 1, zs); }
+  }
 }
 
 template <typename T>

@@ -639,13 +639,16 @@ def test_too_large_ndim_fails_loudly():
 
 # ---------------------------------------------------------------------------------- device-side ObserT (time-displaced lattice observables)
 @pytest.mark.gpu
-@pytest.mark.parametrize("which", ["hubbard_mz_symm", "hubbard_su2", "hubbard_mz_nosymm", "kondo", "projector"])
+@pytest.mark.parametrize("which", ["hubbard_mz_symm", "hubbard_su2", "hubbard_mz_nosymm", "kondo", "projector", "hubbard_mz_8x8_diag", "hubbard_su2_8x8_diag", "kondo_8x4_diag"])
 def test_obs_tau_on_device(which):
     """Green / SpinZ / SpinXY / Den time-displaced correlation functions and their backgrounds, accumulated on the device where TAU_M /
     Tau_p call ham%ObserT (with Hop_mod_Symm when Symm), against the oracle's restatement of Predefined_Obs_tau_*_measure."""
     model = {"hubbard_mz_symm": lambda: hubbard_square(4, 4, 0.8), "hubbard_su2": lambda: hubbard_square(4, 4, 0.8, Mz=False),
              "hubbard_mz_nosymm": lambda: hubbard_square(4, 2, 0.6, symm=False), "kondo": lambda: kondo_square(2, 2, 0.6),
-             "projector": lambda: hubbard_square(4, 4, 0.6, projector=True, theta=0.3, trial="dimer")}[which]()
+             "projector": lambda: hubbard_square(4, 4, 0.6, projector=True, theta=0.3, trial="dimer"),
+             # N a multiple of 32 and the numbering invariant under a shift by 32 sites: the register-accumulating kernel k_obs_tau_diag
+             "hubbard_mz_8x8_diag": lambda: hubbard_square(8, 8, 0.4), "hubbard_su2_8x8_diag": lambda: hubbard_square(8, 8, 0.4, Mz=False),
+             "kondo_8x4_diag": lambda: kondo_square(8, 4, 0.4)}[which]()
     seeds = SEEDS[:2]; nwrap = 4
     g = AlfB200(model, n_chains=len(seeds), nwrap=nwrap); g.set_seeds(seeds); g.fields_set(); g.init_sweep(); g.obs_tau_enable()
     orcs = []
@@ -670,12 +673,13 @@ def test_obs_tau_on_device(which):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("which", ["hubbard_mz_symm", "hubbard_su2", "kondo"])
+@pytest.mark.parametrize("which", ["hubbard_mz_symm", "hubbard_su2", "kondo", "hubbard_mz_8x8_diag", "kondo_8x4_diag"])
 def test_obs_eq_on_device(which):
     """Equal-time Green / SpinZ / SpinXY / Den correlation functions accumulated on the device at every measured slice (on the
     symmetrised G, as main.F90:761-764 hands GR_Tilde to ham%Obser) against the oracle's restatement of Predefined_Obs_eq_*_measure."""
     model = {"hubbard_mz_symm": lambda: hubbard_square(4, 4, 0.8), "hubbard_su2": lambda: hubbard_square(4, 4, 0.8, Mz=False),
-             "kondo": lambda: kondo_square(2, 2, 0.6)}[which]()
+             "kondo": lambda: kondo_square(2, 2, 0.6), "hubbard_mz_8x8_diag": lambda: hubbard_square(8, 8, 0.4),
+             "kondo_8x4_diag": lambda: kondo_square(8, 4, 0.4)}[which]()
     seeds = SEEDS[:2]; nwrap = 4
     g = AlfB200(model, n_chains=len(seeds), nwrap=nwrap); g.set_seeds(seeds); g.fields_set(); g.init_sweep(); g.obs_eq_enable()
     orcs = []
