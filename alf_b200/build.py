@@ -36,6 +36,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
         flags.append("-Xptxas=-v")
     if os.environ.get("ALF_QR_PROF"):      # experimental: phase accounting inside k_qrp_reg (alf_qrblk2.cuh)
         flags.append("-DALF_QR_PROF")
+    if os.environ.get("ALF_UPD_PROF"):     # experimental: phase accounting inside k_wrapgr_fast (alf_update_fast.cuh)
+        flags.append("-DALF_UPD_PROF")
 
     def cc(u):
         o = os.path.join(OBJ, u.replace(".cu", ".o"))

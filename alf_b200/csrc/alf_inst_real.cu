@@ -8,3 +8,9 @@ extern "C" void alf_b200_qr_prof_read(unsigned long long* out, int reset) {     
   if (reset) { unsigned long long z[16] = {0}; cudaMemcpyToSymbol(g_qr_prof, z, sizeof(z)); }
 }
 #endif
+#ifdef ALF_UPD_PROF
+extern "C" void alf_b200_upd_prof_read(unsigned long long* out, int reset) {      // experimental builds only (build.py: ALF_UPD_PROF=1)
+  cudaMemcpyFromSymbol(out, g_upd_prof, sizeof(unsigned long long) * 16);
+  if (reset) { unsigned long long z[16] = {0}; cudaMemcpyToSymbol(g_upd_prof, z, sizeof(z)); }
+}
+#endif

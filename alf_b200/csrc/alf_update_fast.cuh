@@ -156,6 +156,14 @@ __device__ __forceinline__ void upd_phase(cplx& ph, double rt) { if (rt < 0.0) p
 __device__ __forceinline__ void upd_phase(cplx& ph, cplx rt) { const double ar = abs_(rt); ph = ph * cplx(rt.x / ar, rt.y / ar); }
 
 #define ALF_WIN 16          // visits per window
+#ifdef ALF_UPD_PROF      // experimental build only: clock64 accounting of the phases of k_wrapgr_fast (thread 0, summed over CTAs)
+__device__ unsigned long long g_upd_prof[16];
+#define UPP_T0 long long up_t = clock64();
+#define UPP_ACC(i) if (threadIdx.x == 0) { const long long t_ = clock64(); atomicAdd(&g_upd_prof[i], (unsigned long long)(t_ - up_t)); up_t = t_; }
+#else
+#define UPP_T0
+#define UPP_ACC(i)
+#endif
 #define ALF_CH 8            // accepted flips whose G0 column/row are in flight at once in the bulk phase
 
 // The kernel visits the vertices n0 .. n0 + cnt - 1 of the slice (a GROUP of vertices with pairwise disjoint supports; Mtot =
@@ -198,6 +206,7 @@ __global__ void __launch_bounds__(512, 1) k_wrapgr_fast(T* __restrict__ G, int N
   int8_t* st_snew = st_sold + M;
   int8_t* st_type = st_snew + M;
 
+  UPP_T0
   T* Gc = G + (long)chain * F * N * N;
   int8_t* fld = fields + ((long)chain * Ltrot + (nt - 1)) * Mtot;
   auto vertex_of = [&](int s) { const int pv = PAIR ? (s >> 1) : s; return UP ? n0 + pv : n0 + cnt - 1 - pv; };
@@ -255,6 +264,7 @@ __global__ void __launch_bounds__(512, 1) k_wrapgr_fast(T* __restrict__ G, int N
   }
   __syncthreads();
 
+  UPP_ACC(0)
   cplx ph = phase[chain];
   unsigned long long n_acc = 0, n_flush = 0;
   int nd = 0;
@@ -279,7 +289,7 @@ __global__ void __launch_bounds__(512, 1) k_wrapgr_fast(T* __restrict__ G, int N
   int v0 = 0;
   bool raw_valid = true;
   while (v0 < M) {
-    if (nd == KD) { do_flush(); raw_valid = false; }
+    if (nd == KD) { UPP_ACC(1) do_flush(); raw_valid = false; UPP_ACC(2) }
     if (!raw_valid) { gw_prefetch(v0); raw_valid = true; }
     const int Wn = min(W, M - v0), cap = min(KD - nd, W);
     // ---- (a) G_cur on the window's sites: DL G0 DR - X Y^T restricted to (P_w, P_w)
@@ -299,6 +309,7 @@ __global__ void __launch_bounds__(512, 1) k_wrapgr_fast(T* __restrict__ G, int N
       }
     }
     __syncthreads();
+    UPP_ACC(3)
     // ---- (b) one warp: the window's Metropolis decisions on the small block (Upgrade2 for rank-1 vertices).  This is the only
     // sequential part of the slice, so it is written for latency: per visit 1 shared load + a handful of dependent FP64 ops.
     if (warp == 0) {
@@ -370,6 +381,7 @@ __global__ void __launch_bounds__(512, 1) k_wrapgr_fast(T* __restrict__ G, int N
       if (lane == 0) { win_nvis = v; win_nacc = nacc; }
     }
     __syncthreads();
+    UPP_ACC(4)
     const int nvis = win_nvis, nacc = win_nacc, nd0 = nd;
     // ---- (c) all threads: full-length factors of the accepted flips; thread (f, i) owns element i of every factor of flavor f
     {
@@ -465,8 +477,10 @@ __global__ void __launch_bounds__(512, 1) k_wrapgr_fast(T* __restrict__ G, int N
     nd = nd0 + nacc; v0 += nvis;
     if (nd < KD && v0 < M) gw_prefetch(v0);       // next window's raw block (G0 is unchanged unless a flush comes first)
     __syncthreads();
+    UPP_ACC(5)
   }
   do_flush();
+  UPP_ACC(2)
   if (tid == 0) {
     phase[chain] = ph;
     counters[chain * 4 + 0] += (unsigned long long)cnt; // NC_up
