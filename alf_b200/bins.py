@@ -79,20 +79,8 @@ def fourier_r_to_k(x_r, latt):
     return (phase @ np.asarray(x_r, dtype=np.complex128)) / latt.N, kv
 
 
-def print_bin_latt(name, obs_sum, bg_sum, sign_sum, n_meas_per_chain, n_chains, latt, dtau=None, channel="---", n_coord=2, orb_pos=None):
-    """Print_bin_Latt (Prog/observables_mod.F90:355-515), text layout (:494-512): appends one bin to `<name>_tau` (or `<name>_eq` if
-    there is a single time point).  obs_sum[nt, no, no1, r]: real-space accumulator summed over chains (Obs_Latt(imj, nt, no, no1));
-    bg_sum[no]: Obs_Latt0 summed over chains and time points; n_meas_per_chain = Obs%N.  n_coord, orb_pos[no][:] = Latt_unit%N_coord and
-    Latt_unit%Orb_pos_p (Prog/Predefined_Latt_mod.F90:117-237; default: square lattice, one orbital at the origin): they go into the
-    `_info` file (:457-491) in exactly the order Analysis/ana_mod.F90:285-309 reads them back."""
-    obs_sum = np.asarray(obs_sum, dtype=np.complex128); ntau, norb, _, ns = obs_sum.shape
-    assert ns == latt.N
-    suffix = "_eq" if ntau == 1 else "_tau"
-    file_pr = name + suffix
-    norm = float(n_meas_per_chain) * float(n_chains)
-    obs = obs_sum / norm                                               # Obs_Latt / N, averaged over ranks
-    bg = np.asarray(bg_sum, dtype=np.complex128) / (norm * ns * ntau)  # Obs_Latt0 / (N Ns Ntau)
-    ave_sign = float(sign_sum) / norm
+def _write_info(file_pr, channel, ntau, dtau, latt, norb, n_coord, orb_pos):
+    """`<file>_info`, written once (Prog/observables_mod.F90:457-491 and :664-698, same text for both record types)."""
     info = file_pr + "_info"
     if orb_pos is None:
         orb_pos = np.zeros((norb, 2))
@@ -108,6 +96,23 @@ def print_bin_latt(name, obs_sum, bg_sum, sign_sum, n_meas_per_chain, n_chains, 
             f.write(f"{'Coordination number':>20s}: {int(n_coord):10d}\n{'Number of orbitals':>20s}: {norb:10d}\n{'Ndim':>20s}: {orb_pos.shape[1]:10d}\n")
             for no in range(norb):
                 f.write(f"{'Orbital %d' % (no + 1):>20s}: " + "".join(_e(x, 26) for x in orb_pos[no]) + "\n")
+
+
+def print_bin_latt(name, obs_sum, bg_sum, sign_sum, n_meas_per_chain, n_chains, latt, dtau=None, channel="---", n_coord=2, orb_pos=None):
+    """Print_bin_Latt (Prog/observables_mod.F90:355-515), text layout (:494-512): appends one bin to `<name>_tau` (or `<name>_eq` if
+    there is a single time point).  obs_sum[nt, no, no1, r]: real-space accumulator summed over chains (Obs_Latt(imj, nt, no, no1));
+    bg_sum[no]: Obs_Latt0 summed over chains and time points; n_meas_per_chain = Obs%N.  n_coord, orb_pos[no][:] = Latt_unit%N_coord and
+    Latt_unit%Orb_pos_p (Prog/Predefined_Latt_mod.F90:117-237; default: square lattice, one orbital at the origin): they go into the
+    `_info` file (:457-491) in exactly the order Analysis/ana_mod.F90:285-309 reads them back."""
+    obs_sum = np.asarray(obs_sum, dtype=np.complex128); ntau, norb, _, ns = obs_sum.shape
+    assert ns == latt.N
+    suffix = "_eq" if ntau == 1 else "_tau"
+    file_pr = name + suffix
+    norm = float(n_meas_per_chain) * float(n_chains)
+    obs = obs_sum / norm                                               # Obs_Latt / N, averaged over ranks
+    bg = np.asarray(bg_sum, dtype=np.complex128) / (norm * ns * ntau)  # Obs_Latt0 / (N Ns Ntau)
+    ave_sign = float(sign_sum) / norm
+    _write_info(file_pr, channel, ntau, dtau, latt, norb, n_coord, orb_pos)
     lines = []
     if ntau == 1:
         lines.append(_e(ave_sign, 25) + f"{norb:11d}{latt.N:11d}")
@@ -131,6 +136,57 @@ def print_bin_latt(name, obs_sum, bg_sum, sign_sum, n_meas_per_chain, n_chains, 
     with open(file_pr, "a") as f:
         f.write("\n".join(lines) + "\n")
     return file_pr
+
+
+def print_bin_latt_local(name, obs_sum, sign_sum, n_meas_per_chain, n_chains, latt, dtau=None, channel="---", n_coord=2, orb_pos=None):
+    """Print_bin_Latt_Local (Prog/observables_mod.F90:578-767), text layout (:700-717): appends one bin of a site-resolved
+    observable to `<name>_local` (one time point) or `<name>_localtau`.  obs_sum[nt, no, r] = Obs_Latt(I, nt, no) summed over
+    chains; no Fourier transform and no background: each unit cell is headed by its real-space position list(I,1) a1 + list(I,2) a2."""
+    obs_sum = np.asarray(obs_sum, dtype=np.complex128); ntau, norb, ns = obs_sum.shape
+    assert ns == latt.N
+    file_pr = name + ("_local" if ntau == 1 else "_localtau")
+    norm = float(n_meas_per_chain) * float(n_chains)
+    obs = obs_sum / norm
+    ave_sign = float(sign_sum) / norm
+    _write_info(file_pr, channel, ntau, dtau, latt, norb, n_coord, orb_pos)
+    if ntau == 1:
+        lines = [_e(ave_sign, 25) + f"{norb:11d}{latt.N:11d}"]
+    else:
+        lines = [_e(ave_sign, 25) + f"{norb:11d}{latt.N:11d}{ntau:11d}" + _e(dtau or 0.0, 26)]
+    pts = np.asarray(latt.list, dtype=np.float64)
+    for i in range(latt.N):
+        lines.append(_e(pts[i, 0], 25) + " " + _e(pts[i, 1], 25))
+        for nt in range(ntau):
+            for no in range(norb):
+                z = obs[nt, no, i]
+                lines.append("(" + _e(z.real, 25) + "," + _e(z.imag, 25) + ")")
+    with open(file_pr, "a") as f:
+        f.write("\n".join(lines) + "\n")
+    return file_pr
+
+
+def read_latt_local(file_pr):
+    """Reads `_local` / `_localtau` bins back the way Analysis/ana_mod.F90 (read_latt with no background and one orbital index) does:
+    returns (sign[nb], obs[nb, ntau, norb, r], x_r[r, 2])."""
+    def cplx(s):
+        a, b = s.strip()[1:-1].split(",")
+        return complex(float(a), float(b))
+    with open(file_pr) as f:
+        rows = [ln.rstrip("\n") for ln in f if ln.strip()]
+    signs, bins, pos = [], [], None
+    p = 0
+    while p < len(rows):
+        head = rows[p].split(); p += 1
+        norb, ns = int(head[1]), int(head[2]); ntau = int(head[3]) if len(head) > 3 else 1
+        signs.append(float(head[0]))
+        obs = np.zeros((ntau, norb, ns), dtype=np.complex128); xr = np.zeros((ns, 2))
+        for i in range(ns):
+            xr[i] = [float(t) for t in rows[p].split()]; p += 1
+            for nt in range(ntau):
+                for no in range(norb):
+                    obs[nt, no, i] = cplx(rows[p]); p += 1
+        bins.append(obs); pos = xr
+    return np.array(signs), np.array(bins), pos
 
 
 def read_latt(file_pr):

@@ -87,3 +87,29 @@ def test_conf_roundtrip_all_field_types(tmp_path):
     assert int(lines[1]) == int(f[0, 0].real) and lines[4].strip().startswith("(")          # I fastest: line 1 + I of slice 1
     sv2, f2 = conf.read_conf(p, ltrot, types)
     assert np.array_equal(sv2, sv) and np.array_equal(f2, f)
+
+
+def test_latt_local_bin_layout_and_roundtrip(tmp_path):
+    """`_local` / `_localtau` records (Prog/observables_mod.F90:700-717): header, then per unit cell its real-space position
+    followed by Ntau*Norb values; no Fourier transform, no background line."""
+    from alf_b200.bins import print_bin_latt_local, read_latt_local, read_latt_info
+    from alf_b200.model import Lattice
+    latt = Lattice(4, 2); nchains, nmeas = 3, 7
+    rng = np.random.default_rng(5)
+    for ntau, suffix, ncol in ((1, "_local", 3), (4, "_localtau", 5)):
+        x = rng.standard_normal((ntau, 2, latt.N)) + 1j * rng.standard_normal((ntau, 2, latt.N))
+        p = None
+        for k in range(2):
+            p = print_bin_latt_local(str(tmp_path / "SpinZ"), x * nchains * nmeas * (k + 1), 0.5 * nchains * nmeas, nmeas, nchains, latt,
+                                     dtau=0.1, orb_pos=[[0, 0], [0.5, 0.5]])
+        assert p.endswith("SpinZ" + suffix)
+        rows = open(p).read().split("\n")
+        assert len(rows[0].split()) == ncol and len(rows[0]) == 25 + (ncol - 1 if ntau == 1 else 3) * 11 + (0 if ntau == 1 else 26)
+        assert len(rows[1]) == 25 + 1 + 25 and rows[2].startswith("(") and len(rows[2]) == 2 * 25 + 3
+        assert len(rows) - 1 == 2 * (1 + latt.N * (1 + ntau * 2))
+        sign, obs, xr = read_latt_local(p)
+        assert np.allclose(sign, 0.5) and obs.shape == (2, ntau, 2, latt.N)
+        assert np.allclose(obs[0], x, rtol=1e-15, atol=0) and np.allclose(obs[1], 2 * x, rtol=1e-15, atol=0)
+        assert np.array_equal(xr, np.asarray(latt.list, dtype=float))
+        info = read_latt_info(p)
+        assert info[1] == ntau and info[9] == 2 and info[10][1, 0] == 0.5
