@@ -456,7 +456,7 @@ struct Engine : EngineBase {
   LaWork<T> w;
   cplx* d_z = nullptr; double* d_angle = nullptr; double* d_angle_tab = nullptr; double* d_cmp = nullptr;
   VopDev<T>* d_vops = nullptr; T* d_place_tab = nullptr; int* d_place_pk = nullptr; unsigned char* d_is_cont = nullptr; ModelDev md; FieldTabDev ft;
-  ModelFixDev mf; bool fix_any = false; int fix_max_ops = 0;      // resident-descriptor form of the bond-operator lists (k_apply_ops_fixed)
+  ModelFixDev mf; bool fix_any = false; int fix_max_ops = 0, fix_max_ring = 0, fix_nmax = 8;      // resident-descriptor form of the bond-operator lists (k_apply_ops_fixed)
   std::vector<void*> owned;     // device allocations of the op lists
   bool dense_t = false; T* d_dense[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // fwd, inv, c, half, halfinv (N*N*F each)
   int KD = 16; size_t upd_smem = 0; int ops_lk = 0; size_t ops_smem = 0;   // ops_lk = log2 of the largest small-operator dimension
@@ -503,22 +503,91 @@ struct Engine : EngineBase {
   // Resident-descriptor form of a fixed list of k = 2 bond operators (k_apply_ops_fixed): families = maximal runs of consecutive operators with
   // pairwise disjoint supports, one 32-bit word per operator.
   FixListDev upload_fixed(const ListBuild& lb) {
-    FixListDev d = {0, 0, nullptr, nullptr, nullptr, nullptr};
+    FixListDev d; std::memset(&d, 0, sizeof(d));
     if (lb.nvar != 1 || lb.k.empty() || N * OPS_PW > 65535 + OPS_PW || getenv("ALF_B200_NO_FIXED_OPS")) return d;
     for (int kk : lb.k) if (kk != 2) return d;
     const int n = (int)lb.k.size();
     std::vector<int> fs = lb.levels(N, 1 << 30);
-    std::vector<unsigned> offs(n); std::vector<T> m((size_t)n * 4); std::vector<unsigned char> uni(fs.size() - 1, 1);
+    const int nfam = (int)fs.size() - 1;
+    std::vector<unsigned> offs(n); std::vector<T> m((size_t)n * 4); std::vector<unsigned char> uni(nfam, 1);
+    auto P0 = [&](int o) { return lb.P[(size_t)o * ALF_KMAX]; };
+    auto P1 = [&](int o) { return lb.P[(size_t)o * ALF_KMAX + 1]; };
+    auto A = [&](int o, int a, int b) { return lb.mat[(size_t)o * ALF_KMAX * ALF_KMAX + a + (size_t)b * ALF_KMAX]; };
     for (int o = 0; o < n; ++o) {
-      offs[o] = (unsigned)(lb.P[(size_t)o * ALF_KMAX] * OPS_PW) | ((unsigned)(lb.P[(size_t)o * ALF_KMAX + 1] * OPS_PW) << 16);
-      const cd* a = &lb.mat[(size_t)o * ALF_KMAX * ALF_KMAX];
-      m[4 * o] = to_T<T>(a[0]); m[4 * o + 1] = to_T<T>(a[1]); m[4 * o + 2] = to_T<T>(a[ALF_KMAX]); m[4 * o + 3] = to_T<T>(a[ALF_KMAX + 1]);
+      offs[o] = (unsigned)(P0(o) * OPS_PW) | ((unsigned)(P1(o) * OPS_PW) << 16);
+      m[4 * o] = to_T<T>(A(o, 0, 0)); m[4 * o + 1] = to_T<T>(A(o, 1, 0)); m[4 * o + 2] = to_T<T>(A(o, 0, 1)); m[4 * o + 3] = to_T<T>(A(o, 1, 1));
     }
-    for (size_t c = 0; c + 1 < fs.size(); ++c) for (int o = fs[c]; o < fs[c + 1]; ++o) for (int e = 0; e < 4; ++e) {
-      const cd x = lb.mat[(size_t)o * ALF_KMAX * ALF_KMAX + (e & 1) + (size_t)(e >> 1) * ALF_KMAX], y = lb.mat[(size_t)fs[c] * ALF_KMAX * ALF_KMAX + (e & 1) + (size_t)(e >> 1) * ALF_KMAX];
-      if (x != y) uni[c] = 0; }
-    d.n_fam = (int)fs.size() - 1; d.n_ops = n; d.fam_start = dupload(fs); d.offs = dupload(offs); d.mat = dupload(m); d.uniform = dupload(uni);
-    fix_any = true; fix_max_ops = std::max(fix_max_ops, n);
+    for (int c = 0; c < nfam; ++c) for (int o = fs[c]; o < fs[c + 1]; ++o) for (int e = 0; e < 4; ++e)
+      if (A(o, e & 1, e >> 1) != A(fs[c], e & 1, e >> 1)) uni[c] = 0;
+    // ---- ring groups (alf_ops.cuh): consecutive families over two perfect matchings A, B of the same sites whose union consists of rings of one length <= 32
+    std::vector<FixGroupDev> grp; std::vector<FixFamDev> rfam(nfam, FixFamDev{0, 0, 0, 0}); std::vector<unsigned short> ring; std::vector<T> rmat;
+    const bool rings_on = !getenv("ALF_B200_NO_RING_OPS");
+    auto partner_of = [&](int c, std::vector<int>& part, std::vector<int>& opi) {      // part[site] = partner in family c (or -1), opi[site] = its operator
+      part.assign(N, -1); opi.assign(N, -1);
+      for (int o = fs[c]; o < fs[c + 1]; ++o) { part[P0(o)] = P1(o); part[P1(o)] = P0(o); opi[P0(o)] = o; opi[P1(o)] = o; }
+    };
+    int c = 0;
+    while (c < nfam) {
+      FixGroupDev g = {0, c, 1, 0, 0, 0, 0, 0};
+      std::vector<int> pa, oa, pb, ob, pc, oc;
+      bool ok = rings_on && c + 1 < nfam;
+      if (ok) {
+        partner_of(c, pa, oa); partner_of(c + 1, pb, ob);
+        for (int i = 0; i < N && ok; ++i) if ((pa[i] < 0) != (pb[i] < 0)) ok = false;                 // same support
+        if (ok && pa == pb) ok = false;
+      }
+      std::vector<std::vector<int>> rings;
+      if (ok) {
+        std::vector<char> seen(N, 0);
+        for (int s0 = 0; s0 < N && ok; ++s0) {
+          if (pa[s0] < 0 || seen[s0]) continue;
+          std::vector<int> r; int cur = s0;
+          while (true) {
+            r.push_back(cur); seen[cur] = 1; const int nx = pa[cur]; r.push_back(nx); seen[nx] = 1;
+            cur = pb[nx]; if (cur == s0) break;
+            if (seen[cur] || (int)r.size() > 32) { ok = false; break; }
+          }
+          if (ok && (int)r.size() > 32) ok = false;
+          if (ok && !rings.empty() && r.size() != rings[0].size()) ok = false;
+          if (ok) rings.push_back(r);
+        }
+      }
+      if (ok) {
+        const int rn = (int)rings[0].size(), nmax = rn <= 8 ? 8 : rn <= 16 ? 16 : 32;
+        if (sizeof(T) > 8 && nmax > 16 && !getenv("ALF_B200_CPLX_RING32")) ok = false;       // complex: at most 16 ring values in registers by default
+        if (ok) {
+          // which of the following families reuse the two matchings
+          int c2 = c;
+          std::vector<int> types;
+          while (c2 < nfam) { partner_of(c2, pc, oc); if (pc == pa) types.push_back(0); else if (pc == pb) types.push_back(1); else break; ++c2; }
+          g.kind = 1; g.nfam = c2 - c; g.n = rn; g.nrings = (int)rings.size(); g.nmax = nmax; g.ring_off = (int)ring.size(); g.cover = (rn * g.nrings == N) ? 1 : 0;
+          for (auto& r : rings) for (int i = 0; i < OPS_RSTR; ++i) ring.push_back((unsigned short)(i < rn ? r[i] * OPS_PW : 0));
+          for (int fi = 0; fi < g.nfam; ++fi) {
+            const int cf = c + fi; partner_of(cf, pc, oc);
+            std::vector<T> mm((size_t)g.nrings * (OPS_RSTR / 2) * 4, zero_<T>());
+            bool u = true; cd first[4] = {cd(0, 0), cd(0, 0), cd(0, 0), cd(0, 0)}; bool have = false;
+            for (int rg = 0; rg < g.nrings; ++rg) for (int i = 0; i < rn / 2; ++i) {
+              const int sa = types[fi] == 0 ? rings[rg][2 * i] : rings[rg][2 * i + 1], sb = types[fi] == 0 ? rings[rg][2 * i + 1] : rings[rg][(2 * i + 2) % rn];
+              const int o = oc[sa];
+              cd e4[4];                                              // a00, a10, a01, a11 in the orientation (sa, sb)
+              if (P0(o) == sa && P1(o) == sb) { e4[0] = A(o, 0, 0); e4[1] = A(o, 1, 0); e4[2] = A(o, 0, 1); e4[3] = A(o, 1, 1); }
+              else { e4[0] = A(o, 1, 1); e4[1] = A(o, 0, 1); e4[2] = A(o, 1, 0); e4[3] = A(o, 0, 0); }
+              for (int e = 0; e < 4; ++e) { mm[((size_t)rg * (OPS_RSTR / 2) + i) * 4 + e] = to_T<T>(e4[e]); if (have && e4[e] != first[e]) u = false; }
+              if (!have) { for (int e = 0; e < 4; ++e) first[e] = e4[e]; have = true; }
+            }
+            rfam[cf].type = types[fi]; rfam[cf].uniform = u ? 1 : 0; rfam[cf].mat_off = (int)rmat.size();
+            if (u) for (int e = 0; e < 4; ++e) rmat.push_back(to_T<T>(first[e])); else rmat.insert(rmat.end(), mm.begin(), mm.end());
+          }
+          c = c2;
+        }
+      }
+      if (!ok) { g.kind = 0; g.nfam = 1; c += 1; }
+      grp.push_back(g);
+    }
+    while (ring.size() % 8) ring.push_back(0);
+    d.n_fam = nfam; d.n_ops = n; d.fam_start = dupload(fs); d.offs = dupload(offs); d.mat = dupload(m); d.uniform = dupload(uni);
+    d.n_grp = (int)grp.size(); d.n_ring = (int)ring.size(); d.grp = dupload(grp); d.rfam = dupload(rfam); d.ring = dupload(ring); d.rmat = dupload(rmat);
+    fix_any = true; fix_max_ops = std::max(fix_max_ops, n); fix_max_ring = std::max(fix_max_ring, (int)ring.size()); for (auto& gg : grp) if (gg.kind == 1) fix_nmax = std::max(fix_nmax, gg.nmax);
     return d;
   }
   // vertex list usable as a row scaling: only k = 1 (diagonal) factors, every site at most once
@@ -526,6 +595,11 @@ struct Engine : EngineBase {
     std::vector<char> seen(N, 0);
     for (size_t o = 0; o < lb.k.size(); ++o) { if (lb.k[o] != 1) return 0; const int p = lb.P[o * ALF_KMAX]; if (seen[p]) return 0; seen[p] = 1; }
     return 1;
+  }
+  const int* upload_vsite(const ListBuild& lb) {           // operator index acting on site i (diagonal lists), or -1
+    std::vector<int> v(N, -1);
+    if (diag_list_ok(lb)) for (size_t o = 0; o < lb.k.size(); ++o) v[lb.P[o * ALF_KMAX]] = (int)o;
+    return dupload(v);
   }
   bool fixed_mode_ok(int mode) const {
     if (!fix_any) return false;
@@ -661,8 +735,12 @@ struct Engine : EngineBase {
                             CK(alf_raise_smem(k_apply_ops<T, 1, LKV>)); } while (0)
     if (ops_lk == 0) OPS_ATTR(0); else if (ops_lk == 1) OPS_ATTR(1); else OPS_ATTR(2);
 #undef OPS_ATTR
-    if (fix_any && ops_fixed_smem(sizeof(T), N, fix_max_ops) > 227 * 1024) fix_any = false;
-    if (fix_any) { CK(alf_raise_smem(k_apply_ops_fixed<T, 0>)); CK(alf_raise_smem(k_apply_ops_fixed<T, 1>)); }
+    if (fix_any && ops_fixed_smem(sizeof(T), N, fix_max_ops, fix_max_ring) > 227 * 1024) fix_any = false;
+    if (fix_any) {
+      if (fix_nmax <= 8) { CK(alf_raise_smem(k_apply_ops_fixed<T, 0, 8>)); CK(alf_raise_smem(k_apply_ops_fixed<T, 1, 8>)); }
+      else if (fix_nmax <= 16) { CK(alf_raise_smem(k_apply_ops_fixed<T, 0, 16>)); CK(alf_raise_smem(k_apply_ops_fixed<T, 1, 16>)); }
+      else { CK(alf_raise_smem(k_apply_ops_fixed<T, 0, 32>)); CK(alf_raise_smem(k_apply_ops_fixed<T, 1, 32>)); }
+    }
   }
   ~Engine() { for (void* p : owned) cudaFree(p); w.release(); if (proj) wp.release(); if (w2_ready) w2.release(); }
   // Optional (ALF_B200_L2_PERSIST=1): persisting-L2 access window over the batch of Green functions.  Measured on B200 with
@@ -775,6 +853,7 @@ struct Engine : EngineBase {
         vc.add(op.N, op.P.data(), n, mc); }
       md.lists[L_VL_N][f] = upload_list(vn); md.lists[L_VL_C][f] = upload_list(vc); md.lists[L_VR_INV][f] = upload_list(vri);
       mf.diag_ok[L_VL_N][f] = diag_list_ok(vn); mf.diag_ok[L_VL_C][f] = diag_list_ok(vc); mf.diag_ok[L_VR_INV][f] = diag_list_ok(vri);
+      mf.vsite[L_VL_N][f] = upload_vsite(vn); mf.vsite[L_VL_C][f] = upload_vsite(vc); mf.vsite[L_VR_INV][f] = upload_vsite(vri);
     }
     d_vops = dupload(vops); d_angle_tab = dupload(angle_tab); md.fields_c = h->d_fields_c;
     { std::vector<unsigned char> tc(M); for (int n = 0; n < M; ++n) tc[n] = h->opv[n].type == 3 ? 1 : 0; d_is_cont = dupload(tc); }
@@ -809,9 +888,11 @@ struct Engine : EngineBase {
     const ModelDev& md = mdo ? *mdo : this->md;
     dim3 grid((nvec + OPS_PW - 1) / OPS_PW, NM);
     if (!mdo && fixed_mode_ok(mode)) {             // bond-operator hopping list (+ diagonal vertices): resident-descriptor kernel
-      const size_t sm = ops_fixed_smem(sizeof(T), N, fix_max_ops);
-      if (side == 0) KL(KC_OPS, st, k_apply_ops_fixed<T, 0><<<grid, OPS_NT, sm, st>>>(Mx, n2, N, nvec, md, mf, F, mode, nt_a, nt_b, h->d_fields, L, M, Mout));
-      else KL(KC_OPS, st, k_apply_ops_fixed<T, 1><<<grid, OPS_NT, sm, st>>>(Mx, n2, N, nvec, md, mf, F, mode, nt_a, nt_b, h->d_fields, L, M, Mout));
+      const size_t sm = ops_fixed_smem(sizeof(T), N, fix_max_ops, fix_max_ring);
+#define OPSF_LAUNCH(SD, NMX) KL(KC_OPS, st, k_apply_ops_fixed<T, SD, NMX><<<grid, OPS_NT, sm, st>>>(Mx, n2, N, nvec, md, mf, F, mode, nt_a, nt_b, h->d_fields, L, M, Mout))
+      if (side == 0) { if (fix_nmax <= 8) OPSF_LAUNCH(0, 8); else if (fix_nmax <= 16) OPSF_LAUNCH(0, 16); else OPSF_LAUNCH(0, 32); }
+      else { if (fix_nmax <= 8) OPSF_LAUNCH(1, 8); else if (fix_nmax <= 16) OPSF_LAUNCH(1, 16); else OPSF_LAUNCH(1, 32); }
+#undef OPSF_LAUNCH
       CKL(); return;
     }
 #define OPS_LAUNCH(SD, LKV) KL(KC_OPS, st, k_apply_ops<T, SD, LKV><<<grid, OPS_NT, ops_smem, st>>>(Mx, n2, N, nvec, md, F, mode, nt_a, nt_b, h->d_fields, L, M, Mout))

@@ -253,31 +253,117 @@ __global__ void __launch_bounds__(OPS_NT) k_apply_ops(T* M, long sM, int N, int 
 // (checkerboard decomposition) and its vertex list, if any, of diagonal single-site factors (every Hubbard variant).
 // k_apply_ops is instruction bound (ncu: 55 % issue-slot utilisation; about 45 % of its instructions are the per-chunk descriptor
 // pipeline that resolves field-dependent matrices).  Here the descriptors of the WHOLE hopping list are resident in shared memory
-// in their final form (one 32-bit word per operator: the two panel-row offsets), a family (= level of pairwise disjoint operators)
-// is processed between two barriers without any chunking, the 2 x 2 matrix of a translation-invariant family sits in registers,
-// and e^{V(s)} of a slice is a row scaling built once per slice from the field values.
+// in their final form, and e^{V(s)} of a slice is a row scaling built once per slice from the field values.
+//
+// RING GROUPS.  A checkerboard family is a perfect matching of the sites; the union of two matchings A, B decomposes into even
+// rings r_0 r_1 ... r_{n-1} whose bonds alternate: A = (r_2i, r_2i+1), B = (r_2i+1, r_2i+2 mod n) (square lattice, ALF's families:
+// staircases of 2 L sites).  Consecutive families that use only these two matchings (1 2 | 3 4 3 | 2 1 of the symmetric Trotter
+// order) form a GROUP: one thread takes one ring of one panel lane into registers (n <= 32 values), applies every family of the
+// group as register rotations and stores the ring: one shared-memory pass per group instead of one per family (7 -> 3 passes per
+// e^{-dtau T}), and the diagonal vertices of a slice are fused into the first / last pass of the slice as a scaling on load / store.
+// Families that do not pair up (ring too long, different supports) keep the one-pass-per-family form (kind 0).
 // ------------------------------------------------------------------------------------------------------------------------
+struct FixFamDev { int type, uniform, mat_off, pad; };    // type 0: bonds (r_2i, r_2i+1), 1: (r_2i+1, r_2i+2 mod n); mat_off into rmat: 4 entries (uniform) or nrings * 16 * 4
+struct FixGroupDev { int kind, fam0, nfam, n, nrings, nmax, ring_off, cover; };   // kind 1: ring group; ring_off: first entry of its table in `ring`; cover: the rings contain every row
 struct FixListDev {
   int n_fam, n_ops;                 // n_fam = 0: the list has no fixed form
   const int* fam_start;             // n_fam + 1
   const unsigned* offs;             // n_ops: (P0 * 32) | (P1 * 32) << 16   (panel-row offsets, 16 bits each)
   const void* mat;                  // n_ops * 4 entries of T: a00, a10, a01, a11
   const unsigned char* uniform;     // n_fam: all operators of the family carry the same matrix
+  int n_grp, n_ring;                // groups of consecutive families; n_ring entries of the ring tables
+  const FixGroupDev* grp;           // n_grp
+  const FixFamDev* rfam;            // n_fam (meaningful for the families of ring groups)
+  const unsigned short* ring;       // ring tables: per ring group nrings * 32 panel-row offsets (row * 32), padded with 0
+  const void* rmat;                 // matrices of the ring groups in ring orientation
 };
 struct ModelFixDev {
   FixListDev fix[L_COUNT][ALF_FMAX];
   unsigned char diag_ok[L_COUNT][ALF_FMAX];   // vertex lists: only k = 1 factors, every site at most once
+  const int* vsite[L_COUNT][ALF_FMAX];        // vertex lists with diag_ok: operator index acting on site i, or -1
 };
-static inline size_t ops_fixed_smem(size_t sizeof_T, int N, int max_ops) { return sizeof_T * ((size_t)N * OPS_PW + N) + sizeof(unsigned) * (size_t)(max_ops + 4) + 16; }
+static inline size_t ops_fixed_smem(size_t sizeof_T, int N, int max_ops, int max_ring) {
+  return sizeof_T * ((size_t)N * OPS_PW + N) + sizeof(unsigned) * (size_t)(max_ops + 4) + sizeof(unsigned short) * (size_t)(max_ring + 8) + 32;
+}
 
-template <typename T, int SIDE>
-__global__ void __launch_bounds__(OPS_NT) k_apply_ops_fixed(T* M, long sM, int N, int nvec, ModelDev md, ModelFixDev mf, int F, int mode, int nt_a, int nt_b,
+__device__ __forceinline__ void ops_cp_async(double* smem_dst, const double* gsrc) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"(sa), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void ops_cp_async(cplx* smem_dst, const cplx* gsrc) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(sa), "l"(gsrc) : "memory");
+}
+#define OPS_RSTR 32          // stride of the ring tables (entries per ring, padded)
+// One ring group on the staged panel: warp = ring, lane = panel lane.  NMAX = compile-time bound of the ring length (registers).
+template <typename T, int NMAX>
+__device__ __forceinline__ void ops_ring_pass(T* __restrict__ S, const unsigned short* __restrict__ rt, const FixGroupDev g, const FixFamDev* __restrict__ rfam,
+                                              const T* __restrict__ rmat, const T* __restrict__ pre, const T* __restrict__ post) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const int n = g.n;
+  for (int ring = warp; ring < g.nrings; ring += nw) {
+    const uint4* ro4 = reinterpret_cast<const uint4*>(rt + (long)ring * OPS_RSTR);
+    unsigned wq[NMAX / 2];           // two 16-bit panel-row offsets per word
+#pragma unroll
+    for (int q = 0; q < NMAX / 8; ++q) { const uint4 w = ro4[q]; wq[4 * q] = w.x; wq[4 * q + 1] = w.y; wq[4 * q + 2] = w.z; wq[4 * q + 3] = w.w; }
+#define ALF_RO(i) (((i) & 1) ? (int)(wq[(i) >> 1] >> 16) : (int)(wq[(i) >> 1] & 0xffffu))
+    T r[NMAX];
+#pragma unroll
+    for (int i = 0; i < NMAX; ++i) if (i < n) r[i] = S[ops_sw(ALF_RO(i), lane)];
+    if (pre) {
+#pragma unroll
+      for (int i = 0; i < NMAX; ++i) if (i < n) r[i] = pre[ALF_RO(i) >> 5] * r[i];
+    }
+    for (int fi = 0; fi < g.nfam; ++fi) {
+      const FixFamDev fd = rfam[g.fam0 + fi];
+      const T* m = rmat + fd.mat_off;
+      if (fd.uniform) {
+        const T a00 = m[0], a10 = m[1], a01 = m[2], a11 = m[3];
+#define ALF_ROT(x, y) { const T t0_ = a00 * (x) + a01 * (y); (y) = a10 * (x) + a11 * (y); (x) = t0_; }
+        if (fd.type == 0) {
+#pragma unroll
+          for (int i = 0; i < NMAX / 2; ++i) if (2 * i + 1 < n) ALF_ROT(r[2 * i], r[2 * i + 1])
+        } else {
+#pragma unroll
+          for (int i = 0; i < NMAX / 2; ++i) {
+            if (2 * i + 2 < n) { if (2 * i + 2 < NMAX) ALF_ROT(r[2 * i + 1], r[(2 * i + 2) % NMAX]) }
+            else if (2 * i + 2 == n) ALF_ROT(r[2 * i + 1], r[0])
+          }
+        }
+#undef ALF_ROT
+      } else {
+        m += (long)ring * (OPS_RSTR / 2) * 4;
+#define ALF_ROT(x, y, i) { const T a00 = m[4 * (i)], a10 = m[4 * (i) + 1], a01 = m[4 * (i) + 2], a11 = m[4 * (i) + 3]; const T t0_ = a00 * (x) + a01 * (y); (y) = a10 * (x) + a11 * (y); (x) = t0_; }
+        if (fd.type == 0) {
+#pragma unroll
+          for (int i = 0; i < NMAX / 2; ++i) if (2 * i + 1 < n) ALF_ROT(r[2 * i], r[2 * i + 1], i)
+        } else {
+#pragma unroll
+          for (int i = 0; i < NMAX / 2; ++i) {
+            if (2 * i + 2 < n) { if (2 * i + 2 < NMAX) ALF_ROT(r[2 * i + 1], r[(2 * i + 2) % NMAX], i) }
+            else if (2 * i + 2 == n) ALF_ROT(r[2 * i + 1], r[0], i)
+          }
+        }
+#undef ALF_ROT
+      }
+    }
+    if (post) {
+#pragma unroll
+      for (int i = 0; i < NMAX; ++i) if (i < n) r[i] = post[ALF_RO(i) >> 5] * r[i];
+    }
+#pragma unroll
+    for (int i = 0; i < NMAX; ++i) if (i < n) S[ops_sw(ALF_RO(i), lane)] = r[i];
+#undef ALF_RO
+  }
+}
+
+template <typename T, int SIDE, int NMAX>
+__global__ void __launch_bounds__(OPS_NT, (sizeof(T) == 8 && NMAX <= 16) ? 3 : sizeof(T) * NMAX <= 256 ? 2 : 1) k_apply_ops_fixed(T* M, long sM, int N, int nvec, ModelDev md, ModelFixDev mf, int F, int mode, int nt_a, int nt_b,
                                                             const int8_t* __restrict__ fields, int Ltrot, int n_opv, T* Mout) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int ldp = OPS_PW;
   T* S = reinterpret_cast<T*>(smem_raw);
   T* dsc = S + (long)N * ldp;
-  unsigned* offs = reinterpret_cast<unsigned*>(dsc + N);
   const int b = blockIdx.y, chain = b / F, f = b % F;
   M += (long)b * sM; Mout += (long)b * sM;
   const int v0 = blockIdx.x * OPS_PW, pw = min(OPS_PW, nvec - v0);
@@ -296,67 +382,94 @@ __global__ void __launch_bounds__(OPS_NT) k_apply_ops_fixed(T* M, long sM, int N
     case MODE_PROPRM1: li0 = L_TR_INV; li1 = L_VR_INV; uf1 = 1; break;
   }
   const FixListDev FL = mf.fix[uf0 ? li1 : li0][f];          // the program's hopping list (exactly one per mode)
+  unsigned* offs = reinterpret_cast<unsigned*>(dsc + N);
+  unsigned short* rtab = reinterpret_cast<unsigned short*>(smem_raw + ((reinterpret_cast<unsigned char*>(offs + FL.n_ops) - smem_raw + 15) & ~(size_t)15));
   for (int e = tid; e < FL.n_ops; e += blockDim.x) offs[e] = FL.offs[e];
+  for (int e = tid; e < FL.n_ring; e += blockDim.x) rtab[e] = FL.ring[e];
   // ---- stage the panel (coalesced global reads; the XOR-swizzled rows keep the transposing writes conflict free)
+  // LDGSTS: the whole panel is requested at once (no register staging, so every thread has all of its 8- / 16-byte copies in flight:
+  // with plain loads the kernel was bound by the latency of a few dependent load -> store rounds per thread, ncu: 1.7 TB/s of DRAM traffic)
   if (SIDE == 0) {
-    for (int j = warp; j < pw; j += nw) { const T* col = M + (long)(v0 + j) * N; for (int i = lane; i < N; i += 32) S[ops_sw(i * ldp, j)] = col[i]; }
+    for (int j = warp; j < pw; j += nw) { const T* col = M + (long)(v0 + j) * N; for (int i = lane; i < N; i += 32) ops_cp_async(&S[ops_sw(i * ldp, j)], col + i); }
   } else {
-    if (lane < pw) { const T* src = M + v0 + lane; for (int i = warp; i < N; i += nw) S[ops_sw(i * ldp, lane)] = src[(long)i * N]; }
+    if (lane < pw) { const T* src = M + v0 + lane; for (int i = warp; i < N; i += nw) ops_cp_async(&S[ops_sw(i * ldp, lane)], src + (long)i * N); }
   }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
   __syncthreads();
   const bool lane_ok = lane < pw;
   const T* mats = reinterpret_cast<const T*>(FL.mat);
-  const int ns = (uf0 || uf1) ? (nt_b - nt_a + 1) : 1;
+  const T* rmat = reinterpret_cast<const T*>(FL.rmat);
+  const bool has_v = uf0 || uf1;
+  const int ns = has_v ? (nt_b - nt_a + 1) : 1;
+  const int lv = uf0 ? li0 : li1;                              // the vertex list, if any
+  // the scaling is fused into the first (V before T) / last (T before V) group if that group's rings contain every row
+  const bool fuse = has_v && FL.n_grp > 0 && FL.grp[uf0 ? 0 : FL.n_grp - 1].kind == 1 && FL.grp[uf0 ? 0 : FL.n_grp - 1].cover;
   for (int sl = 0; sl < ns; ++sl) {
     const int nt = (dir > 0) ? nt_a + sl : nt_b - sl;
-    for (int part = 0; part < 2; ++part) {
-      const int li = part ? li1 : li0; if (li < 0) continue;
-      if (!(part ? uf1 : uf0)) {
-        for (int fa = 0; fa < FL.n_fam; ++fa) {
-          const int o0 = FL.fam_start[fa], o1 = FL.fam_start[fa + 1];
-          if (FL.uniform[fa]) {
-            const T a00 = mats[4 * o0], a10 = mats[4 * o0 + 1], a01 = mats[4 * o0 + 2], a11 = mats[4 * o0 + 3];
-            for (int o = o0 + warp; o < o1; o += 2 * nw) {
-              const bool two = o + nw < o1;
-              const unsigned d0 = offs[o], d1 = offs[two ? o + nw : o];
-              if (lane_ok) {
-                const int p0 = ops_sw(d0 & 0xffff, lane), p1 = ops_sw(d0 >> 16, lane), q0 = ops_sw(d1 & 0xffff, lane), q1 = ops_sw(d1 >> 16, lane);
-                const T x0 = S[p0], x1 = S[p1], y0 = S[q0], y1 = S[q1];
-                S[p0] = a00 * x0 + a01 * x1; S[p1] = a10 * x0 + a11 * x1;
-                if (two) { S[q0] = a00 * y0 + a01 * y1; S[q1] = a10 * y0 + a11 * y1; }
-              }
-            }
-          } else {
-            for (int o = o0 + warp; o < o1; o += nw) {
-              const unsigned d0 = offs[o];
-              const T a00 = mats[4 * o], a10 = mats[4 * o + 1], a01 = mats[4 * o + 2], a11 = mats[4 * o + 3];
-              if (lane_ok) {
-                const int p0 = ops_sw(d0 & 0xffff, lane), p1 = ops_sw(d0 >> 16, lane);
-                const T x0 = S[p0], x1 = S[p1];
-                S[p0] = a00 * x0 + a01 * x1; S[p1] = a10 * x0 + a11 * x1;
-              }
-            }
-          }
-          __syncthreads();
-        }
-      } else {
-        // diagonal vertices of slice nt: row scaling d(P_n) = exp(+-g phi(s_n) E_n) (tabulated per field value; continuous fields on the fly)
-        const OpListDev& L = md.lists[li][f];
-        const T* vm = reinterpret_cast<const T*>(L.mat);
-        const int8_t* fl = fields + ((long)chain * Ltrot + (nt - 1)) * n_opv;
-        const double* fc = md.fields_c ? md.fields_c + ((long)chain * Ltrot + (nt - 1)) * n_opv : nullptr;
-        for (int i = tid; i < N; i += blockDim.x) dsc[i] = one_<T>();
-        __syncthreads();
-        for (int o = tid; o < L.n_ops; o += blockDim.x) {
-          const int n = L.fidx[o]; T v;
+    if (has_v) {
+      // diagonal vertices of slice nt: row scaling d(P_n) = exp(+-g phi(s_n) E_n) (tabulated per field value; continuous fields on the fly)
+      const OpListDev& L = md.lists[lv][f];
+      const T* vm = reinterpret_cast<const T*>(L.mat);
+      const int* vsite = mf.vsite[lv][f];
+      const int8_t* fl = fields + ((long)chain * Ltrot + (nt - 1)) * n_opv;
+      const double* fc = md.fields_c ? md.fields_c + ((long)chain * Ltrot + (nt - 1)) * n_opv : nullptr;
+      for (int i = tid; i < N; i += blockDim.x) {
+        const int o = vsite[i]; T v = one_<T>();
+        if (o >= 0) {
+          const int n = L.fidx[o];
           if (fc && L.cont[o]) v = exp_(vm[((long)o * L.nvar) * (ALF_KMAX * ALF_KMAX)] * fc[n]);
           else v = vm[((long)o * L.nvar + (int)fl[n] + 2) * (ALF_KMAX * ALF_KMAX)];
-          dsc[L.P[(long)o * ALF_KMAX]] = v;
         }
-        __syncthreads();
+        dsc[i] = v;
+      }
+      __syncthreads();
+      if (uf0 && !fuse) {
         if (lane_ok) for (int i = warp; i < N; i += nw) { const int e = ops_sw(i * ldp, lane); S[e] = dsc[i] * S[e]; }
         __syncthreads();
       }
+    }
+    for (int gi = 0; gi < FL.n_grp; ++gi) {
+      const FixGroupDev g = FL.grp[gi];
+      if (g.kind == 1) {
+        const T* pre = (uf0 && fuse && gi == 0) ? dsc : nullptr;
+        const T* post = (uf1 && fuse && gi == FL.n_grp - 1) ? dsc : nullptr;
+        const unsigned short* rt = rtab + g.ring_off;
+        ops_ring_pass<T, NMAX>(S, rt, g, FL.rfam, rmat, pre, post);
+        __syncthreads();
+        continue;
+      }
+      for (int fa = g.fam0; fa < g.fam0 + g.nfam; ++fa) {
+        const int o0 = FL.fam_start[fa], o1 = FL.fam_start[fa + 1];
+        if (FL.uniform[fa]) {
+          const T a00 = mats[4 * o0], a10 = mats[4 * o0 + 1], a01 = mats[4 * o0 + 2], a11 = mats[4 * o0 + 3];
+          for (int o = o0 + warp; o < o1; o += 2 * nw) {
+            const bool two = o + nw < o1;
+            const unsigned d0 = offs[o], d1 = offs[two ? o + nw : o];
+            if (lane_ok) {
+              const int p0 = ops_sw(d0 & 0xffff, lane), p1 = ops_sw(d0 >> 16, lane), q0 = ops_sw(d1 & 0xffff, lane), q1 = ops_sw(d1 >> 16, lane);
+              const T x0 = S[p0], x1 = S[p1], y0 = S[q0], y1 = S[q1];
+              S[p0] = a00 * x0 + a01 * x1; S[p1] = a10 * x0 + a11 * x1;
+              if (two) { S[q0] = a00 * y0 + a01 * y1; S[q1] = a10 * y0 + a11 * y1; }
+            }
+          }
+        } else {
+          for (int o = o0 + warp; o < o1; o += nw) {
+            const unsigned d0 = offs[o];
+            const T a00 = mats[4 * o], a10 = mats[4 * o + 1], a01 = mats[4 * o + 2], a11 = mats[4 * o + 3];
+            if (lane_ok) {
+              const int p0 = ops_sw(d0 & 0xffff, lane), p1 = ops_sw(d0 >> 16, lane);
+              const T x0 = S[p0], x1 = S[p1];
+              S[p0] = a00 * x0 + a01 * x1; S[p1] = a10 * x0 + a11 * x1;
+            }
+          }
+        }
+        __syncthreads();
+      }
+    }
+    if (uf1 && !fuse) {
+      if (lane_ok) for (int i = warp; i < N; i += nw) { const int e = ops_sw(i * ldp, lane); S[e] = dsc[i] * S[e]; }
+      __syncthreads();
     }
   }
   // ---- write back
