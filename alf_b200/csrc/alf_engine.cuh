@@ -456,7 +456,7 @@ struct Engine : EngineBase {
   LaWork<T> w;
   cplx* d_z = nullptr; double* d_angle = nullptr; double* d_angle_tab = nullptr; double* d_cmp = nullptr;
   VopDev<T>* d_vops = nullptr; T* d_place_tab = nullptr; int* d_place_pk = nullptr; unsigned char* d_is_cont = nullptr; ModelDev md; FieldTabDev ft;
-  ModelFixDev mf; bool fix_any = false; int fix_max_ops = 0, fix_max_ring = 0, fix_nmax = 8;      // resident-descriptor form of the bond-operator lists (k_apply_ops_fixed)
+  ModelFixDev mf; bool fix_any = false; int fix_max_blob = 0, fix_nmax = 8, fix_nbuf = 1, fix_nt = 256, fix_grid = 148; size_t fix_smem = 0;      // resident-descriptor form of the bond-operator lists (k_apply_ops_fixed)
   std::vector<void*> owned;     // device allocations of the op lists
   bool dense_t = false; T* d_dense[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // fwd, inv, c, half, halfinv (N*N*F each)
   int KD = 16; size_t upd_smem = 0; int ops_lk = 0; size_t ops_smem = 0;   // ops_lk = log2 of the largest small-operator dimension
@@ -584,10 +584,20 @@ struct Engine : EngineBase {
       if (!ok) { g.kind = 0; g.nfam = 1; c += 1; }
       grp.push_back(g);
     }
-    while (ring.size() % 8) ring.push_back(0);
-    d.n_fam = nfam; d.n_ops = n; d.fam_start = dupload(fs); d.offs = dupload(offs); d.mat = dupload(m); d.uniform = dupload(uni);
-    d.n_grp = (int)grp.size(); d.n_ring = (int)ring.size(); d.grp = dupload(grp); d.rfam = dupload(rfam); d.ring = dupload(ring); d.rmat = dupload(rmat);
-    fix_any = true; fix_max_ops = std::max(fix_max_ops, n); fix_max_ring = std::max(fix_max_ring, (int)ring.size()); for (auto& gg : grp) if (gg.kind == 1) fix_nmax = std::max(fix_nmax, gg.nmax);
+    // ---- one blob per list (copied to shared memory by every CTA)
+    std::vector<unsigned char> blob;
+    auto put = [&](const void* src, size_t bytes) { while (blob.size() % 16) blob.push_back(0); const int off = (int)blob.size(); const unsigned char* q = (const unsigned char*)src; blob.insert(blob.end(), q, q + bytes); return off; };
+    bool any_plain = false; for (auto& gg : grp) if (gg.kind == 0) any_plain = true;
+    std::vector<T> m4((size_t)nfam * 4); for (int c2 = 0; c2 < nfam; ++c2) for (int e = 0; e < 4; ++e) m4[(size_t)c2 * 4 + e] = m[(size_t)fs[c2] * 4 + e];
+    if (rmat.empty()) rmat.push_back(zero_<T>());
+    if (ring.empty()) ring.resize(8, 0);
+    d.o_grp = put(grp.data(), grp.size() * sizeof(FixGroupDev)); d.o_rfam = put(rfam.data(), rfam.size() * sizeof(FixFamDev));
+    d.o_rmat = put(rmat.data(), rmat.size() * sizeof(T)); d.o_ring = put(ring.data(), ring.size() * sizeof(unsigned short));
+    d.o_offs = put(offs.data(), any_plain ? offs.size() * sizeof(unsigned) : 4); d.o_fs = put(fs.data(), fs.size() * sizeof(int));
+    d.o_uni = put(uni.data(), uni.size()); d.o_m4 = put(m4.data(), m4.size() * sizeof(T));
+    while (blob.size() % 16) blob.push_back(0);
+    d.n_fam = nfam; d.n_ops = n; d.n_grp = (int)grp.size(); d.blob_bytes = (int)blob.size(); d.blob = dupload(blob); d.mat = dupload(m);
+    fix_any = true; fix_max_blob = std::max(fix_max_blob, (int)blob.size()); for (auto& gg : grp) if (gg.kind == 1) fix_nmax = std::max(fix_nmax, gg.nmax);
     return d;
   }
   // vertex list usable as a row scaling: only k = 1 (diagonal) factors, every site at most once
@@ -596,10 +606,14 @@ struct Engine : EngineBase {
     for (size_t o = 0; o < lb.k.size(); ++o) { if (lb.k[o] != 1) return 0; const int p = lb.P[o * ALF_KMAX]; if (seen[p]) return 0; seen[p] = 1; }
     return 1;
   }
-  const int* upload_vsite(const ListBuild& lb) {           // operator index acting on site i (diagonal lists), or -1
-    std::vector<int> v(N, -1);
-    if (diag_list_ok(lb)) for (size_t o = 0; o < lb.k.size(); ++o) v[lb.P[o * ALF_KMAX]] = (int)o;
-    return dupload(v);
+  VDiagDev upload_vdiag(const ListBuild& lb) {             // diagonal vertex list by site (k_apply_ops_fixed)
+    std::vector<T> tab((size_t)N * ALF_NVAR, one_<T>()); std::vector<int> fi(N, -1); std::vector<unsigned char> ct(N, 0);
+    if (diag_list_ok(lb) && lb.nvar == ALF_NVAR) for (size_t o = 0; o < lb.k.size(); ++o) {
+      const int p = lb.P[o * ALF_KMAX]; fi[p] = lb.fidx[o]; ct[p] = lb.cont[o];
+      for (int var = 0; var < ALF_NVAR; ++var) tab[(size_t)p * ALF_NVAR + var] = to_T<T>(lb.mat[(o * ALF_NVAR + var) * ALF_KMAX * ALF_KMAX]);
+    }
+    VDiagDev v; v.tab = dupload(tab); v.fidx = dupload(fi); v.cont = dupload(ct);
+    return v;
   }
   bool fixed_mode_ok(int mode) const {
     if (!fix_any) return false;
@@ -735,11 +749,19 @@ struct Engine : EngineBase {
                             CK(alf_raise_smem(k_apply_ops<T, 1, LKV>)); } while (0)
     if (ops_lk == 0) OPS_ATTR(0); else if (ops_lk == 1) OPS_ATTR(1); else OPS_ATTR(2);
 #undef OPS_ATTR
-    if (fix_any && ops_fixed_smem(sizeof(T), N, fix_max_ops, fix_max_ring) > 227 * 1024) fix_any = false;
+    if (fix_any) {      // persistent resident-descriptor kernel: two panel buffers if they fit, CTAs per SM from the occupancy calculator
+      fix_nbuf = ops_fixed_smem2(sizeof(T), N, fix_max_blob, F, 2) <= 227 * 1024 ? 2 : 1;
+      fix_smem = ops_fixed_smem2(sizeof(T), N, fix_max_blob, F, fix_nbuf);
+      fix_nt = (N >= 192 && fix_nmax <= 16 && sizeof(T) == 8) ? OPSF_NT : 256;      // rings of 32 values (and complex ones) need more than 128 registers per thread
+      if (fix_smem > 227 * 1024) fix_any = false;
+    }
     if (fix_any) {
-      if (fix_nmax <= 8) { CK(alf_raise_smem(k_apply_ops_fixed<T, 0, 8>)); CK(alf_raise_smem(k_apply_ops_fixed<T, 1, 8>)); }
-      else if (fix_nmax <= 16) { CK(alf_raise_smem(k_apply_ops_fixed<T, 0, 16>)); CK(alf_raise_smem(k_apply_ops_fixed<T, 1, 16>)); }
-      else { CK(alf_raise_smem(k_apply_ops_fixed<T, 0, 32>)); CK(alf_raise_smem(k_apply_ops_fixed<T, 1, 32>)); }
+      int dev = 0, nsm = 148, occ = 1; CK(cudaGetDevice(&dev)); CK(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
+#define OPSF_ATTR(NMX) do { CK(alf_raise_smem(k_apply_ops_fixed<T, 0, NMX>)); CK(alf_raise_smem(k_apply_ops_fixed<T, 1, NMX>)); \
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_apply_ops_fixed<T, 0, NMX>, fix_nt, fix_smem)); } while (0)
+      if (fix_nmax <= 8) OPSF_ATTR(8); else if (fix_nmax <= 16) OPSF_ATTR(16); else OPSF_ATTR(32);
+#undef OPSF_ATTR
+      fix_grid = nsm * std::max(occ, 1);
     }
   }
   ~Engine() { for (void* p : owned) cudaFree(p); w.release(); if (proj) wp.release(); if (w2_ready) w2.release(); }
@@ -853,7 +875,7 @@ struct Engine : EngineBase {
         vc.add(op.N, op.P.data(), n, mc); }
       md.lists[L_VL_N][f] = upload_list(vn); md.lists[L_VL_C][f] = upload_list(vc); md.lists[L_VR_INV][f] = upload_list(vri);
       mf.diag_ok[L_VL_N][f] = diag_list_ok(vn); mf.diag_ok[L_VL_C][f] = diag_list_ok(vc); mf.diag_ok[L_VR_INV][f] = diag_list_ok(vri);
-      mf.vsite[L_VL_N][f] = upload_vsite(vn); mf.vsite[L_VL_C][f] = upload_vsite(vc); mf.vsite[L_VR_INV][f] = upload_vsite(vri);
+      mf.vd[L_VL_N][f] = upload_vdiag(vn); mf.vd[L_VL_C][f] = upload_vdiag(vc); mf.vd[L_VR_INV][f] = upload_vdiag(vri);
     }
     d_vops = dupload(vops); d_angle_tab = dupload(angle_tab); md.fields_c = h->d_fields_c;
     { std::vector<unsigned char> tc(M); for (int n = 0; n < M; ++n) tc[n] = h->opv[n].type == 3 ? 1 : 0; d_is_cont = dupload(tc); }
@@ -888,8 +910,8 @@ struct Engine : EngineBase {
     const ModelDev& md = mdo ? *mdo : this->md;
     dim3 grid((nvec + OPS_PW - 1) / OPS_PW, NM);
     if (!mdo && fixed_mode_ok(mode)) {             // bond-operator hopping list (+ diagonal vertices): resident-descriptor kernel
-      const size_t sm = ops_fixed_smem(sizeof(T), N, fix_max_ops, fix_max_ring);
-#define OPSF_LAUNCH(SD, NMX) KL(KC_OPS, st, k_apply_ops_fixed<T, SD, NMX><<<grid, OPS_NT, sm, st>>>(Mx, n2, N, nvec, md, mf, F, mode, nt_a, nt_b, h->d_fields, L, M, Mout))
+      const int npan = (nvec + OPS_PW - 1) / OPS_PW, total = npan * NM, gridp = std::min(total, fix_grid), bstride = (fix_max_blob + 15) & ~15;
+#define OPSF_LAUNCH(SD, NMX) KL(KC_OPS, st, k_apply_ops_fixed<T, SD, NMX><<<gridp, fix_nt, fix_smem, st>>>(Mx, n2, N, nvec, md, mf, F, mode, nt_a, nt_b, h->d_fields, L, M, Mout, npan, total, fix_nbuf, bstride))
       if (side == 0) { if (fix_nmax <= 8) OPSF_LAUNCH(0, 8); else if (fix_nmax <= 16) OPSF_LAUNCH(0, 16); else OPSF_LAUNCH(0, 32); }
       else { if (fix_nmax <= 8) OPSF_LAUNCH(1, 8); else if (fix_nmax <= 16) OPSF_LAUNCH(1, 16); else OPSF_LAUNCH(1, 32); }
 #undef OPSF_LAUNCH

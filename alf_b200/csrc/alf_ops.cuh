@@ -265,26 +265,24 @@ __global__ void __launch_bounds__(OPS_NT) k_apply_ops(T* M, long sM, int N, int 
 // ------------------------------------------------------------------------------------------------------------------------
 struct FixFamDev { int type, uniform, mat_off, pad; };    // type 0: bonds (r_2i, r_2i+1), 1: (r_2i+1, r_2i+2 mod n); mat_off into rmat: 4 entries (uniform) or nrings * 16 * 4
 struct FixGroupDev { int kind, fam0, nfam, n, nrings, nmax, ring_off, cover; };   // kind 1: ring group; ring_off: first entry of its table in `ring`; cover: the rings contain every row
+// The descriptors of one list live in ONE blob that every CTA copies to shared memory together with its panel (cp.async), so the
+// family loop never waits for global memory (ncu on the first version: 30 % of the stall samples were dependent descriptor loads).
+// Sections (byte offsets, 16-byte aligned): groups, ring-family records, ring matrices, ring tables (panel-row offsets row * 32 as
+// 16-bit entries, OPS_RSTR per ring), and for the families outside ring groups: operator offsets (P0 * 32) | (P1 * 32) << 16,
+// family starts, uniform flags, one 2 x 2 matrix per family (a00, a10, a01, a11).
 struct FixListDev {
-  int n_fam, n_ops;                 // n_fam = 0: the list has no fixed form
-  const int* fam_start;             // n_fam + 1
-  const unsigned* offs;             // n_ops: (P0 * 32) | (P1 * 32) << 16   (panel-row offsets, 16 bits each)
-  const void* mat;                  // n_ops * 4 entries of T: a00, a10, a01, a11
-  const unsigned char* uniform;     // n_fam: all operators of the family carry the same matrix
-  int n_grp, n_ring;                // groups of consecutive families; n_ring entries of the ring tables
-  const FixGroupDev* grp;           // n_grp
-  const FixFamDev* rfam;            // n_fam (meaningful for the families of ring groups)
-  const unsigned short* ring;       // ring tables: per ring group nrings * 32 panel-row offsets (row * 32), padded with 0
-  const void* rmat;                 // matrices of the ring groups in ring orientation
+  int n_fam, n_ops, n_grp;          // n_fam = 0: the list has no fixed form
+  int blob_bytes, o_grp, o_rfam, o_rmat, o_ring, o_offs, o_fs, o_uni, o_m4;
+  const unsigned char* blob;
+  const void* mat;                  // global: n_ops * 4 entries of T (only read for families whose operators carry different matrices)
 };
+struct VDiagDev { const void* tab; const int* fidx; const unsigned char* cont; };   // diagonal vertex list by site: tab[i * 5 + s + 2] (continuous: slot 0 = coefficient), field index or -1
 struct ModelFixDev {
   FixListDev fix[L_COUNT][ALF_FMAX];
   unsigned char diag_ok[L_COUNT][ALF_FMAX];   // vertex lists: only k = 1 factors, every site at most once
-  const int* vsite[L_COUNT][ALF_FMAX];        // vertex lists with diag_ok: operator index acting on site i, or -1
+  VDiagDev vd[L_COUNT][ALF_FMAX];
 };
-static inline size_t ops_fixed_smem(size_t sizeof_T, int N, int max_ops, int max_ring) {
-  return sizeof_T * ((size_t)N * OPS_PW + N) + sizeof(unsigned) * (size_t)(max_ops + 4) + sizeof(unsigned short) * (size_t)(max_ring + 8) + 32;
-}
+static inline size_t ops_fixed_smem(size_t sizeof_T, int N, int max_blob) { return sizeof_T * ((size_t)N * OPS_PW + N) + (size_t)max_blob + 64; }
 
 __device__ __forceinline__ void ops_cp_async(double* smem_dst, const double* gsrc) {
   const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
@@ -294,80 +292,91 @@ __device__ __forceinline__ void ops_cp_async(cplx* smem_dst, const cplx* gsrc) {
   const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(sa), "l"(gsrc) : "memory");
 }
+__device__ __forceinline__ void ops_cp_async16(void* smem_dst, const void* gsrc) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" :: "r"(sa), "l"(gsrc) : "memory");
+}
 #define OPS_RSTR 32          // stride of the ring tables (entries per ring, padded)
-// One ring group on the staged panel: warp = ring, lane = panel lane.  NMAX = compile-time bound of the ring length (registers).
-template <typename T, int NMAX>
-__device__ __forceinline__ void ops_ring_pass(T* __restrict__ S, const unsigned short* __restrict__ rt, const FixGroupDev g, const FixFamDev* __restrict__ rfam,
-                                              const T* __restrict__ rmat, const T* __restrict__ pre, const T* __restrict__ post) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  const int n = g.n;
-  for (int ring = warp; ring < g.nrings; ring += nw) {
-    const uint4* ro4 = reinterpret_cast<const uint4*>(rt + (long)ring * OPS_RSTR);
-    unsigned wq[NMAX / 2];           // two 16-bit panel-row offsets per word
+
+// One ring of one panel lane: n values to registers, every family of the group as register rotations, back.  FULL: n == NMAX (no predicates).
+template <typename T, int NMAX, bool FULL>
+__device__ __forceinline__ void ops_ring_task(T* __restrict__ S, const unsigned short* __restrict__ ro, int ring, int n, int nfam, const FixFamDev* __restrict__ rfam,
+                                              const T* __restrict__ rmat, const T* __restrict__ pre, const T* __restrict__ post, int lane) {
+  const uint4* ro4 = reinterpret_cast<const uint4*>(ro);
+  unsigned wq[NMAX / 2];           // two 16-bit panel-row offsets per word
 #pragma unroll
-    for (int q = 0; q < NMAX / 8; ++q) { const uint4 w = ro4[q]; wq[4 * q] = w.x; wq[4 * q + 1] = w.y; wq[4 * q + 2] = w.z; wq[4 * q + 3] = w.w; }
+  for (int q = 0; q < NMAX / 8; ++q) { const uint4 w = ro4[q]; wq[4 * q] = w.x; wq[4 * q + 1] = w.y; wq[4 * q + 2] = w.z; wq[4 * q + 3] = w.w; }
 #define ALF_RO(i) (((i) & 1) ? (int)(wq[(i) >> 1] >> 16) : (int)(wq[(i) >> 1] & 0xffffu))
-    T r[NMAX];
+  constexpr bool KEEP = NMAX <= 8;          // element addresses stay in registers between load and store
+  T r[NMAX]; int ad[KEEP ? NMAX : 1];
 #pragma unroll
-    for (int i = 0; i < NMAX; ++i) if (i < n) r[i] = S[ops_sw(ALF_RO(i), lane)];
-    if (pre) {
+  for (int i = 0; i < NMAX; ++i) if (FULL || i < n) { const int a = ops_sw(ALF_RO(i), lane); if (KEEP) ad[i] = a; r[i] = S[a]; }
+  if (pre) {
 #pragma unroll
-      for (int i = 0; i < NMAX; ++i) if (i < n) r[i] = pre[ALF_RO(i) >> 5] * r[i];
-    }
-    for (int fi = 0; fi < g.nfam; ++fi) {
-      const FixFamDev fd = rfam[g.fam0 + fi];
-      const T* m = rmat + fd.mat_off;
-      if (fd.uniform) {
-        const T a00 = m[0], a10 = m[1], a01 = m[2], a11 = m[3];
-#define ALF_ROT(x, y) { const T t0_ = a00 * (x) + a01 * (y); (y) = a10 * (x) + a11 * (y); (x) = t0_; }
-        if (fd.type == 0) {
-#pragma unroll
-          for (int i = 0; i < NMAX / 2; ++i) if (2 * i + 1 < n) ALF_ROT(r[2 * i], r[2 * i + 1])
-        } else {
-#pragma unroll
-          for (int i = 0; i < NMAX / 2; ++i) {
-            if (2 * i + 2 < n) { if (2 * i + 2 < NMAX) ALF_ROT(r[2 * i + 1], r[(2 * i + 2) % NMAX]) }
-            else if (2 * i + 2 == n) ALF_ROT(r[2 * i + 1], r[0])
-          }
-        }
-#undef ALF_ROT
-      } else {
-        m += (long)ring * (OPS_RSTR / 2) * 4;
-#define ALF_ROT(x, y, i) { const T a00 = m[4 * (i)], a10 = m[4 * (i) + 1], a01 = m[4 * (i) + 2], a11 = m[4 * (i) + 3]; const T t0_ = a00 * (x) + a01 * (y); (y) = a10 * (x) + a11 * (y); (x) = t0_; }
-        if (fd.type == 0) {
-#pragma unroll
-          for (int i = 0; i < NMAX / 2; ++i) if (2 * i + 1 < n) ALF_ROT(r[2 * i], r[2 * i + 1], i)
-        } else {
-#pragma unroll
-          for (int i = 0; i < NMAX / 2; ++i) {
-            if (2 * i + 2 < n) { if (2 * i + 2 < NMAX) ALF_ROT(r[2 * i + 1], r[(2 * i + 2) % NMAX], i) }
-            else if (2 * i + 2 == n) ALF_ROT(r[2 * i + 1], r[0], i)
-          }
-        }
-#undef ALF_ROT
-      }
-    }
-    if (post) {
-#pragma unroll
-      for (int i = 0; i < NMAX; ++i) if (i < n) r[i] = post[ALF_RO(i) >> 5] * r[i];
-    }
-#pragma unroll
-    for (int i = 0; i < NMAX; ++i) if (i < n) S[ops_sw(ALF_RO(i), lane)] = r[i];
-#undef ALF_RO
+    for (int i = 0; i < NMAX; ++i) if (FULL || i < n) r[i] = pre[ALF_RO(i) >> 5] * r[i];
   }
+  for (int fi = 0; fi < nfam; ++fi) {
+    const FixFamDev fd = rfam[fi];
+    const T* m = rmat + fd.mat_off;
+    if (fd.uniform) {
+      const T a00 = m[0], a10 = m[1], a01 = m[2], a11 = m[3];
+#define ALF_ROT(x, y) { const T t0_ = a00 * (x) + a01 * (y); (y) = a10 * (x) + a11 * (y); (x) = t0_; }
+      if (fd.type == 0) {
+#pragma unroll
+        for (int i = 0; i < NMAX / 2; ++i) if (FULL || 2 * i + 1 < n) ALF_ROT(r[2 * i], r[2 * i + 1])
+      } else {
+#pragma unroll
+        for (int i = 0; i < NMAX / 2; ++i) {
+          if (2 * i + 2 < NMAX && (FULL || 2 * i + 2 < n)) ALF_ROT(r[2 * i + 1], r[(2 * i + 2) % NMAX])
+          else if (FULL ? (2 * i + 2 == NMAX) : (2 * i + 2 == n)) ALF_ROT(r[2 * i + 1], r[0])
+        }
+      }
+#undef ALF_ROT
+    } else {
+      m += (long)ring * (OPS_RSTR / 2) * 4;
+#define ALF_ROT(x, y, i) { const T a00 = m[4 * (i)], a10 = m[4 * (i) + 1], a01 = m[4 * (i) + 2], a11 = m[4 * (i) + 3]; const T t0_ = a00 * (x) + a01 * (y); (y) = a10 * (x) + a11 * (y); (x) = t0_; }
+      if (fd.type == 0) {
+#pragma unroll
+        for (int i = 0; i < NMAX / 2; ++i) if (FULL || 2 * i + 1 < n) ALF_ROT(r[2 * i], r[2 * i + 1], i)
+      } else {
+#pragma unroll
+        for (int i = 0; i < NMAX / 2; ++i) {
+          if (2 * i + 2 < NMAX && (FULL || 2 * i + 2 < n)) ALF_ROT(r[2 * i + 1], r[(2 * i + 2) % NMAX], i)
+          else if (FULL ? (2 * i + 2 == NMAX) : (2 * i + 2 == n)) ALF_ROT(r[2 * i + 1], r[0], i)
+        }
+      }
+#undef ALF_ROT
+    }
+  }
+  if (post) {
+#pragma unroll
+    for (int i = 0; i < NMAX; ++i) if (FULL || i < n) r[i] = post[ALF_RO(i) >> 5] * r[i];
+  }
+#pragma unroll
+  for (int i = 0; i < NMAX; ++i) if (FULL || i < n) S[KEEP ? ad[KEEP ? i : 0] : ops_sw(ALF_RO(i), lane)] = r[i];
+#undef ALF_RO
 }
 
+#define OPSF_NT 512          // threads of the persistent kernel at large N (one CTA per SM, 128 registers per thread)
+static inline size_t ops_fixed_smem2(size_t sizeof_T, int N, int max_blob, int F, int nbuf) {
+  return sizeof_T * ((size_t)N * OPS_PW * nbuf + N) + (size_t)(max_blob + 16) * F + 64;
+}
+
+// PERSISTENT form: the CTAs walk over the panels of the whole batch (panel q = blockIdx.x + k gridDim.x: matrix q / npan, panel q % npan);
+// with nbuf = 2 the panel of step k + 1 is in flight (cp.async) while the families run on panel k and panel k - 1 drains to HBM, so the
+// load -> compute -> store phases of the resident CTAs no longer run in lockstep (ncu on the one-panel-per-CTA form: 2 TB/s of DRAM
+// traffic, shared-memory pipe 43 % busy, i.e. neither resource saturated).  The descriptor blobs of all flavors are staged once per CTA.
 template <typename T, int SIDE, int NMAX>
-__global__ void __launch_bounds__(OPS_NT, (sizeof(T) == 8 && NMAX <= 16) ? 3 : sizeof(T) * NMAX <= 256 ? 2 : 1) k_apply_ops_fixed(T* M, long sM, int N, int nvec, ModelDev md, ModelFixDev mf, int F, int mode, int nt_a, int nt_b,
-                                                            const int8_t* __restrict__ fields, int Ltrot, int n_opv, T* Mout) {
+__global__ void __launch_bounds__((NMAX > 16 || sizeof(T) > 8) ? 256 : OPSF_NT, 1) k_apply_ops_fixed(
+    T* M, long sM, int N, int nvec, ModelDev md, ModelFixDev mf, int F, int mode, int nt_a, int nt_b, const int8_t* __restrict__ fields, int Ltrot, int n_opv, T* Mout,
+    int npan, int total, int nbuf, int blob_stride) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int ldp = OPS_PW;
-  T* S = reinterpret_cast<T*>(smem_raw);
-  T* dsc = S + (long)N * ldp;
-  const int b = blockIdx.y, chain = b / F, f = b % F;
-  M += (long)b * sM; Mout += (long)b * sM;
-  const int v0 = blockIdx.x * OPS_PW, pw = min(OPS_PW, nvec - v0);
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+  T* Sb = reinterpret_cast<T*>(smem_raw);
+  T* dsc = Sb + (long)N * ldp * nbuf;
+  unsigned char* blob0 = reinterpret_cast<unsigned char*>(dsc + N);
+  blob0 = smem_raw + (((size_t)(blob0 - smem_raw) + 15) & ~(size_t)15);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5, nthr = blockDim.x;
   int li0 = 0, li1 = -1, uf0 = 0, uf1 = 0, dir = 1;
   switch (mode) {
     case MODE_WRAPUR: li0 = L_TL_FWD; li1 = L_VL_N; uf1 = 1; break;
@@ -381,101 +390,131 @@ __global__ void __launch_bounds__(OPS_NT, (sizeof(T) == 8 && NMAX <= 16) ? 3 : s
     case MODE_TR_HALFINV: li0 = L_TR_HALFINV; break;
     case MODE_PROPRM1: li0 = L_TR_INV; li1 = L_VR_INV; uf1 = 1; break;
   }
-  const FixListDev FL = mf.fix[uf0 ? li1 : li0][f];          // the program's hopping list (exactly one per mode)
-  unsigned* offs = reinterpret_cast<unsigned*>(dsc + N);
-  unsigned short* rtab = reinterpret_cast<unsigned short*>(smem_raw + ((reinterpret_cast<unsigned char*>(offs + FL.n_ops) - smem_raw + 15) & ~(size_t)15));
-  for (int e = tid; e < FL.n_ops; e += blockDim.x) offs[e] = FL.offs[e];
-  for (int e = tid; e < FL.n_ring; e += blockDim.x) rtab[e] = FL.ring[e];
-  // ---- stage the panel (coalesced global reads; the XOR-swizzled rows keep the transposing writes conflict free)
-  // LDGSTS: the whole panel is requested at once (no register staging, so every thread has all of its 8- / 16-byte copies in flight:
-  // with plain loads the kernel was bound by the latency of a few dependent load -> store rounds per thread, ncu: 1.7 TB/s of DRAM traffic)
-  if (SIDE == 0) {
-    for (int j = warp; j < pw; j += nw) { const T* col = M + (long)(v0 + j) * N; for (int i = lane; i < N; i += 32) ops_cp_async(&S[ops_sw(i * ldp, j)], col + i); }
-  } else {
-    if (lane < pw) { const T* src = M + v0 + lane; for (int i = warp; i < N; i += nw) ops_cp_async(&S[ops_sw(i * ldp, lane)], src + (long)i * N); }
-  }
-  asm volatile("cp.async.commit_group;" ::: "memory");
-  asm volatile("cp.async.wait_group 0;" ::: "memory");
-  __syncthreads();
-  const bool lane_ok = lane < pw;
-  const T* mats = reinterpret_cast<const T*>(FL.mat);
-  const T* rmat = reinterpret_cast<const T*>(FL.rmat);
+  const int lt = uf0 ? li1 : li0;                              // the program's hopping list (exactly one per mode)
   const bool has_v = uf0 || uf1;
   const int ns = has_v ? (nt_b - nt_a + 1) : 1;
   const int lv = uf0 ? li0 : li1;                              // the vertex list, if any
-  // the scaling is fused into the first (V before T) / last (T before V) group if that group's rings contain every row
-  const bool fuse = has_v && FL.n_grp > 0 && FL.grp[uf0 ? 0 : FL.n_grp - 1].kind == 1 && FL.grp[uf0 ? 0 : FL.n_grp - 1].cover;
-  for (int sl = 0; sl < ns; ++sl) {
-    const int nt = (dir > 0) ? nt_a + sl : nt_b - sl;
+  // ---- panel q -> buffer: LDGSTS, every thread has all of its copies in flight; the XOR-swizzled rows keep the transposing writes of the
+  // left-multiplication panel conflict free
+  auto stage = [&](int q, T* S) {
+    const int b = q / npan, v0 = (q - b * npan) * OPS_PW, pw = min(OPS_PW, nvec - v0);
+    const T* Mb = M + (long)b * sM;
+    if (SIDE == 0) {
+      for (int j = warp; j < pw; j += nw) { const T* col = Mb + (long)(v0 + j) * N; for (int i = lane; i < N; i += 32) ops_cp_async(&S[ops_sw(i * ldp, j)], col + i); }
+    } else {
+      if (lane < pw) { const T* src = Mb + v0 + lane; for (int i = warp; i < N; i += nw) ops_cp_async(&S[ops_sw(i * ldp, lane)], src + (long)i * N); }
+    }
+  };
+  const int G = gridDim.x;
+  int q = blockIdx.x;
+  for (int f = 0; f < F; ++f) { const FixListDev& FLf = mf.fix[lt][f]; for (int e = tid * 16; e < FLf.blob_bytes; e += nthr * 16) ops_cp_async16(blob0 + (long)f * blob_stride + e, FLf.blob + e); }
+  if (q < total) stage(q, Sb);
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  if (nbuf == 2) { if (q + G < total) stage(q + G, Sb + (long)N * ldp); asm volatile("cp.async.commit_group;" ::: "memory"); }
+  for (int k = 0; q < total; q += G, ++k) {
+    T* S = Sb + ((nbuf == 2 && (k & 1)) ? (long)N * ldp : 0);
+    const int b = q / npan, chain = b / F, f = b - chain * F, v0 = (q - b * npan) * OPS_PW, pw = min(OPS_PW, nvec - v0);
+    const FixListDev& FL = mf.fix[lt][f];
+    const unsigned char* blob = blob0 + (long)f * blob_stride;
+    // diagonal vertices: thread i owns site i (+ blockDim.x, ...): the field value of the NEXT slice of the thread's first site is fetched one slice ahead
+    const VDiagDev VD = mf.vd[has_v ? lv : 0][f];
+    const T* vtab = reinterpret_cast<const T*>(VD.tab);
+    const int8_t* flc = fields + (long)chain * Ltrot * n_opv;
+    const double* fcc = md.fields_c ? md.fields_c + (long)chain * Ltrot * n_opv : nullptr;
+    int vn0 = -1; int8_t fnext = 0;
     if (has_v) {
-      // diagonal vertices of slice nt: row scaling d(P_n) = exp(+-g phi(s_n) E_n) (tabulated per field value; continuous fields on the fly)
-      const OpListDev& L = md.lists[lv][f];
-      const T* vm = reinterpret_cast<const T*>(L.mat);
-      const int* vsite = mf.vsite[lv][f];
-      const int8_t* fl = fields + ((long)chain * Ltrot + (nt - 1)) * n_opv;
-      const double* fc = md.fields_c ? md.fields_c + ((long)chain * Ltrot + (nt - 1)) * n_opv : nullptr;
-      for (int i = tid; i < N; i += blockDim.x) {
-        const int o = vsite[i]; T v = one_<T>();
-        if (o >= 0) {
-          const int n = L.fidx[o];
-          if (fc && L.cont[o]) v = exp_(vm[((long)o * L.nvar) * (ALF_KMAX * ALF_KMAX)] * fc[n]);
-          else v = vm[((long)o * L.nvar + (int)fl[n] + 2) * (ALF_KMAX * ALF_KMAX)];
+      if (tid < N) vn0 = VD.fidx[tid];
+      if (vn0 >= 0) fnext = flc[(long)((dir > 0 ? nt_a : nt_b) - 1) * n_opv + vn0];
+    }
+    if (nbuf == 2) asm volatile("cp.async.wait_group 1;" ::: "memory"); else asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+    const FixGroupDev* grp = reinterpret_cast<const FixGroupDev*>(blob + FL.o_grp);
+    const FixFamDev* rfam = reinterpret_cast<const FixFamDev*>(blob + FL.o_rfam);
+    const T* rmat = reinterpret_cast<const T*>(blob + FL.o_rmat);
+    const unsigned short* rtab = reinterpret_cast<const unsigned short*>(blob + FL.o_ring);
+    const unsigned* offs = reinterpret_cast<const unsigned*>(blob + FL.o_offs);
+    const int* fam_start = reinterpret_cast<const int*>(blob + FL.o_fs);
+    const unsigned char* funi = blob + FL.o_uni;
+    const T* fm4 = reinterpret_cast<const T*>(blob + FL.o_m4);
+    const bool lane_ok = lane < pw;
+    const T* mats = reinterpret_cast<const T*>(FL.mat);
+    const int n_grp = FL.n_grp;
+    // the scaling is fused into the first (V before T) / last (T before V) group if that group's rings contain every row
+    const bool fuse = has_v && n_grp > 0 && grp[uf0 ? 0 : n_grp - 1].kind == 1 && grp[uf0 ? 0 : n_grp - 1].cover;
+    for (int sl = 0; sl < ns; ++sl) {
+      const int nt = (dir > 0) ? nt_a + sl : nt_b - sl;
+      if (has_v) {
+        // diagonal vertices of slice nt: row scaling d(P_n) = exp(+-g phi(s_n) E_n) (tabulated per field value; continuous fields on the fly)
+        for (int i = tid; i < N; i += nthr) {
+          const int n = (i == tid) ? vn0 : VD.fidx[i];
+          T v = one_<T>();
+          if (n >= 0) {
+            if (fcc && VD.cont[i]) v = exp_(vtab[(long)i * ALF_NVAR] * fcc[(long)(nt - 1) * n_opv + n]);
+            else v = vtab[(long)i * ALF_NVAR + (int)((i == tid) ? fnext : flc[(long)(nt - 1) * n_opv + n]) + 2];
+          }
+          dsc[i] = v;
         }
-        dsc[i] = v;
+        if (sl + 1 < ns && vn0 >= 0) fnext = flc[(long)(((dir > 0) ? nt + 1 : nt - 1) - 1) * n_opv + vn0];
+        __syncthreads();
+        if (uf0 && !fuse) {
+          if (lane_ok) for (int i = warp; i < N; i += nw) { const int e = ops_sw(i * ldp, lane); S[e] = dsc[i] * S[e]; }
+          __syncthreads();
+        }
       }
-      __syncthreads();
-      if (uf0 && !fuse) {
+      for (int gi = 0; gi < n_grp; ++gi) {
+        const FixGroupDev g = grp[gi];
+        if (g.kind == 1) {
+          const T* pre = (uf0 && fuse && gi == 0) ? dsc : nullptr;
+          const T* post = (uf1 && fuse && gi == n_grp - 1) ? dsc : nullptr;
+          const unsigned short* rt = rtab + g.ring_off;
+          if (g.n == NMAX) { for (int ring = warp; ring < g.nrings; ring += nw) ops_ring_task<T, NMAX, true>(S, rt + ring * OPS_RSTR, ring, g.n, g.nfam, rfam + g.fam0, rmat, pre, post, lane); }
+          else { for (int ring = warp; ring < g.nrings; ring += nw) ops_ring_task<T, NMAX, false>(S, rt + ring * OPS_RSTR, ring, g.n, g.nfam, rfam + g.fam0, rmat, pre, post, lane); }
+          __syncthreads();
+          continue;
+        }
+        for (int fa = g.fam0; fa < g.fam0 + g.nfam; ++fa) {
+          const int o0 = fam_start[fa], o1 = fam_start[fa + 1];
+          if (funi[fa]) {
+            const T a00 = fm4[4 * fa], a10 = fm4[4 * fa + 1], a01 = fm4[4 * fa + 2], a11 = fm4[4 * fa + 3];
+            for (int o = o0 + warp; o < o1; o += 2 * nw) {
+              const bool two = o + nw < o1;
+              const unsigned d0 = offs[o], d1 = offs[two ? o + nw : o];
+              if (lane_ok) {
+                const int p0 = ops_sw(d0 & 0xffff, lane), p1 = ops_sw(d0 >> 16, lane), q0 = ops_sw(d1 & 0xffff, lane), q1 = ops_sw(d1 >> 16, lane);
+                const T x0 = S[p0], x1 = S[p1], y0 = S[q0], y1 = S[q1];
+                S[p0] = a00 * x0 + a01 * x1; S[p1] = a10 * x0 + a11 * x1;
+                if (two) { S[q0] = a00 * y0 + a01 * y1; S[q1] = a10 * y0 + a11 * y1; }
+              }
+            }
+          } else {
+            for (int o = o0 + warp; o < o1; o += nw) {
+              const unsigned d0 = offs[o];
+              const T a00 = mats[4 * o], a10 = mats[4 * o + 1], a01 = mats[4 * o + 2], a11 = mats[4 * o + 3];
+              if (lane_ok) {
+                const int p0 = ops_sw(d0 & 0xffff, lane), p1 = ops_sw(d0 >> 16, lane);
+                const T x0 = S[p0], x1 = S[p1];
+                S[p0] = a00 * x0 + a01 * x1; S[p1] = a10 * x0 + a11 * x1;
+              }
+            }
+          }
+          __syncthreads();
+        }
+      }
+      if (uf1 && !fuse) {
         if (lane_ok) for (int i = warp; i < N; i += nw) { const int e = ops_sw(i * ldp, lane); S[e] = dsc[i] * S[e]; }
         __syncthreads();
       }
     }
-    for (int gi = 0; gi < FL.n_grp; ++gi) {
-      const FixGroupDev g = FL.grp[gi];
-      if (g.kind == 1) {
-        const T* pre = (uf0 && fuse && gi == 0) ? dsc : nullptr;
-        const T* post = (uf1 && fuse && gi == FL.n_grp - 1) ? dsc : nullptr;
-        const unsigned short* rt = rtab + g.ring_off;
-        ops_ring_pass<T, NMAX>(S, rt, g, FL.rfam, rmat, pre, post);
-        __syncthreads();
-        continue;
-      }
-      for (int fa = g.fam0; fa < g.fam0 + g.nfam; ++fa) {
-        const int o0 = FL.fam_start[fa], o1 = FL.fam_start[fa + 1];
-        if (FL.uniform[fa]) {
-          const T a00 = mats[4 * o0], a10 = mats[4 * o0 + 1], a01 = mats[4 * o0 + 2], a11 = mats[4 * o0 + 3];
-          for (int o = o0 + warp; o < o1; o += 2 * nw) {
-            const bool two = o + nw < o1;
-            const unsigned d0 = offs[o], d1 = offs[two ? o + nw : o];
-            if (lane_ok) {
-              const int p0 = ops_sw(d0 & 0xffff, lane), p1 = ops_sw(d0 >> 16, lane), q0 = ops_sw(d1 & 0xffff, lane), q1 = ops_sw(d1 >> 16, lane);
-              const T x0 = S[p0], x1 = S[p1], y0 = S[q0], y1 = S[q1];
-              S[p0] = a00 * x0 + a01 * x1; S[p1] = a10 * x0 + a11 * x1;
-              if (two) { S[q0] = a00 * y0 + a01 * y1; S[q1] = a10 * y0 + a11 * y1; }
-            }
-          }
-        } else {
-          for (int o = o0 + warp; o < o1; o += nw) {
-            const unsigned d0 = offs[o];
-            const T a00 = mats[4 * o], a10 = mats[4 * o + 1], a01 = mats[4 * o + 2], a11 = mats[4 * o + 3];
-            if (lane_ok) {
-              const int p0 = ops_sw(d0 & 0xffff, lane), p1 = ops_sw(d0 >> 16, lane);
-              const T x0 = S[p0], x1 = S[p1];
-              S[p0] = a00 * x0 + a01 * x1; S[p1] = a10 * x0 + a11 * x1;
-            }
-          }
-        }
-        __syncthreads();
-      }
+    // ---- write back, then refill this buffer with the panel two steps ahead (one step ahead with a single buffer)
+    T* Mo = Mout + (long)b * sM;
+    if (SIDE == 0) {
+      for (int j = warp; j < pw; j += nw) { T* col = Mo + (long)(v0 + j) * N; for (int i = lane; i < N; i += 32) col[i] = S[ops_sw(i * ldp, j)]; }
+    } else {
+      if (lane < pw) { T* dst = Mo + v0 + lane; for (int i = warp; i < N; i += nw) dst[(long)i * N] = S[ops_sw(i * ldp, lane)]; }
     }
-    if (uf1 && !fuse) {
-      if (lane_ok) for (int i = warp; i < N; i += nw) { const int e = ops_sw(i * ldp, lane); S[e] = dsc[i] * S[e]; }
-      __syncthreads();
-    }
-  }
-  // ---- write back
-  if (SIDE == 0) {
-    for (int j = warp; j < pw; j += nw) { T* col = Mout + (long)(v0 + j) * N; for (int i = lane; i < N; i += 32) col[i] = S[ops_sw(i * ldp, j)]; }
-  } else {
-    if (lane < pw) { T* dst = Mout + v0 + lane; for (int i = warp; i < N; i += nw) dst[(long)i * N] = S[ops_sw(i * ldp, lane)]; }
+    __syncthreads();
+    const int qn = q + nbuf * G;
+    if (qn < total) stage(qn, S);
+    asm volatile("cp.async.commit_group;" ::: "memory");
   }
 }
