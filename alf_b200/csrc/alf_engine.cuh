@@ -520,7 +520,7 @@ struct Engine : EngineBase {
     for (int c = 0; c < nfam; ++c) for (int o = fs[c]; o < fs[c + 1]; ++o) for (int e = 0; e < 4; ++e)
       if (A(o, e & 1, e >> 1) != A(fs[c], e & 1, e >> 1)) uni[c] = 0;
     // ---- ring groups (alf_ops.cuh): consecutive families over two perfect matchings A, B of the same sites whose union consists of rings of one length <= 32
-    std::vector<FixGroupDev> grp; std::vector<FixFamDev> rfam(nfam, FixFamDev{0, 0, 0, 0}); std::vector<unsigned short> ring; std::vector<T> rmat;
+    std::vector<FixGroupDev> grp; std::vector<FixFamDev> rfam(nfam, FixFamDev{0, 0, 0, 0}); std::vector<unsigned> ring; std::vector<T> rmat;
     const bool rings_on = !getenv("ALF_B200_NO_RING_OPS");
     auto partner_of = [&](int c, std::vector<int>& part, std::vector<int>& opi) {      // part[site] = partner in family c (or -1), opi[site] = its operator
       part.assign(N, -1); opi.assign(N, -1);
@@ -561,7 +561,7 @@ struct Engine : EngineBase {
           std::vector<int> types;
           while (c2 < nfam) { partner_of(c2, pc, oc); if (pc == pa) types.push_back(0); else if (pc == pb) types.push_back(1); else break; ++c2; }
           g.kind = 1; g.nfam = c2 - c; g.n = rn; g.nrings = (int)rings.size(); g.nmax = nmax; g.ring_off = (int)ring.size(); g.cover = (rn * g.nrings == N) ? 1 : 0;
-          for (auto& r : rings) for (int i = 0; i < OPS_RSTR; ++i) ring.push_back((unsigned short)(i < rn ? r[i] * OPS_PW : 0));
+          for (auto& r : rings) for (int i = 0; i < OPS_RSTR; ++i) ring.push_back((unsigned)(i < rn ? r[i] * OPS_PW + (r[i] & 31) : 0));
           for (int fi = 0; fi < g.nfam; ++fi) {
             const int cf = c + fi; partner_of(cf, pc, oc);
             std::vector<T> mm((size_t)g.nrings * (OPS_RSTR / 2) * 4, zero_<T>());
@@ -592,7 +592,7 @@ struct Engine : EngineBase {
     if (rmat.empty()) rmat.push_back(zero_<T>());
     if (ring.empty()) ring.resize(8, 0);
     d.o_grp = put(grp.data(), grp.size() * sizeof(FixGroupDev)); d.o_rfam = put(rfam.data(), rfam.size() * sizeof(FixFamDev));
-    d.o_rmat = put(rmat.data(), rmat.size() * sizeof(T)); d.o_ring = put(ring.data(), ring.size() * sizeof(unsigned short));
+    d.o_rmat = put(rmat.data(), rmat.size() * sizeof(T)); d.o_ring = put(ring.data(), ring.size() * sizeof(unsigned));
     d.o_offs = put(offs.data(), any_plain ? offs.size() * sizeof(unsigned) : 4); d.o_fs = put(fs.data(), fs.size() * sizeof(int));
     d.o_uni = put(uni.data(), uni.size()); d.o_m4 = put(m4.data(), m4.size() * sizeof(T));
     while (blob.size() % 16) blob.push_back(0);

@@ -267,8 +267,8 @@ struct FixFamDev { int type, uniform, mat_off, pad; };    // type 0: bonds (r_2i
 struct FixGroupDev { int kind, fam0, nfam, n, nrings, nmax, ring_off, cover; };   // kind 1: ring group; ring_off: first entry of its table in `ring`; cover: the rings contain every row
 // The descriptors of one list live in ONE blob that every CTA copies to shared memory together with its panel (cp.async), so the
 // family loop never waits for global memory (ncu on the first version: 30 % of the stall samples were dependent descriptor loads).
-// Sections (byte offsets, 16-byte aligned): groups, ring-family records, ring matrices, ring tables (panel-row offsets row * 32 as
-// 16-bit entries, OPS_RSTR per ring), and for the families outside ring groups: operator offsets (P0 * 32) | (P1 * 32) << 16,
+// Sections (byte offsets, 16-byte aligned): groups, ring-family records, ring matrices, ring tables (32-bit entries row * 32 + (row & 31),
+// OPS_RSTR per ring), and for the families outside ring groups: operator offsets (P0 * 32) | (P1 * 32) << 16,
 // family starts, uniform flags, one 2 x 2 matrix per family (a00, a10, a01, a11).
 struct FixListDev {
   int n_fam, n_ops, n_grp;          // n_fam = 0: the list has no fixed form
@@ -299,21 +299,20 @@ __device__ __forceinline__ void ops_cp_async16(void* smem_dst, const void* gsrc)
 #define OPS_RSTR 32          // stride of the ring tables (entries per ring, padded)
 
 // One ring of one panel lane: n values to registers, every family of the group as register rotations, back.  FULL: n == NMAX (no predicates).
+// Ring table entry t = row * 32 + (row & 31): the element of panel lane l sits at S[t ^ l] (the XOR touches the low five bits only).
 template <typename T, int NMAX, bool FULL>
-__device__ __forceinline__ void ops_ring_task(T* __restrict__ S, const unsigned short* __restrict__ ro, int ring, int n, int nfam, const FixFamDev* __restrict__ rfam,
-                                              const T* __restrict__ rmat, const T* __restrict__ pre, const T* __restrict__ post, int lane) {
+__device__ __forceinline__ void ops_ring_task(T* __restrict__ S, const unsigned* __restrict__ ro, int ring, int n, int nfam, const FixFamDev* __restrict__ rfam,
+                                              const T* __restrict__ rmat, const T* __restrict__ pre, const T* __restrict__ post, unsigned lane) {
   const uint4* ro4 = reinterpret_cast<const uint4*>(ro);
-  unsigned wq[NMAX / 2];           // two 16-bit panel-row offsets per word
+  unsigned ad[NMAX];
 #pragma unroll
-  for (int q = 0; q < NMAX / 8; ++q) { const uint4 w = ro4[q]; wq[4 * q] = w.x; wq[4 * q + 1] = w.y; wq[4 * q + 2] = w.z; wq[4 * q + 3] = w.w; }
-#define ALF_RO(i) (((i) & 1) ? (int)(wq[(i) >> 1] >> 16) : (int)(wq[(i) >> 1] & 0xffffu))
-  constexpr bool KEEP = NMAX <= 8;          // element addresses stay in registers between load and store
-  T r[NMAX]; int ad[KEEP ? NMAX : 1];
+  for (int q = 0; q < NMAX / 4; ++q) { const uint4 w = ro4[q]; ad[4 * q] = w.x ^ lane; ad[4 * q + 1] = w.y ^ lane; ad[4 * q + 2] = w.z ^ lane; ad[4 * q + 3] = w.w ^ lane; }
+  T r[NMAX];
 #pragma unroll
-  for (int i = 0; i < NMAX; ++i) if (FULL || i < n) { const int a = ops_sw(ALF_RO(i), lane); if (KEEP) ad[i] = a; r[i] = S[a]; }
+  for (int i = 0; i < NMAX; ++i) if (FULL || i < n) r[i] = S[ad[i]];
   if (pre) {
 #pragma unroll
-    for (int i = 0; i < NMAX; ++i) if (FULL || i < n) r[i] = pre[ALF_RO(i) >> 5] * r[i];
+    for (int i = 0; i < NMAX; ++i) if (FULL || i < n) r[i] = pre[ad[i] >> 5] * r[i];
   }
   for (int fi = 0; fi < nfam; ++fi) {
     const FixFamDev fd = rfam[fi];
@@ -350,11 +349,10 @@ __device__ __forceinline__ void ops_ring_task(T* __restrict__ S, const unsigned 
   }
   if (post) {
 #pragma unroll
-    for (int i = 0; i < NMAX; ++i) if (FULL || i < n) r[i] = post[ALF_RO(i) >> 5] * r[i];
+    for (int i = 0; i < NMAX; ++i) if (FULL || i < n) r[i] = post[ad[i] >> 5] * r[i];
   }
 #pragma unroll
-  for (int i = 0; i < NMAX; ++i) if (FULL || i < n) S[KEEP ? ad[KEEP ? i : 0] : ops_sw(ALF_RO(i), lane)] = r[i];
-#undef ALF_RO
+  for (int i = 0; i < NMAX; ++i) if (FULL || i < n) S[ad[i]] = r[i];
 }
 
 #define OPSF_NT 512          // threads of the persistent kernel at large N (one CTA per SM, 128 registers per thread)
@@ -399,10 +397,13 @@ __global__ void __launch_bounds__((NMAX > 16 || sizeof(T) > 8) ? 256 : OPSF_NT, 
   auto stage = [&](int q, T* S) {
     const int b = q / npan, v0 = (q - b * npan) * OPS_PW, pw = min(OPS_PW, nvec - v0);
     const T* Mb = M + (long)b * sM;
-    if (SIDE == 0) {
-      for (int j = warp; j < pw; j += nw) { const T* col = Mb + (long)(v0 + j) * N; for (int i = lane; i < N; i += 32) ops_cp_async(&S[ops_sw(i * ldp, j)], col + i); }
+    if (SIDE == 0) {      // lane = row within a block of 32 rows: S[(l + 32 k) * 32 + (j ^ l)] = base + 1024 k
+      for (int j = warp; j < pw; j += nw) {
+        const T* col = Mb + (long)(v0 + j) * N + lane; T* sp = S + (lane * ldp + (j ^ lane));
+        for (int i = lane; i < N; i += 32, col += 32, sp += 32 * ldp) ops_cp_async(sp, col);
+      }
     } else {
-      if (lane < pw) { const T* src = Mb + v0 + lane; for (int i = warp; i < N; i += nw) ops_cp_async(&S[ops_sw(i * ldp, lane)], src + (long)i * N); }
+      if (lane < pw) { const T* src = Mb + v0 + lane + (long)warp * N; const long st = (long)nw * N; for (int i = warp; i < N; i += nw, src += st) ops_cp_async(&S[i * ldp + (lane ^ (i & 31))], src); }
     }
   };
   const int G = gridDim.x;
@@ -431,7 +432,7 @@ __global__ void __launch_bounds__((NMAX > 16 || sizeof(T) > 8) ? 256 : OPSF_NT, 
     const FixGroupDev* grp = reinterpret_cast<const FixGroupDev*>(blob + FL.o_grp);
     const FixFamDev* rfam = reinterpret_cast<const FixFamDev*>(blob + FL.o_rfam);
     const T* rmat = reinterpret_cast<const T*>(blob + FL.o_rmat);
-    const unsigned short* rtab = reinterpret_cast<const unsigned short*>(blob + FL.o_ring);
+    const unsigned* rtab = reinterpret_cast<const unsigned*>(blob + FL.o_ring);
     const unsigned* offs = reinterpret_cast<const unsigned*>(blob + FL.o_offs);
     const int* fam_start = reinterpret_cast<const int*>(blob + FL.o_fs);
     const unsigned char* funi = blob + FL.o_uni;
@@ -466,7 +467,7 @@ __global__ void __launch_bounds__((NMAX > 16 || sizeof(T) > 8) ? 256 : OPSF_NT, 
         if (g.kind == 1) {
           const T* pre = (uf0 && fuse && gi == 0) ? dsc : nullptr;
           const T* post = (uf1 && fuse && gi == n_grp - 1) ? dsc : nullptr;
-          const unsigned short* rt = rtab + g.ring_off;
+          const unsigned* rt = rtab + g.ring_off;
           if (g.n == NMAX) { for (int ring = warp; ring < g.nrings; ring += nw) ops_ring_task<T, NMAX, true>(S, rt + ring * OPS_RSTR, ring, g.n, g.nfam, rfam + g.fam0, rmat, pre, post, lane); }
           else { for (int ring = warp; ring < g.nrings; ring += nw) ops_ring_task<T, NMAX, false>(S, rt + ring * OPS_RSTR, ring, g.n, g.nfam, rfam + g.fam0, rmat, pre, post, lane); }
           __syncthreads();
@@ -508,9 +509,12 @@ __global__ void __launch_bounds__((NMAX > 16 || sizeof(T) > 8) ? 256 : OPSF_NT, 
     // ---- write back, then refill this buffer with the panel two steps ahead (one step ahead with a single buffer)
     T* Mo = Mout + (long)b * sM;
     if (SIDE == 0) {
-      for (int j = warp; j < pw; j += nw) { T* col = Mo + (long)(v0 + j) * N; for (int i = lane; i < N; i += 32) col[i] = S[ops_sw(i * ldp, j)]; }
+      for (int j = warp; j < pw; j += nw) {
+        T* col = Mo + (long)(v0 + j) * N + lane; const T* sp = S + (lane * ldp + (j ^ lane));
+        for (int i = lane; i < N; i += 32, col += 32, sp += 32 * ldp) *col = *sp;
+      }
     } else {
-      if (lane < pw) { T* dst = Mo + v0 + lane; for (int i = warp; i < N; i += nw) dst[(long)i * N] = S[ops_sw(i * ldp, lane)]; }
+      if (lane < pw) { T* dst = Mo + v0 + lane + (long)warp * N; const long st = (long)nw * N; for (int i = warp; i < N; i += nw, dst += st) *dst = S[i * ldp + (lane ^ (i & 31))]; }
     }
     __syncthreads();
     const int qn = q + nbuf * G;
