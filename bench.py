@@ -26,6 +26,11 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 METRIC = "sweeps/sec on 16x16 Hubbard beta=10"
+
+
+def metric_name(workload):
+    """BASELINE.json's metric for the default workload; the other configurations are named after themselves."""
+    return METRIC if workload == "hubbard_16x16_beta10" else "sweeps/sec on " + workload
 UNIT = "sweeps/s"
 WORKLOADS = {
     # name: (L1, L2, beta, dtau, U, nwrap, default chains per GPU)
@@ -176,7 +181,7 @@ def run_reference(args):
     tot = sum(times)
     value = cores * len(times) * (seg / nseg) / tot
     sample = _cpu_sample_text(seg, nseg, cores)
-    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+    line = {"impl": "reference", "metric": metric_name(args.workload), "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * tot / len(times), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "c128 (complex f64, as ALF)",
             "data": "synthetic", "config": {"workload": args.workload, "ltau": args.ltau, "chains": cores},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
@@ -380,7 +385,7 @@ def run_b200(args):
             times, seg, nseg, cpu_prec = cpu_sample(args.workload, args.ltau, cores, 30.0, 1, 0)
             cpu = {"value": cores * (seg / nseg) / times[0], "unit": UNIT, "cores": cores, "kind": "port", "sample": _cpu_sample_text(seg, nseg, cores)}
         nl = sum(v[1] for v in stats.values())
-        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+        line = {"metric": metric_name(args.workload), "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "c128" if g.is_complex else "f64", "data": "synthetic",
                 "config": {"workload": args.workload, "N_dim": N, "L_trot": L, "N_FL": F, "nwrap": nwrap, "ltau": args.ltau, "chains_per_gpu": H * C, "chains": world * H * C,
                            "handles_per_gpu": H, "chains_per_handle": C,
