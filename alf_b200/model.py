@@ -431,8 +431,10 @@ def kondo_square(L1: int, L2: int, beta: float, dtau: float = 0.1, t: float = 1.
     """SU(N) Kondo lattice on the bilayer square lattice, Hamiltonian_Kondo_smod.F90:464-530: orbital 1 = conduction
     (hops), orbital 2 = f (no hopping); vertices U_f (k=1, imaginary g: Predefined_Int_U_SUN, Ham_V :497-505) and
     J_K (k=2 vertex, Predefined_Int_V_SUN with Ham_JK/2 for N_SUN=2, :507-514).  The conduction-layer hopping uses the
-    square-lattice checkerboard families here (the reference's bilayer family split, Predefined_Hop_mod.F90:1005-1040,
-    groups the same bonds differently; the sweep path only sees a list of 2x2 bond operators either way)."""
+    checkerboard families of Set_Default_hopping_parameters_Bilayer_square for Ham_T2 = Ham_Tperp = 0
+    (Predefined_Hop_mod.F90:1126-1175): bond 1 = (0, 1), bond 2 = (1, 0) between conduction orbitals, families 1 / 2 = bonds 1 / 2 of
+    the unit cells with even i1 + i2, families 3 / 4 = those of the odd ones -- the same grouping and order as the square lattice
+    (:336-360), so _square_hopping_families serves both; Symmetrize_Families (:1422-1495) is applied on top of it."""
     latt = Lattice(L1, L2)
     Nc = latt.N
     Ndim = 2 * Nc                                  # Invlist(I,no) = (I-1)*Norb + no (Predefined_Latt_mod.F90:250-260)
