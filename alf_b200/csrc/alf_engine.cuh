@@ -425,7 +425,7 @@ template <typename T>
 __global__ void k_g0t_init(T* __restrict__ G0T, const T* __restrict__ G, long sM, int n) {
   const int b = blockIdx.y; G0T += (long)b * sM; G += (long)b * sM;
   for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < (long)n * n; e += (long)gridDim.x * blockDim.x) {
-    int i = (int)(e % n), j = (int)(e / n);
+    int j = (int)((unsigned)e / (unsigned)n), i = (int)((unsigned)e - (unsigned)j * (unsigned)n);
     G0T[e] = G[e] - ((i == j) ? one_<T>() : zero_<T>());
   }
 }
@@ -441,7 +441,7 @@ template <typename T>
 __global__ void k_axpb_identity(T* __restrict__ dst, const T* __restrict__ src, long sM, int n, double alpha, double beta) {
   const int b = blockIdx.y; dst += (long)b * sM; src += (long)b * sM;
   for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < (long)n * n; e += (long)gridDim.x * blockDim.x) {
-    const int i = (int)(e % n), j = (int)(e / n);
+    const int j = (int)((unsigned)e / (unsigned)n), i = (int)((unsigned)e - (unsigned)j * (unsigned)n);
     dst[e] = alpha * src[e] + ((i == j) ? make_<T>(beta, 0.0) : zero_<T>());
   }
 }

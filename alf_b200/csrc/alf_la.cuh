@@ -305,7 +305,7 @@ __device__ void qrp_device(T* __restrict__ A, int m, int n, int ld, T* __restric
   for (int i = tid; i < kmax; i += nthr) { double x = abs_(A[i + (long)i * ld]); D[i] = x; red_s[i] = x; }
   __syncthreads();
   for (long e = tid; e < (long)kmax * n; e += nthr) {
-    int i = (int)(e % kmax), c = (int)(e / kmax);
+    int c = (int)((unsigned)e / (unsigned)kmax), i = (int)((unsigned)e - (unsigned)c * (unsigned)kmax);
     if (c >= i) A[i + (long)c * ld] = A[i + (long)c * ld] * (1.0 / red_s[i]);
   }
   for (int c = tid; c < n; c += nthr) jpvt[c] = ipv_s[c];
@@ -341,10 +341,10 @@ __global__ void __launch_bounds__(512) k_qrp(T* __restrict__ A, int m, int n, in
   double* red_s = vn_s + n;
   int* ipv_s = reinterpret_cast<int*>(red_s + (n > 32 ? n : 32));
   if (STAGE) {
-    for (long e = threadIdx.x; e < (long)m * n; e += blockDim.x) { int i = (int)(e % m), c = (int)(e / m); As[i + (long)c * m] = A[i + (long)c * ld]; }
+    for (long e = threadIdx.x; e < (long)m * n; e += blockDim.x) { int c = (int)((unsigned)e / (unsigned)m), i = (int)((unsigned)e - (unsigned)c * (unsigned)m); As[i + (long)c * m] = A[i + (long)c * ld]; }
     __syncthreads();
     qrp_device<T, MAXR, PIVOT>(As, m, n, lds, tau, jpvt, D, out + b, v_s, vn_s, ipv_s, red_s);
-    for (long e = threadIdx.x; e < (long)m * n; e += blockDim.x) { int i = (int)(e % m), c = (int)(e / m); A[i + (long)c * ld] = As[i + (long)c * m]; }
+    for (long e = threadIdx.x; e < (long)m * n; e += blockDim.x) { int c = (int)((unsigned)e / (unsigned)m), i = (int)((unsigned)e - (unsigned)c * (unsigned)m); A[i + (long)c * ld] = As[i + (long)c * m]; }
   } else {
     qrp_device<T, MAXR, PIVOT>(A, m, n, ld, tau, jpvt, D, out + b, v_s, vn_s, ipv_s, red_s);
   }
@@ -463,7 +463,7 @@ __global__ void __launch_bounds__(512) k_formq(T* __restrict__ A, int m, int n, 
   T* W = A; int lw = ld;
   if (STAGE) {
     W = p; lw = m; p += (long)m * n;
-    for (long e = tid; e < (long)m * n; e += nthr) { int i = (int)(e % m), c = (int)(e / m); W[i + (long)c * m] = A[i + (long)c * ld]; }
+    for (long e = tid; e < (long)m * n; e += nthr) { int c = (int)((unsigned)e / (unsigned)m), i = (int)((unsigned)e - (unsigned)c * (unsigned)m); W[i + (long)c * m] = A[i + (long)c * ld]; }
   }
   T* v_s = p;
   __syncthreads();
@@ -490,7 +490,7 @@ __global__ void __launch_bounds__(512) k_formq(T* __restrict__ A, int m, int n, 
     __syncthreads();
   }
   if (STAGE) {
-    for (long e = tid; e < (long)m * n; e += nthr) { int i = (int)(e % m), c = (int)(e / m); A[i + (long)c * ld] = W[i + (long)c * m]; }
+    for (long e = tid; e < (long)m * n; e += nthr) { int c = (int)((unsigned)e / (unsigned)m), i = (int)((unsigned)e - (unsigned)c * (unsigned)m); A[i + (long)c * ld] = W[i + (long)c * m]; }
   }
 }
 
@@ -808,7 +808,7 @@ __global__ void k_permcopy(T* __restrict__ dst, int ldd, long sDst, const T* __r
   dst += (long)b * sDst; src += (long)b * sSrc;
   if (perm) perm += (long)b * sP;
   for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < (long)m * n; e += (long)gridDim.x * blockDim.x) {
-    int i = (int)(e % m), j = (int)(e / m);
+    int j = (int)((unsigned)e / (unsigned)m), i = (int)((unsigned)e - (unsigned)j * (unsigned)m);
     T v = src[i + (long)j * lds];
     if (MODE == 0) dst[i + (long)j * ldd] = v;
     else if (MODE == 1) dst[i + (long)j * ldd] = src[perm[i] + (long)j * lds];
@@ -836,7 +836,7 @@ template <typename T>
 __global__ void k_colscale(T* __restrict__ A, int ld, long sA, int m, int n, const double* __restrict__ d, long sD) {
   const int b = blockIdx.y; A += (long)b * sA; d += (long)b * sD;
   for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < (long)m * n; e += (long)gridDim.x * blockDim.x) {
-    int i = (int)(e % m), j = (int)(e / m);
+    int j = (int)((unsigned)e / (unsigned)m), i = (int)((unsigned)e - (unsigned)j * (unsigned)m);
     A[i + (long)j * ld] = A[i + (long)j * ld] * d[j];
   }
 }
@@ -859,7 +859,7 @@ template <typename T>
 __global__ void k_set_identity(T* __restrict__ A, int ld, long sA, int m, int n) {
   const int b = blockIdx.y; A += (long)b * sA;
   for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < (long)m * n; e += (long)gridDim.x * blockDim.x) {
-    int i = (int)(e % m), j = (int)(e / m);
+    int j = (int)((unsigned)e / (unsigned)m), i = (int)((unsigned)e - (unsigned)j * (unsigned)m);
     A[i + (long)j * ld] = (i == j) ? one_<T>() : zero_<T>();
   }
 }
@@ -878,7 +878,7 @@ __global__ void k_cgr_tpup(T* __restrict__ OUT, const T* __restrict__ TP, const 
                            const double* __restrict__ DR, const double* __restrict__ DL, long sD) {
   const int b = blockIdx.y; OUT += (long)b * sM; TP += (long)b * sM; RHS += (long)b * sM; DR += (long)b * sD; DL += (long)b * sD;
   for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < (long)n * n; e += (long)gridDim.x * blockDim.x) {
-    int i = (int)(e % n), j = (int)(e / n);
+    int j = (int)((unsigned)e / (unsigned)n), i = (int)((unsigned)e - (unsigned)j * (unsigned)n);
     double dr = DR[i], dl = DL[j];
     T t = TP[e], r = RHS[e], o;
     if (!SEP) o = (dr * t) * dl + r;
@@ -894,7 +894,7 @@ template <typename T, int ROWS>
 __global__ void k_sep_scale(T* __restrict__ A, long sA, int n, const double* __restrict__ d, long sD) {
   const int b = blockIdx.y; A += (long)b * sA; d += (long)b * sD;
   for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < (long)n * n; e += (long)gridDim.x * blockDim.x) {
-    int i = (int)(e % n), j = (int)(e / n);
+    int j = (int)((unsigned)e / (unsigned)n), i = (int)((unsigned)e - (unsigned)j * (unsigned)n);
     double x = d[ROWS ? i : j];
     if (x > 1.0) A[e] = A[e] * (1.0 / x);
   }
@@ -905,7 +905,7 @@ template <typename T>
 __global__ void k_rowscale_inv(T* __restrict__ A, int ld, long sA, int m, int n, const double* __restrict__ d, long sD) {
   const int b = blockIdx.y; A += (long)b * sA; d += (long)b * sD;
   for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < (long)m * n; e += (long)gridDim.x * blockDim.x) {
-    int i = (int)(e % m), j = (int)(e / m);
+    int j = (int)((unsigned)e / (unsigned)m), i = (int)((unsigned)e - (unsigned)j * (unsigned)m);
     A[i + (long)j * ld] = A[i + (long)j * ld] * (1.0 / d[i]);
   }
 }
@@ -922,7 +922,7 @@ __global__ void k_cgr22_build(T* __restrict__ HLPB1, T* __restrict__ HLP, long s
   const bool fst = D1[0] > D2[0];
   if (blockIdx.x == 0 && threadIdx.x == 0) first[b] = fst ? 1 : 0;
   for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < (long)N2 * N2; e += (long)gridDim.x * blockDim.x) {
-    const int I2 = (int)(e % N2), J2 = (int)(e / N2);
+    const int J2 = (int)((unsigned)e / (unsigned)N2), I2 = (int)((unsigned)e - (unsigned)J2 * (unsigned)N2);
     const int bi = I2 >= N, bj = J2 >= N, I = I2 - bi * N, J = J2 - bj * N;
     // blocks of HLPB2 in the "first" ordering: (0,0) V1INV, (0,1) D1 U1^H, (1,0) -D2 V2, (1,1) U2^H ; otherwise both block rows and columns swap roles
     const int kind = fst ? (bi * 2 + bj) : ((1 - bi) * 2 + (1 - bj));
@@ -946,7 +946,7 @@ __global__ void k_cgr22_blocks(const T* __restrict__ INP, long s22, T* __restric
   INP += (long)b * s22; GT0 += (long)b * sM; G00 += (long)b * sM; GTT += (long)b * sM; G0T += (long)b * sM;
   const bool fst = first[b] != 0;
   for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < (long)N * N; e += (long)gridDim.x * blockDim.x) {
-    const int I = (int)(e % N), J = (int)(e / N);
+    const int J = (int)((unsigned)e / (unsigned)N), I = (int)((unsigned)e - (unsigned)J * (unsigned)N);
     const T a = INP[I + (long)J * N2], d = INP[(I + N) + (long)(J + N) * N2], c = INP[(I + N) + (long)J * N2], bb = INP[I + (long)(J + N) * N2];
     if (fst) { G00[e] = a; G0T[e] = bb; GT0[e] = c; GTT[e] = d; }
     else { GTT[e] = a; GT0[e] = bb; G0T[e] = c; G00[e] = d; }

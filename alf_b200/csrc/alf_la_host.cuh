@@ -357,7 +357,7 @@ template <typename T>
 __global__ void k_one_minus(T* __restrict__ G, long sM, int n) {
   const int b = blockIdx.y; G += (long)b * sM;
   for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < (long)n * n; e += (long)gridDim.x * blockDim.x) {
-    const int i = (int)(e % n), j = (int)(e / n);
+    const int j = (int)((unsigned)e / (unsigned)n), i = (int)((unsigned)e - (unsigned)j * (unsigned)n);
     G[e] = ((i == j) ? one_<T>() : zero_<T>()) - G[e];
   }
 }
