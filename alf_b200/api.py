@@ -351,6 +351,10 @@ class AlfB200:
     def obs_reset(self):
         self._ck(lib().alf_b200_obs_reset(self.h))
 
+    def set_measure_interval(self, lobs_st=0, lobs_en=0):
+        """LOBS_ST / LOBS_EN of VAR_QMC (alf_b200_set_measure_interval): equal-time measurements on the slices lobs_st <= NTAU1 <= lobs_en; 0 = default."""
+        self._ck(lib().alf_b200_set_measure_interval(self.h, int(lobs_st), int(lobs_en)))
+
     def set_obs_scal_tables(self, tab):
         """Kin / Pot / Ener of ham%Obser on the device from tables (alf_b200_set_obs_scal_tables); `tab` = alf_b200.model.obs_scal_tables(model)."""
         a = {k: np.ascontiguousarray(tab[k], dtype=np.int32) for k in ("kin_i", "kin_j", "kin_nf", "pot_i1", "pot_nf1", "pot_i2", "pot_nf2")}

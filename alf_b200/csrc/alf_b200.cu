@@ -118,6 +118,16 @@ int alf_b200_set_global_tau_sampling(alf_b200_handle* h, int nt_sequential_start
   h->nt_seq_start = nt_sequential_start; h->nt_seq_end = nt_sequential_end; h->n_global_tau = n_global_tau;
   return ALF_OK;
 }
+int alf_b200_set_measure_interval(alf_b200_handle* h, int lobs_st, int lobs_en) {
+  if (!h) return ALF_ERROR_GENERIC;
+  if (lobs_st < 0 || lobs_en < 0 || lobs_st > h->ltrot || lobs_en > h->ltrot) { h->err = "alf_b200_set_measure_interval: 0 <= LOBS_ST, LOBS_EN <= Ltrot"; return ALF_ERROR_GENERIC; }
+  if (h->projector) {       // set_default_values_measuring_interval, QMC_runtime_var_mod.F90:163-180
+    if (lobs_st != 0 && lobs_st < h->thtrot + 1) { h->err = "Measuring out of dedicating interval, LOBS_ST too small."; return ALF_ERROR_GENERIC; }
+    if (lobs_en != 0 && lobs_en > h->ltrot - h->thtrot) { h->err = "Measuring out of dedicating interval, LOBS_EN too big."; return ALF_ERROR_GENERIC; }
+  }
+  h->lobs_st = lobs_st; h->lobs_en = lobs_en;
+  return ALF_OK;
+}
 int alf_b200_set_global_move_tau_ising(alf_b200_handle* h, int n_sites, const int* move_start, const int* move_fields, int n_terms, const int* site_term_start,
                                        const int* term_start, const int* entry_op, const int* entry_dt, const double* w, int open_boundaries) {
   if (!h) return ALF_ERROR_GENERIC;

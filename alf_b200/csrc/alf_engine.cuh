@@ -168,6 +168,7 @@ struct alf_b200_handle {
   bool s0_on = false; int s0_open_bc = 0, propose_s0 = 0; std::vector<int> s0_op_start, s0_term_start, s0_e_op, s0_e_dt; std::vector<double> s0_w;
   // Nt_sequential_start / _end, N_Global_tau (Overide_global_tau_sampling_parameters) and ham%Global_move_tau as tables (see GmtDev)
   int nt_seq_start = 1, nt_seq_end = -1, n_global_tau = 0;
+  int lobs_st = 0, lobs_en = 0;          // 0 = default window (alf_b200_set_measure_interval)
   bool gmt_on = false; int gmt_n_sites = 0, gmt_open_bc = 0; std::vector<int> gmt_move_start, gmt_move_fields, gmt_op_start, gmt_term_start, gmt_e_op, gmt_e_dt; std::vector<double> gmt_w;
   // projective algorithm (Prog/Hamiltonian_main_mod.F90:181-197: Projector, Thtrot, WF_L, WF_R)
   bool projector = false; int thtrot = 0, n_part = 0; std::vector<std::vector<cd>> wf_l, wf_r;   // per flavor, Ndim x N_part column-major
@@ -1166,7 +1167,7 @@ struct Engine : EngineBase {
 
   // where main.F90:757-773 / 789-802 call ham%Obser: NTAU1 in [LOBS_ST, LOBS_EN] (defaults of QMC_runtime_var_mod.F90:156-189)
   void measure_hook(int ntau1) {
-    const int lobs_st = proj ? thtrot + 1 : 1, lobs_en = proj ? L - thtrot : L;
+    const int lobs_st = h->lobs_st > 0 ? h->lobs_st : (proj ? thtrot + 1 : 1), lobs_en = h->lobs_en > 0 ? h->lobs_en : (proj ? L - thtrot : L);
     if (ntau1 < lobs_st || ntau1 > lobs_en) return;
     KL(KC_OBS, st, k_obs_scalar<T><<<C, 128, 0, st>>>(G, n2, N, F, h->n_sun, h->d_phase, h->d_obs));
     const bool scal_tab = h->n_kin > 0 || h->n_pot > 0;

@@ -70,6 +70,10 @@ int alf_b200_set_s0_ising(alf_b200_handle* h, int n_terms, const int* op_start /
  * the fields nt_sequential_start .. nt_sequential_end one by one and then (before, on the way down) make n_global_tau global-in-slice moves
  * (Prog/Wrapgr_mod.F90:112-153, 189-194).  Defaults: 1, size(Op_V,1), 0.  Before alf_b200_finalize_model. */
 int alf_b200_set_global_tau_sampling(alf_b200_handle* h, int nt_sequential_start, int nt_sequential_end, int n_global_tau);
+/* LOBS_ST, LOBS_EN of the VAR_QMC namelist (Prog/QMC_runtime_var_mod.F90:156-189, handed to ham%Obser's call sites Prog/main.F90:757-773,789-802 and
+ * to TAU_M / Tau_p): equal-time measurements are taken on the slices lobs_st <= NTAU1 <= lobs_en.  0 = the reference's default (1 and Ltrot; Thtrot + 1
+ * and Ltrot - Thtrot in the projective algorithm); a projective window outside [Thtrot + 1, Ltrot - Thtrot] is an error as in the reference. */
+int alf_b200_set_measure_interval(alf_b200_handle* h, int lobs_st, int lobs_en);
 /* The plugin callback ham%Global_move_tau for Ising "star" moves as tables (Prog/Hamiltonians/Hamiltonian_Z2_Matter_smod.F90:535-643), so that
  * the batched sweep needs no host in the loop: per move a site I = nranf(n_sites) is drawn from the chain's stream; Flip_list =
  * move_fields[move_start[I-1] .. move_start[I]-1] (1-based field indices, ascending = after Wrapgr_sort, at most 16, Ising fields only),

@@ -73,3 +73,27 @@ def test_reduce_bins_single_rank_communicator():
         assert np.array_equal(a, b)
     assert ctl["NC_up"] == before[3]["NC_up"] and ctl["XMAXG"] == before[3]["XMAXG"]
     g.close()
+
+
+def test_measure_interval_lobs():
+    """alf_b200_set_measure_interval = LOBS_ST / LOBS_EN of VAR_QMC (Prog/QMC_runtime_var_mod.F90:156-189): ham%Obser is called for lobs_st <= NTAU1 <= lobs_en
+    on the way up (NTAU1 = 1 .. Ltrot, Prog/main.F90:757-773) and on the way down (NTAU1 = Ltrot - 1 .. 0, :789-802); the projective window is checked."""
+    m = hubbard_square(4, 4, 1.0); L = m.Ltrot; seeds = SEEDS[:2]
+    for (a, b) in ((0, 0), (3, 7), (1, 1), (L, L)):
+        g = AlfB200(m, n_chains=len(seeds), nwrap=5); g.set_seeds(seeds); g.fields_set(); g.init_sweep()
+        g.set_measure_interval(a, b); g.sweep(1, 0)
+        lo, hi = (a or 1), (b or L)
+        n_up = sum(1 for nt1 in range(1, L + 1) if lo <= nt1 <= hi); n_dn = sum(1 for nt1 in range(L - 1, -1, -1) if lo <= nt1 <= hi)
+        assert g.obs()[0] == len(seeds) * (n_up + n_dn), (a, b)
+        g.close()
+    g = AlfB200(m, n_chains=1, nwrap=5)
+    with pytest.raises(api.AlfError):
+        g.set_measure_interval(L + 1, 0)
+    g.close()
+    from alf_b200.model import hubbard_chain
+    mp = hubbard_chain(4, 1.0, 0.1, projector=True, theta=0.5)
+    gp = AlfB200(mp, n_chains=1, nwrap=5)
+    with pytest.raises(api.AlfError):
+        gp.set_measure_interval(1, 0)            # LOBS_ST < Thtrot + 1
+    gp.set_measure_interval(mp.Thtrot + 1, mp.Ltrot - mp.Thtrot)
+    gp.close()
