@@ -59,6 +59,10 @@ class AlfB200:
             self._ck(L.alf_b200_set_op_v(self.h, o["n"], o["nf"], o["N"], o["nnz"], o["diag"], o["type"], o["P"].ctypes.data_as(_ip),
                                          _d(o["U"]), _d(o["E"]), C.c_double(o["g"].real), C.c_double(o["g"].imag),
                                          C.c_double(o["alpha"].real), C.c_double(o["alpha"].imag)))
+            if o.get("g_t") is not None:
+                if o["g_t"].size != model.Ltrot:
+                    raise ValueError("g_t needs Ltrot entries")
+                self._ck(L.alf_b200_set_op_v_gt(self.h, o["n"], o["nf"], _d(o["g_t"])))
         for o in ot:
             self._ck(L.alf_b200_set_op_t(self.h, o["nc"], o["nf"], o["N"], o["diag"], o["P"].ctypes.data_as(_ip), _d(o["U"]), _d(o["E"]),
                                          C.c_double(o["g"].real), C.c_double(o["g"].imag)))

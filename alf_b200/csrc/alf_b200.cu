@@ -89,6 +89,14 @@ int alf_b200_set_op_v(alf_b200_handle* h, int n, int nf, int N, int nnz, int dia
   h->types[n - 1] = type;
   return fill_host_op(h->opv[(n - 1) + (size_t)h->n_opv * (nf - 1)], N, nnz, diag, type, P, U, E, g_re, g_im, a_re, a_im, h->ndim);
 }
+int alf_b200_set_op_v_gt(alf_b200_handle* h, int n, int nf, const double* g_t) {
+  if (!h || h->finalized || n < 1 || n > h->n_opv || nf < 1 || nf > h->n_fl || !g_t) return ALF_ERROR_HAMILTONIAN;
+  HostOp& op = h->opv[(n - 1) + (size_t)h->n_opv * (nf - 1)];
+  if (!op.set) { h->err = "alf_b200_set_op_v_gt: call alf_b200_set_op_v for this vertex first"; return ALF_ERROR_HAMILTONIAN; }
+  op.g_t.resize(h->ltrot); for (int t = 0; t < h->ltrot; ++t) op.g_t[t] = cd(g_t[2 * t], g_t[2 * t + 1]);
+  h->has_gt = true;
+  return ALF_OK;
+}
 int alf_b200_set_op_t(alf_b200_handle* h, int nc, int nf, int N, int diag, const int* P, const double* U, const double* E, double g_re, double g_im) {
   if (!h || h->finalized || nc < 1 || nc > h->n_opt || nf < 1 || nf > h->n_fl) return ALF_ERROR_HAMILTONIAN;
   return fill_host_op(h->opt[(nc - 1) + (size_t)h->n_opt * (nf - 1)], N, N, diag, 0, P, U, E, g_re, g_im, 0, 0, h->ndim);
@@ -177,11 +185,13 @@ int alf_b200_finalize_model(alf_b200_handle* h) {
     if (o.type == 3) { has_cont = true; if (o.N != 1) { h->err = "continuous fields (type 3) are supported for single-site vertices only in this build"; return ALF_ERROR_UNSUPPORTED; } }
     else if (o.type != 1 && o.type != 2) { h->err = "field types 1, 2 (discrete) and 3 (continuous, real) are supported in this build; type 4 is not"; return ALF_ERROR_UNSUPPORTED; }
   }
+  if (h->has_gt && (h->n_global_tau > 0 || h->s0_on)) { h->err = "time-dependent couplings g_t together with Ising action tables / global moves are not supported in this build"; return ALF_ERROR_UNSUPPORTED; }
   if (has_cont && (h->n_global_tau > 0 || h->s0_on)) { h->err = "continuous fields together with Ising action tables / global moves are not supported in this build"; return ALF_ERROR_UNSUPPORTED; }
   // real instantiation iff every table the sweep touches is real
   bool cplx_needed = false;
   for (auto& o : h->opt) { if (o.g.imag() != 0.0) cplx_needed = true; for (auto& u : o.U) if (u.imag() != 0.0) cplx_needed = true; }
-  for (auto& o : h->opv) { if (o.g.imag() != 0.0 || (o.g * o.alpha).imag() != 0.0) cplx_needed = true; for (auto& u : o.U) if (u.imag() != 0.0) cplx_needed = true; }
+  for (auto& o : h->opv) { if (o.g.imag() != 0.0 || (o.g * o.alpha).imag() != 0.0) cplx_needed = true; for (auto& u : o.U) if (u.imag() != 0.0) cplx_needed = true;
+    for (auto& gt : o.g_t) if (gt.imag() != 0.0 || (gt * o.alpha).imag() != 0.0) cplx_needed = true; }
   if (h->projector) {
     for (int f = 0; f < h->n_fl; ++f) {
       if (h->wf_l[f].size() != (size_t)h->ndim * h->n_part || h->wf_r[f].size() != (size_t)h->ndim * h->n_part) {
@@ -291,6 +301,7 @@ int alf_b200_udv_reset(alf_b200_handle* h, int which, char side) { API_BEGIN(h) 
 int alf_b200_cgr(alf_b200_handle* h, int nvar) { API_BEGIN(h) NEED_FINAL(h) h->eng->cgr_call(nvar); h->eng->sync(); API_END(h) }
 int alf_b200_langevin_forces(alf_b200_handle* h, double* forces) {
   API_BEGIN(h) NEED_FINAL(h)
+  if (h->has_gt) { h->err = "time-dependent couplings g_t are not supported by the Langevin / HMC updates in this build"; return ALF_ERROR_UNSUPPORTED; }
   if (!forces) return ALF_ERROR_GENERIC;
   std::vector<cd> f((size_t)h->n_chains * h->ltrot * h->n_opv);
   h->eng->langevin_get_forces(f.data());
@@ -300,12 +311,14 @@ int alf_b200_langevin_forces(alf_b200_handle* h, double* forces) {
 int alf_b200_langevin_update(alf_b200_handle* h, double delta_t, double max_force, double* delta_t_running) {
   API_BEGIN(h) NEED_FINAL(h)
   if (!(delta_t > 0.0) || !(max_force > 0.0)) return ALF_ERROR_GENERIC;
+  if (h->has_gt) { h->err = "time-dependent couplings g_t are not supported by the Langevin / HMC updates in this build"; return ALF_ERROR_UNSUPPORTED; }
   h->eng->langevin_update(delta_t, max_force, delta_t_running);
   API_END(h)
 }
 int alf_b200_hmc_update(alf_b200_handle* h, double delta_t, int leapfrog_steps, double* weight, uint8_t* accepted) {
   API_BEGIN(h) NEED_FINAL(h)
   if (!(delta_t > 0.0) || leapfrog_steps < 1) return ALF_ERROR_GENERIC;
+  if (h->has_gt) { h->err = "time-dependent couplings g_t are not supported by the Langevin / HMC updates in this build"; return ALF_ERROR_UNSUPPORTED; }
   h->eng->hmc_update(delta_t, leapfrog_steps, weight, accepted);
   API_END(h)
 }

@@ -24,6 +24,7 @@ static const double kEpsMachine = 2.220446049250313e-16;
 struct HostOp {
   int N = 0, nnz = 0, diag = 0, type = 0; bool set = false;
   std::vector<int> P; std::vector<cd> U; std::vector<double> E; cd g = 0, alpha = 0;
+  std::vector<cd> g_t;          // time-dependent coupling g_t(1..Ltrot) (Operator_mod.F90:66), empty if not allocated
 };
 
 static void host_op_exp(cd g, const HostOp& op, std::vector<cd>& Mat) {   // Prog/Operator_mod.F90:491-529 (Kahan summation)
@@ -83,6 +84,7 @@ template <> inline cd from_T<cplx>(cplx v) { return cd(v.x, v.y); }
 
 // one operator list under construction
 struct ListBuild {
+  long nt_stride = 0;                   // > 0: mat holds one table per time slice (g_t), nt_stride entries each
   int nvar = 1; std::vector<int> k, P, fidx; std::vector<cd> mat;   // mat: per op nvar*KMAX*KMAX
   std::vector<unsigned char> cont;      // 1: continuous field, slot 0 of mat holds the coefficient c of exp(c phi)
   void add(int kk, const int* p, int fi, const std::vector<std::vector<cd>>& mats /* nvar matrices kk x kk col-major */, bool is_cont = false) {
@@ -168,6 +170,7 @@ struct alf_b200_handle {
   bool s0_on = false; int s0_open_bc = 0, propose_s0 = 0; std::vector<int> s0_op_start, s0_term_start, s0_e_op, s0_e_dt; std::vector<double> s0_w;
   // Nt_sequential_start / _end, N_Global_tau (Overide_global_tau_sampling_parameters) and ham%Global_move_tau as tables (see GmtDev)
   int nt_seq_start = 1, nt_seq_end = -1, n_global_tau = 0;
+  bool has_gt = false;                   // some Op_V carries g_t: vertex tables are built per time slice
   int lobs_st = 0, lobs_en = 0;          // 0 = default window (alf_b200_set_measure_interval)
   bool gmt_on = false; int gmt_n_sites = 0, gmt_open_bc = 0; std::vector<int> gmt_move_start, gmt_move_fields, gmt_op_start, gmt_term_start, gmt_e_op, gmt_e_dt; std::vector<double> gmt_w;
   // projective algorithm (Prog/Hamiltonian_main_mod.F90:181-197: Projector, Thtrot, WF_L, WF_R)
@@ -200,14 +203,14 @@ static __global__ void k_fields_set(int8_t* fields, uint64_t* rng, int n_chains,
 
 // sum over (n, nt) of Im(g alpha phi(s)) per (chain, flavor)  -- Op_phase, Prog/Operator_mod.F90:160-181
 static __global__ void k_op_phase(const int8_t* __restrict__ fields, const double* __restrict__ angle_tab, int F, int n_opv, int Ltrot, double* __restrict__ out,
-                                  const double* __restrict__ fields_c, const unsigned char* __restrict__ is_cont) {
+                                  const double* __restrict__ fields_c, const unsigned char* __restrict__ is_cont, long nt_stride) {
   __shared__ double red[8];
   const int b = blockIdx.x, chain = b / F, f = b % F;
   const int8_t* fl = fields + (long)chain * Ltrot * n_opv;
   double s = 0.0;
   const double* fc = fields_c ? fields_c + (long)chain * Ltrot * n_opv : nullptr;
-  for (long e = threadIdx.x; e < (long)Ltrot * n_opv; e += blockDim.x) { int n = (int)(e % n_opv);
-    if (fc && is_cont[n]) s += angle_tab[((long)n * F + f) * ALF_NVAR] * fc[e]; else s += angle_tab[((long)n * F + f) * ALF_NVAR + fl[e] + 2]; }
+  for (long e = threadIdx.x; e < (long)Ltrot * n_opv; e += blockDim.x) { int n = (int)(e % n_opv); const double* at = angle_tab + (e / n_opv) * nt_stride;      // g_t: one table per time slice
+    if (fc && is_cont[n]) s += at[((long)n * F + f) * ALF_NVAR] * fc[e]; else s += at[((long)n * F + f) * ALF_NVAR + fl[e] + 2]; }
   s = warp_sum(s);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
   __syncthreads();
@@ -482,7 +485,7 @@ struct Engine : EngineBase {
   UdvDev<T> alloc_udv() { UdvDev<T> u; u.U = dalloc<T>(n2 * NM); u.V = dalloc<T>(n2 * NM); u.D = dalloc<double>((size_t)N * NM); u.det = dalloc<cplx>(NM); return u; }
 
   OpListDev upload_list(const ListBuild& lb) {
-    OpListDev d; d.n_ops = (int)lb.k.size(); d.nvar = lb.nvar;
+    OpListDev d; d.n_ops = (int)lb.k.size(); d.nvar = lb.nvar; d.mat_nt_stride = lb.nt_stride;
     std::vector<int> ls = lb.levels(N, OPS_CH); d.n_levels = (int)ls.size() - 1;
     for (int kk : lb.k) { while ((1 << ops_lk) < kk) ++ops_lk; }
     d.level_start = dupload(ls); d.k = dupload(lb.k); d.P = dupload(lb.P); d.fidx = dupload(lb.fidx);
@@ -608,12 +611,13 @@ struct Engine : EngineBase {
     return 1;
   }
   VDiagDev upload_vdiag(const ListBuild& lb) {             // diagonal vertex list by site (k_apply_ops_fixed)
-    std::vector<T> tab((size_t)N * ALF_NVAR, one_<T>()); std::vector<int> fi(N, -1); std::vector<unsigned char> ct(N, 0);
-    if (diag_list_ok(lb) && lb.nvar == ALF_NVAR) for (size_t o = 0; o < lb.k.size(); ++o) {
+    const int nsl = lb.nt_stride > 0 ? L : 1;
+    std::vector<T> tab((size_t)nsl * N * ALF_NVAR, one_<T>()); std::vector<int> fi(N, -1); std::vector<unsigned char> ct(N, 0);
+    if (diag_list_ok(lb) && lb.nvar == ALF_NVAR) for (int sl = 0; sl < nsl; ++sl) for (size_t o = 0; o < lb.k.size(); ++o) {
       const int p = lb.P[o * ALF_KMAX]; fi[p] = lb.fidx[o]; ct[p] = lb.cont[o];
-      for (int var = 0; var < ALF_NVAR; ++var) tab[(size_t)p * ALF_NVAR + var] = to_T<T>(lb.mat[(o * ALF_NVAR + var) * ALF_KMAX * ALF_KMAX]);
+      for (int var = 0; var < ALF_NVAR; ++var) tab[((size_t)sl * N + p) * ALF_NVAR + var] = to_T<T>(lb.mat[(size_t)sl * lb.nt_stride + (o * ALF_NVAR + var) * ALF_KMAX * ALF_KMAX]);
     }
-    VDiagDev v; v.tab = dupload(tab); v.fidx = dupload(fi); v.cont = dupload(ct);
+    VDiagDev v; v.tab = dupload(tab); v.fidx = dupload(fi); v.cont = dupload(ct); v.tab_nt_stride = nsl > 1 ? (long)N * ALF_NVAR : 0;
     return v;
   }
   bool fixed_mode_ok(int mode) const {
@@ -831,49 +835,59 @@ struct Engine : EngineBase {
         for (int q = 0; q < 5; ++q) { std::vector<T> t(n2); for (long i = 0; i < n2; ++i) t[i] = to_T<T>((*src[q])[i]); CK(cudaMemcpy(d_dense[q] + n2 * f, t.data(), sizeof(T) * n2, cudaMemcpyHostToDevice)); }
       }
     }
-    // vertices
-    std::vector<VopDev<T>> vops((size_t)M * F);
-    std::vector<double> angle_tab((size_t)M * F * ALF_NVAR, 0.0);
+    // vertices.  With time-dependent couplings g_t (Operator_mod.F90:66: the reference then evaluates Op_exp on the fly, :583-604, 677-699, 768-791, 885-908)
+    // every table below exists once per time slice: vops[sl][n][f], angle_tab[sl][n][f][var], the matrices of the three vertex lists [sl][op][var].
+    const int nsl = h->has_gt ? L : 1;
+    std::vector<VopDev<T>> vops((size_t)nsl * M * F);
+    std::vector<double> angle_tab((size_t)nsl * M * F * ALF_NVAR, 0.0);
     for (int f = 0; f < F; ++f) {
+      ListBuild vn0, vc0, vri0; std::vector<cd> vn_mat, vc_mat, vri_mat;
+      for (int sl = 0; sl < nsl; ++sl) {
       ListBuild vn, vc, vri; vn.nvar = vc.nvar = vri.nvar = ALF_NVAR;
+      auto gof = [&](const HostOp& o) { return o.g_t.empty() ? o.g : o.g_t[sl]; };
       std::vector<std::vector<std::vector<cd>>> mexp(M);   // [n][var] k x k
       for (int n = 0; n < M; ++n) {
-        const HostOp& op = h->opv[n + (size_t)M * f]; const int k = op.N;
+        const HostOp& op = h->opv[n + (size_t)M * f]; const int k = op.N; const cd og = gof(op);
         if (k > ALF_KMAX) throw CudaError("interaction vertex with N > ALF_KMAX is not supported in this build");
-        VopDev<T>& v = vops[(size_t)n * F + f];
+        VopDev<T>& v = vops[((size_t)sl * M + n) * F + f];
         std::memset(&v, 0, sizeof(v));
         v.k = k; v.nnz = op.nnz; v.diag = op.diag; v.type = op.type;
-        for (int a = 0; a < ALF_KMAX; ++a) v.gE[a] = to_T<T>(a < op.nnz ? op.g * op.E[a] : cd(0, 0));
-        v.galpha = to_T<T>(op.g * op.alpha);
+        for (int a = 0; a < ALF_KMAX; ++a) v.gE[a] = to_T<T>(a < op.nnz ? og * op.E[a] : cd(0, 0));
+        v.galpha = to_T<T>(og * op.alpha);
         for (int a = 0; a < k; ++a) v.P[a] = op.P[a];
         for (int a = 0; a < k; ++a) for (int b = 0; b < k; ++b) v.U[a + b * ALF_KMAX] = to_T<T>(op.U[a + (size_t)b * k]);
         mexp[n].resize(ALF_NVAR);
         for (int var = 0; var < ALF_NVAR; ++var) {
           const int s = var - 2; const bool valid = (s != 0) && (std::abs(s) <= op.type);
           const double ph = valid ? phi_st(op.type, s) : 0.0;
-          for (int a = 0; a < ALF_KMAX; ++a) v.E_exp[a][var] = to_T<T>((a < op.nnz && valid) ? std::exp(op.g * op.E[a] * ph) : cd(1, 0));
-          host_op_exp(op.g * ph, op, mexp[n][var]);
-          angle_tab[((size_t)n * F + f) * ALF_NVAR + var] = (op.type == 3) ? (op.g * op.alpha).imag() : (valid ? (op.g * op.alpha * ph).imag() : 0.0);   // type 3: coefficient of phi
+          for (int a = 0; a < ALF_KMAX; ++a) v.E_exp[a][var] = to_T<T>((a < op.nnz && valid) ? std::exp(og * op.E[a] * ph) : cd(1, 0));
+          host_op_exp(og * ph, op, mexp[n][var]);
+          angle_tab[(((size_t)sl * M + n) * F + f) * ALF_NVAR + var] = (op.type == 3) ? (og * op.alpha).imag() : (valid ? (og * op.alpha * ph).imag() : 0.0);   // type 3: coefficient of phi
           for (int var2 = 0; var2 < ALF_NVAR; ++var2) {
             const int s2 = var2 - 2; const bool valid2 = (s2 != 0) && (std::abs(s2) <= op.type);
             const double dphi = (valid && valid2) ? (phi_st(op.type, s2) - ph) : 0.0;
-            for (int a = 0; a < ALF_KMAX; ++a) v.delta[a][var][var2] = to_T<T>((a < op.nnz) ? std::exp(op.g * dphi * op.E[a]) - 1.0 : cd(0, 0));
-            v.expalpha[var][var2] = to_T<T>(std::exp(op.g * dphi * op.alpha));
+            for (int a = 0; a < ALF_KMAX; ++a) v.delta[a][var][var2] = to_T<T>((a < op.nnz) ? std::exp(og * dphi * op.E[a]) - 1.0 : cd(0, 0));
+            v.expalpha[var][var2] = to_T<T>(std::exp(og * dphi * op.alpha));
           }
         }
       }
       auto ct = [](const std::vector<cd>& A, int k) { std::vector<cd> B(A.size()); for (int i = 0; i < k; ++i) for (int j = 0; j < k; ++j) B[i + (size_t)j * k] = std::conj(A[j + (size_t)i * k]); return B; };
-      for (int n = 0; n < M; ++n) { const HostOp& op = h->opv[n + (size_t)M * f]; if (std::abs(op.g) < kEpsMachine) continue;   // quick return, Operator_mod.F90:576,668
+      for (int n = 0; n < M; ++n) { const HostOp& op = h->opv[n + (size_t)M * f]; const cd og = gof(op); if (!h->has_gt && std::abs(op.g) < kEpsMachine) continue;   // quick return, Operator_mod.F90:576,668 (with g_t the factor of a slice with g_t = 0 is the identity)
         if (op.type == 3) {      // continuous field, k = 1: the kernels evaluate exp(c phi) with c = +g E (B), -g E (B^-1)
-          std::vector<std::vector<cd>> c1(ALF_NVAR, std::vector<cd>(1, op.g * op.E[0])), c2(ALF_NVAR, std::vector<cd>(1, -op.g * op.E[0]));
+          std::vector<std::vector<cd>> c1(ALF_NVAR, std::vector<cd>(1, og * op.E[0])), c2(ALF_NVAR, std::vector<cd>(1, -og * op.E[0]));
           vn.add(1, op.P.data(), n, c1, true); vri.add(1, op.P.data(), n, c2, true); continue; }
         vn.add(op.N, op.P.data(), n, mexp[n]);
         std::vector<std::vector<cd>> mi(ALF_NVAR); for (int var = 0; var < ALF_NVAR; ++var) mi[var] = tr(mexp[n][ALF_NVAR - 1 - var], op.N);   // exp(-phi g O)^T
         vri.add(op.N, op.P.data(), n, mi); }
-      for (int n = M - 1; n >= 0; --n) { const HostOp& op = h->opv[n + (size_t)M * f]; if (std::abs(op.g) < kEpsMachine) continue;
-        if (op.type == 3) { std::vector<std::vector<cd>> c3(ALF_NVAR, std::vector<cd>(1, std::conj(op.g * op.E[0]))); vc.add(1, op.P.data(), n, c3, true); continue; }   // (B)^dagger
+      for (int n = M - 1; n >= 0; --n) { const HostOp& op = h->opv[n + (size_t)M * f]; const cd og = gof(op); if (!h->has_gt && std::abs(op.g) < kEpsMachine) continue;
+        if (op.type == 3) { std::vector<std::vector<cd>> c3(ALF_NVAR, std::vector<cd>(1, std::conj(og * op.E[0]))); vc.add(1, op.P.data(), n, c3, true); continue; }   // (B)^dagger
         std::vector<std::vector<cd>> mc(ALF_NVAR); for (int var = 0; var < ALF_NVAR; ++var) mc[var] = ct(mexp[n][var], op.N);
         vc.add(op.N, op.P.data(), n, mc); }
+      if (sl == 0) { vn0 = vn; vc0 = vc; vri0 = vri; }
+      vn_mat.insert(vn_mat.end(), vn.mat.begin(), vn.mat.end()); vc_mat.insert(vc_mat.end(), vc.mat.begin(), vc.mat.end()); vri_mat.insert(vri_mat.end(), vri.mat.begin(), vri.mat.end());
+      }   // time slices
+      ListBuild& vn = vn0; ListBuild& vc = vc0; ListBuild& vri = vri0;
+      if (nsl > 1) { vn.nt_stride = (long)vn.mat.size(); vc.nt_stride = (long)vc.mat.size(); vri.nt_stride = (long)vri.mat.size(); vn.mat = vn_mat; vc.mat = vc_mat; vri.mat = vri_mat; }
       md.lists[L_VL_N][f] = upload_list(vn); md.lists[L_VL_C][f] = upload_list(vc); md.lists[L_VR_INV][f] = upload_list(vri);
       mf.diag_ok[L_VL_N][f] = diag_list_ok(vn); mf.diag_ok[L_VL_C][f] = diag_list_ok(vc); mf.diag_ok[L_VR_INV][f] = diag_list_ok(vri);
       mf.vd[L_VL_N][f] = upload_vdiag(vn); mf.vd[L_VL_C][f] = upload_vdiag(vc); mf.vd[L_VR_INV][f] = upload_vdiag(vri);
@@ -988,7 +1002,7 @@ struct Engine : EngineBase {
     std::swap(G, G2);
     l2_window(G, sizeof(T) * n2 * NM);
     double* ang = nullptr;
-    if (h->is_complex) { KL(KC_EW, st, k_op_phase<<<NM, 256, 0, st>>>(h->d_fields, d_angle_tab, F, M, L, d_angle, h->d_fields_c, d_is_cont)); ang = d_angle; }
+    if (h->is_complex) { KL(KC_EW, st, k_op_phase<<<NM, 256, 0, st>>>(h->d_fields, d_angle_tab, F, M, L, d_angle, h->d_fields_c, d_is_cont, h->has_gt ? (long)M * F * ALF_NVAR : 0)); ang = d_angle; }
     KL(KC_EW, st, k_phase_update<<<(C + 127) / 128, 128, 0, st>>>(d_z, ang, F, h->n_sun, h->d_phase, h->d_ctl, compare ? 1 : 0, C));
   }
   void cgr_call(int nvar) override { cgr_and_phase(nvar, false); }
@@ -1009,7 +1023,7 @@ struct Engine : EngineBase {
     gm_alloc();
     const size_t smem = gm_smem();
     CK(alf_raise_smem(k_random_update<T>));
-    KL(KC_UPDATE, st, k_random_update<T><<<C, 512, smem, st>>>(G, G2, N, F, h->n_sun, M, d_vops, ft, h->d_fields, L, ntau, h->d_rng, h->d_phase, h->d_counters, d_mpos,
+    KL(KC_UPDATE, st, k_random_update<T><<<C, 512, smem, st>>>(G, G2, N, F, h->n_sun, M, d_vops + (h->has_gt ? (size_t)(ntau - 1) * M * F : 0), ft, h->d_fields, L, ntau, h->d_rng, h->d_phase, h->d_counters, d_mpos,
                                                                h->n_global_tau, 1, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, place_to, gmtdev, gm_stage, d_place_tab, d_place_pk, gm_stage_f));
   }
   void rotate_group(const VGroup& g, bool in) {     // G <- U^H G U (in) / U G U^H (out) for all vertices of a pair group
@@ -1025,11 +1039,11 @@ struct Engine : EngineBase {
       const VGroup& g = groups[up ? gi : (int)groups.size() - 1 - gi];
       if (g.n0 < seq_lo || g.n0 >= seq_hi) continue;                  // not visited sequentially (Nt_sequential_start .. Nt_sequential_end)
       if (g.kind == 0) {
-        if (up) KL(KC_UPDATE, st, k_wrapgr<T, 1><<<C, 512, upd_smem, st>>>(G, N, F, h->n_sun, g.n0, g.cnt, M, off, d_vops, ft, h->d_fields, L, nt, h->d_rng, h->d_phase, h->d_counters, KD, lg, h->propose_s0, s0dev, stage_g, h->d_fields_c, h->s0_gaussian ? 1 : 0, h->amplitude));
-        else KL(KC_UPDATE, st, k_wrapgr<T, 0><<<C, 512, upd_smem, st>>>(G, N, F, h->n_sun, g.n0, g.cnt, M, off, d_vops, ft, h->d_fields, L, nt, h->d_rng, h->d_phase, h->d_counters, KD, lg, h->propose_s0, s0dev, stage_g, h->d_fields_c, h->s0_gaussian ? 1 : 0, h->amplitude));
+        if (up) KL(KC_UPDATE, st, k_wrapgr<T, 1><<<C, 512, upd_smem, st>>>(G, N, F, h->n_sun, g.n0, g.cnt, M, off, d_vops + (h->has_gt ? (size_t)(nt - 1) * M * F : 0), ft, h->d_fields, L, nt, h->d_rng, h->d_phase, h->d_counters, KD, lg, h->propose_s0, s0dev, stage_g, h->d_fields_c, h->s0_gaussian ? 1 : 0, h->amplitude));
+        else KL(KC_UPDATE, st, k_wrapgr<T, 0><<<C, 512, upd_smem, st>>>(G, N, F, h->n_sun, g.n0, g.cnt, M, off, d_vops + (h->has_gt ? (size_t)(nt - 1) * M * F : 0), ft, h->d_fields, L, nt, h->d_rng, h->d_phase, h->d_counters, KD, lg, h->propose_s0, s0dev, stage_g, h->d_fields_c, h->s0_gaussian ? 1 : 0, h->amplitude));
       } else {
         if (g.kind == 2) rotate_group(g, true);
-#define FAST_LAUNCH(UPV, IPT, PR) KL(KC_UPDATE, st, k_wrapgr_fast<T, UPV, IPT, PR><<<C, 512, fast_smem, st>>>(G, N, F, h->n_sun, g.n0, g.cnt, M, off, d_vops, ft, h->d_fields, L, nt, h->d_rng, h->d_phase, h->d_counters, KDf, ldxf, lg))
+#define FAST_LAUNCH(UPV, IPT, PR) KL(KC_UPDATE, st, k_wrapgr_fast<T, UPV, IPT, PR><<<C, 512, fast_smem, st>>>(G, N, F, h->n_sun, g.n0, g.cnt, M, off, d_vops + (h->has_gt ? (size_t)(nt - 1) * M * F : 0), ft, h->d_fields, L, nt, h->d_rng, h->d_phase, h->d_counters, KDf, ldxf, lg))
         if (g.kind == 1) {
           if (up) { if (iptf == 1) FAST_LAUNCH(1, 1, 0); else FAST_LAUNCH(1, 4, 0); }
           else { if (iptf == 1) FAST_LAUNCH(0, 1, 0); else FAST_LAUNCH(0, 4, 0); }
@@ -1399,7 +1413,7 @@ struct Engine : EngineBase {
     }
     const size_t smem = gm_smem();
     CK(alf_raise_smem(k_random_update<T>));
-    KL(KC_UPDATE, st, k_random_update<T><<<C, 512, smem, st>>>(G, G2, N, F, h->n_sun, M, d_vops, ft, h->d_fields, L, ntau, h->d_rng, h->d_phase, h->d_counters, d_mpos,
+    KL(KC_UPDATE, st, k_random_update<T><<<C, 512, smem, st>>>(G, G2, N, F, h->n_sun, M, d_vops + (h->has_gt ? (size_t)(ntau - 1) * M * F : 0), ft, h->d_fields, L, ntau, h->d_rng, h->d_phase, h->d_counters, d_mpos,
                                                                n_moves, std::max(maxlen, 1), d_len, d_list, d_val, d_t0, d_s0, d_acc, place_to, GmtDev{0, 0, nullptr, nullptr, {0, 0, nullptr, nullptr, nullptr, nullptr, nullptr}}, gm_stage, d_place_tab, d_place_pk, gm_stage_f));
     if (acc_out && n_moves > 0) { CK(cudaMemcpyAsync(acc_out, d_acc, np, cudaMemcpyDeviceToHost, st)); }
     sync();

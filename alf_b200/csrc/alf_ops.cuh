@@ -27,6 +27,7 @@ struct OpListDev {
   const void* mat;                  // n_ops * nvar * KMAX*KMAX entries of T, column-major a + b*KMAX
   const unsigned char* uniform;     // n_levels: 1 if every operator of the chunk is a k = 2 operator with one and the same matrix
   const unsigned char* cont;        // n_ops (vertex lists only): 1 = continuous field (type 3, k = 1): mat slot 0 holds the coefficient c, the factor is exp(c phi)
+  long mat_nt_stride;               // time-dependent couplings g_t (Operator_mod.F90:66): one table per time slice, mat + (nt - 1) * mat_nt_stride; else 0
 };
 
 enum {  // which operator lists a launch applies (per slice nt in [nt_a, nt_b])
@@ -173,7 +174,7 @@ __global__ void __launch_bounds__(OPS_NT) k_apply_ops(T* M, long sM, int N, int 
   struct Pref { int4 rP; T rM[MPT]; int rcnt; bool runi; };
   Pref pf0, pf1; pf0.rcnt = pf1.rcnt = 0; pf0.runi = pf1.runi = false;
   int f_sl = 0, f_r = 0, f_n = 0;                     // cursor of the next meta load
-  bool m_second = false; int m_a0 = 0, m_cnt = 0; bool m_uni = false; const int8_t* m_fld = nullptr; const double* m_fc = nullptr;
+  bool m_second = false; int m_a0 = 0, m_cnt = 0, m_nt = 1; bool m_uni = false; const int8_t* m_fld = nullptr; const double* m_fc = nullptr;
   auto meta_load = [&]() {
     if (f_n >= total) { m_cnt = 0; return; }
     m_second = f_r >= nch0;
@@ -183,6 +184,7 @@ __global__ void __launch_bounds__(OPS_NT) k_apply_ops(T* M, long sM, int N, int 
     const int nt = (dir > 0) ? nt_a + f_sl : nt_b - f_sl;
     m_fld = ((m_second ? uf1 : uf0) && fbase) ? fbase + (nt - 1) * n_opv : nullptr;
     m_fc = (m_fld && md.fields_c) ? md.fields_c + ((long)chain * Ltrot + (nt - 1)) * n_opv : nullptr;
+    m_nt = nt;
     ++f_n; if (++f_r == per) { f_r = 0; ++f_sl; }
   };
   auto data_issue = [&](Pref& pf) {                   // uses the meta registers loaded one step earlier
@@ -192,7 +194,7 @@ __global__ void __launch_bounds__(OPS_NT) k_apply_ops(T* M, long sM, int N, int 
       const int4 p = reinterpret_cast<const int4*>(L.P)[m_a0 + tid];
       pf.rP = make_int4((p.x * ldp) | (L.k[m_a0 + tid] << 28), p.y * ldp, p.z * ldp, p.w * ldp);
     }
-    const T* mats = reinterpret_cast<const T*>(L.mat);
+    const T* mats = reinterpret_cast<const T*>(L.mat) + (long)(m_nt - 1) * L.mat_nt_stride;
 #pragma unroll
     for (int u = 0; u < MPT; ++u) {
       const int e = tid + u * OPS_NT;
@@ -276,7 +278,7 @@ struct FixListDev {
   const unsigned char* blob;
   const void* mat;                  // global: n_ops * 4 entries of T (only read for families whose operators carry different matrices)
 };
-struct VDiagDev { const void* tab; const int* fidx; const unsigned char* cont; };   // diagonal vertex list by site: tab[i * 5 + s + 2] (continuous: slot 0 = coefficient), field index or -1
+struct VDiagDev { const void* tab; const int* fidx; const unsigned char* cont; long tab_nt_stride; };   // diagonal vertex list by site: tab[i * 5 + s + 2] (continuous: slot 0 = coefficient), field index or -1
 struct ModelFixDev {
   FixListDev fix[L_COUNT][ALF_FMAX];
   unsigned char diag_ok[L_COUNT][ALF_FMAX];   // vertex lists: only k = 1 factors, every site at most once
@@ -450,8 +452,9 @@ __global__ void __launch_bounds__((NMAX > 16 || sizeof(T) > 8) ? 256 : OPSF_NT, 
           const int n = (i == tid) ? vn0 : VD.fidx[i];
           T v = one_<T>();
           if (n >= 0) {
-            if (fcc && VD.cont[i]) v = exp_(vtab[(long)i * ALF_NVAR] * fcc[(long)(nt - 1) * n_opv + n]);
-            else v = vtab[(long)i * ALF_NVAR + (int)((i == tid) ? fnext : flc[(long)(nt - 1) * n_opv + n]) + 2];
+            const T* vt = vtab + (long)(nt - 1) * VD.tab_nt_stride;          // g_t: one table per time slice
+            if (fcc && VD.cont[i]) v = exp_(vt[(long)i * ALF_NVAR] * fcc[(long)(nt - 1) * n_opv + n]);
+            else v = vt[(long)i * ALF_NVAR + (int)((i == tid) ? fnext : flc[(long)(nt - 1) * n_opv + n]) + 2];
           }
           dsc[i] = v;
         }

@@ -40,6 +40,7 @@ class Operator:
     diag: bool = False
     U: Optional[np.ndarray] = None
     E: Optional[np.ndarray] = None
+    g_t: Optional[np.ndarray] = None      # time-dependent coupling g_t(1..Ltrot) of an interaction vertex (Operator_mod.F90:66), or None
 
 
 def Op_make(N: int) -> Operator:
@@ -675,7 +676,8 @@ def flatten_ops(model: Model):
             out_v.append(dict(n=n + 1, nf=nf + 1, N=op.N, nnz=op.N_non_zero, diag=int(op.diag), type=op.type,
                               P=np.ascontiguousarray(op.P, dtype=np.int32),
                               U=np.asfortranarray(op.U, dtype=np.complex128),
-                              E=np.ascontiguousarray(op.E, dtype=np.float64), g=complex(op.g), alpha=complex(op.alpha)))
+                              E=np.ascontiguousarray(op.E, dtype=np.float64), g=complex(op.g), alpha=complex(op.alpha),
+                              g_t=None if op.g_t is None else np.ascontiguousarray(op.g_t, dtype=np.complex128)))
     for nc, row in enumerate(model.Op_T):
         for nf, op in enumerate(row):
             out_t.append(dict(nc=nc + 1, nf=nf + 1, N=op.N, diag=int(op.diag),

@@ -51,6 +51,11 @@ int alf_b200_set_op_v(alf_b200_handle* h, int n, int nf, int N, int n_non_zero, 
                       const double* U, const double* E, double g_re, double g_im, double alpha_re, double alpha_im);
 int alf_b200_set_op_t(alf_b200_handle* h, int nc, int nf, int N, int diag, const int* P, const double* U, const double* E,
                       double g_re, double g_im);
+/* Time-dependent coupling of an interaction vertex: Op_V(n,nf)%g_t(1:Ltrot) (Prog/Operator_mod.F90:66; used instead of g by Op_mmultL/R, Op_Wrapup/do,
+ * Upgrade2 and Op_phase, :175,577,671,768-791,885-908).  g_t: Ltrot complex values (re, im).  After alf_b200_set_op_v of the same vertex, before
+ * alf_b200_finalize_model; the vertex tables are then built once per time slice.  Not combined with Ising action tables / global-in-slice moves, nor with
+ * the Langevin / HMC updates (ALF_ERROR_UNSUPPORTED). */
+int alf_b200_set_op_v_gt(alf_b200_handle* h, int n, int nf, const double* g_t);
 /* Projective algorithm (Projector = .T.): Thtrot and N_part, then WF_L(nf)%P / WF_R(nf)%P (Ndim x N_part, column-major
  * complex) per flavor -- the public module variables read by Prog/main.F90:366-376,596-599.  Call before finalize_model;
  * UDV_State then carries U(Ndim, N_part) without V (Prog/udv_state_mod.F90:131-150), CGR dispatches to CGRP

@@ -160,6 +160,7 @@ struct Op {
   std::vector<cd> U;            // N x N col-major
   std::vector<double> E;
   cd g = 0, alpha = 0;
+  std::vector<cd> g_t;          // time-dependent coupling g_t(nt) (Operator_mod.F90:66), empty if not allocated
   std::vector<cd> E_exp;        // [n + N*(sp+type)]
   std::vector<cd> M_exp;        // [N*N*(sp+type)]
 };
@@ -531,17 +532,21 @@ struct Oracle {
   }
 
   // ---- exp(sign*phi*g*E(I)) and exp(sign*phi*g*O) for one operator and field value
+  // g_t allocated: the coupling of the time slice the caller works on (cur_nt, set by every routine that loops over slices), and the exponentials are
+  // computed on the fly as in Operator_mod.F90:583-604, 677-699, 768-791, 885-908
+  int cur_nt = 1;
+  cd geff(const Op& op) const { return op.g_t.empty() ? op.g : op.g_t[cur_nt - 1]; }
   cd eexp(const Op& op, int I, cd field, int sign) {
-    if (op.type < 3) { int sp = sign * FieldTables::nint(field.real()); return op.E_exp[I + (size_t)op.N * (sp + op.type)]; }
-    return std::exp((double)sign * ft.phi(op.type, field) * op.g * op.E[I]);
+    if (op.type < 3 && op.g_t.empty()) { int sp = sign * FieldTables::nint(field.real()); return op.E_exp[I + (size_t)op.N * (sp + op.type)]; }
+    return std::exp((double)sign * ft.phi(op.type, field) * geff(op) * op.E[I]);
   }
   void mexp(const Op& op, cd field, int sign, cd* out) {
-    if (op.type < 3) { int sp = sign * FieldTables::nint(field.real()); std::memcpy(out, &op.M_exp[(size_t)op.N * op.N * (sp + op.type)], sizeof(cd) * op.N * op.N); }
-    else op_exp((double)sign * op.g * ft.phi(op.type, field), op, out);
+    if (op.type < 3 && op.g_t.empty()) { int sp = sign * FieldTables::nint(field.real()); std::memcpy(out, &op.M_exp[(size_t)op.N * op.N * (sp + op.type)], sizeof(cd) * op.N * op.N); }
+    else op_exp((double)sign * geff(op) * ft.phi(op.type, field), op, out);
   }
   // Operator_mod.F90:555-620 : Mat = Mat * op( exp(sign*phi*g*P^T O P) )
   void op_mmultL(cd* Mat, int N1, int N2, const Op& op, cd field, char cop, int sign) {
-    if (std::abs(op.g) < 2.220446049250313e-16) return;
+    if (std::abs(geff(op)) < 2.220446049250313e-16) return;
     bool cc = (cop == 'c' || cop == 'C');
     if (op.diag) {
       for (int I = 0; I < op.N; ++I) { cd z = eexp(op, I, field, sign); if (cc) z = std::conj(z);
@@ -550,7 +555,7 @@ struct Oracle {
   }
   // Operator_mod.F90:648-717 : Mat = op( exp(phi*g*P^T O P) ) * Mat
   void op_mmultR(cd* Mat, int N1, int N2, const Op& op, cd field, char cop) {
-    if (std::abs(op.g) < 2.220446049250313e-16) return;
+    if (std::abs(geff(op)) < 2.220446049250313e-16) return;
     bool cc = (cop == 'c' || cop == 'C');
     if (op.diag) {
       for (int I = 0; I < op.N; ++I) { cd z = eexp(op, I, field, 1); if (cc) z = std::conj(z);
@@ -598,7 +603,7 @@ struct Oracle {
   void op_phase(cd& Phase, int nf) {  // Operator_mod.F90:160-181
     for (int n = 0; n < n_opv; ++n) for (int nt = 1; nt <= ltrot; ++nt) {
       const Op& op = OpV(n, nf);
-      double angle = (op.g * op.alpha * ft.phi(op.type, fld(n, nt))).imag();
+      cur_nt = nt; double angle = (geff(op) * op.alpha * ft.phi(op.type, fld(n, nt))).imag();
       Phase *= cd(std::cos(angle), std::sin(angle));
     }
   }
@@ -606,7 +611,7 @@ struct Oracle {
   // ---- Prog/wrapur_mod.F90:102-123
   void wrapur(int NTAU, int NTAU1, std::vector<UDV>& udv) {
     for (int nf = 0; nf < n_fl; ++nf) {
-      for (int NT = NTAU + 1; NT <= NTAU1; ++NT) {
+      for (int NT = NTAU + 1; NT <= NTAU1; ++NT) { cur_nt = NT;
         mmthr(udv[nf].U.data(), ndim, udv[nf].npart, nf);
         for (int n = 0; n < n_opv; ++n) op_mmultR(udv[nf].U.data(), ndim, udv[nf].npart, OpV(n, nf), fld(n, NT), 'n');
       }
@@ -616,7 +621,7 @@ struct Oracle {
   // ---- Prog/wrapul_mod.F90:108-129
   void wrapul(int NTAU1, int NTAU, std::vector<UDV>& udv) {
     for (int nf = 0; nf < n_fl; ++nf) {
-      for (int NT = NTAU1; NT >= NTAU + 1; --NT) {
+      for (int NT = NTAU1; NT >= NTAU + 1; --NT) { cur_nt = NT;
         for (int n = n_opv - 1; n >= 0; --n) op_mmultR(udv[nf].U.data(), ndim, udv[nf].npart, OpV(n, nf), fld(n, NT), 'c');
         mmthlc(udv[nf].U.data(), ndim, udv[nf].npart, nf);
       }
@@ -649,7 +654,7 @@ struct Oracle {
     cd phi_new = ft.phi(type, Hs_new), phi_old = ft.phi(type, fld(n_op, nt));
     for (int nf = 0; nf < n_fl; ++nf) {
       const Op& op = OpV(n_op, nf); const cd* G = GR[nf].data();
-      cd Z1 = op.g * (phi_new - phi_old); int od = op.nnz; cd D_mat;
+      cur_nt = nt; cd Z1 = geff(op) * (phi_new - phi_old); int od = op.nnz; cd D_mat;
       for (int m = 0; m < od; ++m) {
         cd myexp = std::exp(Z1 * op.E[m]); cd Z = myexp - 1.0; Delta[m + (size_t)op_dim * nf] = Z;
         for (int n = 0; n < od; ++n) Mat[n + m * op_dim] = -Z * G[op.P[n] + (size_t)op.P[m] * ndim];
@@ -724,6 +729,7 @@ struct Oracle {
 
   // ---- Prog/Wrapgr_mod.F90:247-312 : move GR between operator positions m -> m1 inside time slice ntau (m, m1 in 0..n_opv)
   void wrapgr_placegr(int m, int m1, int ntau) {
+    cur_nt = ntau;
     if (m1 > m) {
       for (int n = m + 1; n <= m1; ++n) { cd HS = fld(n - 1, ntau);
         for (int nf = 0; nf < n_fl; ++nf) op_wrapup(GR[nf].data(), OpV(n - 1, nf), HS, 1);
@@ -737,7 +743,7 @@ struct Oracle {
   // ---- Prog/Wrapgr_mod.F90:317-433 : ONE global-in-slice proposal (what ham%Global_move_tau returned is passed in).
   // Flip_list is 1-based; returns the acceptance; m is updated as in the reference.
   bool wrapgr_random_update_one(int& m, int ntau, double T0_Proposal_ratio, double S0_ratio, std::vector<int> Flip_list, std::vector<cd> Flip_value) {
-    const double Zero = 10e-8; bool Acc = false; const int Flip_length = (int)Flip_list.size();
+    const double Zero = 10e-8; bool Acc = false; const int Flip_length = (int)Flip_list.size(); cur_nt = ntau;
     if (!(T0_Proposal_ratio > Zero)) return false;
     for (;;) { int swaps = 0;                               // wrapgr_sort (:437-480)
       for (int nc = 0; nc + 1 < Flip_length; ++nc) if (Flip_list[nc] > Flip_list[nc + 1]) { std::swap(Flip_list[nc], Flip_list[nc + 1]); std::swap(Flip_value[nc], Flip_value[nc + 1]); swaps++; }
@@ -860,7 +866,7 @@ struct Oracle {
 
   // ---- Prog/Wrapgr_mod.F90:81-157
   void wrapgrup(int NTAU) {
-    int NTAU1 = NTAU + 1;
+    int NTAU1 = NTAU + 1; cur_nt = NTAU1;
     for (int nf = 0; nf < n_fl; ++nf) { mmthr(GR[nf].data(), ndim, ndim, nf); mmthl_m1(GR[nf].data(), ndim, ndim, nf); }
     for (int n = nt_seq_start - 1; n < seq_end(); ++n) {
       cd HS_Field = fld(n, NTAU1);
@@ -878,6 +884,7 @@ struct Oracle {
   }
   // ---- Prog/Wrapgr_mod.F90:160-243
   void wrapgrdo(int NTAU) {
+    cur_nt = NTAU;
     if (n_global_tau > 0) { int m = n_opv; wrapgr_random_update(m, NTAU); wrapgr_placegr(m, seq_end(), NTAU); }        // :189-194
     for (int n = seq_end() - 1; n >= nt_seq_start - 1; --n) {
       cd HS_Field = fld(n, NTAU);
@@ -1160,10 +1167,12 @@ struct Oracle {
 
   // ---- Prog/tau_m_mod.F90:215-263
   void propr(std::vector<std::vector<cd>>& A, int nt) {
+    cur_nt = nt;
     for (int nf = 0; nf < n_fl; ++nf) { mmthr(A[nf].data(), ndim, ndim, nf);
       for (int n = 0; n < n_opv; ++n) op_mmultR(A[nf].data(), ndim, ndim, OpV(n, nf), fld(n, nt), 'n'); }
   }
   void proprm1(std::vector<std::vector<cd>>& A, int nt) {
+    cur_nt = nt;
     for (int nf = 0; nf < n_fl; ++nf) { mmthl_m1(A[nf].data(), ndim, ndim, nf);
       for (int n = 0; n < n_opv; ++n) op_mmultL(A[nf].data(), ndim, ndim, OpV(n, nf), fld(n, nt), 'n', -1); }
   }
@@ -1378,6 +1387,12 @@ static void fill_op(Op& op, int N, int nnz, int diag, int type, const int* P, co
   op.g = cd(g_re, g_im); op.alpha = cd(a_re, a_im);
 }
 
+// time-dependent coupling of vertex (n, nf): g_t(1..Ltrot) (Operator_mod.F90:66); call after orc_set_op_v
+int orc_set_op_v_gt(void* h, int n, int nf, const double* g_t) {
+  Oracle* o = (Oracle*)h; Op& op = o->OpV(n - 1, nf - 1);
+  op.g_t.resize(o->ltrot); for (int t = 0; t < o->ltrot; ++t) op.g_t[t] = cd(g_t[2 * t], g_t[2 * t + 1]);
+  return 0;
+}
 // Interaction vertex; builds E_exp / M_exp exactly as Op_set does (Operator_mod.F90:400-470)
 int orc_set_op_v(void* h, int n, int nf, int N, int nnz, int diag, int type, const int* P, const double* U, const double* E,
                  double g_re, double g_im, double a_re, double a_im) {
@@ -1520,7 +1535,7 @@ void orc_wrapgrdo(void* h, int ntau) { ((Oracle*)h)->wrapgrdo(ntau); }
 
 // B-slice product helper: A <- B(nt) A  (PROPR on one flavor)
 void orc_propr(void* h, int nf, double* A, int nt) {
-  Oracle* o = (Oracle*)h; cd* a = (cd*)A; --nf; o->mmthr(a, o->ndim, o->ndim, nf);
+  Oracle* o = (Oracle*)h; cd* a = (cd*)A; --nf; o->cur_nt = nt; o->mmthr(a, o->ndim, o->ndim, nf);
   for (int n = 0; n < o->n_opv; ++n) o->op_mmultR(a, o->ndim, o->ndim, o->OpV(n, nf), o->fld(n, nt), 'n');
 }
 

@@ -67,6 +67,9 @@ class Oracle:
             L.orc_set_op_v(self.h, o["n"], o["nf"], o["N"], o["nnz"], o["diag"], o["type"], o["P"].ctypes.data_as(_ip),
                            _d(o["U"]), _d(o["E"]), C.c_double(o["g"].real), C.c_double(o["g"].imag),
                            C.c_double(o["alpha"].real), C.c_double(o["alpha"].imag))
+            if o.get("g_t") is not None:
+                assert o["g_t"].size == model.Ltrot
+                L.orc_set_op_v_gt(self.h, o["n"], o["nf"], _d(o["g_t"]))
         for o in ot:
             L.orc_set_op_t(self.h, o["nc"], o["nf"], o["N"], o["diag"], o["P"].ctypes.data_as(_ip), _d(o["U"]), _d(o["E"]),
                            C.c_double(o["g"].real), C.c_double(o["g"].imag))
