@@ -95,3 +95,34 @@ def exchange_step(handles, rng, n_exchange_steps=1, rebuild=True):
         for h in handles:
             h.init_sweep()
     return np.array(acc_all), np.array(w_all), pairs_all
+
+
+def global_updates(handle, propose, rng, n_global=1, rebuild=True):
+    """Global_Updates (Prog/Global_mod.F90:450-639) for all chains of a handle: n_global whole-configuration proposals per chain.
+    propose(fields_old [chain, Ltrot, n_opv] complex, rng) -> (fields_new, log_T0_proposal_ratio [chain]) plays ham%Global_move_log_T0 (-inf = no proposal,
+    LOG_T0_REJECTED).  Per proposal: Compute_Fermion_Det of the new configuration on the device, Ratiotot = Compute_Ratio_Global, Weight =
+    |Re(Phase_old Ratiotot) / Re(Phase_old)| (:569), accepted if Weight > ranf; rejected chains take their fields back.  Returns (accepted [n_global, chain],
+    weight [n_global, chain]); the phase a chain would carry is Phase_old Ratiotot / |Ratiotot| (what Control_PrecisionP_Glob compares, :571-572).
+    With rebuild=True the handle recomputes storage, G and phase from its fields at the end (the reference rebuilds them in :601-637)."""
+    m = handle.m; C = handle.C
+    f_old = handle.get_fields(); phase_old = np.asarray(handle.phase(), dtype=np.complex128).copy()
+    ld_old, ph_old = handle.compute_fermion_det()
+    acc_all, w_all = [], []
+    for _ in range(n_global):
+        f_new, log_t0 = propose(f_old.copy(), rng)
+        log_t0 = np.asarray(log_t0, dtype=np.float64); live = np.isfinite(log_t0)
+        f_try = np.where(live[:, None, None], f_new, f_old)
+        handle.set_fields(f_try)
+        ld_new, ph_new = handle.compute_fermion_det()
+        r1, r2 = compute_ratio_global(m, ld_old, ph_old, ld_new, ph_new, f_old, f_try)
+        ratiotot = r1 * np.exp(r2 + np.where(live, log_t0, 0.0))
+        weight = np.abs((phase_old * ratiotot).real / phase_old.real)
+        toggle = live & (weight > rng.random(C))
+        f_old = np.where(toggle[:, None, None], f_try, f_old)
+        ld_old = np.where(toggle[:, None], ld_new, ld_old); ph_old = np.where(toggle[:, None], ph_new, ph_old)
+        phase_old = np.where(toggle, phase_old * ratiotot / np.abs(ratiotot), phase_old)
+        acc_all.append(toggle); w_all.append(np.where(live, weight, 0.0))
+    handle.set_fields(f_old)
+    if rebuild:
+        handle.init_sweep()
+    return np.array(acc_all), np.array(w_all)

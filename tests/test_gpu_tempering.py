@@ -69,3 +69,41 @@ def test_exchange_needs_an_even_ring():
         tempering.exchange_step(hs, np.random.default_rng(0))
     for h in hs:
         h.close()
+
+
+def test_global_updates_site_flip():
+    """Global_Updates (Prog/Global_mod.F90:450-639) with a proposal that flips the fields of one site on every time slice: weights against the oracle's
+    determinants, accepted / rejected bookkeeping, detailed balance of a move and its inverse, and the carried phase against the rebuilt one."""
+    m = hubbard_square(4, 4, 1.0, U=4.0, Mz=False); seeds = SEEDS[:4]
+    g = AlfB200(m, n_chains=len(seeds), nwrap=5); g.set_seeds(seeds); g.fields_set(); g.init_sweep(); g.sweep(1, 0)
+    f0 = g.get_fields(); ph0 = np.asarray(g.phase()).copy()
+    sites = [3, 7, 0, 12]
+
+    def propose(f, rng):
+        for c, s in enumerate(sites):
+            f[c, :, s] = -f[c, :, s]
+        lt0 = np.zeros(len(sites)); lt0[3] = -np.inf               # chain 3: LOG_T0_REJECTED, no proposal
+        return f, lt0
+    want = np.zeros(len(seeds))
+    for c in range(3):
+        o = Oracle(m, nwrap=5); o.ranset(SEEDS[0]); o.fields_set(); o.init()
+        o.set_fields(f0[c]); pa, da = o.compute_fermion_det()
+        fn = f0[c].copy(); fn[:, sites[c]] *= -1
+        o.set_fields(fn); pb, db = o.compute_fermion_det()
+        r1, r2 = tempering.compute_ratio_global(m, da.sum(axis=1)[None], pa[None], db.sum(axis=1)[None], pb[None], f0[c][None], fn[None])
+        rt = r1[0] * np.exp(r2[0]); want[c] = abs((ph0[c] * rt).real / ph0[c].real)
+    acc, w = tempering.global_updates(g, propose, np.random.default_rng(5), n_global=1)
+    assert np.allclose(w[0, :3], want[:3], rtol=1e-6) and w[0, 3] == 0.0 and not acc[0, 3]
+    f1 = g.get_fields()
+    for c in range(4):
+        fn = f0[c].copy()
+        if acc[0, c]:
+            fn[:, sites[c]] *= -1
+        assert np.array_equal(f1[c], fn)
+    # the reverse move has the inverse weight (compare on the chains that accepted; phases are +-1-ish complex numbers of modulus 1 here)
+    g2 = AlfB200(m, n_chains=len(seeds), nwrap=5); g2.set_seeds(seeds); g2.fields_set(); g2.set_fields(f1); g2.init_sweep()
+    acc2, w2 = tempering.global_updates(g2, propose, np.random.default_rng(6), n_global=1, rebuild=False)
+    for c in range(3):
+        if acc[0, c] and abs(ph0[c].imag) < 1e-9:
+            assert abs(w[0, c] * w2[0, c] - 1.0) < 1e-6
+    g.close(); g2.close()
