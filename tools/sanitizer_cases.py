@@ -24,3 +24,15 @@ for mz in (True, False):
     model = hubbard_square(4, 4, 0.4, Mz=mz, continuous=True)
     g = AlfB200(model, n_chains=2, nwrap=2); g.set_seeds([5, 6]); g.fields_set(); g.init_sweep()
     ld, ph = g.compute_fermion_det(); g.langevin_update(0.02, 1.5); acc, w = g.hmc_update(0.05, 2); print("det / langevin / hmc", ld[0], w); g.close()
+# round-2 additions: ring-group op kernel (persistent, double-buffered cp.async panels; rings of 16 = FULL path, rings of 4 = predicated path), register-panel QR,
+# block-diagonal observable kernel, scalar tables, time-dependent couplings, 8 x 8 (rings of 8)
+from alf_b200.model import obs_scal_tables
+for (l1, l2, beta, nw) in ((16, 16, 0.3, 2), (8, 8, 0.3, 2), (8, 4, 0.3, 2)):
+    model = hubbard_square(l1, l2, beta)
+    g = AlfB200(model, n_chains=2, nwrap=nw); g.set_seeds([5, 6]); g.fields_set(); g.set_obs_scal_tables(obs_scal_tables(model)); g.init_sweep()
+    g.obs_eq_enable(True); g.obs_tau_enable(True); g.sweep(1, 1); print(model.name, l1, l2, g.control()["XMAXG"], g.obs()[:6]); g.close()
+model = hubbard_square(4, 4, 0.4)
+for n, row in enumerate(model.Op_V):
+    for op in row:
+        op.g_t = np.array([op.g * (1.0 + 0.2 * np.cos(nt + n)) for nt in range(model.Ltrot)], dtype=np.complex128)
+g = AlfB200(model, n_chains=2, nwrap=2); g.set_seeds([5, 6]); g.fields_set(); g.init_sweep(); g.sweep(1, 1); print("g_t", g.control()["XMAXG"]); g.close()
