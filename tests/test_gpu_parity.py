@@ -1044,3 +1044,28 @@ def test_taum_time_dependent_coupling():
     """TAU_M with Op_V%g_t: PROPR / PROPRM1 (Prog/tau_m_mod.F90:215-263) use the coupling of the slice they propagate over."""
     _run_taum(_with_g_t(config1()), SEEDS[:2], nwrap=10)
     _run_taum(_with_g_t(config1(Mz=False)), SEEDS[:2], nwrap=10)
+
+
+@pytest.mark.parametrize("shape", [(4, 4), (8, 4), (6, 6), (12, 12), (16, 16), (16, 8)])
+def test_hop_ring_groups_bond_dependent_amplitudes(shape):
+    """Checkerboard hopping with a different amplitude on every bond operator (no translation invariance): the ring-group op kernel takes its per-bond
+    matrices path (rings of 4 / 8 / 6 / 12 / 16 sites; 16 x 8: two ring lengths in one list), compared with the oracle for the six Hop_mod entry points."""
+    model = hubbard_square(shape[0], shape[1], 0.3)
+    rng = np.random.default_rng(shape[0] * 100 + shape[1])
+    for row in model.Op_T:
+        for op in row:
+            op.g = op.g * (1.0 + 0.4 * rng.random())
+    _hop_check(model)
+    _hop_check(model, nf=2)
+
+
+def test_sweep_bond_dependent_hopping():
+    """A full sweep (wraps with the diagonal vertices fused into the ring passes, TAU_M) with bond-dependent hopping amplitudes: per-bond ring matrices."""
+    for shape, nw in (((4, 4), 5), ((8, 8), 10)):
+        model = hubbard_square(shape[0], shape[1], 1.0)
+        rng = np.random.default_rng(11)
+        for row in model.Op_T:
+            for op in row:
+                op.g = op.g * (1.0 + 0.4 * rng.random())
+        _run_parity(model, SEEDS[:2], nwrap=nw, n_sweeps=1)
+        _run_taum(model, SEEDS[:1], nwrap=nw)
