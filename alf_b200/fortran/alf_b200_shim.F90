@@ -20,6 +20,7 @@ module alf_b200_shim
   use Operator_mod               ! type Operator (Prog/Operator_mod.F90:56-90)
   use Fields_mod                 ! type Fields   (Prog/Fields_mod.F90:79-99)
   use UDV_State_mod              ! type UDV_State (Prog/udv_state_mod.F90:85-110)
+  use QMC_runtime_var           ! get_LOBS_ST, get_LOBS_EN (Prog/QMC_runtime_var_mod.F90)
   use Hamiltonian_main           ! Op_V, Op_T, nsigma, Ndim, N_FL, N_FL_eff, Calc_Fl_map, N_SUN, Ltrot, Symm, Projector, WF_L, WF_R (Hamiltonian_main_mod.F90:181-197)
   implicit none
   private
@@ -61,6 +62,8 @@ contains
           call check(alf_b200_set_op_v(alf_b200_handle_ptr, n, nf, Op_V(n,nf)%N, Op_V(n,nf)%N_non_zero, merge(1,0,Op_V(n,nf)%diag), Op_V(n,nf)%type, &
                & Op_V(n,nf)%P, Op_V(n,nf)%U, Op_V(n,nf)%E, dble(Op_V(n,nf)%g), aimag(Op_V(n,nf)%g), dble(Op_V(n,nf)%alpha), aimag(Op_V(n,nf)%alpha)), &
                & __FILE__, __LINE__)
+          ! time-dependent coupling (Operator_mod.F90:66): the device then builds its vertex tables per time slice
+          if (Op_V(n,nf)%get_g_t_alloc()) call check(alf_b200_set_op_v_gt(alf_b200_handle_ptr, n, nf, Op_V(n,nf)%g_t), __FILE__, __LINE__)
        enddo
        do n = 1, size(Op_T,1)
           call check(alf_b200_set_op_t(alf_b200_handle_ptr, n, nf, Op_T(n,nf)%N, merge(1,0,Op_T(n,nf)%diag), Op_T(n,nf)%P, Op_T(n,nf)%U, Op_T(n,nf)%E, &
@@ -74,6 +77,7 @@ contains
        enddo
     endif
     call check(alf_b200_finalize_model(alf_b200_handle_ptr), __FILE__, __LINE__)
+    call check(alf_b200_set_measure_interval(alf_b200_handle_ptr, get_LOBS_ST(), get_LOBS_EN()), __FILE__, __LINE__)      ! VAR_QMC, QMC_runtime_var_mod.F90:156-189
     call check(alf_b200_set_seeds(alf_b200_handle_ptr, int(seeds, c_int32_t)), __FILE__, __LINE__)
   end subroutine alf_b200_attach
 
