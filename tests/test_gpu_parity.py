@@ -1069,3 +1069,9 @@ def test_sweep_bond_dependent_hopping():
                 op.g = op.g * (1.0 + 0.4 * rng.random())
         _run_parity(model, SEEDS[:2], nwrap=nw, n_sweeps=1)
         _run_taum(model, SEEDS[:1], nwrap=nw)
+
+
+def test_projector_time_dependent_coupling():
+    """Projective algorithm + Tau_p with Op_V%g_t (wraps, CGRP and the time-displaced propagation all use the coupling of their slice)."""
+    _run_projector(_with_g_t(hubbard_square(4, 4, 1.0, 0.1, 4.0, projector=True, theta=0.6, trial="dimer")), SEEDS[:2], nwrap=4, ltau=1)
+    _run_projector(_with_g_t(hubbard_square(4, 4, 0.8, 0.1, 4.0, Mz=False, projector=True, theta=0.3)), SEEDS[:2], nwrap=6, ltau=1)
