@@ -136,16 +136,34 @@ __global__ void __launch_bounds__(256) k_obs_tau_diag(const T* __restrict__ GT0,
   for (int q = 0; q < 4; ++q)
 #pragma unroll
     for (int ch = 0; ch < OBST_NCH; ++ch) v[q][ch] = cplx(0.0, 0.0);
+  // both operands of tile k + 1 are requested (into registers) before tile k is worked on, so a step costs one memory latency at most
+  const int nfl = F < 2 ? F : 2;
+  T pg0t[2][4], pgt0[2][4];           // [f][q]: G0T(j0 + tx, i0 + ty + 8 q) and GT0(i0 + tx, j0 + ty + 8 q) of the NEXT tile
+  auto fetch = [&](int k) {
+    const int J = k, I = (k + delta) % ntl, i0 = 32 * I, j0 = 32 * J;
+#pragma unroll
+    for (int f = 0; f < 2; ++f)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        pg0t[f][q] = zero_<T>(); pgt0[f][q] = zero_<T>();
+        if (f < nfl) { pg0t[f][q] = G0T[base + f * sM + (j0 + tx) + (long)(i0 + ty + 8 * q) * N]; pgt0[f][q] = GT0[base + f * sM + (i0 + tx) + (long)(j0 + ty + 8 * q) * N]; }
+      }
+  };
+  fetch(0);
   for (int k = 0; k < ntl; ++k) {
     const int J = k, I = (k + delta) % ntl, i0 = 32 * I, j0 = 32 * J;
-    for (int f = 0; f < F && f < 2; ++f)
-      for (int r = ty; r < 32; r += 8) tB[f][r][tx] = G0T[base + f * sM + (j0 + tx) + (long)(i0 + r) * N];      // G0T(jj, ii): jj fastest
+    T cgt0[2][4];
+#pragma unroll
+    for (int f = 0; f < 2; ++f)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) { if (f < nfl) tB[f][ty + 8 * q][tx] = pg0t[f][q]; cgt0[f][q] = pgt0[f][q]; }      // G0T(jj, ii): jj fastest
     __syncthreads();
+    if (k + 1 < ntl) fetch(k + 1);
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       const int r = ty + 8 * q, i = i0 + tx, j = j0 + r;
       cplx gt0[2], g0t[2];
-      for (int f = 0; f < F && f < 2; ++f) { const T a = GT0[base + f * sM + i + (long)j * N], b2 = tB[f][tx][r]; gt0[f] = cplx(real_(a), imag_(a)); g0t[f] = cplx(real_(b2), imag_(b2)); }
+      for (int f = 0; f < F && f < 2; ++f) { const T a = cgt0[f][q], b2 = tB[f][tx][r]; gt0[f] = cplx(real_(a), imag_(a)); g0t[f] = cplx(real_(b2), imag_(b2)); }
       cplx zi = cplx(0.0, 0.0), zj = cplx(0.0, 0.0), zz = cplx(0.0, 0.0), gsum = cplx(0.0, 0.0);
       for (int f = 0; f < F && f < 2; ++f) {
         const T a = dTT[f * N + i], b2 = d00[f * N + j];
