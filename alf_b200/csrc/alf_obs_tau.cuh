@@ -116,7 +116,7 @@ __global__ void __launch_bounds__(256) k_obs_tau(const T* __restrict__ GT0, cons
 // four channels accumulate in REGISTERS over the whole diagonal and go to the shared-memory bins once.
 // ------------------------------------------------------------------------------------------------------------------------
 template <typename T, int EQ>
-__global__ void __launch_bounds__(256) k_obs_tau_diag(const T* __restrict__ GT0, const T* __restrict__ G0T, const T* __restrict__ G00, const T* __restrict__ GTT,
+__global__ void __launch_bounds__(256, 2) k_obs_tau_diag(const T* __restrict__ GT0, const T* __restrict__ G0T, const T* __restrict__ G00, const T* __restrict__ GTT,
                                                       long sM, int N, int F, int n_sun, const cplx* __restrict__ phase, LattDev lt, int nt, int ntau,
                                                       double* __restrict__ acc, double* __restrict__ bg, double* __restrict__ cnt) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
