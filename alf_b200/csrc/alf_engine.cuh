@@ -345,12 +345,14 @@ static __global__ void k_hmc_momenta(double* __restrict__ p, uint64_t* __restric
 // p -= x dt (Forces_0 + Re(Phase F)/Re(Phase)), Forces_0 = phi (Gaussian action)      (:436-440, :476-484)
 static __global__ void k_hmc_kick(double* __restrict__ p, const double* __restrict__ fc, const cplx* __restrict__ forces, const cplx* __restrict__ phase, double xdt, long per_chain, int n_chains) {
   const int chain = blockIdx.y; const cplx ph = phase[chain];
+#pragma unroll 4
   for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < per_chain; e += (long)gridDim.x * blockDim.x) {
     const long q = (long)chain * per_chain + e; const cplx pf = ph * forces[q];
     p[q] -= xdt * (fc[q] + pf.x / ph.x);
   }
 }
 static __global__ void k_hmc_drift(double* __restrict__ fc, const double* __restrict__ p, double dt, long n) {      // nsigma%f += dt p (:447-449)
+#pragma unroll 4
   for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long)gridDim.x * blockDim.x) fc[e] += dt * p[e];
 }
 // Compute_Ratio_Global (Prog/Global_mod.F90:651-760) with the Gaussian Get_Delta_S0_global, Weight, Metropolis test, restore on rejection (:516-563).
@@ -397,6 +399,7 @@ static __global__ void k_hmc_decide(double* __restrict__ fc, const double* __res
 template <typename T>
 __global__ void k_fdet_build(T* __restrict__ TP, const T* __restrict__ U, const T* __restrict__ V, const double* __restrict__ D, long sM, int n, double* __restrict__ extra) {
   const int b = blockIdx.y; TP += (long)b * sM; U += (long)b * sM; V += (long)b * sM; D += (long)b * n;
+#pragma unroll 4
   for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < (long)n * n; e += (long)gridDim.x * blockDim.x) {
     const int j = (int)(e / n); const double d = D[j];
     TP[e] = (d <= 1.0) ? U[e] + V[e] * d : U[e] * (1.0 / d) + V[e];
@@ -428,6 +431,7 @@ static __global__ void k_fdet_addlog(const double* __restrict__ D, int ldD, int 
 template <typename T>
 __global__ void k_g0t_init(T* __restrict__ G0T, const T* __restrict__ G, long sM, int n) {
   const int b = blockIdx.y; G0T += (long)b * sM; G += (long)b * sM;
+#pragma unroll 4
   for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < (long)n * n; e += (long)gridDim.x * blockDim.x) {
     int j = (int)((unsigned)e / (unsigned)n), i = (int)((unsigned)e - (unsigned)j * (unsigned)n);
     G0T[e] = G[e] - ((i == j) ? one_<T>() : zero_<T>());
@@ -438,12 +442,14 @@ __global__ void k_g0t_init(T* __restrict__ G0T, const T* __restrict__ G, long sM
 template <typename T>
 __global__ void k_set_wf(T* __restrict__ U, long sM, const T* __restrict__ wf, int F, int N, int NP) {
   const int b = blockIdx.y, f = b % F; U += (long)b * sM; wf += (long)f * N * NP;
+#pragma unroll 4
   for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < (long)N * NP; e += (long)gridDim.x * blockDim.x) U[e] = wf[e];
 }
 // dst = alpha * src + beta * 1
 template <typename T>
 __global__ void k_axpb_identity(T* __restrict__ dst, const T* __restrict__ src, long sM, int n, double alpha, double beta) {
   const int b = blockIdx.y; dst += (long)b * sM; src += (long)b * sM;
+#pragma unroll 4
   for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < (long)n * n; e += (long)gridDim.x * blockDim.x) {
     const int j = (int)((unsigned)e / (unsigned)n), i = (int)((unsigned)e - (unsigned)j * (unsigned)n);
     dst[e] = alpha * src[e] + ((i == j) ? make_<T>(beta, 0.0) : zero_<T>());

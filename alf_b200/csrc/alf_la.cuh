@@ -807,6 +807,7 @@ __global__ void k_permcopy(T* __restrict__ dst, int ldd, long sDst, const T* __r
   const int b = blockIdx.y;
   dst += (long)b * sDst; src += (long)b * sSrc;
   if (perm) perm += (long)b * sP;
+#pragma unroll 4
   for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < (long)m * n; e += (long)gridDim.x * blockDim.x) {
     int j = (int)((unsigned)e / (unsigned)m), i = (int)((unsigned)e - (unsigned)j * (unsigned)m);
     T v = src[i + (long)j * lds];
@@ -835,6 +836,7 @@ __global__ void __launch_bounds__(256) k_transpose_conj(T* __restrict__ dst, int
 template <typename T>
 __global__ void k_colscale(T* __restrict__ A, int ld, long sA, int m, int n, const double* __restrict__ d, long sD) {
   const int b = blockIdx.y; A += (long)b * sA; d += (long)b * sD;
+#pragma unroll 4
   for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < (long)m * n; e += (long)gridDim.x * blockDim.x) {
     int j = (int)((unsigned)e / (unsigned)m), i = (int)((unsigned)e - (unsigned)j * (unsigned)m);
     A[i + (long)j * ld] = A[i + (long)j * ld] * d[j];
@@ -852,21 +854,25 @@ template <typename T>
 __global__ void k_copy_col0scale(T* __restrict__ dst, const T* __restrict__ src, long sM, int n, const cplx* __restrict__ s, long count) {
   const int b = blockIdx.y; dst += (long)b * sM; src += (long)b * sM;
   const T st = make_<T>(s[b].x, s[b].y);
+#pragma unroll 4
   for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < count; e += (long)gridDim.x * blockDim.x) dst[e] = (e < n) ? src[e] * st : src[e];
 }
 // identity / zero fill
 template <typename T>
 __global__ void k_set_identity(T* __restrict__ A, int ld, long sA, int m, int n) {
   const int b = blockIdx.y; A += (long)b * sA;
+#pragma unroll 4
   for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < (long)m * n; e += (long)gridDim.x * blockDim.x) {
     int j = (int)((unsigned)e / (unsigned)m), i = (int)((unsigned)e - (unsigned)j * (unsigned)m);
     A[i + (long)j * ld] = (i == j) ? one_<T>() : zero_<T>();
   }
 }
 static __global__ void k_fill_double(double* p, long n, double v) {
+#pragma unroll 4
   for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long)gridDim.x * blockDim.x) p[e] = v;
 }
 static __global__ void k_fill_cplx(cplx* p, long n, cplx v) {
+#pragma unroll 4
   for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long)gridDim.x * blockDim.x) p[e] = v;
 }
 
@@ -877,6 +883,7 @@ template <typename T, int SEP, int CT>
 __global__ void k_cgr_tpup(T* __restrict__ OUT, const T* __restrict__ TP, const T* __restrict__ RHS, long sM, int n,
                            const double* __restrict__ DR, const double* __restrict__ DL, long sD) {
   const int b = blockIdx.y; OUT += (long)b * sM; TP += (long)b * sM; RHS += (long)b * sM; DR += (long)b * sD; DL += (long)b * sD;
+#pragma unroll 4
   for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < (long)n * n; e += (long)gridDim.x * blockDim.x) {
     int j = (int)((unsigned)e / (unsigned)n), i = (int)((unsigned)e - (unsigned)j * (unsigned)n);
     double dr = DR[i], dl = DL[j];
@@ -893,6 +900,7 @@ __global__ void k_cgr_tpup(T* __restrict__ OUT, const T* __restrict__ TP, const 
 template <typename T, int ROWS>
 __global__ void k_sep_scale(T* __restrict__ A, long sA, int n, const double* __restrict__ d, long sD) {
   const int b = blockIdx.y; A += (long)b * sA; d += (long)b * sD;
+#pragma unroll 4
   for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < (long)n * n; e += (long)gridDim.x * blockDim.x) {
     int j = (int)((unsigned)e / (unsigned)n), i = (int)((unsigned)e - (unsigned)j * (unsigned)n);
     double x = d[ROWS ? i : j];
@@ -904,6 +912,7 @@ __global__ void k_sep_scale(T* __restrict__ A, long sA, int n, const double* __r
 template <typename T>
 __global__ void k_rowscale_inv(T* __restrict__ A, int ld, long sA, int m, int n, const double* __restrict__ d, long sD) {
   const int b = blockIdx.y; A += (long)b * sA; d += (long)b * sD;
+#pragma unroll 4
   for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < (long)m * n; e += (long)gridDim.x * blockDim.x) {
     int j = (int)((unsigned)e / (unsigned)m), i = (int)((unsigned)e - (unsigned)j * (unsigned)m);
     A[i + (long)j * ld] = A[i + (long)j * ld] * (1.0 / d[i]);
@@ -921,6 +930,7 @@ __global__ void k_cgr22_build(T* __restrict__ HLPB1, T* __restrict__ HLP, long s
   HLPB1 += (long)b * s22; HLP += (long)b * s22; V1INV += (long)b * sM; U1 += (long)b * sM; U2 += (long)b * sM; V2 += (long)b * sM; D1 += (long)b * sD; D2 += (long)b * sD;
   const bool fst = D1[0] > D2[0];
   if (blockIdx.x == 0 && threadIdx.x == 0) first[b] = fst ? 1 : 0;
+#pragma unroll 4
   for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < (long)N2 * N2; e += (long)gridDim.x * blockDim.x) {
     const int J2 = (int)((unsigned)e / (unsigned)N2), I2 = (int)((unsigned)e - (unsigned)J2 * (unsigned)N2);
     const int bi = I2 >= N, bj = J2 >= N, I = I2 - bi * N, J = J2 - bj * N;
@@ -945,6 +955,7 @@ __global__ void k_cgr22_blocks(const T* __restrict__ INP, long s22, T* __restric
   const int b = blockIdx.y; const int N2 = 2 * N;
   INP += (long)b * s22; GT0 += (long)b * sM; G00 += (long)b * sM; GTT += (long)b * sM; G0T += (long)b * sM;
   const bool fst = first[b] != 0;
+#pragma unroll 4
   for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < (long)N * N; e += (long)gridDim.x * blockDim.x) {
     const int J = (int)((unsigned)e / (unsigned)N), I = (int)((unsigned)e - (unsigned)J * (unsigned)N);
     const T a = INP[I + (long)J * N2], d = INP[(I + N) + (long)(J + N) * N2], c = INP[(I + N) + (long)J * N2], bb = INP[I + (long)(J + N) * N2];

@@ -64,7 +64,8 @@ struct KScope {
 template <typename T> static inline double flop_scale() { return std::is_same<T, double>::value ? 1.0 : 4.0; }
 static inline void count_flops(int cat, double f) { if (t_prof) t_prof->add_flops(cat, f); }
 
-static inline int ew_blocks(long n) { long b = (n + 255) / 256; return (int)(b > 2048 ? 2048 : (b < 1 ? 1 : b)); }
+// grid.x of the element-wise kernels: four elements per thread (their grid-stride loops are unrolled by 4, so every thread has four loads in flight)
+static inline int ew_blocks(long n) { long b = (n + 1023) / 1024; return (int)(b > 2048 ? 2048 : (b < 1 ? 1 : b)); }
 
 template <typename T>
 struct UdvDev {            // batch of UDV_State objects (Prog/udv_state_mod.F90:85-110), one per (chain, flavor)
@@ -356,6 +357,7 @@ static __global__ void k_cgrp_z(const QrOut* __restrict__ q, cplx* __restrict__ 
 template <typename T>
 __global__ void k_one_minus(T* __restrict__ G, long sM, int n) {
   const int b = blockIdx.y; G += (long)b * sM;
+#pragma unroll 4
   for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < (long)n * n; e += (long)gridDim.x * blockDim.x) {
     const int j = (int)((unsigned)e / (unsigned)n), i = (int)((unsigned)e - (unsigned)j * (unsigned)n);
     G[e] = ((i == j) ? one_<T>() : zero_<T>()) - G[e];
