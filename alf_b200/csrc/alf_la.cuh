@@ -948,6 +948,46 @@ __global__ void k_cgr22_build(T* __restrict__ HLPB1, T* __restrict__ HLP, long s
     HLP[I2 + (long)J2 * N2] = hl;
   }
 }
+// The same for N a multiple of 32: one CTA per 32 x 32 tile (inside one quadrant), every global access coalesced -- the transposed operands
+// (U1^H, U2^H) and the transposed output HLPB1 go through a shared-memory tile.  grid = ((2N/32)^2, batch), 256 threads.
+template <typename T, int STAB3>
+__global__ void __launch_bounds__(256) k_cgr22_build_tiled(T* __restrict__ HLPB1, T* __restrict__ HLP, long s22, const T* __restrict__ V1INV, const T* __restrict__ U1,
+                                                           const double* __restrict__ D1, const T* __restrict__ U2, const T* __restrict__ V2, const double* __restrict__ D2,
+                                                           long sM, long sD, int N, int* __restrict__ first) {
+  __shared__ T tile[32][33];       // tile[j][i] = v(I2 = i0 + i, J2 = j0 + j)
+  const int b = blockIdx.y, N2 = 2 * N, nt2 = N2 >> 5, ti = blockIdx.x % nt2, tj = blockIdx.x / nt2, i0 = ti * 32, j0 = tj * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  HLPB1 += (long)b * s22; HLP += (long)b * s22; V1INV += (long)b * sM; U1 += (long)b * sM; U2 += (long)b * sM; V2 += (long)b * sM; D1 += (long)b * sD; D2 += (long)b * sD;
+  const bool fst = D1[0] > D2[0];
+  if (blockIdx.x == 0 && threadIdx.x == 0) first[b] = fst ? 1 : 0;
+  const int bi = i0 >= N, bj = j0 >= N, I0 = i0 - bi * N, J0 = j0 - bj * N;
+  const int kind = fst ? (bi * 2 + bj) : ((1 - bi) * 2 + (1 - bj));
+  const bool keep = (kind == 0 || kind == 3);                  // the blocks that also go into HLP
+  if (kind == 0 || kind == 2) {                                // direct operands: lanes along I
+    for (int r = ty; r < 32; r += 8) {
+      const int I = I0 + tx, J = J0 + r;
+      const double d1 = D1[I], d2 = D2[I];
+      T v;
+      if (kind == 0) v = V1INV[I + (long)J * N] * ((STAB3 && d1 > 1.0) ? 1.0 / d1 : 1.0);
+      else v = -(((STAB3 && d2 > 1.0) ? 1.0 : d2) * V2[I + (long)J * N]);
+      tile[r][tx] = v;
+    }
+  } else {                                                     // transposed operands U^H(I, J) = conj(U(J, I)): lanes along J
+    for (int r = ty; r < 32; r += 8) {
+      const int I = I0 + r, J = J0 + tx;
+      const double d1 = D1[I], d2 = D2[I];
+      T v;
+      if (kind == 1) v = ((STAB3 && d1 > 1.0) ? 1.0 : d1) * conj_(U1[J + (long)I * N]);
+      else v = conj_(U2[J + (long)I * N]) * ((STAB3 && d2 > 1.0) ? 1.0 / d2 : 1.0);
+      tile[tx][r] = v;
+    }
+  }
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {
+    HLP[(i0 + tx) + (long)(j0 + r) * N2] = keep ? tile[r][tx] : zero_<T>();          // lanes along I2
+    HLPB1[(j0 + tx) + (long)(i0 + r) * N2] = conj_(tile[tx][r]);                      // lanes along J2
+  }
+}
 // get_blocks (cgr2_2_mod.F90:55-72) with the ordering flag: first: (A,B,C,D) = (G00,G0T,GT0,GTT), else (GTT,GT0,G0T,G00)
 template <typename T>
 __global__ void k_cgr22_blocks(const T* __restrict__ INP, long s22, T* __restrict__ GT0, T* __restrict__ G00, T* __restrict__ GTT, T* __restrict__ G0T,

@@ -453,6 +453,11 @@ static void la_cgr2_2(LaWork<T>& w, LaWork<T>& w2, int stab, const UdvDev<T>& ud
   KL(KC_EW, st, k_permcopy<T, 0><<<eg, 256, 0, st>>>(w.W[2], N, n2, udv1.V, N, n2, N, N, nullptr, 0));
   la_inverse<T>(w, w.W[2], w.W[3]);
   // HLPB1 = HLPB2^H in w2.W[0]; right-hand side HLP in w2.W[1]
+  if (N % 32 == 0) {      // every access coalesced through 32 x 32 tiles
+    const dim3 gt((2 * N / 32) * (2 * N / 32), NM);
+    if (stab == 3) KL(KC_EW, st, k_cgr22_build_tiled<T, 1><<<gt, 256, 0, st>>>(w2.W[0], w2.W[1], n22, w.W[3], udv1.U, udv1.D, udv2.U, udv2.V, udv2.D, n2, N, N, first));
+    else KL(KC_EW, st, k_cgr22_build_tiled<T, 0><<<gt, 256, 0, st>>>(w2.W[0], w2.W[1], n22, w.W[3], udv1.U, udv1.D, udv2.U, udv2.V, udv2.D, n2, N, N, first));
+  } else
   if (stab == 3) KL(KC_EW, st, k_cgr22_build<T, 1><<<eg2, 256, 0, st>>>(w2.W[0], w2.W[1], n22, w.W[3], udv1.U, udv1.D, udv2.U, udv2.V, udv2.D, n2, N, N, first));
   else KL(KC_EW, st, k_cgr22_build<T, 0><<<eg2, 256, 0, st>>>(w2.W[0], w2.W[1], n22, w.W[3], udv1.U, udv1.D, udv2.U, udv2.V, udv2.D, n2, N, N, first));
   la_qrp<T>(w2, w2.W[0], N2, N2, w2.Dq);
